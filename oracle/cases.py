@@ -1,0 +1,53 @@
+"""Oracle (test infrastructure): the named, fully deterministic test cases shared by the
+golden generator and the parity tests.  Inputs come from numpy PCG64 seeds only."""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import grid_ref
+from .unet_ref import UNetSpec
+
+CASES = {
+    # smallest case with the full structure: GroupNorm(8), 2 levels, attention centre.
+    "micro": dict(
+        spec=UNetSpec(dim=8, u_net_levels=2, timesteps=10, groups=8),
+        cells=(16, 8, 8), hole=((3, 7), (2, 6), (0, 5)), batch=2, seed=101, save_taps=True,
+    ),
+    # BASELINE.json configs[0]: tiny TurbDiff (2 levels, 16 ch) on a 32x16x16 grid, B=2.
+    "tiny": dict(
+        spec=UNetSpec(dim=16, u_net_levels=2, timesteps=10, groups=8),
+        cells=(32, 16, 16), hole=((4, 8), (5, 11), (0, 10)), batch=2, seed=202, save_taps=False,
+    ),
+    # dim=32 (the channel plan of the shapes config: 64/128/256 ...) on a small grid with
+    # 3 levels: exercises every channel width the tcgen05 path is specialised for.
+    "dim32": dict(
+        spec=UNetSpec(dim=32, u_net_levels=3, timesteps=500, groups=8),
+        cells=(30, 14, 12), hole=((5, 9), (3, 8), (0, 7)), batch=2, seed=303, save_taps=False,
+    ),
+    # other normalisation variants of ddpm.py:424-431
+    "micro-layer": dict(
+        spec=UNetSpec(dim=8, u_net_levels=2, timesteps=10, groups=1),
+        cells=(16, 8, 8), hole=None, batch=1, seed=404, save_taps=False,
+    ),
+    "micro-instance": dict(
+        spec=UNetSpec(dim=8, u_net_levels=2, timesteps=10, groups=None),
+        cells=(16, 8, 8), hole=None, batch=1, seed=505, save_taps=False,
+    ),
+}
+
+
+def case_inputs(case):
+    """(x, t, c_local, geometry) for a case.  x ~ N(0,1) fp32 (B,F,X,Y,Z) on the padded
+    grid, t spread over [0,T), c_local = a seeded 6x4 cell-type table looked up on the
+    geometry's cell-type map."""
+    spec: UNetSpec = case["spec"]
+    geo = grid_ref.channel_geometry(cells=case["cells"], hole=case["hole"], seed=case["seed"])
+    rng = np.random.Generator(np.random.PCG64(case["seed"] + 1))
+    B = case["batch"]
+    x = rng.standard_normal((B, spec.in_features, *geo.padded)).astype(np.float32)
+    t = np.array([(3 + 5 * b) % spec.timesteps for b in range(B)], dtype=np.int64)
+    table = rng.standard_normal((6, spec.c_local_features)).astype(np.float32)
+    c_local = np.ascontiguousarray(grid_ref.cell_type_embedding(geo, table))
+    return torch.from_numpy(x), torch.from_numpy(t), torch.from_numpy(c_local), geo

@@ -1,0 +1,250 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference
+(`/root/reference`, importable only in the build container) on deterministic inputs.
+
+    python tests/golden/make_golden.py
+
+The reference imports a few packages that are absent here (pytorch_lightning, h5py,
+omegaconf, more_itertools, lightning_utilities); they are stubbed in ``sys.modules``
+before ``import turbdiff``.  None of the stubbed code is on the
+denoising path.  Inputs and weights come from numpy PCG64 seeds
+(``oracle.unet_ref.synth_state_dict``), so the fixtures only hold the reference's OUTPUTS;
+``tests/test_oracle_golden.py`` rebuilds the inputs and checks the oracle against them.
+"""
+
+import importlib.machinery
+import json
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parents[1]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, "/root/reference")
+
+
+def _stub(name, pkg=False, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    m.__spec__ = importlib.machinery.ModuleSpec(name, None, is_package=pkg)
+    if pkg:
+        m.__path__ = []
+    sys.modules[name] = m
+    return m
+
+
+class _LM(torch.nn.Module):
+    pass
+
+
+_stub("h5py", File=object, Group=object)
+_pl = _stub("pytorch_lightning", pkg=True, LightningModule=_LM, LightningDataModule=object, Callback=object, Trainer=object)
+_stub("pytorch_lightning.callbacks", ModelCheckpoint=object)
+_stub("pytorch_lightning.utilities", rank_zero_only=lambda f: f)
+_pl.loggers = _stub("pytorch_lightning.loggers", Logger=object)
+_stub("lightning_utilities", pkg=True)
+_stub("lightning_utilities.core", pkg=True)
+_stub("lightning_utilities.core.apply_func", apply_to_collection=lambda *a, **k: None)
+_stub("more_itertools", chunked=lambda it, n: [it[i : i + n] for i in range(0, len(it), n)])
+_stub("omegaconf", DictConfig=dict, OmegaConf=object)
+
+import warnings  # noqa: E402
+
+warnings.filterwarnings("ignore")
+
+import turbdiff.models.ddpm as ref  # noqa: E402
+from turbdiff.data import ofles  # noqa: E402
+from turbdiff.models import utils as ref_utils  # noqa: E402
+from turbdiff.models.cell_type_embeddings import CellTypeLearnedEmbedding  # noqa: E402
+from turbdiff.models.conditioning import Conditioning  # noqa: E402
+
+from oracle import grid_ref  # noqa: E402
+from oracle.cases import CASES, case_inputs  # noqa: E402
+from oracle.unet_ref import UNetSpec, state_dict_layout, synth_state_dict  # noqa: E402
+
+NORM_NAME = {8: "group", 1: "layer", None: "instance"}
+
+
+def build_ref_model(spec: UNetSpec, sd):
+    m = ref.DenoisingModel(
+        in_features=spec.in_features, out_features=spec.out_features, c_local_features=spec.c_local_features,
+        c_global_features=0, timesteps=spec.timesteps, dim=spec.dim, u_net_levels=spec.u_net_levels,
+        norm_type=NORM_NAME[spec.groups],
+    )
+    m.load_state_dict(sd, strict=True)
+    return m.eval()
+
+
+def gen_schedules():
+    out = {}
+    for name in ("linear", "log-linear", "log-snr-linear", "cosine", "sigmoid"):
+        for T in (10, 500, 1000):
+            gd = ref.GaussianDiffusion(torch.nn.Identity(), timesteps=T, beta_schedule=name)
+            for b, v in gd.named_buffers():
+                out[f"{name}/{T}/{b}"] = v.numpy()
+    np.savez_compressed(HERE / "schedules.npz", **out)
+
+
+def gen_time_embedding():
+    out = {}
+    for dim, T in ((32, 500), (32, 1000), (16, 10), (8, 10)):
+        emb = ref.NyquistFrequencyEmbedding(dim, T)
+        out[f"{dim}/{T}"] = emb(torch.arange(T)).numpy()
+        out[f"{dim}/{T}/scale"] = emb.scale.numpy()
+    np.savez_compressed(HERE / "time_embedding.npz", **out)
+
+
+def gen_layout():
+    spec = UNetSpec()  # shapes config
+    with torch.device("meta"):
+        m = ref.DenoisingModel(in_features=4, out_features=4, c_local_features=4, c_global_features=0,
+                               timesteps=500, dim=32, u_net_levels=4, norm_type="group")
+    ref_layout = [(k, list(v.shape)) for k, v in m.state_dict().items()]
+    mine = [(k, list(s)) for k, s in state_dict_layout(spec)]
+    assert ref_layout == mine, "state-dict layout of the oracle differs from the reference"
+    (HERE / "state_dict_layout_shapes.json").write_text(json.dumps(ref_layout))
+    print("layout entries", len(ref_layout), "params", sum(int(np.prod(s)) for _, s in ref_layout))
+
+
+def gen_unet():
+    out = {}
+    for cname, case in CASES.items():
+        spec = case["spec"]
+        sd = synth_state_dict(spec, case["seed"])
+        m = build_ref_model(spec, sd)
+        x, t, c_local, _ = case_inputs(case)
+        taps = {}
+        hooks = []
+
+        def grab(name):
+            def hook(_mod, _inp, outp):
+                taps[name] = outp.detach()
+            return hook
+
+        un = m.u_net
+        for i, blk in enumerate(un.downsampling_blocks):
+            hooks.append(blk.register_forward_hook(grab(f"down{i}")))
+        for i, blk in enumerate(un.upsampling_blocks):
+            hooks.append(blk.register_forward_hook(grab(f"up{i}")))
+        for i in range(3):
+            hooks.append(un.center_block[i].register_forward_hook(grab(f"center{i}")))
+        hooks.append(m.decode[0].register_forward_hook(grab("decode0")))
+        hooks.append(m.process_c.register_forward_hook(grab("c")))
+        with torch.no_grad():
+            y = m(x, t, {Conditioning.Type.CELL_TYPE: c_local})
+        for h in hooks:
+            h.remove()
+        out[f"{cname}/out"] = y.numpy()
+        if case.get("save_taps"):
+            for k, v in taps.items():
+                out[f"{cname}/tap/{k}"] = v.numpy()
+        else:  # only cheap checksums of the intermediates
+            for k, v in taps.items():
+                out[f"{cname}/tapsum/{k}"] = np.array([v.double().sum().item(), v.double().pow(2).sum().item()])
+        print(cname, "out", tuple(y.shape), float(y.abs().mean()))
+    np.savez_compressed(HERE / "unet.npz", **out)
+
+
+class _MD:
+    def __init__(self, idx):
+        self.cell_idx = idx
+
+
+def gen_diffusion():
+    out = {}
+    for cname in ("micro", "tiny"):
+        case = CASES[cname]
+        spec = case["spec"]
+        sd = synth_state_dict(spec, case["seed"])
+        x, t, c_local, geo = case_inputs(case)
+        cell_idx = torch.from_numpy(geo.cell_idx)
+        C = {Conditioning.Type.CELL_TYPE: c_local}
+        for noise_bcs in (True, False):
+            tag = f"{cname}/noise_bcs={int(noise_bcs)}"
+            m = build_ref_model(spec, sd)
+            gd = ref.GaussianDiffusion(m, timesteps=spec.timesteps, beta_schedule="log-snr-linear",
+                                       loss_type="l2", noise_bcs=noise_bcs)
+            # sampling, full chain and start_from
+            torch.manual_seed(1234)
+            out[f"{tag}/sample"] = gd.p_sample_loop(x, C, cell_idx).numpy()
+            torch.manual_seed(1234)
+            out[f"{tag}/sample_from4"] = gd.p_sample_loop(x, C, cell_idx, start_from=4).numpy()
+            # one p_sample at t=3 and t=0
+            for tt in (3, 0):
+                mean, lv = gd.p_sample(x, tt, C, cell_idx)
+                out[f"{tag}/p_sample_mean/{tt}"] = mean.numpy()
+                out[f"{tag}/p_sample_logvar/{tt}"] = lv.numpy()
+            # training loss + grads
+            m.train()
+            torch.manual_seed(4321)
+            loss, tdraw = gd(x, C, _MD(cell_idx), None)
+            loss.backward()
+            out[f"{tag}/loss"] = np.array(loss.item())
+            out[f"{tag}/t"] = tdraw.numpy()
+            for k, p in m.named_parameters():
+                g = p.grad
+                if g.numel() <= 4096 and cname == "micro":
+                    out[f"{tag}/grad/{k}"] = g.numpy()
+                out[f"{tag}/gradsum/{k}"] = np.array([g.double().sum().item(), g.double().pow(2).sum().item()])
+            if cname == "micro":
+                # l1 loss value too
+                gd1 = ref.GaussianDiffusion(m, timesteps=spec.timesteps, beta_schedule="log-snr-linear",
+                                            loss_type="l1", noise_bcs=noise_bcs)
+                torch.manual_seed(4321)
+                out[f"{tag}/loss_l1"] = np.array(gd1(x, C, _MD(cell_idx), None)[0].item())
+            print(tag, "loss", loss.item())
+    np.savez_compressed(HERE / "diffusion.npz", **out)
+
+
+def gen_grid():
+    """grid_embedding / cell types / cell helpers through the reference's own dataclasses
+    (SURVEY.md appendix C)."""
+    V = ofles.Variable
+    BC = ofles.BoundaryCondition
+    out = {}
+    geo = grid_ref.channel_geometry(cells=(12, 6, 5), hole=((3, 6), (1, 4), (0, 3)), seed=3)
+    rng = np.random.Generator(np.random.PCG64(11))
+    B, n = 2, len(geo.cell_idx)
+    u = rng.standard_normal((B, n, 3)).astype(np.float32)
+    p = rng.standard_normal((B, n, 1)).astype(np.float32)
+    bnd = {k: {"type": "patch", "idx": torch.from_numpy(v)} for k, v in geo.boundaries.items()}
+    bcs = {
+        V.U: {"inlets": BC(BC.Type.FIXED_VALUE, torch.tensor([20.0, 0.0, 0.0])),
+              "walls": BC(BC.Type.FIXED_VALUE, torch.tensor([0.0, 0.0, 0.0]))},
+        V.P: {"outlets": BC(BC.Type.FIXED_VALUE, torch.tensor([0.0]))},
+    }
+    md = ofles.OpenFOAMMetadata(file=Path("/synthetic/case/data.h5"), nu=1e-5, h=torch.ones(3),
+                                cell_counts=np.array(geo.padded), cell_idx=torch.from_numpy(geo.cell_idx),
+                                boundaries=bnd, boundary_conditions=bcs, holes=[])
+    data = ofles.OpenFOAMData(md, torch.zeros(B), {V.U: torch.from_numpy(u), V.P: torch.from_numpy(p)})
+    grid = data.grid_embedding((V.U, V.P))
+    out["grid_embedding"] = grid.numpy()
+    emb = CellTypeLearnedEmbedding(4)
+    table = rng.standard_normal((6, 4)).astype(np.float32)
+    with torch.no_grad():
+        emb.embedding.weight.copy_(torch.from_numpy(table))
+        out["cell_types"] = emb.cell_types(data).numpy()
+        out["cell_type_embedding"] = emb(data).numpy()
+    out["table"] = table
+    other = torch.from_numpy(rng.standard_normal(grid.shape).astype(np.float32))
+    out["other"] = other.numpy()
+    out["where_cells"] = ref_utils.where_cells(md.cell_idx, grid, other).numpy()
+    out["where_cells_zero"] = ref_utils.where_cells(md.cell_idx, other).numpy()
+    out["select_cells"] = ref_utils.select_cells(other, md.cell_idx).numpy()
+    np.savez_compressed(HERE / "grid.npz", **out)
+    print("grid", grid.shape, np.bincount(out["cell_types"].ravel(), minlength=6))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    gen_layout()
+    gen_schedules()
+    gen_time_embedding()
+    gen_grid()
+    gen_unet()
+    gen_diffusion()
+    for f in sorted(HERE.glob("*.npz")):
+        print(f.name, f.stat().st_size // 1024, "KiB")
