@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""Benchmark of the TurbDiff denoising hot path (BASELINE.json metric: DDPM samples/sec at
+192x48x48 on 1/2/4/8 B200).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
+
+One "step" = one ancestral-sampling step of the shapes-config model (dim 32, 4 levels, padded grid
+194x50x50, u+p) over a batch of B samples per GPU: U-Net forward, two Gaussian draws and the fused
+posterior update.  A full sample is T such steps, so samples/s = B*N / (T * t_step).  Samples are
+independent: ranks share nothing (weak scaling, no data-path collective).
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT, ROOT / "generative-turbulence_b200"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CELLS = (192, 48, 48)
+HOLE = ((12, 24), (16, 32), (0, 32))  # scripts/generate-performance-dataset.py:25 ("wide pillar")
+METRIC = "ddpm_samples_per_sec"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4, help="samples per GPU per step")
+    ap.add_argument("--timesteps", type=int, default=1000, help="T of the sampled chain (BASELINE configs[2]: 1000)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--e2e-steps", type=int, default=8, help="chain length of one end-to-end public-API call")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+def shapes_spec(T):
+    from oracle.unet_ref import UNetSpec
+
+    return UNetSpec(in_features=4, out_features=4, c_local_features=4, timesteps=T, dim=32, u_net_levels=4, groups=8)
+
+
+def synthetic_inputs(B, seed):
+    """x_bcs ~ N(0,1) on the padded grid, cell-type conditioning from a seeded 6x4 table."""
+    from oracle import grid_ref
+
+    geo = grid_ref.channel_geometry(cells=CELLS, hole=HOLE, seed=0)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    table = rng.standard_normal((6, 4)).astype(np.float32)
+    c_local = torch.from_numpy(np.ascontiguousarray(grid_ref.cell_type_embedding(geo, table)))
+    x = torch.from_numpy(rng.standard_normal((B, 4, *geo.padded)).astype(np.float32))
+    return geo, x, c_local
+
+
+def conv_flops_per_sample(spec, spatial):
+    """Algorithmic FLOPs of one denoiser forward (2*Cin*Cout*k^3*voxels summed over the 3x3x3 and
+    1x1x1 convs; SURVEY.md section 8a: 666.2 GFLOP at the shapes config)."""
+    from oracle.unet_ref import level_sizes
+
+    sizes = level_sizes(spatial, spec.u_net_levels)
+    vox = [int(np.prod(s)) for s in sizes]
+    d = spec.dim
+    total = 0.0
+
+    def rb(cin, cout, lvl):
+        f = 2.0 * 27 * vox[lvl] * (cin * cout + cout * cout)
+        if cin != cout:
+            f += 2.0 * vox[lvl] * cin * cout
+        return f
+
+    total += 2.0 * vox[0] * (spec.in_features * d + spec.c_local_features * d)  # encoders
+    for l, (cin, cout) in enumerate(spec.down_channels()):
+        total += rb(cin, cout, l)
+    L = spec.u_net_levels
+    cd = spec.center_dim
+    total += 2 * rb(cd, cd, L)
+    total += 2.0 * vox[L] * (cd * 384 + 128 * cd)
+    for i, (cin, cout) in enumerate(spec.up_channels()):
+        total += rb(cin, cout, L - 1 - i)
+    total += rb(d, d, 0) + 2.0 * vox[0] * d * spec.out_features
+    return total
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples of one GPU during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def time_cpu_reference(T, n_steps, warm, threads=None):
+    """The reference algorithm (CPU oracle port: oracle/unet_ref.py + oracle/diffusion_ref.py) on the host
+    cores: B=1 denoise steps of the shapes config.  Returns (seconds per step, cores)."""
+    from oracle.diffusion_ref import DiffusionRef
+    from oracle.unet_ref import denoiser_forward, synth_state_dict
+
+    if threads:
+        torch.set_num_threads(threads)
+    spec = shapes_spec(T)
+    sd = synth_state_dict(spec, 0)
+    geo, x, c_local = synthetic_inputs(1, 1)
+    idx = torch.from_numpy(geo.cell_idx)
+    d = DiffusionRef(lambda xt, tt: denoiser_forward(sd, spec, xt, tt, c_local), timesteps=T, beta_schedule="log-snr-linear", noise_bcs=True)
+    times = []
+    with torch.no_grad():
+        xt = torch.randn_like(x)
+        for i in range(warm + n_steps):
+            t0 = time.perf_counter()
+            tt = torch.full((1,), T - 1 - i, dtype=torch.long)
+            _, _, mean, log_var = d.predictions(xt, tt, idx)
+            z = torch.randn_like(xt)
+            xt = mean + (log_var / 2).exp() * z
+            from oracle.diffusion_ref import where_cells
+
+            xt = where_cells(idx, xt, d.q_sample(x, tt, torch.randn_like(x)))
+            if i >= warm:
+                times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    T = args.timesteps
+    sec, cores = time_cpu_reference(T, max(1, args.steps), max(0, args.warmup))
+    value = 1.0 / (sec * T)
+    sample = f"B=1 single denoise steps of the shapes config ({args.steps} timed, {args.warmup} warm-up), extrapolated to T={T} steps per sample"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs[2] DDPM ancestral sampling, shapes config 194x50x50 u+p, T={T}", "batch_per_step": 1, "timesteps": T},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    from oracle.unet_ref import synth_state_dict
+    from turbdiff_b200 import DenoisingModel, GaussianDiffusion, _lib
+    from turbdiff_b200.models.conditioning import Conditioning
+    from turbdiff_b200.models.utils import inside_mask
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    T, B = args.timesteps, args.batch
+    spec = shapes_spec(T)
+    model = DenoisingModel(in_features=4, out_features=4, c_local_features=4, c_global_features=0, timesteps=T, dim=32, u_net_levels=4,
+                           norm_type="group", precision=args.precision)
+    model.load_state_dict(synth_state_dict(spec, 0))
+    model = model.to(dev).eval()
+    gd = GaussianDiffusion(model, timesteps=T, beta_schedule="log-snr-linear", loss_type="l2", noise_bcs=True).to(dev)
+    geo, x_host, c_local = synthetic_inputs(B, 100 + rank)
+    x_pinned = x_host.pin_memory()
+    out_pinned = torch.empty_like(x_host).pin_memory()
+    x_bcs = x_pinned.to(dev, non_blocking=True)
+    C = {Conditioning.Type.CELL_TYPE: c_local.to(dev)}
+    cl = C[Conditioning.Type.CELL_TYPE]
+    cell_idx = torch.from_numpy(geo.cell_idx).to(dev)
+    nvox = int(np.prod(geo.padded))
+    mask = inside_mask(cell_idx, nvox)
+    coef = gd._coef_table(dev)
+    eng = model.engine()
+    flags = _lib.STEP_NOISE_BCS
+
+    x_t = torch.randn_like(x_bcs)
+    t_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    t_vec = torch.zeros(B, dtype=torch.int64, device=dev)
+    step_no = [0]
+
+    graph = None
+
+    def unet():
+        if graph is not None:
+            graph.replay()
+            return eng.plan(B, geo.padded, dev)["eps"]
+        return eng.forward(x_t, t_vec, cl)
+
+    def one_step():
+        t = T - 1 - (step_no[0] % (T - 1))
+        step_no[0] += 1
+        t_dev.fill_(t)
+        t_vec.fill_(t)
+        eps = unet()
+        z = torch.randn_like(x_t)
+        z_bc = torch.randn_like(x_bcs)
+        _lib.call("tdb_ddpm_step", x_t.data_ptr(), eps.data_ptr(), z.data_ptr(), z_bc.data_ptr(), x_bcs.data_ptr(), mask.data_ptr(),
+                  coef.data_ptr(), t_dev.data_ptr(), x_t.data_ptr(), B, 4, nvox, flags, _lib.stream_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up (also builds the plan and the packed-weight cache), then capture the U-Net launch program
+    one_step()
+    torch.cuda.synchronize()
+    launches_per_unet = None
+    if not args.no_graph:
+        n0 = _lib.launch_count()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            eng.forward(x_t, t_vec, cl)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            eng.forward(x_t, t_vec, cl)
+        launches_per_unet = (_lib.launch_count() - n0) // 2
+        graph = g
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+
+    # ---- timed region: device-resident inputs ---------------------------------------------------
+    clocks = ClockSampler(local)
+    barrier()
+    n_l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - n_l0
+    if graph is not None:
+        launches += launches_per_unet * args.steps  # graph replays re-issue the captured C-ABI launches
+    clk = clocks.stop()
+    tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    ms_per_step = ms / args.steps
+    value = world * B / (T * ms_per_step * 1e-3)
+
+    # ---- end to end through the public API: host buffers in, host buffers out -----------------------
+    S = max(2, args.e2e_steps)
+    graph_saved, graph = graph, None
+
+    def e2e_call():
+        xb = x_pinned.to(dev, non_blocking=True)
+        s = gd.p_sample_loop(xb, C, cell_idx, start_from=S)
+        out_pinned.copy_(s, non_blocking=True)
+
+    e2e_call()
+    barrier()
+    reps = 2
+    e0.record()
+    for _ in range(reps):
+        e2e_call()
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * B / (float(e2e_ms.item()) * 1e-3 * T / S)
+    graph = graph_saved
+
+    # ---- per-kernel device times (CUDA events around every C-ABI launch, eager, after the timed region)
+    roof = None
+    if rank == 0:
+        _lib.PROFILE = {}
+        graph_saved, graph = graph, None
+        for _ in range(3):
+            one_step()
+        torch.cuda.synchronize()
+        prof = {k: sum(a.elapsed_time(b) for a, b in v) / 3 for k, v in _lib.PROFILE.items()}
+        _lib.PROFILE = None
+        graph = graph_saved
+        pk = peaks()
+        conv_ms = prof.get("tdb_conv3d_bf16", prof.get("tdb_conv3d_f32", 0.0))
+        flops = conv_flops_per_sample(spec, geo.padded) * B
+        ach = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        peak = pk["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "kernel": "conv3d_bf16_tc_kernel (all 34 conv launches of one step)", "achieved": ach, "peak": peak,
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_src": f"{pk['src']} bf16 sustained (kernel timed inside a long step)",
+                "conv_ms_per_step": conv_ms, "kernel_ms_per_step": prof}
+        # the bandwidth-bound update kernel against the HBM roofline: 6 tensors x 4 B per element
+        st_ms = prof.get("tdb_ddpm_step", 0.0)
+        if st_ms > 0:
+            bytes_step = 6 * 4 * B * 4 * nvox + nvox
+            roof["ddpm_step"] = {"bound": "hbm", "achieved": bytes_step / (st_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                 "frac": bytes_step / (st_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "algorithmic_bytes": bytes_step}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, cores = time_cpu_reference(T, 3, 1)
+        cpu = {"value": 1.0 / (sec * T), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"3 timed B=1 denoise steps of the same workload on the host ({sec:.2f} s/step), extrapolated to T={T}"}
+
+    if rank == 0:
+        h2d = x_pinned.numel() * 4
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"configs[2] DDPM ancestral sampling, shapes config 194x50x50 u+p (dim 32, 4 levels, 55.2M params), T={T}",
+                       "batch_per_gpu": B, "timesteps": T, "step": "one denoise step of the whole batch (U-Net forward + 2 randn + fused update)",
+                       "l2": "activations exceed L2 (>= 270 MB per level-0 tensor), no flush needed", "cuda_graph": graph is not None,
+                       "samples_per_sec_T500": value * T / 500},
+            "clocks": clk, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
+                    "how": f"GaussianDiffusion.p_sample_loop(start_from={S}) on pinned host x_bcs -> pinned host sample, scaled by T/{S}"},
+            "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (turbdiff_b200 has no CPU path); use --impl reference for the host baseline")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

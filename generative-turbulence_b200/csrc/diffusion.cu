@@ -1,0 +1,254 @@
+// The DDPM process around the denoiser as single-pass, HBM-bound kernels on the reference's
+// NCDHW fp32 tensors: the fused ancestral-sampling update, q_sample, the masked training loss
+// (+ gradient) and the bit-exact cell indexing helpers.
+//
+// The update arithmetic uses explicitly rounded multiplies/adds (__fmul_rn/__fadd_rn, no FMA
+// contraction) in the reference's evaluation order, so given identical eps and noise the result
+// is bit-identical to the reference's chain of elementwise torch kernels (ddpm.py:711-728,797-814).
+#include "common.cuh"
+
+using namespace tdb;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct StepCoef {
+    float recip, recipm1, c1, c2, sigma, sa, s1m;
+};
+
+__device__ __forceinline__ StepCoef load_coef(const float* __restrict__ coef, int t) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(coef + (int64_t)t * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(coef + (int64_t)t * 8 + 4));
+    return StepCoef{a.x, a.y, a.z, a.w, b.x, b.y, b.z};
+}
+
+__device__ __forceinline__ float step_one(float xt, float e, float z, float zbc, float xb, bool inside,
+                                          const StepCoef& k, bool t0, unsigned flags) {
+    float x0 = __fsub_rn(__fmul_rn(k.recip, xt), __fmul_rn(k.recipm1, e));
+    if (!(flags & TDB_STEP_NOISE_BCS) && !inside) x0 = xt;
+    if (flags & TDB_STEP_CLIP) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+    float x = __fadd_rn(__fmul_rn(k.c1, x0), __fmul_rn(k.c2, xt));
+    if (!t0) {
+        if (flags & TDB_STEP_NOISE_BCS) {
+            x = __fadd_rn(x, __fmul_rn(k.sigma, z));
+            if (!inside) x = __fadd_rn(__fmul_rn(k.sa, xb), __fmul_rn(k.s1m, zbc));
+        } else {
+            x = __fadd_rn(x, __fmul_rn(k.sigma, inside ? z : 0.0f));
+        }
+    }
+    if ((flags & TDB_STEP_FINAL) && !inside) x = xb;
+    return x;
+}
+
+// VEC = 4: float4 path (nvox % 4 == 0 and 16-byte aligned bases); VEC = 1: scalar fallback.
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+ddpm_step_kernel(const float* __restrict__ x_t, const float* __restrict__ eps, const float* __restrict__ z,
+                 const float* __restrict__ z_bc, const float* __restrict__ x_bcs, const uint8_t* __restrict__ mask,
+                 const float* __restrict__ coef, const int32_t* __restrict__ t_ptr, float* __restrict__ x_out,
+                 int64_t rows, int64_t nvox, unsigned flags) {
+    const int t = *t_ptr;
+    const StepCoef k = load_coef(coef, t);
+    const bool t0 = t == 0;
+    const bool need_z = !t0;
+    const bool need_zbc = !t0 && (flags & TDB_STEP_NOISE_BCS);
+    const bool need_xb = need_zbc || (flags & TDB_STEP_FINAL);
+    const int64_t per_row = nvox / VEC;
+    const int64_t total = rows * per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = (i % per_row) * VEC;
+        const int64_t off = i * VEC;
+        if constexpr (VEC == 4) {
+            const float4 xt = *reinterpret_cast<const float4*>(x_t + off);
+            const float4 e = *reinterpret_cast<const float4*>(eps + off);
+            const uchar4 m = *reinterpret_cast<const uchar4*>(mask + v);
+            float4 zz = make_float4(0, 0, 0, 0), zb = zz, xb = zz;
+            if (need_z) zz = *reinterpret_cast<const float4*>(z + off);
+            if (need_zbc) zb = *reinterpret_cast<const float4*>(z_bc + off);
+            if (need_xb) xb = *reinterpret_cast<const float4*>(x_bcs + off);
+            float4 o;
+            o.x = step_one(xt.x, e.x, zz.x, zb.x, xb.x, m.x != 0, k, t0, flags);
+            o.y = step_one(xt.y, e.y, zz.y, zb.y, xb.y, m.y != 0, k, t0, flags);
+            o.z = step_one(xt.z, e.z, zz.z, zb.z, xb.z, m.z != 0, k, t0, flags);
+            o.w = step_one(xt.w, e.w, zz.w, zb.w, xb.w, m.w != 0, k, t0, flags);
+            *reinterpret_cast<float4*>(x_out + off) = o;
+        } else {
+            x_out[off] = step_one(x_t[off], eps[off], need_z ? z[off] : 0.f, need_zbc ? z_bc[off] : 0.f,
+                                  need_xb ? x_bcs[off] : 0.f, mask[v] != 0, k, t0, flags);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const int64_t* __restrict__ t,
+                const float* __restrict__ coef, const uint8_t* __restrict__ mask, float* __restrict__ out, int B,
+                int F, int64_t nvox, int noise_bcs) {
+    const int64_t per_sample = (int64_t)F * nvox;
+    const int64_t total = (int64_t)B * per_sample;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per_sample);
+        const StepCoef k = load_coef(coef, (int)t[b]);
+        float v = __fadd_rn(__fmul_rn(k.sa, x0[i]), __fmul_rn(k.s1m, noise[i]));
+        if (!noise_bcs && mask[i % nvox] == 0) v = x0[i];
+        out[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+masked_loss_kernel(const float* __restrict__ eps, const float* __restrict__ noise, const uint8_t* __restrict__ mask,
+                   double* __restrict__ loss_acc, float* __restrict__ grad, int64_t total, int64_t nvox,
+                   double inv_count, int l1) {
+    __shared__ double warp_part[kThreads / 32];
+    double local = 0.0;
+    const float gscale = (float)((l1 ? 1.0 : 2.0) * inv_count);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool inside = mask[i % nvox] != 0;
+        const float d = eps[i] - noise[i];
+        float g = 0.0f;
+        if (inside) {
+            if (l1) {
+                local += (double)fabsf(d);
+                g = d > 0.f ? gscale : (d < 0.f ? -gscale : 0.f);
+            } else {
+                local += (double)d * (double)d;
+                g = gscale * d;
+            }
+        }
+        if (grad) grad[i] = g;
+    }
+    local = warp_sum(local);
+    if (threadIdx.x % 32 == 0) warp_part[threadIdx.x / 32] = local;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < kThreads / 32 ? warp_part[threadIdx.x] : 0.0;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(loss_acc, v * inv_count);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+where_cells_kernel(const float* __restrict__ a, const float* __restrict__ other, const uint8_t* __restrict__ mask,
+                   float* __restrict__ out, int64_t total, int64_t nvox) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = mask[i % nvox] ? a[i] : (other ? other[i] : 0.0f);
+}
+
+__global__ void __launch_bounds__(kThreads)
+select_cells_kernel(const float* __restrict__ x, const int64_t* __restrict__ cell_idx, float* __restrict__ out,
+                    int64_t rows, int64_t nvox, int64_t n_cells) {
+    const int64_t total = rows * n_cells;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n_cells, j = i % n_cells;
+        out[i] = x[r * nvox + cell_idx[j]];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+scatter_cells_kernel(const float* __restrict__ samples, const int64_t* __restrict__ cell_idx, float* __restrict__ grid,
+                     int B, int F, int64_t nvox, int64_t n_cells) {
+    const int64_t total = (int64_t)B * n_cells * F;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(i % F);
+        const int64_t j = (i / F) % n_cells;
+        const int64_t b = i / ((int64_t)F * n_cells);
+        grid[(b * F + f) * nvox + cell_idx[j]] = samples[i];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+build_mask_kernel(const int64_t* __restrict__ cell_idx, uint8_t* __restrict__ mask, int64_t n_cells, int64_t nvox) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = cell_idx[i];
+        if (v >= 0 && v < nvox) mask[v] = 1;
+    }
+}
+
+int blocks_for(int64_t n) {
+    int64_t b = ceil_div(n, kThreads);
+    const int64_t cap = 148 * 8;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+extern "C" {
+
+int tdb_ddpm_step(const float* x_t, const float* eps, const float* z, const float* z_bc, const float* x_bcs,
+                  const uint8_t* mask, const float* coef, const int32_t* t_ptr, float* x_out, int B, int F,
+                  int64_t nvox, unsigned flags, void* stream) {
+    TDB_REQUIRE(x_t && eps && mask && coef && t_ptr && x_out && z, TDB_E_BADARG, "tdb_ddpm_step: null pointer");
+    TDB_REQUIRE(x_bcs || !(flags & (TDB_STEP_NOISE_BCS | TDB_STEP_FINAL)), TDB_E_BADARG, "tdb_ddpm_step: x_bcs required");
+    TDB_REQUIRE(z_bc || !(flags & TDB_STEP_NOISE_BCS), TDB_E_BADARG, "tdb_ddpm_step: z_bc required with NOISE_BCS");
+    const int64_t rows = (int64_t)B * F;
+    auto al = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+    const bool vec = nvox % 4 == 0 && al(x_t) && al(eps) && al(z) && al(z_bc) && al(x_bcs) && al(x_out) &&
+                     ((uintptr_t)mask & 3) == 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (vec)
+        ddpm_step_kernel<4><<<blocks_for(rows * nvox / 4), kThreads, 0, s>>>(x_t, eps, z, z_bc, x_bcs, mask, coef, t_ptr,
+                                                                              x_out, rows, nvox, flags);
+    else
+        ddpm_step_kernel<1><<<blocks_for(rows * nvox), kThreads, 0, s>>>(x_t, eps, z, z_bc, x_bcs, mask, coef, t_ptr, x_out,
+                                                                          rows, nvox, flags);
+    TDB_CHECK_LAUNCH("tdb_ddpm_step");
+    return 0;
+}
+
+int tdb_q_sample(const float* x0, const float* noise, const int64_t* t, const float* coef, const uint8_t* mask,
+                 float* out, int B, int F, int64_t nvox, int noise_bcs, void* stream) {
+    TDB_REQUIRE(x0 && noise && t && coef && out && (noise_bcs || mask), TDB_E_BADARG, "tdb_q_sample: null pointer");
+    q_sample_kernel<<<blocks_for((int64_t)B * F * nvox), kThreads, 0, (cudaStream_t)stream>>>(x0, noise, t, coef, mask, out,
+                                                                                               B, F, nvox, noise_bcs);
+    TDB_CHECK_LAUNCH("tdb_q_sample");
+    return 0;
+}
+
+int tdb_masked_loss(const float* eps, const float* noise, const uint8_t* mask, double* loss_acc, float* grad, int B,
+                    int F, int64_t nvox, int64_t n_inside, int l1, void* stream) {
+    TDB_REQUIRE(eps && noise && mask && loss_acc && n_inside > 0, TDB_E_BADARG, "tdb_masked_loss: bad argument");
+    const int64_t total = (int64_t)B * F * nvox;
+    const double inv_count = 1.0 / ((double)B * F * (double)n_inside);
+    masked_loss_kernel<<<blocks_for(total), kThreads, 0, (cudaStream_t)stream>>>(eps, noise, mask, loss_acc, grad, total,
+                                                                                  nvox, inv_count, l1);
+    TDB_CHECK_LAUNCH("tdb_masked_loss");
+    return 0;
+}
+
+int tdb_where_cells(const float* a, const float* other, const uint8_t* mask, float* out, int64_t rows, int64_t nvox,
+                    void* stream) {
+    TDB_REQUIRE(a && mask && out, TDB_E_BADARG, "tdb_where_cells: null pointer");
+    if (rows * nvox == 0) return 0;
+    where_cells_kernel<<<blocks_for(rows * nvox), kThreads, 0, (cudaStream_t)stream>>>(a, other, mask, out, rows * nvox, nvox);
+    TDB_CHECK_LAUNCH("tdb_where_cells");
+    return 0;
+}
+
+int tdb_select_cells(const float* x, const int64_t* cell_idx, float* out, int64_t rows, int64_t nvox, int64_t n_cells,
+                     void* stream) {
+    if (rows * n_cells == 0) return 0;
+    TDB_REQUIRE(x && cell_idx && out, TDB_E_BADARG, "tdb_select_cells: null pointer");
+    select_cells_kernel<<<blocks_for(rows * n_cells), kThreads, 0, (cudaStream_t)stream>>>(x, cell_idx, out, rows, nvox, n_cells);
+    TDB_CHECK_LAUNCH("tdb_select_cells");
+    return 0;
+}
+
+int tdb_scatter_cells(const float* samples, const int64_t* cell_idx, float* grid, int B, int F, int64_t nvox,
+                      int64_t n_cells, void* stream) {
+    if ((int64_t)B * F * n_cells == 0) return 0;
+    TDB_REQUIRE(samples && cell_idx && grid, TDB_E_BADARG, "tdb_scatter_cells: null pointer");
+    scatter_cells_kernel<<<blocks_for((int64_t)B * F * n_cells), kThreads, 0, (cudaStream_t)stream>>>(samples, cell_idx, grid,
+                                                                                                       B, F, nvox, n_cells);
+    TDB_CHECK_LAUNCH("tdb_scatter_cells");
+    return 0;
+}
+
+int tdb_build_mask(const int64_t* cell_idx, uint8_t* mask, int64_t n_cells, int64_t nvox, void* stream) {
+    if (n_cells == 0) return 0;
+    TDB_REQUIRE(cell_idx && mask, TDB_E_BADARG, "tdb_build_mask: null pointer");
+    build_mask_kernel<<<blocks_for(n_cells), kThreads, 0, (cudaStream_t)stream>>>(cell_idx, mask, n_cells, nvox);
+    TDB_CHECK_LAUNCH("tdb_build_mask");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+"""ctypes binding of libturbdiff_b200.so (the C ABI declared in include/turbdiff_b200.h).
+
+The library is built in-tree by ``generative-turbulence_b200/build.py``.  A missing library
+is a hard error: the product path has no fallback."""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+LIB_PATH = Path(__file__).resolve().parent / "libturbdiff_b200.so"
+
+F32, BF16 = 0, 1
+PW_SILU, PW_NOHALO = 1, 2
+STEP_NOISE_BCS, STEP_CLIP, STEP_FINAL = 1, 2, 4
+
+_p, _i, _l, _u, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint, C.c_float
+
+# name -> argument types (all return int unless noted)
+SIGNATURES = {
+    "tdb_encode_input": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "tdb_decode_output": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "tdb_conv3d_f32": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "tdb_conv3d_bf16": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
+    "tdb_gn_stats": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "tdb_pointwise": [_p, _i, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _f, _u, _i, _p],
+    "tdb_trilinear": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "tdb_attention": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "tdb_time_film": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "tdb_ddpm_step": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _l, _u, _p],
+    "tdb_q_sample": [_p, _p, _p, _p, _p, _p, _i, _i, _l, _i, _p],
+    "tdb_masked_loss": [_p, _p, _p, _p, _p, _i, _i, _l, _l, _i, _p],
+    "tdb_where_cells": [_p, _p, _p, _p, _l, _l, _p],
+    "tdb_select_cells": [_p, _p, _p, _l, _l, _l, _p],
+    "tdb_scatter_cells": [_p, _p, _p, _i, _i, _l, _l, _p],
+    "tdb_build_mask": [_p, _p, _l, _l, _p],
+}
+OTHER = {"tdb_last_error": ([], C.c_char_p), "tdb_version": ([], _i), "tdb_launch_count": ([], _l)}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python generative-turbulence_b200/build.py` "
+                "(turbdiff_b200 has no CPU or PyTorch fallback)"
+            )
+        lib = C.CDLL(str(LIB_PATH))
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = _i
+        for name, (args, res) in OTHER.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = res
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().tdb_last_error().decode(errors="replace")
+        raise RuntimeError(f"libturbdiff_b200 {what} failed (code {rc}): {msg}")
+
+
+# Optional per-kernel timing (bench.py): name -> list of (start, end) CUDA events recorded on the
+# launching stream around each C-ABI call.  None = off (the normal case: zero overhead).
+PROFILE: dict | None = None
+
+
+def call(name: str, *args) -> None:
+    if PROFILE is None:
+        check(getattr(load(), name)(*args), name)
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    check(getattr(load(), name)(*args), name)
+    b.record()
+    PROFILE.setdefault(name, []).append((a, b))
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def launch_count() -> int:
+    return int(load().tdb_launch_count())
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"turbdiff_b200: {what} must live on a CUDA device (got {t.device}); there is no CPU path")

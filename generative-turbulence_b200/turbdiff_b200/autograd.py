@@ -1,0 +1,40 @@
+"""torch.autograd glue: pairs the forward launch programs with their backward programs."""
+
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import call
+
+
+class _MaskedLoss(torch.autograd.Function):
+    """mean_b mean_{f, inside cells} |eps - noise|^p and d/d eps in one pass (ddpm.py:845-852)."""
+
+    @staticmethod
+    def forward(ctx, eps, noise, mask, n_inside, l1):
+        eps = eps.contiguous()
+        noise = noise.contiguous()
+        B, F = eps.shape[:2]
+        nvox = eps[0, 0].numel()
+        acc = torch.zeros(1, dtype=torch.float64, device=eps.device)
+        grad = torch.empty_like(eps) if eps.requires_grad else None
+        call("tdb_masked_loss", eps.data_ptr(), noise.data_ptr(), mask.data_ptr(), acc.data_ptr(), _lib.ptr(grad), B, F, nvox,
+             n_inside, 1 if l1 else 0, _lib.stream_ptr())
+        ctx.grad = grad
+        return acc.to(torch.float32).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        return (ctx.grad * g if ctx.grad is not None else None), None, None, None, None
+
+
+def masked_loss(eps, noise, mask, n_inside: int, l1: bool):
+    return _MaskedLoss.apply(eps, noise, mask, n_inside, l1)
+
+
+def denoise_with_grad(model, x, t, c_local):
+    raise NotImplementedError(
+        "turbdiff_b200: the backward launch program of the denoiser is not built yet; call the model under "
+        "torch.no_grad() (sampling / evaluation)"
+    )

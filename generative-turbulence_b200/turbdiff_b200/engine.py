@@ -1,0 +1,348 @@
+"""Static launch program for the denoiser: workspace planning + kernel sequencing.
+
+The nn.Module tree in ``models/ddpm.py`` only owns the parameters (same names as the
+reference, for checkpoint compatibility).  The compute is organised B200-first: for a given
+(batch, grid, precision) a *plan* lays every activation out once in HBM as halo grids
+(channels-last, replicate halo materialised, skip tensors written straight into the channel
+slice of the consumer's concat buffer), and a flat list of C-ABI kernel launches walks it.
+Nothing is allocated while the program runs, so a whole denoise step is CUDA-graph capturable.
+
+Reference semantics implemented here: DenoisingModel.forward ddpm.py:477-505,
+UNet.forward :351-372, ResnetBlock :190-197, Block :168-177, Attention :295-308.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, PW_NOHALO, PW_SILU, call, ptr
+
+GN_EPS = 1e-5
+
+
+@dataclass
+class View:
+    """A halo-grid tensor (or a channel slice of one): base tensor, channel offset/count, pitch."""
+
+    t: torch.Tensor  # [B, Xp, Yp, Zp, ld]
+    c0: int
+    C: int
+    level: int
+
+    @property
+    def ld(self) -> int:
+        return self.t.shape[-1]
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr() + self.c0 * self.t.element_size()
+
+    def slice(self, c0: int, C: int) -> "View":
+        return View(self.t, self.c0 + c0, C, self.level)
+
+
+def level_sizes(spatial, levels):
+    """max(int(s/2), 3) per axis per level (ddpm.py:358)."""
+    sizes = [tuple(int(s) for s in spatial)]
+    for _ in range(levels):
+        sizes.append(tuple(max(int(s * 0.5), 3) for s in sizes[-1]))
+    return sizes
+
+
+class _BlockParams:
+    """Flat parameter handles of one ResnetBlock."""
+
+    def __init__(self, blk, film_offset):
+        self.blk = blk
+        self.cin = blk.block1.conv.in_channels
+        self.cout = blk.block1.conv.out_channels
+        self.has_proj = not isinstance(blk.conv, torch.nn.Identity)
+        self.film_offset = film_offset
+
+
+class DenoiserEngine:
+    def __init__(self, model, precision: str = "fp32"):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        self.model = model
+        self.precision = precision
+        self.dt = F32 if precision == "fp32" else BF16
+        self.tdtype = torch.float32 if precision == "fp32" else torch.bfloat16
+        self.fused_stats = precision == "bf16"
+        self._plans = {}
+        self._wcache = None
+        self._wversion = None
+
+        m = model
+        un = m.u_net
+        self.blocks: dict[str, _BlockParams] = {}
+        off = 0
+        order = [("decode0", m.decode[0])]
+        order += [(f"down{i}", b) for i, b in enumerate(un.downsampling_blocks)]
+        order += [(f"up{i}", b) for i, b in enumerate(un.upsampling_blocks)]
+        order += [("center0", un.center_block[0]), ("center2", un.center_block[2])]
+        for name, blk in order:
+            bp = _BlockParams(blk, off)
+            self.blocks[name] = bp
+            off += 2 * bp.cout
+        self.film_rows = off
+        self.block_order = [n for n, _ in order]
+
+    # ------------------------------------------------------------------ derived weight cache
+    def _param_version(self):
+        return tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+
+    def weights(self):
+        """Kernel-layout copies of the conv weights, refreshed when any parameter changed
+        (optimizer step / load_state_dict).  Layout: fp32 [ntaps][Cin][Cout]; bf16 [Cout][ntaps*Cin]."""
+        ver = self._param_version()
+        if self._wcache is not None and ver == self._wversion:
+            return self._wcache
+        m = self.model
+        w = {}
+
+        def pack(conv):
+            wt = conv.weight.detach()
+            cout, cin = wt.shape[:2]
+            taps = wt.shape[2] * wt.shape[3] * wt.shape[4]
+            if self.precision == "fp32":
+                return wt.permute(2, 3, 4, 1, 0).reshape(taps, cin, cout).contiguous().float()
+            return wt.permute(0, 2, 3, 4, 1).reshape(cout, taps * cin).contiguous().to(torch.bfloat16)
+
+        for name, bp in self.blocks.items():
+            w[f"{name}.conv1"] = pack(bp.blk.block1.conv)
+            w[f"{name}.conv2"] = pack(bp.blk.block2.conv)
+            if bp.has_proj:
+                w[f"{name}.proj"] = pack(bp.blk.conv)
+        att = m.u_net.center_block[1].fn.fn
+        w["attn.qkv"] = pack(att.to_qkv)
+        w["attn.out"] = pack(att.to_out)
+        w["film_w"] = torch.cat([self.blocks[n].blk.project_onto_scale_shift.weight.detach() for n in self.block_order]).contiguous().float()
+        w["film_b"] = torch.cat([self.blocks[n].blk.project_onto_scale_shift.bias.detach() for n in self.block_order]).contiguous().float()
+        self._wcache, self._wversion = w, ver
+        return w
+
+    # ------------------------------------------------------------------ workspace
+    def plan(self, B, spatial, device):
+        key = (B, tuple(spatial), str(device))
+        if key in self._plans:
+            return self._plans[key]
+        m = self.model
+        L = m.u_net_levels
+        dim = m.dim
+        sizes = level_sizes(spatial, L)
+        td = self.tdtype
+
+        def grid(level, C):
+            X, Y, Z = sizes[level]
+            return View(torch.zeros((B, X + 2, Y + 2, Z + 2, C), dtype=td, device=device), 0, C, level)
+
+        p = {"sizes": sizes, "B": B}
+        c_in0 = dim + (dim if m.c_local_features > 0 else 0)
+        p["xin0"] = grid(0, c_in0)
+        cd = [dim * 2 ** (l + 1) for l in range(L)]  # channels of down block l's output / skip
+        p["cat"] = [grid(l, 2 * cd[l]) for l in range(L)]
+        p["xin"] = [p["xin0"]] + [grid(l, cd[l - 1]) for l in range(1, L)]
+        center = dim * 2**L
+        p["center_in"] = grid(L, center)
+        p["center0"] = grid(L, center)
+        p["center1"] = grid(L, center)
+        p["center2"] = grid(L, center)
+        p["up_out"] = [grid(l, dim * 2**l) for l in range(L)]
+        p["dec_out"] = grid(0, dim)
+        att = m.u_net.center_block[1].fn.fn
+        hid = att.heads * att.dim_head
+        p["attn_norm"] = grid(L, center)
+        p["attn_qkv"] = grid(L, 3 * hid)
+        p["attn_o"] = grid(L, hid)
+        p["attn_proj"] = grid(L, center)
+        # scratch sized for the largest (rows x Cout) of any block at each level
+        max_c = {}
+        for name, bp in self.blocks.items():
+            lvl = self._block_level(name)
+            max_c[lvl] = max(max_c.get(lvl, 0), bp.cout)
+        p["raw"] = {l: grid(l, c) for l, c in max_c.items()}
+        p["act"] = {l: grid(l, c) for l, c in max_c.items()}
+        p["res"] = {l: grid(l, c) for l, c in max_c.items()}
+        n_norms = 2 * len(self.blocks) + 1
+        gmax = max(self._groups(bp.cout) for bp in self.blocks.values())
+        # one flat slot per norm layer, used as [B][G][2] doubles (sum, sum of squares)
+        p["stats"] = torch.zeros((n_norms, B * gmax * 2), dtype=torch.float64, device=device)
+        p["film"] = torch.zeros((B, self.film_rows), dtype=torch.float32, device=device)
+        p["c"] = torch.zeros((B, dim), dtype=torch.float32, device=device)
+        p["eps"] = torch.zeros((B, m.out_features, *spatial), dtype=torch.float32, device=device)
+        self._plans[key] = p
+        return p
+
+    def _block_level(self, name):
+        L = self.model.u_net_levels
+        if name == "decode0":
+            return 0
+        if name.startswith("down"):
+            return int(name[4:])
+        if name.startswith("up"):
+            return L - 1 - int(name[2:])
+        return L
+
+    def _groups(self, C):
+        g = self.model.norm_groups
+        return C if g is None else g
+
+    # ------------------------------------------------------------------ kernels
+    def _conv(self, p, x: View, w, bias, out: View, ntaps, stats=None, G=0):
+        B = p["B"]
+        X, Y, Z = p["sizes"][x.level]
+        s = _lib.stream_ptr()
+        if self.precision == "fp32":
+            call("tdb_conv3d_f32", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ntaps, s)
+        else:
+            call("tdb_conv3d_bf16", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ntaps,
+                 ptr(stats), G, s)
+
+    def _stats(self, p, x: View, stats, G):
+        X, Y, Z = p["sizes"][x.level]
+        call("tdb_gn_stats", x.ptr, x.ld, stats.data_ptr(), p["B"], X, Y, Z, x.C, G, self.dt, _lib.stream_ptr())
+
+    def _pointwise(self, p, raw: View, stats, norm, film_ptr, res: View | None, out: View, flags, G=1):
+        X, Y, Z = p["sizes"][raw.level]
+        call(
+            "tdb_pointwise", raw.ptr, raw.ld, ptr(stats), ptr(norm.weight) if norm is not None else None,
+            ptr(norm.bias) if norm is not None else None, film_ptr, self.film_rows,
+            res.ptr if res is not None else None, res.ld if res is not None else 0, out.ptr, out.ld,
+            p["B"], X, Y, Z, raw.C, G, GN_EPS, flags, self.dt, _lib.stream_ptr(),
+        )
+
+    def _trilinear(self, p, x: View, out: View):
+        Xi, Yi, Zi = p["sizes"][x.level]
+        Xo, Yo, Zo = p["sizes"][out.level]
+        call("tdb_trilinear", x.ptr, x.ld, Xi, Yi, Zi, out.ptr, out.ld, Xo, Yo, Zo, p["B"], x.C, self.dt, _lib.stream_ptr())
+
+    def _norm_conv(self, p, x: View, w, conv, norm, raw: View, stats_slot):
+        """conv (+bias) followed by GroupNorm moments of its output."""
+        G = self._groups(raw.C)
+        stats = p["stats"][stats_slot]
+        fused = self.fused_stats and ((raw.C // G) % 16 == 0 or 16 % (raw.C // G) == 0)
+        self._conv(p, x, w, conv.bias, raw, 27, stats if fused else None, G)
+        if not fused:
+            self._stats(p, raw, stats, G)
+        return stats, G
+
+    def _resblock(self, p, name, x: View, out: View, slot):
+        bp = self.blocks[name]
+        w = self.weights()
+        lvl = x.level
+        blk = bp.blk
+        raw = p["raw"][lvl].slice(0, bp.cout)
+        act = p["act"][lvl].slice(0, bp.cout)
+        film_ptr = p["film"].data_ptr() + 4 * bp.film_offset
+        st, G = self._norm_conv(p, x, w[f"{name}.conv1"], blk.block1.conv, blk.block1.norm, raw, slot)
+        self._pointwise(p, raw, st, blk.block1.norm, film_ptr, None, act, PW_SILU, G)
+        st, G = self._norm_conv(p, act, w[f"{name}.conv2"], blk.block2.conv, blk.block2.norm, raw, slot + 1)
+        if bp.has_proj:
+            res = p["res"][lvl].slice(0, bp.cout)
+            self._conv(p, x, w[f"{name}.proj"], blk.conv.bias, res, 1)
+        else:
+            res = x
+        self._pointwise(p, raw, st, blk.block2.norm, None, res, out, PW_SILU, G)
+
+    def _attention(self, p, x: View, out: View, slot):
+        m = self.model
+        w = self.weights()
+        pre = m.u_net.center_block[1].fn
+        att = pre.fn
+        X, Y, Z = p["sizes"][x.level]
+        G = self._groups(x.C)
+        stats = p["stats"][slot]
+        self._stats(p, x, stats, G)
+        hn = p["attn_norm"]
+        self._pointwise(p, x, stats, pre.norm, None, None, hn, PW_NOHALO, G)
+        self._conv(p, hn, w["attn.qkv"], None, p["attn_qkv"], 1)
+        call("tdb_attention", p["attn_qkv"].ptr, p["attn_qkv"].ld, p["attn_o"].ptr, p["attn_o"].ld, p["B"], X, Y, Z,
+             att.heads, att.dim_head, self.dt, _lib.stream_ptr())
+        self._conv(p, p["attn_o"], w["attn.out"], att.to_out.bias, p["attn_proj"], 1)
+        self._pointwise(p, p["attn_proj"], None, None, None, x, out, 0)
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, t: torch.Tensor, c_local: torch.Tensor | None, taps: dict | None = None):
+        """eps = U-Net(x, t, c_local).  x (B,F,X,Y,Z) fp32 CUDA contiguous, t int64 (B,)."""
+        m = self.model
+        _lib.require_cuda(x, "x")
+        if x.dtype != torch.float32:
+            raise RuntimeError("turbdiff_b200: x must be float32 at the module boundary")
+        x = x.contiguous()
+        t = t.to(device=x.device, dtype=torch.int64).contiguous()
+        B, F = x.shape[:2]
+        spatial = tuple(x.shape[2:])
+        L = m.u_net_levels
+        p = self.plan(B, spatial, x.device)
+        w = self.weights()
+        s = _lib.stream_ptr()
+        X, Y, Z = spatial
+        Fc = m.c_local_features
+        if Fc > 0:
+            if c_local is None:
+                raise RuntimeError("turbdiff_b200: model expects local conditioning but C has none")
+            c_local = c_local.to(torch.float32).contiguous()
+            if tuple(c_local.shape) != (Fc, X, Y, Z):
+                raise RuntimeError(f"c_local shape {tuple(c_local.shape)} != {(Fc, X, Y, Z)}")
+
+        p["stats"].zero_()
+        pc = m.process_c
+        call("tdb_time_film", t.data_ptr(), m.encode_t.scale.data_ptr(), m.encode_t.bias.data_ptr(), pc[0].weight.data_ptr(),
+             pc[0].bias.data_ptr(), pc[2].weight.data_ptr(), pc[2].bias.data_ptr(), w["film_w"].data_ptr(),
+             w["film_b"].data_ptr(), p["c"].data_ptr(), p["film"].data_ptr(), B, m.dim, self.film_rows, s)
+        xin0 = p["xin0"]
+        call("tdb_encode_input", x.data_ptr(), ptr(c_local), m.encode_x.weight.data_ptr(), m.encode_x.bias.data_ptr(),
+             ptr(m.encode_c_local.weight) if Fc > 0 else None, ptr(m.encode_c_local.bias) if Fc > 0 else None,
+             xin0.ptr, xin0.ld, B, F, Fc, m.dim, X, Y, Z, 3, self.dt, s)
+
+        def tap(name, v: View):
+            if taps is not None:
+                taps[name] = self.to_ncdhw(v)
+
+        slot = 0
+        cur = xin0
+        for l in range(L):
+            cd = p["cat"][l].C // 2
+            out = p["cat"][l].slice(cd, cd)
+            self._resblock(p, f"down{l}", cur, out, slot)
+            slot += 2
+            tap(f"down{l}", out)
+            nxt = p["xin"][l + 1] if l + 1 < L else p["center_in"]
+            self._trilinear(p, out, nxt)
+            cur = nxt
+        self._resblock(p, "center0", cur, p["center0"], slot)
+        slot += 2
+        tap("center0", p["center0"])
+        self._attention(p, p["center0"], p["center1"], slot)
+        slot += 1
+        tap("center1", p["center1"])
+        self._resblock(p, "center2", p["center1"], p["center2"], slot)
+        slot += 2
+        tap("center2", p["center2"])
+        cur = p["center2"]
+        for i in range(L):
+            l = L - 1 - i
+            cat = p["cat"][l]
+            self._trilinear(p, cur, cat.slice(0, cat.C // 2))
+            self._resblock(p, f"up{i}", cat, p["up_out"][l], slot)
+            slot += 2
+            tap(f"up{i}", p["up_out"][l])
+            cur = p["up_out"][l]
+        self._resblock(p, "decode0", cur, p["dec_out"], slot)
+        tap("decode0", p["dec_out"])
+        dec = m.decode[1]
+        eps = p["eps"]
+        call("tdb_decode_output", p["dec_out"].ptr, p["dec_out"].ld, dec.weight.data_ptr(), dec.bias.data_ptr(), eps.data_ptr(),
+             B, X, Y, Z, m.dim, m.out_features, self.dt, s)
+        return eps
+
+    @staticmethod
+    def to_ncdhw(v: View) -> torch.Tensor:
+        """Interior of a halo-grid view as an fp32 NCDHW tensor (debug / tests)."""
+        t = v.t[:, 1:-1, 1:-1, 1:-1, v.c0 : v.c0 + v.C]
+        return t.permute(0, 4, 1, 2, 3).float().contiguous()

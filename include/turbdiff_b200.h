@@ -1,0 +1,188 @@
+/*
+ * turbdiff_b200.h - C ABI of libturbdiff_b200.so, the sm_100a kernel library behind the
+ * TurbDiff denoising hot path (3-D U-Net denoiser forward/backward + DDPM ancestral
+ * sampling).  Reference = martenlienen/generative-turbulence; citations are
+ * `turbdiff/...py:line` in that repository.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer borrowed for the
+ *     duration of the stream-ordered call; nothing is allocated or synchronised inside
+ *     (all entry points are CUDA-graph capturable);
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value: 0 = ok, >0 = cudaError_t of the failed launch, <0 = TDB_E_* argument
+ *     error.  tdb_last_error() returns a static message for the calling thread;
+ *   - `dtype`: TDB_F32 (0) or TDB_BF16 (1) = storage type of *activation* buffers.
+ *     Parameters (weights, biases, norm scales, FiLM) are always fp32 unless noted;
+ *   - activation layout ("halo grid"): channels-last with a materialised one-voxel
+ *     replicate halo, [B][X+2][Y+2][Z+2][ld] elements, channel c of voxel (b,x,y,z) at
+ *       (((b*(X+2) + x+1)*(Y+2) + y+1)*(Z+2) + z+1)*ld + c
+ *     `ld` (>= C) is the channel pitch in elements, so a tensor can be a channel slice of
+ *     a wider buffer (skip concatenation without a copy).  X,Y,Z are the *unhaloed* dims of
+ *     that U-Net level (194x50x50 at level 0 of the shapes config);
+ *   - module-boundary tensors (x_t, eps, noise ...) are the reference's: NCDHW fp32
+ *     contiguous (B,F,X,Y,Z).
+ */
+#ifndef TURBDIFF_B200_H
+#define TURBDIFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TDB_API __attribute__((visibility("default")))
+#else
+#define TDB_API
+#endif
+
+#define TDB_F32 0
+#define TDB_BF16 1
+
+#define TDB_E_BADARG (-1)      /* inconsistent sizes / null pointer */
+#define TDB_E_UNSUPPORTED (-2) /* shape not supported by this kernel (e.g. channel multiple) */
+#define TDB_E_NODEVICE (-3)    /* no sm_100 device / driver entry point missing */
+
+/* pointwise flags (tdb_pointwise) */
+#define TDB_PW_SILU 1u   /* apply x*sigmoid(x) after the affine part */
+#define TDB_PW_NOHALO 2u /* write interior voxels only */
+
+/* ddpm step flags (tdb_ddpm_step) */
+#define TDB_STEP_NOISE_BCS 1u /* GaussianDiffusion(noise_bcs=True)  */
+#define TDB_STEP_CLIP 2u      /* clip_denoised: clamp x0 to [-1,1]  */
+#define TDB_STEP_FINAL 4u     /* after the update also pin non-inside voxels to x_bcs (ddpm.py:814) */
+
+TDB_API const char* tdb_last_error(void);
+TDB_API int tdb_version(void);
+/* number of kernel launches issued through this library by the calling process */
+TDB_API int64_t tdb_launch_count(void);
+
+/* ---- input / output stages -------------------------------------------------------- */
+
+/* encode_x / encode_c_local 1x1x1 convs + channel concat, written into a halo grid
+ * (ddpm.py:433,436,495-501).  x: (B,F,X,Y,Z) fp32; c_local: (Fc,X,Y,Z) fp32, unbatched, may
+ * be NULL when Fc == 0.  wx: (dim,F), wc: (dim,Fc) fp32.  out channels: [0,dim) = encode_x,
+ * [dim,2dim) = encode_c_local.  parts: bit0 write the x half, bit1 write the c half. */
+TDB_API int tdb_encode_input(const float* x, const float* c_local, const float* wx, const float* bx,
+                     const float* wc, const float* bc, void* out, int ld_out, int B, int F, int Fc,
+                     int dim, int X, int Y, int Z, int parts, int dtype, void* stream);
+
+/* decode[1]: 1x1x1 conv dim -> F on a halo grid, written as NCDHW fp32 (ddpm.py:459,505). */
+TDB_API int tdb_decode_output(const void* act, int ld, const float* w, const float* b, float* out, int B,
+                      int X, int Y, int Z, int dim, int F, int dtype, void* stream);
+
+/* ---- convolution --------------------------------------------------------------------- */
+
+/* 3x3x3 replicate-padded conv (ntaps=27) or 1x1x1 conv (ntaps=1) over a halo grid
+ * (ddpm.py:164,188; nn.Conv3d(padding_mode="replicate") == valid conv over the halo).
+ * fp32 CUDA-core path: exact fp32 FMA accumulation (the 1e-5 parity path).
+ * w: packed [ntaps][Cin][Cout] fp32 (tap = (kx*3+ky)*3+kz).  bias may be NULL.
+ * out is a halo grid whose halo rows hold unspecified values. Cin % 8 == 0, Cout % 4 == 0. */
+TDB_API int tdb_conv3d_f32(const float* in, int ld_in, const float* w, const float* bias, float* out,
+                   int ld_out, int B, int X, int Y, int Z, int Cin, int Cout, int ntaps,
+                   void* stream);
+
+/* bf16 tensor-core path: implicit GEMM on tcgen05 with TMEM accumulators and TMA-staged
+ * operand tiles; fp32 accumulation.  w: packed [Cout][ntaps*Cin] bf16 (k = tap*Cin + ci).
+ * Cin % 16 == 0, Cout % 16 == 0, ld_in % 8 == 0, ld_out % 8 == 0.
+ * gn_stats (nullable): double [B][G][2] (sum, sum of squares) accumulated from the fp32
+ * accumulators over interior voxels, G groups of Cout/G channels. */
+TDB_API int tdb_conv3d_bf16(const void* in, int ld_in, const void* w, const float* bias, void* out,
+                    int ld_out, int B, int X, int Y, int Z, int Cin, int Cout, int ntaps,
+                    double* gn_stats, int G, void* stream);
+
+/* ---- normalisation / pointwise --------------------------------------------------------- */
+
+/* GroupNorm statistics over the interior voxels of a halo grid (ddpm.py:165,170,472):
+ * stats[b][g] = (sum, sum of squares) in double, ACCUMULATED into a pre-zeroed buffer. */
+TDB_API int tdb_gn_stats(const void* raw, int ld, double* stats, int B, int X, int Y, int Z, int C, int G,
+                 int dtype, void* stream);
+
+/* Fused GroupNorm-apply + FiLM + SiLU + residual + halo materialisation
+ * (ddpm.py:170-176,197,48): for every voxel p of the OUTPUT halo grid (halo voxels read
+ * their clamped interior source):
+ *     v = raw[src][c]
+ *     if stats: v = (v - mean)*rstd*gamma[c] + beta[c]          (eps, biased variance)
+ *     if film:  v = film[b][C + c] + (film[b][c] + 1) * v        (scale first, shift second)
+ *     if flags & TDB_PW_SILU: v = v * sigmoid(v)
+ *     if res:   v += res[src][c]
+ *     out[p][c] = v
+ * stats: double [B][G][2] from tdb_gn_stats; film: fp32 [B][film_ld] with this block's
+ * (scale|shift) at film[b][0..2C). */
+TDB_API int tdb_pointwise(const void* raw, int ld_raw, const double* stats, const float* gamma,
+                  const float* beta, const float* film, int film_ld, const void* res, int ld_res,
+                  void* out, int ld_out, int B, int X, int Y, int Z, int C, int G, float eps,
+                  unsigned flags, int dtype, void* stream);
+
+/* Trilinear resampling, align_corners=True, halo grid -> halo grid incl. halo
+ * (ddpm.py:358-361,367-369): src = i*(n_in-1)/(n_out-1) per axis in fp32. */
+TDB_API int tdb_trilinear(const void* in, int ld_in, int Xi, int Yi, int Zi, void* out, int ld_out, int Xo,
+                  int Yo, int Zo, int B, int C, int dtype, void* stream);
+
+/* ---- bottleneck attention ---------------------------------------------------------------- */
+
+/* softmax(q k^T / sqrt(dh)) v per (sample, head) over the S = X*Y*Z interior voxels
+ * (ddpm.py:295-308, attention.py:9-15).  qkv: halo grid with 3*heads*dh channels ordered
+ * q|k|v, channel = head*dh + d.  out: halo grid, heads*dh channels (interior rows written). */
+TDB_API int tdb_attention(const void* qkv, int ld_qkv, void* out, int ld_out, int B, int X, int Y, int Z,
+                  int heads, int dh, int dtype, void* stream);
+
+/* ---- timestep conditioning ------------------------------------------------------------------ */
+
+/* Nyquist embedding -> process_c MLP -> all FiLM projections of the network in one call
+ * (ddpm.py:147-148,447-452,184,191).  t: int64 (B,).  emb_scale/emb_bias: (dim,).
+ * w1 (4dim,dim) b1 (4dim) w2 (dim,4dim) b2 (dim).  film_w: (film_rows, dim) = all
+ * project_onto_scale_shift weights stacked, film_b (film_rows).  Outputs: c (B,dim),
+ * film (B,film_rows). */
+TDB_API int tdb_time_film(const int64_t* t, const float* emb_scale, const float* emb_bias, const float* w1,
+                  const float* b1, const float* w2, const float* b2, const float* film_w,
+                  const float* film_b, float* c, float* film, int B, int dim, int film_rows,
+                  void* stream);
+
+/* ---- diffusion process ------------------------------------------------------------------------ */
+
+/* One ancestral sampling update, masked to inside cells, as a single bandwidth-bound
+ * kernel (ddpm.py:711-715,722-728,745-752,797-814).  All tensors (B,F,nvox) fp32 NCDHW.
+ *   coef: device table [T][8] fp32 rows = {sqrt_recip_acp, sqrt_recipm1_acp, post_coef1,
+ *         post_coef2, exp(0.5*log_betas), sqrt_acp, sqrt_one_minus_acp, 0}
+ *   t_ptr: device int32 holding the current step t (so a captured graph can be replayed)
+ *   mask: uint8 (nvox), 1 on inside cells (== where_cells' cell_idx set)
+ *   z: posterior noise; z_bc: boundary re-noising draw (NULL unless NOISE_BCS). At t==0 the
+ *   noise tensors are ignored (x <- mean). x_out may alias x_t. */
+TDB_API int tdb_ddpm_step(const float* x_t, const float* eps, const float* z, const float* z_bc,
+                  const float* x_bcs, const uint8_t* mask, const float* coef, const int32_t* t_ptr,
+                  float* x_out, int B, int F, int64_t nvox, unsigned flags, void* stream);
+
+/* q_sample with optional inside-cell masking (ddpm.py:818-822,837-838):
+ * out = sqrt_acp[t_b]*x0 + sqrt(1-acp)[t_b]*noise ; where mask==0 and !noise_bcs: out = x0.
+ * t: int64 (B,) device. coef as in tdb_ddpm_step. */
+TDB_API int tdb_q_sample(const float* x0, const float* noise, const int64_t* t, const float* coef,
+                 const uint8_t* mask, float* out, int B, int F, int64_t nvox, int noise_bcs,
+                 void* stream);
+
+/* Masked training loss and its gradient (ddpm.py:845-852):
+ * loss = mean_b mean_{f, inside} |eps-noise|^p  (p=2: l2, p=1: l1), accumulated in double into
+ * loss_acc[0] (pre-zeroed); grad (nullable) = dloss/deps, zero outside the mask.
+ * n_inside = number of inside cells. */
+TDB_API int tdb_masked_loss(const float* eps, const float* noise, const uint8_t* mask, double* loss_acc,
+                    float* grad, int B, int F, int64_t nvox, int64_t n_inside, int l1, void* stream);
+
+/* ---- cell indexing (bit-exact) -------------------------------------------------------------------- */
+
+/* out = mask ? a : other (other NULL -> 0): models/utils.py:22-28 where_cells. (R, nvox) rows. */
+TDB_API int tdb_where_cells(const float* a, const float* other, const uint8_t* mask, float* out, int64_t rows,
+                    int64_t nvox, void* stream);
+/* out[r][j] = x[r][cell_idx[j]]: models/utils.py:14-15 select_cells. */
+TDB_API int tdb_select_cells(const float* x, const int64_t* cell_idx, float* out, int64_t rows, int64_t nvox,
+                     int64_t n_cells, void* stream);
+/* grid[b][f][cell_idx[j]] = samples[b][j][f] on a pre-zeroed grid: data/ofles.py:220-232. */
+TDB_API int tdb_scatter_cells(const float* samples, const int64_t* cell_idx, float* grid, int B, int F,
+                      int64_t nvox, int64_t n_cells, void* stream);
+/* mask[cell_idx[j]] = 1 on a pre-zeroed mask. */
+TDB_API int tdb_build_mask(const int64_t* cell_idx, uint8_t* mask, int64_t n_cells, int64_t nvox, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TURBDIFF_B200_H */

@@ -1,0 +1,327 @@
+"""Per-kernel parity on a B200: every C-ABI entry point against the CPU oracle on identical
+inputs.  Tolerances: fp32 path rel-L2 <= 1e-5; bf16 path <= 2e-2 (BASELINE.json north_star);
+integer / indexing / update-arithmetic kernels bit-exact."""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import from_halo, halo_is_replicated, rel_l2, to_halo
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-5, "bf16": 2e-2}
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from turbdiff_b200 import _lib
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    _lib.load()
+    return _lib
+
+
+def _dt(prec):
+    return (0, torch.float32) if prec == "fp32" else (1, torch.bfloat16)
+
+
+def gen(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+# --------------------------------------------------------------------------- convolution
+CONV_CASES = [
+    # B, X, Y, Z, Cin, Cout, ntaps
+    (2, 9, 7, 6, 16, 16, 27),
+    (1, 17, 9, 9, 32, 64, 27),
+    (2, 12, 6, 5, 64, 64, 27),
+    (1, 8, 6, 6, 128, 32, 27),
+    (1, 6, 3, 3, 256, 512, 27),
+    (2, 10, 6, 6, 64, 128, 1),
+    (1, 12, 3, 3, 512, 384, 1),
+    (1, 34, 18, 18, 64, 64, 27),
+]
+
+
+def _conv_ref(x, w, b, ntaps):
+    if ntaps == 27:
+        return F.conv3d(F.pad(x, (1,) * 6, mode="replicate"), w, b)
+    return F.conv3d(x, w, b)
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv3d_f32(lib, case):
+    B, X, Y, Z, Cin, Cout, ntaps = case
+    k = 3 if ntaps == 27 else 1
+    x = gen(B, Cin, X, Y, Z, seed=1)
+    w = gen(Cout, Cin, k, k, k, seed=2, scale=1 / math.sqrt(Cin * ntaps))
+    b = gen(Cout, seed=3, scale=0.1)
+    xin = to_halo(x, ld=Cin + 8, c0=8)  # exercise a channel-slice view
+    wp = w.permute(2, 3, 4, 1, 0).reshape(ntaps, Cin, Cout).contiguous()
+    out = torch.zeros((B, X + 2, Y + 2, Z + 2, Cout), device="cuda")
+    lib.call("tdb_conv3d_f32", xin.data_ptr() + 8 * 4, Cin + 8, wp.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z,
+             Cin, Cout, ntaps, lib.stream_ptr())
+    want = _conv_ref(x.double().cpu(), w.double().cpu(), b.double().cpu(), ntaps)
+    assert rel_l2(from_halo(out), want) < 1e-5
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("fused_stats", [False, True])
+def test_conv3d_bf16_tensor_core(lib, case, fused_stats):
+    B, X, Y, Z, Cin, Cout, ntaps = case
+    k = 3 if ntaps == 27 else 1
+    x = gen(B, Cin, X, Y, Z, seed=1).bfloat16().float()
+    w = gen(Cout, Cin, k, k, k, seed=2, scale=1 / math.sqrt(Cin * ntaps)).bfloat16().float()
+    b = gen(Cout, seed=3, scale=0.1)
+    xin = to_halo(x, dtype=torch.bfloat16)
+    wp = w.permute(0, 2, 3, 4, 1).reshape(Cout, ntaps * Cin).contiguous().bfloat16()
+    out = torch.zeros((B, X + 2, Y + 2, Z + 2, Cout), device="cuda", dtype=torch.bfloat16)
+    G = 8
+    stats = torch.zeros((B, G, 2), dtype=torch.float64, device="cuda")
+    lib.call("tdb_conv3d_bf16", xin.data_ptr(), Cin, wp.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
+             ntaps, stats.data_ptr() if fused_stats else None, G, lib.stream_ptr())
+    torch.cuda.synchronize()
+    want = _conv_ref(x.double().cpu(), w.double().cpu(), b.double().cpu(), ntaps)
+    # inputs are exactly representable in bf16, accumulation is fp32: only the bf16 output rounding remains
+    assert rel_l2(from_halo(out), want) < 4e-3
+    if fused_stats:
+        wg = want.reshape(B, G, -1)
+        np.testing.assert_allclose(stats[..., 0].cpu().numpy(), wg.sum(-1).numpy(), rtol=1e-4, atol=1e-2)
+        np.testing.assert_allclose(stats[..., 1].cpu().numpy(), (wg**2).sum(-1).numpy(), rtol=1e-4)
+
+
+# --------------------------------------------------------------------------- GroupNorm / pointwise
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("C,G", [(64, 8), (16, 8), (32, 1), (16, 16), (512, 8)])
+def test_gn_stats_and_pointwise(lib, prec, C, G):
+    code, td = _dt(prec)
+    B, X, Y, Z = 2, 7, 5, 6
+    x = (gen(B, C, X, Y, Z, seed=4) * 1.5 + 0.3).to(td).float()
+    res = gen(B, C, X, Y, Z, seed=5).to(td).float()
+    gamma, beta = gen(C, seed=6) * 0.2 + 1, gen(C, seed=7) * 0.1
+    film = gen(B, 2 * C + 6, seed=8) * 0.3
+    raw = to_halo(x, dtype=td)
+    raw[:, 0] = 77.0  # halo rows of a conv output are garbage: must never be read
+    resg = to_halo(res, dtype=td)
+    stats = torch.zeros((B, G, 2), dtype=torch.float64, device="cuda")
+    lib.call("tdb_gn_stats", raw.data_ptr(), C, stats.data_ptr(), B, X, Y, Z, C, G, code, lib.stream_ptr())
+    xg = x.double().cpu().reshape(B, G, -1)
+    np.testing.assert_allclose(stats[..., 0].cpu().numpy(), xg.sum(-1).numpy(), rtol=1e-6, atol=1e-4)
+    np.testing.assert_allclose(stats[..., 1].cpu().numpy(), (xg**2).sum(-1).numpy(), rtol=1e-6)
+
+    out = torch.zeros((B, X + 2, Y + 2, Z + 2, C), device="cuda", dtype=td)
+    lib.call("tdb_pointwise", raw.data_ptr(), C, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), film.data_ptr() + 4 * 3,
+             2 * C + 6, resg.data_ptr(), C, out.data_ptr(), C, B, X, Y, Z, C, G, 1e-5, lib.PW_SILU, code, lib.stream_ptr())
+    xd = x.double().cpu()
+    h = F.group_norm(xd, G, gamma.double().cpu(), beta.double().cpu(), eps=1e-5)
+    fl = film.double().cpu()[:, 3 : 3 + 2 * C]
+    h = fl[:, C:, None, None, None] + (fl[:, :C, None, None, None] + 1) * h
+    want = F.silu(h) + res.double().cpu()
+    assert rel_l2(from_halo(out), want) < (2e-6 if prec == "fp32" else 6e-3)
+    assert halo_is_replicated(out)
+
+    # plain residual add without norm / activation, interior only
+    out2 = torch.full_like(out, 5.0)
+    lib.call("tdb_pointwise", raw.data_ptr(), C, None, None, None, None, 0, resg.data_ptr(), C, out2.data_ptr(), C, B, X, Y, Z, C,
+             1, 1e-5, lib.PW_NOHALO, code, lib.stream_ptr())
+    assert rel_l2(from_halo(out2), xd + res.double().cpu()) < (1e-6 if prec == "fp32" else 6e-3)
+    assert float(out2[:, 0].float().min()) == 5.0
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("sizes", [((11, 7, 5), (5, 3, 3)), ((5, 3, 3), (11, 7, 5)), ((12, 3, 3), (24, 6, 6)), ((6, 6, 6), (6, 6, 6))])
+def test_trilinear(lib, prec, sizes):
+    code, td = _dt(prec)
+    (Xi, Yi, Zi), (Xo, Yo, Zo) = sizes
+    B, C = 2, 16
+    x = gen(B, C, Xi, Yi, Zi, seed=9).to(td).float()
+    xin = to_halo(x, dtype=td)
+    out = torch.zeros((B, Xo + 2, Yo + 2, Zo + 2, 2 * C), device="cuda", dtype=td)
+    lib.call("tdb_trilinear", xin.data_ptr(), C, Xi, Yi, Zi, out.data_ptr() + C * out.element_size(), 2 * C, Xo, Yo, Zo, B, C, code,
+             lib.stream_ptr())
+    want = F.interpolate(x.double().cpu(), size=(Xo, Yo, Zo), mode="trilinear", align_corners=True)
+    assert rel_l2(from_halo(out, C, C), want) < (2e-6 if prec == "fp32" else 5e-3)
+    assert float(out[..., :C].float().abs().max()) == 0.0  # the other half of the concat buffer is untouched
+    assert halo_is_replicated(out[..., C:].contiguous())
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("spatial", [(12, 3, 3), (8, 4, 4), (4, 2, 2)])
+def test_attention(lib, prec, spatial):
+    code, td = _dt(prec)
+    X, Y, Z = spatial
+    B, heads, dh = 2, 4, 32
+    hid = heads * dh
+    qkv = gen(B, 3 * hid, X, Y, Z, seed=10).to(td).float()
+    qg = to_halo(qkv, dtype=td)
+    out = torch.zeros((B, X + 2, Y + 2, Z + 2, hid), device="cuda", dtype=td)
+    lib.call("tdb_attention", qg.data_ptr(), 3 * hid, out.data_ptr(), hid, B, X, Y, Z, heads, dh, code, lib.stream_ptr())
+    S = X * Y * Z
+    q, k, v = (qkv.double().cpu()[:, i * hid : (i + 1) * hid].reshape(B, heads, dh, S).transpose(2, 3) for i in range(3))
+    want = F.scaled_dot_product_attention(q, k, v).transpose(2, 3).reshape(B, hid, X, Y, Z)
+    assert rel_l2(from_halo(out), want) < (2e-6 if prec == "fp32" else 5e-3)
+
+
+def test_time_film(lib):
+    from oracle.unet_ref import UNetSpec, process_time, synth_state_dict
+
+    spec = UNetSpec(dim=32, u_net_levels=1, timesteps=500)
+    sd = synth_state_dict(spec, 5)
+    t = torch.tensor([0, 1, 250, 499], dtype=torch.int64)
+    c_ref = process_time(t, sd, spec, torch.float32)
+    fw = torch.randn(96, 32, generator=torch.Generator().manual_seed(1)) * 0.2
+    fb = torch.randn(96, generator=torch.Generator().manual_seed(2)) * 0.1
+    film_ref = F.linear(c_ref, fw, fb)
+    from turbdiff_b200.models.ddpm import NyquistFrequencyEmbedding
+
+    emb = NyquistFrequencyEmbedding(32, 500).cuda()
+    d = {k: v.cuda() for k, v in sd.items()}
+    c = torch.zeros(4, 32, device="cuda")
+    film = torch.zeros(4, 96, device="cuda")
+    fwc, fbc, tc = fw.cuda(), fb.cuda(), t.cuda()
+    lib.call("tdb_time_film", tc.data_ptr(), emb.scale.data_ptr(), emb.bias.data_ptr(), d["process_c.0.weight"].data_ptr(),
+             d["process_c.0.bias"].data_ptr(), d["process_c.2.weight"].data_ptr(), d["process_c.2.bias"].data_ptr(), fwc.data_ptr(),
+             fbc.data_ptr(), c.data_ptr(), film.data_ptr(), 4, 32, 96, lib.stream_ptr())
+    assert rel_l2(c, c_ref) < 1e-5
+    assert rel_l2(film, film_ref) < 1e-5
+
+
+# --------------------------------------------------------------------------- encode / decode
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_encode_decode(lib, prec):
+    code, td = _dt(prec)
+    B, Fx, Fc, dim, X, Y, Z = 2, 4, 4, 16, 9, 6, 5
+    x, cl = gen(B, Fx, X, Y, Z, seed=11), gen(Fc, X, Y, Z, seed=12)
+    wx, bx, wc, bc = gen(dim, Fx, seed=13), gen(dim, seed=14), gen(dim, Fc, seed=15), gen(dim, seed=16)
+    out = torch.zeros((B, X + 2, Y + 2, Z + 2, 2 * dim), device="cuda", dtype=td)
+    lib.call("tdb_encode_input", x.data_ptr(), cl.data_ptr(), wx.data_ptr(), bx.data_ptr(), wc.data_ptr(), bc.data_ptr(),
+             out.data_ptr(), 2 * dim, B, Fx, Fc, dim, X, Y, Z, 3, code, lib.stream_ptr())
+    ex = F.conv3d(x.double().cpu(), wx.double().cpu()[:, :, None, None, None], bx.double().cpu())
+    ec = F.conv3d(cl.double().cpu()[None], wc.double().cpu()[:, :, None, None, None], bc.double().cpu()).expand(B, -1, -1, -1, -1)
+    tol = 2e-6 if prec == "fp32" else 5e-3
+    assert rel_l2(from_halo(out), torch.cat((ex, ec), 1)) < tol
+    assert halo_is_replicated(out)
+
+    wd, bd = gen(Fx, 2 * dim, seed=17), gen(Fx, seed=18)
+    y = torch.zeros((B, Fx, X, Y, Z), device="cuda")
+    lib.call("tdb_decode_output", out.data_ptr(), 2 * dim, wd.data_ptr(), bd.data_ptr(), y.data_ptr(), B, X, Y, Z, 2 * dim, Fx, code,
+             lib.stream_ptr())
+    want = F.conv3d(from_halo(out).double().cpu(), wd.double().cpu()[:, :, None, None, None], bd.double().cpu())
+    assert rel_l2(y, want) < 2e-6
+
+
+# --------------------------------------------------------------------------- diffusion kernels (bit-exact)
+def _coef(T=10, name="log-snr-linear"):
+    from oracle.diffusion_ref import diffusion_buffers
+
+    b = diffusion_buffers(name, T)
+    tab = torch.stack((b["sqrt_recip_alphas_cumprod"], b["sqrt_recipm1_alphas_cumprod"], b["posterior_mean_coef1"],
+                       b["posterior_mean_coef2"], (b["log_betas"] / 2).exp(), b["sqrt_alphas_cumprod"],
+                       b["sqrt_one_minus_alphas_cumprod"], torch.zeros(T)), dim=1).contiguous()
+    return b, tab
+
+
+@pytest.mark.parametrize("noise_bcs", [True, False])
+@pytest.mark.parametrize("clip", [False, True])
+@pytest.mark.parametrize("nvox", [7 * 5 * 4, 6 * 5 * 3 + 1])
+def test_ddpm_step_bit_exact(lib, noise_bcs, clip, nvox):
+    from oracle.diffusion_ref import DiffusionRef
+
+    B, Fx, T = 2, 4, 10
+    shape = (B, Fx, nvox, 1, 1)
+    g = torch.Generator().manual_seed(3)
+    x_t, eps, z, zbc, xb = (torch.randn(shape, generator=g) for _ in range(5))
+    idx = torch.randperm(nvox, generator=g)[: nvox * 2 // 3]
+    mask = torch.zeros(nvox, dtype=torch.uint8)
+    mask[idx] = 1
+    b, tab = _coef(T)
+    d = DiffusionRef(None, timesteps=T, beta_schedule="log-snr-linear", noise_bcs=noise_bcs, clip_denoised=clip)
+    from oracle.diffusion_ref import where_cells
+
+    for t in (7, 1, 0):
+        tt = torch.full((B,), t, dtype=torch.long)
+        x0 = d.predict_start(x_t, tt, eps)
+        if not noise_bcs:
+            x0 = where_cells(idx, x0, x_t)
+        if clip:
+            x0 = x0.clamp(-1, 1)
+        mean = d.posterior_mean(x0, x_t, tt)
+        if t == 0:
+            want = mean
+        else:
+            zz = z if noise_bcs else where_cells(idx, z)
+            want = mean + (b["log_betas"][t] / 2).exp() * zz
+            if noise_bcs:
+                want = where_cells(idx, want, d.q_sample(xb, tt, zbc))
+        for final in (False, True):
+            w2 = where_cells(idx, want, xb) if final else want
+            flags = (lib.STEP_NOISE_BCS if noise_bcs else 0) | (lib.STEP_CLIP if clip else 0) | (lib.STEP_FINAL if final else 0)
+            dx, de, dz, dzb, dxb, dm, dtab = (v.cuda().contiguous() for v in (x_t, eps, z, zbc, xb, mask, tab))
+            t_dev = torch.tensor([t], dtype=torch.int32, device="cuda")
+            out = torch.empty_like(dx)
+            lib.call("tdb_ddpm_step", dx.data_ptr(), de.data_ptr(), dz.data_ptr(), dzb.data_ptr(), dxb.data_ptr(), dm.data_ptr(),
+                     dtab.data_ptr(), t_dev.data_ptr(), out.data_ptr(), B, Fx, nvox, flags, lib.stream_ptr())
+            assert torch.equal(out.cpu(), w2), (t, final)
+
+
+def test_q_sample_loss_and_cells(lib):
+    from oracle.diffusion_ref import DiffusionRef, select_cells, where_cells
+
+    B, Fx, T, nvox = 3, 4, 10, 6 * 5 * 4
+    shape = (B, Fx, 6, 5, 4)
+    g = torch.Generator().manual_seed(5)
+    x0, noise, eps = (torch.randn(shape, generator=g) for _ in range(3))
+    idx = torch.randperm(nvox, generator=g)[:77]
+    t = torch.tensor([0, 4, 9])
+    _, tab = _coef(T)
+    d = DiffusionRef(None, timesteps=T, beta_schedule="log-snr-linear")
+    dm = torch.zeros(nvox, dtype=torch.uint8, device="cuda")
+    didx = idx.cuda()
+    lib.call("tdb_build_mask", didx.data_ptr(), dm.data_ptr(), idx.numel(), nvox, lib.stream_ptr())
+    want_mask = torch.zeros(nvox, dtype=torch.uint8)
+    want_mask[idx] = 1
+    assert torch.equal(dm.cpu(), want_mask)
+    dx0, dn, de, dtab, dt = x0.cuda(), noise.cuda(), eps.cuda(), tab.cuda(), t.cuda()
+    for noise_bcs in (1, 0):
+        out = torch.empty_like(dx0)
+        lib.call("tdb_q_sample", dx0.data_ptr(), dn.data_ptr(), dt.data_ptr(), dtab.data_ptr(), dm.data_ptr(), out.data_ptr(), B, Fx,
+                 nvox, noise_bcs, lib.stream_ptr())
+        want = d.q_sample(x0, t, noise)
+        if not noise_bcs:
+            want = where_cells(idx, want, x0)
+        assert torch.equal(out.cpu(), want)
+    # masked loss + grad
+    for l1 in (0, 1):
+        acc = torch.zeros(1, dtype=torch.float64, device="cuda")
+        grad = torch.empty_like(de)
+        lib.call("tdb_masked_loss", de.data_ptr(), dn.data_ptr(), dm.data_ptr(), acc.data_ptr(), grad.data_ptr(), B, Fx, nvox,
+                 idx.numel(), l1, lib.stream_ptr())
+        e = eps.double().requires_grad_()
+        per = (e - noise.double()).abs() if l1 else (e - noise.double()) ** 2
+        loss = per.flatten(-3)[..., idx].reshape(B, -1).mean(1).mean()
+        loss.backward()
+        np.testing.assert_allclose(acc.item(), loss.item(), rtol=1e-6)
+        assert rel_l2(grad, e.grad) < 1e-6
+    # where / select / scatter
+    other = torch.randn(shape, generator=g)
+    out = torch.empty_like(dx0)
+    lib.call("tdb_where_cells", dx0.data_ptr(), other.cuda().data_ptr(), dm.data_ptr(), out.data_ptr(), B * Fx, nvox, lib.stream_ptr())
+    assert torch.equal(out.cpu(), where_cells(idx, x0, other))
+    lib.call("tdb_where_cells", dx0.data_ptr(), None, dm.data_ptr(), out.data_ptr(), B * Fx, nvox, lib.stream_ptr())
+    assert torch.equal(out.cpu(), where_cells(idx, x0))
+    sel = torch.empty((B, Fx, idx.numel()), device="cuda")
+    lib.call("tdb_select_cells", dx0.data_ptr(), didx.data_ptr(), sel.data_ptr(), B * Fx, nvox, idx.numel(), lib.stream_ptr())
+    assert torch.equal(sel.cpu(), select_cells(x0, idx))
+    samples = torch.randn(B, idx.numel(), Fx, generator=g)
+    grid = torch.zeros((B, Fx, nvox), device="cuda")
+    lib.call("tdb_scatter_cells", samples.cuda().data_ptr(), didx.data_ptr(), grid.data_ptr(), B, Fx, nvox, idx.numel(), lib.stream_ptr())
+    want = torch.zeros(B, Fx, nvox)
+    want[:, :, idx] = samples.transpose(1, 2)
+    assert torch.equal(grid.cpu(), want)
+    # empty index set
+    lib.call("tdb_select_cells", dx0.data_ptr(), didx.data_ptr(), sel.data_ptr(), B * Fx, nvox, 0, lib.stream_ptr())

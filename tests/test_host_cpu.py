@@ -1,0 +1,119 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every symbol
+declared in include/turbdiff_b200.h, the module tree honours the reference's checkpoint contract,
+the schedule buffers equal the reference's bit for bit, and the launch program is well formed.
+No kernel is executed here (there is no GPU in the build container and no CPU fallback)."""
+
+import ctypes
+import json
+import re
+from collections import Counter
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    import __graft_entry__ as ge
+
+    ge.build()
+    from turbdiff_b200 import _lib
+
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    header = (ROOT / "include" / "turbdiff_b200.h").read_text()
+    declared = set(re.findall(r"\b(tdb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 19
+    lib = ctypes.CDLL(str(built_lib.LIB_PATH))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    bound = set(built_lib.SIGNATURES) | set(built_lib.OTHER)
+    assert declared == bound, declared ^ bound
+    assert built_lib.load().tdb_version() >= 100
+    assert built_lib.load().tdb_last_error() is not None
+
+
+def test_argument_errors_are_reported_without_a_gpu(built_lib):
+    lib = built_lib.load()
+    rc = lib.tdb_conv3d_f32(None, 8, None, None, None, 8, 1, 4, 4, 4, 8, 8, 27, None)
+    assert rc == -1
+    assert b"null pointer" in lib.tdb_last_error()
+    with pytest.raises(RuntimeError, match="null pointer"):
+        built_lib.call("tdb_gn_stats", None, 8, None, 1, 4, 4, 4, 8, 8, 0, None)
+
+
+def test_no_cpu_path(built_lib):
+    from turbdiff_b200 import DenoisingModel
+    from turbdiff_b200.models.conditioning import Conditioning
+
+    m = DenoisingModel(in_features=4, out_features=4, c_local_features=4, c_global_features=0, timesteps=10, dim=8, u_net_levels=2,
+                       norm_type="group")
+    with pytest.raises(RuntimeError, match="CUDA"), torch.no_grad():
+        m(torch.zeros(1, 4, 16, 8, 8), torch.zeros(1, dtype=torch.long), {Conditioning.Type.CELL_TYPE: torch.zeros(4, 16, 8, 8)})
+
+
+def test_checkpoint_contract(built_lib):
+    from turbdiff_b200 import DenoisingModel, GaussianDiffusion
+
+    ref = json.loads((GOLDEN / "state_dict_layout_shapes.json").read_text())
+    with torch.device("meta"):
+        m = DenoisingModel(in_features=4, out_features=4, c_local_features=4, c_global_features=0, timesteps=500, dim=32, u_net_levels=4,
+                           norm_type="group")
+    assert [[k, list(v.shape)] for k, v in m.state_dict().items()] == ref
+    gd = GaussianDiffusion(m, timesteps=10)
+    assert all(k.startswith("model.") for k in gd.state_dict())  # schedule buffers are non-persistent
+    with pytest.raises(RuntimeError, match="Unknown norm type"):
+        DenoisingModel(in_features=4, out_features=4, c_local_features=4, c_global_features=0, timesteps=10, dim=8, u_net_levels=1,
+                       norm_type="batch")
+    with pytest.raises(ValueError, match="unknown beta schedule"):
+        GaussianDiffusion(m, beta_schedule="nope")
+
+
+@pytest.mark.parametrize("name", ["linear", "log-linear", "log-snr-linear", "cosine", "sigmoid"])
+@pytest.mark.parametrize("T", [10, 500, 1000])
+def test_schedule_buffers_equal_reference(built_lib, name, T):
+    from turbdiff_b200 import GaussianDiffusion
+
+    g = np.load(GOLDEN / "schedules.npz")
+    gd = GaussianDiffusion(torch.nn.Identity(), timesteps=T, beta_schedule=name)
+    bufs = dict(gd.named_buffers())
+    assert len(bufs) == 10
+    for b, v in bufs.items():
+        np.testing.assert_array_equal(v.numpy(), g[f"{name}/{T}/{b}"], err_msg=b)
+        assert v.dtype == torch.float32
+
+
+def test_time_embedding_buffers(built_lib):
+    from turbdiff_b200.models.ddpm import NyquistFrequencyEmbedding
+
+    g = np.load(GOLDEN / "time_embedding.npz")
+    np.testing.assert_array_equal(NyquistFrequencyEmbedding(32, 500).scale.numpy(), g["32/500/scale"])
+
+
+def test_launch_program_is_well_formed(built_lib, monkeypatch):
+    """Dry run of the launch program with the kernel calls recorded instead of executed."""
+    from turbdiff_b200 import DenoisingModel, _lib, engine
+    from turbdiff_b200.models.conditioning import Conditioning
+
+    calls = []
+    monkeypatch.setattr(engine, "call", lambda name, *a: calls.append((name, a)))
+    monkeypatch.setattr(_lib, "stream_ptr", lambda: 0)
+    monkeypatch.setattr(_lib, "require_cuda", lambda t, w: None)
+    m = DenoisingModel(in_features=4, out_features=4, c_local_features=4, c_global_features=0, timesteps=500, dim=32, u_net_levels=4,
+                       norm_type="group", precision="bf16")
+    x = torch.zeros(1, 4, 26, 10, 10)
+    with torch.no_grad():
+        y = m(x, torch.zeros(1, dtype=torch.long), {Conditioning.Type.CELL_TYPE: torch.zeros(4, 26, 10, 10)})
+    assert y.shape == x.shape
+    n = Counter(c[0] for c in calls)
+    # 22 3x3x3 convs + 7 residual 1x1 + 2 attention 1x1; 22 block pointwise + 2 attention pointwise; 8 resamplings
+    assert n["tdb_conv3d_bf16"] == 31 and n["tdb_pointwise"] == 24 and n["tdb_trilinear"] == 8
+    assert n["tdb_attention"] == 1 and n["tdb_time_film"] == 1 and n["tdb_encode_input"] == 1 and n["tdb_decode_output"] == 1
+    # level sizes follow max(int(s/2), 3)
+    assert engine.level_sizes((194, 50, 50), 4) == [(194, 50, 50), (97, 25, 25), (48, 12, 12), (24, 6, 6), (12, 3, 3)]
