@@ -28,7 +28,8 @@ def sources() -> list[Path]:
 
 def _digest() -> str:
     h = hashlib.sha256()
-    for f in sorted(list(CSRC.glob("*")) + [HERE.parent / "include" / "turbdiff_b200.h", Path(__file__)]):
+    files = [f for f in CSRC.glob("*") if f.is_file()]
+    for f in sorted(files + [HERE.parent / "include" / "turbdiff_b200.h", Path(__file__)]):
         h.update(f.name.encode())
         h.update(f.read_bytes())
     return h.hexdigest()

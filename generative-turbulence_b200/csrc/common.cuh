@@ -50,6 +50,26 @@ struct Grid3 {
     }
 };
 
+// ---- division by a launch-time constant (32-bit, dividend < 2^31): one mul.hi + shift ---------
+struct FastDiv {
+    uint32_t d, m, s;
+    FastDiv() : d(1), m(0), s(0) {}
+    explicit FastDiv(uint32_t div) : d(div), m(0), s(0) {
+        if (div > 1) {
+            int l = 0;
+            while ((1u << l) < div) ++l;
+            const int p = 31 + l;
+            m = (uint32_t)((((uint64_t)1 << p) + div - 1) / div);
+            s = (uint32_t)(p - 32);
+        }
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : (__umulhi(n, m) >> s); }
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+        q = div(n);
+        r = n - q * d;
+    }
+};
+
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // ---- 16-byte channel vectors -------------------------------------------------------------------

@@ -16,12 +16,9 @@
 // elected lane), warps 2-5 = epilogue (TMEM lane group = warp % 4): tcgen05.ld -> +bias ->
 // optional GroupNorm partial moments (from the fp32 accumulators) -> bf16 -> global.
 // Two CTAs fit per SM for the narrow layers, so one CTA's epilogue overlaps the other's MMAs.
-#include <cuda.h>
-
-#include <mutex>
-
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tma_host.cuh"
 
 using namespace tdb;
 using bf16 = __nv_bfloat16;
@@ -210,41 +207,6 @@ conv3d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
 // ---- host side ---------------------------------------------------------------------------------
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    });
-    return fn;
-}
-
-// 2-D bf16 tensor map: dim0 (contiguous) = cols, dim1 = rows with pitch `pitch_elems`.
-bool make_map_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems,
-                 uint32_t box_cols, uint32_t box_rows) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return false;
-    cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {pitch_elems * 2};
-    cuuint32_t box[2] = {box_cols, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    const uint32_t row_bytes = box_cols * 2;
-    CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                             : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS;
-}
-
 int pick_bn(int cout) {
     for (int bn = 256; bn >= 16; bn -= 16)
         if (cout % bn == 0) return bn;
@@ -293,9 +255,9 @@ extern "C" int tdb_conv3d_bf16(const void* in, int ld_in, const void* w, const f
 
     CUtensorMap map_a, map_b;
     TDB_REQUIRE(encode_fn() != nullptr, TDB_E_NODEVICE, "tdb_conv3d_bf16: cuTensorMapEncodeTiled unavailable (no driver)");
-    TDB_REQUIRE(make_map_2d(&map_a, in, (uint64_t)Cin, (uint64_t)g.rows, (uint64_t)ld_in, (uint32_t)P.KC, BM), TDB_E_BADARG,
+    TDB_REQUIRE(make_map_2d_bf16(&map_a, in, (uint64_t)Cin, (uint64_t)g.rows, (uint64_t)ld_in, (uint32_t)P.KC, BM), TDB_E_BADARG,
                 "tdb_conv3d_bf16: tensor map (activations) rejected");
-    TDB_REQUIRE(make_map_2d(&map_b, w, (uint64_t)ntaps * Cin, (uint64_t)Cout, (uint64_t)ntaps * Cin, (uint32_t)P.KC,
+    TDB_REQUIRE(make_map_2d_bf16(&map_b, w, (uint64_t)ntaps * Cin, (uint64_t)Cout, (uint64_t)ntaps * Cin, (uint32_t)P.KC,
                             (uint32_t)P.BN),
                 TDB_E_BADARG, "tdb_conv3d_bf16: tensor map (weights) rejected");
 

@@ -11,34 +11,38 @@ namespace {
 
 constexpr int kThreads = 256;
 
-__device__ __forceinline__ void split_row(int64_t r, const Grid3& g, int& xp, int& yp, int& zp) {
-    zp = (int)(r % g.Zp);
-    r /= g.Zp;
-    yp = (int)(r % g.Yp);
-    xp = (int)(r / g.Yp);
-}
+// Row index -> haloed coordinates with launch-time fast dividers (Zp, Yp).
+struct RowSplit {
+    FastDiv by_z, by_y;
+    __device__ __forceinline__ void operator()(uint32_t r, int& xp, int& yp, int& zp) const {
+        uint32_t q, zz, xx, yy;
+        by_z.divmod(r, q, zz);
+        by_y.divmod(q, xx, yy);
+        xp = (int)xx; yp = (int)yy; zp = (int)zz;
+    }
+};
 
 // ---------------------------------------------------------------- encode_x / encode_c_local
+// grid = (blocks per sample, B); thread = one 16-byte channel vector of one haloed voxel.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 encode_input_kernel(const float* __restrict__ x, const float* __restrict__ c_local,
                     const float* __restrict__ wx, const float* __restrict__ bx,
                     const float* __restrict__ wc, const float* __restrict__ bc, T* __restrict__ out,
-                    int ld_out, Grid3 g, int F, int Fc, int dim, int parts) {
+                    int ld_out, Grid3 g, int F, int Fc, int dim, int parts, RowSplit split, FastDiv by_chunks) {
     constexpr int N = Vec<T>::N;
-    const int ctot = dim + (Fc > 0 ? dim : 0);
-    const int chunks = ctot / N;
-    const int64_t total = g.rows * chunks;
+    const int b = blockIdx.y;
+    const uint32_t chunks = by_chunks.d;
+    const uint32_t total = (uint32_t)g.vox_p * chunks;
     const int64_t nvox = (int64_t)g.X * g.Y * g.Z;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t p = idx / chunks;
-        const int c0 = (int)(idx % chunks) * N;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        uint32_t r, ch;
+        by_chunks.divmod(idx, r, ch);
+        const int c0 = (int)ch * N;
         const bool c_half = c0 >= dim;
         if (c_half ? !(parts & 2) : !(parts & 1)) continue;
-        const int b = (int)(p / g.vox_p);
         int xp, yp, zp;
-        split_row(p % g.vox_p, g, xp, yp, zp);
+        split(r, xp, yp, zp);
         const int xs = clampi(xp - 1, 0, g.X - 1), ys = clampi(yp - 1, 0, g.Y - 1), zs = clampi(zp - 1, 0, g.Z - 1);
         const int64_t v = ((int64_t)xs * g.Y + ys) * g.Z + zs;
         const int nf = c_half ? Fc : F;
@@ -52,10 +56,12 @@ encode_input_kernel(const float* __restrict__ x, const float* __restrict__ c_loc
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             float acc = __ldg(bias + i);
-            for (int f = 0; f < nf; ++f) acc = fmaf(__ldg(w + i * nf + f), in[f], acc);
+#pragma unroll
+            for (int f = 0; f < 8; ++f)
+                if (f < nf) acc = fmaf(__ldg(w + i * nf + f), in[f], acc);
             o[i] = acc;
         }
-        Vec<T>::store(out + p * ld_out + c0, o);
+        Vec<T>::store(out + ((int64_t)b * g.vox_p + r) * ld_out + c0, o);
     }
 }
 
@@ -165,7 +171,7 @@ pointwise_kernel(const T* __restrict__ raw, int ld_raw, const double* __restrict
                  const float* __restrict__ gamma, const float* __restrict__ beta,
                  const float* __restrict__ film, int film_ld, const T* __restrict__ res, int ld_res,
                  T* __restrict__ out, int ld_out, Grid3 g, int C, int G, float eps, unsigned flags,
-                 int rows_per_block) {
+                 int rows_per_block, RowSplit split, FastDiv by_chunks) {
     constexpr int N = Vec<T>::N;
     extern __shared__ float coef[];  // [C] scale, [C] offset
     const int b = blockIdx.y;
@@ -192,17 +198,19 @@ pointwise_kernel(const T* __restrict__ raw, int ld_raw, const double* __restrict
         coef[C + c] = o;
     }
     __syncthreads();
-    const int chunks = C / N;
+    const uint32_t chunks = by_chunks.d;
     const bool interior_only = flags & TDB_PW_NOHALO;
     const bool act = flags & TDB_PW_SILU;
-    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
-    const int64_t r_end = min(g.vox_p, r_begin + rows_per_block);
-    const int64_t total = (r_end - r_begin) * chunks;
-    for (int64_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int64_t r = r_begin + idx / chunks;
-        const int c0 = (int)(idx % chunks) * N;
+    const uint32_t r_begin = blockIdx.x * (uint32_t)rows_per_block;
+    const uint32_t r_end = min((uint32_t)g.vox_p, r_begin + (uint32_t)rows_per_block);
+    const uint32_t total = (r_end - r_begin) * chunks;
+    for (uint32_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        uint32_t rq, ch;
+        by_chunks.divmod(idx, rq, ch);
+        const uint32_t r = r_begin + rq;
+        const int c0 = (int)ch * N;
         int xp, yp, zp;
-        split_row(r, g, xp, yp, zp);
+        split(r, xp, yp, zp);
         const int xs = clampi(xp, 1, g.X), ys = clampi(yp, 1, g.Y), zs = clampi(zp, 1, g.Z);
         if (interior_only && (xs != xp || ys != yp || zs != zp)) continue;
         const int64_t src = (int64_t)b * g.vox_p + ((int64_t)xs * g.Yp + ys) * g.Zp + zs;
@@ -240,19 +248,21 @@ __device__ __forceinline__ Lerp axis_lerp(int o, int n_in, int n_out) {
     return r;
 }
 
+// grid = (blocks per sample, B)
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-trilinear_kernel(const T* __restrict__ in, int ld_in, Grid3 gi, T* __restrict__ out, int ld_out, Grid3 go, int C) {
+trilinear_kernel(const T* __restrict__ in, int ld_in, Grid3 gi, T* __restrict__ out, int ld_out, Grid3 go, int C,
+                 RowSplit split, FastDiv by_chunks) {
     constexpr int N = Vec<T>::N;
-    const int chunks = C / N;
-    const int64_t total = go.rows * chunks;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t p = idx / chunks;
-        const int c0 = (int)(idx % chunks) * N;
-        const int b = (int)(p / go.vox_p);
+    const int b = blockIdx.y;
+    const uint32_t chunks = by_chunks.d;
+    const uint32_t total = (uint32_t)go.vox_p * chunks;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        uint32_t r, ch;
+        by_chunks.divmod(idx, r, ch);
+        const int c0 = (int)ch * N;
         int xp, yp, zp;
-        split_row(p % go.vox_p, go, xp, yp, zp);
+        split(r, xp, yp, zp);
         const Lerp lx = axis_lerp(clampi(xp - 1, 0, go.X - 1), gi.X, go.X);
         const Lerp ly = axis_lerp(clampi(yp - 1, 0, go.Y - 1), gi.Y, go.Y);
         const Lerp lz = axis_lerp(clampi(zp - 1, 0, go.Z - 1), gi.Z, go.Z);
@@ -271,8 +281,23 @@ trilinear_kernel(const T* __restrict__ in, int ld_in, Grid3 gi, T* __restrict__ 
 #pragma unroll
             for (int i = 0; i < N; ++i) acc[i] = fmaf(w, v[i], acc[i]);
         }
-        Vec<T>::store(out + p * ld_out + c0, acc);
+        Vec<T>::store(out + ((int64_t)b * go.vox_p + r) * ld_out + c0, acc);
     }
+}
+
+RowSplit make_split(const Grid3& g) {
+    RowSplit s;
+    s.by_z = FastDiv((uint32_t)g.Zp);
+    s.by_y = FastDiv((uint32_t)g.Yp);
+    return s;
+}
+
+// blocks per sample so that the whole launch is ~16 resident waves of 148 SMs at most
+int blocks_per_sample(int64_t items_per_sample, int B) {
+    int64_t blocks = ceil_div(items_per_sample, kThreads);
+    int64_t cap = (148 * 16) / (B < 1 ? 1 : B);
+    if (cap < 8) cap = 8;
+    return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 
 int grid_for(int64_t work_items) {
@@ -298,12 +323,15 @@ int tdb_encode_input(const float* x, const float* c_local, const float* wx, cons
                 "tdb_encode_input: dim/ld_out must be multiples of %d and out 16B aligned", n);
     Grid3 g(B, X, Y, Z);
     const int ctot = dim + (Fc > 0 ? dim : 0);
-    const int blocks = grid_for(g.rows * (ctot / n));
+    TDB_REQUIRE(g.vox_p * (ctot / n) < (1ll << 31), TDB_E_UNSUPPORTED, "tdb_encode_input: grid too large for 32-bit indexing");
+    dim3 grid((unsigned)blocks_per_sample(g.vox_p * (ctot / n), B), (unsigned)B);
+    const RowSplit split = make_split(g);
+    const FastDiv by_chunks((uint32_t)(ctot / n));
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == TDB_BF16)
-        encode_input_kernel<bf16><<<blocks, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (bf16*)out, ld_out, g, F, Fc, dim, parts);
+        encode_input_kernel<bf16><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (bf16*)out, ld_out, g, F, Fc, dim, parts, split, by_chunks);
     else
-        encode_input_kernel<float><<<blocks, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (float*)out, ld_out, g, F, Fc, dim, parts);
+        encode_input_kernel<float><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (float*)out, ld_out, g, F, Fc, dim, parts, split, by_chunks);
     TDB_CHECK_LAUNCH("tdb_encode_input");
     return 0;
 }
@@ -360,21 +388,26 @@ int tdb_pointwise(const void* raw, int ld_raw, const double* stats, const float*
                 TDB_E_UNSUPPORTED, "tdb_pointwise: channel counts / pitches must be multiples of %d", n);
     if (G < 1) G = 1;
     Grid3 g(B, X, Y, Z);
-    // ~8 blocks per SM per sample-slab keeps the per-block coefficient prologue negligible
-    int64_t rows_per_block = ceil_div(g.vox_p, 148 * 8 / (B < 8 ? B : 8) + 1);
+    TDB_REQUIRE(g.vox_p * (C / n) < (1ll << 31), TDB_E_UNSUPPORTED, "tdb_pointwise: grid too large for 32-bit indexing");
+    // ~8 resident blocks per SM over the whole launch keeps the per-block coefficient prologue negligible
+    int64_t bps = (148 * 8) / B;
+    if (bps < 1) bps = 1;
+    int64_t rows_per_block = ceil_div(g.vox_p, bps);
     const int64_t min_rows = ceil_div(kThreads * 4, C / n);
     if (rows_per_block < min_rows) rows_per_block = min_rows;
+    const RowSplit split = make_split(g);
+    const FastDiv by_chunks((uint32_t)(C / n));
     dim3 grid((unsigned)ceil_div(g.vox_p, rows_per_block), (unsigned)B);
     const size_t smem = (size_t)2 * C * sizeof(float);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == TDB_BF16)
         pointwise_kernel<bf16><<<grid, kThreads, smem, s>>>((const bf16*)raw, ld_raw, stats, gamma, beta, film, film_ld,
                                                              (const bf16*)res, ld_res, (bf16*)out, ld_out, g, C, G, eps,
-                                                             flags, (int)rows_per_block);
+                                                             flags, (int)rows_per_block, split, by_chunks);
     else
         pointwise_kernel<float><<<grid, kThreads, smem, s>>>((const float*)raw, ld_raw, stats, gamma, beta, film, film_ld,
                                                               (const float*)res, ld_res, (float*)out, ld_out, g, C, G, eps,
-                                                              flags, (int)rows_per_block);
+                                                              flags, (int)rows_per_block, split, by_chunks);
     TDB_CHECK_LAUNCH("tdb_pointwise");
     return 0;
 }
@@ -386,12 +419,15 @@ int tdb_trilinear(const void* in, int ld_in, int Xi, int Yi, int Zi, void* out, 
     TDB_REQUIRE(C % n == 0 && ld_in % n == 0 && ld_out % n == 0 && aligned16(in) && aligned16(out),
                 TDB_E_UNSUPPORTED, "tdb_trilinear: channel counts / pitches must be multiples of %d", n);
     Grid3 gi(B, Xi, Yi, Zi), go(B, Xo, Yo, Zo);
-    const int blocks = grid_for(go.rows * (C / n));
+    TDB_REQUIRE(go.vox_p * (C / n) < (1ll << 31), TDB_E_UNSUPPORTED, "tdb_trilinear: grid too large for 32-bit indexing");
+    dim3 grid((unsigned)blocks_per_sample(go.vox_p * (C / n), B), (unsigned)B);
+    const RowSplit split = make_split(go);
+    const FastDiv by_chunks((uint32_t)(C / n));
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == TDB_BF16)
-        trilinear_kernel<bf16><<<blocks, kThreads, 0, s>>>((const bf16*)in, ld_in, gi, (bf16*)out, ld_out, go, C);
+        trilinear_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)in, ld_in, gi, (bf16*)out, ld_out, go, C, split, by_chunks);
     else
-        trilinear_kernel<float><<<blocks, kThreads, 0, s>>>((const float*)in, ld_in, gi, (float*)out, ld_out, go, C);
+        trilinear_kernel<float><<<grid, kThreads, 0, s>>>((const float*)in, ld_in, gi, (float*)out, ld_out, go, C, split, by_chunks);
     TDB_CHECK_LAUNCH("tdb_trilinear");
     return 0;
 }

@@ -72,6 +72,7 @@ class DenoiserEngine:
         self.dt = F32 if precision == "fp32" else BF16
         self.tdtype = torch.float32 if precision == "fp32" else torch.bfloat16
         self.fused_stats = precision == "bf16"
+        self.fold = True
         self._plans = {}
         self._wcache = None
         self._wversion = None
@@ -110,6 +111,9 @@ class DenoiserEngine:
             taps = wt.shape[2] * wt.shape[3] * wt.shape[4]
             if self.precision == "fp32":
                 return wt.permute(2, 3, 4, 1, 0).reshape(taps, cin, cout).contiguous().float()
+            if self.use_fold(taps, cout):
+                # kz folded into N: row = kz*Cout + co, col = (kx*3+ky)*Cin + ci
+                return wt.permute(4, 0, 2, 3, 1).reshape(3 * cout, 9 * cin).contiguous().to(torch.bfloat16)
             return wt.permute(0, 2, 3, 4, 1).reshape(cout, taps * cin).contiguous().to(torch.bfloat16)
 
         for name, bp in self.blocks.items():
@@ -120,10 +124,15 @@ class DenoiserEngine:
         att = m.u_net.center_block[1].fn.fn
         w["attn.qkv"] = pack(att.to_qkv)
         w["attn.out"] = pack(att.to_out)
-        w["film_w"] = torch.cat([self.blocks[n].blk.project_onto_scale_shift.weight.detach() for n in self.block_order]).contiguous().float()
+        # stacked over blocks and transposed to (dim, film_rows) for coalesced reads in tdb_time_film
+        w["film_w"] = torch.cat([self.blocks[n].blk.project_onto_scale_shift.weight.detach() for n in self.block_order]).t().contiguous().float()
         w["film_b"] = torch.cat([self.blocks[n].blk.project_onto_scale_shift.bias.detach() for n in self.block_order]).contiguous().float()
         self._wcache, self._wversion = w, ver
         return w
+
+    def use_fold(self, ntaps, cout) -> bool:
+        """Narrow 3x3x3 layers run the kz-folded persistent kernel (tdb_conv3d_bf16_fold)."""
+        return self.precision == "bf16" and self.fold and ntaps == 27 and 3 * cout <= 256
 
     # ------------------------------------------------------------------ workspace
     def plan(self, B, spatial, device):
@@ -198,6 +207,9 @@ class DenoiserEngine:
         s = _lib.stream_ptr()
         if self.precision == "fp32":
             call("tdb_conv3d_f32", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ntaps, s)
+        elif self.use_fold(ntaps, out.C):
+            call("tdb_conv3d_bf16_fold", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C,
+                 ptr(stats), G, s)
         else:
             call("tdb_conv3d_bf16", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ntaps,
                  ptr(stats), G, s)

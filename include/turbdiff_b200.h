@@ -92,6 +92,14 @@ TDB_API int tdb_conv3d_bf16(const void* in, int ld_in, const void* w, const floa
                     int ld_out, int B, int X, int Y, int Z, int Cin, int Cout, int ntaps,
                     double* gn_stats, int G, void* stream);
 
+/* Same convolution (3x3x3 only) for narrow layers, 3*Cout <= 256: the kz filter axis is folded
+ * into the GEMM N dimension (9 row-shifted A boxes instead of 27, 3x wider MMAs), persistent CTAs,
+ * double-buffered TMEM accumulators, weights resident in shared memory when they fit.
+ * w_fold: packed [3*Cout][9*Cin] bf16, row = kz*Cout + co, col = (kx*3+ky)*Cin + ci. */
+TDB_API int tdb_conv3d_bf16_fold(const void* in, int ld_in, const void* w_fold, const float* bias, void* out,
+                         int ld_out, int B, int X, int Y, int Z, int Cin, int Cout, double* gn_stats,
+                         int G, void* stream);
+
 /* ---- normalisation / pointwise --------------------------------------------------------- */
 
 /* GroupNorm statistics over the interior voxels of a halo grid (ddpm.py:165,170,472):
@@ -132,11 +140,11 @@ TDB_API int tdb_attention(const void* qkv, int ld_qkv, void* out, int ld_out, in
 
 /* Nyquist embedding -> process_c MLP -> all FiLM projections of the network in one call
  * (ddpm.py:147-148,447-452,184,191).  t: int64 (B,).  emb_scale/emb_bias: (dim,).
- * w1 (4dim,dim) b1 (4dim) w2 (dim,4dim) b2 (dim).  film_w: (film_rows, dim) = all
- * project_onto_scale_shift weights stacked, film_b (film_rows).  Outputs: c (B,dim),
- * film (B,film_rows). */
+ * w1 (4dim,dim) b1 (4dim) w2 (dim,4dim) b2 (dim).  film_wt: (dim, film_rows) = all
+ * project_onto_scale_shift weights stacked along rows and TRANSPOSED (coalesced reads),
+ * film_b (film_rows).  Outputs: c (B,dim), film (B,film_rows). */
 TDB_API int tdb_time_film(const int64_t* t, const float* emb_scale, const float* emb_bias, const float* w1,
-                  const float* b1, const float* w2, const float* b2, const float* film_w,
+                  const float* b1, const float* w2, const float* b2, const float* film_wt,
                   const float* film_b, float* c, float* film, int B, int dim, int film_rows,
                   void* stream);
 

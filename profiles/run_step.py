@@ -1,0 +1,60 @@
+"""One denoise step of the bench workload between cudaProfilerStart/Stop, for ncu:
+
+  ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+      --log-file gpurun_out/launches.csv python profiles/run_step.py [--batch 4] [--precision bf16]
+"""
+
+import argparse
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path[:0] = [str(ROOT), str(ROOT / "generative-turbulence_b200")]
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from oracle.unet_ref import synth_state_dict  # noqa: E402
+from turbdiff_b200 import DenoisingModel, GaussianDiffusion, _lib  # noqa: E402
+from turbdiff_b200.models.utils import inside_mask  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=4)
+ap.add_argument("--precision", default="bf16")
+ap.add_argument("--steps", type=int, default=1)
+a = ap.parse_args()
+T, B = 1000, a.batch
+dev = torch.device("cuda", 0)
+spec = bench.shapes_spec(T)
+m = DenoisingModel(in_features=4, out_features=4, c_local_features=4, c_global_features=0, timesteps=T, dim=32, u_net_levels=4,
+                   norm_type="group", precision=a.precision)
+m.load_state_dict(synth_state_dict(spec, 0))
+m = m.to(dev).eval()
+gd = GaussianDiffusion(m, timesteps=T, beta_schedule="log-snr-linear", noise_bcs=True).to(dev)
+geo, x, c_local = bench.synthetic_inputs(B, 100)
+x_bcs, cl = x.to(dev), c_local.to(dev)
+idx = torch.from_numpy(geo.cell_idx).to(dev)
+nvox = int(np.prod(geo.padded))
+mask, coef, eng = inside_mask(idx, nvox), gd._coef_table(dev), m.engine()
+x_t = torch.randn_like(x_bcs)
+t_dev = torch.full((1,), 500, dtype=torch.int32, device=dev)
+t_vec = torch.full((B,), 500, dtype=torch.int64, device=dev)
+
+
+def step():
+    eps = eng.forward(x_t, t_vec, cl)
+    z, zb = torch.randn_like(x_t), torch.randn_like(x_bcs)
+    _lib.call("tdb_ddpm_step", x_t.data_ptr(), eps.data_ptr(), z.data_ptr(), zb.data_ptr(), x_bcs.data_ptr(), mask.data_ptr(),
+              coef.data_ptr(), t_dev.data_ptr(), x_t.data_ptr(), B, 4, nvox, _lib.STEP_NOISE_BCS, _lib.stream_ptr())
+
+
+for _ in range(2):
+    step()
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+for _ in range(a.steps):
+    step()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print("done")

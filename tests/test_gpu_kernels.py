@@ -95,6 +95,37 @@ def test_conv3d_bf16_tensor_core(lib, case, fused_stats):
         np.testing.assert_allclose(stats[..., 1].cpu().numpy(), (wg**2).sum(-1).numpy(), rtol=1e-4)
 
 
+FOLD_CASES = [c for c in CONV_CASES if c[6] == 27 and 3 * c[5] <= 256] + [
+    (2, 20, 9, 7, 32, 32, 27),     # weights resident in shared memory, several tiles per CTA
+    (1, 40, 30, 30, 64, 64, 27),   # 288 tiles over 148 persistent CTAs: both TMEM stages recycle
+    (3, 21, 11, 9, 128, 32, 27),
+    (1, 13, 6, 5, 16, 48, 27),
+]
+
+
+@pytest.mark.parametrize("case", FOLD_CASES)
+@pytest.mark.parametrize("fused_stats", [False, True])
+def test_conv3d_bf16_kz_folded(lib, case, fused_stats):
+    B, X, Y, Z, Cin, Cout, _ = case
+    x = gen(B, Cin, X, Y, Z, seed=1).bfloat16().float()
+    w = gen(Cout, Cin, 3, 3, 3, seed=2, scale=1 / math.sqrt(Cin * 27)).bfloat16().float()
+    b = gen(Cout, seed=3, scale=0.1)
+    xin = to_halo(x, dtype=torch.bfloat16)
+    wf = w.permute(4, 0, 2, 3, 1).reshape(3 * Cout, 9 * Cin).contiguous().bfloat16()
+    out = torch.zeros((B, X + 2, Y + 2, Z + 2, Cout), device="cuda", dtype=torch.bfloat16)
+    G = 8
+    stats = torch.zeros((B, G, 2), dtype=torch.float64, device="cuda")
+    lib.call("tdb_conv3d_bf16_fold", xin.data_ptr(), Cin, wf.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
+             stats.data_ptr() if fused_stats else None, G, lib.stream_ptr())
+    torch.cuda.synchronize()
+    want = _conv_ref(x.double().cpu(), w.double().cpu(), b.double().cpu(), 27)
+    assert rel_l2(from_halo(out), want) < 4e-3
+    if fused_stats:
+        wg = want.reshape(B, G, -1)
+        np.testing.assert_allclose(stats[..., 0].cpu().numpy(), wg.sum(-1).numpy(), rtol=1e-4, atol=1e-2)
+        np.testing.assert_allclose(stats[..., 1].cpu().numpy(), (wg**2).sum(-1).numpy(), rtol=1e-4)
+
+
 # --------------------------------------------------------------------------- GroupNorm / pointwise
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 @pytest.mark.parametrize("C,G", [(64, 8), (16, 8), (32, 1), (16, 16), (512, 8)])
@@ -183,7 +214,7 @@ def test_time_film(lib):
     d = {k: v.cuda() for k, v in sd.items()}
     c = torch.zeros(4, 32, device="cuda")
     film = torch.zeros(4, 96, device="cuda")
-    fwc, fbc, tc = fw.cuda(), fb.cuda(), t.cuda()
+    fwc, fbc, tc = fw.t().contiguous().cuda(), fb.cuda(), t.cuda()
     lib.call("tdb_time_film", tc.data_ptr(), emb.scale.data_ptr(), emb.bias.data_ptr(), d["process_c.0.weight"].data_ptr(),
              d["process_c.0.bias"].data_ptr(), d["process_c.2.weight"].data_ptr(), d["process_c.2.bias"].data_ptr(), fwc.data_ptr(),
              fbc.data_ptr(), c.data_ptr(), film.data_ptr(), 4, 32, 96, lib.stream_ptr())
