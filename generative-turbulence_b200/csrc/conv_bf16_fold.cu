@@ -1,21 +1,26 @@
-// kz-folded, persistent bf16 implicit-GEMM 3x3x3 convolution for the narrow layers (3*Cout <= 256),
-// which carry 60 % of the network's FLOPs at full resolution and are L2->SMEM bound in the plain
-// per-tap kernel (conv_bf16_tc.cu: every input row is fetched 27 times for only Cout MACs each).
+// kz-folded, persistent bf16 implicit-GEMM 3x3x3 convolution for the narrow layers (Cout in
+// {16,32,64}), which carry 60 % of the network's FLOPs at full resolution and are L2->SMEM bound in
+// the plain per-tap kernel (conv_bf16_tc.cu fetches every input row 27 times for only Cout MACs each).
 //
 // Fold the fastest filter axis into the GEMM N dimension.  With rows linearised over the halo grid,
 //     out[p] = sum_kz Y_kz[p + kz - 1],      Y_kz[q] = sum_{kx,ky,ci} W[kx,ky,kz][ci] * in[q + s(kx,ky)][ci]
 //     s(kx,ky) = (kx-1)*Yp*Zp + (ky-1)*Zp
-// so one GEMM with N' = 3*Cout (column kz*Cout+co) and K' = 9*Cin produces all three Y_kz for a
-// 128-row tile from only NINE row-shifted A boxes (3x less activation traffic, 3x wider MMAs: the
-// SMEM operand bandwidth per MMA cycle drops below the 128 B/clk limit), and the kz shift becomes a
-// +-1 LANE shift of the accumulator rows in the epilogue (warp shuffles + a 2-row exchange between
-// neighbouring epilogue warps).  A tile therefore yields 126 output rows; tiles advance by 126.
+// so one GEMM with N' = 3*Cout (column kz*Cout+co) and K' = 9*Cin produces all three Y_kz from only
+// NINE row-shifted A tiles (3x less activation traffic, 3x wider MMAs so the SMEM operand bandwidth
+// per MMA cycle stays below 128 B/clk), and the kz shift becomes a +-1 LANE shift of accumulator rows
+// in the epilogue (two warp shuffles per value).  To keep the shift inside a warp, the 128-row A tile
+// is assembled from FOUR 32-row TMA boxes that overlap by two rows: TMEM lane group w holds rows
+// q = tile*120 + 30*w - 1 + lane, and lanes 1..30 of each warp produce outputs (120 rows per tile).
 //
 // Persistent CTAs (one per SM) walk tiles round-robin.  TMEM holds two accumulator stages so the
 // epilogue of tile j overlaps the MMAs of tile j+1.  When the folded weights fit (<= 112 KB: the
 // 32->32 layers) they are loaded into shared memory ONCE per CTA and only activations stream.
+// GroupNorm moments are accumulated in registers across all tiles of the CTA and flushed with one
+// double atomicAdd per (warp, group) at the end (or when the sample index changes).
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issue, warps 2-5 epilogue.
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issue, warps 2-9 epilogue
+// (two warps per TMEM lane group, alternating 16-column chunks: two warps per scheduler hide the
+// TMEM-load / shuffle latencies).
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tma_host.cuh"
@@ -26,48 +31,53 @@ using bf16 = __nv_bfloat16;
 namespace {
 
 constexpr int BM = 128;
-constexpr int ROWS_OUT = BM - 2;  // output rows per tile
-constexpr int THREADS = 192;
+constexpr int ROWS_WARP = 30;             // output rows per lane group
+constexpr int ROWS_OUT = 4 * ROWS_WARP;   // output rows per tile
+constexpr int THREADS = 320;
 constexpr int MAX_STAGES = 12;
 
 struct FoldParams {
-    int64_t rows, vox_p;
+    int64_t rows;
+    uint32_t vox_p;
     int Xp, Yp, Zp;
-    int Cin, Cout;
+    FastDiv by_vox, by_z, by_y;
+    int Cin;
     int KC;          // channels per K chunk
-    int NF;          // 3*Cout
     int stages;
     int a_bytes;     // per-stage A tile bytes (1024-aligned)
     int b_bytes;     // B chunk bytes (1024-aligned)
     int b_resident;  // 1: all 9*Cin/KC B chunks live in smem for the whole kernel
     int tmem_half;   // columns per accumulator stage
     int ld_out;
-    int G;
+    int G;           // groups for fused GroupNorm moments (0 = off); (Cout/G) even
     int num_tiles;
 };
 
+// interior test of a linear halo-grid row; returns the sample index through b
 __device__ __forceinline__ bool interior_row(int64_t p, const FoldParams& P, int& b) {
     if (p < 0 || p >= P.rows) return false;
-    b = (int)(p / P.vox_p);
-    int64_t r = p - (int64_t)b * P.vox_p;
-    const int zp = (int)(r % P.Zp);
-    r /= P.Zp;
-    const int yp = (int)(r % P.Yp);
-    const int xp = (int)(r / P.Yp);
-    return xp >= 1 && xp <= P.Xp - 2 && yp >= 1 && yp <= P.Yp - 2 && zp >= 1 && zp <= P.Zp - 2;
+    uint32_t bb, r, q, zp, xp, yp;
+    P.by_vox.divmod((uint32_t)p, bb, r);
+    P.by_z.divmod(r, q, zp);
+    P.by_y.divmod(q, xp, yp);
+    b = (int)bb;
+    return xp >= 1u && xp <= (uint32_t)(P.Xp - 2) && yp >= 1u && yp <= (uint32_t)(P.Yp - 2) && zp >= 1u &&
+           zp <= (uint32_t)(P.Zp - 2);
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
+template <int COUT>
 __global__ void __launch_bounds__(THREADS, 1)
 conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                         const float* __restrict__ bias, bf16* __restrict__ out, double* __restrict__ gn_stats,
                         const FoldParams P) {
+    constexpr int NF = 3 * COUT;
+    constexpr int NCH = COUT / 16;           // 16-column chunks per kz block
+    constexpr int CH_PER_WARP = (NCH + 1) / 2;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 5];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float xch[2][2][4][16];  // [parity][0: lane31's kz=0 chunk, 1: lane0's kz=2 chunk][warp][col]
+    __shared__ __align__(16) float s_bias[COUT];
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const uint32_t full_bar = ptx::smem_u32(&bars[0]);
@@ -81,6 +91,7 @@ conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     const uint32_t stage_bytes = (uint32_t)P.a_bytes + (P.b_resident ? 0u : (uint32_t)P.b_bytes);
     const uint32_t stage_base = smem_base + b_region;
 
+    for (int i = threadIdx.x; i < COUT; i += THREADS) s_bias[i] = bias ? bias[i] : 0.0f;
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_b);
@@ -90,7 +101,7 @@ conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(acc_full + 8 * s, 1);
-            ptx::mbar_init(acc_empty + 8 * s, 4);  // one arrival per epilogue warp
+            ptx::mbar_init(acc_empty + 8 * s, 8);  // one arrival per epilogue warp
         }
         ptx::mbar_init(b_full, 1);
         ptx::fence_barrier_init();
@@ -108,12 +119,13 @@ conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         // ===== TMA producer =====
         if (lane == 0) {
             if (P.b_resident) {
-                ptx::mbar_arrive_expect_tx(b_full, (uint32_t)(k_iters * P.NF * P.KC * 2));
+                ptx::mbar_arrive_expect_tx(b_full, (uint32_t)(k_iters * NF * P.KC * 2));
                 for (int kc = 0; kc < k_iters; ++kc)
                     ptx::tma_load_2d(smem_base + kc * P.b_bytes, &map_b, b_full, kc * P.KC, 0);
             }
             const int yz = P.Yp * P.Zp;
-            const uint32_t tx = (uint32_t)(BM * P.KC * 2) + (P.b_resident ? 0u : (uint32_t)(P.NF * P.KC * 2));
+            const uint32_t quarter = (uint32_t)(32 * P.KC * 2);
+            const uint32_t tx = (uint32_t)(BM * P.KC * 2) + (P.b_resident ? 0u : (uint32_t)(NF * P.KC * 2));
             int it = 0;
             for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
                 const int64_t q0 = (int64_t)tile * ROWS_OUT - 1;
@@ -125,7 +137,9 @@ conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                         ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1u);
                         const uint32_t a_dst = stage_base + s * stage_bytes;
                         ptx::mbar_arrive_expect_tx(full_bar + 8 * s, tx);
-                        ptx::tma_load_2d(a_dst, &map_a, full_bar + 8 * s, ch * P.KC, row);
+#pragma unroll
+                        for (int w = 0; w < 4; ++w)  // four 32-row boxes overlapping by two rows
+                            ptx::tma_load_2d(a_dst + w * quarter, &map_a, full_bar + 8 * s, ch * P.KC, row + ROWS_WARP * w);
                         if (!P.b_resident)
                             ptx::tma_load_2d(a_dst + P.a_bytes, &map_b, full_bar + 8 * s, (t9 * chunks + ch) * P.KC, 0);
                     }
@@ -135,7 +149,7 @@ conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(BM, (uint32_t)P.NF);
+            const uint32_t idesc = ptx::umma_idesc_bf16(BM, (uint32_t)NF);
             const uint32_t row_bytes = (uint32_t)P.KC * 2u;
             const int kk = P.KC / 16;
             if (P.b_resident) {
@@ -166,81 +180,101 @@ conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             }
         }
     } else {
-        // ===== epilogue =====
-        const int lg = warp % 4;        // TMEM lane group of this warp; rows lg*32 .. lg*32+31 of the tile
-        const int i_row = lg * 32 + lane;
+        // ===== epilogue: 8 warps, lane group lg = warp % 4, column half = (warp - 2) / 4 =====
+        const int lg = warp % 4;
+        const int half = (warp - 2) / 4;
         const bool do_stats = gn_stats != nullptr;
-        const int cpg = do_stats ? P.Cout / P.G : 1;
-        int local = 0, par = 0;
+        // per-thread GroupNorm partials: column PAIRS of this warp's chunks, across all tiles of one sample
+        float st_s[CH_PER_WARP][8], st_q[CH_PER_WARP][8];
+#pragma unroll
+        for (int a = 0; a < CH_PER_WARP; ++a)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) st_s[a][j] = st_q[a][j] = 0.0f;
+        int st_b = -1;
+
+        auto flush_stats = [&]() {
+            // pairs -> groups (cpg even), warp reduce in double, one atomic per (warp, group, moment)
+            const int cpg = COUT / P.G;
+#pragma unroll
+            for (int a = 0; a < CH_PER_WARP; ++a) {
+                const int cidx = 2 * a + half;  // chunk index of this warp
+                if (cidx < NCH) {
+                    double gs = 0.0, gq = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        gs += (double)st_s[a][j];
+                        gq += (double)st_q[a][j];
+                        st_s[a][j] = st_q[a][j] = 0.0f;
+                        const int col_end = cidx * 16 + 2 * j + 2;
+                        if (col_end % cpg == 0 || j == 7) {
+                            const double ws = warp_sum(gs), wq = warp_sum(gq);
+                            if (lane == 0) {
+                                const int g = (col_end - 1) / cpg;
+                                atomicAdd(gn_stats + ((int64_t)st_b * P.G + g) * 2, ws);
+                                atomicAdd(gn_stats + ((int64_t)st_b * P.G + g) * 2 + 1, wq);
+                            }
+                            gs = gq = 0.0;
+                        }
+                    }
+                }
+            }
+        };
+
+        int local = 0;
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++local) {
             const int as = local & 1;
             const uint32_t aph = (uint32_t)(local >> 1) & 1u;
+            const int64_t p = (int64_t)tile * ROWS_OUT + ROWS_WARP * lg - 1 + lane;
+            int b = 0;
+            const bool valid = lane >= 1 && lane <= ROWS_WARP && interior_row(p, P, b);
+            if (do_stats) {
+                // valid rows of one warp share one sample (a sample boundary is two halo planes wide)
+                const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+                if (vmask) {
+                    const int b_warp = __shfl_sync(0xffffffffu, b, __ffs(vmask) - 1);
+                    if (b_warp != st_b) {
+                        if (st_b >= 0) flush_stats();
+                        st_b = b_warp;
+                    }
+                }
+            }
             ptx::mbar_wait(acc_full + 8 * as, aph);
             ptx::tc_fence_after();
-            const int64_t p = (int64_t)tile * ROWS_OUT - 1 + i_row;
-            int b = 0;
-            const bool valid = i_row >= 1 && i_row <= BM - 2 && interior_row(p, P, b);
-            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-            const int b_warp = __shfl_sync(0xffffffffu, b, vmask ? __ffs(vmask) - 1 : 0);
             const uint32_t t_row = tmem_d + (uint32_t)(as * P.tmem_half) + ((uint32_t)(lg * 32) << 16);
             bf16* orow = out + p * P.ld_out;
-            float gs = 0.0f, gss = 0.0f;
-            for (int c = 0; c < P.Cout; c += 16, par ^= 1) {
-                uint32_t r0[16], r1[16], r2[16];
-                ptx::tmem_ld_x16(t_row + (uint32_t)c, r0);
-                ptx::tmem_ld_x16(t_row + (uint32_t)(P.Cout + c), r1);
-                ptx::tmem_ld_x16(t_row + (uint32_t)(2 * P.Cout + c), r2);
-                ptx::tmem_ld_wait();
-                // rows cross warps at lanes 0 / 31: hand the boundary rows over through shared memory
-                if (lane == 31) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) xch[par][0][lg][j] = __uint_as_float(r0[j]);
-                }
-                if (lane == 0) {
+            for (int a = 0; a < CH_PER_WARP; ++a) {
+                const int c = (2 * a + half) * 16;
+                if (c < COUT) {
+                    uint32_t r0[16], r1[16], r2[16];
+                    ptx::tmem_ld_x16(t_row + (uint32_t)c, r0);
+                    ptx::tmem_ld_x16(t_row + (uint32_t)(COUT + c), r1);
+                    ptx::tmem_ld_x16(t_row + (uint32_t)(2 * COUT + c), r2);
+                    ptx::tmem_ld_wait();
+                    float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) xch[par][1][lg][j] = __uint_as_float(r2[j]);
-                }
-                epi_bar_sync();
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float up = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[j]), 1);    // Y_0 of row i-1
-                    float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);  // Y_2 of row i+1
-                    if (lane == 0) up = lg > 0 ? xch[par][0][lg - 1][j] : 0.0f;
-                    if (lane == 31) dn = lg < 3 ? xch[par][1][lg + 1][j] : 0.0f;
-                    v[j] = up + __uint_as_float(r1[j]) + dn + (bias ? __ldg(bias + c + j) : 0.0f);
-                }
-                if (valid) {
-                    uint4 lo, hi;
-                    __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&lo);
-                    __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&hi);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        h0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                        h1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
+                    for (int j = 0; j < 16; ++j) {
+                        const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[j]), 1);    // Y_0 of row i-1
+                        const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);  // Y_2 of row i+1
+                        v[j] = (up + __uint_as_float(r1[j])) + (dn + s_bias[c + j]);
                     }
-                    *reinterpret_cast<uint4*>(orow + c) = lo;
-                    *reinterpret_cast<uint4*>(orow + c + 8) = hi;
-                }
-                if (do_stats) {
-                    const int sub = cpg >= 16 ? 16 : cpg;
-                    for (int j0 = 0; j0 < 16; j0 += sub) {
+                    if (valid) {
+                        uint4 lo, hi;
+                        __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&lo);
+                        __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&hi);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if (j >= j0 && j < j0 + sub && valid) {
-                                gs += v[j];
-                                gss = fmaf(v[j], v[j], gss);
-                            }
+                        for (int j = 0; j < 4; ++j) {
+                            h0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                            h1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
                         }
-                        const int col_end = c + j0 + sub;
-                        if (col_end % cpg == 0) {
-                            const double ds = warp_sum((double)gs), dss = warp_sum((double)gss);
-                            if (lane == 0 && vmask) {
-                                const int g = (col_end - 1) / cpg;
-                                atomicAdd(gn_stats + ((int64_t)b_warp * P.G + g) * 2, ds);
-                                atomicAdd(gn_stats + ((int64_t)b_warp * P.G + g) * 2 + 1, dss);
+                        *reinterpret_cast<uint4*>(orow + c) = lo;
+                        *reinterpret_cast<uint4*>(orow + c + 8) = hi;
+                        if (do_stats) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                st_s[a][j] += v[2 * j] + v[2 * j + 1];
+                                st_q[a][j] = fmaf(v[2 * j], v[2 * j], fmaf(v[2 * j + 1], v[2 * j + 1], st_q[a][j]));
                             }
-                            gs = gss = 0.0f;
                         }
                     }
                 }
@@ -250,6 +284,7 @@ conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(acc_empty + 8 * as);
         }
+        if (do_stats && st_b >= 0) flush_stats();
     }
 
     ptx::tc_fence_before();
@@ -262,18 +297,29 @@ conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 
 int g_num_sms = 0;
 
+template <int COUT>
+int launch_fold(const CUtensorMap& map_a, const CUtensorMap& map_b, const float* bias, bf16* out, double* gn_stats,
+                const FoldParams& P, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(conv3d_bf16_fold_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_conv3d_bf16_fold: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    const int grid = P.num_tiles < g_num_sms ? P.num_tiles : g_num_sms;
+    conv3d_bf16_fold_kernel<COUT><<<grid, THREADS, smem, stream>>>(map_a, map_b, bias, out, gn_stats, P);
+    TDB_CHECK_LAUNCH("tdb_conv3d_bf16_fold");
+    return 0;
+}
+
 }  // namespace
 
 extern "C" int tdb_conv3d_bf16_fold(const void* in, int ld_in, const void* w_fold, const float* bias, void* out,
                                     int ld_out, int B, int X, int Y, int Z, int Cin, int Cout, double* gn_stats, int G,
                                     void* stream) {
     TDB_REQUIRE(in && w_fold && out, TDB_E_BADARG, "tdb_conv3d_bf16_fold: null pointer");
-    TDB_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0 && 3 * Cout <= 256 && ld_in % 8 == 0 && ld_out % 8 == 0, TDB_E_UNSUPPORTED,
-                "tdb_conv3d_bf16_fold: need Cin %% 16 == 0, Cout %% 16 == 0, 3*Cout <= 256 (Cin=%d Cout=%d)", Cin, Cout);
+    TDB_REQUIRE(Cin % 16 == 0 && (Cout == 16 || Cout == 32 || Cout == 64) && ld_in % 8 == 0 && ld_out % 8 == 0, TDB_E_UNSUPPORTED,
+                "tdb_conv3d_bf16_fold: need Cin %% 16 == 0 and Cout in {16,32,64} (Cin=%d Cout=%d)", Cin, Cout);
     TDB_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)w_fold & 15) == 0, TDB_E_UNSUPPORTED,
                 "tdb_conv3d_bf16_fold: pointers must be 16-byte aligned");
-    TDB_REQUIRE(!gn_stats || (G >= 1 && Cout % G == 0 && ((Cout / G) % 16 == 0 || 16 % (Cout / G) == 0)), TDB_E_UNSUPPORTED,
-                "tdb_conv3d_bf16_fold: fused GroupNorm moments need Cout/G to divide or be a multiple of 16");
+    TDB_REQUIRE(!gn_stats || (G >= 1 && Cout % G == 0 && (Cout / G) % 2 == 0), TDB_E_UNSUPPORTED,
+                "tdb_conv3d_bf16_fold: fused GroupNorm moments need an even number of channels per group");
     Grid3 g(B, X, Y, Z);
     TDB_REQUIRE(g.rows < (1ll << 31) - 4096, TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_fold: too many rows for 32-bit TMA coordinates");
     if (g_num_sms == 0) {
@@ -285,14 +331,17 @@ extern "C" int tdb_conv3d_bf16_fold(const void* in, int ld_in, const void* w_fol
 
     FoldParams P;
     P.rows = g.rows;
-    P.vox_p = g.vox_p;
+    P.vox_p = (uint32_t)g.vox_p;
     P.Xp = g.Xp; P.Yp = g.Yp; P.Zp = g.Zp;
-    P.Cin = Cin; P.Cout = Cout;
+    P.by_vox = FastDiv((uint32_t)g.vox_p);
+    P.by_z = FastDiv((uint32_t)g.Zp);
+    P.by_y = FastDiv((uint32_t)g.Yp);
+    P.Cin = Cin;
     P.KC = Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 16);
-    P.NF = 3 * Cout;
+    const int NF = 3 * Cout;
     auto up1k = [](int v) { return (v + 1023) & ~1023; };
     P.a_bytes = up1k(BM * P.KC * 2);
-    P.b_bytes = up1k(P.NF * P.KC * 2);
+    P.b_bytes = up1k(NF * P.KC * 2);
     const int k_iters = 9 * (Cin / P.KC);
     const int budget = 222 * 1024;  // dynamic smem we allow ourselves (227 KB max, minus static + alignment slack)
     P.b_resident = (int64_t)k_iters * P.b_bytes <= 112 * 1024 ? 1 : 0;
@@ -302,7 +351,7 @@ extern "C" int tdb_conv3d_bf16_fold(const void* in, int ld_in, const void* w_fol
     TDB_REQUIRE(stages >= 2, TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_fold: tiles do not fit in shared memory");
     P.stages = stages;
     int half = 32;
-    while (half < P.NF) half *= 2;
+    while (half < NF) half *= 2;
     P.tmem_half = half;
     P.ld_out = ld_out;
     P.G = gn_stats ? G : 0;
@@ -310,16 +359,15 @@ extern "C" int tdb_conv3d_bf16_fold(const void* in, int ld_in, const void* w_fol
 
     CUtensorMap map_a, map_b;
     TDB_REQUIRE(encode_fn() != nullptr, TDB_E_NODEVICE, "tdb_conv3d_bf16_fold: cuTensorMapEncodeTiled unavailable (no driver)");
-    TDB_REQUIRE(make_map_2d_bf16(&map_a, in, (uint64_t)Cin, (uint64_t)g.rows, (uint64_t)ld_in, (uint32_t)P.KC, BM), TDB_E_BADARG,
+    // A: 32-row boxes (one per TMEM lane group); B: one box of all 3*Cout folded rows
+    TDB_REQUIRE(make_map_2d_bf16(&map_a, in, (uint64_t)Cin, (uint64_t)g.rows, (uint64_t)ld_in, (uint32_t)P.KC, 32), TDB_E_BADARG,
                 "tdb_conv3d_bf16_fold: tensor map (activations) rejected");
-    TDB_REQUIRE(make_map_2d_bf16(&map_b, w_fold, (uint64_t)9 * Cin, (uint64_t)P.NF, (uint64_t)9 * Cin, (uint32_t)P.KC, (uint32_t)P.NF),
+    TDB_REQUIRE(make_map_2d_bf16(&map_b, w_fold, (uint64_t)9 * Cin, (uint64_t)NF, (uint64_t)9 * Cin, (uint32_t)P.KC, (uint32_t)NF),
                 TDB_E_BADARG, "tdb_conv3d_bf16_fold: tensor map (weights) rejected");
 
     const size_t smem = (size_t)(P.b_resident ? k_iters * P.b_bytes : 0) + (size_t)stages * stage_bytes + 1024;
-    cudaError_t e = cudaFuncSetAttribute(conv3d_bf16_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_conv3d_bf16_fold: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-    const int grid = P.num_tiles < g_num_sms ? P.num_tiles : g_num_sms;
-    conv3d_bf16_fold_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, bias, (bf16*)out, gn_stats, P);
-    TDB_CHECK_LAUNCH("tdb_conv3d_bf16_fold");
-    return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (Cout == 16) return launch_fold<16>(map_a, map_b, bias, (bf16*)out, gn_stats, P, smem, s);
+    if (Cout == 32) return launch_fold<32>(map_a, map_b, bias, (bf16*)out, gn_stats, P, smem, s);
+    return launch_fold<64>(map_a, map_b, bias, (bf16*)out, gn_stats, P, smem, s);
 }

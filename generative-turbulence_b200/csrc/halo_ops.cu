@@ -23,42 +23,49 @@ struct RowSplit {
 };
 
 // ---------------------------------------------------------------- encode_x / encode_c_local
-// grid = (blocks per sample, B); thread = one 16-byte channel vector of one haloed voxel.
+// grid = (blocks per sample, B).  A thread owns ONE 16-byte channel vector position (its 1x1-conv
+// weights live in registers for the whole kernel) and walks haloed voxels.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 encode_input_kernel(const float* __restrict__ x, const float* __restrict__ c_local,
                     const float* __restrict__ wx, const float* __restrict__ bx,
                     const float* __restrict__ wc, const float* __restrict__ bc, T* __restrict__ out,
-                    int ld_out, Grid3 g, int F, int Fc, int dim, int parts, RowSplit split, FastDiv by_chunks) {
+                    int ld_out, Grid3 g, int F, int Fc, int dim, int parts, RowSplit split, int chunks) {
     constexpr int N = Vec<T>::N;
     const int b = blockIdx.y;
-    const uint32_t chunks = by_chunks.d;
-    const uint32_t total = (uint32_t)g.vox_p * chunks;
+    const int vox_step = kThreads / chunks;
+    const int ch = threadIdx.x % chunks, lane_vox = threadIdx.x / chunks;
+    if (lane_vox >= vox_step) return;
+    const int c0 = ch * N;
+    const bool c_half = c0 >= dim;
+    if (c_half ? !(parts & 2) : !(parts & 1)) return;
+    const int nf = c_half ? Fc : F;
+    const float* w = c_half ? wc + (int64_t)(c0 - dim) * Fc : wx + (int64_t)c0 * F;
+    const float* bias = c_half ? bc + (c0 - dim) : bx + c0;
+    float wr[N][8], br[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        br[i] = bias[i];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) wr[i][f] = f < nf ? w[i * nf + f] : 0.0f;
+    }
     const int64_t nvox = (int64_t)g.X * g.Y * g.Z;
-    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        uint32_t r, ch;
-        by_chunks.divmod(idx, r, ch);
-        const int c0 = (int)ch * N;
-        const bool c_half = c0 >= dim;
-        if (c_half ? !(parts & 2) : !(parts & 1)) continue;
+    const float* src0 = c_half ? c_local : x + (int64_t)b * F * nvox;
+    const uint32_t total = (uint32_t)g.vox_p;
+    for (uint32_t r = blockIdx.x * vox_step + lane_vox; r < total; r += gridDim.x * vox_step) {
         int xp, yp, zp;
         split(r, xp, yp, zp);
         const int xs = clampi(xp - 1, 0, g.X - 1), ys = clampi(yp - 1, 0, g.Y - 1), zs = clampi(zp - 1, 0, g.Z - 1);
-        const int64_t v = ((int64_t)xs * g.Y + ys) * g.Z + zs;
-        const int nf = c_half ? Fc : F;
-        const float* src = c_half ? c_local + v : x + (int64_t)b * F * nvox + v;
-        const float* w = c_half ? wc + (int64_t)(c0 - dim) * Fc : wx + (int64_t)c0 * F;
-        const float* bias = c_half ? bc + (c0 - dim) : bx + c0;
+        const float* src = src0 + ((int64_t)xs * g.Y + ys) * g.Z + zs;
         float in[8];
 #pragma unroll
         for (int f = 0; f < 8; ++f) in[f] = f < nf ? __ldg(src + (int64_t)f * nvox) : 0.0f;
         float o[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            float acc = __ldg(bias + i);
+            float acc = br[i];
 #pragma unroll
-            for (int f = 0; f < 8; ++f)
-                if (f < nf) acc = fmaf(__ldg(w + i * nf + f), in[f], acc);
+            for (int f = 0; f < 8; ++f) acc = fmaf(wr[i][f], in[f], acc);
             o[i] = acc;
         }
         Vec<T>::store(out + ((int64_t)b * g.vox_p + r) * ld_out + c0, o);
@@ -166,49 +173,59 @@ gn_stats_kernel(const T* __restrict__ raw, int ld, double* __restrict__ stats, G
 
 // ---------------------------------------------------------------- fused pointwise
 template <typename T>
+__device__ __forceinline__ float act_silu(float v) {
+    if constexpr (sizeof(T) == 2)  // bf16 storage: the fast exp/rcp are far below the output rounding
+        return __fdividef(v, 1.0f + __expf(-v));
+    else
+        return silu_f(v);
+}
+
+// grid = (blocks per sample, B).  A thread owns one 16-byte channel vector position: its affine
+// coefficients (GroupNorm mean/rstd/gamma/beta folded with FiLM scale/shift) live in registers.
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
 pointwise_kernel(const T* __restrict__ raw, int ld_raw, const double* __restrict__ stats,
                  const float* __restrict__ gamma, const float* __restrict__ beta,
                  const float* __restrict__ film, int film_ld, const T* __restrict__ res, int ld_res,
                  T* __restrict__ out, int ld_out, Grid3 g, int C, int G, float eps, unsigned flags,
-                 int rows_per_block, RowSplit split, FastDiv by_chunks) {
+                 RowSplit split, int chunks) {
     constexpr int N = Vec<T>::N;
-    extern __shared__ float coef[];  // [C] scale, [C] offset
     const int b = blockIdx.y;
-    const int cpg = C / G;
-    const double inv_n = 1.0 / ((double)cpg * g.X * g.Y * g.Z);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float a = 1.0f, o = 0.0f;
-        if (stats) {
-            const int gi = c / cpg;
-            const double mean = stats[((int64_t)b * G + gi) * 2] * inv_n;
-            double var = stats[((int64_t)b * G + gi) * 2 + 1] * inv_n - mean * mean;
-            var = var > 0.0 ? var : 0.0;
-            const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-            a = rstd * gamma[c];
-            o = beta[c] - (float)mean * a;
+    const int vox_step = kThreads / chunks;
+    const int ch = threadIdx.x % chunks, lane_vox = threadIdx.x / chunks;
+    if (lane_vox >= vox_step) return;
+    const int c0 = ch * N;
+    float ca[N], co[N];
+    {
+        const int cpg = C / G;
+        const double inv_n = 1.0 / ((double)cpg * g.X * g.Y * g.Z);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int c = c0 + i;
+            float a = 1.0f, o = 0.0f;
+            if (stats) {
+                const int gi = c / cpg;
+                const double mean = stats[((int64_t)b * G + gi) * 2] * inv_n;
+                double var = stats[((int64_t)b * G + gi) * 2 + 1] * inv_n - mean * mean;
+                var = var > 0.0 ? var : 0.0;
+                const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+                a = rstd * gamma[c];
+                o = beta[c] - (float)mean * a;
+            }
+            if (film) {
+                const float sc = film[(int64_t)b * film_ld + c] + 1.0f;
+                const float sh = film[(int64_t)b * film_ld + C + c];
+                a *= sc;
+                o = fmaf(o, sc, sh);
+            }
+            ca[i] = a;
+            co[i] = o;
         }
-        if (film) {
-            const float sc = film[(int64_t)b * film_ld + c] + 1.0f;
-            const float sh = film[(int64_t)b * film_ld + C + c];
-            a *= sc;
-            o = fmaf(o, sc, sh);
-        }
-        coef[c] = a;
-        coef[C + c] = o;
     }
-    __syncthreads();
-    const uint32_t chunks = by_chunks.d;
     const bool interior_only = flags & TDB_PW_NOHALO;
     const bool act = flags & TDB_PW_SILU;
-    const uint32_t r_begin = blockIdx.x * (uint32_t)rows_per_block;
-    const uint32_t r_end = min((uint32_t)g.vox_p, r_begin + (uint32_t)rows_per_block);
-    const uint32_t total = (r_end - r_begin) * chunks;
-    for (uint32_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        uint32_t rq, ch;
-        by_chunks.divmod(idx, rq, ch);
-        const uint32_t r = r_begin + rq;
-        const int c0 = (int)ch * N;
+    const uint32_t total = (uint32_t)g.vox_p;
+    for (uint32_t r = blockIdx.x * vox_step + lane_vox; r < total; r += gridDim.x * vox_step) {
         int xp, yp, zp;
         split(r, xp, yp, zp);
         const int xs = clampi(xp, 1, g.X), ys = clampi(yp, 1, g.Y), zs = clampi(zp, 1, g.Z);
@@ -218,8 +235,8 @@ pointwise_kernel(const T* __restrict__ raw, int ld_raw, const double* __restrict
         Vec<T>::load(raw + src * ld_raw + c0, v);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            float y = fmaf(coef[c0 + i], v[i], coef[C + c0 + i]);
-            v[i] = act ? silu_f(y) : y;
+            const float y = fmaf(ca[i], v[i], co[i]);
+            v[i] = act ? act_silu<T>(y) : y;
         }
         if (res) {
             float rr[N];
@@ -236,9 +253,8 @@ struct Lerp {
     int i0, i1;
     float l0, l1;
 };
-__device__ __forceinline__ Lerp axis_lerp(int o, int n_in, int n_out) {
+__device__ __forceinline__ Lerp axis_lerp(int o, int n_in, float scale) {
     // ATen: scale = (float)(n_in-1)/(n_out-1); src = scale*o; i0 = (int)src; lambda = src - i0
-    const float scale = n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.0f;
     const float src = scale * (float)o;
     Lerp r;
     r.i0 = min((int)src, n_in - 1);
@@ -252,20 +268,20 @@ __device__ __forceinline__ Lerp axis_lerp(int o, int n_in, int n_out) {
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 trilinear_kernel(const T* __restrict__ in, int ld_in, Grid3 gi, T* __restrict__ out, int ld_out, Grid3 go, int C,
-                 RowSplit split, FastDiv by_chunks) {
+                 RowSplit split, int chunks, float sx, float sy, float sz) {
     constexpr int N = Vec<T>::N;
     const int b = blockIdx.y;
-    const uint32_t chunks = by_chunks.d;
-    const uint32_t total = (uint32_t)go.vox_p * chunks;
-    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        uint32_t r, ch;
-        by_chunks.divmod(idx, r, ch);
-        const int c0 = (int)ch * N;
+    const int vox_step = kThreads / chunks;
+    const int ch = threadIdx.x % chunks, lane_vox = threadIdx.x / chunks;
+    if (lane_vox >= vox_step) return;
+    const int c0 = ch * N;
+    const uint32_t total = (uint32_t)go.vox_p;
+    for (uint32_t r = blockIdx.x * vox_step + lane_vox; r < total; r += gridDim.x * vox_step) {
         int xp, yp, zp;
         split(r, xp, yp, zp);
-        const Lerp lx = axis_lerp(clampi(xp - 1, 0, go.X - 1), gi.X, go.X);
-        const Lerp ly = axis_lerp(clampi(yp - 1, 0, go.Y - 1), gi.Y, go.Y);
-        const Lerp lz = axis_lerp(clampi(zp - 1, 0, go.Z - 1), gi.Z, go.Z);
+        const Lerp lx = axis_lerp(clampi(xp - 1, 0, go.X - 1), gi.X, sx);
+        const Lerp ly = axis_lerp(clampi(yp - 1, 0, go.Y - 1), gi.Y, sy);
+        const Lerp lz = axis_lerp(clampi(zp - 1, 0, go.Z - 1), gi.Z, sz);
         float acc[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) acc[i] = 0.0f;
@@ -323,15 +339,15 @@ int tdb_encode_input(const float* x, const float* c_local, const float* wx, cons
                 "tdb_encode_input: dim/ld_out must be multiples of %d and out 16B aligned", n);
     Grid3 g(B, X, Y, Z);
     const int ctot = dim + (Fc > 0 ? dim : 0);
-    TDB_REQUIRE(g.vox_p * (ctot / n) < (1ll << 31), TDB_E_UNSUPPORTED, "tdb_encode_input: grid too large for 32-bit indexing");
-    dim3 grid((unsigned)blocks_per_sample(g.vox_p * (ctot / n), B), (unsigned)B);
+    const int chunks = ctot / n;
+    TDB_REQUIRE(g.vox_p < (1ll << 31) && chunks <= kThreads, TDB_E_UNSUPPORTED, "tdb_encode_input: grid too large for 32-bit indexing");
+    dim3 grid((unsigned)blocks_per_sample(g.vox_p * chunks, B), (unsigned)B);
     const RowSplit split = make_split(g);
-    const FastDiv by_chunks((uint32_t)(ctot / n));
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == TDB_BF16)
-        encode_input_kernel<bf16><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (bf16*)out, ld_out, g, F, Fc, dim, parts, split, by_chunks);
+        encode_input_kernel<bf16><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (bf16*)out, ld_out, g, F, Fc, dim, parts, split, chunks);
     else
-        encode_input_kernel<float><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (float*)out, ld_out, g, F, Fc, dim, parts, split, by_chunks);
+        encode_input_kernel<float><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (float*)out, ld_out, g, F, Fc, dim, parts, split, chunks);
     TDB_CHECK_LAUNCH("tdb_encode_input");
     return 0;
 }
@@ -388,26 +404,19 @@ int tdb_pointwise(const void* raw, int ld_raw, const double* stats, const float*
                 TDB_E_UNSUPPORTED, "tdb_pointwise: channel counts / pitches must be multiples of %d", n);
     if (G < 1) G = 1;
     Grid3 g(B, X, Y, Z);
-    TDB_REQUIRE(g.vox_p * (C / n) < (1ll << 31), TDB_E_UNSUPPORTED, "tdb_pointwise: grid too large for 32-bit indexing");
-    // ~8 resident blocks per SM over the whole launch keeps the per-block coefficient prologue negligible
-    int64_t bps = (148 * 8) / B;
-    if (bps < 1) bps = 1;
-    int64_t rows_per_block = ceil_div(g.vox_p, bps);
-    const int64_t min_rows = ceil_div(kThreads * 4, C / n);
-    if (rows_per_block < min_rows) rows_per_block = min_rows;
+    const int chunks = C / n;
+    TDB_REQUIRE(g.vox_p < (1ll << 31) && chunks <= kThreads, TDB_E_UNSUPPORTED, "tdb_pointwise: grid too large for 32-bit indexing");
+    dim3 grid((unsigned)blocks_per_sample(g.vox_p * chunks, B), (unsigned)B);
     const RowSplit split = make_split(g);
-    const FastDiv by_chunks((uint32_t)(C / n));
-    dim3 grid((unsigned)ceil_div(g.vox_p, rows_per_block), (unsigned)B);
-    const size_t smem = (size_t)2 * C * sizeof(float);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == TDB_BF16)
-        pointwise_kernel<bf16><<<grid, kThreads, smem, s>>>((const bf16*)raw, ld_raw, stats, gamma, beta, film, film_ld,
+        pointwise_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)raw, ld_raw, stats, gamma, beta, film, film_ld,
                                                              (const bf16*)res, ld_res, (bf16*)out, ld_out, g, C, G, eps,
-                                                             flags, (int)rows_per_block, split, by_chunks);
+                                                             flags, split, chunks);
     else
-        pointwise_kernel<float><<<grid, kThreads, smem, s>>>((const float*)raw, ld_raw, stats, gamma, beta, film, film_ld,
+        pointwise_kernel<float><<<grid, kThreads, 0, s>>>((const float*)raw, ld_raw, stats, gamma, beta, film, film_ld,
                                                               (const float*)res, ld_res, (float*)out, ld_out, g, C, G, eps,
-                                                              flags, (int)rows_per_block, split, by_chunks);
+                                                              flags, split, chunks);
     TDB_CHECK_LAUNCH("tdb_pointwise");
     return 0;
 }
@@ -419,15 +428,17 @@ int tdb_trilinear(const void* in, int ld_in, int Xi, int Yi, int Zi, void* out, 
     TDB_REQUIRE(C % n == 0 && ld_in % n == 0 && ld_out % n == 0 && aligned16(in) && aligned16(out),
                 TDB_E_UNSUPPORTED, "tdb_trilinear: channel counts / pitches must be multiples of %d", n);
     Grid3 gi(B, Xi, Yi, Zi), go(B, Xo, Yo, Zo);
-    TDB_REQUIRE(go.vox_p * (C / n) < (1ll << 31), TDB_E_UNSUPPORTED, "tdb_trilinear: grid too large for 32-bit indexing");
-    dim3 grid((unsigned)blocks_per_sample(go.vox_p * (C / n), B), (unsigned)B);
+    const int chunks = C / n;
+    TDB_REQUIRE(go.vox_p < (1ll << 31) && chunks <= kThreads, TDB_E_UNSUPPORTED, "tdb_trilinear: grid too large for 32-bit indexing");
+    dim3 grid((unsigned)blocks_per_sample(go.vox_p * chunks, B), (unsigned)B);
     const RowSplit split = make_split(go);
-    const FastDiv by_chunks((uint32_t)(C / n));
+    auto scale_of = [](int n_in, int n_out) { return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.0f; };
+    const float sx = scale_of(Xi, Xo), sy = scale_of(Yi, Yo), sz = scale_of(Zi, Zo);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == TDB_BF16)
-        trilinear_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)in, ld_in, gi, (bf16*)out, ld_out, go, C, split, by_chunks);
+        trilinear_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)in, ld_in, gi, (bf16*)out, ld_out, go, C, split, chunks, sx, sy, sz);
     else
-        trilinear_kernel<float><<<grid, kThreads, 0, s>>>((const float*)in, ld_in, gi, (float*)out, ld_out, go, C, split, by_chunks);
+        trilinear_kernel<float><<<grid, kThreads, 0, s>>>((const float*)in, ld_in, gi, (float*)out, ld_out, go, C, split, chunks, sx, sy, sz);
     TDB_CHECK_LAUNCH("tdb_trilinear");
     return 0;
 }

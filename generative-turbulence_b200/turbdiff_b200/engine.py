@@ -132,7 +132,7 @@ class DenoiserEngine:
 
     def use_fold(self, ntaps, cout) -> bool:
         """Narrow 3x3x3 layers run the kz-folded persistent kernel (tdb_conv3d_bf16_fold)."""
-        return self.precision == "bf16" and self.fold and ntaps == 27 and 3 * cout <= 256
+        return self.precision == "bf16" and self.fold and ntaps == 27 and cout in (16, 32, 64)
 
     # ------------------------------------------------------------------ workspace
     def plan(self, B, spatial, device):
@@ -236,7 +236,11 @@ class DenoiserEngine:
         """conv (+bias) followed by GroupNorm moments of its output."""
         G = self._groups(raw.C)
         stats = p["stats"][stats_slot]
-        fused = self.fused_stats and ((raw.C // G) % 16 == 0 or 16 % (raw.C // G) == 0)
+        cpg = raw.C // G
+        if self.use_fold(27, raw.C):
+            fused = self.fused_stats and cpg % 2 == 0
+        else:
+            fused = self.fused_stats and (cpg % 16 == 0 or 16 % cpg == 0)
         self._conv(p, x, w, conv.bias, raw, 27, stats if fused else None, G)
         if not fused:
             self._stats(p, raw, stats, G)

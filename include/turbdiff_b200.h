@@ -92,7 +92,7 @@ TDB_API int tdb_conv3d_bf16(const void* in, int ld_in, const void* w, const floa
                     int ld_out, int B, int X, int Y, int Z, int Cin, int Cout, int ntaps,
                     double* gn_stats, int G, void* stream);
 
-/* Same convolution (3x3x3 only) for narrow layers, 3*Cout <= 256: the kz filter axis is folded
+/* Same convolution (3x3x3 only) for narrow layers, Cout in {16,32,64}: the kz filter axis is folded
  * into the GEMM N dimension (9 row-shifted A boxes instead of 27, 3x wider MMAs), persistent CTAs,
  * double-buffered TMEM accumulators, weights resident in shared memory when they fit.
  * w_fold: packed [3*Cout][9*Cin] bf16, row = kz*Cout + co, col = (kx*3+ky)*Cin + ci. */
