@@ -9,8 +9,13 @@
 // NINE row-shifted A tiles (3x less activation traffic, 3x wider MMAs so the SMEM operand bandwidth
 // per MMA cycle stays below 128 B/clk), and the kz shift becomes a +-1 LANE shift of accumulator rows
 // in the epilogue (two warp shuffles per value).  To keep the shift inside a warp, the 128-row A tile
-// is assembled from FOUR 32-row TMA boxes that overlap by two rows: TMEM lane group w holds rows
+// consists of FOUR 32-row groups that overlap by two rows: TMEM lane group w holds rows
 // q = tile*120 + 30*w - 1 + lane, and lanes 1..30 of each warp produce outputs (120 rows per tile).
+// ONE 4-D TMA box fetches a whole pipeline stage of A: the tensor map views the activation matrix as
+// [ky (pitch Zp rows)][w (pitch 30 rows)][r][c], so the box {KC, 32, 4, TY} lands as TY consecutive
+// canonical 128-row K-major tiles (TY = 3 ky taps per stage when shared memory allows, else 1).  The
+// overlapping view cannot rely on TMA's out-of-bounds fill, so the caller guarantees `pad_rows`
+// readable rows before and after the halo grid (never used by a stored output).
 //
 // Persistent CTAs (one per SM) walk tiles round-robin.  TMEM holds two accumulator stages so the
 // epilogue of tile j overlaps the MMAs of tile j+1.  When the folded weights fit (<= 112 KB: the
@@ -44,8 +49,10 @@ struct FoldParams {
     int Cin;
     int KC;          // channels per K chunk
     int stages;
-    int a_bytes;     // per-stage A tile bytes (1024-aligned)
-    int b_bytes;     // B chunk bytes (1024-aligned)
+    int TY;          // ky taps per pipeline stage (1 or 3)
+    int a_bytes;     // one 128-row A tile (1024-aligned)
+    int b_bytes;     // one B chunk (1024-aligned)
+    int pad_rows;    // rows of padding in front of the halo grid (tensor-map row 0 = grid row -pad_rows)
     int b_resident;  // 1: all 9*Cin/KC B chunks live in smem for the whole kernel
     int tmem_half;   // columns per accumulator stage
     int ld_out;
@@ -86,9 +93,9 @@ conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     const uint32_t acc_empty = ptx::smem_u32(&bars[2 * MAX_STAGES + 2]);  // [2]
     const uint32_t b_full = ptx::smem_u32(&bars[2 * MAX_STAGES + 4]);
     const int chunks = P.Cin / P.KC;
-    const int k_iters = 9 * chunks;
-    const uint32_t b_region = P.b_resident ? (uint32_t)(k_iters * P.b_bytes) : 0u;
-    const uint32_t stage_bytes = (uint32_t)P.a_bytes + (P.b_resident ? 0u : (uint32_t)P.b_bytes);
+    const int n_bchunks = 9 * chunks;           // B chunks of KC channels: index t9*chunks + ch
+    const uint32_t b_region = P.b_resident ? (uint32_t)(n_bchunks * P.b_bytes) : 0u;
+    const uint32_t stage_bytes = (uint32_t)(P.TY * (P.a_bytes + (P.b_resident ? 0 : P.b_bytes)));
     const uint32_t stage_base = smem_base + b_region;
 
     for (int i = threadIdx.x; i < COUT; i += THREADS) s_bias[i] = bias ? bias[i] : 0.0f;
@@ -116,68 +123,88 @@ conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     const uint32_t tmem_d = tmem_base_slot;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            if (P.b_resident) {
-                ptx::mbar_arrive_expect_tx(b_full, (uint32_t)(k_iters * NF * P.KC * 2));
-                for (int kc = 0; kc < k_iters; ++kc)
-                    ptx::tma_load_2d(smem_base + kc * P.b_bytes, &map_b, b_full, kc * P.KC, 0);
-            }
-            const int yz = P.Yp * P.Zp;
-            const uint32_t quarter = (uint32_t)(32 * P.KC * 2);
-            const uint32_t tx = (uint32_t)(BM * P.KC * 2) + (P.b_resident ? 0u : (uint32_t)(NF * P.KC * 2));
-            int it = 0;
-            for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-                const int64_t q0 = (int64_t)tile * ROWS_OUT - 1;
-                for (int t9 = 0; t9 < 9; ++t9) {
-                    const int row = (int)(q0 + (int64_t)(t9 / 3 - 1) * yz + (int64_t)(t9 % 3 - 1) * P.Zp);
-                    for (int ch = 0; ch < chunks; ++ch, ++it) {
-                        const int s = it % P.stages;
-                        const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
-                        ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1u);
-                        const uint32_t a_dst = stage_base + s * stage_bytes;
-                        ptx::mbar_arrive_expect_tx(full_bar + 8 * s, tx);
-#pragma unroll
-                        for (int w = 0; w < 4; ++w)  // four 32-row boxes overlapping by two rows
-                            ptx::tma_load_2d(a_dst + w * quarter, &map_a, full_bar + 8 * s, ch * P.KC, row + ROWS_WARP * w);
-                        if (!P.b_resident)
-                            ptx::tma_load_2d(a_dst + P.a_bytes, &map_b, full_bar + 8 * s, (t9 * chunks + ch) * P.KC, 0);
+        // ===== TMA producer: the whole warp walks the (warp-uniform) loop, one elected lane issues =====
+        if (P.b_resident && ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(b_full, (uint32_t)(n_bchunks * NF * P.KC * 2));
+            for (int t9 = 0; t9 < 9; ++t9)
+                for (int ch = 0; ch < chunks; ++ch)
+                    ptx::tma_load_3d(smem_base + (t9 * chunks + ch) * P.b_bytes, &map_b, b_full, ch * P.KC, 0, t9);
+        }
+        __syncwarp();
+        const int yz = P.Yp * P.Zp;
+        const uint32_t tx = (uint32_t)(P.TY * BM * P.KC * 2) + (P.b_resident ? 0u : (uint32_t)(P.TY * NF * P.KC * 2));
+        const int ny = 3 / P.TY;  // ky steps walked by the producer (1 when a stage holds all three)
+        uint32_t s = 0, ph = 1;   // ring position and the parity of "slot is free"
+        for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+            const int q0 = tile * ROWS_OUT - 1 + P.pad_rows;
+            for (int kx = 0; kx < 3; ++kx) {
+                for (int kyi = 0; kyi < ny; ++kyi) {
+                    const int row = q0 + (kx - 1) * yz + (kyi - 1) * P.Zp;
+                    for (int ch = 0; ch < chunks; ++ch) {
+                        ptx::mbar_wait(empty_bar + 8 * s, ph);
+                        if (ptx::elect_one()) {
+                            const uint32_t a_dst = stage_base + s * stage_bytes;
+                            ptx::mbar_arrive_expect_tx(full_bar + 8 * s, tx);
+                            // {c, r, w, ky}: TY x (4 groups of 32 rows overlapping by two)
+                            ptx::tma_load_4d(a_dst, &map_a, full_bar + 8 * s, ch * P.KC, row, 0, 0);
+                            if (!P.b_resident)
+                                ptx::tma_load_3d(a_dst + P.TY * P.a_bytes, &map_b, full_bar + 8 * s, ch * P.KC, 0, kx * 3 + kyi);
+                        }
+                        __syncwarp();
+                        if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(BM, (uint32_t)NF);
-            const uint32_t row_bytes = (uint32_t)P.KC * 2u;
-            const int kk = P.KC / 16;
-            if (P.b_resident) {
-                ptx::mbar_wait(b_full, 0);
-                ptx::tc_fence_after();
-            }
-            int it = 0, local = 0;
-            for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++local) {
-                const int as = local & 1;
-                const uint32_t aph = (uint32_t)(local >> 1) & 1u;
-                ptx::mbar_wait(acc_empty + 8 * as, aph ^ 1u);  // epilogue has drained this accumulator stage
-                ptx::tc_fence_after();
-                const uint32_t d_addr = tmem_d + (uint32_t)(as * P.tmem_half);
-                for (int ki = 0; ki < k_iters; ++ki, ++it) {
-                    const int s = it % P.stages;
-                    const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
-                    ptx::mbar_wait(full_bar + 8 * s, ph);
-                    ptx::tc_fence_after();
-                    const uint32_t a_src = stage_base + s * stage_bytes;
-                    const uint32_t b_src = P.b_resident ? smem_base + ki * P.b_bytes : a_src + P.a_bytes;
-                    const uint64_t a_desc = ptx::umma_smem_desc(a_src, row_bytes);
-                    const uint64_t b_desc = ptx::umma_smem_desc(b_src, row_bytes);
-                    for (int k = 0; k < kk; ++k)
-                        ptx::umma_f16(d_addr, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (ki | k) != 0);
-                    ptx::umma_commit(empty_bar + 8 * s);
+        // ===== MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit =====
+        const uint32_t idesc = ptx::umma_idesc_bf16(BM, (uint32_t)NF);
+        const uint32_t row_bytes = (uint32_t)P.KC * 2u;
+        const int kk = P.KC / 16;
+        const int ny = 3 / P.TY;
+        // descriptor templates: only the 14-bit start-address field changes inside the loops
+        const uint64_t desc0 = ptx::umma_smem_desc(0, row_bytes);
+        if (P.b_resident) {
+            ptx::mbar_wait(b_full, 0);
+            ptx::tc_fence_after();
+        }
+        uint32_t s = 0, ph = 0;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++local) {
+            const int as = local & 1;
+            const uint32_t aph = (uint32_t)(local >> 1) & 1u;
+            ptx::mbar_wait(acc_empty + 8 * as, aph ^ 1u);  // epilogue has drained this accumulator stage
+            ptx::tc_fence_after();
+            const uint32_t d_addr = tmem_d + (uint32_t)(as * P.tmem_half);
+            uint32_t accum = 0;
+            for (int kx = 0; kx < 3; ++kx) {
+                for (int kyi = 0; kyi < ny; ++kyi) {
+                    for (int ch = 0; ch < chunks; ++ch) {
+                        ptx::mbar_wait(full_bar + 8 * s, ph);
+                        ptx::tc_fence_after();
+                        if (ptx::elect_one()) {
+                            const uint32_t a_src = stage_base + s * stage_bytes;
+                            for (int ty = 0; ty < P.TY; ++ty) {
+                                const int t9 = kx * 3 + kyi + ty;
+                                const uint32_t b_src = P.b_resident ? smem_base + (t9 * chunks + ch) * P.b_bytes
+                                                                    : a_src + P.TY * P.a_bytes + ty * P.b_bytes;
+                                const uint64_t a_desc = desc0 | (uint64_t)(((a_src + ty * P.a_bytes) & 0x3FFFFu) >> 4);
+                                const uint64_t b_desc = desc0 | (uint64_t)((b_src & 0x3FFFFu) >> 4);
+                                for (int k = 0; k < kk; ++k) {
+                                    ptx::umma_f16(d_addr, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accum);
+                                    accum = 1;
+                                }
+                            }
+                            ptx::umma_commit(empty_bar + 8 * s);
+                        }
+                        accum = 1;
+                        __syncwarp();
+                        if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
+                    }
                 }
-                ptx::umma_commit(acc_full + 8 * as);
             }
+            if (ptx::elect_one()) ptx::umma_commit(acc_full + 8 * as);
+            __syncwarp();
         }
     } else {
         // ===== epilogue: 8 warps, lane group lg = warp % 4, column half = (warp - 2) / 4 =====
@@ -310,7 +337,7 @@ int launch_fold(const CUtensorMap& map_a, const CUtensorMap& map_b, const float*
 
 }  // namespace
 
-extern "C" int tdb_conv3d_bf16_fold(const void* in, int ld_in, const void* w_fold, const float* bias, void* out,
+extern "C" int tdb_conv3d_bf16_fold(const void* in, int ld_in, int pad_rows, const void* w_fold, const float* bias, void* out,
                                     int ld_out, int B, int X, int Y, int Z, int Cin, int Cout, double* gn_stats, int G,
                                     void* stream) {
     TDB_REQUIRE(in && w_fold && out, TDB_E_BADARG, "tdb_conv3d_bf16_fold: null pointer");
@@ -321,7 +348,10 @@ extern "C" int tdb_conv3d_bf16_fold(const void* in, int ld_in, const void* w_fol
     TDB_REQUIRE(!gn_stats || (G >= 1 && Cout % G == 0 && (Cout / G) % 2 == 0), TDB_E_UNSUPPORTED,
                 "tdb_conv3d_bf16_fold: fused GroupNorm moments need an even number of channels per group");
     Grid3 g(B, X, Y, Z);
-    TDB_REQUIRE(g.rows < (1ll << 31) - 4096, TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_fold: too many rows for 32-bit TMA coordinates");
+    TDB_REQUIRE(g.rows + 2ll * pad_rows < (1ll << 31) - 4096, TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_fold: too many rows for 32-bit TMA coordinates");
+    TDB_REQUIRE(pad_rows >= g.Yp * g.Zp + 2 * g.Zp + 256, TDB_E_BADARG,
+                "tdb_conv3d_bf16_fold: pad_rows=%d, need >= Yp*Zp + 2*Zp + 256 = %d readable rows around the grid", pad_rows,
+                g.Yp * g.Zp + 2 * g.Zp + 256);
     if (g_num_sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
@@ -338,15 +368,18 @@ extern "C" int tdb_conv3d_bf16_fold(const void* in, int ld_in, const void* w_fol
     P.by_y = FastDiv((uint32_t)g.Yp);
     P.Cin = Cin;
     P.KC = Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 16);
+    P.pad_rows = pad_rows;
     const int NF = 3 * Cout;
-    auto up1k = [](int v) { return (v + 1023) & ~1023; };
-    P.a_bytes = up1k(BM * P.KC * 2);
-    P.b_bytes = up1k(NF * P.KC * 2);
-    const int k_iters = 9 * (Cin / P.KC);
-    const int budget = 222 * 1024;  // dynamic smem we allow ourselves (227 KB max, minus static + alignment slack)
-    P.b_resident = (int64_t)k_iters * P.b_bytes <= 112 * 1024 ? 1 : 0;
-    const int stage_bytes = P.a_bytes + (P.b_resident ? 0 : P.b_bytes);
-    int stages = (budget - (P.b_resident ? k_iters * P.b_bytes : 0)) / stage_bytes;
+    P.a_bytes = BM * P.KC * 2;   // multiples of the swizzle atom (8 rows): tiles pack densely
+    P.b_bytes = NF * P.KC * 2;
+    const int n_bchunks = 9 * (Cin / P.KC);
+    const int budget = 221 * 1024;  // dynamic smem we allow ourselves (227 KB max, minus static + alignment slack)
+    P.b_resident = (int64_t)n_bchunks * P.b_bytes <= 112 * 1024 ? 1 : 0;
+    const int resident_bytes = P.b_resident ? n_bchunks * P.b_bytes : 0;
+    const int unit = P.a_bytes + (P.b_resident ? 0 : P.b_bytes);
+    // three ky taps per stage (one TMA box, 3x fewer barrier round trips) when >= 4 such stages fit
+    P.TY = (budget - resident_bytes) / (3 * unit) >= 4 ? 3 : 1;
+    int stages = (budget - resident_bytes) / (P.TY * unit);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     TDB_REQUIRE(stages >= 2, TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_fold: tiles do not fit in shared memory");
     P.stages = stages;
@@ -359,13 +392,26 @@ extern "C" int tdb_conv3d_bf16_fold(const void* in, int ld_in, const void* w_fol
 
     CUtensorMap map_a, map_b;
     TDB_REQUIRE(encode_fn() != nullptr, TDB_E_NODEVICE, "tdb_conv3d_bf16_fold: cuTensorMapEncodeTiled unavailable (no driver)");
-    // A: 32-row boxes (one per TMEM lane group); B: one box of all 3*Cout folded rows
-    TDB_REQUIRE(make_map_2d_bf16(&map_a, in, (uint64_t)Cin, (uint64_t)g.rows, (uint64_t)ld_in, (uint32_t)P.KC, 32), TDB_E_BADARG,
-                "tdb_conv3d_bf16_fold: tensor map (activations) rejected");
-    TDB_REQUIRE(make_map_2d_bf16(&map_b, w_fold, (uint64_t)9 * Cin, (uint64_t)NF, (uint64_t)9 * Cin, (uint32_t)P.KC, (uint32_t)NF),
-                TDB_E_BADARG, "tdb_conv3d_bf16_fold: tensor map (weights) rejected");
+    {
+        // A: [ky][w][r][c] overlapping view of the padded activation matrix (row 0 = grid row -pad_rows)
+        const bf16* base = (const bf16*)in - (int64_t)pad_rows * ld_in;
+        const uint64_t total_rows = (uint64_t)g.rows + 2ull * pad_rows;
+        const uint64_t dims[4] = {(uint64_t)Cin, total_rows - 90 - 2ull * g.Zp, 4, 3};
+        const uint64_t strides[3] = {(uint64_t)ld_in, 30ull * ld_in, (uint64_t)g.Zp * ld_in};
+        const uint32_t box[4] = {(uint32_t)P.KC, 32, 4, (uint32_t)P.TY};
+        TDB_REQUIRE(make_map_bf16(&map_a, base, 4, dims, strides, box), TDB_E_BADARG,
+                    "tdb_conv3d_bf16_fold: tensor map (activations) rejected");
+    }
+    {
+        // B: [tap9][n'][ci] view of the folded weights [3*Cout][9*Cin]
+        const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)NF, 9};
+        const uint64_t strides[2] = {9ull * Cin, (uint64_t)Cin};
+        const uint32_t box[3] = {(uint32_t)P.KC, (uint32_t)NF, (uint32_t)(P.b_resident ? 1 : P.TY)};
+        TDB_REQUIRE(make_map_bf16(&map_b, w_fold, 3, dims, strides, box), TDB_E_BADARG,
+                    "tdb_conv3d_bf16_fold: tensor map (weights) rejected");
+    }
 
-    const size_t smem = (size_t)(P.b_resident ? k_iters * P.b_bytes : 0) + (size_t)stages * stage_bytes + 1024;
+    const size_t smem = (size_t)resident_bytes + (size_t)stages * P.TY * unit + 1024;
     cudaStream_t s = (cudaStream_t)stream;
     if (Cout == 16) return launch_fold<16>(map_a, map_b, bias, (bf16*)out, gn_stats, P, smem, s);
     if (Cout == 32) return launch_fold<32>(map_a, map_b, bias, (bf16*)out, gn_stats, P, smem, s);

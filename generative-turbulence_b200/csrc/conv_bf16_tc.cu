@@ -93,48 +93,53 @@ conv3d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const uint32_t tmem_d = tmem_base_slot;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            const int yz = P.Yp * P.Zp;
-            int it = 0;
-            for (int tap = 0; tap < P.ntaps; ++tap) {
-                int64_t delta = 0;
-                if (P.ntaps == 27) delta = (int64_t)(tap / 9 - 1) * yz + (int64_t)((tap / 3) % 3 - 1) * P.Zp + (tap % 3 - 1);
-                const int row = (int)(p0 + delta);
-                for (int ch = 0; ch < chunks; ++ch, ++it) {
-                    const int s = it % P.stages;
-                    const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
-                    ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1u);
+        // ===== TMA producer: warp-uniform loop, one elected lane issues =====
+        const int yz = P.Yp * P.Zp;
+        const uint32_t tx = (uint32_t)((BM + P.BN) * P.KC * 2);
+        uint32_t s = 0, ph = 1;
+        for (int tap = 0; tap < P.ntaps; ++tap) {
+            int64_t delta = 0;
+            if (P.ntaps == 27) delta = (int64_t)(tap / 9 - 1) * yz + (int64_t)((tap / 3) % 3 - 1) * P.Zp + (tap % 3 - 1);
+            const int row = (int)(p0 + delta);
+            for (int ch = 0; ch < chunks; ++ch) {
+                ptx::mbar_wait(empty_bar + 8 * s, ph);
+                if (ptx::elect_one()) {
                     const uint32_t a_dst = smem_base + s * stage_bytes;
-                    const uint32_t b_dst = a_dst + P.a_bytes;
-                    ptx::mbar_arrive_expect_tx(full_bar + 8 * s, (uint32_t)((BM + P.BN) * P.KC * 2));
+                    ptx::mbar_arrive_expect_tx(full_bar + 8 * s, tx);
                     ptx::tma_load_2d(a_dst, &map_a, full_bar + 8 * s, ch * P.KC, row);
-                    ptx::tma_load_2d(b_dst, &map_b, full_bar + 8 * s, tap * P.Cin + ch * P.KC, n0);
+                    ptx::tma_load_2d(a_dst + P.a_bytes, &map_b, full_bar + 8 * s, tap * P.Cin + ch * P.KC, n0);
                 }
+                __syncwarp();
+                if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(BM, (uint32_t)P.BN);
-            const uint32_t row_bytes = (uint32_t)P.KC * 2u;
-            const int kk = P.KC / 16;
-            for (int it = 0; it < k_iters; ++it) {
-                const int s = it % P.stages;
-                const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
-                ptx::mbar_wait(full_bar + 8 * s, ph);
-                ptx::tc_fence_after();
+        // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
+        const uint32_t idesc = ptx::umma_idesc_bf16(BM, (uint32_t)P.BN);
+        const uint32_t row_bytes = (uint32_t)P.KC * 2u;
+        const uint64_t desc0 = ptx::umma_smem_desc(0, row_bytes);
+        const int kk = P.KC / 16;
+        uint32_t s = 0, ph = 0, accum = 0;
+        for (int it = 0; it < k_iters; ++it) {
+            ptx::mbar_wait(full_bar + 8 * s, ph);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
                 const uint32_t a_src = smem_base + s * stage_bytes;
-                const uint64_t a_desc = ptx::umma_smem_desc(a_src, row_bytes);
-                const uint64_t b_desc = ptx::umma_smem_desc(a_src + P.a_bytes, row_bytes);
+                const uint64_t a_desc = desc0 | (uint64_t)((a_src & 0x3FFFFu) >> 4);
+                const uint64_t b_desc = desc0 | (uint64_t)(((a_src + P.a_bytes) & 0x3FFFFu) >> 4);
                 for (int k = 0; k < kk; ++k) {
                     // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in 16-byte units
-                    ptx::umma_f16(tmem_d, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (it | k) != 0);
+                    ptx::umma_f16(tmem_d, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accum);
+                    accum = 1;
                 }
                 ptx::umma_commit(empty_bar + 8 * s);  // smem slot reusable once these MMAs retire
             }
-            ptx::umma_commit(accum_bar);  // accumulator complete
+            accum = 1;
+            __syncwarp();
+            if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
         }
+        if (ptx::elect_one()) ptx::umma_commit(accum_bar);  // accumulator complete
+        __syncwarp();
     } else {
         // ===== epilogue: TMEM -> registers -> global =====
         const int lg = warp % 4;  // TMEM lane group this warp may access

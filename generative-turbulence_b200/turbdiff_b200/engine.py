@@ -130,6 +130,11 @@ class DenoiserEngine:
         self._wcache, self._wversion = w, ver
         return w
 
+    @staticmethod
+    def pad_rows(size) -> int:
+        X, Y, Z = size
+        return (Y + 2) * (Z + 2) + 2 * (Z + 2) + 256
+
     def use_fold(self, ntaps, cout) -> bool:
         """Narrow 3x3x3 layers run the kz-folded persistent kernel (tdb_conv3d_bf16_fold)."""
         return self.precision == "bf16" and self.fold and ntaps == 27 and cout in (16, 32, 64)
@@ -146,8 +151,12 @@ class DenoiserEngine:
         td = self.tdtype
 
         def grid(level, C):
+            # every halo grid is allocated with `pad` zero rows in front and behind: the folded
+            # convolution reads its row-shifted tiles through an overlapping TMA view (no OOB fill)
             X, Y, Z = sizes[level]
-            return View(torch.zeros((B, X + 2, Y + 2, Z + 2, C), dtype=td, device=device), 0, C, level)
+            rows, pad = B * (X + 2) * (Y + 2) * (Z + 2), self.pad_rows(sizes[level])
+            flat = torch.zeros((rows + 2 * pad, C), dtype=td, device=device)
+            return View(flat[pad : pad + rows].view(B, X + 2, Y + 2, Z + 2, C), 0, C, level)
 
         p = {"sizes": sizes, "B": B}
         c_in0 = dim + (dim if m.c_local_features > 0 else 0)
@@ -208,8 +217,8 @@ class DenoiserEngine:
         if self.precision == "fp32":
             call("tdb_conv3d_f32", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ntaps, s)
         elif self.use_fold(ntaps, out.C):
-            call("tdb_conv3d_bf16_fold", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C,
-                 ptr(stats), G, s)
+            call("tdb_conv3d_bf16_fold", x.ptr, x.ld, self.pad_rows((X, Y, Z)), w.data_ptr(), ptr(bias), out.ptr, out.ld,
+                 B, X, Y, Z, x.C, out.C, ptr(stats), G, s)
         else:
             call("tdb_conv3d_bf16", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ntaps,
                  ptr(stats), G, s)

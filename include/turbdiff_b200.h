@@ -95,8 +95,11 @@ TDB_API int tdb_conv3d_bf16(const void* in, int ld_in, const void* w, const floa
 /* Same convolution (3x3x3 only) for narrow layers, Cout in {16,32,64}: the kz filter axis is folded
  * into the GEMM N dimension (9 row-shifted A boxes instead of 27, 3x wider MMAs), persistent CTAs,
  * double-buffered TMEM accumulators, weights resident in shared memory when they fit.
- * w_fold: packed [3*Cout][9*Cin] bf16, row = kz*Cout + co, col = (kx*3+ky)*Cin + ci. */
-TDB_API int tdb_conv3d_bf16_fold(const void* in, int ld_in, const void* w_fold, const float* bias, void* out,
+ * w_fold: packed [3*Cout][9*Cin] bf16, row = kz*Cout + co, col = (kx*3+ky)*Cin + ci.
+ * The activation tiles are fetched through an overlapping 4-D TMA view that cannot use TMA's
+ * out-of-bounds fill: `in` must be preceded AND followed by `pad_rows` >= Yp*Zp + 2*Zp + 256 rows
+ * (of ld_in elements) of readable memory; their contents never reach a stored output. */
+TDB_API int tdb_conv3d_bf16_fold(const void* in, int ld_in, int pad_rows, const void* w_fold, const float* bias, void* out,
                          int ld_out, int B, int X, int Y, int Z, int Cin, int Cout, double* gn_stats,
                          int G, void* stream);
 

@@ -110,12 +110,13 @@ def test_conv3d_bf16_kz_folded(lib, case, fused_stats):
     x = gen(B, Cin, X, Y, Z, seed=1).bfloat16().float()
     w = gen(Cout, Cin, 3, 3, 3, seed=2, scale=1 / math.sqrt(Cin * 27)).bfloat16().float()
     b = gen(Cout, seed=3, scale=0.1)
-    xin = to_halo(x, dtype=torch.bfloat16)
+    pad = (Y + 2) * (Z + 2) + 2 * (Z + 2) + 256
+    xin = to_halo(x, dtype=torch.bfloat16, pad_rows=pad)
     wf = w.permute(4, 0, 2, 3, 1).reshape(3 * Cout, 9 * Cin).contiguous().bfloat16()
     out = torch.zeros((B, X + 2, Y + 2, Z + 2, Cout), device="cuda", dtype=torch.bfloat16)
     G = 8
     stats = torch.zeros((B, G, 2), dtype=torch.float64, device="cuda")
-    lib.call("tdb_conv3d_bf16_fold", xin.data_ptr(), Cin, wf.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
+    lib.call("tdb_conv3d_bf16_fold", xin.data_ptr(), Cin, pad, wf.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
              stats.data_ptr() if fused_stats else None, G, lib.stream_ptr())
     torch.cuda.synchronize()
     want = _conv_ref(x.double().cpu(), w.double().cpu(), b.double().cpu(), 27)

@@ -15,14 +15,19 @@ def rel_l2(a, b) -> float:
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def to_halo(x: torch.Tensor, dtype=torch.float32, ld: int | None = None, c0: int = 0) -> torch.Tensor:
-    """NCDHW -> halo grid [B, X+2, Y+2, Z+2, ld] (replicate halo), channels at [c0, c0+C)."""
+def to_halo(x: torch.Tensor, dtype=torch.float32, ld: int | None = None, c0: int = 0, pad_rows: int = 0) -> torch.Tensor:
+    """NCDHW -> halo grid [B, X+2, Y+2, Z+2, ld] (replicate halo), channels at [c0, c0+C).
+    pad_rows > 0: the grid is a view into a buffer with that many NaN rows in front and behind
+    (tdb_conv3d_bf16_fold reads, but must never use, such padding)."""
     B, C = x.shape[:2]
     xp = F.pad(x.float(), (1, 1, 1, 1, 1, 1), mode="replicate").permute(0, 2, 3, 4, 1)
     ld = ld or C
-    out = torch.zeros((*xp.shape[:4], ld), dtype=dtype, device=x.device)
+    rows = xp.shape[0] * xp.shape[1] * xp.shape[2] * xp.shape[3]
+    flat = torch.full((rows + 2 * pad_rows, ld), float("nan") if pad_rows else 0.0, dtype=dtype, device=x.device)
+    out = flat[pad_rows : pad_rows + rows].view(*xp.shape[:4], ld)
+    out.zero_()
     out[..., c0 : c0 + C] = xp.to(dtype)
-    return out.contiguous()
+    return out
 
 
 def from_halo(g: torch.Tensor, C: int | None = None, c0: int = 0) -> torch.Tensor:
