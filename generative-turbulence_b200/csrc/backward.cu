@@ -1,0 +1,636 @@
+// Backward kernels of the denoiser (training path, ddpm.py:833-882 through autograd in the reference).
+// Gradients travel as halo grids in the storage type of the forward activations.  Convolution
+// input-gradients are produced by the forward convolution kernels themselves (transposed, tap-reversed
+// weights over a zero-halo output gradient, all rows stored); the kernels here provide the rest:
+//   tdb_halo_fold            adjoint of halo materialisation: halo rows are added onto the border voxels
+//   tdb_pointwise_bwd_reduce per-(sample, channel) sums  A1 = sum g_u,  A2 = sum g_u * xhat
+//   tdb_pointwise_bwd_apply  GroupNorm/FiLM/SiLU input gradient from g_out and the sums
+//   tdb_conv3d_wgrad         weight gradient of the 3x3x3 / 1x1x1 convolutions (fp32 accumulate)
+//   tdb_trilinear_bwd        transpose of the align_corners trilinear resampling (gather form)
+//   tdb_attention_bwd        softmax-attention backward per (sample, head)
+//   tdb_cl_nc_outer          out[c][f] = sum_{b,v} G[b,v][c] * Q[b][f][v]  (1x1 encoder/decoder weight grads)
+#include "common.cuh"
+
+using namespace tdb;
+using bf16 = __nv_bfloat16;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct RowSplit {
+    FastDiv by_z, by_y;
+    __device__ __forceinline__ void operator()(uint32_t r, int& xp, int& yp, int& zp) const {
+        uint32_t q, zz, xx, yy;
+        by_z.divmod(r, q, zz);
+        by_y.divmod(q, xx, yy);
+        xp = (int)xx; yp = (int)yy; zp = (int)zz;
+    }
+};
+RowSplit make_split(const Grid3& g) {
+    RowSplit s;
+    s.by_z = FastDiv((uint32_t)g.Zp);
+    s.by_y = FastDiv((uint32_t)g.Yp);
+    return s;
+}
+int blocks_per_sample(int64_t items_per_sample, int B) {
+    int64_t blocks = ceil_div(items_per_sample, kThreads);
+    int64_t cap = (148 * 16) / (B < 1 ? 1 : B);
+    if (cap < 8) cap = 8;
+    return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+// ---------------------------------------------------------------- halo fold
+// haloed coordinates of the images of interior coordinate c (1..n) along one axis
+__device__ __forceinline__ int axis_images(int c, int n, int (&img)[3]) {
+    int k = 0;
+    img[k++] = c;
+    if (c == 1) img[k++] = 0;
+    if (c == n) img[k++] = n + 1;
+    return k;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+halo_fold_kernel(T* __restrict__ g, int ld, Grid3 gr, RowSplit split, int chunks) {
+    constexpr int N = Vec<T>::N;
+    const int b = blockIdx.y;
+    const int vox_step = kThreads / chunks;
+    const int ch = threadIdx.x % chunks, lane_vox = threadIdx.x / chunks;
+    if (lane_vox >= vox_step) return;
+    const int c0 = ch * N;
+    for (uint32_t r = blockIdx.x * vox_step + lane_vox; r < (uint32_t)gr.vox_p; r += gridDim.x * vox_step) {
+        int xp, yp, zp;
+        split(r, xp, yp, zp);
+        const bool interior = xp >= 1 && xp <= gr.X && yp >= 1 && yp <= gr.Y && zp >= 1 && zp <= gr.Z;
+        const bool border = xp == 1 || xp == gr.X || yp == 1 || yp == gr.Y || zp == 1 || zp == gr.Z;
+        if (!interior || !border) continue;
+        int ix[3], iy[3], iz[3];
+        const int nx = axis_images(xp, gr.X, ix), ny = axis_images(yp, gr.Y, iy), nz = axis_images(zp, gr.Z, iz);
+        float acc[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc[i] = 0.0f;
+        for (int a = 0; a < nx; ++a)
+            for (int bb = 0; bb < ny; ++bb)
+                for (int c = 0; c < nz; ++c) {
+                    float v[N];
+                    Vec<T>::load(g + ((int64_t)b * gr.vox_p + ((int64_t)ix[a] * gr.Yp + iy[bb]) * gr.Zp + iz[c]) * ld + c0, v);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) acc[i] += v[i];
+                }
+        Vec<T>::store(g + ((int64_t)b * gr.vox_p + r) * ld + c0, acc);
+    }
+}
+
+// ---------------------------------------------------------------- pointwise backward
+__device__ __forceinline__ float dsilu(float u) {
+    const float s = 1.0f / (1.0f + expf(-u));
+    return s * (1.0f + u * (1.0f - s));
+}
+
+struct PwCoef {  // per channel: forward affine u = a*x + o; xhat = (x - mean) * rstd
+    float a, o, mean, rstd, k;  // k = gamma * (scale + 1)
+};
+
+__device__ __forceinline__ PwCoef pw_coef(int b, int c, int C, int G, const double* stats, const float* gamma, const float* beta,
+                                          const float* film, int film_ld, double inv_n, float eps) {
+    PwCoef r{1.0f, 0.0f, 0.0f, 1.0f, 1.0f};
+    if (stats) {
+        const int gi = c / (C / G);
+        const double mean = stats[((int64_t)b * G + gi) * 2] * inv_n;
+        double var = stats[((int64_t)b * G + gi) * 2 + 1] * inv_n - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        r.rstd = (float)(1.0 / sqrt(var + (double)eps));
+        r.mean = (float)mean;
+        r.a = r.rstd * gamma[c];
+        r.o = beta[c] - r.mean * r.a;
+        r.k = gamma[c];
+    }
+    if (film) {
+        const float sc = film[(int64_t)b * film_ld + c] + 1.0f;
+        r.a *= sc;
+        r.o = fmaf(r.o, sc, film[(int64_t)b * film_ld + C + c]);
+        r.k *= sc;
+    }
+    return r;
+}
+
+// red[b][c] = (sum g_u, sum g_u*xhat) over interior voxels, double atomics (pre-zeroed)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+pw_bwd_reduce_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict__ raw, int ld_raw,
+                     const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ film, int film_ld, double* __restrict__ red, Grid3 gr, int C, int G, float eps,
+                     unsigned flags, int vox_per_block) {
+    constexpr int N = Vec<T>::N;
+    const int b = blockIdx.y;
+    const int chunks = C / N;
+    const int vox_step = kThreads / chunks;
+    const int ch = threadIdx.x % chunks, lane_vox = threadIdx.x / chunks;
+    if (lane_vox >= vox_step) return;
+    const int c0 = ch * N;
+    const double inv_n = 1.0 / ((double)(C / G) * gr.X * gr.Y * gr.Z);
+    PwCoef k[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) k[i] = pw_coef(b, c0 + i, C, G, stats, gamma, beta, film, film_ld, inv_n, eps);
+    const bool act = flags & TDB_PW_SILU;
+    const int64_t nvox = (int64_t)gr.X * gr.Y * gr.Z;
+    const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
+    const int64_t v_end = min(nvox, v_begin + vox_per_block);
+    float a1[N], a2[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) a1[i] = a2[i] = 0.0f;
+    for (int64_t v = v_begin + lane_vox; v < v_end; v += vox_step) {
+        const int z = (int)(v % gr.Z);
+        const int y = (int)((v / gr.Z) % gr.Y);
+        const int x = (int)(v / ((int64_t)gr.Z * gr.Y));
+        const int64_t row = gr.row(b, x, y, z);
+        float xv[N], gv[N];
+        Vec<T>::load(raw + row * ld_raw + c0, xv);
+        Vec<T>::load(g_out + row * ld_g + c0, gv);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const float u = fmaf(k[i].a, xv[i], k[i].o);
+            const float gu = act ? gv[i] * dsilu(u) : gv[i];
+            a1[i] += gu;
+            a2[i] = fmaf(gu, (xv[i] - k[i].mean) * k[i].rstd, a2[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        atomicAdd(&red[((int64_t)b * C + c0 + i) * 2], (double)a1[i]);
+        atomicAdd(&red[((int64_t)b * C + c0 + i) * 2 + 1], (double)a2[i]);
+    }
+}
+
+// d_raw = rstd * (k*g_u - m1 - xhat*m2) on interior rows, 0 on halo rows.  grp[b][g] = (m1, m2) fp32.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+pw_bwd_apply_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict__ raw, int ld_raw,
+                    const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const float* __restrict__ film, int film_ld, const float* __restrict__ grp, T* __restrict__ d_raw, int ld_d,
+                    Grid3 gr, int C, int G, float eps, unsigned flags, RowSplit split, int chunks) {
+    constexpr int N = Vec<T>::N;
+    const int b = blockIdx.y;
+    const int vox_step = kThreads / chunks;
+    const int ch = threadIdx.x % chunks, lane_vox = threadIdx.x / chunks;
+    if (lane_vox >= vox_step) return;
+    const int c0 = ch * N;
+    const double inv_n = 1.0 / ((double)(C / G) * gr.X * gr.Y * gr.Z);
+    PwCoef k[N];
+    float m1[N], m2[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        k[i] = pw_coef(b, c0 + i, C, G, stats, gamma, beta, film, film_ld, inv_n, eps);
+        const int gi = (c0 + i) / (C / G);
+        m1[i] = stats ? grp[((int64_t)b * G + gi) * 2] : 0.0f;
+        m2[i] = stats ? grp[((int64_t)b * G + gi) * 2 + 1] : 0.0f;
+    }
+    const bool act = flags & TDB_PW_SILU;
+    for (uint32_t r = blockIdx.x * vox_step + lane_vox; r < (uint32_t)gr.vox_p; r += gridDim.x * vox_step) {
+        int xp, yp, zp;
+        split(r, xp, yp, zp);
+        const bool interior = xp >= 1 && xp <= gr.X && yp >= 1 && yp <= gr.Y && zp >= 1 && zp <= gr.Z;
+        const int64_t row = (int64_t)b * gr.vox_p + r;
+        float o[N];
+        if (interior) {
+            float xv[N], gv[N];
+            Vec<T>::load(raw + row * ld_raw + c0, xv);
+            Vec<T>::load(g_out + row * ld_g + c0, gv);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const float u = fmaf(k[i].a, xv[i], k[i].o);
+                const float gu = act ? gv[i] * dsilu(u) : gv[i];
+                const float xh = (xv[i] - k[i].mean) * k[i].rstd;
+                o[i] = stats ? k[i].rstd * (k[i].k * gu - m1[i] - xh * m2[i]) : gu;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) o[i] = 0.0f;
+        }
+        Vec<T>::store(d_raw + row * ld_d + c0, o);
+    }
+}
+
+// ---------------------------------------------------------------- conv weight gradient
+// dW[tap][ci][co] += sum_{p interior} in[p + delta(tap)][ci] * d_out[p][co]  (halo rows of d_out are masked).
+// Block = one (tap, 64x64 tile) over a slice of rows; 4x4 register tile per thread; fp32 atomics at the end.
+struct InteriorTest {
+    FastDiv by_vox, by_z, by_y;
+    int X, Y, Z;
+    __device__ __forceinline__ bool operator()(int64_t p) const {
+        uint32_t bb, r, q, zp, xp, yp;
+        by_vox.divmod((uint32_t)p, bb, r);
+        by_z.divmod(r, q, zp);
+        by_y.divmod(q, xp, yp);
+        return xp >= 1u && xp <= (uint32_t)X && yp >= 1u && yp <= (uint32_t)Y && zp >= 1u && zp <= (uint32_t)Z;
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_wgrad_kernel(const T* __restrict__ in, int ld_in, const T* __restrict__ d_out, int ld_do, float* __restrict__ dw,
+                  int64_t rows, int yz_p, int z_p, int Cin, int Cout, int ntaps, int ci_tiles, int co_tiles, int rows_per_block,
+                  InteriorTest interior) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64 + 4];
+    const int tile = blockIdx.y;
+    const int tap = tile / (ci_tiles * co_tiles);
+    const int ci0 = ((tile / co_tiles) % ci_tiles) * 64;
+    const int co0 = (tile % co_tiles) * 64;
+    int64_t delta = 0;
+    if (ntaps == 27) delta = (int64_t)(tap / 9 - 1) * yz_p + (int64_t)((tap / 3) % 3 - 1) * z_p + (tap % 3 - 1);
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int lr = tid / 16, lc = (tid % 16) * 4;  // loader: row 0..15, 4 consecutive channels
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r_end = min(rows, r_begin + rows_per_block);
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += 16) {
+        const int64_t p = r0 + lr;
+        float a[4] = {0.f, 0.f, 0.f, 0.f}, bq[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p < r_end && interior(p)) {
+            const int64_t q = p + delta;
+            if (q >= 0 && q < rows) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (ci0 + lc + i < Cin) a[i] = (float)in[q * ld_in + ci0 + lc + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (co0 + lc + i < Cout) bq[i] = (float)d_out[p * ld_do + co0 + lc + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            As[lr][lc + i] = a[i];
+            Bs[lr][lc + i] = bq[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ci = ci0 + ty * 4 + i, co = co0 + tx * 4 + j;
+            if (ci < Cin && co < Cout) atomicAdd(&dw[((int64_t)tap * Cin + ci) * Cout + co], acc[i][j]);
+        }
+}
+
+// ---------------------------------------------------------------- trilinear backward (gather)
+struct Lerp {
+    int i0, i1;
+    float l0, l1;
+};
+__device__ __forceinline__ Lerp axis_lerp(int o, int n_in, float scale) {
+    const float src = scale * (float)o;
+    Lerp r;
+    r.i0 = min((int)src, n_in - 1);
+    r.i1 = r.i0 + (r.i0 < n_in - 1 ? 1 : 0);
+    r.l1 = src - (float)r.i0;
+    r.l0 = 1.0f - r.l1;
+    return r;
+}
+// outputs o (and their weights) that read input index i along one axis (host guarantees <= 12: scale >= 0.2)
+__device__ __forceinline__ int axis_sources(int i, int n_in, int n_out, float scale, int (&oo)[12], float (&ww)[12]) {
+    int k = 0;
+    int lo = 0, hi = n_out - 1;
+    if (scale > 0.0f) {
+        lo = max(0, (int)floorf((float)(i - 1) / scale) - 1);
+        hi = min(n_out - 1, (int)ceilf((float)(i + 1) / scale) + 1);
+    }
+    for (int o = lo; o <= hi && k < 12; ++o) {
+        const Lerp l = axis_lerp(o, n_in, scale);
+        float w = 0.0f;
+        if (l.i0 == i) w += l.l0;
+        if (l.i1 == i) w += l.l1;
+        if (w != 0.0f) {
+            oo[k] = o;
+            ww[k] = w;
+            ++k;
+        }
+    }
+    return k;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+trilinear_bwd_kernel(const T* __restrict__ g_out, int ld_g, Grid3 go, T* __restrict__ d_in, int ld_d, Grid3 gi, int C,
+                     RowSplit split, int chunks, float sx, float sy, float sz) {
+    constexpr int N = Vec<T>::N;
+    const int b = blockIdx.y;
+    const int vox_step = kThreads / chunks;
+    const int ch = threadIdx.x % chunks, lane_vox = threadIdx.x / chunks;
+    if (lane_vox >= vox_step) return;
+    const int c0 = ch * N;
+    for (uint32_t r = blockIdx.x * vox_step + lane_vox; r < (uint32_t)gi.vox_p; r += gridDim.x * vox_step) {
+        int xp, yp, zp;
+        split(r, xp, yp, zp);
+        const bool interior = xp >= 1 && xp <= gi.X && yp >= 1 && yp <= gi.Y && zp >= 1 && zp <= gi.Z;
+        float acc[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc[i] = 0.0f;
+        if (interior) {
+            int ox[12], oy[12], oz[12];
+            float wx[12], wy[12], wz[12];
+            const int nx = axis_sources(xp - 1, gi.X, go.X, sx, ox, wx);
+            const int ny = axis_sources(yp - 1, gi.Y, go.Y, sy, oy, wy);
+            const int nz = axis_sources(zp - 1, gi.Z, go.Z, sz, oz, wz);
+            for (int a = 0; a < nx; ++a)
+                for (int bb = 0; bb < ny; ++bb)
+                    for (int c = 0; c < nz; ++c) {
+                        const float w = wx[a] * wy[bb] * wz[c];
+                        float v[N];
+                        Vec<T>::load(g_out + go.row(b, ox[a], oy[bb], oz[c]) * ld_g + c0, v);
+#pragma unroll
+                        for (int i = 0; i < N; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+                    }
+        }
+        Vec<T>::store(d_in + ((int64_t)b * gi.vox_p + r) * ld_d + c0, acc);
+    }
+}
+
+// ---------------------------------------------------------------- attention backward
+// One CTA per (sample, head); q,k,v,dO and the S x S probability / score-gradient matrices live in smem.
+template <typename T>
+__global__ void __launch_bounds__(256)
+attention_bwd_kernel(const T* __restrict__ qkv, int ld_qkv, const T* __restrict__ d_out, int ld_do, T* __restrict__ d_qkv,
+                     int ld_dq, Grid3 g, int heads, int S) {
+    constexpr int DH = 32;
+    extern __shared__ float sm[];
+    float* sq = sm;
+    float* sk = sq + (size_t)S * (DH + 1);
+    float* sv = sk + (size_t)S * (DH + 1);
+    float* sdo = sv + (size_t)S * (DH + 1);
+    float* sp = sdo + (size_t)S * (DH + 1);  // [S][S+1] probabilities
+    float* sds = sp + (size_t)S * (S + 1);   // [S][S+1] dS
+    const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+    const int hid = heads * DH;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nwarps = blockDim.x / 32;
+    const float scale = rsqrtf((float)DH);
+    auto row_of = [&](int s) {
+        const int z = s % g.Z, y = (s / g.Z) % g.Y, x = s / (g.Z * g.Y);
+        return g.row(b, x, y, z);
+    };
+    for (int i = threadIdx.x; i < S * DH; i += blockDim.x) {
+        const int s = i / DH, d = i % DH;
+        const int64_t row = row_of(s);
+        const T* p = qkv + row * ld_qkv + h * DH + d;
+        sq[s * (DH + 1) + d] = (float)p[0];
+        sk[s * (DH + 1) + d] = (float)p[hid];
+        sv[s * (DH + 1) + d] = (float)p[2 * hid];
+        sdo[s * (DH + 1) + d] = (float)d_out[row * ld_do + h * DH + d];
+    }
+    __syncthreads();
+    // P and dS rows
+    for (int i = warp; i < S; i += nwarps) {
+        float mx = -INFINITY;
+        for (int j = lane; j < S; j += 32) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) acc = fmaf(sq[i * (DH + 1) + d], sk[j * (DH + 1) + d], acc);
+            acc *= scale;
+            sp[i * (S + 1) + j] = acc;
+            mx = fmaxf(mx, acc);
+        }
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int j = lane; j < S; j += 32) {
+            const float e = expf(sp[i * (S + 1) + j] - mx);
+            sp[i * (S + 1) + j] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        float dsum = 0.0f;
+        for (int j = lane; j < S; j += 32) {
+            const float p = sp[i * (S + 1) + j] * inv;
+            sp[i * (S + 1) + j] = p;
+            float dp = 0.0f;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) dp = fmaf(sdo[i * (DH + 1) + d], sv[j * (DH + 1) + d], dp);
+            sds[i * (S + 1) + j] = dp;
+            dsum = fmaf(p, dp, dsum);
+        }
+        dsum = warp_sum(dsum);
+        for (int j = lane; j < S; j += 32) sds[i * (S + 1) + j] = sp[i * (S + 1) + j] * (sds[i * (S + 1) + j] - dsum) * scale;
+    }
+    __syncthreads();
+    // dQ[i] = sum_j dS[i][j] K[j];  dK[j] = sum_i dS[i][j] Q[i];  dV[j] = sum_i P[i][j] dO[i]
+    for (int idx = threadIdx.x; idx < S * DH; idx += blockDim.x) {
+        const int s = idx / DH, d = idx % DH;
+        float dq = 0.0f, dk = 0.0f, dv = 0.0f;
+        for (int j = 0; j < S; ++j) {
+            dq = fmaf(sds[s * (S + 1) + j], sk[j * (DH + 1) + d], dq);
+            dk = fmaf(sds[j * (S + 1) + s], sq[j * (DH + 1) + d], dk);
+            dv = fmaf(sp[j * (S + 1) + s], sdo[j * (DH + 1) + d], dv);
+        }
+        T* o = d_qkv + row_of(s) * ld_dq + h * DH + d;
+        o[0] = (T)dq;
+        o[hid] = (T)dk;
+        o[2 * hid] = (T)dv;
+    }
+}
+
+// ---------------------------------------------------------------- channels-last x channels-first outer product
+// out[c][f] += sum_{b, v interior} G[b,v][c] * Q[b*q_bstride + f*nvox + v]   (thread = one (c,f) pair)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+cl_nc_outer_kernel(const T* __restrict__ G, int ld, const float* __restrict__ Q, int64_t q_bstride, float* __restrict__ out,
+                   Grid3 gr, int C, int F, int vox_per_block) {
+    const int b = blockIdx.y;
+    const int64_t nvox = (int64_t)gr.X * gr.Y * gr.Z;
+    const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
+    const int64_t v_end = min(nvox, v_begin + vox_per_block);
+    for (int pair = threadIdx.x; pair < C * F; pair += blockDim.x) {
+        const int c = pair % C, f = pair / C;
+        const float* q = Q + (int64_t)b * q_bstride + (int64_t)f * nvox;
+        float acc = 0.0f;
+        for (int64_t v = v_begin; v < v_end; ++v) {
+            const int z = (int)(v % gr.Z);
+            const int y = (int)((v / gr.Z) % gr.Y);
+            const int x = (int)(v / ((int64_t)gr.Z * gr.Y));
+            acc = fmaf((float)G[gr.row(b, x, y, z) * ld + c], __ldg(q + v), acc);
+        }
+        atomicAdd(&out[(int64_t)c * F + f], acc);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int tdb_halo_fold(void* g, int ld, int B, int X, int Y, int Z, int C, int dtype, void* stream) {
+    TDB_REQUIRE(g, TDB_E_BADARG, "tdb_halo_fold: null pointer");
+    const int n = dtype == TDB_BF16 ? 8 : 4;
+    TDB_REQUIRE(C % n == 0 && ld % n == 0 && C / n <= kThreads && aligned16(g), TDB_E_UNSUPPORTED, "tdb_halo_fold: C/ld must be multiples of %d", n);
+    Grid3 gr(B, X, Y, Z);
+    const int chunks = C / n;
+    dim3 grid((unsigned)blocks_per_sample(gr.vox_p * chunks, B), (unsigned)B);
+    if (dtype == TDB_BF16)
+        halo_fold_kernel<bf16><<<grid, kThreads, 0, (cudaStream_t)stream>>>((bf16*)g, ld, gr, make_split(gr), chunks);
+    else
+        halo_fold_kernel<float><<<grid, kThreads, 0, (cudaStream_t)stream>>>((float*)g, ld, gr, make_split(gr), chunks);
+    TDB_CHECK_LAUNCH("tdb_halo_fold");
+    return 0;
+}
+
+int tdb_pointwise_bwd_reduce(const void* g_out, int ld_g, const void* raw, int ld_raw, const double* stats, const float* gamma,
+                             const float* beta, const float* film, int film_ld, double* red, int B, int X, int Y, int Z, int C,
+                             int G, float eps, unsigned flags, int dtype, void* stream) {
+    TDB_REQUIRE(g_out && raw && red, TDB_E_BADARG, "tdb_pointwise_bwd_reduce: null pointer");
+    TDB_REQUIRE(!stats || (gamma && beta && G >= 1 && C % G == 0), TDB_E_BADARG, "tdb_pointwise_bwd_reduce: norm args");
+    const int n = dtype == TDB_BF16 ? 8 : 4;
+    TDB_REQUIRE(C % n == 0 && ld_g % n == 0 && ld_raw % n == 0 && C / n <= kThreads && aligned16(g_out) && aligned16(raw),
+                TDB_E_UNSUPPORTED, "tdb_pointwise_bwd_reduce: C/ld must be multiples of %d", n);
+    if (G < 1) G = 1;
+    Grid3 gr(B, X, Y, Z);
+    const int chunks = C / n;
+    const int vox_per_block = (kThreads / chunks) * 32;
+    dim3 grid((unsigned)ceil_div((int64_t)X * Y * Z, vox_per_block), (unsigned)B);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == TDB_BF16)
+        pw_bwd_reduce_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)g_out, ld_g, (const bf16*)raw, ld_raw, stats, gamma, beta,
+                                                              film, film_ld, red, gr, C, G, eps, flags, vox_per_block);
+    else
+        pw_bwd_reduce_kernel<float><<<grid, kThreads, 0, s>>>((const float*)g_out, ld_g, (const float*)raw, ld_raw, stats, gamma,
+                                                               beta, film, film_ld, red, gr, C, G, eps, flags, vox_per_block);
+    TDB_CHECK_LAUNCH("tdb_pointwise_bwd_reduce");
+    return 0;
+}
+
+int tdb_pointwise_bwd_apply(const void* g_out, int ld_g, const void* raw, int ld_raw, const double* stats, const float* gamma,
+                            const float* beta, const float* film, int film_ld, const float* grp, void* d_raw, int ld_d, int B,
+                            int X, int Y, int Z, int C, int G, float eps, unsigned flags, int dtype, void* stream) {
+    TDB_REQUIRE(g_out && raw && d_raw, TDB_E_BADARG, "tdb_pointwise_bwd_apply: null pointer");
+    TDB_REQUIRE(!stats || (gamma && beta && grp && G >= 1 && C % G == 0), TDB_E_BADARG, "tdb_pointwise_bwd_apply: norm args");
+    const int n = dtype == TDB_BF16 ? 8 : 4;
+    TDB_REQUIRE(C % n == 0 && ld_g % n == 0 && ld_raw % n == 0 && ld_d % n == 0 && C / n <= kThreads && aligned16(g_out) &&
+                    aligned16(raw) && aligned16(d_raw),
+                TDB_E_UNSUPPORTED, "tdb_pointwise_bwd_apply: C/ld must be multiples of %d", n);
+    if (G < 1) G = 1;
+    Grid3 gr(B, X, Y, Z);
+    const int chunks = C / n;
+    dim3 grid((unsigned)blocks_per_sample(gr.vox_p * chunks, B), (unsigned)B);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == TDB_BF16)
+        pw_bwd_apply_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)g_out, ld_g, (const bf16*)raw, ld_raw, stats, gamma, beta, film,
+                                                             film_ld, grp, (bf16*)d_raw, ld_d, gr, C, G, eps, flags, make_split(gr), chunks);
+    else
+        pw_bwd_apply_kernel<float><<<grid, kThreads, 0, s>>>((const float*)g_out, ld_g, (const float*)raw, ld_raw, stats, gamma, beta,
+                                                              film, film_ld, grp, (float*)d_raw, ld_d, gr, C, G, eps, flags,
+                                                              make_split(gr), chunks);
+    TDB_CHECK_LAUNCH("tdb_pointwise_bwd_apply");
+    return 0;
+}
+
+int tdb_conv3d_wgrad(const void* in, int ld_in, const void* d_out, int ld_do, float* dw, int B, int X, int Y, int Z, int Cin,
+                     int Cout, int ntaps, int dtype, void* stream) {
+    TDB_REQUIRE(in && d_out && dw, TDB_E_BADARG, "tdb_conv3d_wgrad: null pointer");
+    TDB_REQUIRE(ntaps == 1 || ntaps == 27, TDB_E_BADARG, "tdb_conv3d_wgrad: ntaps must be 1 or 27");
+    Grid3 g(B, X, Y, Z);
+    TDB_REQUIRE(g.rows < (1ll << 31), TDB_E_UNSUPPORTED, "tdb_conv3d_wgrad: too many rows");
+    InteriorTest it;
+    it.by_vox = FastDiv((uint32_t)g.vox_p);
+    it.by_z = FastDiv((uint32_t)g.Zp);
+    it.by_y = FastDiv((uint32_t)g.Yp);
+    it.X = X; it.Y = Y; it.Z = Z;
+    const int ci_tiles = (int)ceil_div(Cin, 64), co_tiles = (int)ceil_div(Cout, 64);
+    const int tiles = ntaps * ci_tiles * co_tiles;
+    // enough row slices to fill the machine ~4x, at least 256 rows each
+    int64_t slices = ceil_div(148 * 4, tiles);
+    int64_t rows_per_block = ceil_div(g.rows, slices < 1 ? 1 : slices);
+    if (rows_per_block < 256) rows_per_block = 256;
+    rows_per_block = ceil_div(rows_per_block, 16) * 16;
+    dim3 grid((unsigned)ceil_div(g.rows, rows_per_block), (unsigned)tiles);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == TDB_BF16)
+        conv_wgrad_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)in, ld_in, (const bf16*)d_out, ld_do, dw, g.rows, g.Yp * g.Zp, g.Zp,
+                                                     Cin, Cout, ntaps, ci_tiles, co_tiles, (int)rows_per_block, it);
+    else
+        conv_wgrad_kernel<float><<<grid, 256, 0, s>>>((const float*)in, ld_in, (const float*)d_out, ld_do, dw, g.rows, g.Yp * g.Zp,
+                                                      g.Zp, Cin, Cout, ntaps, ci_tiles, co_tiles, (int)rows_per_block, it);
+    TDB_CHECK_LAUNCH("tdb_conv3d_wgrad");
+    return 0;
+}
+
+int tdb_trilinear_bwd(const void* g_out, int ld_g, int Xo, int Yo, int Zo, void* d_in, int ld_d, int Xi, int Yi, int Zi, int B,
+                      int C, int dtype, void* stream) {
+    TDB_REQUIRE(g_out && d_in, TDB_E_BADARG, "tdb_trilinear_bwd: null pointer");
+    const int n = dtype == TDB_BF16 ? 8 : 4;
+    TDB_REQUIRE(C % n == 0 && ld_g % n == 0 && ld_d % n == 0 && C / n <= kThreads && aligned16(g_out) && aligned16(d_in),
+                TDB_E_UNSUPPORTED, "tdb_trilinear_bwd: C/ld must be multiples of %d", n);
+    Grid3 gi(B, Xi, Yi, Zi), go(B, Xo, Yo, Zo);
+    const int chunks = C / n;
+    dim3 grid((unsigned)blocks_per_sample(gi.vox_p * chunks, B), (unsigned)B);
+    auto scale_of = [](int n_in, int n_out) { return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.0f; };
+    const float sx = scale_of(Xi, Xo), sy = scale_of(Yi, Yo), sz = scale_of(Zi, Zo);
+    auto ok = [](float sc, int n_out) { return n_out == 1 || sc >= 0.2f; };
+    TDB_REQUIRE(ok(sx, Xo) && ok(sy, Yo) && ok(sz, Zo), TDB_E_UNSUPPORTED, "tdb_trilinear_bwd: upsampling factor above 5 per axis");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == TDB_BF16)
+        trilinear_bwd_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)g_out, ld_g, go, (bf16*)d_in, ld_d, gi, C, make_split(gi), chunks,
+                                                              sx, sy, sz);
+    else
+        trilinear_bwd_kernel<float><<<grid, kThreads, 0, s>>>((const float*)g_out, ld_g, go, (float*)d_in, ld_d, gi, C, make_split(gi),
+                                                               chunks, sx, sy, sz);
+    TDB_CHECK_LAUNCH("tdb_trilinear_bwd");
+    return 0;
+}
+
+int tdb_attention_bwd(const void* qkv, int ld_qkv, const void* d_out, int ld_do, void* d_qkv, int ld_dq, int B, int X, int Y,
+                      int Z, int heads, int dh, int dtype, void* stream) {
+    TDB_REQUIRE(qkv && d_out && d_qkv, TDB_E_BADARG, "tdb_attention_bwd: null pointer");
+    TDB_REQUIRE(dh == 32, TDB_E_UNSUPPORTED, "tdb_attention_bwd: dim_head must be 32 (got %d)", dh);
+    const int S = X * Y * Z;
+    const size_t smem = ((size_t)4 * S * 33 + (size_t)2 * S * (S + 1)) * sizeof(float);
+    TDB_REQUIRE(smem <= 220 * 1024, TDB_E_UNSUPPORTED, "tdb_attention_bwd: sequence of %d voxels exceeds shared memory", S);
+    Grid3 g(B, X, Y, Z);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e;
+    if (dtype == TDB_BF16) {
+        e = cudaFuncSetAttribute(attention_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            attention_bwd_kernel<bf16><<<B * heads, 256, smem, s>>>((const bf16*)qkv, ld_qkv, (const bf16*)d_out, ld_do, (bf16*)d_qkv, ld_dq,
+                                                                    g, heads, S);
+    } else {
+        e = cudaFuncSetAttribute(attention_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            attention_bwd_kernel<float><<<B * heads, 256, smem, s>>>((const float*)qkv, ld_qkv, (const float*)d_out, ld_do, (float*)d_qkv,
+                                                                     ld_dq, g, heads, S);
+    }
+    TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_attention_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    TDB_CHECK_LAUNCH("tdb_attention_bwd");
+    return 0;
+}
+
+int tdb_cl_nc_outer(const void* G, int ld, const float* Q, int64_t q_bstride, float* out, int B, int X, int Y, int Z, int C, int F,
+                    int dtype, void* stream) {
+    TDB_REQUIRE(G && Q && out, TDB_E_BADARG, "tdb_cl_nc_outer: null pointer");
+    Grid3 gr(B, X, Y, Z);
+    const int vox_per_block = 512;
+    dim3 grid((unsigned)ceil_div((int64_t)X * Y * Z, vox_per_block), (unsigned)B);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == TDB_BF16)
+        cl_nc_outer_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)G, ld, Q, q_bstride, out, gr, C, F, vox_per_block);
+    else
+        cl_nc_outer_kernel<float><<<grid, kThreads, 0, s>>>((const float*)G, ld, Q, q_bstride, out, gr, C, F, vox_per_block);
+    TDB_CHECK_LAUNCH("tdb_cl_nc_outer");
+    return 0;
+}
+
+}  // extern "C"

@@ -58,6 +58,7 @@ struct FoldParams {
     int ld_out;
     int G;           // groups for fused GroupNorm moments (0 = off); (Cout/G) even
     int num_tiles;
+    int all_rows;    // 1: store halo rows too (input-gradient use)
 };
 
 // interior test of a linear halo-grid row; returns the sample index through b
@@ -253,7 +254,8 @@ conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             const uint32_t aph = (uint32_t)(local >> 1) & 1u;
             const int64_t p = (int64_t)tile * ROWS_OUT + ROWS_WARP * lg - 1 + lane;
             int b = 0;
-            const bool valid = lane >= 1 && lane <= ROWS_WARP && interior_row(p, P, b);
+            const bool inter = lane >= 1 && lane <= ROWS_WARP && interior_row(p, P, b);
+            const bool valid = P.all_rows ? (lane >= 1 && lane <= ROWS_WARP && p >= 0 && p < P.rows) : inter;
             if (do_stats) {
                 // valid rows of one warp share one sample (a sample boundary is two halo planes wide)
                 const unsigned vmask = __ballot_sync(0xffffffffu, valid);
@@ -339,7 +341,7 @@ int launch_fold(const CUtensorMap& map_a, const CUtensorMap& map_b, const float*
 
 extern "C" int tdb_conv3d_bf16_fold(const void* in, int ld_in, int pad_rows, const void* w_fold, const float* bias, void* out,
                                     int ld_out, int B, int X, int Y, int Z, int Cin, int Cout, double* gn_stats, int G,
-                                    void* stream) {
+                                    unsigned flags, void* stream) {
     TDB_REQUIRE(in && w_fold && out, TDB_E_BADARG, "tdb_conv3d_bf16_fold: null pointer");
     TDB_REQUIRE(Cin % 16 == 0 && (Cout == 16 || Cout == 32 || Cout == 64) && ld_in % 8 == 0 && ld_out % 8 == 0, TDB_E_UNSUPPORTED,
                 "tdb_conv3d_bf16_fold: need Cin %% 16 == 0 and Cout in {16,32,64} (Cin=%d Cout=%d)", Cin, Cout);
@@ -389,6 +391,8 @@ extern "C" int tdb_conv3d_bf16_fold(const void* in, int ld_in, int pad_rows, con
     P.ld_out = ld_out;
     P.G = gn_stats ? G : 0;
     P.num_tiles = (int)ceil_div(g.rows, ROWS_OUT);
+    P.all_rows = (flags & TDB_CONV_ALL_ROWS) ? 1 : 0;
+    TDB_REQUIRE(!(P.all_rows && gn_stats), TDB_E_BADARG, "tdb_conv3d_bf16_fold: fused moments are not available with ALL_ROWS");
 
     CUtensorMap map_a, map_b;
     TDB_REQUIRE(encode_fn() != nullptr, TDB_E_NODEVICE, "tdb_conv3d_bf16_fold: cuTensorMapEncodeTiled unavailable (no driver)");

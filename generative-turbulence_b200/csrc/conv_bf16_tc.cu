@@ -41,6 +41,7 @@ struct ConvParams {
     int tmem_cols;
     int ld_out;
     int G;              // groups for fused GroupNorm moments (0 = off)
+    int all_rows;       // 1: store halo rows too (input-gradient use)
 };
 
 __device__ __forceinline__ bool row_is_interior(int64_t p, const ConvParams& P, int& b) {
@@ -149,6 +150,7 @@ conv3d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         int b = 0;
         const bool interior = p < P.rows && row_is_interior(p, P, b);
         const uint32_t t_row = tmem_d + ((uint32_t)(lg * 32) << 16);
+        const bool store = P.all_rows ? (p < P.rows) : interior;
         bf16* orow = out + p * P.ld_out + n0;
         const bool do_stats = gn_stats != nullptr;
         const int cpg = do_stats ? P.Cout / P.G : 1;
@@ -163,7 +165,7 @@ conv3d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + n0 + c + j) : 0.0f);
-            if (interior) {
+            if (store) {
                 uint4 lo, hi;
                 __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&lo);
                 __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&hi);
@@ -222,7 +224,7 @@ int pick_bn(int cout) {
 
 extern "C" int tdb_conv3d_bf16(const void* in, int ld_in, const void* w, const float* bias, void* out, int ld_out,
                                int B, int X, int Y, int Z, int Cin, int Cout, int ntaps, double* gn_stats, int G,
-                               void* stream) {
+                               unsigned flags, void* stream) {
     TDB_REQUIRE(in && w && out, TDB_E_BADARG, "tdb_conv3d_bf16: null pointer");
     TDB_REQUIRE(ntaps == 1 || ntaps == 27, TDB_E_BADARG, "tdb_conv3d_bf16: ntaps must be 1 or 27");
     TDB_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0, TDB_E_UNSUPPORTED,
@@ -257,6 +259,7 @@ extern "C" int tdb_conv3d_bf16(const void* in, int ld_in, const void* w, const f
     P.tmem_cols = cols;
     P.ld_out = ld_out;
     P.G = gn_stats ? G : 0;
+    P.all_rows = (flags & TDB_CONV_ALL_ROWS) ? 1 : 0;
 
     CUtensorMap map_a, map_b;
     TDB_REQUIRE(encode_fn() != nullptr, TDB_E_NODEVICE, "tdb_conv3d_bf16: cuTensorMapEncodeTiled unavailable (no driver)");

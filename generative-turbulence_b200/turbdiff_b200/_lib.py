@@ -15,6 +15,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libturbdiff_b200.so"
 F32, BF16 = 0, 1
 PW_SILU, PW_NOHALO = 1, 2
 STEP_NOISE_BCS, STEP_CLIP, STEP_FINAL = 1, 2, 4
+CONV_ALL_ROWS = 1
 
 _p, _i, _l, _u, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint, C.c_float
 
@@ -23,8 +24,8 @@ SIGNATURES = {
     "tdb_encode_input": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_decode_output": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_conv3d_f32": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
-    "tdb_conv3d_bf16": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
-    "tdb_conv3d_bf16_fold": [_p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
+    "tdb_conv3d_bf16": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _u, _p],
+    "tdb_conv3d_bf16_fold": [_p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _u, _p],
     "tdb_gn_stats": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_pointwise": [_p, _i, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _f, _u, _i, _p],
     "tdb_trilinear": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
@@ -33,6 +34,13 @@ SIGNATURES = {
     "tdb_ddpm_step": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _l, _u, _p],
     "tdb_q_sample": [_p, _p, _p, _p, _p, _p, _i, _i, _l, _i, _p],
     "tdb_masked_loss": [_p, _p, _p, _p, _p, _i, _i, _l, _l, _i, _p],
+    "tdb_halo_fold": [_p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "tdb_pointwise_bwd_reduce": [_p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _f, _u, _i, _p],
+    "tdb_pointwise_bwd_apply": [_p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _u, _i, _p],
+    "tdb_conv3d_wgrad": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "tdb_trilinear_bwd": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "tdb_attention_bwd": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "tdb_cl_nc_outer": [_p, _i, _p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_where_cells": [_p, _p, _p, _p, _l, _l, _p],
     "tdb_select_cells": [_p, _p, _p, _l, _l, _l, _p],
     "tdb_scatter_cells": [_p, _p, _p, _i, _i, _l, _l, _p],

@@ -33,8 +33,31 @@ def masked_loss(eps, noise, mask, n_inside: int, l1: bool):
     return _MaskedLoss.apply(eps, noise, mask, n_inside, l1)
 
 
+class _Denoise(torch.autograd.Function):
+    """eps = U-Net(x, t, c_local): forward launch program (training mode keeps the per-block
+    intermediates), backward launch program (turbdiff_b200.backward).  x itself gets no gradient:
+    the reference never differentiates with respect to the noisy input."""
+
+    @staticmethod
+    def forward(ctx, model, x, t, c_local, *params):
+        ctx.model = model
+        ctx.n_params = len(params)
+        return model.engine().forward(x, t, c_local, train=True).clone()
+
+    @staticmethod
+    def backward(ctx, g_eps):
+        model = ctx.model
+        grads, g_c_local = model.engine().backward(g_eps)
+        out = []
+        for name, prm in model.named_parameters():
+            g = grads.get(name)
+            if g is None:
+                raise RuntimeError(f"turbdiff_b200: no gradient produced for parameter {name}")
+            out.append(g.to(prm.dtype).reshape(prm.shape))
+        return (None, None, None, g_c_local, *out)
+
+
 def denoise_with_grad(model, x, t, c_local):
-    raise NotImplementedError(
-        "turbdiff_b200: the backward launch program of the denoiser is not built yet; call the model under "
-        "torch.no_grad() (sampling / evaluation)"
-    )
+    _lib.require_cuda(x, "x")
+    params = [p for _, p in model.named_parameters()]
+    return _Denoise.apply(model, x, t, c_local, *params)

@@ -1,0 +1,302 @@
+"""Backward launch program of the denoiser (the reverse walk of engine.DenoiserEngine.forward).
+
+The reference obtains these gradients from torch.autograd over ddpm.py:477-505; here every
+activation gradient is produced by a C-ABI kernel over halo grids:
+
+* convolution input gradients reuse the *forward* convolution kernels with tap-reversed, transposed
+  weights over the (zero-halo) output gradient, storing every row; the halo rows of the result are
+  then folded onto the border voxels (``tdb_halo_fold`` = adjoint of the replicate halo);
+* weight gradients: ``tdb_conv3d_wgrad`` (fp32 accumulation), ``tdb_cl_nc_outer`` for the 1x1x1
+  encoders / decoder;
+* GroupNorm + FiLM + SiLU: ``tdb_pointwise_bwd_reduce`` / ``_apply``; trilinear: ``tdb_trilinear_bwd``;
+  attention: ``tdb_attention_bwd``.
+
+Only O(B*C)-sized bookkeeping (turning the per-channel sums into parameter gradients, the timestep
+MLP with its 32..128-wide matrices) is done with torch ops on tiny tensors.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import PW_NOHALO, PW_SILU, call, ptr
+from .engine import GN_EPS, View
+
+
+class BackwardProgram:
+    def __init__(self, eng):
+        self.eng = eng
+        self.m = eng.model
+
+    # ------------------------------------------------------------------ helpers
+    def _gbuf(self, p, v: View, key) -> View:
+        """Gradient buffer with the geometry of forward view `v` (cached per plan)."""
+        gb = p.setdefault("gbuf", {})
+        if key not in gb:
+            gb[key] = p["grid"](v.level, v.t.shape[-1])
+        base = gb[key]
+        return View(base.t, v.c0, v.C, v.level)
+
+    def _tmp(self, p, level, C, key) -> View:
+        gb = p.setdefault("gbuf", {})
+        k = ("tmp", key, level)
+        if k not in gb or gb[k].t.shape[-1] < C:
+            gb[k] = p["grid"](level, max(C, p["max_c"].get(level, C)))
+        return gb[k].slice(0, C)
+
+    def _dgrad_weights(self, conv, key):
+        """Kernel-layout weights of the input-gradient convolution: W'[ci][co][k] = W[co][ci][2-k]."""
+        eng = self.eng
+        cache = eng._wcache.setdefault("dgrad", {})
+        if key not in cache:
+            wt = conv.weight.detach()
+            taps = wt.shape[2] * wt.shape[3] * wt.shape[4]
+            wt = wt.flip(2, 3, 4).transpose(0, 1)  # (Cin, Cout, k, k, k): "Cout'" = Cin, "Cin'" = Cout
+            cout, cin = wt.shape[:2]
+            if eng.precision == "fp32":
+                w = wt.permute(2, 3, 4, 1, 0).reshape(taps, cin, cout).contiguous().float()
+            elif eng.use_fold(taps, cout):
+                w = wt.permute(4, 0, 2, 3, 1).reshape(3 * cout, 9 * cin).contiguous().to(torch.bfloat16)
+            else:
+                w = wt.permute(0, 2, 3, 4, 1).reshape(cout, taps * cin).contiguous().to(torch.bfloat16)
+            cache[key] = w
+        return cache[key]
+
+    def _fold(self, p, g: View):
+        X, Y, Z = p["sizes"][g.level]
+        call("tdb_halo_fold", g.ptr, g.ld, p["B"], X, Y, Z, g.C, self.eng.dt, _lib.stream_ptr())
+
+    def _wgrad(self, p, x: View, d_out: View, conv, ntaps):
+        X, Y, Z = p["sizes"][x.level]
+        dw = torch.zeros((ntaps, x.C, d_out.C), dtype=torch.float32, device=x.t.device)
+        call("tdb_conv3d_wgrad", x.ptr, x.ld, d_out.ptr, d_out.ld, dw.data_ptr(), p["B"], X, Y, Z, x.C, d_out.C, ntaps, self.eng.dt,
+             _lib.stream_ptr())
+        k = 3 if ntaps == 27 else 1
+        return dw.view(k, k, k, x.C, d_out.C).permute(4, 3, 0, 1, 2).contiguous()
+
+    def _colsum(self, p, g: View):
+        """Per-channel sum over interior voxels and samples (conv bias gradients)."""
+        X, Y, Z = p["sizes"][g.level]
+        acc = torch.zeros((p["B"], g.C, 2), dtype=torch.float64, device=g.t.device)
+        call("tdb_gn_stats", g.ptr, g.ld, acc.data_ptr(), p["B"], X, Y, Z, g.C, g.C, self.eng.dt, _lib.stream_ptr())
+        return acc[:, :, 0].sum(0).float()
+
+    def _pw_bwd(self, p, g_out: View, raw: View, stats, norm, film_view, d_raw: View, flags, G):
+        """Backward of tdb_pointwise.  Returns (A1, A2) fp32 [B, C] and writes d_raw (zero halo)."""
+        eng = self.eng
+        X, Y, Z = p["sizes"][raw.level]
+        B, C = p["B"], raw.C
+        dev = raw.t.device
+        film_ptr = None if film_view is None else film_view.data_ptr()
+        gamma = ptr(norm.weight) if norm is not None else None
+        beta = ptr(norm.bias) if norm is not None else None
+        red = torch.zeros((B, C, 2), dtype=torch.float64, device=dev)
+        call("tdb_pointwise_bwd_reduce", g_out.ptr, g_out.ld, raw.ptr, raw.ld, ptr(stats), gamma, beta, film_ptr, eng.film_rows,
+             red.data_ptr(), B, X, Y, Z, C, G, GN_EPS, flags, eng.dt, _lib.stream_ptr())
+        grp = None
+        if stats is not None:
+            k = norm.weight.detach().double()[None, :].expand(B, C)
+            if film_view is not None:
+                k = k * (film_view[:, :C].double() + 1.0)
+            n = (C // G) * X * Y * Z
+            grp = ((k[..., None] * red).view(B, G, C // G, 2).sum(2) / n).float().contiguous()
+        call("tdb_pointwise_bwd_apply", g_out.ptr, g_out.ld, raw.ptr, raw.ld, ptr(stats), gamma, beta, film_ptr, eng.film_rows,
+             ptr(grp), d_raw.ptr, d_raw.ld, B, X, Y, Z, C, G, GN_EPS, flags, eng.dt, _lib.stream_ptr())
+        return red[..., 0], red[..., 1]
+
+    def _add_interior(self, p, a: View, b: View):
+        """a[interior] += b[interior] (halo rows of `a` untouched)."""
+        eng = self.eng
+        X, Y, Z = p["sizes"][a.level]
+        call("tdb_pointwise", a.ptr, a.ld, None, None, None, None, 0, b.ptr, b.ld, a.ptr, a.ld, p["B"], X, Y, Z, a.C, 1, GN_EPS,
+             PW_NOHALO, eng.dt, _lib.stream_ptr())
+
+    # ------------------------------------------------------------------ blocks
+    def _resblock_bwd(self, p, name, g_out: View, grads: dict, d_film: torch.Tensor):
+        """g_out: folded gradient of the block output.  Returns the folded gradient of the block input."""
+        eng = self.eng
+        bp = eng.blocks[name]
+        blk = bp.blk
+        sv = p["saved"][name]
+        x, slot = sv["x"], sv["slot"]
+        lvl = x.level
+        C = bp.cout
+        G = eng._groups(C)
+        pre = self.prefix[name]
+        film = p["film"][:, bp.film_offset : bp.film_offset + 2 * C]
+        d_raw = self._tmp(p, lvl, C, "d_raw")
+        g_act = self._tmp(p, lvl, C, "g_act")
+
+        # block2: pointwise (norm, SiLU, + residual) then conv2
+        a1, a2 = self._pw_bwd(p, g_out, sv["raw2"], p["stats"][slot + 1], blk.block2.norm, None, d_raw, PW_SILU, G)
+        grads[f"{pre}.block2.norm.weight"] = a2.sum(0).float()
+        grads[f"{pre}.block2.norm.bias"] = a1.sum(0).float()
+        grads[f"{pre}.block2.conv.weight"] = self._wgrad(p, sv["act1"], d_raw, blk.block2.conv, 27)
+        grads[f"{pre}.block2.conv.bias"] = self._colsum(p, d_raw)
+        eng._conv(p, d_raw, self._dgrad_weights(blk.block2.conv, f"{name}.conv2"), None, g_act, 27, all_rows=True)
+        self._fold(p, g_act)
+
+        # block1: pointwise (norm, FiLM, SiLU) then conv1
+        a1, a2 = self._pw_bwd(p, g_act, sv["raw1"], p["stats"][slot], blk.block1.norm, film, d_raw, PW_SILU, G)
+        sc1 = film[:, :C].double() + 1.0
+        gam, bet = blk.block1.norm.weight.detach().double(), blk.block1.norm.bias.detach().double()
+        grads[f"{pre}.block1.norm.weight"] = (sc1 * a2).sum(0).float()
+        grads[f"{pre}.block1.norm.bias"] = (sc1 * a1).sum(0).float()
+        d_film[:, bp.film_offset : bp.film_offset + C] = (gam * a2 + bet * a1).float()
+        d_film[:, bp.film_offset + C : bp.film_offset + 2 * C] = a1.float()
+        grads[f"{pre}.block1.conv.weight"] = self._wgrad(p, x, d_raw, blk.block1.conv, 27)
+        grads[f"{pre}.block1.conv.bias"] = self._colsum(p, d_raw)
+        g_x = self._gbuf(p, x, ("g", name))
+        eng._conv(p, d_raw, self._dgrad_weights(blk.block1.conv, f"{name}.conv1"), None, g_x, 27, all_rows=True)
+        self._fold(p, g_x)
+
+        # residual branch
+        if bp.has_proj:
+            grads[f"{pre}.conv.weight"] = self._wgrad(p, x, g_out, blk.conv, 1)
+            grads[f"{pre}.conv.bias"] = self._colsum(p, g_out)
+            g_res = self._tmp(p, lvl, x.C, "g_res")
+            eng._conv(p, g_out, self._dgrad_weights(blk.conv, f"{name}.proj"), None, g_res, 1, all_rows=True)
+            self._add_interior(p, g_x, g_res)
+        else:
+            self._add_interior(p, g_x, g_out)
+        return g_x
+
+    def _attention_bwd(self, p, g_out: View, grads: dict):
+        eng, m = self.eng, self.m
+        pre_mod = m.u_net.center_block[1].fn
+        att = pre_mod.fn
+        x = p["center0"]
+        X, Y, Z = p["sizes"][x.level]
+        B = p["B"]
+        s = _lib.stream_ptr
+        pre = "u_net.center_block.1.fn"
+        G = eng._groups(x.C)
+        # to_out (1x1 conv + bias) on the attention output
+        grads[f"{pre}.fn.to_out.weight"] = self._wgrad(p, p["attn_o"], g_out, att.to_out, 1)
+        grads[f"{pre}.fn.to_out.bias"] = self._colsum(p, g_out)
+        g_o = self._gbuf(p, p["attn_o"], ("g", "attn_o"))
+        eng._conv(p, g_out, self._dgrad_weights(att.to_out, "attn.out"), None, g_o, 1, all_rows=True)
+        # softmax attention
+        g_qkv = self._gbuf(p, p["attn_qkv"], ("g", "attn_qkv"))
+        call("tdb_attention_bwd", p["attn_qkv"].ptr, p["attn_qkv"].ld, g_o.ptr, g_o.ld, g_qkv.ptr, g_qkv.ld, B, X, Y, Z, att.heads,
+             att.dim_head, eng.dt, s())
+        # to_qkv (1x1 conv, no bias) on the normalised input
+        grads[f"{pre}.fn.to_qkv.weight"] = self._wgrad(p, p["attn_norm"], g_qkv, att.to_qkv, 1)
+        g_hn = self._gbuf(p, p["attn_norm"], ("g", "attn_norm"))
+        eng._conv(p, g_qkv, self._dgrad_weights(att.to_qkv, "attn.qkv"), None, g_hn, 1, all_rows=True)
+        # pre-norm
+        g_x = self._gbuf(p, x, ("g", "attn_x"))
+        a1, a2 = self._pw_bwd(p, g_hn, x, p["stats"][p["attn_slot"]], pre_mod.norm, None, g_x, 0, G)
+        grads[f"{pre}.norm.weight"] = a2.sum(0).float()
+        grads[f"{pre}.norm.bias"] = a1.sum(0).float()
+        # residual: out = proj + x
+        self._add_interior(p, g_x, g_out)
+        return g_x
+
+    # ------------------------------------------------------------------ whole network
+    @torch.no_grad()
+    def run(self, g_eps: torch.Tensor):
+        eng, m = self.eng, self.m
+        x_in, t, c_local = None, None, None
+        key = None
+        for k, pl in eng._plans.items():
+            if "last_input" in pl:
+                key = k
+        if key is None:
+            raise RuntimeError("turbdiff_b200: backward called without a preceding forward(train=True)")
+        p = eng._plans[key]
+        x_in, t, c_local = p["last_input"]
+        B, F = x_in.shape[:2]
+        X, Y, Z = x_in.shape[2:]
+        L = m.u_net_levels
+        dev = x_in.device
+        s = _lib.stream_ptr
+        dt = eng.dt
+        eng.weights()
+        g_eps = g_eps.to(torch.float32).contiguous()
+        grads: dict[str, torch.Tensor] = {}
+        d_film = torch.zeros((B, eng.film_rows), dtype=torch.float32, device=dev)
+        self.prefix = {"decode0": "decode.0", "center0": "u_net.center_block.0", "center2": "u_net.center_block.2"}
+        for i in range(L):
+            self.prefix[f"down{i}"] = f"u_net.downsampling_blocks.{i}"
+            self.prefix[f"up{i}"] = f"u_net.upsampling_blocks.{i}"
+
+        # decode[1]: 1x1 conv dim -> F read from NCDHW eps gradient
+        dec = m.decode[1]
+        dec_out = p["dec_out"]
+        dw = torch.zeros((m.dim, F), dtype=torch.float32, device=dev)
+        call("tdb_cl_nc_outer", dec_out.ptr, dec_out.ld, g_eps.data_ptr(), F * X * Y * Z, dw.data_ptr(), B, X, Y, Z, m.dim, F, dt, s())
+        grads["decode.1.weight"] = dw.t().reshape(dec.weight.shape).contiguous()
+        grads["decode.1.bias"] = g_eps.sum(dim=(0, 2, 3, 4))
+        g_dec = self._gbuf(p, dec_out, ("g", "dec_out"))
+        wt = dec.weight.detach().reshape(F, m.dim).t().contiguous()  # (dim, F)
+        zero_b = torch.zeros(m.dim, dtype=torch.float32, device=dev)
+        call("tdb_encode_input", g_eps.data_ptr(), None, wt.data_ptr(), zero_b.data_ptr(), None, None, g_dec.ptr, g_dec.ld, B, F, 0,
+             m.dim, X, Y, Z, 1, dt, s())  # halo rows hold copies, never read: the 1x1 conv only saw interior voxels
+
+        g = self._resblock_bwd(p, "decode0", g_dec, grads, d_film)
+        # up path (reverse): block input = cat[l] = [upsampled | skip]
+        for i in reversed(range(L)):
+            l = L - 1 - i
+            g_cat = self._resblock_bwd(p, f"up{i}", g, grads, d_film)  # folded, 2C channels
+            C = g_cat.C // 2
+            src = p["up_out"][l + 1] if l + 1 < L else p["center2"]
+            g = self._gbuf(p, src, ("g", "up_src", l))
+            Xo, Yo, Zo = p["sizes"][l]
+            Xi, Yi, Zi = p["sizes"][l + 1]
+            up_half = g_cat.slice(0, C)
+            call("tdb_trilinear_bwd", up_half.ptr, up_half.ld, Xo, Yo, Zo, g.ptr, g.ld, Xi, Yi, Zi, B, C, dt, s())
+            p.setdefault("g_skip", {})[l] = g_cat.slice(C, C)
+        # centre
+        g = self._resblock_bwd(p, "center2", g, grads, d_film)
+        g = self._attention_bwd(p, g, grads)
+        g = self._resblock_bwd(p, "center0", g, grads, d_film)
+        # down path (reverse): skip gradient + gradient through the downsampling
+        for l in reversed(range(L)):
+            g_skip = p["g_skip"][l]
+            Xi, Yi, Zi = p["sizes"][l]
+            Xo, Yo, Zo = p["sizes"][l + 1]
+            tmp = self._tmp(p, l, g_skip.C, "g_down")
+            call("tdb_trilinear_bwd", g.ptr, g.ld, Xo, Yo, Zo, tmp.ptr, tmp.ld, Xi, Yi, Zi, B, g_skip.C, dt, s())
+            self._add_interior(p, g_skip, tmp)
+            g = self._resblock_bwd(p, f"down{l}", g_skip, grads, d_film)
+
+        # encoders (g = folded gradient of xin0: [encode_x | encode_c_local])
+        dim, Fc = m.dim, m.c_local_features
+        nvox = X * Y * Z
+        gx = g.slice(0, dim)
+        dwx = torch.zeros((dim, F), dtype=torch.float32, device=dev)
+        call("tdb_cl_nc_outer", gx.ptr, gx.ld, x_in.data_ptr(), F * nvox, dwx.data_ptr(), B, X, Y, Z, dim, F, dt, s())
+        grads["encode_x.weight"] = dwx.reshape(m.encode_x.weight.shape)
+        grads["encode_x.bias"] = self._colsum(p, gx)
+        g_c_local = None
+        if Fc > 0:
+            gc = g.slice(dim, dim)
+            dwc = torch.zeros((dim, Fc), dtype=torch.float32, device=dev)
+            call("tdb_cl_nc_outer", gc.ptr, gc.ld, c_local.data_ptr(), 0, dwc.data_ptr(), B, X, Y, Z, dim, Fc, dt, s())
+            grads["encode_c_local.weight"] = dwc.reshape(m.encode_c_local.weight.shape)
+            grads["encode_c_local.bias"] = self._colsum(p, gc)
+            wct = m.encode_c_local.weight.detach().reshape(dim, Fc).t().contiguous()  # (Fc, dim)
+            zb = torch.zeros(Fc, dtype=torch.float32, device=dev)
+            per_sample = torch.empty((B, Fc, X, Y, Z), dtype=torch.float32, device=dev)
+            call("tdb_decode_output", gc.ptr, gc.ld, wct.data_ptr(), zb.data_ptr(), per_sample.data_ptr(), B, X, Y, Z, dim, Fc, dt, s())
+            g_c_local = per_sample.sum(0)
+
+        # timestep MLP + FiLM projections: (B, <=128)-sized matrices, differentiated with torch on the fly
+        with torch.enable_grad():
+            pc = m.process_c
+            tp = [pc[0].weight, pc[0].bias, pc[2].weight, pc[2].bias]
+            lin = [eng.blocks[n].blk.project_onto_scale_shift for n in eng.block_order]
+            emb = torch.addcmul(m.encode_t.bias, m.encode_t.scale, t[..., None].to(torch.float32)).sin()
+            c = torch.nn.functional.silu(torch.nn.functional.linear(emb, tp[0], tp[1]))
+            c = torch.nn.functional.silu(torch.nn.functional.linear(c, tp[2], tp[3]))
+            film = torch.cat([torch.nn.functional.linear(c, q.weight, q.bias) for q in lin], dim=1)
+            params = tp + [q.weight for q in lin] + [q.bias for q in lin]
+            gs = torch.autograd.grad(film, params, d_film)
+        names = ["process_c.0.weight", "process_c.0.bias", "process_c.2.weight", "process_c.2.bias"]
+        names += [f"{self.prefix[n]}.project_onto_scale_shift.weight" for n in eng.block_order]
+        names += [f"{self.prefix[n]}.project_onto_scale_shift.bias" for n in eng.block_order]
+        for n, gg in zip(names, gs):
+            grads[n] = gg
+        return grads, g_c_local

@@ -185,6 +185,8 @@ class DenoiserEngine:
         p["raw"] = {l: grid(l, c) for l, c in max_c.items()}
         p["act"] = {l: grid(l, c) for l, c in max_c.items()}
         p["res"] = {l: grid(l, c) for l, c in max_c.items()}
+        p["grid"] = grid  # allocator for the (lazily built) training buffers
+        p["max_c"] = max_c
         n_norms = 2 * len(self.blocks) + 1
         gmax = max(self._groups(bp.cout) for bp in self.blocks.values())
         # one flat slot per norm layer, used as [B][G][2] doubles (sum, sum of squares)
@@ -210,18 +212,21 @@ class DenoiserEngine:
         return C if g is None else g
 
     # ------------------------------------------------------------------ kernels
-    def _conv(self, p, x: View, w, bias, out: View, ntaps, stats=None, G=0):
+    def _conv(self, p, x: View, w, bias, out: View, ntaps, stats=None, G=0, all_rows=False):
+        """3x3x3 / 1x1x1 convolution over halo grids.  all_rows: also store the halo rows of the output
+        (input-gradient convolutions; the fp32 kernel always stores every row)."""
         B = p["B"]
         X, Y, Z = p["sizes"][x.level]
         s = _lib.stream_ptr()
+        flags = _lib.CONV_ALL_ROWS if all_rows else 0
         if self.precision == "fp32":
             call("tdb_conv3d_f32", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ntaps, s)
         elif self.use_fold(ntaps, out.C):
             call("tdb_conv3d_bf16_fold", x.ptr, x.ld, self.pad_rows((X, Y, Z)), w.data_ptr(), ptr(bias), out.ptr, out.ld,
-                 B, X, Y, Z, x.C, out.C, ptr(stats), G, s)
+                 B, X, Y, Z, x.C, out.C, ptr(stats), G, flags, s)
         else:
             call("tdb_conv3d_bf16", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ntaps,
-                 ptr(stats), G, s)
+                 ptr(stats), G, flags, s)
 
     def _stats(self, p, x: View, stats, G):
         X, Y, Z = p["sizes"][x.level]
@@ -255,16 +260,31 @@ class DenoiserEngine:
             self._stats(p, raw, stats, G)
         return stats, G
 
-    def _resblock(self, p, name, x: View, out: View, slot):
+    def _saved(self, p, name):
+        """Per-block activation buffers kept for the backward program (training mode only)."""
+        sv = p.setdefault("saved", {})
+        if name not in sv:
+            bp = self.blocks[name]
+            lvl = self._block_level(name)
+            sv[name] = {k: p["grid"](lvl, bp.cout) for k in ("raw1", "act1", "raw2")}
+        return sv[name]
+
+    def _resblock(self, p, name, x: View, out: View, slot, train=False):
         bp = self.blocks[name]
         w = self.weights()
         lvl = x.level
         blk = bp.blk
-        raw = p["raw"][lvl].slice(0, bp.cout)
-        act = p["act"][lvl].slice(0, bp.cout)
+        if train:
+            sv = self._saved(p, name)
+            raw, act, raw_b = sv["raw1"], sv["act1"], sv["raw2"]
+            sv["x"], sv["out"], sv["slot"] = x, out, slot
+        else:
+            raw = raw_b = p["raw"][lvl].slice(0, bp.cout)
+            act = p["act"][lvl].slice(0, bp.cout)
         film_ptr = p["film"].data_ptr() + 4 * bp.film_offset
         st, G = self._norm_conv(p, x, w[f"{name}.conv1"], blk.block1.conv, blk.block1.norm, raw, slot)
         self._pointwise(p, raw, st, blk.block1.norm, film_ptr, None, act, PW_SILU, G)
+        raw = raw_b
         st, G = self._norm_conv(p, act, w[f"{name}.conv2"], blk.block2.conv, blk.block2.norm, raw, slot + 1)
         if bp.has_proj:
             res = p["res"][lvl].slice(0, bp.cout)
@@ -292,8 +312,9 @@ class DenoiserEngine:
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward(self, x: torch.Tensor, t: torch.Tensor, c_local: torch.Tensor | None, taps: dict | None = None):
-        """eps = U-Net(x, t, c_local).  x (B,F,X,Y,Z) fp32 CUDA contiguous, t int64 (B,)."""
+    def forward(self, x: torch.Tensor, t: torch.Tensor, c_local: torch.Tensor | None, taps: dict | None = None, train: bool = False):
+        """eps = U-Net(x, t, c_local).  x (B,F,X,Y,Z) fp32 CUDA contiguous, t int64 (B,).
+        train=True keeps every block's intermediates in dedicated buffers for `backward`."""
         m = self.model
         _lib.require_cuda(x, "x")
         if x.dtype != torch.float32:
@@ -334,19 +355,20 @@ class DenoiserEngine:
         for l in range(L):
             cd = p["cat"][l].C // 2
             out = p["cat"][l].slice(cd, cd)
-            self._resblock(p, f"down{l}", cur, out, slot)
+            self._resblock(p, f"down{l}", cur, out, slot, train)
             slot += 2
             tap(f"down{l}", out)
             nxt = p["xin"][l + 1] if l + 1 < L else p["center_in"]
             self._trilinear(p, out, nxt)
             cur = nxt
-        self._resblock(p, "center0", cur, p["center0"], slot)
+        self._resblock(p, "center0", cur, p["center0"], slot, train)
         slot += 2
         tap("center0", p["center0"])
         self._attention(p, p["center0"], p["center1"], slot)
+        p["attn_slot"] = slot
         slot += 1
         tap("center1", p["center1"])
-        self._resblock(p, "center2", p["center1"], p["center2"], slot)
+        self._resblock(p, "center2", p["center1"], p["center2"], slot, train)
         slot += 2
         tap("center2", p["center2"])
         cur = p["center2"]
@@ -354,17 +376,25 @@ class DenoiserEngine:
             l = L - 1 - i
             cat = p["cat"][l]
             self._trilinear(p, cur, cat.slice(0, cat.C // 2))
-            self._resblock(p, f"up{i}", cat, p["up_out"][l], slot)
+            self._resblock(p, f"up{i}", cat, p["up_out"][l], slot, train)
             slot += 2
             tap(f"up{i}", p["up_out"][l])
             cur = p["up_out"][l]
-        self._resblock(p, "decode0", cur, p["dec_out"], slot)
+        self._resblock(p, "decode0", cur, p["dec_out"], slot, train)
         tap("decode0", p["dec_out"])
         dec = m.decode[1]
         eps = p["eps"]
         call("tdb_decode_output", p["dec_out"].ptr, p["dec_out"].ld, dec.weight.data_ptr(), dec.bias.data_ptr(), eps.data_ptr(),
              B, X, Y, Z, m.dim, m.out_features, self.dt, s)
+        if train:
+            p["last_input"] = (x, t, c_local)
         return eps
+
+    def backward(self, g_eps: torch.Tensor):
+        """Gradients of every parameter (and of c_local) for the last `forward(train=True)`."""
+        from .backward import BackwardProgram
+
+        return BackwardProgram(self).run(g_eps)
 
     @staticmethod
     def to_ncdhw(v: View) -> torch.Tensor:

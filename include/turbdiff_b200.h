@@ -48,6 +48,9 @@ extern "C" {
 #define TDB_PW_SILU 1u   /* apply x*sigmoid(x) after the affine part */
 #define TDB_PW_NOHALO 2u /* write interior voxels only */
 
+/* convolution flags (tdb_conv3d_bf16, tdb_conv3d_bf16_fold) */
+#define TDB_CONV_ALL_ROWS 1u /* also store the halo rows of the output (input-gradient convolutions) */
+
 /* ddpm step flags (tdb_ddpm_step) */
 #define TDB_STEP_NOISE_BCS 1u /* GaussianDiffusion(noise_bcs=True)  */
 #define TDB_STEP_CLIP 2u      /* clip_denoised: clamp x0 to [-1,1]  */
@@ -90,7 +93,7 @@ TDB_API int tdb_conv3d_f32(const float* in, int ld_in, const float* w, const flo
  * accumulators over interior voxels, G groups of Cout/G channels. */
 TDB_API int tdb_conv3d_bf16(const void* in, int ld_in, const void* w, const float* bias, void* out,
                     int ld_out, int B, int X, int Y, int Z, int Cin, int Cout, int ntaps,
-                    double* gn_stats, int G, void* stream);
+                    double* gn_stats, int G, unsigned flags, void* stream);
 
 /* Same convolution (3x3x3 only) for narrow layers, Cout in {16,32,64}: the kz filter axis is folded
  * into the GEMM N dimension (9 row-shifted A boxes instead of 27, 3x wider MMAs), persistent CTAs,
@@ -101,7 +104,7 @@ TDB_API int tdb_conv3d_bf16(const void* in, int ld_in, const void* w, const floa
  * (of ld_in elements) of readable memory; their contents never reach a stored output. */
 TDB_API int tdb_conv3d_bf16_fold(const void* in, int ld_in, int pad_rows, const void* w_fold, const float* bias, void* out,
                          int ld_out, int B, int X, int Y, int Z, int Cin, int Cout, double* gn_stats,
-                         int G, void* stream);
+                         int G, unsigned flags, void* stream);
 
 /* ---- normalisation / pointwise --------------------------------------------------------- */
 
@@ -178,6 +181,45 @@ TDB_API int tdb_q_sample(const float* x0, const float* noise, const int64_t* t, 
  * n_inside = number of inside cells. */
 TDB_API int tdb_masked_loss(const float* eps, const float* noise, const uint8_t* mask, double* loss_acc,
                     float* grad, int B, int F, int64_t nvox, int64_t n_inside, int l1, void* stream);
+
+/* ---- backward (training path; the reference gets these from torch.autograd) ---------------------- */
+
+/* Adjoint of halo materialisation: for every border voxel, add the gradient stored on its halo images
+ * (in place; halo rows are left untouched and must not be read afterwards). */
+TDB_API int tdb_halo_fold(void* g, int ld, int B, int X, int Y, int Z, int C, int dtype, void* stream);
+
+/* Backward of tdb_pointwise, pass 1: red[b][c] = (sum g_u, sum g_u*xhat) over interior voxels in double
+ * (pre-zeroed), where u is the forward pre-activation, g_u = g_out*silu'(u) (or g_out) and
+ * xhat = (raw-mean)*rstd.  g_out must already be folded. */
+TDB_API int tdb_pointwise_bwd_reduce(const void* g_out, int ld_g, const void* raw, int ld_raw, const double* stats,
+                             const float* gamma, const float* beta, const float* film, int film_ld, double* red,
+                             int B, int X, int Y, int Z, int C, int G, float eps, unsigned flags, int dtype,
+                             void* stream);
+
+/* Pass 2: d_raw = rstd*(k*g_u - m1 - xhat*m2) on interior rows and 0 on halo rows, k = gamma*(scale+1),
+ * grp[b][g] = (m1, m2) = group means of k*A1 and k*A2 (fp32).  Without stats: d_raw = g_u. */
+TDB_API int tdb_pointwise_bwd_apply(const void* g_out, int ld_g, const void* raw, int ld_raw, const double* stats,
+                            const float* gamma, const float* beta, const float* film, int film_ld,
+                            const float* grp, void* d_raw, int ld_d, int B, int X, int Y, int Z, int C, int G,
+                            float eps, unsigned flags, int dtype, void* stream);
+
+/* Weight gradient of tdb_conv3d_*: dw[tap][ci][co] += sum over interior rows p of
+ * in[p+delta(tap)][ci]*d_out[p][co]; dw fp32 [ntaps][Cin][Cout], accumulated (pre-zero it). */
+TDB_API int tdb_conv3d_wgrad(const void* in, int ld_in, const void* d_out, int ld_do, float* dw, int B, int X, int Y,
+                     int Z, int Cin, int Cout, int ntaps, int dtype, void* stream);
+
+/* Transpose of tdb_trilinear: d_in (interior rows; halo rows zero) from the folded output gradient. */
+TDB_API int tdb_trilinear_bwd(const void* g_out, int ld_g, int Xo, int Yo, int Zo, void* d_in, int ld_d, int Xi,
+                      int Yi, int Zi, int B, int C, int dtype, void* stream);
+
+/* Backward of tdb_attention: d_qkv (q|k|v gradient, interior rows) from qkv and d_out. S <= 128. */
+TDB_API int tdb_attention_bwd(const void* qkv, int ld_qkv, const void* d_out, int ld_do, void* d_qkv, int ld_dq, int B,
+                      int X, int Y, int Z, int heads, int dh, int dtype, void* stream);
+
+/* out[c][f] += sum_{b, interior v} G[b,v][c] * Q[b*q_bstride + f*nvox + v]: weight gradients of the 1x1x1
+ * encoders / decoder between a halo grid G and NCDHW planes Q (q_bstride = 0 for an unbatched Q). */
+TDB_API int tdb_cl_nc_outer(const void* G, int ld, const float* Q, int64_t q_bstride, float* out, int B, int X, int Y,
+                    int Z, int C, int F, int dtype, void* stream);
 
 /* ---- cell indexing (bit-exact) -------------------------------------------------------------------- */
 

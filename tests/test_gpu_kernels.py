@@ -84,7 +84,7 @@ def test_conv3d_bf16_tensor_core(lib, case, fused_stats):
     G = 8
     stats = torch.zeros((B, G, 2), dtype=torch.float64, device="cuda")
     lib.call("tdb_conv3d_bf16", xin.data_ptr(), Cin, wp.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
-             ntaps, stats.data_ptr() if fused_stats else None, G, lib.stream_ptr())
+             ntaps, stats.data_ptr() if fused_stats else None, G, 0, lib.stream_ptr())
     torch.cuda.synchronize()
     want = _conv_ref(x.double().cpu(), w.double().cpu(), b.double().cpu(), ntaps)
     # inputs are exactly representable in bf16, accumulation is fp32: only the bf16 output rounding remains
@@ -117,7 +117,7 @@ def test_conv3d_bf16_kz_folded(lib, case, fused_stats):
     G = 8
     stats = torch.zeros((B, G, 2), dtype=torch.float64, device="cuda")
     lib.call("tdb_conv3d_bf16_fold", xin.data_ptr(), Cin, pad, wf.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
-             stats.data_ptr() if fused_stats else None, G, lib.stream_ptr())
+             stats.data_ptr() if fused_stats else None, G, 0, lib.stream_ptr())
     torch.cuda.synchronize()
     want = _conv_ref(x.double().cpu(), w.double().cpu(), b.double().cpu(), 27)
     assert rel_l2(from_halo(out), want) < 4e-3

@@ -137,3 +137,73 @@ def test_state_dict_roundtrip_and_init_order():
         m = DenoisingModel(in_features=4, out_features=4, c_local_features=4, c_global_features=0, timesteps=500, dim=32,
                            u_net_levels=4, norm_type="group")
     assert [[k, list(v.shape)] for k, v in m.state_dict().items()] == ref
+
+
+def _oracle_grads(case, G, dtype=torch.float64):
+    """Reference gradients of sum(eps * G) w.r.t. every parameter and c_local (CPU oracle, fp64)."""
+    from oracle.cases import case_inputs
+    from oracle.unet_ref import denoiser_forward, synth_state_dict
+
+    sd = {k: v.requires_grad_() for k, v in synth_state_dict(case["spec"], case["seed"], dtype).items()}
+    x, t, c_local, _ = case_inputs(case)
+    cl = c_local.to(dtype).requires_grad_()
+    eps = denoiser_forward(sd, case["spec"], x.to(dtype), t, cl)
+    (eps * G.to(dtype)).sum().backward()
+    return {k: v.grad for k, v in sd.items()}, cl.grad
+
+
+@pytest.mark.parametrize("cname,precision,tol", [("micro", "fp32", 2e-4), ("tiny", "fp32", 2e-4), ("micro-layer", "fp32", 2e-4),
+                                                  ("tiny", "bf16", 6e-2), ("dim32", "bf16", 6e-2)])
+def test_denoiser_backward_matches_oracle(cname, precision, tol):
+    from oracle.cases import CASES, case_inputs
+
+    case = CASES[cname]
+    m = build(case, precision).train()
+    x, t, c_local, _ = case_inputs(case)
+    G = torch.randn(x.shape, generator=torch.Generator().manual_seed(9))
+    want, want_cl = _oracle_grads(case, G)
+    cl = c_local.cuda().requires_grad_()
+    eps = m(x.cuda(), t.cuda(), {key_of(): cl})
+    assert eps.requires_grad
+    (eps * G.cuda()).sum().backward()
+    errs = {}
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        ref = want[k]
+        if float(ref.abs().max()) < 1e-9:  # exactly-zero gradients (bias in front of a 1-channel group)
+            assert float(p.grad.abs().max()) < 1e-4 * max(1.0, float(G.abs().max())), k
+            continue
+        errs[k] = rel_l2(p.grad, ref)
+    errs["c_local"] = rel_l2(cl.grad, want_cl)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    print(cname, precision, [(k, f"{v:.2e}") for k, v in worst])
+    assert worst[0][1] < tol, worst
+
+
+@pytest.mark.parametrize("noise_bcs", [True, False])
+def test_training_step_gradients_match_reference_golden(golden, noise_bcs):
+    """GaussianDiffusion.forward + backward against the reference's own loss.backward() (golden)."""
+    from oracle.cases import CASES, case_inputs
+    from turbdiff_b200 import GaussianDiffusion
+
+    g = golden["diffusion"]
+    tag = f"micro/noise_bcs={int(noise_bcs)}"
+    case = CASES["micro"]
+    m = build(case, "fp32").train()
+    x, _, c_local, geo = case_inputs(case)
+
+    class MD:
+        cell_idx = torch.from_numpy(geo.cell_idx).cuda()
+
+    gd = GaussianDiffusion(m, timesteps=case["spec"].timesteps, beta_schedule="log-snr-linear", loss_type="l2", noise_bcs=noise_bcs).cuda()
+    with cpu_seeded_randn(4321):
+        loss, t = gd(x.cuda(), {key_of(): c_local.cuda()}, MD, None)
+    np.testing.assert_allclose(loss.item(), g[f"{tag}/loss"], rtol=2e-5)
+    loss.backward()
+    for k, p in m.named_parameters():
+        gs = g[f"{tag}/gradsum/{k}"]
+        got = p.grad.double().pow(2).sum().item()
+        np.testing.assert_allclose(got, gs[1], rtol=2e-3, atol=1e-10, err_msg=k)
+        key = f"{tag}/grad/{k}"
+        if key in g.files and np.abs(g[key]).max() > 1e-7:
+            assert rel_l2(p.grad, g[key]) < 5e-4, k
