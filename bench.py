@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--timesteps", type=int, default=1000, help="T of the sampled chain (BASELINE configs[2]: 1000)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--e2e-steps", type=int, default=8, help="chain length of one end-to-end public-API call")
+    ap.add_argument("--train-steps", type=int, default=3, help="timed training steps (configs[1]/[3]: fwd+bwd+all-reduce+optimizer); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     return ap.parse_args()
@@ -119,7 +120,7 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -359,6 +360,49 @@ def run_ours(args):
             roof["ddpm_step"] = {"bound": "hbm", "achieved": bytes_step / (st_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                  "frac": bytes_step / (st_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "algorithmic_bytes": bytes_step}
 
+    # ---- training step (BASELINE configs[1] / [3]): q_sample + U-Net fwd + bwd (+ NCCL grad all-reduce) + clip + RAdam
+    train = None
+    if args.train_steps > 0:
+        from turbdiff_b200.parallel import GradientAllReduce
+
+        graph = None
+        torch.cuda.empty_cache()
+        model.train()
+        opt = torch.optim.RAdam(model.parameters(), lr=1e-4)
+        reducer = GradientAllReduce(model.parameters())
+
+        class MD:
+            pass
+
+        MD.cell_idx = cell_idx
+
+        def train_step():
+            opt.zero_grad(set_to_none=True)
+            loss, _ = gd(x_bcs, C, MD, None)
+            loss.backward()
+            reducer()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
+            opt.step()
+            return loss
+
+        train_step()
+        barrier()
+        n_t0 = _lib.launch_count()
+        e0.record()
+        for _ in range(args.train_steps):
+            loss = train_step()
+        e1.record()
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1) / args.train_steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        train = {"steps_per_sec": 1e3 / float(tt.item()), "ms_per_step": float(tt.item()), "batch_per_gpu": B, "global_batch": B * world,
+                 "loss": float(loss.item()), "kernel_launches_per_step": (_lib.launch_count() - n_t0) // args.train_steps,
+                 "includes": "q_sample + U-Net forward + backward + bucketed NCCL gradient all-reduce (N>1) + clip_grad_norm(0.1) + RAdam step",
+                 "train_flops_per_step": 3 * conv_flops_per_sample(spec, geo.padded) * B}
+        train["tflops"] = train["train_flops_per_step"] / (train["ms_per_step"] * 1e-3) / 1e12
+        model.eval()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, cores = time_cpu_reference(T, 3, 1)
@@ -378,7 +422,7 @@ def run_ours(args):
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
                     "how": f"GaussianDiffusion.p_sample_loop(start_from={S}) on pinned host x_bcs -> pinned host sample, scaled by T/{S}"},
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "cpu_baseline": cpu, "train": train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
