@@ -203,7 +203,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def run_ours(args):
@@ -424,12 +424,24 @@ def run_ours(args):
                     "how": f"GaussianDiffusion.p_sample_loop(start_from={S}) on pinned host x_bcs -> pinned host sample, scaled by T/{S}"},
             "roofline": roof, "cpu_baseline": cpu, "train": train,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # C-level writers to fd 1 (e.g. the "NCCL version" banner) must not pollute the JSON line
     args = parse()
     if args.impl == "reference":
         run_reference(args)
