@@ -73,7 +73,9 @@ __device__ __forceinline__ bool interior_row(int64_t p, const FoldParams& P, int
            zp <= (uint32_t)(P.Zp - 2);
 }
 
-template <int COUT>
+// KC_T / TY_T / RES_T > 0 (>= 0 for RES_T) specialise the K chunk, taps per stage and weight residency at
+// compile time (the hot shapes of the shapes config); -1 reads them from the launch parameters.
+template <int COUT, int KC_T, int TY_T, int RES_T>
 __global__ void __launch_bounds__(THREADS, 1)
 conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                         const float* __restrict__ bias, bf16* __restrict__ out, double* __restrict__ gn_stats,
@@ -93,10 +95,15 @@ conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     const uint32_t acc_full = ptx::smem_u32(&bars[2 * MAX_STAGES]);       // [2]
     const uint32_t acc_empty = ptx::smem_u32(&bars[2 * MAX_STAGES + 2]);  // [2]
     const uint32_t b_full = ptx::smem_u32(&bars[2 * MAX_STAGES + 4]);
-    const int chunks = P.Cin / P.KC;
-    const int n_bchunks = 9 * chunks;           // B chunks of KC channels: index t9*chunks + ch
-    const uint32_t b_region = P.b_resident ? (uint32_t)(n_bchunks * P.b_bytes) : 0u;
-    const uint32_t stage_bytes = (uint32_t)(P.TY * (P.a_bytes + (P.b_resident ? 0 : P.b_bytes)));
+    const int KC = KC_T > 0 ? KC_T : P.KC;
+    const int TY = TY_T > 0 ? TY_T : P.TY;
+    const bool resident = RES_T >= 0 ? (RES_T != 0) : (P.b_resident != 0);
+    const int chunks = P.Cin / KC;
+    const int n_bchunks = 9 * chunks;           // B chunks of KC channels
+    const int k_iters = n_bchunks / TY;         // pipeline stages per tile, walked as (kx, [ky], ch)
+    const uint32_t a_bytes = (uint32_t)(BM * KC * 2), b_bytes = (uint32_t)(NF * KC * 2);
+    const uint32_t b_region = resident ? (uint32_t)n_bchunks * b_bytes : 0u;
+    const uint32_t stage_bytes = (uint32_t)TY * (a_bytes + (resident ? 0u : b_bytes));
     const uint32_t stage_base = smem_base + b_region;
 
     for (int i = threadIdx.x; i < COUT; i += THREADS) s_bias[i] = bias ? bias[i] : 0.0f;
@@ -125,16 +132,20 @@ conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 
     if (warp == 0) {
         // ===== TMA producer: the whole warp walks the (warp-uniform) loop, one elected lane issues =====
-        if (P.b_resident && ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(b_full, (uint32_t)(n_bchunks * NF * P.KC * 2));
+        // Resident weights: chunk (tap t9 = kx*3+ky, ch) lives in slot ((kx*chunks + ch)*3 + ky) for TY = 3 and
+        // slot (t9*chunks + ch) for TY = 1, i.e. always slot = stage*TY + ty in the order the MMA warp walks.
+        if (resident && ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(b_full, (uint32_t)n_bchunks * b_bytes);
             for (int t9 = 0; t9 < 9; ++t9)
-                for (int ch = 0; ch < chunks; ++ch)
-                    ptx::tma_load_3d(smem_base + (t9 * chunks + ch) * P.b_bytes, &map_b, b_full, ch * P.KC, 0, t9);
+                for (int ch = 0; ch < chunks; ++ch) {
+                    const int slot = TY == 3 ? ((t9 / 3) * chunks + ch) * 3 + t9 % 3 : t9 * chunks + ch;
+                    ptx::tma_load_3d(smem_base + slot * b_bytes, &map_b, b_full, ch * KC, 0, t9);
+                }
         }
         __syncwarp();
         const int yz = P.Yp * P.Zp;
-        const uint32_t tx = (uint32_t)(P.TY * BM * P.KC * 2) + (P.b_resident ? 0u : (uint32_t)(P.TY * NF * P.KC * 2));
-        const int ny = 3 / P.TY;  // ky steps walked by the producer (1 when a stage holds all three)
+        const uint32_t tx = (uint32_t)TY * (a_bytes + (resident ? 0u : b_bytes));
+        const int ny = 3 / TY;  // ky steps walked by the producer (1 when a stage holds all three)
         uint32_t s = 0, ph = 1;   // ring position and the parity of "slot is free"
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
             const int q0 = tile * ROWS_OUT - 1 + P.pad_rows;
@@ -147,9 +158,9 @@ conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                             const uint32_t a_dst = stage_base + s * stage_bytes;
                             ptx::mbar_arrive_expect_tx(full_bar + 8 * s, tx);
                             // {c, r, w, ky}: TY x (4 groups of 32 rows overlapping by two)
-                            ptx::tma_load_4d(a_dst, &map_a, full_bar + 8 * s, ch * P.KC, row, 0, 0);
-                            if (!P.b_resident)
-                                ptx::tma_load_3d(a_dst + P.TY * P.a_bytes, &map_b, full_bar + 8 * s, ch * P.KC, 0, kx * 3 + kyi);
+                            ptx::tma_load_4d(a_dst, &map_a, full_bar + 8 * s, ch * KC, row, 0, 0);
+                            if (!resident)
+                                ptx::tma_load_3d(a_dst + TY * a_bytes, &map_b, full_bar + 8 * s, ch * KC, 0, kx * 3 + kyi);
                         }
                         __syncwarp();
                         if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
@@ -158,14 +169,15 @@ conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit =====
+        // ===== MMA issuer: warp-uniform flat loop over the stages of a tile, one elected lane issues =====
         const uint32_t idesc = ptx::umma_idesc_bf16(BM, (uint32_t)NF);
-        const uint32_t row_bytes = (uint32_t)P.KC * 2u;
-        const int kk = P.KC / 16;
-        const int ny = 3 / P.TY;
-        // descriptor templates: only the 14-bit start-address field changes inside the loops
-        const uint64_t desc0 = ptx::umma_smem_desc(0, row_bytes);
-        if (P.b_resident) {
+        const int kk = KC / 16;
+        // descriptors are the template below plus a 14-bit start address (>> 4): all steps are additive
+        const uint64_t desc0 = ptx::umma_smem_desc(0, (uint32_t)KC * 2u);
+        const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4, st_step = stage_bytes >> 4;
+        const uint64_t a_base = desc0 | (uint64_t)((stage_base & 0x3FFFFu) >> 4);
+        const uint64_t b_base = desc0 | (uint64_t)(((resident ? smem_base : stage_base + TY * a_bytes) & 0x3FFFFu) >> 4);
+        if (resident) {
             ptx::mbar_wait(b_full, 0);
             ptx::tc_fence_after();
         }
@@ -177,32 +189,27 @@ conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             ptx::mbar_wait(acc_empty + 8 * as, aph ^ 1u);  // epilogue has drained this accumulator stage
             ptx::tc_fence_after();
             const uint32_t d_addr = tmem_d + (uint32_t)(as * P.tmem_half);
-            uint32_t accum = 0;
-            for (int kx = 0; kx < 3; ++kx) {
-                for (int kyi = 0; kyi < ny; ++kyi) {
-                    for (int ch = 0; ch < chunks; ++ch) {
-                        ptx::mbar_wait(full_bar + 8 * s, ph);
-                        ptx::tc_fence_after();
-                        if (ptx::elect_one()) {
-                            const uint32_t a_src = stage_base + s * stage_bytes;
-                            for (int ty = 0; ty < P.TY; ++ty) {
-                                const int t9 = kx * 3 + kyi + ty;
-                                const uint32_t b_src = P.b_resident ? smem_base + (t9 * chunks + ch) * P.b_bytes
-                                                                    : a_src + P.TY * P.a_bytes + ty * P.b_bytes;
-                                const uint64_t a_desc = desc0 | (uint64_t)(((a_src + ty * P.a_bytes) & 0x3FFFFu) >> 4);
-                                const uint64_t b_desc = desc0 | (uint64_t)((b_src & 0x3FFFFu) >> 4);
-                                for (int k = 0; k < kk; ++k) {
-                                    ptx::umma_f16(d_addr, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accum);
-                                    accum = 1;
-                                }
+            for (int i = 0; i < k_iters; ++i) {
+                ptx::mbar_wait(full_bar + 8 * s, ph);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint64_t a_st = a_base + (uint64_t)(s * st_step);
+                    const uint64_t b_st = resident ? b_base + (uint64_t)((uint32_t)(i * TY) * b_step) : b_base + (uint64_t)(s * st_step);
+#pragma unroll
+                    for (int ty = 0; ty < (TY_T > 0 ? TY_T : 3); ++ty) {
+                        if (ty < TY) {
+#pragma unroll
+                            for (int k = 0; k < (KC_T > 0 ? KC_T / 16 : 4); ++k) {
+                                if (k < kk)
+                                    ptx::umma_f16(d_addr, a_st + (uint64_t)(ty * a_step + 2 * k), b_st + (uint64_t)(ty * b_step + 2 * k), idesc,
+                                                  (uint32_t)((i | ty | k) != 0));
                             }
-                            ptx::umma_commit(empty_bar + 8 * s);
                         }
-                        accum = 1;
-                        __syncwarp();
-                        if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
                     }
+                    ptx::umma_commit(empty_bar + 8 * s);
                 }
+                __syncwarp();
+                if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
             }
             if (ptx::elect_one()) ptx::umma_commit(acc_full + 8 * as);
             __syncwarp();
@@ -326,15 +333,27 @@ conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 
 int g_num_sms = 0;
 
+template <int COUT, int KC_T, int TY_T, int RES_T>
+int launch_fold_as(const CUtensorMap& map_a, const CUtensorMap& map_b, const float* bias, bf16* out, double* gn_stats,
+                   const FoldParams& P, size_t smem, cudaStream_t stream) {
+    auto kern = conv3d_bf16_fold_kernel<COUT, KC_T, TY_T, RES_T>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_conv3d_bf16_fold: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    const int grid = P.num_tiles < g_num_sms ? P.num_tiles : g_num_sms;
+    kern<<<grid, THREADS, smem, stream>>>(map_a, map_b, bias, out, gn_stats, P);
+    TDB_CHECK_LAUNCH("tdb_conv3d_bf16_fold");
+    return 0;
+}
+
+// hot shapes of the shapes config get fully specialised kernels; everything else the generic one
 template <int COUT>
 int launch_fold(const CUtensorMap& map_a, const CUtensorMap& map_b, const float* bias, bf16* out, double* gn_stats,
                 const FoldParams& P, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(conv3d_bf16_fold_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_conv3d_bf16_fold: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-    const int grid = P.num_tiles < g_num_sms ? P.num_tiles : g_num_sms;
-    conv3d_bf16_fold_kernel<COUT><<<grid, THREADS, smem, stream>>>(map_a, map_b, bias, out, gn_stats, P);
-    TDB_CHECK_LAUNCH("tdb_conv3d_bf16_fold");
-    return 0;
+    if (P.KC == 64 && P.TY == 1 && !P.b_resident)
+        return launch_fold_as<COUT, 64, 1, 0>(map_a, map_b, bias, out, gn_stats, P, smem, stream);
+    if (P.KC == 32 && P.TY == 3 && P.b_resident)
+        return launch_fold_as<COUT, 32, 3, 1>(map_a, map_b, bias, out, gn_stats, P, smem, stream);
+    return launch_fold_as<COUT, -1, -1, -1>(map_a, map_b, bias, out, gn_stats, P, smem, stream);
 }
 
 }  // namespace
