@@ -11,6 +11,7 @@ namespace {
 
 constexpr int DH = 32;      // head dim == warp size: lane d owns output feature d
 constexpr int WARPS = 8;
+constexpr int QB = 16;     // queries per CTA: grid = (B*heads, ceil(S/QB)) so that even 108 tokens fill ~100 SMs
 
 template <typename T>
 __global__ void __launch_bounds__(WARPS * 32)
@@ -36,7 +37,8 @@ attention_kernel(const T* __restrict__ qkv, int ld_qkv, T* __restrict__ out, int
     __syncthreads();
 
     float* p = sp + (size_t)warp * S;
-    for (int i = warp; i < S; i += WARPS) {
+    const int q_end = min(S, (int)(blockIdx.y + 1) * QB);
+    for (int i = blockIdx.y * QB + warp; i < q_end; i += WARPS) {
         const float* qi = sq + i * (DH + 1);
         float mx = -INFINITY;
         for (int j = lane; j < S; j += 32) {
@@ -80,11 +82,11 @@ extern "C" int tdb_attention(const void* qkv, int ld_qkv, void* out, int ld_out,
     if (dtype == TDB_BF16) {
         e = cudaFuncSetAttribute(attention_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess)
-            attention_kernel<bf16><<<B * heads, WARPS * 32, smem, s>>>((const bf16*)qkv, ld_qkv, (bf16*)out, ld_out, g, heads, S);
+            attention_kernel<bf16><<<dim3((unsigned)(B * heads), (unsigned)((S + QB - 1) / QB)), WARPS * 32, smem, s>>>((const bf16*)qkv, ld_qkv, (bf16*)out, ld_out, g, heads, S);
     } else {
         e = cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess)
-            attention_kernel<float><<<B * heads, WARPS * 32, smem, s>>>((const float*)qkv, ld_qkv, (float*)out, ld_out, g, heads, S);
+            attention_kernel<float><<<dim3((unsigned)(B * heads), (unsigned)((S + QB - 1) / QB)), WARPS * 32, smem, s>>>((const float*)qkv, ld_qkv, (float*)out, ld_out, g, heads, S);
     }
     TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     TDB_CHECK_LAUNCH("tdb_attention");

@@ -42,6 +42,7 @@ struct ConvParams {
     int ld_out;
     int G;              // groups for fused GroupNorm moments (0 = off)
     int all_rows;       // 1: store halo rows too (input-gradient use)
+    int splits;         // split-K factor (gridDim.z); > 1: fp32 partial sums are atomically added to `scratch`
 };
 
 __device__ __forceinline__ bool row_is_interior(int64_t p, const ConvParams& P, int& b) {
@@ -57,7 +58,7 @@ __device__ __forceinline__ bool row_is_interior(int64_t p, const ConvParams& P, 
 __global__ void __launch_bounds__(THREADS)
 conv3d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const float* __restrict__ bias, bf16* __restrict__ out, double* __restrict__ gn_stats,
-                      const ConvParams P) {
+                      float* __restrict__ scratch, const ConvParams P) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment (swizzle-128B atoms) is established by hand; the launcher over-allocates.
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -72,7 +73,12 @@ conv3d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const uint32_t empty_bar = ptx::smem_u32(&bars[MAX_STAGES]);
     const uint32_t accum_bar = ptx::smem_u32(&bars[2 * MAX_STAGES]);
     const int chunks = P.Cin / P.KC;
-    const int k_iters = P.ntaps * chunks;
+    // split-K: this CTA walks k-steps [it_begin, it_end) of the ntaps*chunks (tap, channel-chunk) sequence
+    const int k_total = P.ntaps * chunks;
+    const int k_per = (k_total + P.splits - 1) / P.splits;
+    const int it_begin = (int)blockIdx.z * k_per;
+    const int it_end = min(k_total, it_begin + k_per);
+    const int k_iters = it_end - it_begin;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
@@ -98,21 +104,21 @@ conv3d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const int yz = P.Yp * P.Zp;
         const uint32_t tx = (uint32_t)((BM + P.BN) * P.KC * 2);
         uint32_t s = 0, ph = 1;
-        for (int tap = 0; tap < P.ntaps; ++tap) {
+        int tap = it_begin / chunks, ch = it_begin % chunks;
+        for (int it = it_begin; it < it_end; ++it) {
             int64_t delta = 0;
             if (P.ntaps == 27) delta = (int64_t)(tap / 9 - 1) * yz + (int64_t)((tap / 3) % 3 - 1) * P.Zp + (tap % 3 - 1);
             const int row = (int)(p0 + delta);
-            for (int ch = 0; ch < chunks; ++ch) {
-                ptx::mbar_wait(empty_bar + 8 * s, ph);
-                if (ptx::elect_one()) {
-                    const uint32_t a_dst = smem_base + s * stage_bytes;
-                    ptx::mbar_arrive_expect_tx(full_bar + 8 * s, tx);
-                    ptx::tma_load_2d(a_dst, &map_a, full_bar + 8 * s, ch * P.KC, row);
-                    ptx::tma_load_2d(a_dst + P.a_bytes, &map_b, full_bar + 8 * s, tap * P.Cin + ch * P.KC, n0);
-                }
-                __syncwarp();
-                if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
+            ptx::mbar_wait(empty_bar + 8 * s, ph);
+            if (ptx::elect_one()) {
+                const uint32_t a_dst = smem_base + s * stage_bytes;
+                ptx::mbar_arrive_expect_tx(full_bar + 8 * s, tx);
+                ptx::tma_load_2d(a_dst, &map_a, full_bar + 8 * s, ch * P.KC, row);
+                ptx::tma_load_2d(a_dst + P.a_bytes, &map_b, full_bar + 8 * s, tap * P.Cin + ch * P.KC, n0);
             }
+            __syncwarp();
+            if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
+            if (++ch == chunks) { ch = 0; ++tap; }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
@@ -162,6 +168,17 @@ conv3d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             uint32_t r[16];
             ptx::tmem_ld_x16(t_row + (uint32_t)c, r);
             ptx::tmem_ld_wait();
+            if (scratch) {
+                // split-K partial: fp32 vector reductions into the [rows][Cout] scratch (bias etc. in the finalize pass)
+                if (p < P.rows && k_iters > 0) {
+                    float* dst = scratch + p * P.Cout + n0 + c;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        atomicAdd(reinterpret_cast<float4*>(dst + j),
+                                  make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+                }
+                continue;
+            }
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + n0 + c + j) : 0.0f);
@@ -212,6 +229,28 @@ conv3d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
 }
 
+// split-K finalize: out[p][c] = bf16(scratch[p][c] + bias[c]) on interior rows (all rows with all_rows)
+__global__ void __launch_bounds__(256)
+splitk_finalize_kernel(const float* __restrict__ scratch, const float* __restrict__ bias, bf16* __restrict__ out,
+                       const ConvParams P) {
+    const int chunks = P.Cout / 8;
+    const int64_t total = P.rows * chunks;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = idx / chunks;
+        const int c0 = (int)(idx % chunks) * 8;
+        int b;
+        if (!P.all_rows && !row_is_interior(p, P, b)) continue;
+        const float4 a = *reinterpret_cast<const float4*>(scratch + p * P.Cout + c0);
+        const float4 c = *reinterpret_cast<const float4*>(scratch + p * P.Cout + c0 + 4);
+        float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        if (bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += __ldg(bias + c0 + j);
+        }
+        Vec<bf16>::store(out + p * P.ld_out + c0, v);
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 
 int pick_bn(int cout) {
@@ -224,7 +263,7 @@ int pick_bn(int cout) {
 
 extern "C" int tdb_conv3d_bf16(const void* in, int ld_in, const void* w, const float* bias, void* out, int ld_out,
                                int B, int X, int Y, int Z, int Cin, int Cout, int ntaps, double* gn_stats, int G,
-                               unsigned flags, void* stream) {
+                               unsigned flags, float* splitk_scratch, void* stream) {
     TDB_REQUIRE(in && w && out, TDB_E_BADARG, "tdb_conv3d_bf16: null pointer");
     TDB_REQUIRE(ntaps == 1 || ntaps == 27, TDB_E_BADARG, "tdb_conv3d_bf16: ntaps must be 1 or 27");
     TDB_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0, TDB_E_UNSUPPORTED,
@@ -273,7 +312,35 @@ extern "C" int tdb_conv3d_bf16(const void* in, int ld_in, const void* w, const f
     cudaError_t e = cudaFuncSetAttribute(conv3d_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_conv3d_bf16: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     dim3 grid((unsigned)ceil_div(g.rows, BM), (unsigned)(Cout / P.BN));
-    conv3d_bf16_tc_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, bias, (bf16*)out, gn_stats, P);
-    TDB_CHECK_LAUNCH("tdb_conv3d_bf16");
+    // split-K for the small-M / huge-K layers of the deep levels: few output tiles, hundreds of serial k-steps
+    const int ctas = (int)(grid.x * grid.y);
+    const int k_total = ntaps * (Cin / P.KC);
+    int splits = 1;
+    if (splitk_scratch && ctas < 120 && k_total >= 32) {
+        splits = (2 * 148) / ctas;
+        if (splits > k_total / 8) splits = k_total / 8;
+        if (splits > 16) splits = 16;
+        if (splits < 1) splits = 1;
+        const int k_per = (k_total + splits - 1) / splits;
+        splits = (k_total + k_per - 1) / k_per;  // every split owns at least one k-step
+    }
+    P.splits = splits;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (splits == 1) {
+        conv3d_bf16_tc_kernel<<<grid, THREADS, smem, s>>>(map_a, map_b, bias, (bf16*)out, gn_stats, nullptr, P);
+        TDB_CHECK_LAUNCH("tdb_conv3d_bf16");
+        return 0;
+    }
+    grid.z = (unsigned)splits;
+    e = cudaMemsetAsync(splitk_scratch, 0, (size_t)g.rows * Cout * sizeof(float), s);
+    TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_conv3d_bf16: cudaMemsetAsync: %s", cudaGetErrorString(e));
+    conv3d_bf16_tc_kernel<<<grid, THREADS, smem, s>>>(map_a, map_b, nullptr, (bf16*)out, nullptr, splitk_scratch, P);
+    TDB_CHECK_LAUNCH("tdb_conv3d_bf16 (split-K)");
+    const int64_t items = g.rows * (Cout / 8);
+    int fblocks = (int)ceil_div(items, 256);
+    if (fblocks > 148 * 8) fblocks = 148 * 8;
+    splitk_finalize_kernel<<<fblocks, 256, 0, s>>>(splitk_scratch, bias, (bf16*)out, P);
+    TDB_CHECK_LAUNCH("tdb_conv3d_bf16 (split-K finalize)");
+    if (gn_stats) return tdb_gn_stats(out, ld_out, gn_stats, B, X, Y, Z, Cout, G, TDB_BF16, stream);
     return 0;
 }

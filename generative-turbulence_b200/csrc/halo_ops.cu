@@ -25,7 +25,7 @@ struct RowSplit {
 // ---------------------------------------------------------------- encode_x / encode_c_local
 // grid = (blocks per sample, B).  A thread owns ONE 16-byte channel vector position (its 1x1-conv
 // weights live in registers for the whole kernel) and walks haloed voxels.
-template <typename T>
+template <typename T, int FMAX>
 __global__ void __launch_bounds__(kThreads)
 encode_input_kernel(const float* __restrict__ x, const float* __restrict__ c_local,
                     const float* __restrict__ wx, const float* __restrict__ bx,
@@ -42,12 +42,12 @@ encode_input_kernel(const float* __restrict__ x, const float* __restrict__ c_loc
     const int nf = c_half ? Fc : F;
     const float* w = c_half ? wc + (int64_t)(c0 - dim) * Fc : wx + (int64_t)c0 * F;
     const float* bias = c_half ? bc + (c0 - dim) : bx + c0;
-    float wr[N][8], br[N];
+    float wr[N][FMAX], br[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         br[i] = bias[i];
 #pragma unroll
-        for (int f = 0; f < 8; ++f) wr[i][f] = f < nf ? w[i * nf + f] : 0.0f;
+        for (int f = 0; f < FMAX; ++f) wr[i][f] = f < nf ? w[i * nf + f] : 0.0f;
     }
     const int64_t nvox = (int64_t)g.X * g.Y * g.Z;
     const float* src0 = c_half ? c_local : x + (int64_t)b * F * nvox;
@@ -57,15 +57,15 @@ encode_input_kernel(const float* __restrict__ x, const float* __restrict__ c_loc
         split(r, xp, yp, zp);
         const int xs = clampi(xp - 1, 0, g.X - 1), ys = clampi(yp - 1, 0, g.Y - 1), zs = clampi(zp - 1, 0, g.Z - 1);
         const float* src = src0 + ((int64_t)xs * g.Y + ys) * g.Z + zs;
-        float in[8];
+        float in[FMAX];
 #pragma unroll
-        for (int f = 0; f < 8; ++f) in[f] = f < nf ? __ldg(src + (int64_t)f * nvox) : 0.0f;
+        for (int f = 0; f < FMAX; ++f) in[f] = f < nf ? __ldg(src + (int64_t)f * nvox) : 0.0f;
         float o[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             float acc = br[i];
 #pragma unroll
-            for (int f = 0; f < 8; ++f) acc = fmaf(wr[i][f], in[f], acc);
+            for (int f = 0; f < FMAX; ++f) acc = fmaf(wr[i][f], in[f], acc);
             o[i] = acc;
         }
         Vec<T>::store(out + ((int64_t)b * g.vox_p + r) * ld_out + c0, o);
@@ -344,10 +344,18 @@ int tdb_encode_input(const float* x, const float* c_local, const float* wx, cons
     dim3 grid((unsigned)blocks_per_sample(g.vox_p * chunks, B), (unsigned)B);
     const RowSplit split = make_split(g);
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == TDB_BF16)
-        encode_input_kernel<bf16><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (bf16*)out, ld_out, g, F, Fc, dim, parts, split, chunks);
-    else
-        encode_input_kernel<float><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (float*)out, ld_out, g, F, Fc, dim, parts, split, chunks);
+    const bool small = F <= 4 && Fc <= 4;  // u+p and the 4-d cell-type embedding: keep the weights in 32 registers
+    if (dtype == TDB_BF16) {
+        if (small)
+            encode_input_kernel<bf16, 4><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (bf16*)out, ld_out, g, F, Fc, dim, parts, split, chunks);
+        else
+            encode_input_kernel<bf16, 8><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (bf16*)out, ld_out, g, F, Fc, dim, parts, split, chunks);
+    } else {
+        if (small)
+            encode_input_kernel<float, 4><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (float*)out, ld_out, g, F, Fc, dim, parts, split, chunks);
+        else
+            encode_input_kernel<float, 8><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (float*)out, ld_out, g, F, Fc, dim, parts, split, chunks);
+    }
     TDB_CHECK_LAUNCH("tdb_encode_input");
     return 0;
 }
@@ -379,8 +387,11 @@ int tdb_gn_stats(const void* raw, int ld, double* stats, int B, int X, int Y, in
     Grid3 g(B, X, Y, Z);
     const int chunks = C / n;
     const int vox_step = kThreads / chunks;
-    const int vox_per_block = vox_step * 64;
     const int64_t nvox = (int64_t)X * Y * Z;
+    // <= 64 voxels per thread (fp32 partial sums), fewer on small grids so that the launch still fills the SMs
+    int64_t iters = ceil_div(nvox, (int64_t)vox_step * ((148 * 2) / (B < 1 ? 1 : B) + 1));
+    iters = iters < 1 ? 1 : (iters > 64 ? 64 : iters);
+    const int vox_per_block = vox_step * (int)iters;
     dim3 grid((unsigned)ceil_div(nvox, vox_per_block), (unsigned)B);
     const size_t smem = (size_t)2 * G * sizeof(double);
     cudaStream_t s = (cudaStream_t)stream;

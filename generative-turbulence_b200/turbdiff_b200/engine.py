@@ -185,6 +185,10 @@ class DenoiserEngine:
         p["raw"] = {l: grid(l, c) for l, c in max_c.items()}
         p["act"] = {l: grid(l, c) for l, c in max_c.items()}
         p["res"] = {l: grid(l, c) for l, c in max_c.items()}
+        # fp32 split-K workspace of the tensor-core convolution: large enough for the two deepest levels
+        deep = max(1, L - 1)
+        Xd, Yd, Zd = sizes[deep]
+        p["splitk"] = torch.zeros(B * (Xd + 2) * (Yd + 2) * (Zd + 2) * 1024, dtype=torch.float32, device=device)
         p["grid"] = grid  # allocator for the (lazily built) training buffers
         p["max_c"] = max_c
         n_norms = 2 * len(self.blocks) + 1
@@ -225,8 +229,10 @@ class DenoiserEngine:
             call("tdb_conv3d_bf16_fold", x.ptr, x.ld, self.pad_rows((X, Y, Z)), w.data_ptr(), ptr(bias), out.ptr, out.ld,
                  B, X, Y, Z, x.C, out.C, ptr(stats), G, flags, s)
         else:
+            rows = B * (X + 2) * (Y + 2) * (Z + 2)
+            scratch = p["splitk"] if rows * out.C <= p["splitk"].numel() else None
             call("tdb_conv3d_bf16", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ntaps,
-                 ptr(stats), G, flags, s)
+                 ptr(stats), G, flags, ptr(scratch), s)
 
     def _stats(self, p, x: View, stats, G):
         X, Y, Z = p["sizes"][x.level]
@@ -312,7 +318,8 @@ class DenoiserEngine:
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward(self, x: torch.Tensor, t: torch.Tensor, c_local: torch.Tensor | None, taps: dict | None = None, train: bool = False):
+    def forward(self, x: torch.Tensor, t: torch.Tensor, c_local: torch.Tensor | None, taps: dict | None = None, train: bool = False,
+                c_static: bool = False):
         """eps = U-Net(x, t, c_local).  x (B,F,X,Y,Z) fp32 CUDA contiguous, t int64 (B,).
         train=True keeps every block's intermediates in dedicated buffers for `backward`."""
         m = self.model
@@ -342,9 +349,14 @@ class DenoiserEngine:
              pc[0].bias.data_ptr(), pc[2].weight.data_ptr(), pc[2].bias.data_ptr(), w["film_w"].data_ptr(),
              w["film_b"].data_ptr(), p["c"].data_ptr(), p["film"].data_ptr(), B, m.dim, self.film_rows, s)
         xin0 = p["xin0"]
+        # encode_c_local(c_local) does not depend on the step (the reference recomputes it, ddpm.py:480 TODO):
+        # its half of the concat buffer is rewritten only when c_local or the encoder weights changed
+        # (c_static=True is the caller's promise that c_local and the weights are those of the previous call on this plan)
+        parts = 1 if (c_static and Fc > 0 and p.get("c_valid") and not train) else 3
+        p["c_valid"] = Fc > 0
         call("tdb_encode_input", x.data_ptr(), ptr(c_local), m.encode_x.weight.data_ptr(), m.encode_x.bias.data_ptr(),
              ptr(m.encode_c_local.weight) if Fc > 0 else None, ptr(m.encode_c_local.bias) if Fc > 0 else None,
-             xin0.ptr, xin0.ld, B, F, Fc, m.dim, X, Y, Z, 3, self.dt, s)
+             xin0.ptr, xin0.ld, B, F, Fc, m.dim, X, Y, Z, parts, self.dt, s)
 
         def tap(name, v: View):
             if taps is not None:

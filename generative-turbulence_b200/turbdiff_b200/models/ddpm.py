@@ -410,10 +410,13 @@ class GaussianDiffusion(nn.Module):
             from tqdm.auto import tqdm
 
             steps = tqdm(steps, desc="sampling loop time step", total=T, position=1)
+        first = True
         for t in steps:
             t_dev.fill_(t)
             t_vec.fill_(t)
-            eps = eng.forward(x_t, t_vec, c_local)
+            # C is constant along the chain: encode_c_local's half of the input buffer is written once
+            eps = eng.forward(x_t, t_vec, c_local, c_static=not first)
+            first = False
             if t > 0:
                 z = torch.randn_like(x_t)
                 z_bc = torch.randn_like(x_bcs) if self.noise_bcs else None

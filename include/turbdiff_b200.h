@@ -90,10 +90,12 @@ TDB_API int tdb_conv3d_f32(const float* in, int ld_in, const float* w, const flo
  * operand tiles; fp32 accumulation.  w: packed [Cout][ntaps*Cin] bf16 (k = tap*Cin + ci).
  * Cin % 16 == 0, Cout % 16 == 0, ld_in % 8 == 0, ld_out % 8 == 0.
  * gn_stats (nullable): double [B][G][2] (sum, sum of squares) accumulated from the fp32
- * accumulators over interior voxels, G groups of Cout/G channels. */
+ * accumulators over interior voxels, G groups of Cout/G channels.
+ * splitk_scratch (nullable): fp32 [rows][Cout] workspace; when given, layers with few output tiles
+ * and a long K loop (the deep U-Net levels) are split along K over up to 16 CTAs per tile. */
 TDB_API int tdb_conv3d_bf16(const void* in, int ld_in, const void* w, const float* bias, void* out,
                     int ld_out, int B, int X, int Y, int Z, int Cin, int Cout, int ntaps,
-                    double* gn_stats, int G, unsigned flags, void* stream);
+                    double* gn_stats, int G, unsigned flags, float* splitk_scratch, void* stream);
 
 /* Same convolution (3x3x3 only) for narrow layers, Cout in {16,32,64}: the kz filter axis is folded
  * into the GEMM N dimension (9 row-shifted A boxes instead of 27, 3x wider MMAs), persistent CTAs,

@@ -43,7 +43,7 @@ t_vec = torch.full((B,), 500, dtype=torch.int64, device=dev)
 
 
 def step():
-    eps = eng.forward(x_t, t_vec, cl)
+    eps = eng.forward(x_t, t_vec, cl, c_static=True)
     z, zb = torch.randn_like(x_t), torch.randn_like(x_bcs)
     _lib.call("tdb_ddpm_step", x_t.data_ptr(), eps.data_ptr(), z.data_ptr(), zb.data_ptr(), x_bcs.data_ptr(), mask.data_ptr(),
               coef.data_ptr(), t_dev.data_ptr(), x_t.data_ptr(), B, 4, nvox, _lib.STEP_NOISE_BCS, _lib.stream_ptr())

@@ -70,9 +70,10 @@ def test_conv3d_f32(lib, case):
     assert rel_l2(from_halo(out), want) < 1e-5
 
 
-@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("case", CONV_CASES + [(2, 12, 3, 3, 512, 512, 27), (1, 6, 6, 6, 1024, 256, 27)])
 @pytest.mark.parametrize("fused_stats", [False, True])
-def test_conv3d_bf16_tensor_core(lib, case, fused_stats):
+@pytest.mark.parametrize("splitk", [False, True])
+def test_conv3d_bf16_tensor_core(lib, case, fused_stats, splitk):
     B, X, Y, Z, Cin, Cout, ntaps = case
     k = 3 if ntaps == 27 else 1
     x = gen(B, Cin, X, Y, Z, seed=1).bfloat16().float()
@@ -83,16 +84,18 @@ def test_conv3d_bf16_tensor_core(lib, case, fused_stats):
     out = torch.zeros((B, X + 2, Y + 2, Z + 2, Cout), device="cuda", dtype=torch.bfloat16)
     G = 8
     stats = torch.zeros((B, G, 2), dtype=torch.float64, device="cuda")
+    scratch = torch.empty(B * (X + 2) * (Y + 2) * (Z + 2) * Cout, dtype=torch.float32, device="cuda") if splitk else None
     lib.call("tdb_conv3d_bf16", xin.data_ptr(), Cin, wp.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
-             ntaps, stats.data_ptr() if fused_stats else None, G, 0, lib.stream_ptr())
+             ntaps, stats.data_ptr() if fused_stats else None, G, 0, lib.ptr(scratch), lib.stream_ptr())
     torch.cuda.synchronize()
     want = _conv_ref(x.double().cpu(), w.double().cpu(), b.double().cpu(), ntaps)
     # inputs are exactly representable in bf16, accumulation is fp32: only the bf16 output rounding remains
     assert rel_l2(from_halo(out), want) < 4e-3
     if fused_stats:
         wg = want.reshape(B, G, -1)
-        np.testing.assert_allclose(stats[..., 0].cpu().numpy(), wg.sum(-1).numpy(), rtol=1e-4, atol=1e-2)
-        np.testing.assert_allclose(stats[..., 1].cpu().numpy(), (wg**2).sum(-1).numpy(), rtol=1e-4)
+        # with split-K the moments are taken from the bf16-rounded output
+        np.testing.assert_allclose(stats[..., 0].cpu().numpy(), wg.sum(-1).numpy(), rtol=1e-4, atol=1e-2 if not splitk else 0.5)
+        np.testing.assert_allclose(stats[..., 1].cpu().numpy(), (wg**2).sum(-1).numpy(), rtol=1e-4 if not splitk else 2e-3)
 
 
 FOLD_CASES = [c for c in CONV_CASES if c[6] == 27 and c[5] in (16, 32, 64)] + [
