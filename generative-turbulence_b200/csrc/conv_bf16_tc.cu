@@ -42,6 +42,7 @@ struct ConvParams {
     int ld_out;
     int G;              // groups for fused GroupNorm moments (0 = off)
     int all_rows;       // 1: store halo rows too (input-gradient use)
+    int mc;             // 1: launched as 2-CTA clusters along M, the weight tile is fetched once per cluster (TMA multicast)
     int splits;         // split-K factor (gridDim.z); > 1: fp32 partial sums are atomically added to `scratch`
 };
 
@@ -85,7 +86,7 @@ conv3d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         ptx::prefetch_tensormap(&map_b);
         for (int s = 0; s < P.stages; ++s) {
             ptx::mbar_init(full_bar + 8 * s, 1);
-            ptx::mbar_init(empty_bar + 8 * s, 1);
+            ptx::mbar_init(empty_bar + 8 * s, P.mc ? 2 : 1);  // with multicast both CTAs' MMAs must release a slot
         }
         ptx::mbar_init(accum_bar, 1);
         ptx::fence_barrier_init();
@@ -96,6 +97,7 @@ conv3d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (P.mc) ptx::cluster_sync();  // the peer's barriers are initialised before anything can arrive on them
     ptx::tc_fence_after();
     const uint32_t tmem_d = tmem_base_slot;
 
@@ -114,7 +116,14 @@ conv3d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 const uint32_t a_dst = smem_base + s * stage_bytes;
                 ptx::mbar_arrive_expect_tx(full_bar + 8 * s, tx);
                 ptx::tma_load_2d(a_dst, &map_a, full_bar + 8 * s, ch * P.KC, row);
-                ptx::tma_load_2d(a_dst + P.a_bytes, &map_b, full_bar + 8 * s, tap * P.Cin + ch * P.KC, n0);
+                if (P.mc) {
+                    // each CTA of the pair fetches one half of the weight tile and multicasts it to both
+                    const uint32_t half_rows = (uint32_t)P.BN / 2, rank = ptx::cluster_ctarank();
+                    ptx::tma_load_2d_mc(a_dst + P.a_bytes + rank * half_rows * (uint32_t)P.KC * 2u, &map_b, full_bar + 8 * s,
+                                        tap * P.Cin + ch * P.KC, n0 + (int)(rank * half_rows), (uint16_t)0x3);
+                } else {
+                    ptx::tma_load_2d(a_dst + P.a_bytes, &map_b, full_bar + 8 * s, tap * P.Cin + ch * P.KC, n0);
+                }
             }
             __syncwarp();
             if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
@@ -139,7 +148,9 @@ conv3d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     ptx::umma_f16(tmem_d, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accum);
                     accum = 1;
                 }
-                ptx::umma_commit(empty_bar + 8 * s);  // smem slot reusable once these MMAs retire
+                // smem slot reusable once these MMAs retire (in BOTH CTAs when the weight tile is shared)
+                if (P.mc) ptx::umma_commit_mc(empty_bar + 8 * s, (uint16_t)0x3);
+                else ptx::umma_commit(empty_bar + 8 * s);
             }
             accum = 1;
             __syncwarp();
@@ -223,6 +234,7 @@ conv3d_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (P.mc) ptx::cluster_sync();  // no CTA leaves while its peer can still write into it / signal its barriers
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_d, (uint32_t)P.tmem_cols);
@@ -304,14 +316,19 @@ extern "C" int tdb_conv3d_bf16(const void* in, int ld_in, const void* w, const f
     TDB_REQUIRE(encode_fn() != nullptr, TDB_E_NODEVICE, "tdb_conv3d_bf16: cuTensorMapEncodeTiled unavailable (no driver)");
     TDB_REQUIRE(make_map_2d_bf16(&map_a, in, (uint64_t)Cin, (uint64_t)g.rows, (uint64_t)ld_in, (uint32_t)P.KC, BM), TDB_E_BADARG,
                 "tdb_conv3d_bf16: tensor map (activations) rejected");
+    // Opt-in: 2-CTA clusters along M share the weight tile (TMA multicast).  Measured on B200 (round 1) this is
+    // 5-10 % SLOWER than independent CTAs: these layers are bound by the per-SM shared-memory ingest
+    // (~60 B/clk/SM), which multicast does not reduce - kept for the cta_group::2 follow-up.
+    P.mc = ((flags & TDB_CONV_CLUSTER_MC) && ceil_div(g.rows, BM) >= 8 && P.BN % 16 == 0) ? 1 : 0;
     TDB_REQUIRE(make_map_2d_bf16(&map_b, w, (uint64_t)ntaps * Cin, (uint64_t)Cout, (uint64_t)ntaps * Cin, (uint32_t)P.KC,
-                            (uint32_t)P.BN),
+                            (uint32_t)(P.mc ? P.BN / 2 : P.BN)),
                 TDB_E_BADARG, "tdb_conv3d_bf16: tensor map (weights) rejected");
 
     const size_t smem = (size_t)stages * stage_bytes + 1024;
     cudaError_t e = cudaFuncSetAttribute(conv3d_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_conv3d_bf16: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     dim3 grid((unsigned)ceil_div(g.rows, BM), (unsigned)(Cout / P.BN));
+    if (P.mc) grid.x = (grid.x + 1) & ~1u;  // whole clusters; a surplus CTA computes (and stores) nothing
     // split-K for the small-M / huge-K layers of the deep levels: few output tiles, hundreds of serial k-steps
     const int ctas = (int)(grid.x * grid.y);
     const int k_total = ntaps * (Cin / P.KC);
@@ -326,15 +343,33 @@ extern "C" int tdb_conv3d_bf16(const void* in, int ld_in, const void* w, const f
     }
     P.splits = splits;
     cudaStream_t s = (cudaStream_t)stream;
+    auto launch = [&](const float* bias_, double* stats_, float* scratch_) -> cudaError_t {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = P.mc ? 2 : 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        bf16* out_ = (bf16*)out;
+        return cudaLaunchKernelEx(&cfg, conv3d_bf16_tc_kernel, map_a, map_b, bias_, out_, stats_, scratch_, P);
+    };
     if (splits == 1) {
-        conv3d_bf16_tc_kernel<<<grid, THREADS, smem, s>>>(map_a, map_b, bias, (bf16*)out, gn_stats, nullptr, P);
+        e = launch(bias, gn_stats, nullptr);
+        TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_conv3d_bf16: launch: %s", cudaGetErrorString(e));
         TDB_CHECK_LAUNCH("tdb_conv3d_bf16");
         return 0;
     }
     grid.z = (unsigned)splits;
     e = cudaMemsetAsync(splitk_scratch, 0, (size_t)g.rows * Cout * sizeof(float), s);
     TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_conv3d_bf16: cudaMemsetAsync: %s", cudaGetErrorString(e));
-    conv3d_bf16_tc_kernel<<<grid, THREADS, smem, s>>>(map_a, map_b, nullptr, (bf16*)out, nullptr, splitk_scratch, P);
+    e = launch(nullptr, nullptr, splitk_scratch);
+    TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_conv3d_bf16: launch (split-K): %s", cudaGetErrorString(e));
     TDB_CHECK_LAUNCH("tdb_conv3d_bf16 (split-K)");
     const int64_t items = g.rows * (Cout / 8);
     int fblocks = (int)ceil_div(items, 256);

@@ -16,6 +16,7 @@ F32, BF16 = 0, 1
 PW_SILU, PW_NOHALO = 1, 2
 STEP_NOISE_BCS, STEP_CLIP, STEP_FINAL = 1, 2, 4
 CONV_ALL_ROWS = 1
+CONV_CLUSTER_MC = 2
 
 _p, _i, _l, _u, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint, C.c_float
 

@@ -50,6 +50,7 @@ extern "C" {
 
 /* convolution flags (tdb_conv3d_bf16, tdb_conv3d_bf16_fold) */
 #define TDB_CONV_ALL_ROWS 1u /* also store the halo rows of the output (input-gradient convolutions) */
+#define TDB_CONV_CLUSTER_MC 2u /* tdb_conv3d_bf16: share weight tiles across a 2-CTA cluster by TMA multicast (opt-in) */
 
 /* ddpm step flags (tdb_ddpm_step) */
 #define TDB_STEP_NOISE_BCS 1u /* GaussianDiffusion(noise_bcs=True)  */

@@ -72,8 +72,8 @@ def test_conv3d_f32(lib, case):
 
 @pytest.mark.parametrize("case", CONV_CASES + [(2, 12, 3, 3, 512, 512, 27), (1, 6, 6, 6, 1024, 256, 27)])
 @pytest.mark.parametrize("fused_stats", [False, True])
-@pytest.mark.parametrize("splitk", [False, True])
-def test_conv3d_bf16_tensor_core(lib, case, fused_stats, splitk):
+@pytest.mark.parametrize("splitk,multicast", [(False, False), (True, False), (False, True)])
+def test_conv3d_bf16_tensor_core(lib, case, fused_stats, splitk, multicast):
     B, X, Y, Z, Cin, Cout, ntaps = case
     k = 3 if ntaps == 27 else 1
     x = gen(B, Cin, X, Y, Z, seed=1).bfloat16().float()
@@ -86,7 +86,7 @@ def test_conv3d_bf16_tensor_core(lib, case, fused_stats, splitk):
     stats = torch.zeros((B, G, 2), dtype=torch.float64, device="cuda")
     scratch = torch.empty(B * (X + 2) * (Y + 2) * (Z + 2) * Cout, dtype=torch.float32, device="cuda") if splitk else None
     lib.call("tdb_conv3d_bf16", xin.data_ptr(), Cin, wp.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
-             ntaps, stats.data_ptr() if fused_stats else None, G, 0, lib.ptr(scratch), lib.stream_ptr())
+             ntaps, stats.data_ptr() if fused_stats else None, G, lib.CONV_CLUSTER_MC if multicast else 0, lib.ptr(scratch), lib.stream_ptr())
     torch.cuda.synchronize()
     want = _conv_ref(x.double().cpu(), w.double().cpu(), b.double().cpu(), ntaps)
     # inputs are exactly representable in bf16, accumulation is fp32: only the bf16 output rounding remains
