@@ -45,7 +45,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4, help="samples per GPU per step")
+    ap.add_argument("--batch", type=int, default=8, help="samples per GPU per sampling step (configs[2]: 64 samples over 8 GPUs)")
+    ap.add_argument("--train-batch", type=int, default=4, help="samples per GPU per training step (configs[1]: batch 4)")
     ap.add_argument("--timesteps", type=int, default=1000, help="T of the sampled chain (BASELINE configs[2]: 1000)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--e2e-steps", type=int, default=8, help="chain length of one end-to-end public-API call")
@@ -376,9 +377,12 @@ def run_ours(args):
 
         MD.cell_idx = cell_idx
 
+        TB = min(args.train_batch, B)
+        x_train = x_bcs[:TB].contiguous()
+
         def train_step():
             opt.zero_grad(set_to_none=True)
-            loss, _ = gd(x_bcs, C, MD, None)
+            loss, _ = gd(x_train, C, MD, None)
             loss.backward()
             reducer()
             torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
@@ -396,10 +400,18 @@ def run_ours(args):
         tt = torch.tensor([e0.elapsed_time(e1) / args.train_steps], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        train = {"steps_per_sec": 1e3 / float(tt.item()), "ms_per_step": float(tt.item()), "batch_per_gpu": B, "global_batch": B * world,
+        train_prof = None
+        if rank == 0:
+            _lib.PROFILE = {}
+            train_step()
+            torch.cuda.synchronize()
+            train_prof = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in _lib.PROFILE.items()}
+            _lib.PROFILE = None
+        train = {"steps_per_sec": 1e3 / float(tt.item()), "ms_per_step": float(tt.item()), "batch_per_gpu": TB, "global_batch": TB * world,
+                 "kernel_ms_per_step": train_prof,
                  "loss": float(loss.item()), "kernel_launches_per_step": (_lib.launch_count() - n_t0) // args.train_steps,
                  "includes": "q_sample + U-Net forward + backward + bucketed NCCL gradient all-reduce (N>1) + clip_grad_norm(0.1) + RAdam step",
-                 "train_flops_per_step": 3 * conv_flops_per_sample(spec, geo.padded) * B}
+                 "train_flops_per_step": 3 * conv_flops_per_sample(spec, geo.padded) * TB}
         train["tflops"] = train["train_flops_per_step"] / (train["ms_per_step"] * 1e-3) / 1e12
         model.eval()
 

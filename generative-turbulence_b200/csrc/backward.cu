@@ -9,6 +9,8 @@
 //   tdb_trilinear_bwd        transpose of the align_corners trilinear resampling (gather form)
 //   tdb_attention_bwd        softmax-attention backward per (sample, head)
 //   tdb_cl_nc_outer          out[c][f] = sum_{b,v} G[b,v][c] * Q[b][f][v]  (1x1 encoder/decoder weight grads)
+#include <mma.h>
+
 #include "common.cuh"
 
 using namespace tdb;
@@ -291,6 +293,73 @@ conv_wgrad_kernel(const T* __restrict__ in, int ld_in, const T* __restrict__ d_o
         }
 }
 
+// bf16 variant on the warp-level tensor-core path (wmma, fp32 accumulators): same tiling (64x64 per tap over a
+// row slice, 8 warps = 4 (ci) x 2 (co), two 16x16 accumulators each), 64-row K chunks staged in shared memory
+// with 16-byte loads.  d_out must be ZERO on halo rows and `in` must be readable for Yp*Zp+Zp+1 rows before and
+// after the grid (the halo-grid workspace guarantees both), so no per-row masking is needed.
+// (Stepping stone: a tcgen05 wgrad with MN-major operands is the follow-up.)
+__global__ void __launch_bounds__(256)
+conv_wgrad_wmma_kernel(const bf16* __restrict__ in, int ld_in, const bf16* __restrict__ d_out, int ld_do, float* __restrict__ dw,
+                       int64_t rows, int yz_p, int z_p, int Cin, int Cout, int ntaps, int ci_tiles, int co_tiles, int rows_per_block) {
+    using namespace nvcuda;
+    constexpr int KR = 64, LDS = 64 + 8;
+    __shared__ __align__(32) bf16 sbuf[2 * KR * LDS];
+    bf16 (*As)[LDS] = reinterpret_cast<bf16 (*)[LDS]>(sbuf);             // [row][ci] -> matrix_a col_major (m = ci, k = row)
+    bf16 (*Bs)[LDS] = reinterpret_cast<bf16 (*)[LDS]>(sbuf + KR * LDS);  // [row][co] -> matrix_b row_major (k = row, n = co)
+    const int tile = blockIdx.y;
+    const int tap = tile / (ci_tiles * co_tiles);
+    const int ci0 = ((tile / co_tiles) % ci_tiles) * 64;
+    const int co0 = (tile % co_tiles) * 64;
+    int64_t delta = 0;
+    if (ntaps == 27) delta = (int64_t)(tap / 9 - 1) * yz_p + (int64_t)((tap / 3) % 3 - 1) * z_p + (tap % 3 - 1);
+    const int tid = threadIdx.x, warp = tid / 32;
+    const int wm = warp % 4, wn = warp / 4;  // warp tile: ci [16*wm, +16), co [32*wn, +32)
+    wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[2];
+    wmma::fill_fragment(acc[0], 0.0f);
+    wmma::fill_fragment(acc[1], 0.0f);
+    const int lr = tid / 8, lc = (tid % 8) * 8;  // loader: rows lr and lr+32, 8 consecutive channels
+    const bool a_ok = ci0 + lc < Cin, b_ok = co0 + lc < Cout;
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r_end = min(rows, r_begin + rows_per_block);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += KR) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t p = r0 + lr + 32 * h;
+            uint4 a = zero, b = zero;
+            if (p < r_end) {
+                if (a_ok) a = *reinterpret_cast<const uint4*>(in + (p + delta) * ld_in + ci0 + lc);
+                if (b_ok) b = *reinterpret_cast<const uint4*>(d_out + p * ld_do + co0 + lc);
+            }
+            *reinterpret_cast<uint4*>(&As[lr + 32 * h][lc]) = a;
+            *reinterpret_cast<uint4*>(&Bs[lr + 32 * h][lc]) = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < KR; k += 16) {
+            wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::col_major> fa;
+            wmma::load_matrix_sync(fa, &As[k][16 * wm], LDS);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::row_major> fb;
+                wmma::load_matrix_sync(fb, &Bs[k][32 * wn + 16 * j], LDS);
+                wmma::mma_sync(acc[j], fa, fb, acc[j]);
+            }
+        }
+        __syncthreads();
+    }
+    // accumulators -> shared (reuse As as fp32 scratch) -> fp32 atomics
+    float* cs = reinterpret_cast<float*>(sbuf);  // 64 x 64 floats = 16 KB
+    static_assert(sizeof(sbuf) >= 64 * 64 * sizeof(float), "scratch");
+#pragma unroll
+    for (int j = 0; j < 2; ++j) wmma::store_matrix_sync(cs + (16 * wm) * 64 + 32 * wn + 16 * j, acc[j], 64, wmma::mem_row_major);
+    __syncthreads();
+    for (int i = tid; i < 64 * 64; i += 256) {
+        const int ci = ci0 + i / 64, co = co0 + i % 64;
+        if (ci < Cin && co < Cout) atomicAdd(&dw[((int64_t)tap * Cin + ci) * Cout + co], cs[i]);
+    }
+}
+
 // ---------------------------------------------------------------- trilinear backward (gather)
 struct Lerp {
     int i0, i1;
@@ -539,7 +608,7 @@ int tdb_pointwise_bwd_apply(const void* g_out, int ld_g, const void* raw, int ld
 }
 
 int tdb_conv3d_wgrad(const void* in, int ld_in, const void* d_out, int ld_do, float* dw, int B, int X, int Y, int Z, int Cin,
-                     int Cout, int ntaps, int dtype, void* stream) {
+                     int Cout, int ntaps, int dtype, unsigned flags, void* stream) {
     TDB_REQUIRE(in && d_out && dw, TDB_E_BADARG, "tdb_conv3d_wgrad: null pointer");
     TDB_REQUIRE(ntaps == 1 || ntaps == 27, TDB_E_BADARG, "tdb_conv3d_wgrad: ntaps must be 1 or 27");
     Grid3 g(B, X, Y, Z);
@@ -558,7 +627,14 @@ int tdb_conv3d_wgrad(const void* in, int ld_in, const void* d_out, int ld_do, fl
     rows_per_block = ceil_div(rows_per_block, 16) * 16;
     dim3 grid((unsigned)ceil_div(g.rows, rows_per_block), (unsigned)tiles);
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == TDB_BF16)
+    const bool tensor_path = dtype == TDB_BF16 && (flags & TDB_WGRAD_ZERO_HALO) && Cin % 8 == 0 && Cout % 8 == 0 && ld_in % 8 == 0 &&
+                             ld_do % 8 == 0 && aligned16(in) && aligned16(d_out);
+    if (tensor_path) {
+        rows_per_block = ceil_div(rows_per_block, 64) * 64;
+        grid.x = (unsigned)ceil_div(g.rows, rows_per_block);
+        conv_wgrad_wmma_kernel<<<grid, 256, 0, s>>>((const bf16*)in, ld_in, (const bf16*)d_out, ld_do, dw, g.rows, g.Yp * g.Zp, g.Zp, Cin,
+                                                    Cout, ntaps, ci_tiles, co_tiles, (int)rows_per_block);
+    } else if (dtype == TDB_BF16)
         conv_wgrad_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)in, ld_in, (const bf16*)d_out, ld_do, dw, g.rows, g.Yp * g.Zp, g.Zp,
                                                      Cin, Cout, ntaps, ci_tiles, co_tiles, (int)rows_per_block, it);
     else

@@ -17,6 +17,7 @@ PW_SILU, PW_NOHALO = 1, 2
 STEP_NOISE_BCS, STEP_CLIP, STEP_FINAL = 1, 2, 4
 CONV_ALL_ROWS = 1
 CONV_CLUSTER_MC = 2
+WGRAD_ZERO_HALO = 1
 
 _p, _i, _l, _u, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint, C.c_float
 
@@ -38,7 +39,7 @@ SIGNATURES = {
     "tdb_halo_fold": [_p, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_pointwise_bwd_reduce": [_p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _f, _u, _i, _p],
     "tdb_pointwise_bwd_apply": [_p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _u, _i, _p],
-    "tdb_conv3d_wgrad": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "tdb_conv3d_wgrad": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _u, _p],
     "tdb_trilinear_bwd": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_attention_bwd": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_cl_nc_outer": [_p, _i, _p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _p],

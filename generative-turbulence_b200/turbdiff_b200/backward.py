@@ -67,11 +67,12 @@ class BackwardProgram:
         X, Y, Z = p["sizes"][g.level]
         call("tdb_halo_fold", g.ptr, g.ld, p["B"], X, Y, Z, g.C, self.eng.dt, _lib.stream_ptr())
 
-    def _wgrad(self, p, x: View, d_out: View, conv, ntaps):
+    def _wgrad(self, p, x: View, d_out: View, conv, ntaps, zero_halo=False):
+        """zero_halo: d_out comes from tdb_pointwise_bwd_apply (halo rows are zero) - lets the bf16 path use tensor cores."""
         X, Y, Z = p["sizes"][x.level]
         dw = torch.zeros((ntaps, x.C, d_out.C), dtype=torch.float32, device=x.t.device)
         call("tdb_conv3d_wgrad", x.ptr, x.ld, d_out.ptr, d_out.ld, dw.data_ptr(), p["B"], X, Y, Z, x.C, d_out.C, ntaps, self.eng.dt,
-             _lib.stream_ptr())
+             _lib.WGRAD_ZERO_HALO if zero_halo else 0, _lib.stream_ptr())
         k = 3 if ntaps == 27 else 1
         return dw.view(k, k, k, x.C, d_out.C).permute(4, 3, 0, 1, 2).contiguous()
 
@@ -132,7 +133,7 @@ class BackwardProgram:
         a1, a2 = self._pw_bwd(p, g_out, sv["raw2"], p["stats"][slot + 1], blk.block2.norm, None, d_raw, PW_SILU, G)
         grads[f"{pre}.block2.norm.weight"] = a2.sum(0).float()
         grads[f"{pre}.block2.norm.bias"] = a1.sum(0).float()
-        grads[f"{pre}.block2.conv.weight"] = self._wgrad(p, sv["act1"], d_raw, blk.block2.conv, 27)
+        grads[f"{pre}.block2.conv.weight"] = self._wgrad(p, sv["act1"], d_raw, blk.block2.conv, 27, zero_halo=True)
         grads[f"{pre}.block2.conv.bias"] = self._colsum(p, d_raw)
         eng._conv(p, d_raw, self._dgrad_weights(blk.block2.conv, f"{name}.conv2"), None, g_act, 27, all_rows=True)
         self._fold(p, g_act)
@@ -145,7 +146,7 @@ class BackwardProgram:
         grads[f"{pre}.block1.norm.bias"] = (sc1 * a1).sum(0).float()
         d_film[:, bp.film_offset : bp.film_offset + C] = (gam * a2 + bet * a1).float()
         d_film[:, bp.film_offset + C : bp.film_offset + 2 * C] = a1.float()
-        grads[f"{pre}.block1.conv.weight"] = self._wgrad(p, x, d_raw, blk.block1.conv, 27)
+        grads[f"{pre}.block1.conv.weight"] = self._wgrad(p, x, d_raw, blk.block1.conv, 27, zero_halo=True)
         grads[f"{pre}.block1.conv.bias"] = self._colsum(p, d_raw)
         g_x = self._gbuf(p, x, ("g", name))
         eng._conv(p, d_raw, self._dgrad_weights(blk.block1.conv, f"{name}.conv1"), None, g_x, 27, all_rows=True)

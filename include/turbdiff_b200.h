@@ -207,9 +207,12 @@ TDB_API int tdb_pointwise_bwd_apply(const void* g_out, int ld_g, const void* raw
                             float eps, unsigned flags, int dtype, void* stream);
 
 /* Weight gradient of tdb_conv3d_*: dw[tap][ci][co] += sum over interior rows p of
- * in[p+delta(tap)][ci]*d_out[p][co]; dw fp32 [ntaps][Cin][Cout], accumulated (pre-zero it). */
+ * in[p+delta(tap)][ci]*d_out[p][co]; dw fp32 [ntaps][Cin][Cout], accumulated (pre-zero it).
+ * flags & TDB_WGRAD_ZERO_HALO: the caller guarantees that d_out is zero on halo rows and that `in` is readable
+ * Yp*Zp+Zp+1 rows before/after the grid; the bf16 path then runs on tensor cores without per-row masking. */
+#define TDB_WGRAD_ZERO_HALO 1u
 TDB_API int tdb_conv3d_wgrad(const void* in, int ld_in, const void* d_out, int ld_do, float* dw, int B, int X, int Y,
-                     int Z, int Cin, int Cout, int ntaps, int dtype, void* stream);
+                     int Z, int Cin, int Cout, int ntaps, int dtype, unsigned flags, void* stream);
 
 /* Transpose of tdb_trilinear: d_in (interior rows; halo rows zero) from the folded output gradient. */
 TDB_API int tdb_trilinear_bwd(const void* g_out, int ld_g, int Xo, int Yo, int Zo, void* d_in, int ld_d, int Xi,
