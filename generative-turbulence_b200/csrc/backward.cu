@@ -118,7 +118,8 @@ __device__ __forceinline__ PwCoef pw_coef(int b, int c, int C, int G, const doub
     return r;
 }
 
-// red[b][c] = (sum g_u, sum g_u*xhat) over interior voxels, double atomics (pre-zeroed)
+// red[b][c] = (sum g_u, sum g_u*xhat) over interior voxels (pre-zeroed): fp32 per thread (<= 32 voxels), fp32 shared
+// atomics per CTA, one double atomic per (CTA, channel, moment)
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 pw_bwd_reduce_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict__ raw, int ld_raw,
@@ -126,44 +127,50 @@ pw_bwd_reduce_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict_
                      const float* __restrict__ film, int film_ld, double* __restrict__ red, Grid3 gr, int C, int G, float eps,
                      unsigned flags, int vox_per_block) {
     constexpr int N = Vec<T>::N;
+    extern __shared__ float sred[];  // [C][2]
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.0f;
+    __syncthreads();
     const int b = blockIdx.y;
     const int chunks = C / N;
     const int vox_step = kThreads / chunks;
     const int ch = threadIdx.x % chunks, lane_vox = threadIdx.x / chunks;
-    if (lane_vox >= vox_step) return;
-    const int c0 = ch * N;
-    const double inv_n = 1.0 / ((double)(C / G) * gr.X * gr.Y * gr.Z);
-    PwCoef k[N];
+    if (lane_vox < vox_step) {
+        const int c0 = ch * N;
+        const double inv_n = 1.0 / ((double)(C / G) * gr.X * gr.Y * gr.Z);
+        PwCoef k[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) k[i] = pw_coef(b, c0 + i, C, G, stats, gamma, beta, film, film_ld, inv_n, eps);
-    const bool act = flags & TDB_PW_SILU;
-    const int64_t nvox = (int64_t)gr.X * gr.Y * gr.Z;
-    const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
-    const int64_t v_end = min(nvox, v_begin + vox_per_block);
-    float a1[N], a2[N];
+        for (int i = 0; i < N; ++i) k[i] = pw_coef(b, c0 + i, C, G, stats, gamma, beta, film, film_ld, inv_n, eps);
+        const bool act = flags & TDB_PW_SILU;
+        const int64_t nvox = (int64_t)gr.X * gr.Y * gr.Z;
+        const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
+        const int64_t v_end = min(nvox, v_begin + vox_per_block);
+        float a1[N], a2[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) a1[i] = a2[i] = 0.0f;
-    for (int64_t v = v_begin + lane_vox; v < v_end; v += vox_step) {
-        const int z = (int)(v % gr.Z);
-        const int y = (int)((v / gr.Z) % gr.Y);
-        const int x = (int)(v / ((int64_t)gr.Z * gr.Y));
-        const int64_t row = gr.row(b, x, y, z);
-        float xv[N], gv[N];
-        Vec<T>::load(raw + row * ld_raw + c0, xv);
-        Vec<T>::load(g_out + row * ld_g + c0, gv);
+        for (int i = 0; i < N; ++i) a1[i] = a2[i] = 0.0f;
+        for (int64_t v = v_begin + lane_vox; v < v_end; v += vox_step) {
+            const int z = (int)(v % gr.Z);
+            const int y = (int)((v / gr.Z) % gr.Y);
+            const int x = (int)(v / ((int64_t)gr.Z * gr.Y));
+            const int64_t row = gr.row(b, x, y, z);
+            float xv[N], gv[N];
+            Vec<T>::load(raw + row * ld_raw + c0, xv);
+            Vec<T>::load(g_out + row * ld_g + c0, gv);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const float u = fmaf(k[i].a, xv[i], k[i].o);
+                const float gu = act ? gv[i] * dsilu(u) : gv[i];
+                a1[i] += gu;
+                a2[i] = fmaf(gu, (xv[i] - k[i].mean) * k[i].rstd, a2[i]);
+            }
+        }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const float u = fmaf(k[i].a, xv[i], k[i].o);
-            const float gu = act ? gv[i] * dsilu(u) : gv[i];
-            a1[i] += gu;
-            a2[i] = fmaf(gu, (xv[i] - k[i].mean) * k[i].rstd, a2[i]);
+            atomicAdd(&sred[2 * (c0 + i)], a1[i]);
+            atomicAdd(&sred[2 * (c0 + i) + 1], a2[i]);
         }
     }
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        atomicAdd(&red[((int64_t)b * C + c0 + i) * 2], (double)a1[i]);
-        atomicAdd(&red[((int64_t)b * C + c0 + i) * 2 + 1], (double)a2[i]);
-    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&red[(int64_t)b * 2 * C + i], (double)sred[i]);
 }
 
 // d_raw = rstd * (k*g_u - m1 - xhat*m2) on interior rows, 0 on halo rows.  grp[b][g] = (m1, m2) fp32.
@@ -298,14 +305,18 @@ conv_wgrad_kernel(const T* __restrict__ in, int ld_in, const T* __restrict__ d_o
 // with 16-byte loads.  d_out must be ZERO on halo rows and `in` must be readable for Yp*Zp+Zp+1 rows before and
 // after the grid (the halo-grid workspace guarantees both), so no per-row masking is needed.
 // (Stepping stone: a tcgen05 wgrad with MN-major operands is the follow-up.)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(n) : "memory");
+}
+
 __global__ void __launch_bounds__(256)
 conv_wgrad_wmma_kernel(const bf16* __restrict__ in, int ld_in, const bf16* __restrict__ d_out, int ld_do, float* __restrict__ dw,
                        int64_t rows, int yz_p, int z_p, int Cin, int Cout, int ntaps, int ci_tiles, int co_tiles, int rows_per_block) {
     using namespace nvcuda;
-    constexpr int KR = 64, LDS = 64 + 8;
-    __shared__ __align__(32) bf16 sbuf[2 * KR * LDS];
-    bf16 (*As)[LDS] = reinterpret_cast<bf16 (*)[LDS]>(sbuf);             // [row][ci] -> matrix_a col_major (m = ci, k = row)
-    bf16 (*Bs)[LDS] = reinterpret_cast<bf16 (*)[LDS]>(sbuf + KR * LDS);  // [row][co] -> matrix_b row_major (k = row, n = co)
+    constexpr int KR = 64, LDS = 64 + 8, STAGE = 2 * KR * LDS;
+    __shared__ __align__(32) bf16 sbuf[2 * STAGE];  // 2 stages x {A [row][ci], B [row][co]}
     const int tile = blockIdx.y;
     const int tap = tile / (ci_tiles * co_tiles);
     const int ci0 = ((tile / co_tiles) % ci_tiles) * 64;
@@ -321,35 +332,48 @@ conv_wgrad_wmma_kernel(const bf16* __restrict__ in, int ld_in, const bf16* __res
     const bool a_ok = ci0 + lc < Cin, b_ok = co0 + lc < Cout;
     const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r_end = min(rows, r_begin + rows_per_block);
-    const uint4 zero = make_uint4(0, 0, 0, 0);
-    for (int64_t r0 = r_begin; r0 < r_end; r0 += KR) {
+
+    auto prefetch = [&](int stage, int64_t r0) {
+        bf16* As = sbuf + stage * STAGE;
+        bf16* Bs = As + KR * LDS;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int64_t p = r0 + lr + 32 * h;
-            uint4 a = zero, b = zero;
-            if (p < r_end) {
-                if (a_ok) a = *reinterpret_cast<const uint4*>(in + (p + delta) * ld_in + ci0 + lc);
-                if (b_ok) b = *reinterpret_cast<const uint4*>(d_out + p * ld_do + co0 + lc);
-            }
-            *reinterpret_cast<uint4*>(&As[lr + 32 * h][lc]) = a;
-            *reinterpret_cast<uint4*>(&Bs[lr + 32 * h][lc]) = b;
+            const bool ok = p < r_end;
+            const int64_t pa = ok ? p + delta : r_begin, pb = ok ? p : r_begin;  // keep the address valid when masked
+            cp_async16(As + (lr + 32 * h) * LDS + lc, in + pa * ld_in + ci0 + (a_ok ? lc : 0), ok && a_ok);
+            cp_async16(Bs + (lr + 32 * h) * LDS + lc, d_out + pb * ld_do + co0 + (b_ok ? lc : 0), ok && b_ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    int stage = 0;
+    if (r_begin < r_end) prefetch(0, r_begin);
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += KR, stage ^= 1) {
+        if (r0 + KR < r_end) {
+            prefetch(stage ^ 1, r0 + KR);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
+        const bf16* As = sbuf + stage * STAGE;
+        const bf16* Bs = As + KR * LDS;
 #pragma unroll
         for (int k = 0; k < KR; k += 16) {
-            wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::col_major> fa;
-            wmma::load_matrix_sync(fa, &As[k][16 * wm], LDS);
+            wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::col_major> fa;  // (m = ci, k = row)
+            wmma::load_matrix_sync(fa, As + k * LDS + 16 * wm, LDS);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::row_major> fb;
-                wmma::load_matrix_sync(fb, &Bs[k][32 * wn + 16 * j], LDS);
+                wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::row_major> fb;  // (k = row, n = co)
+                wmma::load_matrix_sync(fb, Bs + k * LDS + 32 * wn + 16 * j, LDS);
                 wmma::mma_sync(acc[j], fa, fb, acc[j]);
             }
         }
         __syncthreads();
     }
-    // accumulators -> shared (reuse As as fp32 scratch) -> fp32 atomics
-    float* cs = reinterpret_cast<float*>(sbuf);  // 64 x 64 floats = 16 KB
+    // accumulators -> shared (fp32 scratch over the stage buffers) -> fp32 atomics
+    float* cs = reinterpret_cast<float*>(sbuf);
     static_assert(sizeof(sbuf) >= 64 * 64 * sizeof(float), "scratch");
 #pragma unroll
     for (int j = 0; j < 2; ++j) wmma::store_matrix_sync(cs + (16 * wm) * 64 + 32 * wn + 16 * j, acc[j], 64, wmma::mem_row_major);
@@ -573,10 +597,10 @@ int tdb_pointwise_bwd_reduce(const void* g_out, int ld_g, const void* raw, int l
     dim3 grid((unsigned)ceil_div((int64_t)X * Y * Z, vox_per_block), (unsigned)B);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == TDB_BF16)
-        pw_bwd_reduce_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)g_out, ld_g, (const bf16*)raw, ld_raw, stats, gamma, beta,
+        pw_bwd_reduce_kernel<bf16><<<grid, kThreads, (size_t)2 * C * sizeof(float), s>>>((const bf16*)g_out, ld_g, (const bf16*)raw, ld_raw, stats, gamma, beta,
                                                               film, film_ld, red, gr, C, G, eps, flags, vox_per_block);
     else
-        pw_bwd_reduce_kernel<float><<<grid, kThreads, 0, s>>>((const float*)g_out, ld_g, (const float*)raw, ld_raw, stats, gamma,
+        pw_bwd_reduce_kernel<float><<<grid, kThreads, (size_t)2 * C * sizeof(float), s>>>((const float*)g_out, ld_g, (const float*)raw, ld_raw, stats, gamma,
                                                                beta, film, film_ld, red, gr, C, G, eps, flags, vox_per_block);
     TDB_CHECK_LAUNCH("tdb_pointwise_bwd_reduce");
     return 0;
