@@ -73,6 +73,7 @@ class DenoiserEngine:
         self.tdtype = torch.float32 if precision == "fp32" else torch.bfloat16
         self.fused_stats = precision == "bf16"
         self.fold = True
+        self.fold2 = True
         self._plans = {}
         self._wcache = None
         self._wversion = None
@@ -226,7 +227,10 @@ class DenoiserEngine:
         if self.precision == "fp32":
             call("tdb_conv3d_f32", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ntaps, s)
         elif self.use_fold(ntaps, out.C):
-            call("tdb_conv3d_bf16_fold", x.ptr, x.ld, self.pad_rows((X, Y, Z)), w.data_ptr(), ptr(bias), out.ptr, out.ld,
+            # streamed-weight shapes run as CTA pairs (cta_group::2: half the weight ingest per SM, weights resident
+            # when the half fits); 32->32 keeps its weights resident in a single CTA already
+            pair = self.fold2 and x.C % 64 == 0 and out.C in (32, 64) and 9 * x.C * 3 * out.C * 2 > 112 * 1024
+            call("tdb_conv3d_bf16_fold2" if pair else "tdb_conv3d_bf16_fold", x.ptr, x.ld, self.pad_rows((X, Y, Z)), w.data_ptr(), ptr(bias), out.ptr, out.ld,
                  B, X, Y, Z, x.C, out.C, ptr(stats), G, flags, s)
         else:
             rows = B * (X + 2) * (Y + 2) * (Z + 2)

@@ -109,6 +109,13 @@ TDB_API int tdb_conv3d_bf16_fold(const void* in, int ld_in, int pad_rows, const 
                          int ld_out, int B, int X, int Y, int Z, int Cin, int Cout, double* gn_stats,
                          int G, unsigned flags, void* stream);
 
+/* cta_group::2 variant of tdb_conv3d_bf16_fold (same contract; Cin % 64 == 0, Cout in {32,64}): two CTAs of a
+ * cluster issue one 256-row MMA, each staging half of the weight rows, which stay resident in shared memory
+ * when the half fits (64->64, 128->32). */
+TDB_API int tdb_conv3d_bf16_fold2(const void* in, int ld_in, int pad_rows, const void* w_fold, const float* bias,
+                          void* out, int ld_out, int B, int X, int Y, int Z, int Cin, int Cout, double* gn_stats,
+                          int G, unsigned flags, void* stream);
+
 /* ---- normalisation / pointwise --------------------------------------------------------- */
 
 /* GroupNorm statistics over the interior voxels of a halo grid (ddpm.py:165,170,472):

@@ -106,9 +106,12 @@ FOLD_CASES = [c for c in CONV_CASES if c[6] == 27 and c[5] in (16, 32, 64)] + [
 ]
 
 
-@pytest.mark.parametrize("case", FOLD_CASES)
+FOLD2_CASES = [c for c in FOLD_CASES if c[4] % 64 == 0 and c[5] in (32, 64)] + [(1, 20, 12, 12, 256, 64, 27), (2, 194, 6, 5, 64, 64, 27)]
+
+
+@pytest.mark.parametrize("case,entry", [(c, "tdb_conv3d_bf16_fold") for c in FOLD_CASES] + [(c, "tdb_conv3d_bf16_fold2") for c in FOLD2_CASES])
 @pytest.mark.parametrize("fused_stats", [False, True])
-def test_conv3d_bf16_kz_folded(lib, case, fused_stats):
+def test_conv3d_bf16_kz_folded(lib, case, entry, fused_stats):
     B, X, Y, Z, Cin, Cout, _ = case
     x = gen(B, Cin, X, Y, Z, seed=1).bfloat16().float()
     w = gen(Cout, Cin, 3, 3, 3, seed=2, scale=1 / math.sqrt(Cin * 27)).bfloat16().float()
@@ -119,7 +122,7 @@ def test_conv3d_bf16_kz_folded(lib, case, fused_stats):
     out = torch.zeros((B, X + 2, Y + 2, Z + 2, Cout), device="cuda", dtype=torch.bfloat16)
     G = 8
     stats = torch.zeros((B, G, 2), dtype=torch.float64, device="cuda")
-    lib.call("tdb_conv3d_bf16_fold", xin.data_ptr(), Cin, pad, wf.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
+    lib.call(entry, xin.data_ptr(), Cin, pad, wf.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
              stats.data_ptr() if fused_stats else None, G, 0, lib.stream_ptr())
     torch.cuda.synchronize()
     want = _conv_ref(x.double().cpu(), w.double().cpu(), b.double().cpu(), 27)

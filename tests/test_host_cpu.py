@@ -113,8 +113,10 @@ def test_launch_program_is_well_formed(built_lib, monkeypatch):
     assert y.shape == x.shape
     n = Counter(c[0] for c in calls)
     # 22 3x3x3 convs + 7 residual 1x1 + 2 attention 1x1; 22 block pointwise + 2 attention pointwise; 8 resamplings
-    assert n["tdb_conv3d_bf16"] + n["tdb_conv3d_bf16_fold"] == 31 and n["tdb_pointwise"] == 24 and n["tdb_trilinear"] == 8
-    assert n["tdb_conv3d_bf16_fold"] == 8  # Cout <= 64: down0, up2, up3, decode (two 3x3x3 convs each)
+    assert n["tdb_conv3d_bf16"] + n["tdb_conv3d_bf16_fold"] + n["tdb_conv3d_bf16_fold2"] == 31
+    assert n["tdb_pointwise"] == 24 and n["tdb_trilinear"] == 8
+    # Cout <= 64: down0, up2, up3, decode (two 3x3x3 convs each); the three 32->32 layers stay single-CTA
+    assert n["tdb_conv3d_bf16_fold"] == 3 and n["tdb_conv3d_bf16_fold2"] == 5
     assert n["tdb_attention"] == 1 and n["tdb_time_film"] == 1 and n["tdb_encode_input"] == 1 and n["tdb_decode_output"] == 1
     # level sizes follow max(int(s/2), 3)
     assert engine.level_sizes((194, 50, 50), 4) == [(194, 50, 50), (97, 25, 25), (48, 12, 12), (24, 6, 6), (12, 3, 3)]
