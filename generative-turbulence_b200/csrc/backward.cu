@@ -101,9 +101,8 @@ __device__ __forceinline__ PwCoef pw_coef(int b, int c, int C, int G, const doub
     if (stats) {
         const int gi = c / (C / G);
         const double mean = stats[((int64_t)b * G + gi) * 2] * inv_n;
-        double var = stats[((int64_t)b * G + gi) * 2 + 1] * inv_n - mean * mean;
-        var = var > 0.0 ? var : 0.0;
-        r.rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const double var = fma(-mean, mean, stats[((int64_t)b * G + gi) * 2 + 1] * inv_n);
+        r.rstd = 1.0f / sqrtf(fmaxf((float)var, 0.0f) + eps);  // same fp32 rounding as the forward kernel
         r.mean = (float)mean;
         r.a = r.rstd * gamma[c];
         r.o = beta[c] - r.mean * r.a;

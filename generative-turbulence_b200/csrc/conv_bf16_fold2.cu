@@ -36,6 +36,9 @@ struct FoldParams {
     int ld_out;
     int G;
     int num_super;   // pairs of 120-row tiles
+    int n_tiles;     // N tiles of COUT output channels (Cout_total / COUT)
+    int num_items;   // num_super * n_tiles work items, N tile outermost
+    int cout_total;
     int all_rows;
 };
 
@@ -55,7 +58,11 @@ __global__ void __launch_bounds__(THREADS, 1)
 conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const float* __restrict__ bias, bf16* __restrict__ out, double* __restrict__ gn_stats,
                          const FoldParams P) {
-    constexpr int NF = 3 * COUT, NH = NF / 2;  // folded N, and the half staged by each CTA
+    constexpr int NF = 3 * COUT, NH = NF / 2;  // folded N of one N tile, and the half staged by each CTA
+    constexpr int NSUB = NF > 256 ? 2 : 1;     // MMAs per K step (N <= 256 each)
+    constexpr int NSUBN = NF / NSUB;           // N of one MMA
+    constexpr int PIECE = NSUBN / 2;           // weight rows each CTA contributes to one MMA
+    constexpr int ACC_STAGES = NF > 256 ? 1 : 2;  // TMEM holds 512 columns: 384-wide accumulators cannot be double-buffered
     constexpr int NCH = COUT / 16;
     constexpr int CH_PER_WARP = (NCH + 1) / 2;
     constexpr bool resident = RES_T != 0;
@@ -63,7 +70,7 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 5];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ __align__(16) float s_bias[COUT];
+    __shared__ __align__(16) float s_bias[512];
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const uint32_t rank = ptx::cluster_ctarank();
@@ -80,7 +87,7 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     constexpr uint32_t stage_bytes = a_bytes + (resident ? 0u : bh_bytes);
     const uint32_t stage_base = smem_base + b_region;
 
-    for (int i = threadIdx.x; i < COUT; i += THREADS) s_bias[i] = bias ? bias[i] : 0.0f;
+    for (int i = threadIdx.x; i < P.cout_total; i += THREADS) s_bias[i] = bias ? bias[i] : 0.0f;
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_b);
@@ -96,7 +103,7 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc_2sm(ptx::smem_u32(&tmem_base_slot), (uint32_t)(2 * P.tmem_half));
+        ptx::tmem_alloc_2sm(ptx::smem_u32(&tmem_base_slot), (uint32_t)(ACC_STAGES * P.tmem_half));
         ptx::tmem_relinquish_2sm();
     }
     ptx::tc_fence_before();
@@ -118,7 +125,8 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         __syncwarp();
         const int yz = P.Yp * P.Zp;
         uint32_t s = 0, ph = 1;
-        for (int st = cluster_id; st < P.num_super; st += n_clusters) {
+        for (int w = cluster_id; w < P.num_items; w += n_clusters) {
+            const int nt = w / P.num_super, st = w - nt * P.num_super;
             const int tile = 2 * st + (int)rank;
             const int q0 = tile * ROWS_OUT - 1 + P.pad_rows;
             for (int t9 = 0; t9 < 9; ++t9) {
@@ -129,7 +137,13 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                         const uint32_t a_dst = stage_base + s * stage_bytes;
                         const uint32_t full_l = ptx::leader_addr(full_bar + 8 * s);
                         ptx::tma_load_4d_2sm(a_dst, &map_a, full_l, ch * KC, row, 0, 0);
-                        if (!resident) ptx::tma_load_3d_2sm(a_dst + a_bytes, &map_b, full_l, ch * KC, (int)rank * NH, t9);
+                        if (!resident) {
+                            // for MMA j this CTA supplies folded-weight rows [j*NSUBN + rank*PIECE, +PIECE) of N tile nt
+#pragma unroll
+                            for (int j = 0; j < NSUB; ++j)
+                                ptx::tma_load_3d_2sm(a_dst + a_bytes + j * (PIECE * KC * 2), &map_b, full_l, ch * KC,
+                                                     nt * NF + j * NSUBN + (int)rank * PIECE, t9);
+                        }
                         if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar + 8 * s, 2u * stage_bytes);
                         else ptx::mbar_arrive_remote(full_bar + 8 * s, 0);
                     }
@@ -141,7 +155,7 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     } else if (warp == 1) {
         // ===== MMA issuer: leader CTA only; one 256 x NF x 16 MMA spans both SMs =====
         if (rank == 0) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(2 * BM, (uint32_t)NF);
+            const uint32_t idesc = ptx::umma_idesc_bf16(2 * BM, (uint32_t)NSUBN);
             const uint64_t desc0 = ptx::umma_smem_desc(0, (uint32_t)KC * 2u);
             constexpr uint32_t b_step = bh_bytes >> 4, st_step = stage_bytes >> 4;
             const uint64_t a_base = desc0 | (uint64_t)((stage_base & 0x3FFFFu) >> 4);
@@ -152,9 +166,9 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             }
             uint32_t s = 0, ph = 0;
             int local = 0;
-            for (int st = cluster_id; st < P.num_super; st += n_clusters, ++local) {
-                const int as = local & 1;
-                const uint32_t aph = (uint32_t)(local >> 1) & 1u;
+            for (int w = cluster_id; w < P.num_items; w += n_clusters, ++local) {
+                const int as = ACC_STAGES == 2 ? (local & 1) : 0;
+                const uint32_t aph = (uint32_t)(ACC_STAGES == 2 ? (local >> 1) : local) & 1u;
                 ptx::mbar_wait(acc_empty + 8 * as, aph ^ 1u);  // both CTAs' epilogues have drained this stage
                 ptx::tc_fence_after();
                 const uint32_t d_addr = tmem_d + (uint32_t)(as * P.tmem_half);
@@ -165,8 +179,11 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                         const uint64_t a_st = a_base + (uint64_t)(s * st_step);
                         const uint64_t b_st = resident ? b_base + (uint64_t)((uint32_t)i * b_step) : b_base + (uint64_t)(s * st_step);
 #pragma unroll
-                        for (int k = 0; k < KC / 16; ++k)
-                            ptx::umma_f16_2sm(d_addr, a_st + (uint64_t)(2 * k), b_st + (uint64_t)(2 * k), idesc, (uint32_t)((i | k) != 0));
+                        for (int j = 0; j < NSUB; ++j)
+#pragma unroll
+                            for (int k = 0; k < KC / 16; ++k)
+                                ptx::umma_f16_2sm(d_addr + (uint32_t)(j * NSUBN), a_st + (uint64_t)(2 * k),
+                                                  b_st + (uint64_t)(j * ((PIECE * KC * 2) >> 4) + 2 * k), idesc, (uint32_t)((i | k) != 0));
                         ptx::umma_commit_2sm_mc(empty_bar + 8 * s, (uint16_t)0x3);  // frees the slot in both CTAs
                     }
                     __syncwarp();
@@ -187,11 +204,11 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         for (int a = 0; a < CH_PER_WARP; ++a)
 #pragma unroll
             for (int j = 0; j < 8; ++j) st_s[a][j] = st_q[a][j] = 0.0f;
-        int st_b = -1;
+        int st_b = -1, st_nt = 0;
 
         auto flush_stats = [&]() {
             // pairs -> groups (cpg even), warp reduce in double, one atomic per (warp, group, moment)
-            const int cpg = COUT / P.G;
+            const int cpg = P.cout_total / P.G;
 #pragma unroll
             for (int a = 0; a < CH_PER_WARP; ++a) {
                 const int cidx = 2 * a + half;  // chunk index of this warp
@@ -202,7 +219,7 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                         gs += (double)st_s[a][j];
                         gq += (double)st_q[a][j];
                         st_s[a][j] = st_q[a][j] = 0.0f;
-                        const int col_end = cidx * 16 + 2 * j + 2;
+                        const int col_end = st_nt * COUT + cidx * 16 + 2 * j + 2;
                         if (col_end % cpg == 0 || j == 7) {
                             const double ws = warp_sum(gs), wq = warp_sum(gq);
                             if (lane == 0) {
@@ -218,10 +235,12 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         };
 
         int local = 0;
-        for (int st = cluster_id; st < P.num_super; st += n_clusters, ++local) {
+        for (int w = cluster_id; w < P.num_items; w += n_clusters, ++local) {
+            const int nt = w / P.num_super, st = w - nt * P.num_super;
             const int tile = 2 * st + (int)rank;
-            const int as = local & 1;
-            const uint32_t aph = (uint32_t)(local >> 1) & 1u;
+            const int n0 = nt * COUT;
+            const int as = ACC_STAGES == 2 ? (local & 1) : 0;
+            const uint32_t aph = (uint32_t)(ACC_STAGES == 2 ? (local >> 1) : local) & 1u;
             const int64_t p = (int64_t)tile * ROWS_OUT + ROWS_WARP * lg - 1 + lane;
             int b = 0;
             const bool inter = lane >= 1 && lane <= ROWS_WARP && interior_row(p, P, b);
@@ -231,16 +250,17 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                 const unsigned vmask = __ballot_sync(0xffffffffu, valid);
                 if (vmask) {
                     const int b_warp = __shfl_sync(0xffffffffu, b, __ffs(vmask) - 1);
-                    if (b_warp != st_b) {
+                    if (b_warp != st_b || nt != st_nt) {
                         if (st_b >= 0) flush_stats();
                         st_b = b_warp;
+                        st_nt = nt;
                     }
                 }
             }
             ptx::mbar_wait(acc_full + 8 * as, aph);
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_d + (uint32_t)(as * P.tmem_half) + ((uint32_t)(lg * 32) << 16);
-            bf16* orow = out + p * P.ld_out;
+            bf16* orow = out + p * P.ld_out + n0;
 #pragma unroll
             for (int a = 0; a < CH_PER_WARP; ++a) {
                 const int c = (2 * a + half) * 16;
@@ -255,7 +275,7 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                     for (int j = 0; j < 16; ++j) {
                         const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[j]), 1);    // Y_0 of row i-1
                         const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);  // Y_2 of row i+1
-                        v[j] = (up + __uint_as_float(r1[j])) + (dn + s_bias[c + j]);
+                        v[j] = (up + __uint_as_float(r1[j])) + (dn + s_bias[n0 + c + j]);
                     }
                     if (valid) {
                         uint4 lo, hi;
@@ -294,7 +314,7 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     ptx::cluster_sync();  // the peer may still signal / be signalled until both are here
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc_2sm(tmem_d, (uint32_t)(2 * P.tmem_half));
+        ptx::tmem_dealloc_2sm(tmem_d, (uint32_t)(ACC_STAGES * P.tmem_half));
     }
 }
 
@@ -306,7 +326,7 @@ int launch_fold2(const CUtensorMap& map_a, const CUtensorMap& map_b, const float
     auto kern = conv3d_bf16_fold2_kernel<COUT, RES_T>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_conv3d_bf16_fold2: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-    int grid = 2 * P.num_super;
+    int grid = 2 * P.num_items;
     const int cap = g_num_sms2 & ~1;
     if (grid > cap) grid = cap;
     cudaLaunchConfig_t cfg{};
@@ -329,13 +349,14 @@ int launch_fold2(const CUtensorMap& map_a, const CUtensorMap& map_b, const float
 
 }  // namespace
 
-// Same contract as tdb_conv3d_bf16_fold (include/turbdiff_b200.h); additionally Cin % 64 == 0 and Cout in {32, 64}.
+// Same contract as tdb_conv3d_bf16_fold (include/turbdiff_b200.h); Cin % 64 == 0 and Cout in {32, 64} or a multiple of
+// 128 (<= 512), which is processed as N tiles of 128 channels: w_fold rows are then ordered [n tile][kz][co in tile].
 extern "C" int tdb_conv3d_bf16_fold2(const void* in, int ld_in, int pad_rows, const void* w_fold, const float* bias, void* out,
                                      int ld_out, int B, int X, int Y, int Z, int Cin, int Cout, double* gn_stats, int G,
                                      unsigned flags, void* stream) {
     TDB_REQUIRE(in && w_fold && out, TDB_E_BADARG, "tdb_conv3d_bf16_fold2: null pointer");
-    TDB_REQUIRE(Cin % 64 == 0 && (Cout == 32 || Cout == 64) && ld_in % 8 == 0 && ld_out % 8 == 0, TDB_E_UNSUPPORTED,
-                "tdb_conv3d_bf16_fold2: need Cin %% 64 == 0 and Cout in {32,64} (Cin=%d Cout=%d)", Cin, Cout);
+    TDB_REQUIRE(Cin % 64 == 0 && (Cout == 32 || Cout == 64 || (Cout % 128 == 0 && Cout <= 512)) && ld_in % 8 == 0 && ld_out % 8 == 0,
+                TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_fold2: need Cin %% 64 == 0 and Cout in {32,64,128k<=512} (Cin=%d Cout=%d)", Cin, Cout);
     TDB_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)w_fold & 15) == 0, TDB_E_UNSUPPORTED,
                 "tdb_conv3d_bf16_fold2: pointers must be 16-byte aligned");
     TDB_REQUIRE(!gn_stats || (G >= 1 && Cout % G == 0 && (Cout / G) % 2 == 0), TDB_E_UNSUPPORTED,
@@ -358,11 +379,14 @@ extern "C" int tdb_conv3d_bf16_fold2(const void* in, int ld_in, int pad_rows, co
     P.by_y = FastDiv((uint32_t)g.Yp);
     P.Cin = Cin;
     P.pad_rows = pad_rows;
-    const int NF = 3 * Cout, NH = NF / 2;
+    const int tile_n = Cout >= 128 ? 128 : Cout;  // output channels per N tile
+    const int NF = 3 * tile_n, NH = NF / 2;
+    P.n_tiles = Cout / tile_n;
+    P.cout_total = Cout;
     const int a_bytes = BM * KC * 2, bh_bytes = NH * KC * 2;
     const int k_iters = 9 * (Cin / KC);
     const int budget = 221 * 1024;
-    P.b_resident = (int64_t)k_iters * bh_bytes <= 112 * 1024 ? 1 : 0;
+    P.b_resident = (P.n_tiles == 1 && (int64_t)k_iters * bh_bytes <= 112 * 1024) ? 1 : 0;
     const int resident_bytes = P.b_resident ? k_iters * bh_bytes : 0;
     const int unit = a_bytes + (P.b_resident ? 0 : bh_bytes);
     int stages = (budget - resident_bytes) / unit;
@@ -375,6 +399,7 @@ extern "C" int tdb_conv3d_bf16_fold2(const void* in, int ld_in, int pad_rows, co
     P.ld_out = ld_out;
     P.G = gn_stats ? G : 0;
     P.num_super = (int)ceil_div(g.rows, 2 * ROWS_OUT);
+    P.num_items = P.num_super * P.n_tiles;
     P.all_rows = (flags & TDB_CONV_ALL_ROWS) ? 1 : 0;
     TDB_REQUIRE(!(P.all_rows && gn_stats), TDB_E_BADARG, "tdb_conv3d_bf16_fold2: fused moments are not available with ALL_ROWS");
 
@@ -389,9 +414,10 @@ extern "C" int tdb_conv3d_bf16_fold2(const void* in, int ld_in, int pad_rows, co
         TDB_REQUIRE(make_map_bf16(&map_a, base, 4, dims, strides, box), TDB_E_BADARG, "tdb_conv3d_bf16_fold2: tensor map (activations) rejected");
     }
     {
-        const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)NF, 9};
+        // folded weights [n_tiles * 3 * tile_n][9 * Cin]; one box = the rows one CTA contributes to one MMA
+        const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)NF * P.n_tiles, 9};
         const uint64_t strides[2] = {9ull * Cin, (uint64_t)Cin};
-        const uint32_t box[3] = {(uint32_t)KC, (uint32_t)NH, 1};
+        const uint32_t box[3] = {(uint32_t)KC, (uint32_t)(NF > 256 ? NF / 4 : NH), 1};
         TDB_REQUIRE(make_map_bf16(&map_b, w_fold, 3, dims, strides, box), TDB_E_BADARG, "tdb_conv3d_bf16_fold2: tensor map (weights) rejected");
     }
     const size_t smem = (size_t)resident_bytes + (size_t)stages * unit + 1024;
@@ -400,6 +426,7 @@ extern "C" int tdb_conv3d_bf16_fold2(const void* in, int ld_in, int pad_rows, co
         if (P.b_resident) return launch_fold2<32, 1>(map_a, map_b, bias, (bf16*)out, gn_stats, P, smem, s);
         return launch_fold2<32, 0>(map_a, map_b, bias, (bf16*)out, gn_stats, P, smem, s);
     }
+    if (Cout >= 128) return launch_fold2<128, 0>(map_a, map_b, bias, (bf16*)out, gn_stats, P, smem, s);
     if (P.b_resident) return launch_fold2<64, 1>(map_a, map_b, bias, (bf16*)out, gn_stats, P, smem, s);
     return launch_fold2<64, 0>(map_a, map_b, bias, (bf16*)out, gn_stats, P, smem, s);
 }

@@ -199,18 +199,25 @@ pointwise_kernel(const T* __restrict__ raw, int ld_raw, const double* __restrict
     {
         const int cpg = C / G;
         const double inv_n = 1.0 / ((double)cpg * g.X * g.Y * g.Z);
+        // group moments: the (few) double-precision operations are done once per group, not per channel -
+        // fp64 issues at 1/64 rate on this part and used to dominate the small launches
+        int g_cached = -1;
+        float mean_f = 0.0f, rstd = 1.0f;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const int c = c0 + i;
             float a = 1.0f, o = 0.0f;
             if (stats) {
                 const int gi = c / cpg;
-                const double mean = stats[((int64_t)b * G + gi) * 2] * inv_n;
-                double var = stats[((int64_t)b * G + gi) * 2 + 1] * inv_n - mean * mean;
-                var = var > 0.0 ? var : 0.0;
-                const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+                if (gi != g_cached) {
+                    const double mean = stats[((int64_t)b * G + gi) * 2] * inv_n;
+                    const double var = fma(-mean, mean, stats[((int64_t)b * G + gi) * 2 + 1] * inv_n);
+                    mean_f = (float)mean;
+                    rstd = 1.0f / sqrtf(fmaxf((float)var, 0.0f) + eps);
+                    g_cached = gi;
+                }
                 a = rstd * gamma[c];
-                o = beta[c] - (float)mean * a;
+                o = beta[c] - mean_f * a;
             }
             if (film) {
                 const float sc = film[(int64_t)b * film_ld + c] + 1.0f;

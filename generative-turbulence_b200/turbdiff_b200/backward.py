@@ -45,22 +45,13 @@ class BackwardProgram:
             gb[k] = p["grid"](level, max(C, p["max_c"].get(level, C)))
         return gb[k].slice(0, C)
 
-    def _dgrad_weights(self, conv, key):
+    def _dgrad_weights(self, conv, key, level):
         """Kernel-layout weights of the input-gradient convolution: W'[ci][co][k] = W[co][ci][2-k]."""
         eng = self.eng
         cache = eng._wcache.setdefault("dgrad", {})
         if key not in cache:
-            wt = conv.weight.detach()
-            taps = wt.shape[2] * wt.shape[3] * wt.shape[4]
-            wt = wt.flip(2, 3, 4).transpose(0, 1)  # (Cin, Cout, k, k, k): "Cout'" = Cin, "Cin'" = Cout
-            cout, cin = wt.shape[:2]
-            if eng.precision == "fp32":
-                w = wt.permute(2, 3, 4, 1, 0).reshape(taps, cin, cout).contiguous().float()
-            elif eng.use_fold(taps, cout):
-                w = wt.permute(4, 0, 2, 3, 1).reshape(3 * cout, 9 * cin).contiguous().to(torch.bfloat16)
-            else:
-                w = wt.permute(0, 2, 3, 4, 1).reshape(cout, taps * cin).contiguous().to(torch.bfloat16)
-            cache[key] = w
+            wt = conv.weight.detach().flip(2, 3, 4).transpose(0, 1)  # (Cin, Cout, k, k, k): "Cout'" = Cin, "Cin'" = Cout
+            cache[key] = eng.pack_conv(wt, level)
         return cache[key]
 
     def _fold(self, p, g: View):
@@ -135,7 +126,7 @@ class BackwardProgram:
         grads[f"{pre}.block2.norm.bias"] = a1.sum(0).float()
         grads[f"{pre}.block2.conv.weight"] = self._wgrad(p, sv["act1"], d_raw, blk.block2.conv, 27, zero_halo=True)
         grads[f"{pre}.block2.conv.bias"] = self._colsum(p, d_raw)
-        eng._conv(p, d_raw, self._dgrad_weights(blk.block2.conv, f"{name}.conv2"), None, g_act, 27, all_rows=True)
+        eng._conv(p, d_raw, self._dgrad_weights(blk.block2.conv, f"{name}.conv2", lvl), None, g_act, 27, all_rows=True)
         self._fold(p, g_act)
 
         # block1: pointwise (norm, FiLM, SiLU) then conv1
@@ -149,7 +140,7 @@ class BackwardProgram:
         grads[f"{pre}.block1.conv.weight"] = self._wgrad(p, x, d_raw, blk.block1.conv, 27, zero_halo=True)
         grads[f"{pre}.block1.conv.bias"] = self._colsum(p, d_raw)
         g_x = self._gbuf(p, x, ("g", name))
-        eng._conv(p, d_raw, self._dgrad_weights(blk.block1.conv, f"{name}.conv1"), None, g_x, 27, all_rows=True)
+        eng._conv(p, d_raw, self._dgrad_weights(blk.block1.conv, f"{name}.conv1", lvl), None, g_x, 27, all_rows=True)
         self._fold(p, g_x)
 
         # residual branch
@@ -157,7 +148,7 @@ class BackwardProgram:
             grads[f"{pre}.conv.weight"] = self._wgrad(p, x, g_out, blk.conv, 1)
             grads[f"{pre}.conv.bias"] = self._colsum(p, g_out)
             g_res = self._tmp(p, lvl, x.C, "g_res")
-            eng._conv(p, g_out, self._dgrad_weights(blk.conv, f"{name}.proj"), None, g_res, 1, all_rows=True)
+            eng._conv(p, g_out, self._dgrad_weights(blk.conv, f"{name}.proj", lvl), None, g_res, 1, all_rows=True)
             self._add_interior(p, g_x, g_res)
         else:
             self._add_interior(p, g_x, g_out)
@@ -177,7 +168,7 @@ class BackwardProgram:
         grads[f"{pre}.fn.to_out.weight"] = self._wgrad(p, p["attn_o"], g_out, att.to_out, 1)
         grads[f"{pre}.fn.to_out.bias"] = self._colsum(p, g_out)
         g_o = self._gbuf(p, p["attn_o"], ("g", "attn_o"))
-        eng._conv(p, g_out, self._dgrad_weights(att.to_out, "attn.out"), None, g_o, 1, all_rows=True)
+        eng._conv(p, g_out, self._dgrad_weights(att.to_out, "attn.out", x.level), None, g_o, 1, all_rows=True)
         # softmax attention
         g_qkv = self._gbuf(p, p["attn_qkv"], ("g", "attn_qkv"))
         call("tdb_attention_bwd", p["attn_qkv"].ptr, p["attn_qkv"].ld, g_o.ptr, g_o.ld, g_qkv.ptr, g_qkv.ld, B, X, Y, Z, att.heads,
@@ -185,7 +176,7 @@ class BackwardProgram:
         # to_qkv (1x1 conv, no bias) on the normalised input
         grads[f"{pre}.fn.to_qkv.weight"] = self._wgrad(p, p["attn_norm"], g_qkv, att.to_qkv, 1)
         g_hn = self._gbuf(p, p["attn_norm"], ("g", "attn_norm"))
-        eng._conv(p, g_qkv, self._dgrad_weights(att.to_qkv, "attn.qkv"), None, g_hn, 1, all_rows=True)
+        eng._conv(p, g_qkv, self._dgrad_weights(att.to_qkv, "attn.qkv", x.level), None, g_hn, 1, all_rows=True)
         # pre-norm
         g_x = self._gbuf(p, x, ("g", "attn_x"))
         a1, a2 = self._pw_bwd(p, g_hn, x, p["stats"][p["attn_slot"]], pre_mod.norm, None, g_x, 0, G)

@@ -74,6 +74,7 @@ class DenoiserEngine:
         self.fused_stats = precision == "bf16"
         self.fold = True
         self.fold2 = True
+        self.fold_wide = True
         self._plans = {}
         self._wcache = None
         self._wversion = None
@@ -106,25 +107,18 @@ class DenoiserEngine:
         m = self.model
         w = {}
 
-        def pack(conv):
-            wt = conv.weight.detach()
-            cout, cin = wt.shape[:2]
-            taps = wt.shape[2] * wt.shape[3] * wt.shape[4]
-            if self.precision == "fp32":
-                return wt.permute(2, 3, 4, 1, 0).reshape(taps, cin, cout).contiguous().float()
-            if self.use_fold(taps, cout):
-                # kz folded into N: row = kz*Cout + co, col = (kx*3+ky)*Cin + ci
-                return wt.permute(4, 0, 2, 3, 1).reshape(3 * cout, 9 * cin).contiguous().to(torch.bfloat16)
-            return wt.permute(0, 2, 3, 4, 1).reshape(cout, taps * cin).contiguous().to(torch.bfloat16)
+        def pack(conv, level):
+            return self.pack_conv(conv.weight.detach(), level)
 
         for name, bp in self.blocks.items():
-            w[f"{name}.conv1"] = pack(bp.blk.block1.conv)
-            w[f"{name}.conv2"] = pack(bp.blk.block2.conv)
+            lvl = self._block_level(name)
+            w[f"{name}.conv1"] = pack(bp.blk.block1.conv, lvl)
+            w[f"{name}.conv2"] = pack(bp.blk.block2.conv, lvl)
             if bp.has_proj:
-                w[f"{name}.proj"] = pack(bp.blk.conv)
+                w[f"{name}.proj"] = pack(bp.blk.conv, lvl)
         att = m.u_net.center_block[1].fn.fn
-        w["attn.qkv"] = pack(att.to_qkv)
-        w["attn.out"] = pack(att.to_out)
+        w["attn.qkv"] = pack(att.to_qkv, m.u_net_levels)
+        w["attn.out"] = pack(att.to_out, m.u_net_levels)
         # stacked over blocks and transposed to (dim, film_rows) for coalesced reads in tdb_time_film
         w["film_w"] = torch.cat([self.blocks[n].blk.project_onto_scale_shift.weight.detach() for n in self.block_order]).t().contiguous().float()
         w["film_b"] = torch.cat([self.blocks[n].blk.project_onto_scale_shift.bias.detach() for n in self.block_order]).contiguous().float()
@@ -136,9 +130,32 @@ class DenoiserEngine:
         X, Y, Z = size
         return (Y + 2) * (Z + 2) + 2 * (Z + 2) + 256
 
-    def use_fold(self, ntaps, cout) -> bool:
-        """Narrow 3x3x3 layers run the kz-folded persistent kernel (tdb_conv3d_bf16_fold)."""
-        return self.precision == "bf16" and self.fold and ntaps == 27 and cout in (16, 32, 64)
+    def fold_kind(self, ntaps, cin, cout, level):
+        """Which bf16 kernel a convolution runs on: None = per-tap kernel (tdb_conv3d_bf16), "fold" = kz-folded
+        persistent kernel, "fold2" = its cta_group::2 (CTA pair) variant.  Pairs take the shapes whose folded
+        weights do not fit one SM (half the weight ingest per SM, resident when the half fits) and, as 128-channel
+        N tiles, the wide layers of all but the two deepest levels (those are split-K territory)."""
+        if self.precision != "bf16" or not self.fold or ntaps != 27:
+            return None
+        if cout in (16, 32, 64):
+            pair = self.fold2 and cin % 64 == 0 and cout in (32, 64) and 9 * cin * 3 * cout * 2 > 112 * 1024
+            return "fold2" if pair else "fold"
+        if self.fold2 and self.fold_wide and cout % 128 == 0 and cout <= 512 and cin % 64 == 0 and level <= self.model.u_net_levels - 2:
+            return "fold2"
+        return None
+
+    def pack_conv(self, wt, level):
+        """Kernel layout of a (Cout, Cin, k, k, k) weight for the kernel fold_kind() selects at `level`."""
+        cout, cin = wt.shape[:2]
+        taps = wt.shape[2] * wt.shape[3] * wt.shape[4]
+        if self.precision == "fp32":
+            return wt.permute(2, 3, 4, 1, 0).reshape(taps, cin, cout).contiguous().float()
+        if self.fold_kind(taps, cin, cout, level) is not None:
+            # kz folded into N, N tiles of <= 128 channels: row = (tile*3 + kz)*T + co, col = (kx*3+ky)*Cin + ci
+            tile = cout if cout < 128 else 128
+            return (wt.reshape(cout // tile, tile, cin, 3, 3, 3).permute(0, 5, 1, 3, 4, 2)
+                    .reshape(3 * cout, 9 * cin).contiguous().to(torch.bfloat16))
+        return wt.permute(0, 2, 3, 4, 1).reshape(cout, taps * cin).contiguous().to(torch.bfloat16)
 
     # ------------------------------------------------------------------ workspace
     def plan(self, B, spatial, device):
@@ -226,10 +243,8 @@ class DenoiserEngine:
         flags = _lib.CONV_ALL_ROWS if all_rows else 0
         if self.precision == "fp32":
             call("tdb_conv3d_f32", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ntaps, s)
-        elif self.use_fold(ntaps, out.C):
-            # streamed-weight shapes run as CTA pairs (cta_group::2: half the weight ingest per SM, weights resident
-            # when the half fits); 32->32 keeps its weights resident in a single CTA already
-            pair = self.fold2 and x.C % 64 == 0 and out.C in (32, 64) and 9 * x.C * 3 * out.C * 2 > 112 * 1024
+        elif self.fold_kind(ntaps, x.C, out.C, x.level) is not None:
+            pair = self.fold_kind(ntaps, x.C, out.C, x.level) == "fold2"
             call("tdb_conv3d_bf16_fold2" if pair else "tdb_conv3d_bf16_fold", x.ptr, x.ld, self.pad_rows((X, Y, Z)), w.data_ptr(), ptr(bias), out.ptr, out.ld,
                  B, X, Y, Z, x.C, out.C, ptr(stats), G, flags, s)
         else:
@@ -261,7 +276,7 @@ class DenoiserEngine:
         G = self._groups(raw.C)
         stats = p["stats"][stats_slot]
         cpg = raw.C // G
-        if self.use_fold(27, raw.C):
+        if self.fold_kind(27, x.C, raw.C, x.level) is not None:
             fused = self.fused_stats and cpg % 2 == 0
         else:
             fused = self.fused_stats and (cpg % 16 == 0 or 16 % cpg == 0)

@@ -106,7 +106,11 @@ FOLD_CASES = [c for c in CONV_CASES if c[6] == 27 and c[5] in (16, 32, 64)] + [
 ]
 
 
-FOLD2_CASES = [c for c in FOLD_CASES if c[4] % 64 == 0 and c[5] in (32, 64)] + [(1, 20, 12, 12, 256, 64, 27), (2, 194, 6, 5, 64, 64, 27)]
+FOLD2_CASES = [c for c in FOLD_CASES if c[4] % 64 == 0 and c[5] in (32, 64)] + [
+    (1, 20, 12, 12, 256, 64, 27), (2, 194, 6, 5, 64, 64, 27),
+    # 128-channel N tiles (two N=192 MMAs per K step, single accumulator stage)
+    (2, 25, 13, 12, 64, 128, 27), (1, 20, 12, 12, 128, 256, 27), (2, 12, 6, 6, 256, 512, 27), (1, 48, 12, 12, 128, 128, 27),
+]
 
 
 @pytest.mark.parametrize("case,entry", [(c, "tdb_conv3d_bf16_fold") for c in FOLD_CASES] + [(c, "tdb_conv3d_bf16_fold2") for c in FOLD2_CASES])
@@ -118,7 +122,8 @@ def test_conv3d_bf16_kz_folded(lib, case, entry, fused_stats):
     b = gen(Cout, seed=3, scale=0.1)
     pad = (Y + 2) * (Z + 2) + 2 * (Z + 2) + 256
     xin = to_halo(x, dtype=torch.bfloat16, pad_rows=pad)
-    wf = w.permute(4, 0, 2, 3, 1).reshape(3 * Cout, 9 * Cin).contiguous().bfloat16()
+    tile = Cout if Cout < 128 else 128
+    wf = w.reshape(Cout // tile, tile, Cin, 3, 3, 3).permute(0, 5, 1, 3, 4, 2).reshape(3 * Cout, 9 * Cin).contiguous().bfloat16()
     out = torch.zeros((B, X + 2, Y + 2, Z + 2, Cout), device="cuda", dtype=torch.bfloat16)
     G = 8
     stats = torch.zeros((B, G, 2), dtype=torch.float64, device="cuda")
