@@ -40,6 +40,8 @@ struct FoldParams {
     int num_items;   // num_super * n_tiles work items, N tile outermost
     int cout_total;
     int all_rows;
+    int proj;        // 1: also compute the block's 1x1 residual projection of the SAME input (centre tap) into out_p
+    int ld_outp;
 };
 
 __device__ __forceinline__ bool interior_row(int64_t p, const FoldParams& P, int& b) {
@@ -56,7 +58,8 @@ __device__ __forceinline__ bool interior_row(int64_t p, const FoldParams& P, int
 template <int COUT, int RES_T>
 __global__ void __launch_bounds__(THREADS, 1)
 conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                         const float* __restrict__ bias, bf16* __restrict__ out, double* __restrict__ gn_stats,
+                         const __grid_constant__ CUtensorMap map_p, const float* __restrict__ bias, bf16* __restrict__ out,
+                         double* __restrict__ gn_stats, const float* __restrict__ bias_p, bf16* __restrict__ out_p,
                          const FoldParams P) {
     constexpr int NF = 3 * COUT, NH = NF / 2;  // folded N of one N tile, and the half staged by each CTA
     constexpr int NSUB = NF > 256 ? 2 : 1;     // MMAs per K step (N <= 256 each)
@@ -68,7 +71,8 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     constexpr bool resident = RES_T != 0;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-    __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 5];
+    __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 6];
+    __shared__ __align__(16) float s_biasp[64];
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float s_bias[512];
 
@@ -80,14 +84,21 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     const uint32_t acc_full = ptx::smem_u32(&bars[2 * MAX_STAGES]);       // [2] per CTA (multicast commit)
     const uint32_t acc_empty = ptx::smem_u32(&bars[2 * MAX_STAGES + 2]);  // [2] used in the leader, 16 arrivals
     const uint32_t b_full = ptx::smem_u32(&bars[2 * MAX_STAGES + 4]);     // used in the leader
+    const uint32_t p_full = ptx::smem_u32(&bars[2 * MAX_STAGES + 5]);     // used in the leader (projection weights)
     const int chunks = P.Cin / KC;
     const int k_iters = 9 * chunks;
     constexpr uint32_t a_bytes = BM * KC * 2, bh_bytes = NH * KC * 2;
     const uint32_t b_region = resident ? (uint32_t)k_iters * bh_bytes : 0u;
     constexpr uint32_t stage_bytes = a_bytes + (resident ? 0u : bh_bytes);
-    const uint32_t stage_base = smem_base + b_region;
+    // fused 1x1 projection (COUT <= 64): each CTA keeps COUT/2 rows x Cin of the projection weights resident
+    constexpr uint32_t ph_bytes = (COUT / 2) * KC * 2;
+    const uint32_t p_base_addr = smem_base + b_region;
+    const uint32_t p_region = P.proj ? (uint32_t)chunks * ph_bytes : 0u;
+    const uint32_t stage_base = smem_base + b_region + p_region;
 
     for (int i = threadIdx.x; i < P.cout_total; i += THREADS) s_bias[i] = bias ? bias[i] : 0.0f;
+    if (P.proj)
+        for (int i = threadIdx.x; i < COUT; i += THREADS) s_biasp[i % 64] = bias_p ? bias_p[i] : 0.0f;
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_b);
@@ -100,6 +111,7 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             ptx::mbar_init(acc_empty + 8 * s, 16);  // 8 epilogue warps in each CTA
         }
         ptx::mbar_init(b_full, 2);
+        ptx::mbar_init(p_full, 2);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -121,6 +133,13 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                 ptx::tma_load_3d_2sm(smem_base + kc * bh_bytes, &map_b, b_full_l, (kc % chunks) * KC, (int)rank * NH, kc / chunks);
             if (rank == 0) ptx::mbar_arrive_expect_tx(b_full, 2u * (uint32_t)k_iters * bh_bytes);
             else ptx::mbar_arrive_remote(b_full, 0);
+        }
+        if (P.proj && ptx::elect_one()) {
+            const uint32_t p_full_l = ptx::leader_addr(p_full);
+            for (int ch = 0; ch < chunks; ++ch)
+                ptx::tma_load_3d_2sm(p_base_addr + ch * ph_bytes, &map_p, p_full_l, ch * KC, (int)rank * (COUT / 2), 0);
+            if (rank == 0) ptx::mbar_arrive_expect_tx(p_full, 2u * (uint32_t)chunks * ph_bytes);
+            else ptx::mbar_arrive_remote(p_full, 0);
         }
         __syncwarp();
         const int yz = P.Yp * P.Zp;
@@ -164,6 +183,12 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                 ptx::mbar_wait(b_full, 0);
                 ptx::tc_fence_after();
             }
+            const uint32_t idesc_p = ptx::umma_idesc_bf16(2 * BM, (uint32_t)(COUT < 128 ? COUT : 64));
+            const uint64_t p_base = desc0 | (uint64_t)((p_base_addr & 0x3FFFFu) >> 4);
+            if (P.proj) {
+                ptx::mbar_wait(p_full, 0);
+                ptx::tc_fence_after();
+            }
             uint32_t s = 0, ph = 0;
             int local = 0;
             for (int w = cluster_id; w < P.num_items; w += n_clusters, ++local) {
@@ -184,6 +209,15 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                             for (int k = 0; k < KC / 16; ++k)
                                 ptx::umma_f16_2sm(d_addr + (uint32_t)(j * NSUBN), a_st + (uint64_t)(2 * k),
                                                   b_st + (uint64_t)(j * ((PIECE * KC * 2) >> 4) + 2 * k), idesc, (uint32_t)((i | k) != 0));
+                        if (P.proj && i >= 4 * chunks && i < 5 * chunks) {
+                            // centre tap (kx = ky = 1): the same activation tile also feeds the 1x1 projection,
+                            // accumulated over the channel chunks into the TMEM columns behind the folded ones
+                            const int ch = i - 4 * chunks;
+#pragma unroll
+                            for (int k = 0; k < KC / 16; ++k)
+                                ptx::umma_f16_2sm(d_addr + (uint32_t)NF, a_st + (uint64_t)(2 * k),
+                                                  p_base + (uint64_t)((uint32_t)ch * (ph_bytes >> 4) + 2 * k), idesc_p, (uint32_t)((ch | k) != 0));
+                        }
                         ptx::umma_commit_2sm_mc(empty_bar + 8 * s, (uint16_t)0x3);  // frees the slot in both CTAs
                     }
                     __syncwarp();
@@ -265,11 +299,28 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             for (int a = 0; a < CH_PER_WARP; ++a) {
                 const int c = (2 * a + half) * 16;
                 if (c < COUT) {
-                    uint32_t r0[16], r1[16], r2[16];
+                    uint32_t r0[16], r1[16], r2[16], r3[16];
                     ptx::tmem_ld_x16(t_row + (uint32_t)c, r0);
                     ptx::tmem_ld_x16(t_row + (uint32_t)(COUT + c), r1);
                     ptx::tmem_ld_x16(t_row + (uint32_t)(2 * COUT + c), r2);
+                    if (P.proj) ptx::tmem_ld_x16(t_row + (uint32_t)(NF + c), r3);
                     ptx::tmem_ld_wait();
+                    if (P.proj && valid) {
+                        // projection rows are unshifted: lane i holds output row i
+                        uint4 lo, hi;
+                        __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&lo);
+                        __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&hi);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            h0[j] = __floats2bfloat162_rn(__uint_as_float(r3[2 * j]) + s_biasp[(c + 2 * j) % 64],
+                                                          __uint_as_float(r3[2 * j + 1]) + s_biasp[(c + 2 * j + 1) % 64]);
+                            h1[j] = __floats2bfloat162_rn(__uint_as_float(r3[8 + 2 * j]) + s_biasp[(c + 8 + 2 * j) % 64],
+                                                          __uint_as_float(r3[8 + 2 * j + 1]) + s_biasp[(c + 8 + 2 * j + 1) % 64]);
+                        }
+                        bf16* prow = out_p + p * P.ld_outp;
+                        *reinterpret_cast<uint4*>(prow + c) = lo;
+                        *reinterpret_cast<uint4*>(prow + c + 8) = hi;
+                    }
                     float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
@@ -321,8 +372,8 @@ conv3d_bf16_fold2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 int g_num_sms2 = 0;
 
 template <int COUT, int RES_T>
-int launch_fold2(const CUtensorMap& map_a, const CUtensorMap& map_b, const float* bias, bf16* out, double* gn_stats,
-                 const FoldParams& P, size_t smem, cudaStream_t stream) {
+int launch_fold2(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap& map_p, const float* bias, bf16* out,
+                 double* gn_stats, const float* bias_p, bf16* out_p, const FoldParams& P, size_t smem, cudaStream_t stream) {
     auto kern = conv3d_bf16_fold2_kernel<COUT, RES_T>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_conv3d_bf16_fold2: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
@@ -341,7 +392,7 @@ int launch_fold2(const CUtensorMap& map_a, const CUtensorMap& map_b, const float
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, map_a, map_b, bias, out, gn_stats, P);
+    e = cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_p, bias, out, gn_stats, bias_p, out_p, P);
     TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_conv3d_bf16_fold2: launch: %s", cudaGetErrorString(e));
     TDB_CHECK_LAUNCH("tdb_conv3d_bf16_fold2");
     return 0;
@@ -353,7 +404,8 @@ int launch_fold2(const CUtensorMap& map_a, const CUtensorMap& map_b, const float
 // 128 (<= 512), which is processed as N tiles of 128 channels: w_fold rows are then ordered [n tile][kz][co in tile].
 extern "C" int tdb_conv3d_bf16_fold2(const void* in, int ld_in, int pad_rows, const void* w_fold, const float* bias, void* out,
                                      int ld_out, int B, int X, int Y, int Z, int Cin, int Cout, double* gn_stats, int G,
-                                     unsigned flags, void* stream) {
+                                     unsigned flags, const void* w_proj, const float* bias_proj, void* out_proj, int ld_outp,
+                                     void* stream) {
     TDB_REQUIRE(in && w_fold && out, TDB_E_BADARG, "tdb_conv3d_bf16_fold2: null pointer");
     TDB_REQUIRE(Cin % 64 == 0 && (Cout == 32 || Cout == 64 || (Cout % 128 == 0 && Cout <= 512)) && ld_in % 8 == 0 && ld_out % 8 == 0,
                 TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_fold2: need Cin %% 64 == 0 and Cout in {32,64,128k<=512} (Cin=%d Cout=%d)", Cin, Cout);
@@ -386,8 +438,14 @@ extern "C" int tdb_conv3d_bf16_fold2(const void* in, int ld_in, int pad_rows, co
     const int a_bytes = BM * KC * 2, bh_bytes = NH * KC * 2;
     const int k_iters = 9 * (Cin / KC);
     const int budget = 221 * 1024;
-    P.b_resident = (P.n_tiles == 1 && (int64_t)k_iters * bh_bytes <= 112 * 1024) ? 1 : 0;
-    const int resident_bytes = P.b_resident ? k_iters * bh_bytes : 0;
+    P.proj = w_proj != nullptr ? 1 : 0;
+    P.ld_outp = ld_outp;
+    TDB_REQUIRE(!P.proj || (Cout <= 64 && out_proj && ld_outp % 8 == 0 && ((uintptr_t)w_proj & 15) == 0 && ((uintptr_t)out_proj & 15) == 0 &&
+                            !(flags & TDB_CONV_ALL_ROWS)),
+                TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_fold2: the fused projection needs Cout <= 64 and aligned buffers");
+    const int proj_bytes = P.proj ? (Cin / KC) * (Cout / 2) * KC * 2 : 0;
+    P.b_resident = (P.n_tiles == 1 && (int64_t)k_iters * bh_bytes + proj_bytes <= 116 * 1024) ? 1 : 0;
+    const int resident_bytes = (P.b_resident ? k_iters * bh_bytes : 0) + proj_bytes;
     const int unit = a_bytes + (P.b_resident ? 0 : bh_bytes);
     int stages = (budget - resident_bytes) / unit;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -403,7 +461,7 @@ extern "C" int tdb_conv3d_bf16_fold2(const void* in, int ld_in, int pad_rows, co
     P.all_rows = (flags & TDB_CONV_ALL_ROWS) ? 1 : 0;
     TDB_REQUIRE(!(P.all_rows && gn_stats), TDB_E_BADARG, "tdb_conv3d_bf16_fold2: fused moments are not available with ALL_ROWS");
 
-    CUtensorMap map_a, map_b;
+    CUtensorMap map_a, map_b, map_p;
     TDB_REQUIRE(encode_fn() != nullptr, TDB_E_NODEVICE, "tdb_conv3d_bf16_fold2: cuTensorMapEncodeTiled unavailable (no driver)");
     {
         const bf16* base = (const bf16*)in - (int64_t)pad_rows * ld_in;
@@ -420,13 +478,23 @@ extern "C" int tdb_conv3d_bf16_fold2(const void* in, int ld_in, int pad_rows, co
         const uint32_t box[3] = {(uint32_t)KC, (uint32_t)(NF > 256 ? NF / 4 : NH), 1};
         TDB_REQUIRE(make_map_bf16(&map_b, w_fold, 3, dims, strides, box), TDB_E_BADARG, "tdb_conv3d_bf16_fold2: tensor map (weights) rejected");
     }
+    {
+        // projection weights [Cout][Cin] (the 1x1 convolution's ordinary layout); one box = the COUT/2 rows of a CTA
+        const void* wp = P.proj ? w_proj : w_fold;
+        const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)(P.proj ? Cout : NF), 1};
+        const uint64_t strides[2] = {(uint64_t)(P.proj ? Cin : 9 * Cin), (uint64_t)Cin * (P.proj ? Cout : NF)};
+        const uint32_t box[3] = {(uint32_t)KC, (uint32_t)(Cout >= 128 ? 64 : Cout / 2), 1};
+        TDB_REQUIRE(make_map_bf16(&map_p, wp, 3, dims, strides, box), TDB_E_BADARG, "tdb_conv3d_bf16_fold2: tensor map (projection) rejected");
+    }
     const size_t smem = (size_t)resident_bytes + (size_t)stages * unit + 1024;
     cudaStream_t s = (cudaStream_t)stream;
+    bf16* o = (bf16*)out;
+    bf16* op = (bf16*)out_proj;
     if (Cout == 32) {
-        if (P.b_resident) return launch_fold2<32, 1>(map_a, map_b, bias, (bf16*)out, gn_stats, P, smem, s);
-        return launch_fold2<32, 0>(map_a, map_b, bias, (bf16*)out, gn_stats, P, smem, s);
+        if (P.b_resident) return launch_fold2<32, 1>(map_a, map_b, map_p, bias, o, gn_stats, bias_proj, op, P, smem, s);
+        return launch_fold2<32, 0>(map_a, map_b, map_p, bias, o, gn_stats, bias_proj, op, P, smem, s);
     }
-    if (Cout >= 128) return launch_fold2<128, 0>(map_a, map_b, bias, (bf16*)out, gn_stats, P, smem, s);
-    if (P.b_resident) return launch_fold2<64, 1>(map_a, map_b, bias, (bf16*)out, gn_stats, P, smem, s);
-    return launch_fold2<64, 0>(map_a, map_b, bias, (bf16*)out, gn_stats, P, smem, s);
+    if (Cout >= 128) return launch_fold2<128, 0>(map_a, map_b, map_p, bias, o, gn_stats, bias_proj, op, P, smem, s);
+    if (P.b_resident) return launch_fold2<64, 1>(map_a, map_b, map_p, bias, o, gn_stats, bias_proj, op, P, smem, s);
+    return launch_fold2<64, 0>(map_a, map_b, map_p, bias, o, gn_stats, bias_proj, op, P, smem, s);
 }

@@ -75,6 +75,7 @@ class DenoiserEngine:
         self.fold = True
         self.fold2 = True
         self.fold_wide = True
+        self.fuse_proj = True
         self._plans = {}
         self._wcache = None
         self._wversion = None
@@ -234,7 +235,7 @@ class DenoiserEngine:
         return C if g is None else g
 
     # ------------------------------------------------------------------ kernels
-    def _conv(self, p, x: View, w, bias, out: View, ntaps, stats=None, G=0, all_rows=False):
+    def _conv(self, p, x: View, w, bias, out: View, ntaps, stats=None, G=0, all_rows=False, proj=None):
         """3x3x3 / 1x1x1 convolution over halo grids.  all_rows: also store the halo rows of the output
         (input-gradient convolutions; the fp32 kernel always stores every row)."""
         B = p["B"]
@@ -243,9 +244,14 @@ class DenoiserEngine:
         flags = _lib.CONV_ALL_ROWS if all_rows else 0
         if self.precision == "fp32":
             call("tdb_conv3d_f32", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ntaps, s)
-        elif self.fold_kind(ntaps, x.C, out.C, x.level) is not None:
-            pair = self.fold_kind(ntaps, x.C, out.C, x.level) == "fold2"
-            call("tdb_conv3d_bf16_fold2" if pair else "tdb_conv3d_bf16_fold", x.ptr, x.ld, self.pad_rows((X, Y, Z)), w.data_ptr(), ptr(bias), out.ptr, out.ld,
+        elif self.fold_kind(ntaps, x.C, out.C, x.level) == "fold2":
+            # proj = (weights [Cout][Cin] bf16, bias, output view): the block's 1x1 residual projection, fused
+            pw, pb, pv = proj if proj is not None else (None, None, None)
+            call("tdb_conv3d_bf16_fold2", x.ptr, x.ld, self.pad_rows((X, Y, Z)), w.data_ptr(), ptr(bias), out.ptr, out.ld,
+                 B, X, Y, Z, x.C, out.C, ptr(stats), G, flags, ptr(pw), ptr(pb), pv.ptr if pv is not None else None,
+                 pv.ld if pv is not None else 0, s)
+        elif self.fold_kind(ntaps, x.C, out.C, x.level) == "fold":
+            call("tdb_conv3d_bf16_fold", x.ptr, x.ld, self.pad_rows((X, Y, Z)), w.data_ptr(), ptr(bias), out.ptr, out.ld,
                  B, X, Y, Z, x.C, out.C, ptr(stats), G, flags, s)
         else:
             rows = B * (X + 2) * (Y + 2) * (Z + 2)
@@ -271,7 +277,11 @@ class DenoiserEngine:
         Xo, Yo, Zo = p["sizes"][out.level]
         call("tdb_trilinear", x.ptr, x.ld, Xi, Yi, Zi, out.ptr, out.ld, Xo, Yo, Zo, p["B"], x.C, self.dt, _lib.stream_ptr())
 
-    def _norm_conv(self, p, x: View, w, conv, norm, raw: View, stats_slot):
+    def can_fuse_proj(self, x: View, cout) -> bool:
+        """The 1x1 residual projection rides on conv1's centre-tap tiles when conv1 runs on a CTA pair (Cout <= 64)."""
+        return self.fuse_proj and cout <= 64 and self.fold_kind(27, x.C, cout, x.level) == "fold2"
+
+    def _norm_conv(self, p, x: View, w, conv, norm, raw: View, stats_slot, proj=None):
         """conv (+bias) followed by GroupNorm moments of its output."""
         G = self._groups(raw.C)
         stats = p["stats"][stats_slot]
@@ -280,7 +290,7 @@ class DenoiserEngine:
             fused = self.fused_stats and cpg % 2 == 0
         else:
             fused = self.fused_stats and (cpg % 16 == 0 or 16 % cpg == 0)
-        self._conv(p, x, w, conv.bias, raw, 27, stats if fused else None, G)
+        self._conv(p, x, w, conv.bias, raw, 27, stats if fused else None, G, proj=proj)
         if not fused:
             self._stats(p, raw, stats, G)
         return stats, G
@@ -307,13 +317,17 @@ class DenoiserEngine:
             raw = raw_b = p["raw"][lvl].slice(0, bp.cout)
             act = p["act"][lvl].slice(0, bp.cout)
         film_ptr = p["film"].data_ptr() + 4 * bp.film_offset
-        st, G = self._norm_conv(p, x, w[f"{name}.conv1"], blk.block1.conv, blk.block1.norm, raw, slot)
+        proj = None
+        if bp.has_proj and self.can_fuse_proj(x, bp.cout):
+            proj = (w[f"{name}.proj"], blk.conv.bias, p["res"][lvl].slice(0, bp.cout))
+        st, G = self._norm_conv(p, x, w[f"{name}.conv1"], blk.block1.conv, blk.block1.norm, raw, slot, proj=proj)
         self._pointwise(p, raw, st, blk.block1.norm, film_ptr, None, act, PW_SILU, G)
         raw = raw_b
         st, G = self._norm_conv(p, act, w[f"{name}.conv2"], blk.block2.conv, blk.block2.norm, raw, slot + 1)
         if bp.has_proj:
             res = p["res"][lvl].slice(0, bp.cout)
-            self._conv(p, x, w[f"{name}.proj"], blk.conv.bias, res, 1)
+            if proj is None:
+                self._conv(p, x, w[f"{name}.proj"], blk.conv.bias, res, 1)
         else:
             res = x
         self._pointwise(p, raw, st, blk.block2.norm, None, res, out, PW_SILU, G)

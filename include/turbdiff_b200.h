@@ -109,12 +109,16 @@ TDB_API int tdb_conv3d_bf16_fold(const void* in, int ld_in, int pad_rows, const 
                          int ld_out, int B, int X, int Y, int Z, int Cin, int Cout, double* gn_stats,
                          int G, unsigned flags, void* stream);
 
-/* cta_group::2 variant of tdb_conv3d_bf16_fold (same contract; Cin % 64 == 0, Cout in {32,64}): two CTAs of a
- * cluster issue one 256-row MMA, each staging half of the weight rows, which stay resident in shared memory
- * when the half fits (64->64, 128->32). */
+/* cta_group::2 variant of tdb_conv3d_bf16_fold (same contract; Cin % 64 == 0; Cout in {32,64} or a multiple of 128
+ * <= 512, processed as 128-channel N tiles with w_fold rows ordered [tile][kz][co]): two CTAs of a cluster issue
+ * one 256-row MMA, each staging half of the weight rows, which stay resident in shared memory when the half fits.
+ * w_proj (nullable, Cout <= 64): bf16 [Cout][Cin] weights of the ResnetBlock's 1x1x1 residual projection of the SAME
+ * input (ddpm.py:188,197); it is evaluated on the centre-tap activation tiles at no extra traffic and written
+ * (+ bias_proj) to the halo grid out_proj (interior rows). */
 TDB_API int tdb_conv3d_bf16_fold2(const void* in, int ld_in, int pad_rows, const void* w_fold, const float* bias,
                           void* out, int ld_out, int B, int X, int Y, int Z, int Cin, int Cout, double* gn_stats,
-                          int G, unsigned flags, void* stream);
+                          int G, unsigned flags, const void* w_proj, const float* bias_proj, void* out_proj,
+                          int ld_outp, void* stream);
 
 /* ---- normalisation / pointwise --------------------------------------------------------- */
 

@@ -127,9 +127,21 @@ def test_conv3d_bf16_kz_folded(lib, case, entry, fused_stats):
     out = torch.zeros((B, X + 2, Y + 2, Z + 2, Cout), device="cuda", dtype=torch.bfloat16)
     G = 8
     stats = torch.zeros((B, G, 2), dtype=torch.float64, device="cuda")
+    extra = ()
+    fuse = entry.endswith("fold2") and Cout <= 64
+    if entry.endswith("fold2"):
+        # the fused 1x1 residual projection of the same input (only where the engine uses it: Cout <= 64)
+        wp = gen(Cout, Cin, 1, 1, 1, seed=21, scale=1 / math.sqrt(Cin)).bfloat16().float()
+        bp = gen(Cout, seed=22, scale=0.1)
+        outp = torch.zeros((B, X + 2, Y + 2, Z + 2, Cout + 8), device="cuda", dtype=torch.bfloat16)
+        wpp = wp.reshape(Cout, Cin).contiguous().bfloat16()
+        extra = (wpp.data_ptr(), bp.data_ptr(), outp.data_ptr() + 16, Cout + 8) if fuse else (None, None, None, 0)
     lib.call(entry, xin.data_ptr(), Cin, pad, wf.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
-             stats.data_ptr() if fused_stats else None, G, 0, lib.stream_ptr())
+             stats.data_ptr() if fused_stats else None, G, 0, *extra, lib.stream_ptr())
     torch.cuda.synchronize()
+    if fuse:
+        want_p = _conv_ref(x.double().cpu(), wp.double().cpu(), bp.double().cpu(), 1)
+        assert rel_l2(from_halo(outp, Cout, 8), want_p) < 4e-3
     want = _conv_ref(x.double().cpu(), w.double().cpu(), b.double().cpu(), 27)
     assert rel_l2(from_halo(out), want) < 4e-3
     if fused_stats:
