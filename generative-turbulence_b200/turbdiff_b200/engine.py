@@ -76,6 +76,7 @@ class DenoiserEngine:
         self.fold2 = True
         self.fold_wide = True
         self.fuse_proj = True
+        self.use_graph = True  # p_sample_loop replays the denoiser from a CUDA graph
         self._plans = {}
         self._wcache = None
         self._wversion = None
@@ -434,6 +435,46 @@ class DenoiserEngine:
         if train:
             p["last_input"] = (x, t, c_local)
         return eps
+
+    # ------------------------------------------------------------------ sampling state / CUDA graph
+    def sampler_state(self, B, spatial, device, c_local):
+        """Persistent per-plan state of an ancestral-sampling chain: the state tensor x_t, the timestep tensors and a
+        copy of c_local, all at fixed addresses, plus a CUDA graph of the denoiser launch program over them.  The
+        graph is (re)captured when the kernel-layout weights changed; replays cost one launch instead of ~80."""
+        p = self.plan(B, spatial, device)
+        m = self.model
+        st = p.get("sampler")
+        if st is None:
+            st = p["sampler"] = {
+                "x_t": torch.zeros((B, m.in_features, *spatial), dtype=torch.float32, device=device),
+                "t_vec": torch.zeros(B, dtype=torch.int64, device=device),
+                "t_dev": torch.zeros(1, dtype=torch.int32, device=device),
+                "c_local": None if c_local is None else torch.zeros_like(c_local, dtype=torch.float32),
+                "graph": None, "wver": None,
+            }
+        if c_local is not None:
+            st["c_local"].copy_(c_local)
+        return st
+
+    def forward_graphed(self, st):
+        """eps for the sampler state `st` (x_t, t_vec, c_local buffers); captures the graph on first use."""
+        self.weights()
+        if not self.use_graph:
+            return self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=True)
+        if st["graph"] is None or st["wver"] != self._wversion:
+            # eager warm-up on a side stream (also (re)writes the c_local half), then capture
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=False)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=True)
+            st["graph"], st["wver"] = g, self._wversion
+        st["graph"].replay()
+        B = st["x_t"].shape[0]
+        return self.plan(B, tuple(st["x_t"].shape[2:]), st["x_t"].device)["eps"]
 
     def backward(self, g_eps: torch.Tensor):
         """Gradients of every parameter (and of c_local) for the last `forward(train=True)`."""

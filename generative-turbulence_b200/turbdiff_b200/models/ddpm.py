@@ -393,30 +393,30 @@ class GaussianDiffusion(nn.Module):
         s = _lib.stream_ptr
 
         if start_from is None:
-            x_t = torch.randn_like(x_bcs)
+            x_init = torch.randn_like(x_bcs)
             T = self.num_timesteps
         else:
             tt = torch.full((B,), start_from - 1, dtype=torch.long, device=dev)
-            x_t = self.q_sample(x_bcs, tt, torch.randn_like(x_bcs))
+            x_init = self.q_sample(x_bcs, tt, torch.randn_like(x_bcs))
             T = start_from
         if not self.noise_bcs:
-            x_t = where_cells(cell_idx, x_t, x_bcs)
+            x_init = where_cells(cell_idx, x_init, x_bcs)
 
+        # chain state at fixed addresses + CUDA graph of the denoiser launch program (engine.sampler_state)
+        st = eng.sampler_state(B, tuple(x_bcs.shape[2:]), dev, c_local)
+        x_t, t_dev, t_vec = st["x_t"], st["t_dev"], st["t_vec"]
+        x_t.copy_(x_init)
         flags = (STEP_NOISE_BCS if self.noise_bcs else 0) | (STEP_CLIP if self.clip_denoised else 0)
-        t_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-        t_vec = torch.zeros(B, dtype=torch.int64, device=dev)
         steps = reversed(range(0, T))
         if pbar:
             from tqdm.auto import tqdm
 
             steps = tqdm(steps, desc="sampling loop time step", total=T, position=1)
-        first = True
         for t in steps:
             t_dev.fill_(t)
             t_vec.fill_(t)
             # C is constant along the chain: encode_c_local's half of the input buffer is written once
-            eps = eng.forward(x_t, t_vec, c_local, c_static=not first)
-            first = False
+            eps = eng.forward_graphed(st)
             if t > 0:
                 z = torch.randn_like(x_t)
                 z_bc = torch.randn_like(x_bcs) if self.noise_bcs else None
@@ -424,9 +424,10 @@ class GaussianDiffusion(nn.Module):
                 z, z_bc = x_t, (x_t if self.noise_bcs else None)  # ignored at t == 0
             call("tdb_ddpm_step", x_t.data_ptr(), eps.data_ptr(), z.data_ptr(), ptr(z_bc), x_bcs.data_ptr(), mask.data_ptr(),
                  coef.data_ptr(), t_dev.data_ptr(), x_t.data_ptr(), B, F, nvox, flags | (STEP_FINAL if t == 0 else 0), s())
+        out = x_t.clone()  # outputs are freshly allocated; the state buffer is reused by the next chain
         if T == 0:
-            x_t = where_cells(cell_idx, x_t, x_bcs)
-        return x_t
+            out = where_cells(cell_idx, out, x_bcs)
+        return out
 
     @property
     def loss_fn(self):
