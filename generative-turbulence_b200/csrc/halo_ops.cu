@@ -282,29 +282,39 @@ trilinear_kernel(const T* __restrict__ in, int ld_in, Grid3 gi, T* __restrict__ 
     const int ch = threadIdx.x % chunks, lane_vox = threadIdx.x / chunks;
     if (lane_vox >= vox_step) return;
     const int c0 = ch * N;
-    const uint32_t total = (uint32_t)go.vox_p;
-    for (uint32_t r = blockIdx.x * vox_step + lane_vox; r < total; r += gridDim.x * vox_step) {
-        int xp, yp, zp;
-        split(r, xp, yp, zp);
-        const Lerp lx = axis_lerp(clampi(xp - 1, 0, go.X - 1), gi.X, sx);
-        const Lerp ly = axis_lerp(clampi(yp - 1, 0, go.Y - 1), gi.Y, sy);
-        const Lerp lz = axis_lerp(clampi(zp - 1, 0, go.Z - 1), gi.Z, sz);
-        float acc[N];
+    // line walker over the output grid: x/y interpolation and the four input line bases once per (x, y) line
+    const uint32_t lines = (uint32_t)(go.Xp * go.Yp);
+    for (uint32_t line = blockIdx.x * vox_step + lane_vox; line < lines; line += gridDim.x * vox_step) {
+        uint32_t xq, yq;
+        split.by_y.divmod(line, xq, yq);
+        const Lerp lx = axis_lerp(clampi((int)xq - 1, 0, go.X - 1), gi.X, sx);
+        const Lerp ly = axis_lerp(clampi((int)yq - 1, 0, go.Y - 1), gi.Y, sy);
+        const T* base[4];
+        float wxy[4];
 #pragma unroll
-        for (int i = 0; i < N; ++i) acc[i] = 0.0f;
-#pragma unroll
-        for (int corner = 0; corner < 8; ++corner) {
-            const int xi = (corner & 4) ? lx.i1 : lx.i0;
-            const int yi = (corner & 2) ? ly.i1 : ly.i0;
-            const int zi = (corner & 1) ? lz.i1 : lz.i0;
-            const float w = ((corner & 4) ? lx.l1 : lx.l0) * ((corner & 2) ? ly.l1 : ly.l0) *
-                            ((corner & 1) ? lz.l1 : lz.l0);
-            float v[N];
-            Vec<T>::load(in + gi.row(b, xi, yi, zi) * ld_in + c0, v);
-#pragma unroll
-            for (int i = 0; i < N; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+        for (int k = 0; k < 4; ++k) {
+            const int xi = (k & 2) ? lx.i1 : lx.i0, yi = (k & 1) ? ly.i1 : ly.i0;
+            base[k] = in + gi.row(b, xi, yi, 0) * ld_in + c0;
+            wxy[k] = ((k & 2) ? lx.l1 : lx.l0) * ((k & 1) ? ly.l1 : ly.l0);
         }
-        Vec<T>::store(out + ((int64_t)b * go.vox_p + r) * ld_out + c0, acc);
+        T* dst = out + ((int64_t)b * go.vox_p + (int64_t)line * go.Zp) * ld_out + c0;
+#pragma unroll 2
+        for (int zp = 0; zp < go.Zp; ++zp) {
+            const Lerp lz = axis_lerp(clampi(zp - 1, 0, go.Z - 1), gi.Z, sz);
+            float acc[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) acc[i] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float v0[N], v1[N];
+                Vec<T>::load(base[k] + (int64_t)lz.i0 * ld_in, v0);
+                Vec<T>::load(base[k] + (int64_t)lz.i1 * ld_in, v1);
+                const float w0 = wxy[k] * lz.l0, w1 = wxy[k] * lz.l1;
+#pragma unroll
+                for (int i = 0; i < N; ++i) acc[i] = fmaf(w0, v0[i], fmaf(w1, v1[i], acc[i]));
+            }
+            Vec<T>::store(dst + (int64_t)zp * ld_out, acc);
+        }
     }
 }
 
@@ -448,7 +458,7 @@ int tdb_trilinear(const void* in, int ld_in, int Xi, int Yi, int Zi, void* out, 
     Grid3 gi(B, Xi, Yi, Zi), go(B, Xo, Yo, Zo);
     const int chunks = C / n;
     TDB_REQUIRE(go.vox_p < (1ll << 31) && chunks <= kThreads, TDB_E_UNSUPPORTED, "tdb_trilinear: grid too large for 32-bit indexing");
-    dim3 grid((unsigned)blocks_per_sample(go.vox_p * chunks, B), (unsigned)B);
+    dim3 grid((unsigned)blocks_per_sample((int64_t)go.Xp * go.Yp * chunks, B), (unsigned)B);
     const RowSplit split = make_split(go);
     auto scale_of = [](int n_in, int n_out) { return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.0f; };
     const float sx = scale_of(Xi, Xo), sy = scale_of(Yi, Yo), sz = scale_of(Zi, Zo);

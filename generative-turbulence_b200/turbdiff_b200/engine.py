@@ -136,13 +136,13 @@ class DenoiserEngine:
         """Which bf16 kernel a convolution runs on: None = per-tap kernel (tdb_conv3d_bf16), "fold" = kz-folded
         persistent kernel, "fold2" = its cta_group::2 (CTA pair) variant.  Pairs take the shapes whose folded
         weights do not fit one SM (half the weight ingest per SM, resident when the half fits) and, as 128-channel
-        N tiles, the wide layers of all but the two deepest levels (those are split-K territory)."""
+        N tiles, the wide layers of every level but the bottleneck (tiny M, huge K: split-K territory)."""
         if self.precision != "bf16" or not self.fold or ntaps != 27:
             return None
         if cout in (16, 32, 64):
             pair = self.fold2 and cin % 64 == 0 and cout in (32, 64) and 9 * cin * 3 * cout * 2 > 112 * 1024
             return "fold2" if pair else "fold"
-        if self.fold2 and self.fold_wide and cout % 128 == 0 and cout <= 512 and cin % 64 == 0 and level <= self.model.u_net_levels - 2:
+        if self.fold2 and self.fold_wide and cout % 128 == 0 and cout <= 512 and cin % 64 == 0 and level <= self.model.u_net_levels - 1:
             return "fold2"
         return None
 
