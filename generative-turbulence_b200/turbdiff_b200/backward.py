@@ -190,12 +190,8 @@ class BackwardProgram:
     @torch.no_grad()
     def run(self, g_eps: torch.Tensor):
         eng, m = self.eng, self.m
-        x_in, t, c_local = None, None, None
-        key = None
-        for k, pl in eng._plans.items():
-            if "last_input" in pl:
-                key = k
-        if key is None:
+        key = eng._last_train_key
+        if key is None or key not in eng._plans:
             raise RuntimeError("turbdiff_b200: backward called without a preceding forward(train=True)")
         p = eng._plans[key]
         x_in, t, c_local = p["last_input"]

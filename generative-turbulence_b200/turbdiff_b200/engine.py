@@ -80,6 +80,7 @@ class DenoiserEngine:
         self._plans = {}
         self._wcache = None
         self._wversion = None
+        self._last_train_key = None
 
         m = model
         un = m.u_net
@@ -434,6 +435,7 @@ class DenoiserEngine:
              B, X, Y, Z, m.dim, m.out_features, self.dt, s)
         if train:
             p["last_input"] = (x, t, c_local)
+            self._last_train_key = (B, tuple(spatial), str(x.device))
         return eps
 
     # ------------------------------------------------------------------ sampling state / CUDA graph
