@@ -400,11 +400,13 @@ def run_ours(args):
         tt = torch.tensor([e0.elapsed_time(e1) / args.train_steps], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        # one more step with per-kernel events (every rank takes part: the step contains a collective)
         train_prof = None
         if rank == 0:
             _lib.PROFILE = {}
-            train_step()
-            torch.cuda.synchronize()
+        train_step()
+        torch.cuda.synchronize()
+        if rank == 0:
             train_prof = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in _lib.PROFILE.items()}
             _lib.PROFILE = None
         train = {"steps_per_sec": 1e3 / float(tt.item()), "ms_per_step": float(tt.item()), "batch_per_gpu": TB, "global_batch": TB * world,
