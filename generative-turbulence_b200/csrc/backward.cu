@@ -2,7 +2,7 @@
 // Gradients travel as halo grids in the storage type of the forward activations.  Convolution
 // input-gradients are produced by the forward convolution kernels themselves (transposed, tap-reversed
 // weights over a zero-halo output gradient, all rows stored); the kernels here provide the rest:
-//   tdb_halo_fold            adjoint of halo materialisation: halo rows are added onto the border voxels
+//   tdb_halo_fold            adjoint of halo materialisation: halo rows are added onto the border voxels (and zeroed)
 //   tdb_pointwise_bwd_reduce per-(sample, channel) sums  A1 = sum g_u,  A2 = sum g_u * xhat
 //   tdb_pointwise_bwd_apply  GroupNorm/FiLM/SiLU input gradient from g_out and the sums
 //   tdb_conv3d_wgrad         weight gradient of the 3x3x3 / 1x1x1 convolutions (fp32 accumulate)
@@ -77,9 +77,16 @@ halo_fold_kernel(T* __restrict__ g, int ld, Grid3 gr, RowSplit split, int chunks
             for (int bb = 0; bb < ny; ++bb)
                 for (int c = 0; c < nz; ++c) {
                     float v[N];
-                    Vec<T>::load(g + ((int64_t)b * gr.vox_p + ((int64_t)ix[a] * gr.Yp + iy[bb]) * gr.Zp + iz[c]) * ld + c0, v);
+                    T* src = g + ((int64_t)b * gr.vox_p + ((int64_t)ix[a] * gr.Yp + iy[bb]) * gr.Zp + iz[c]) * ld + c0;
+                    Vec<T>::load(src, v);
 #pragma unroll
                     for (int i = 0; i < N; ++i) acc[i] += v[i];
+                    if (a | bb | c) {  // every halo row is the image of exactly one border voxel: leave it zero
+                        float z[N];
+#pragma unroll
+                        for (int i = 0; i < N; ++i) z[i] = 0.0f;
+                        Vec<T>::store(src, z);
+                    }
                 }
         Vec<T>::store(g + ((int64_t)b * gr.vox_p + r) * ld + c0, acc);
     }
@@ -650,6 +657,11 @@ int tdb_conv3d_wgrad(const void* in, int ld_in, const void* d_out, int ld_do, fl
     rows_per_block = ceil_div(rows_per_block, 16) * 16;
     dim3 grid((unsigned)ceil_div(g.rows, rows_per_block), (unsigned)tiles);
     cudaStream_t s = (cudaStream_t)stream;
+    // bf16 with a zero-halo output gradient: tcgen05 kernel (MN-major operands straight from the halo grids)
+    if (dtype == TDB_BF16 && (flags & TDB_WGRAD_ZERO_HALO) && Cin % 32 == 0 &&
+        (Cout == 32 || (Cout <= 256 && Cout % 64 == 0) || Cout % 256 == 0) && ld_in % 8 == 0 && ld_do % 8 == 0 && aligned16(in) &&
+        aligned16(d_out) && aligned16(dw))
+        return tdb_conv3d_wgrad_tc(in, ld_in, d_out, ld_do, dw, B, X, Y, Z, Cin, Cout, ntaps, TDB_WGRAD_SHARE_KZ, stream);
     const bool tensor_path = dtype == TDB_BF16 && (flags & TDB_WGRAD_ZERO_HALO) && Cin % 8 == 0 && Cout % 8 == 0 && ld_in % 8 == 0 &&
                              ld_do % 8 == 0 && aligned16(in) && aligned16(d_out);
     if (tensor_path) {

@@ -145,7 +145,8 @@ class BackwardProgram:
 
         # residual branch
         if bp.has_proj:
-            grads[f"{pre}.conv.weight"] = self._wgrad(p, x, g_out, blk.conv, 1)
+            # g_out is a folded gradient: tdb_halo_fold left its halo rows zero
+            grads[f"{pre}.conv.weight"] = self._wgrad(p, x, g_out, blk.conv, 1, zero_halo=True)
             grads[f"{pre}.conv.bias"] = self._colsum(p, g_out)
             g_res = self._tmp(p, lvl, x.C, "g_res")
             eng._conv(p, g_out, self._dgrad_weights(blk.conv, f"{name}.proj", lvl), None, g_res, 1, all_rows=True)

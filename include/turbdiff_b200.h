@@ -199,7 +199,7 @@ TDB_API int tdb_masked_loss(const float* eps, const float* noise, const uint8_t*
 /* ---- backward (training path; the reference gets these from torch.autograd) ---------------------- */
 
 /* Adjoint of halo materialisation: for every border voxel, add the gradient stored on its halo images
- * (in place; halo rows are left untouched and must not be read afterwards). */
+ * (in place); the halo rows are then set to zero, so a folded gradient qualifies for TDB_WGRAD_ZERO_HALO. */
 TDB_API int tdb_halo_fold(void* g, int ld, int B, int X, int Y, int Z, int C, int dtype, void* stream);
 
 /* Backward of tdb_pointwise, pass 1: red[b][c] = (sum g_u, sum g_u*xhat) over interior voxels in double
@@ -224,6 +224,14 @@ TDB_API int tdb_pointwise_bwd_apply(const void* g_out, int ld_g, const void* raw
 #define TDB_WGRAD_ZERO_HALO 1u
 TDB_API int tdb_conv3d_wgrad(const void* in, int ld_in, const void* d_out, int ld_do, float* dw, int B, int X, int Y,
                      int Z, int Cin, int Cout, int ntaps, int dtype, unsigned flags, void* stream);
+
+/* The bf16 tensor-core form of tdb_conv3d_wgrad (tcgen05.mma with MN-major operands straight from the halo grids);
+ * same contract as TDB_WGRAD_ZERO_HALO (d_out zero on halo rows); needs Cin % 32 == 0 and Cout in {32, 64*n <= 256,
+ * 256*n}.  tdb_conv3d_wgrad dispatches here when it can.  mode: TDB_WGRAD_SHARE_KZ = load one row window per
+ * (kx, ky) and use it for the three kz taps through row-shifted matrix descriptors (0 = one window per tap). */
+#define TDB_WGRAD_SHARE_KZ 1u
+TDB_API int tdb_conv3d_wgrad_tc(const void* in, int ld_in, const void* d_out, int ld_do, float* dw, int B, int X, int Y,
+                        int Z, int Cin, int Cout, int ntaps, unsigned mode, void* stream);
 
 /* Transpose of tdb_trilinear: d_in (interior rows; halo rows zero) from the folded output gradient. */
 TDB_API int tdb_trilinear_bwd(const void* g_out, int ld_g, int Xo, int Yo, int Zo, void* d_in, int ld_d, int Xi,

@@ -380,3 +380,91 @@ def test_q_sample_loss_and_cells(lib):
     assert torch.equal(grid.cpu(), want)
     # empty index set
     lib.call("tdb_select_cells", dx0.data_ptr(), didx.data_ptr(), sel.data_ptr(), B * Fx, nvox, 0, lib.stream_ptr())
+
+
+# --------------------------------------------------------------------------- convolution weight gradient
+WGRAD_CASES = [
+    # B, X, Y, Z, Cin, Cout, ntaps
+    (2, 12, 6, 5, 64, 64, 27),
+    (1, 17, 9, 9, 128, 32, 27),
+    (2, 9, 7, 6, 32, 32, 27),
+    (1, 10, 6, 6, 64, 128, 27),
+    (1, 8, 5, 5, 256, 64, 27),
+    (1, 6, 4, 4, 128, 256, 27),
+    (1, 6, 3, 3, 512, 512, 27),
+    (2, 10, 6, 6, 64, 128, 1),
+    (1, 34, 18, 18, 64, 64, 27),
+]
+
+
+def _wgrad_ref(x, dy, ntaps):
+    """d/dw of sum(conv(x, w) * dy) in float64 on the CPU (torch.autograd, like the reference's loss.backward())."""
+    x, dy = x.double().cpu(), dy.double().cpu()
+    k = 3 if ntaps == 27 else 1
+    w = torch.zeros(dy.shape[1], x.shape[1], k, k, k, dtype=torch.float64, requires_grad=True)
+    (g,) = torch.autograd.grad(_conv_ref(x, w, None, ntaps), w, dy)
+    return g
+
+
+def _wgrad_inputs(case, ld_extra=0):
+    B, X, Y, Z, Cin, Cout, ntaps = case
+    x = gen(B, Cin, X, Y, Z, seed=31).bfloat16().float()
+    dy = gen(B, Cout, X, Y, Z, seed=32).bfloat16().float()
+    xin = to_halo(x, dtype=torch.bfloat16, ld=Cin + ld_extra, c0=ld_extra)
+    dyh = torch.zeros((B, X + 2, Y + 2, Z + 2, Cout), device="cuda", dtype=torch.bfloat16)  # zero halo
+    dyh[:, 1:-1, 1:-1, 1:-1, :] = dy.permute(0, 2, 3, 4, 1).bfloat16()
+    return x, dy, xin, dyh
+
+
+def _dw_to_torch(dw, ntaps, Cin, Cout):
+    k = 3 if ntaps == 27 else 1
+    return dw.view(k, k, k, Cin, Cout).permute(4, 3, 0, 1, 2)
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_conv3d_wgrad_tensor_core(lib, case, mode):
+    """tcgen05 weight gradient (MN-major operands from the halo grids); mode 1 shares one row window per kz triple."""
+    B, X, Y, Z, Cin, Cout, ntaps = case
+    ld_extra = 8 if Cin == 64 else 0  # channel-pitched input view (concat slices)
+    x, dy, xin, dyh = _wgrad_inputs(case, ld_extra)
+    dw = torch.zeros((ntaps, Cin, Cout), dtype=torch.float32, device="cuda")
+    lib.call("tdb_conv3d_wgrad_tc", xin.data_ptr() + 2 * ld_extra, Cin + ld_extra, dyh.data_ptr(), Cout, dw.data_ptr(), B, X, Y, Z,
+             Cin, Cout, ntaps, mode, lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert rel_l2(_dw_to_torch(dw, ntaps, Cin, Cout), _wgrad_ref(x, dy, ntaps)) < 1e-4
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES[:4] + WGRAD_CASES[7:8])
+@pytest.mark.parametrize("prec,zero_halo", [("fp32", False), ("bf16", False), ("bf16", True)])
+def test_conv3d_wgrad_dispatch(lib, case, prec, zero_halo):
+    """tdb_conv3d_wgrad: masked SIMT path (halo rows of d_out hold garbage) and the zero-halo tensor-core path."""
+    B, X, Y, Z, Cin, Cout, ntaps = case
+    code, dt = _dt(prec)
+    x, dy, xin, dyh = _wgrad_inputs(case)
+    xin, dyh = xin.to(dt), dyh.to(dt)
+    if not zero_halo:
+        dyh = to_halo(dy, dtype=dt)  # non-zero halo rows must be ignored
+    dw = torch.zeros((ntaps, Cin, Cout), dtype=torch.float32, device="cuda")
+    lib.call("tdb_conv3d_wgrad", xin.data_ptr(), Cin, dyh.data_ptr(), Cout, dw.data_ptr(), B, X, Y, Z, Cin, Cout, ntaps, code,
+             lib.WGRAD_ZERO_HALO if zero_halo else 0, lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert rel_l2(_dw_to_torch(dw, ntaps, Cin, Cout), _wgrad_ref(x, dy, ntaps)) < 1e-4
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_halo_fold_is_adjoint_of_replicate_pad(lib, prec):
+    """tdb_halo_fold: border voxels collect the gradient of their halo images (autograd of F.pad(mode="replicate")),
+    and the halo rows are left zero."""
+    code, dt = _dt(prec)
+    B, C, X, Y, Z = 2, 16, 6, 4, 3
+    g = gen(B, X + 2, Y + 2, Z + 2, C, seed=41).to(dt)
+    x = torch.zeros(B, C, X, Y, Z, dtype=torch.float64, requires_grad=True)
+    (want,) = torch.autograd.grad(F.pad(x, (1,) * 6, mode="replicate"), x, g.double().cpu().permute(0, 4, 1, 2, 3))
+    buf = g.clone()
+    lib.call("tdb_halo_fold", buf.data_ptr(), C, B, X, Y, Z, C, code, lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert rel_l2(from_halo(buf), want) < (1e-6 if prec == "fp32" else 8e-3)
+    halo = buf.clone()
+    halo[:, 1:-1, 1:-1, 1:-1, :] = 0
+    assert float(halo.abs().max()) == 0.0
