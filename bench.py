@@ -343,7 +343,7 @@ def run_ours(args):
         for _ in range(3):
             one_step()
         torch.cuda.synchronize()
-        prof = {k: sum(a.elapsed_time(b) for a, b in v) / 3 for k, v in _lib.PROFILE.items()}
+        prof = {k: sum(a.elapsed_time(b) for a, b, _ in v) / 3 for k, v in _lib.PROFILE.items()}
         _lib.PROFILE = None
         graph = graph_saved
         pk = peaks()
@@ -393,8 +393,10 @@ def run_ours(args):
         barrier()
         n_t0 = _lib.launch_count()
         e0.record()
+        th0 = time.perf_counter()
         for _ in range(args.train_steps):
             loss = train_step()
+        host_ms = (time.perf_counter() - th0) * 1e3 / args.train_steps  # CPU time to enqueue one step (no sync inside)
         e1.record()
         barrier()
         tt = torch.tensor([e0.elapsed_time(e1) / args.train_steps], device=dev, dtype=torch.float64)
@@ -407,10 +409,15 @@ def run_ours(args):
         train_step()
         torch.cuda.synchronize()
         if rank == 0:
-            train_prof = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in _lib.PROFILE.items()}
+            train_prof = {k: sum(a.elapsed_time(b) for a, b, _ in v) for k, v in _lib.PROFILE.items()}
+            if os.environ.get("TDB_PROFILE_CALLS"):  # per-call dump (name, ms, small integer arguments) for kernel work
+                with open(os.environ["TDB_PROFILE_CALLS"], "w") as fh:
+                    for k, v in _lib.PROFILE.items():
+                        for a, b, ints in v:
+                            fh.write(f"{k}\t{a.elapsed_time(b):.4f}\t{ints}\n")
             _lib.PROFILE = None
         train = {"steps_per_sec": 1e3 / float(tt.item()), "ms_per_step": float(tt.item()), "batch_per_gpu": TB, "global_batch": TB * world,
-                 "kernel_ms_per_step": train_prof,
+                 "kernel_ms_per_step": train_prof, "host_enqueue_ms_per_step": host_ms,
                  "loss": float(loss.item()), "kernel_launches_per_step": (_lib.launch_count() - n_t0) // args.train_steps,
                  "includes": "q_sample + U-Net forward + backward + bucketed NCCL gradient all-reduce (N>1) + clip_grad_norm(0.1) + RAdam step",
                  "train_flops_per_step": 3 * conv_flops_per_sample(spec, geo.padded) * TB}

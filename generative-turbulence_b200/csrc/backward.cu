@@ -54,6 +54,33 @@ __device__ __forceinline__ int axis_images(int c, int n, int (&img)[3]) {
 }
 
 template <typename T>
+__device__ __forceinline__ void fold_border_voxel(T* __restrict__ g, int ld, const Grid3& gr, int b, int xp, int yp, int zp, int c0) {
+    constexpr int N = Vec<T>::N;
+    int ix[3], iy[3], iz[3];
+    const int nx = axis_images(xp, gr.X, ix), ny = axis_images(yp, gr.Y, iy), nz = axis_images(zp, gr.Z, iz);
+    float acc[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc[i] = 0.0f;
+    for (int a = 0; a < nx; ++a)
+        for (int bb = 0; bb < ny; ++bb)
+            for (int c = 0; c < nz; ++c) {
+                float v[N];
+                T* src = g + ((int64_t)b * gr.vox_p + ((int64_t)ix[a] * gr.Yp + iy[bb]) * gr.Zp + iz[c]) * ld + c0;
+                Vec<T>::load(src, v);
+#pragma unroll
+                for (int i = 0; i < N; ++i) acc[i] += v[i];
+                if (a | bb | c) {  // every halo row is the image of exactly one border voxel: leave it zero
+                    float z[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) z[i] = 0.0f;
+                    Vec<T>::store(src, z);
+                }
+            }
+    Vec<T>::store(g + ((int64_t)b * gr.vox_p + ((int64_t)xp * gr.Yp + yp) * gr.Zp + zp) * ld + c0, acc);
+}
+
+// generic form: walks every row and keeps the border voxels (grids with an axis of length 1)
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
 halo_fold_kernel(T* __restrict__ g, int ld, Grid3 gr, RowSplit split, int chunks) {
     constexpr int N = Vec<T>::N;
@@ -61,40 +88,85 @@ halo_fold_kernel(T* __restrict__ g, int ld, Grid3 gr, RowSplit split, int chunks
     const int vox_step = kThreads / chunks;
     const int ch = threadIdx.x % chunks, lane_vox = threadIdx.x / chunks;
     if (lane_vox >= vox_step) return;
-    const int c0 = ch * N;
     for (uint32_t r = blockIdx.x * vox_step + lane_vox; r < (uint32_t)gr.vox_p; r += gridDim.x * vox_step) {
         int xp, yp, zp;
         split(r, xp, yp, zp);
         const bool interior = xp >= 1 && xp <= gr.X && yp >= 1 && yp <= gr.Y && zp >= 1 && zp <= gr.Z;
         const bool border = xp == 1 || xp == gr.X || yp == 1 || yp == gr.Y || zp == 1 || zp == gr.Z;
-        if (!interior || !border) continue;
-        int ix[3], iy[3], iz[3];
-        const int nx = axis_images(xp, gr.X, ix), ny = axis_images(yp, gr.Y, iy), nz = axis_images(zp, gr.Z, iz);
-        float acc[N];
+        if (interior && border) fold_border_voxel<T>(g, ld, gr, b, xp, yp, zp, ch * N);
+    }
+}
+
+// X, Y, Z >= 2: enumerates only the border voxels - the two x faces, then the y faces without the x faces,
+// then the z faces without both (12x fewer work items than rows at 192x48x48).  Every axis has at most one halo
+// image, so the <= 8 image rows are loaded with independent predicated loads before anything is stored.
+struct BorderEnum {
+    uint32_t n_xf, n_yf, n_total;
+    FastDiv by_yz, by_z, by_xz, by_xy, by_ym2;
+};
+__device__ __forceinline__ int halo_image(int c, int n) { return c == 1 ? 0 : (c == n ? n + 1 : -1); }
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+halo_fold_border_kernel(T* __restrict__ g, int ld, Grid3 gr, BorderEnum e, int chunks) {
+    constexpr int N = Vec<T>::N;
+    const int b = blockIdx.y;
+    const int vox_step = kThreads / chunks;
+    const int ch = threadIdx.x % chunks, lane_vox = threadIdx.x / chunks;
+    if (lane_vox >= vox_step) return;
+    T* gb = g + (int64_t)b * gr.vox_p * ld + ch * N;
+    for (uint32_t k = blockIdx.x * vox_step + lane_vox; k < e.n_total; k += gridDim.x * vox_step) {
+        uint32_t face, rem, a, c;
+        int xp, yp, zp;
+        if (k < e.n_xf) {
+            e.by_yz.divmod(k, face, rem);
+            e.by_z.divmod(rem, a, c);
+            xp = face ? gr.X : 1; yp = (int)a + 1; zp = (int)c + 1;
+        } else if (k < e.n_xf + e.n_yf) {
+            e.by_xz.divmod(k - e.n_xf, face, rem);
+            e.by_z.divmod(rem, a, c);
+            xp = (int)a + 2; yp = face ? gr.Y : 1; zp = (int)c + 1;
+        } else {
+            e.by_xy.divmod(k - e.n_xf - e.n_yf, face, rem);
+            e.by_ym2.divmod(rem, a, c);
+            xp = (int)a + 2; yp = (int)c + 2; zp = face ? gr.Z : 1;
+        }
+        const int xi = halo_image(xp, gr.X), yi = halo_image(yp, gr.Y), zi = halo_image(zp, gr.Z);
+        float v[8][N];
+        int64_t off[8];
+        bool on[8];
 #pragma unroll
-        for (int i = 0; i < N; ++i) acc[i] = 0.0f;
-        for (int a = 0; a < nx; ++a)
-            for (int bb = 0; bb < ny; ++bb)
-                for (int c = 0; c < nz; ++c) {
-                    float v[N];
-                    T* src = g + ((int64_t)b * gr.vox_p + ((int64_t)ix[a] * gr.Yp + iy[bb]) * gr.Zp + iz[c]) * ld + c0;
-                    Vec<T>::load(src, v);
+        for (int j = 0; j < 8; ++j) {
+            const int xx = (j & 4) ? xi : xp, yy = (j & 2) ? yi : yp, zz = (j & 1) ? zi : zp;
+            on[j] = xx >= 0 && yy >= 0 && zz >= 0;
+            off[j] = (((int64_t)xx * gr.Yp + yy) * gr.Zp + zz) * ld;
+            if (on[j]) Vec<T>::load(gb + off[j], v[j]);
+        }
+        float acc[N], zero[N];
 #pragma unroll
-                    for (int i = 0; i < N; ++i) acc[i] += v[i];
-                    if (a | bb | c) {  // every halo row is the image of exactly one border voxel: leave it zero
-                        float z[N];
+        for (int i = 0; i < N; ++i) {
+            acc[i] = v[0][i];
+            zero[i] = 0.0f;
+        }
 #pragma unroll
-                        for (int i = 0; i < N; ++i) z[i] = 0.0f;
-                        Vec<T>::store(src, z);
-                    }
-                }
-        Vec<T>::store(g + ((int64_t)b * gr.vox_p + r) * ld + c0, acc);
+        for (int j = 1; j < 8; ++j)
+            if (on[j]) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) acc[i] += v[j][i];
+                Vec<T>::store(gb + off[j], zero);  // every halo row is the image of exactly one border voxel
+            }
+        Vec<T>::store(gb + off[0], acc);
     }
 }
 
 // ---------------------------------------------------------------- pointwise backward
+template <typename T>
 __device__ __forceinline__ float dsilu(float u) {
-    const float s = 1.0f / (1.0f + expf(-u));
+    float s;
+    if constexpr (sizeof(T) == 2)  // bf16 storage: fast exp / reciprocal are far below the output rounding
+        s = __fdividef(1.0f, 1.0f + __expf(-u));
+    else
+        s = 1.0f / (1.0f + expf(-u));
     return s * (1.0f + u * (1.0f - s));
 }
 
@@ -124,17 +196,18 @@ __device__ __forceinline__ PwCoef pw_coef(int b, int c, int C, int G, const doub
     return r;
 }
 
-// red[b][c] = (sum g_u, sum g_u*xhat) over interior voxels (pre-zeroed): fp32 per thread (<= 32 voxels), fp32 shared
-// atomics per CTA, one double atomic per (CTA, channel, moment)
+// red[b][c] = (sum g_u, sum g_u*xhat, sum raw) over interior voxels (pre-zeroed): fp32 per thread (<= 32 voxels),
+// fp32 shared atomics per CTA, one double atomic per (CTA, channel, moment).  The third sum lets the host derive the
+// per-channel sum of d_raw (= the bias gradient of the convolution below) without another pass over d_raw.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 pw_bwd_reduce_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict__ raw, int ld_raw,
                      const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                      const float* __restrict__ film, int film_ld, double* __restrict__ red, Grid3 gr, int C, int G, float eps,
-                     unsigned flags, int vox_per_block) {
+                     unsigned flags, int vox_per_block, FastDiv by_z, FastDiv by_y) {
     constexpr int N = Vec<T>::N;
-    extern __shared__ float sred[];  // [C][2]
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.0f;
+    extern __shared__ float sred[];  // [C][3]
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sred[i] = 0.0f;
     __syncthreads();
     const int b = blockIdx.y;
     const int chunks = C / N;
@@ -143,40 +216,75 @@ pw_bwd_reduce_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict_
     if (lane_vox < vox_step) {
         const int c0 = ch * N;
         const double inv_n = 1.0 / ((double)(C / G) * gr.X * gr.Y * gr.Z);
-        PwCoef k[N];
+        // the loop accumulates raw moments (sum g_u, sum g_u*raw, sum raw); xhat = (raw-mean)*rstd is applied to the
+        // block's partial sums at the flush, which keeps mean/rstd out of the registers of the streaming loop
+        float ka[N], ko[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) k[i] = pw_coef(b, c0 + i, C, G, stats, gamma, beta, film, film_ld, inv_n, eps);
+        for (int i = 0; i < N; ++i) {
+            const PwCoef k = pw_coef(b, c0 + i, C, G, stats, gamma, beta, film, film_ld, inv_n, eps);
+            ka[i] = k.a;
+            ko[i] = k.o;
+        }
         const bool act = flags & TDB_PW_SILU;
-        const int64_t nvox = (int64_t)gr.X * gr.Y * gr.Z;
-        const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
-        const int64_t v_end = min(nvox, v_begin + vox_per_block);
-        float a1[N], a2[N];
+        const uint32_t nvox = (uint32_t)(gr.X * gr.Y * gr.Z);
+        const uint32_t v_begin = blockIdx.x * (uint32_t)vox_per_block;
+        const uint32_t v_end = min(nvox, v_begin + (uint32_t)vox_per_block);
+        const T* rb = raw + (int64_t)b * gr.vox_p * ld_raw + c0;
+        const T* gb = g_out + (int64_t)b * gr.vox_p * ld_g + c0;
+        float a1[N], a2[N], a3[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) a1[i] = a2[i] = 0.0f;
-        for (int64_t v = v_begin + lane_vox; v < v_end; v += vox_step) {
-            const int z = (int)(v % gr.Z);
-            const int y = (int)((v / gr.Z) % gr.Y);
-            const int x = (int)(v / ((int64_t)gr.Z * gr.Y));
-            const int64_t row = gr.row(b, x, y, z);
-            float xv[N], gv[N];
-            Vec<T>::load(raw + row * ld_raw + c0, xv);
-            Vec<T>::load(g_out + row * ld_g + c0, gv);
+        for (int i = 0; i < N; ++i) a1[i] = a2[i] = a3[i] = 0.0f;
+        auto row_of = [&](uint32_t v) {
+            uint32_t q, z, x, y;
+            by_z.divmod(v, q, z);
+            by_y.divmod(q, x, y);
+            return ((int64_t)(x + 1) * gr.Yp + (y + 1)) * gr.Zp + (z + 1);
+        };
+        auto accumulate = [&](const float (&xv)[N], const float (&gv)[N]) {
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                const float u = fmaf(k[i].a, xv[i], k[i].o);
-                const float gu = act ? gv[i] * dsilu(u) : gv[i];
+                const float u = fmaf(ka[i], xv[i], ko[i]);
+                const float gu = act ? gv[i] * dsilu<T>(u) : gv[i];
                 a1[i] += gu;
-                a2[i] = fmaf(gu, (xv[i] - k[i].mean) * k[i].rstd, a2[i]);
+                a2[i] = fmaf(gu, xv[i], a2[i]);
+                a3[i] += xv[i];
             }
+        };
+        uint32_t v = v_begin + lane_vox;
+        for (; v + vox_step < v_end; v += 2 * vox_step) {  // two voxels in flight
+            const int64_t r0 = row_of(v), r1 = row_of(v + vox_step);
+            float x0[N], g0[N], x1[N], g1[N];
+            Vec<T>::load(rb + r0 * ld_raw, x0);
+            Vec<T>::load(gb + r0 * ld_g, g0);
+            Vec<T>::load(rb + r1 * ld_raw, x1);
+            Vec<T>::load(gb + r1 * ld_g, g1);
+            accumulate(x0, g0);
+            accumulate(x1, g1);
+        }
+        if (v < v_end) {
+            const int64_t r0 = row_of(v);
+            float x0[N], g0[N];
+            Vec<T>::load(rb + r0 * ld_raw, x0);
+            Vec<T>::load(gb + r0 * ld_g, g0);
+            accumulate(x0, g0);
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            atomicAdd(&sred[2 * (c0 + i)], a1[i]);
-            atomicAdd(&sred[2 * (c0 + i) + 1], a2[i]);
+            atomicAdd(&sred[3 * (c0 + i)], a1[i]);
+            atomicAdd(&sred[3 * (c0 + i) + 1], a2[i]);
+            atomicAdd(&sred[3 * (c0 + i) + 2], a3[i]);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&red[(int64_t)b * 2 * C + i], (double)sred[i]);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double inv_n = 1.0 / ((double)(C / G) * gr.X * gr.Y * gr.Z);
+        const PwCoef k = pw_coef(b, c, C, G, stats, gamma, beta, film, film_ld, inv_n, eps);
+        const float s1 = sred[3 * c], s2 = sred[3 * c + 1], s3 = sred[3 * c + 2];
+        double* dst = red + ((int64_t)b * C + c) * 3;
+        atomicAdd(dst, (double)s1);
+        atomicAdd(dst + 1, (double)(k.rstd * (s2 - k.mean * s1)));  // sum g_u * xhat
+        atomicAdd(dst + 2, (double)s3);
+    }
 }
 
 // d_raw = rstd * (k*g_u - m1 - xhat*m2) on interior rows, 0 on halo rows.  grp[b][g] = (m1, m2) fp32.
@@ -193,14 +301,19 @@ pw_bwd_apply_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict__
     if (lane_vox >= vox_step) return;
     const int c0 = ch * N;
     const double inv_n = 1.0 / ((double)(C / G) * gr.X * gr.Y * gr.Z);
-    PwCoef k[N];
-    float m1[N], m2[N];
+    // d_raw = rstd*(k*g_u - m1 - xhat*m2) = c1*g_u + c2*raw + c3 with per-channel constants
+    float ka[N], ko[N], c1[N], c2[N], c3[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        k[i] = pw_coef(b, c0 + i, C, G, stats, gamma, beta, film, film_ld, inv_n, eps);
+        const PwCoef k = pw_coef(b, c0 + i, C, G, stats, gamma, beta, film, film_ld, inv_n, eps);
         const int gi = (c0 + i) / (C / G);
-        m1[i] = stats ? grp[((int64_t)b * G + gi) * 2] : 0.0f;
-        m2[i] = stats ? grp[((int64_t)b * G + gi) * 2 + 1] : 0.0f;
+        const float m1 = stats ? grp[((int64_t)b * G + gi) * 2] : 0.0f;
+        const float m2 = stats ? grp[((int64_t)b * G + gi) * 2 + 1] : 0.0f;
+        ka[i] = k.a;
+        ko[i] = k.o;
+        c1[i] = stats ? k.rstd * k.k : 1.0f;
+        c2[i] = stats ? -k.rstd * k.rstd * m2 : 0.0f;
+        c3[i] = stats ? -k.rstd * m1 - c2[i] * k.mean : 0.0f;
     }
     const bool act = flags & TDB_PW_SILU;
     for (uint32_t r = blockIdx.x * vox_step + lane_vox; r < (uint32_t)gr.vox_p; r += gridDim.x * vox_step) {
@@ -215,16 +328,68 @@ pw_bwd_apply_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict__
             Vec<T>::load(g_out + row * ld_g + c0, gv);
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                const float u = fmaf(k[i].a, xv[i], k[i].o);
-                const float gu = act ? gv[i] * dsilu(u) : gv[i];
-                const float xh = (xv[i] - k[i].mean) * k[i].rstd;
-                o[i] = stats ? k[i].rstd * (k[i].k * gu - m1[i] - xh * m2[i]) : gu;
+                const float u = fmaf(ka[i], xv[i], ko[i]);
+                const float gu = act ? gv[i] * dsilu<T>(u) : gv[i];
+                o[i] = fmaf(c1[i], gu, fmaf(c2[i], xv[i], c3[i]));
             }
         } else {
 #pragma unroll
             for (int i = 0; i < N; ++i) o[i] = 0.0f;
         }
         Vec<T>::store(d_raw + row * ld_d + c0, o);
+    }
+}
+
+// ---------------------------------------------------------------- pointwise backward: group / parameter bookkeeping
+// One block.  From red[b][c] = (A1, A2, Sx) and the forward moments: grp[b][g] = (m1, m2) for the apply pass,
+// colsum[c] = sum over samples and voxels of d_raw (bias gradient of the convolution that produced raw),
+// gw[c] / gb[c] = GroupNorm weight / bias gradients, dfilm[b][c], dfilm[b][C + c] = FiLM scale / shift gradients.
+__global__ void __launch_bounds__(kThreads)
+pw_bwd_finalize_kernel(const double* __restrict__ red, const double* __restrict__ stats, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, const float* __restrict__ film, int film_ld, float* __restrict__ grp,
+                       float* __restrict__ colsum, float* __restrict__ gw, float* __restrict__ gb, float* __restrict__ dfilm,
+                       int dfilm_ld, int B, int C, int G, double nv, double eps) {
+    extern __shared__ double sg[];  // [B*G][4] = mean, rstd, m1, m2
+    const int cpg = C / G;
+    const double n = (double)cpg * nv;
+    for (int i = threadIdx.x; i < B * G; i += blockDim.x) {
+        const int b = i / G, g = i % G;
+        const double mean = stats[(int64_t)i * 2] / n;
+        const double var = fmax(stats[(int64_t)i * 2 + 1] / n - mean * mean, 0.0);
+        const double rstd = 1.0 / sqrt(var + eps);
+        double m1 = 0.0, m2 = 0.0;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            double k = (double)gamma[c];
+            if (film) k *= (double)film[(int64_t)b * film_ld + c] + 1.0;
+            m1 += k * red[((int64_t)b * C + c) * 3];
+            m2 += k * red[((int64_t)b * C + c) * 3 + 1];
+        }
+        m1 /= n;
+        m2 /= n;
+        sg[4 * i] = mean; sg[4 * i + 1] = rstd; sg[4 * i + 2] = m1; sg[4 * i + 3] = m2;
+        grp[2 * i] = (float)m1;
+        grp[2 * i + 1] = (float)m2;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        double cs = 0.0, w = 0.0, bsum = 0.0;
+        for (int b = 0; b < B; ++b) {
+            const double* r = red + ((int64_t)b * C + c) * 3;
+            const double* q = sg + 4 * (b * G + g);
+            const double sc = film ? (double)film[(int64_t)b * film_ld + c] + 1.0 : 1.0;
+            const double k = (double)gamma[c] * sc;
+            cs += q[1] * (k * r[0] - nv * q[2] - q[3] * q[1] * (r[2] - nv * q[0]));
+            w += sc * r[1];
+            bsum += sc * r[0];
+            if (dfilm) {
+                dfilm[(int64_t)b * dfilm_ld + c] = (float)((double)gamma[c] * r[1] + (double)beta[c] * r[0]);
+                dfilm[(int64_t)b * dfilm_ld + C + c] = (float)r[0];
+            }
+        }
+        colsum[c] = (float)cs;
+        gw[c] = (float)w;
+        gb[c] = (float)bsum;
     }
 }
 
@@ -569,6 +734,63 @@ cl_nc_outer_kernel(const T* __restrict__ G, int ld, const float* __restrict__ Q,
     }
 }
 
+// Vector form (C/N a power of two <= 32, pitch and base 16-byte aligned): thread = (voxel lane, 16-byte channel
+// chunk) with FMAX x N accumulators in registers; warp shuffles over the voxel lanes, shared-memory atomics over
+// the warps, then one global atomicAdd per (c, f) and block.
+template <typename T, int FMAX>
+__global__ void __launch_bounds__(kThreads)
+cl_nc_outer_vec_kernel(const T* __restrict__ G, int ld, const float* __restrict__ Q, int64_t q_bstride, float* __restrict__ out,
+                       Grid3 gr, int C, int F, int chunks, int vox_per_block, FastDiv by_z, FastDiv by_y) {
+    constexpr int N = Vec<T>::N;
+    __shared__ float sred[32 * N * FMAX];
+    const int b = blockIdx.y;
+    const uint32_t nvox = (uint32_t)(gr.X * gr.Y * gr.Z);
+    const uint32_t v_begin = blockIdx.x * (uint32_t)vox_per_block;
+    const uint32_t v_end = min(nvox, v_begin + (uint32_t)vox_per_block);
+    const int ch = threadIdx.x % chunks, lane_vox = threadIdx.x / chunks, vox_lanes = kThreads / chunks;
+    const T* gb = G + (int64_t)b * gr.vox_p * ld + ch * N;
+    for (int f0 = 0; f0 < F; f0 += FMAX) {
+        const int nf = min(FMAX, F - f0);
+        for (int i = threadIdx.x; i < C * FMAX; i += kThreads) sred[i] = 0.0f;
+        __syncthreads();
+        float acc[FMAX][N];
+#pragma unroll
+        for (int f = 0; f < FMAX; ++f)
+#pragma unroll
+            for (int i = 0; i < N; ++i) acc[f][i] = 0.0f;
+        const float* qb = Q + (int64_t)b * q_bstride + (int64_t)f0 * nvox;
+        for (uint32_t v = v_begin + lane_vox; v < v_end; v += vox_lanes) {
+            uint32_t q, z, x, y;
+            by_z.divmod(v, q, z);
+            by_y.divmod(q, x, y);
+            float g[N];
+            Vec<T>::load(gb + (((int64_t)(x + 1) * gr.Yp + (y + 1)) * gr.Zp + (z + 1)) * ld, g);
+#pragma unroll
+            for (int f = 0; f < FMAX; ++f) {
+                if (f < nf) {
+                    const float qv = __ldg(qb + (int64_t)f * nvox + v);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) acc[f][i] = fmaf(g[i], qv, acc[f][i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < FMAX; ++f)
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                float v = acc[f][i];
+                for (int o = 16; o >= chunks; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if ((threadIdx.x & 31) < chunks && f < nf) atomicAdd(&sred[(ch * N + i) * FMAX + f], v);
+            }
+        __syncthreads();
+        for (int i = threadIdx.x; i < C * FMAX; i += kThreads) {
+            const int c = i / FMAX, f = i % FMAX;
+            if (f < nf) atomicAdd(&out[(int64_t)c * F + f0 + f], sred[i]);
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -579,6 +801,21 @@ int tdb_halo_fold(void* g, int ld, int B, int X, int Y, int Z, int C, int dtype,
     TDB_REQUIRE(C % n == 0 && ld % n == 0 && C / n <= kThreads && aligned16(g), TDB_E_UNSUPPORTED, "tdb_halo_fold: C/ld must be multiples of %d", n);
     Grid3 gr(B, X, Y, Z);
     const int chunks = C / n;
+    if (X >= 2 && Y >= 2 && Z >= 2) {
+        BorderEnum e;
+        e.n_xf = 2u * Y * Z;
+        e.n_yf = 2u * (X - 2) * Z;
+        e.n_total = e.n_xf + e.n_yf + 2u * (X - 2) * (Y - 2);
+        auto fd = [](int v) { return FastDiv((uint32_t)(v < 1 ? 1 : v)); };
+        e.by_yz = fd(Y * Z); e.by_z = fd(Z); e.by_xz = fd((X - 2) * Z); e.by_xy = fd((X - 2) * (Y - 2)); e.by_ym2 = fd(Y - 2);
+        dim3 grid((unsigned)ceil_div((int64_t)e.n_total * chunks, kThreads), (unsigned)B);  // one item per thread
+        if (dtype == TDB_BF16)
+            halo_fold_border_kernel<bf16><<<grid, kThreads, 0, (cudaStream_t)stream>>>((bf16*)g, ld, gr, e, chunks);
+        else
+            halo_fold_border_kernel<float><<<grid, kThreads, 0, (cudaStream_t)stream>>>((float*)g, ld, gr, e, chunks);
+        TDB_CHECK_LAUNCH("tdb_halo_fold");
+        return 0;
+    }
     dim3 grid((unsigned)blocks_per_sample(gr.vox_p * chunks, B), (unsigned)B);
     if (dtype == TDB_BF16)
         halo_fold_kernel<bf16><<<grid, kThreads, 0, (cudaStream_t)stream>>>((bf16*)g, ld, gr, make_split(gr), chunks);
@@ -603,12 +840,29 @@ int tdb_pointwise_bwd_reduce(const void* g_out, int ld_g, const void* raw, int l
     dim3 grid((unsigned)ceil_div((int64_t)X * Y * Z, vox_per_block), (unsigned)B);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == TDB_BF16)
-        pw_bwd_reduce_kernel<bf16><<<grid, kThreads, (size_t)2 * C * sizeof(float), s>>>((const bf16*)g_out, ld_g, (const bf16*)raw, ld_raw, stats, gamma, beta,
-                                                              film, film_ld, red, gr, C, G, eps, flags, vox_per_block);
+        pw_bwd_reduce_kernel<bf16><<<grid, kThreads, (size_t)3 * C * sizeof(float), s>>>((const bf16*)g_out, ld_g, (const bf16*)raw, ld_raw, stats, gamma, beta,
+                                                              film, film_ld, red, gr, C, G, eps, flags, vox_per_block, FastDiv((uint32_t)Z), FastDiv((uint32_t)Y));
     else
-        pw_bwd_reduce_kernel<float><<<grid, kThreads, (size_t)2 * C * sizeof(float), s>>>((const float*)g_out, ld_g, (const float*)raw, ld_raw, stats, gamma,
-                                                               beta, film, film_ld, red, gr, C, G, eps, flags, vox_per_block);
+        pw_bwd_reduce_kernel<float><<<grid, kThreads, (size_t)3 * C * sizeof(float), s>>>((const float*)g_out, ld_g, (const float*)raw, ld_raw, stats, gamma,
+                                                               beta, film, film_ld, red, gr, C, G, eps, flags, vox_per_block, FastDiv((uint32_t)Z), FastDiv((uint32_t)Y));
     TDB_CHECK_LAUNCH("tdb_pointwise_bwd_reduce");
+    return 0;
+}
+
+int tdb_pointwise_bwd_finalize(const double* red, const double* stats, const float* gamma, const float* beta, const float* film,
+                               int film_ld, float* grp, float* colsum, float* gw, float* gb, float* dfilm, int dfilm_ld, int B,
+                               int X, int Y, int Z, int C, int G, float eps, void* stream) {
+    TDB_REQUIRE(red && stats && gamma && beta && grp && colsum && gw && gb, TDB_E_BADARG, "tdb_pointwise_bwd_finalize: null pointer");
+    const size_t smem = (size_t)B * G * 4 * sizeof(double);
+    TDB_REQUIRE(G >= 1 && C % G == 0 && smem <= 200 * 1024, TDB_E_UNSUPPORTED,
+                "tdb_pointwise_bwd_finalize: B*G=%d groups do not fit in shared memory", B * G);
+    if (smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(pw_bwd_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_pointwise_bwd_finalize: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    pw_bwd_finalize_kernel<<<1, kThreads, smem, (cudaStream_t)stream>>>(
+        red, stats, gamma, beta, film, film_ld, grp, colsum, gw, gb, dfilm, dfilm_ld, B, C, G, (double)X * Y * Z, (double)eps);
+    TDB_CHECK_LAUNCH("tdb_pointwise_bwd_finalize");
     return 0;
 }
 
@@ -733,9 +987,29 @@ int tdb_cl_nc_outer(const void* G, int ld, const float* Q, int64_t q_bstride, fl
                     int dtype, void* stream) {
     TDB_REQUIRE(G && Q && out, TDB_E_BADARG, "tdb_cl_nc_outer: null pointer");
     Grid3 gr(B, X, Y, Z);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = dtype == TDB_BF16 ? 8 : 4;
+    const int chunks = C / n;
+    if (C % n == 0 && ld % n == 0 && aligned16(G) && chunks >= 1 && chunks <= 32 && (chunks & (chunks - 1)) == 0 &&
+        (int64_t)X * Y * Z < (1ll << 31)) {
+        const int64_t nvox = (int64_t)X * Y * Z;
+        int64_t blocks = (148 * 8) / (B < 1 ? 1 : B);
+        if (blocks < 1) blocks = 1;
+        int64_t vpb = ceil_div(nvox, blocks);
+        if (vpb < 256) vpb = 256;
+        dim3 grid((unsigned)ceil_div(nvox, vpb), (unsigned)B);
+        const FastDiv by_z((uint32_t)Z), by_y((uint32_t)Y);
+        if (dtype == TDB_BF16)
+            cl_nc_outer_vec_kernel<bf16, 4><<<grid, kThreads, 0, s>>>((const bf16*)G, ld, Q, q_bstride, out, gr, C, F, chunks, (int)vpb, by_z,
+                                                                     by_y);
+        else
+            cl_nc_outer_vec_kernel<float, 4><<<grid, kThreads, 0, s>>>((const float*)G, ld, Q, q_bstride, out, gr, C, F, chunks, (int)vpb,
+                                                                      by_z, by_y);
+        TDB_CHECK_LAUNCH("tdb_cl_nc_outer");
+        return 0;
+    }
     const int vox_per_block = 512;
     dim3 grid((unsigned)ceil_div((int64_t)X * Y * Z, vox_per_block), (unsigned)B);
-    cudaStream_t s = (cudaStream_t)stream;
     if (dtype == TDB_BF16)
         cl_nc_outer_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)G, ld, Q, q_bstride, out, gr, C, F, vox_per_block);
     else

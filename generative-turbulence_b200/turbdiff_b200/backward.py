@@ -74,28 +74,28 @@ class BackwardProgram:
         call("tdb_gn_stats", g.ptr, g.ld, acc.data_ptr(), p["B"], X, Y, Z, g.C, g.C, self.eng.dt, _lib.stream_ptr())
         return acc[:, :, 0].sum(0).float()
 
-    def _pw_bwd(self, p, g_out: View, raw: View, stats, norm, film_view, d_raw: View, flags, G):
-        """Backward of tdb_pointwise.  Returns (A1, A2) fp32 [B, C] and writes d_raw (zero halo)."""
+    def _pw_bwd(self, p, g_out: View, raw: View, stats, norm, film_view, d_raw: View, flags, G, d_film=None, film_offset=0):
+        """Backward of tdb_pointwise (GroupNorm + FiLM + SiLU).  Writes d_raw (zero halo) and, when d_film is given, the
+        FiLM scale/shift gradients of this block into d_film[:, film_offset : film_offset + 2C].  Returns fp32 [C]
+        tensors (norm weight gradient, norm bias gradient, colsum) where colsum = sum of d_raw over samples and interior
+        voxels = the bias gradient of the convolution that produced `raw` (no extra pass over d_raw)."""
         eng = self.eng
         X, Y, Z = p["sizes"][raw.level]
         B, C = p["B"], raw.C
         dev = raw.t.device
         film_ptr = None if film_view is None else film_view.data_ptr()
-        gamma = ptr(norm.weight) if norm is not None else None
-        beta = ptr(norm.bias) if norm is not None else None
-        red = torch.zeros((B, C, 2), dtype=torch.float64, device=dev)
-        call("tdb_pointwise_bwd_reduce", g_out.ptr, g_out.ld, raw.ptr, raw.ld, ptr(stats), gamma, beta, film_ptr, eng.film_rows,
-             red.data_ptr(), B, X, Y, Z, C, G, GN_EPS, flags, eng.dt, _lib.stream_ptr())
-        grp = None
-        if stats is not None:
-            k = norm.weight.detach().double()[None, :].expand(B, C)
-            if film_view is not None:
-                k = k * (film_view[:, :C].double() + 1.0)
-            n = (C // G) * X * Y * Z
-            grp = ((k[..., None] * red).view(B, G, C // G, 2).sum(2) / n).float().contiguous()
-        call("tdb_pointwise_bwd_apply", g_out.ptr, g_out.ld, raw.ptr, raw.ld, ptr(stats), gamma, beta, film_ptr, eng.film_rows,
-             ptr(grp), d_raw.ptr, d_raw.ld, B, X, Y, Z, C, G, GN_EPS, flags, eng.dt, _lib.stream_ptr())
-        return red[..., 0], red[..., 1]
+        red = torch.zeros((B, C, 3), dtype=torch.float64, device=dev)
+        call("tdb_pointwise_bwd_reduce", g_out.ptr, g_out.ld, raw.ptr, raw.ld, ptr(stats), ptr(norm.weight), ptr(norm.bias), film_ptr,
+             eng.film_rows, red.data_ptr(), B, X, Y, Z, C, G, GN_EPS, flags, eng.dt, _lib.stream_ptr())
+        out = torch.empty((3, C), dtype=torch.float32, device=dev)
+        grp = torch.empty((B, G, 2), dtype=torch.float32, device=dev)
+        dfilm_ptr = None if d_film is None else d_film.data_ptr() + 4 * film_offset
+        call("tdb_pointwise_bwd_finalize", red.data_ptr(), ptr(stats), ptr(norm.weight), ptr(norm.bias), film_ptr, eng.film_rows,
+             grp.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), dfilm_ptr, eng.film_rows, B, X, Y, Z, C, G,
+             GN_EPS, _lib.stream_ptr())
+        call("tdb_pointwise_bwd_apply", g_out.ptr, g_out.ld, raw.ptr, raw.ld, ptr(stats), ptr(norm.weight), ptr(norm.bias), film_ptr,
+             eng.film_rows, grp.data_ptr(), d_raw.ptr, d_raw.ld, B, X, Y, Z, C, G, GN_EPS, flags, eng.dt, _lib.stream_ptr())
+        return out[1], out[2], out[0]
 
     def _add_interior(self, p, a: View, b: View):
         """a[interior] += b[interior] (halo rows of `a` untouched)."""
@@ -121,24 +121,21 @@ class BackwardProgram:
         g_act = self._tmp(p, lvl, C, "g_act")
 
         # block2: pointwise (norm, SiLU, + residual) then conv2
-        a1, a2 = self._pw_bwd(p, g_out, sv["raw2"], p["stats"][slot + 1], blk.block2.norm, None, d_raw, PW_SILU, G)
-        grads[f"{pre}.block2.norm.weight"] = a2.sum(0).float()
-        grads[f"{pre}.block2.norm.bias"] = a1.sum(0).float()
+        gw, gb, bias2 = self._pw_bwd(p, g_out, sv["raw2"], p["stats"][slot + 1], blk.block2.norm, None, d_raw, PW_SILU, G)
+        grads[f"{pre}.block2.norm.weight"] = gw
+        grads[f"{pre}.block2.norm.bias"] = gb
         grads[f"{pre}.block2.conv.weight"] = self._wgrad(p, sv["act1"], d_raw, blk.block2.conv, 27, zero_halo=True)
-        grads[f"{pre}.block2.conv.bias"] = self._colsum(p, d_raw)
+        grads[f"{pre}.block2.conv.bias"] = bias2
         eng._conv(p, d_raw, self._dgrad_weights(blk.block2.conv, f"{name}.conv2", lvl), None, g_act, 27, all_rows=True)
         self._fold(p, g_act)
 
-        # block1: pointwise (norm, FiLM, SiLU) then conv1
-        a1, a2 = self._pw_bwd(p, g_act, sv["raw1"], p["stats"][slot], blk.block1.norm, film, d_raw, PW_SILU, G)
-        sc1 = film[:, :C].double() + 1.0
-        gam, bet = blk.block1.norm.weight.detach().double(), blk.block1.norm.bias.detach().double()
-        grads[f"{pre}.block1.norm.weight"] = (sc1 * a2).sum(0).float()
-        grads[f"{pre}.block1.norm.bias"] = (sc1 * a1).sum(0).float()
-        d_film[:, bp.film_offset : bp.film_offset + C] = (gam * a2 + bet * a1).float()
-        d_film[:, bp.film_offset + C : bp.film_offset + 2 * C] = a1.float()
+        # block1: pointwise (norm, FiLM, SiLU) then conv1; the FiLM scale/shift gradients go straight into d_film
+        gw, gb, bias1 = self._pw_bwd(p, g_act, sv["raw1"], p["stats"][slot], blk.block1.norm, film, d_raw, PW_SILU, G,
+                                     d_film=d_film, film_offset=bp.film_offset)
+        grads[f"{pre}.block1.norm.weight"] = gw
+        grads[f"{pre}.block1.norm.bias"] = gb
         grads[f"{pre}.block1.conv.weight"] = self._wgrad(p, x, d_raw, blk.block1.conv, 27, zero_halo=True)
-        grads[f"{pre}.block1.conv.bias"] = self._colsum(p, d_raw)
+        grads[f"{pre}.block1.conv.bias"] = bias1
         g_x = self._gbuf(p, x, ("g", name))
         eng._conv(p, d_raw, self._dgrad_weights(blk.block1.conv, f"{name}.conv1", lvl), None, g_x, 27, all_rows=True)
         self._fold(p, g_x)
@@ -180,9 +177,9 @@ class BackwardProgram:
         eng._conv(p, g_qkv, self._dgrad_weights(att.to_qkv, "attn.qkv", x.level), None, g_hn, 1, all_rows=True)
         # pre-norm
         g_x = self._gbuf(p, x, ("g", "attn_x"))
-        a1, a2 = self._pw_bwd(p, g_hn, x, p["stats"][p["attn_slot"]], pre_mod.norm, None, g_x, 0, G)
-        grads[f"{pre}.norm.weight"] = a2.sum(0).float()
-        grads[f"{pre}.norm.bias"] = a1.sum(0).float()
+        gw, gb, _ = self._pw_bwd(p, g_hn, x, p["stats"][p["attn_slot"]], pre_mod.norm, None, g_x, 0, G)
+        grads[f"{pre}.norm.weight"] = gw
+        grads[f"{pre}.norm.bias"] = gb
         # residual: out = proj + x
         self._add_interior(p, g_x, g_out)
         return g_x

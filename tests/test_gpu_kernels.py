@@ -453,11 +453,13 @@ def test_conv3d_wgrad_dispatch(lib, case, prec, zero_halo):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
-def test_halo_fold_is_adjoint_of_replicate_pad(lib, prec):
+@pytest.mark.parametrize("size", [(6, 4, 3), (2, 5, 2), (4, 1, 3), (13, 4, 4)])
+def test_halo_fold_is_adjoint_of_replicate_pad(lib, prec, size):
     """tdb_halo_fold: border voxels collect the gradient of their halo images (autograd of F.pad(mode="replicate")),
     and the halo rows are left zero."""
     code, dt = _dt(prec)
-    B, C, X, Y, Z = 2, 16, 6, 4, 3
+    B, C = 2, 16
+    X, Y, Z = size
     g = gen(B, X + 2, Y + 2, Z + 2, C, seed=41).to(dt)
     x = torch.zeros(B, C, X, Y, Z, dtype=torch.float64, requires_grad=True)
     (want,) = torch.autograd.grad(F.pad(x, (1,) * 6, mode="replicate"), x, g.double().cpu().permute(0, 4, 1, 2, 3))
