@@ -42,19 +42,19 @@ class _Denoise(torch.autograd.Function):
     def forward(ctx, model, x, t, c_local, *params):
         ctx.model = model
         ctx.n_params = len(params)
-        return model.engine().forward(x, t, c_local, train=True).clone()
+        return model.engine().train_forward(x, t, c_local).clone()
 
     @staticmethod
     def backward(ctx, g_eps):
         model = ctx.model
-        grads, g_c_local = model.engine().backward(g_eps)
+        grads, g_c_local = model.engine().train_backward(g_eps)
         out = []
         for name, prm in model.named_parameters():
             g = grads.get(name)
             if g is None:
                 raise RuntimeError(f"turbdiff_b200: no gradient produced for parameter {name}")
-            out.append(g.to(prm.dtype).reshape(prm.shape))
-        return (None, None, None, g_c_local, *out)
+            out.append(g.to(prm.dtype).reshape(prm.shape).clone())  # the program's buffers are reused by the next step
+        return (None, None, None, None if g_c_local is None else g_c_local.clone(), *out)
 
 
 def denoise_with_grad(model, x, t, c_local):

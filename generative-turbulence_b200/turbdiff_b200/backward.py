@@ -199,6 +199,7 @@ class BackwardProgram:
         dev = x_in.device
         s = _lib.stream_ptr
         dt = eng.dt
+        eng._set_geometry(key[1])
         eng.weights()
         g_eps = g_eps.to(torch.float32).contiguous()
         grads: dict[str, torch.Tensor] = {}
@@ -269,20 +270,34 @@ class BackwardProgram:
             call("tdb_decode_output", gc.ptr, gc.ld, wct.data_ptr(), zb.data_ptr(), per_sample.data_ptr(), B, X, Y, Z, dim, Fc, dt, s())
             g_c_local = per_sample.sum(0)
 
-        # timestep MLP + FiLM projections: (B, <=128)-sized matrices, differentiated with torch on the fly
-        with torch.enable_grad():
-            pc = m.process_c
-            tp = [pc[0].weight, pc[0].bias, pc[2].weight, pc[2].bias]
-            lin = [eng.blocks[n].blk.project_onto_scale_shift for n in eng.block_order]
-            emb = torch.addcmul(m.encode_t.bias, m.encode_t.scale, t[..., None].to(torch.float32)).sin()
-            c = torch.nn.functional.silu(torch.nn.functional.linear(emb, tp[0], tp[1]))
-            c = torch.nn.functional.silu(torch.nn.functional.linear(c, tp[2], tp[3]))
-            film = torch.cat([torch.nn.functional.linear(c, q.weight, q.bias) for q in lin], dim=1)
-            params = tp + [q.weight for q in lin] + [q.bias for q in lin]
-            gs = torch.autograd.grad(film, params, d_film)
-        names = ["process_c.0.weight", "process_c.0.bias", "process_c.2.weight", "process_c.2.bias"]
-        names += [f"{self.prefix[n]}.project_onto_scale_shift.weight" for n in eng.block_order]
-        names += [f"{self.prefix[n]}.project_onto_scale_shift.bias" for n in eng.block_order]
-        for n, gg in zip(names, gs):
-            grads[n] = gg
+        # timestep MLP + FiLM projections (ddpm.py:447-452, :184): (B, <=128)-sized matrices, differentiated by hand with
+        # a few torch matmuls (no nested autograd: the whole program must be CUDA-graph capturable)
+        pc = m.process_c
+        W0, b0, W2, b2 = pc[0].weight.detach(), pc[0].bias.detach(), pc[2].weight.detach(), pc[2].bias.detach()
+        lin = [eng.blocks[n].blk.project_onto_scale_shift for n in eng.block_order]
+        film_w = torch.cat([q.weight.detach() for q in lin])  # (film_rows, dim_c)
+        emb = torch.addcmul(m.encode_t.bias, m.encode_t.scale, t[..., None].to(torch.float32)).sin()
+        z1 = torch.nn.functional.linear(emb, W0, b0)
+        h1 = torch.nn.functional.silu(z1)
+        z2 = torch.nn.functional.linear(h1, W2, b2)
+        c = torch.nn.functional.silu(z2)
+
+        def dsilu(z):
+            sg = torch.sigmoid(z)
+            return sg * (1.0 + z * (1.0 - sg))
+
+        g_film_w = d_film.t() @ c          # (film_rows, dim_c)
+        g_film_b = d_film.sum(0)
+        dz2 = (d_film @ film_w) * dsilu(z2)
+        dz1 = (dz2 @ W2) * dsilu(z1)
+        grads["process_c.2.weight"] = dz2.t() @ h1
+        grads["process_c.2.bias"] = dz2.sum(0)
+        grads["process_c.0.weight"] = dz1.t() @ emb
+        grads["process_c.0.bias"] = dz1.sum(0)
+        off = 0
+        for n, q in zip(eng.block_order, lin):
+            rows = q.weight.shape[0]
+            grads[f"{self.prefix[n]}.project_onto_scale_shift.weight"] = g_film_w[off : off + rows]
+            grads[f"{self.prefix[n]}.project_onto_scale_shift.bias"] = g_film_b[off : off + rows]
+            off += rows
         return grads, g_c_local

@@ -15,6 +15,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
+import os
+
 import torch
 
 from . import _lib
@@ -74,9 +76,16 @@ class DenoiserEngine:
         self.fused_stats = precision == "bf16"
         self.fold = True
         self.fold2 = True
+        self.win = True       # row-window CTA-pair kernel for resident-weight layers with Cout >= 64
+        self._level_zp = {}   # level -> Z + 2 of the plan in use (the window kernel needs Z + 2 <= 63)
         self.fold_wide = True
         self.fuse_proj = True
         self.use_graph = True  # p_sample_loop replays the denoiser from a CUDA graph
+        # training: weight repack + forward program and the backward program are replayed from two CUDA graphs
+        # (TURBDIFF_B200_TRAIN_GRAPH=0 keeps the eager launch programs)
+        self.train_graph = os.environ.get("TURBDIFF_B200_TRAIN_GRAPH", "1") != "0"
+        self._train_graphs = {}
+        self._train_replay = None
         self._plans = {}
         self._wcache = None
         self._wversion = None
@@ -101,10 +110,15 @@ class DenoiserEngine:
     def _param_version(self):
         return tuple((p.data_ptr(), p._version) for p in self.model.parameters())
 
+    def _set_geometry(self, spatial):
+        """Per-level Z + 2 of the grid about to be processed (fold_kind() consults it for the row-window kernel)."""
+        sizes = level_sizes(tuple(spatial), self.model.u_net_levels)
+        self._level_zp = {lvl: sz[2] + 2 for lvl, sz in enumerate(sizes)}
+
     def weights(self):
         """Kernel-layout copies of the conv weights, refreshed when any parameter changed
         (optimizer step / load_state_dict).  Layout: fp32 [ntaps][Cin][Cout]; bf16 [Cout][ntaps*Cin]."""
-        ver = self._param_version()
+        ver = (self._param_version(), tuple(sorted(self._level_zp.items())))  # kernel choice depends on the grid's Z
         if self._wcache is not None and ver == self._wversion:
             return self._wcache
         m = self.model
@@ -140,6 +154,11 @@ class DenoiserEngine:
         N tiles, the wide layers of every level but the bottleneck (tiny M, huge K: split-K territory)."""
         if self.precision != "bf16" or not self.fold or ntaps != 27:
             return None
+        zp = self._level_zp.get(level, 1 << 30)
+        if self.win and cout in (64, 128) and cin % 32 == 0 and 27 * cin * cout <= 116 * 1024 and zp <= 63:
+            # row-window CTA-pair kernel: weights resident, activations staged 3x instead of 9x; needs N >= 64 (with
+            # N = 32 every MMA is bound by its 4 KB shared-memory read of A: measured slower than the kz-folded kernels)
+            return "win"
         if cout in (16, 32, 64):
             pair = self.fold2 and cin % 64 == 0 and cout in (32, 64) and 9 * cin * 3 * cout * 2 > 112 * 1024
             return "fold2" if pair else "fold"
@@ -153,7 +172,7 @@ class DenoiserEngine:
         taps = wt.shape[2] * wt.shape[3] * wt.shape[4]
         if self.precision == "fp32":
             return wt.permute(2, 3, 4, 1, 0).reshape(taps, cin, cout).contiguous().float()
-        if self.fold_kind(taps, cin, cout, level) is not None:
+        if self.fold_kind(taps, cin, cout, level) not in (None, "win"):
             # kz folded into N, N tiles of <= 128 channels: row = (tile*3 + kz)*T + co, col = (kx*3+ky)*Cin + ci
             tile = cout if cout < 128 else 128
             return (wt.reshape(cout // tile, tile, cin, 3, 3, 3).permute(0, 5, 1, 3, 4, 2)
@@ -246,6 +265,10 @@ class DenoiserEngine:
         flags = _lib.CONV_ALL_ROWS if all_rows else 0
         if self.precision == "fp32":
             call("tdb_conv3d_f32", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ntaps, s)
+        elif self.fold_kind(ntaps, x.C, out.C, x.level) == "win":
+            pw, pb, pv = proj if proj is not None else (None, None, None)
+            call("tdb_conv3d_bf16_win", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ptr(stats), G,
+                 flags, ptr(pw), ptr(pb), pv.ptr if pv is not None else None, pv.ld if pv is not None else 0, s)
         elif self.fold_kind(ntaps, x.C, out.C, x.level) == "fold2":
             # proj = (weights [Cout][Cin] bf16, bias, output view): the block's 1x1 residual projection, fused
             pw, pb, pv = proj if proj is not None else (None, None, None)
@@ -281,7 +304,7 @@ class DenoiserEngine:
 
     def can_fuse_proj(self, x: View, cout) -> bool:
         """The 1x1 residual projection rides on conv1's centre-tap tiles when conv1 runs on a CTA pair (Cout <= 64)."""
-        return self.fuse_proj and cout <= 64 and self.fold_kind(27, x.C, cout, x.level) == "fold2"
+        return self.fuse_proj and cout <= 64 and self.fold_kind(27, x.C, cout, x.level) in ("fold2", "win")
 
     def _norm_conv(self, p, x: View, w, conv, norm, raw: View, stats_slot, proj=None):
         """conv (+bias) followed by GroupNorm moments of its output."""
@@ -367,6 +390,7 @@ class DenoiserEngine:
         spatial = tuple(x.shape[2:])
         L = m.u_net_levels
         p = self.plan(B, spatial, x.device)
+        self._set_geometry(spatial)
         w = self.weights()
         s = _lib.stream_ptr()
         X, Y, Z = spatial
@@ -460,6 +484,7 @@ class DenoiserEngine:
 
     def forward_graphed(self, st):
         """eps for the sampler state `st` (x_t, t_vec, c_local buffers); captures the graph on first use."""
+        self._set_geometry(st["x_t"].shape[2:])
         self.weights()
         if not self.use_graph:
             return self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=True)
@@ -483,6 +508,60 @@ class DenoiserEngine:
         from .backward import BackwardProgram
 
         return BackwardProgram(self).run(g_eps)
+
+    # ------------------------------------------------------------------ training step as two CUDA graphs
+    def train_forward(self, x, t, c_local):
+        """forward(train=True).  With train_graph the kernel-layout weight refresh and the launch program run as ONE
+        graph replay over static input buffers (a training step is ~370 kernel launches plus ~1000 small torch ops on
+        the host otherwise); the matching backward graph is captured at the same time."""
+        if not self.train_graph or _lib.PROFILE is not None or not x.is_cuda:
+            self._train_replay = None
+            return self.forward(x, t, c_local, train=True)
+        key = (x.shape[0], tuple(x.shape[2:]), str(x.device), c_local is None)
+        sig = tuple(q.data_ptr() for q in self.model.parameters())
+        tg = self._train_graphs.get(key)
+        if tg is None or tg["sig"] != sig:
+            tg = self._train_graphs[key] = self._capture_train(x, t, c_local, sig)
+        tg["x"].copy_(x)
+        tg["t"].copy_(t)
+        if c_local is not None:
+            tg["c"].copy_(c_local)
+        tg["fwd"].replay()
+        self._last_train_key = key[:3]
+        self._train_replay = tg
+        return tg["eps"]
+
+    def train_backward(self, g_eps):
+        """Backward of the last train_forward: (parameter gradients by name, gradient of c_local)."""
+        tg = self._train_replay
+        if tg is None:
+            return self.backward(g_eps)
+        tg["g_eps"].copy_(g_eps)
+        tg["bwd"].replay()
+        return tg["grads"], tg["g_c_local"]
+
+    def _capture_train(self, x, t, c_local, sig):
+        from .backward import BackwardProgram
+
+        xs = x.detach().to(torch.float32).clone()
+        ts = t.detach().to(device=x.device, dtype=torch.int64).clone()
+        cs = None if c_local is None else c_local.detach().to(torch.float32).clone()
+        gs = torch.zeros((x.shape[0], self.model.out_features, *x.shape[2:]), dtype=torch.float32, device=x.device)
+        # eager warm-up on a side stream: plan buffers, kernel attributes and lazy caches exist before the capture
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.forward(xs, ts, cs, train=True)
+            BackwardProgram(self).run(gs)
+        torch.cuda.current_stream().wait_stream(side)
+        pool = torch.cuda.graph_pool_handle()
+        g_f, g_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_f, pool=pool):
+            self._wcache = None  # the kernel-layout weights are re-derived from the parameters inside the graph
+            eps = self.forward(xs, ts, cs, train=True)
+        with torch.cuda.graph(g_b, pool=pool):
+            grads, g_c = BackwardProgram(self).run(gs)
+        return {"sig": sig, "x": xs, "t": ts, "c": cs, "g_eps": gs, "eps": eps, "fwd": g_f, "bwd": g_b, "grads": grads, "g_c_local": g_c}
 
     @staticmethod
     def to_ncdhw(v: View) -> torch.Tensor:

@@ -1,0 +1,52 @@
+"""Times the level-0 convolutions (B=4) on the kz-folded kernels vs the row-window kernel."""
+import json, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "generative-turbulence_b200"))
+from turbdiff_b200 import _lib
+_lib.load()
+B = int(os.environ.get("B", 4))
+X, Y, Z = 194, 50, 50
+pad = (Y + 2) * (Z + 2) + 2 * (Z + 2) + 256
+rows = B * (X + 2) * (Y + 2) * (Z + 2)
+res = []
+for (Cin, Cout, old) in [(64, 64, "fold2"), (128, 32, "fold2"), (32, 32, "fold"), (32, 128, "v1"), (32, 64, "fold")]:
+    buf = torch.zeros((rows + 2 * pad, Cin), device="cuda", dtype=torch.bfloat16)
+    buf[pad:pad + rows] = (torch.randn(rows, Cin, device="cuda") * 0.5).bfloat16()
+    xin = buf[pad:pad + rows]
+    out = torch.zeros((rows, Cout), device="cuda", dtype=torch.bfloat16)
+    wf = (torch.randn(3 * Cout, 9 * Cin, device="cuda") * 0.02).bfloat16()
+    wk = (torch.randn(Cout, 27 * Cin, device="cuda") * 0.02).bfloat16()
+    bias = torch.zeros(Cout, device="cuda")
+    stats = torch.zeros((B, 8, 2), dtype=torch.float64, device="cuda")
+    s = _lib.stream_ptr
+    def run_old():
+        if old == "fold2":
+            _lib.call("tdb_conv3d_bf16_fold2", xin.data_ptr(), Cin, pad, wf.data_ptr(), bias.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z,
+                      Cin, Cout, stats.data_ptr(), 8, 0, None, None, None, 0, s())
+        elif old == "fold":
+            _lib.call("tdb_conv3d_bf16_fold", xin.data_ptr(), Cin, pad, wf.data_ptr(), bias.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z,
+                      Cin, Cout, stats.data_ptr(), 8, 0, s())
+        else:
+            _lib.call("tdb_conv3d_bf16", xin.data_ptr(), Cin, wk.data_ptr(), bias.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
+                      27, None, 8, 1, None, s())
+    def run_win():
+        _lib.call("tdb_conv3d_bf16_win", xin.data_ptr(), Cin, wk.data_ptr(), bias.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
+                  None if old == "v1" else stats.data_ptr(), 8, 1 if old == "v1" else 0, None, None, None, 0, s())
+    row = {"layer": f"{Cin}->{Cout}", "gflop": 2 * 27 * Cin * Cout * B * X * Y * Z / 1e9, "old_kernel": old}
+    for name, fn in [("old", run_old), ("win", run_win)]:
+        try:
+            fn(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            row[name + "_ms"] = round(ms, 4); row[name + "_tflops"] = round(row["gflop"] / ms, 1)
+        except Exception as ex:  # noqa
+            row[name + "_err"] = str(ex)[:300]
+            break
+    print(json.dumps(row), flush=True)
+    res.append(row)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", "bench_conv_win.json"), "w"), indent=1)

@@ -470,3 +470,62 @@ def test_halo_fold_is_adjoint_of_replicate_pad(lib, prec, size):
     halo = buf.clone()
     halo[:, 1:-1, 1:-1, 1:-1, :] = 0
     assert float(halo.abs().max()) == 0.0
+
+
+# --------------------------------------------------------------------------- row-window CTA-pair convolution
+WIN_CASES = [
+    # B, X, Y, Z, Cin, Cout, fused projection
+    (2, 12, 6, 5, 64, 64, False),
+    (1, 17, 9, 9, 128, 32, True),
+    (2, 9, 7, 6, 32, 32, False),
+    (1, 8, 6, 6, 32, 128, False),
+    (1, 10, 6, 6, 32, 64, True),
+    (1, 34, 18, 18, 64, 64, False),
+    (1, 40, 30, 30, 64, 64, False),    # several tiles per CTA pair: both TMEM stages and the window ring recycle
+    (2, 40, 20, 50, 32, 32, False),    # widest supported z-line class (Z + 2 = 52): 240-row windows
+    (3, 21, 11, 9, 128, 32, False),
+]
+
+
+@pytest.mark.parametrize("case", WIN_CASES)
+@pytest.mark.parametrize("variant", ["plain", "stats", "all_rows"])
+def test_conv3d_bf16_row_window(lib, case, variant):
+    B, X, Y, Z, Cin, Cout, with_proj = case
+    x = gen(B, Cin, X, Y, Z, seed=1).bfloat16().float()
+    w = gen(Cout, Cin, 3, 3, 3, seed=2, scale=1 / math.sqrt(Cin * 27)).bfloat16().float()
+    b = gen(Cout, seed=3, scale=0.1)
+    xin = to_halo(x, dtype=torch.bfloat16, ld=Cin + 8, c0=8)  # channel-pitched input view, no padding rows
+    wk = w.permute(0, 2, 3, 4, 1).reshape(Cout, 27 * Cin).contiguous().bfloat16()
+    out = torch.zeros((B, X + 2, Y + 2, Z + 2, Cout), device="cuda", dtype=torch.bfloat16)
+    G = 8
+    stats = torch.zeros((B, G, 2), dtype=torch.float64, device="cuda")
+    fuse = with_proj and variant != "all_rows"
+    extra = (None, None, None, 0)
+    if fuse:
+        wp = gen(Cout, Cin, 1, 1, 1, seed=21, scale=1 / math.sqrt(Cin)).bfloat16().float()
+        bp = gen(Cout, seed=22, scale=0.1)
+        outp = torch.zeros((B, X + 2, Y + 2, Z + 2, Cout + 8), device="cuda", dtype=torch.bfloat16)
+        wpp = wp.reshape(Cout, Cin).contiguous().bfloat16()
+        extra = (wpp.data_ptr(), bp.data_ptr(), outp.data_ptr() + 16, Cout + 8)
+    lib.call("tdb_conv3d_bf16_win", xin.data_ptr() + 16, Cin + 8, wk.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin,
+             Cout, stats.data_ptr() if variant == "stats" else None, G, lib.CONV_ALL_ROWS if variant == "all_rows" else 0, *extra,
+             lib.stream_ptr())
+    torch.cuda.synchronize()
+    want = _conv_ref(x.double().cpu(), w.double().cpu(), b.double().cpu(), 27)
+    assert rel_l2(from_halo(out), want) < 4e-3
+    if fuse:
+        want_p = _conv_ref(x.double().cpu(), wp.double().cpu(), bp.double().cpu(), 1)
+        assert rel_l2(from_halo(outp, Cout, 8), want_p) < 4e-3
+    if variant == "stats":
+        wg = want.reshape(B, G, -1)
+        np.testing.assert_allclose(stats[..., 0].cpu().numpy(), wg.sum(-1).numpy(), rtol=1e-4, atol=1e-2)
+        np.testing.assert_allclose(stats[..., 1].cpu().numpy(), (wg**2).sum(-1).numpy(), rtol=1e-4)
+    if variant == "all_rows":
+        # input gradients: the input has a ZERO halo, and every row (halo rows too) is the zero-padded convolution
+        xz = torch.zeros((B, X + 2, Y + 2, Z + 2, Cin + 8), device="cuda", dtype=torch.bfloat16)
+        xz[:, 1:-1, 1:-1, 1:-1, 8:] = x.permute(0, 2, 3, 4, 1).bfloat16()
+        lib.call("tdb_conv3d_bf16_win", xz.data_ptr() + 16, Cin + 8, wk.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z,
+                 Cin, Cout, None, G, lib.CONV_ALL_ROWS, None, None, None, 0, lib.stream_ptr())
+        torch.cuda.synchronize()
+        full = F.conv3d(F.pad(F.pad(x.double().cpu(), (1,) * 6), (1,) * 6), w.double().cpu(), b.double().cpu())
+        assert rel_l2(out.permute(0, 4, 1, 2, 3).float(), full) < 4e-3
