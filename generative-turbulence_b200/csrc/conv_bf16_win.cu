@@ -35,6 +35,9 @@ struct WinParams {
     int ld_out;
     int G;
     int num_super;   // pairs of 128-row tiles
+    int n_tiles;     // N tiles of COUT output channels (streamed-weight variant: Cout_total / COUT)
+    int num_items;   // num_super * n_tiles work items, N tile outermost
+    int cout_total;
     int all_rows;
     int proj;
     int ld_outp;
@@ -51,7 +54,9 @@ __device__ __forceinline__ bool interior_row(int64_t p, const WinParams& P, int&
            zp <= (uint32_t)(P.Zp - 2);
 }
 
-template <int COUT, int KC>
+// RES = 1: the CTA's half of ALL weights is resident (one N tile).  RES = 0: N tiles of COUT channels; the nine
+// (ky, kz) weight tiles of the current (kx, channel chunk) travel with the activation window in every stage.
+template <int COUT, int KC, int RES>
 __global__ void __launch_bounds__(THREADS, 1)
 conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const __grid_constant__ CUtensorMap map_p, const float* __restrict__ bias, bf16* __restrict__ out,
@@ -65,8 +70,9 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 6];
+    constexpr bool resident = RES != 0;
     __shared__ __align__(16) float s_biasp[COUT];
-    __shared__ __align__(16) float s_bias[COUT];
+    __shared__ __align__(16) float s_bias[resident ? COUT : 512];
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -79,17 +85,16 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const uint32_t b_full = ptx::smem_u32(&bars[2 * MAX_STAGES + 4]);     // used in the leader
     const uint32_t p_full = ptx::smem_u32(&bars[2 * MAX_STAGES + 5]);     // used in the leader (projection weights)
     const int chunks = P.chunks;
-    const int n_b = 27 * chunks;                        // resident weight tiles (tap, channel chunk) of this CTA
+    const int n_b = resident ? 27 * chunks : 0;         // resident weight tiles (tap, channel chunk) of this CTA
     const uint32_t b_region = (uint32_t)n_b * bh_bytes;
     const uint32_t p_base_addr = smem_base + b_region;
     const uint32_t p_region = P.proj ? (uint32_t)chunks * bh_bytes : 0u;
     const uint32_t stage_base = (smem_base + b_region + p_region + 1023u) & ~1023u;
-    const uint32_t stage_bytes = (uint32_t)P.win_rows * ROWB;
+    const uint32_t win_bytes = (uint32_t)P.win_rows * ROWB;
+    const uint32_t stage_bytes = win_bytes + (resident ? 0u : 9u * bh_bytes);
 
-    for (int i = threadIdx.x; i < COUT; i += THREADS) {
-        s_bias[i] = bias ? bias[i] : 0.0f;
-        s_biasp[i] = (P.proj && bias_p) ? bias_p[i] : 0.0f;
-    }
+    for (int i = threadIdx.x; i < P.cout_total; i += THREADS) s_bias[i] = bias ? bias[i] : 0.0f;
+    for (int i = threadIdx.x; i < COUT; i += THREADS) s_biasp[i] = (P.proj && bias_p) ? bias_p[i] : 0.0f;
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_b);
@@ -118,13 +123,15 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     if (warp == 0) {
         // ===== TMA producer (both CTAs): resident half-weights once, then one row window per (kx, channel chunk);
         // every load signals the LEADER's barrier =====
-        if (ptx::elect_one()) {
+        if (resident && ptx::elect_one()) {
             const uint32_t b_full_l = ptx::leader_addr(b_full);
             for (int i = 0; i < n_b; ++i)
                 ptx::tma_load_3d_2sm(smem_base + (uint32_t)i * bh_bytes, &map_b, b_full_l, (i % chunks) * KC, (int)rank * NH, i / chunks);
             if (rank == 0) ptx::mbar_arrive_expect_tx(b_full, 2u * b_region);
             else ptx::mbar_arrive_remote(b_full, 0);
-            if (P.proj) {
+        }
+        if (P.proj && ptx::elect_one()) {
+            {
                 const uint32_t p_full_l = ptx::leader_addr(p_full);
                 for (int ch = 0; ch < chunks; ++ch)
                     ptx::tma_load_3d_2sm(p_base_addr + (uint32_t)ch * bh_bytes, &map_p, p_full_l, ch * KC, (int)rank * NH, 0);
@@ -135,8 +142,9 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         __syncwarp();
         const int yz = P.Yp * P.Zp;
         uint32_t s = 0, ph = 1;
-        for (int w = cluster_id; w < P.num_super; w += n_clusters) {
-            const int tile = 2 * w + (int)rank;
+        for (int w = cluster_id; w < P.num_items; w += n_clusters) {
+            const int nt = w / P.num_super, st = w - nt * P.num_super;
+            const int tile = 2 * st + (int)rank;
             const int q0 = tile * BM - P.Zp - 1;  // first row of the kx = 1 window (rows outside the grid are zero-filled)
             for (int kx = 0; kx < 3; ++kx) {
                 const int row = q0 + (kx - 1) * yz;
@@ -145,6 +153,12 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     if (ptx::elect_one()) {
                         const uint32_t full_l = ptx::leader_addr(full_bar + 8 * s);
                         ptx::tma_load_2d_2sm(stage_base + s * stage_bytes, &map_a, full_l, ch * KC, row);
+                        if (!resident) {
+#pragma unroll
+                            for (int t = 0; t < 9; ++t)
+                                ptx::tma_load_3d_2sm(stage_base + s * stage_bytes + win_bytes + (uint32_t)t * bh_bytes, &map_b, full_l,
+                                                     ch * KC, nt * COUT + (int)rank * NH, kx * 9 + t);
+                        }
                         if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar + 8 * s, 2u * stage_bytes);
                         else ptx::mbar_arrive_remote(full_bar + 8 * s, 0);
                     }
@@ -164,12 +178,12 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             const uint32_t st_step = stage_bytes >> 4;
             constexpr uint32_t b_step = bh_bytes >> 4, row16 = ROWB >> 4;
             const uint32_t zrow16 = (uint32_t)P.Zp * row16;  // one y step = Zp rows
-            ptx::mbar_wait(b_full, 0);
+            if (resident) ptx::mbar_wait(b_full, 0);
             if (P.proj) ptx::mbar_wait(p_full, 0);
             ptx::tc_fence_after();
             uint32_t s = 0, ph = 0;
             int local = 0;
-            for (int w = cluster_id; w < P.num_super; w += n_clusters, ++local) {
+            for (int w = cluster_id; w < P.num_items; w += n_clusters, ++local) {
                 const int as = local & 1;
                 const uint32_t aph = (uint32_t)(local >> 1) & 1u;
                 ptx::mbar_wait(acc_empty + 8 * as, aph ^ 1u);  // both CTAs' epilogues have drained this stage
@@ -181,13 +195,15 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                         ptx::tc_fence_after();
                         if (ptx::elect_one()) {
                             const uint64_t a_st = a_base + (uint64_t)(s * st_step);
-                            const uint64_t b_st = b_base + (uint64_t)((uint32_t)(kx * 9 * chunks + ch) * b_step);
+                            const uint64_t b_st = resident ? b_base + (uint64_t)((uint32_t)(kx * 9 * chunks + ch) * b_step)
+                                                           : a_st + (uint64_t)(win_bytes >> 4);
+                            const uint32_t b_tap = resident ? (uint32_t)chunks * b_step : b_step;  // tile stride between taps
                             const uint32_t first = (kx | ch) == 0 ? 0u : 1u;
 #pragma unroll
                             for (int t = 0; t < 9; ++t) {
                                 // tap (ky, kz) = (t / 3, t % 3): the window viewed from row ky*Zp + kz
                                 const uint64_t a_t = a_st + (uint64_t)((uint32_t)(t / 3) * zrow16 + (uint32_t)(t % 3) * row16);
-                                const uint64_t b_t = b_st + (uint64_t)((uint32_t)(t * chunks) * b_step);
+                                const uint64_t b_t = b_st + (uint64_t)((uint32_t)t * b_tap);
 #pragma unroll
                                 for (int k = 0; k < KC / 16; ++k)
                                     ptx::umma_f16_2sm(d_addr, a_t + (uint64_t)(2 * k), b_t + (uint64_t)(2 * k), idesc,
@@ -221,10 +237,10 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         for (int a = 0; a < CH_PER_WARP; ++a)
 #pragma unroll
             for (int j = 0; j < 8; ++j) st_s[a][j] = st_q[a][j] = 0.0f;
-        int st_b = -1;
+        int st_b = -1, st_nt = 0;
 
         auto flush_stats = [&]() {
-            const int cpg = COUT / P.G;  // even (checked on the host)
+            const int cpg = P.cout_total / P.G;  // even (checked on the host)
 #pragma unroll
             for (int a = 0; a < CH_PER_WARP; ++a) {
                 const int cidx = 2 * a + half;
@@ -234,7 +250,7 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     gs += (double)st_s[a][j];
                     gq += (double)st_q[a][j];
                     st_s[a][j] = st_q[a][j] = 0.0f;
-                    const int col_end = cidx * 16 + 2 * j + 2;
+                    const int col_end = st_nt * COUT + cidx * 16 + 2 * j + 2;
                     if (col_end % cpg == 0 || j == 7) {
                         const double ws = warp_sum(gs), wq = warp_sum(gq);
                         if (lane == 0) {
@@ -249,8 +265,10 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         };
 
         int local = 0;
-        for (int w = cluster_id; w < P.num_super; w += n_clusters, ++local) {
-            const int tile = 2 * w + (int)rank;
+        for (int w = cluster_id; w < P.num_items; w += n_clusters, ++local) {
+            const int nt = w / P.num_super, st = w - nt * P.num_super;
+            const int tile = 2 * st + (int)rank;
+            const int n0 = nt * COUT;
             const int as = local & 1;
             const uint32_t aph = (uint32_t)(local >> 1) & 1u;
             const int64_t p = (int64_t)tile * BM + 32 * lg + lane;
@@ -262,16 +280,17 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 const unsigned vmask = __ballot_sync(0xffffffffu, valid);
                 if (vmask) {
                     const int b_warp = __shfl_sync(0xffffffffu, b, __ffs(vmask) - 1);
-                    if (b_warp != st_b) {
+                    if (b_warp != st_b || nt != st_nt) {
                         if (st_b >= 0) flush_stats();
                         st_b = b_warp;
+                        st_nt = nt;
                     }
                 }
             }
             ptx::mbar_wait(acc_full + 8 * as, aph);
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_d + (uint32_t)(as * P.tmem_half) + ((uint32_t)(lg * 32) << 16);
-            bf16* orow = out + p * P.ld_out;
+            bf16* orow = out + p * P.ld_out + n0;
 #pragma unroll
             for (int a = 0; a < CH_PER_WARP; ++a) {
                 const int c = (2 * a + half) * 16;
@@ -297,7 +316,7 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 if (valid) {
                     float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]) + s_bias[c + j];
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]) + s_bias[n0 + c + j];
                     uint4 lo, hi;
                     __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&lo);
                     __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&hi);
@@ -339,13 +358,13 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 
 int g_num_sms_win = 0;
 
-template <int COUT, int KC>
+template <int COUT, int KC, int RES>
 int launch_win(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap& map_p, const float* bias, bf16* out,
                double* gn_stats, const float* bias_p, bf16* out_p, const WinParams& P, size_t smem, cudaStream_t stream) {
-    auto kern = conv3d_bf16_win_kernel<COUT, KC>;
+    auto kern = conv3d_bf16_win_kernel<COUT, KC, RES>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_conv3d_bf16_win: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-    int grid = 2 * P.num_super;
+    int grid = 2 * P.num_items;
     const int cap = g_num_sms_win & ~1;
     if (grid > cap) grid = cap;
     cudaLaunchConfig_t cfg{};
@@ -372,8 +391,8 @@ extern "C" int tdb_conv3d_bf16_win(const void* in, int ld_in, const void* w, con
                                    int Y, int Z, int Cin, int Cout, double* gn_stats, int G, unsigned flags, const void* w_proj,
                                    const float* bias_proj, void* out_proj, int ld_outp, void* stream) {
     TDB_REQUIRE(in && w && out, TDB_E_BADARG, "tdb_conv3d_bf16_win: null pointer");
-    TDB_REQUIRE(Cin % 32 == 0 && (Cout == 32 || Cout == 64 || Cout == 128) && ld_in % 8 == 0 && ld_out % 8 == 0, TDB_E_UNSUPPORTED,
-                "tdb_conv3d_bf16_win: need Cin %% 32 == 0 and Cout in {32,64,128} (Cin=%d Cout=%d)", Cin, Cout);
+    TDB_REQUIRE(Cin % 32 == 0 && (Cout == 32 || Cout == 64 || (Cout % 128 == 0 && Cout <= 512)) && ld_in % 8 == 0 && ld_out % 8 == 0,
+                TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_win: need Cin %% 32 == 0 and Cout in {32,64,128k<=512} (Cin=%d Cout=%d)", Cin, Cout);
     TDB_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)w & 15) == 0, TDB_E_UNSUPPORTED,
                 "tdb_conv3d_bf16_win: pointers must be 16-byte aligned");
     TDB_REQUIRE(!gn_stats || (G >= 1 && Cout % G == 0 && (Cout / G) % 2 == 0), TDB_E_UNSUPPORTED,
@@ -402,20 +421,31 @@ extern "C" int tdb_conv3d_bf16_win(const void* in, int ld_in, const void* w, con
     TDB_REQUIRE(!P.proj || (Cout <= 64 && out_proj && ld_outp % 8 == 0 && ((uintptr_t)w_proj & 15) == 0 && ((uintptr_t)out_proj & 15) == 0 &&
                             !(flags & TDB_CONV_ALL_ROWS)),
                 TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_win: the fused projection needs Cout <= 64 and aligned buffers");
-    const int bh_bytes = (Cout / 2) * KC * 2;
-    const int resident = (27 + (P.proj ? 1 : 0)) * P.chunks * bh_bytes;
-    const int stage_bytes = P.win_rows * KC * 2;
+    const int tile_n = Cout > 128 ? 128 : Cout;  // output channels per N tile
+    P.n_tiles = Cout / tile_n;
+    P.cout_total = Cout;
+    const int bh_bytes = (tile_n / 2) * KC * 2;
+    const int win_bytes = P.win_rows * KC * 2;
     const int budget = 221 * 1024;
-    int stages = (budget - resident - 1024) / stage_bytes;
+    const int resident_bytes = (27 + (P.proj ? 1 : 0)) * P.chunks * bh_bytes;
+    // all weights resident when they leave room for two windows; otherwise (Cin % 64 == 0 only) the nine weight
+    // tiles of a (kx, channel chunk) stream with each window and Cout is walked in N tiles of 128
+    const bool res = P.n_tiles == 1 && resident_bytes + 2048 + 2 * win_bytes <= budget;
+    TDB_REQUIRE(res || (KC == 64 && !P.proj && tile_n == 128), TDB_E_UNSUPPORTED,
+                "tdb_conv3d_bf16_win: streamed weights need Cin %% 64 == 0, Cout %% 128 == 0 and no fused projection (Cin=%d Cout=%d)", Cin, Cout);
+    const int fixed_bytes = res ? resident_bytes : 0;
+    const int stage_bytes = win_bytes + (res ? 0 : 9 * bh_bytes);
+    int stages = (budget - fixed_bytes - 2048) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
-    TDB_REQUIRE(stages >= 2, TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_win: weights (%d bytes per CTA) do not leave room for two windows", resident);
+    TDB_REQUIRE(stages >= 2, TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_win: two stages of %d bytes do not fit", stage_bytes);
     P.stages = stages;
     int half = 32;
-    while (half < Cout * (P.proj ? 2 : 1)) half *= 2;
+    while (half < tile_n * (P.proj ? 2 : 1)) half *= 2;
     P.tmem_half = half;
     P.ld_out = ld_out;
     P.G = gn_stats ? G : 0;
     P.num_super = (int)ceil_div(g.rows, 2 * BM);
+    P.num_items = P.num_super * P.n_tiles;
     P.all_rows = (flags & TDB_CONV_ALL_ROWS) ? 1 : 0;
     TDB_REQUIRE(!(P.all_rows && gn_stats), TDB_E_BADARG, "tdb_conv3d_bf16_win: fused moments are not available with ALL_ROWS");
 
@@ -427,28 +457,29 @@ extern "C" int tdb_conv3d_bf16_win(const void* in, int ld_in, const void* w, con
         // weights [Cout][27][Cin]; one box = the Cout/2 rows of a CTA for one (tap, channel chunk)
         const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 27};
         const uint64_t strides[2] = {27ull * Cin, (uint64_t)Cin};
-        const uint32_t box[3] = {(uint32_t)KC, (uint32_t)(Cout / 2), 1};
+        const uint32_t box[3] = {(uint32_t)KC, (uint32_t)(tile_n / 2), 1};
         TDB_REQUIRE(make_map_bf16(&map_b, w, 3, dims, strides, box), TDB_E_BADARG, "tdb_conv3d_bf16_win: tensor map (weights) rejected");
     }
     {
         const void* wp = P.proj ? w_proj : w;
         const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 1};
         const uint64_t strides[2] = {(uint64_t)(P.proj ? Cin : 27 * Cin), (uint64_t)Cin * Cout};
-        const uint32_t box[3] = {(uint32_t)KC, (uint32_t)(Cout / 2), 1};
+        const uint32_t box[3] = {(uint32_t)KC, (uint32_t)(tile_n / 2), 1};
         TDB_REQUIRE(make_map_bf16(&map_p, wp, 3, dims, strides, box), TDB_E_BADARG, "tdb_conv3d_bf16_win: tensor map (projection) rejected");
     }
-    const size_t smem = (size_t)resident + 1024 + (size_t)stages * stage_bytes + 1024;
+    const size_t smem = (size_t)fixed_bytes + 1024 + (size_t)stages * stage_bytes + 1024;
     cudaStream_t s = (cudaStream_t)stream;
     bf16* o = (bf16*)out;
     bf16* op = (bf16*)out_proj;
-#define TDB_WIN_CASE(CO, K) \
-    if (Cout == CO && KC == K) return launch_win<CO, K>(map_a, map_b, map_p, bias, o, gn_stats, bias_proj, op, P, smem, s)
-    TDB_WIN_CASE(32, 64);
-    TDB_WIN_CASE(64, 64);
-    TDB_WIN_CASE(128, 64);
-    TDB_WIN_CASE(32, 32);
-    TDB_WIN_CASE(64, 32);
-    TDB_WIN_CASE(128, 32);
+#define TDB_WIN_CASE(CO, K, R) \
+    if (tile_n == CO && KC == K && (int)res == R) return launch_win<CO, K, R>(map_a, map_b, map_p, bias, o, gn_stats, bias_proj, op, P, smem, s)
+    TDB_WIN_CASE(32, 64, 1);
+    TDB_WIN_CASE(64, 64, 1);
+    TDB_WIN_CASE(128, 64, 1);
+    TDB_WIN_CASE(32, 32, 1);
+    TDB_WIN_CASE(64, 32, 1);
+    TDB_WIN_CASE(128, 32, 1);
+    TDB_WIN_CASE(128, 64, 0);
 #undef TDB_WIN_CASE
     tdb::set_error("tdb_conv3d_bf16_win: no kernel for Cout=%d KC=%d", Cout, KC);
     return TDB_E_UNSUPPORTED;

@@ -298,21 +298,44 @@ trilinear_kernel(const T* __restrict__ in, int ld_in, Grid3 gi, T* __restrict__ 
             wxy[k] = ((k & 2) ? lx.l1 : lx.l0) * ((k & 1) ? ly.l1 : ly.l0);
         }
         T* dst = out + ((int64_t)b * go.vox_p + (int64_t)line * go.Zp) * ld_out + c0;
-#pragma unroll 2
-        for (int zp = 0; zp < go.Zp; ++zp) {
-            const Lerp lz = axis_lerp(clampi(zp - 1, 0, go.Z - 1), gi.Z, sz);
-            float acc[N];
+        // the x/y-interpolated input planes P(iz) are kept in registers while the walk moves along z: an output is
+        // l0*P(i0) + l1*P(i1), and when upsampling each P is reused by about two outputs (i0/i1 are warp-uniform)
+        auto plane = [&](int iz, float (&pl)[N]) {
 #pragma unroll
-            for (int i = 0; i < N; ++i) acc[i] = 0.0f;
+            for (int i = 0; i < N; ++i) pl[i] = 0.0f;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                float v0[N], v1[N];
-                Vec<T>::load(base[k] + (int64_t)lz.i0 * ld_in, v0);
-                Vec<T>::load(base[k] + (int64_t)lz.i1 * ld_in, v1);
-                const float w0 = wxy[k] * lz.l0, w1 = wxy[k] * lz.l1;
+                float v[N];
+                Vec<T>::load(base[k] + (int64_t)iz * ld_in, v);
 #pragma unroll
-                for (int i = 0; i < N; ++i) acc[i] = fmaf(w0, v0[i], fmaf(w1, v1[i], acc[i]));
+                for (int i = 0; i < N; ++i) pl[i] = fmaf(wxy[k], v[i], pl[i]);
             }
+        };
+        int c_i0 = -1, c_i1 = -1;
+        float p0[N], p1[N];
+        for (int zp = 0; zp < go.Zp; ++zp) {
+            const Lerp lz = axis_lerp(clampi(zp - 1, 0, go.Z - 1), gi.Z, sz);
+            if (lz.i0 != c_i0) {
+                if (lz.i0 == c_i1) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) p0[i] = p1[i];
+                } else {
+                    plane(lz.i0, p0);
+                }
+                c_i0 = lz.i0;
+            }
+            if (lz.i1 != c_i1) {
+                if (lz.i1 == c_i0) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) p1[i] = p0[i];
+                } else {
+                    plane(lz.i1, p1);
+                }
+                c_i1 = lz.i1;
+            }
+            float acc[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) acc[i] = fmaf(lz.l0, p0[i], lz.l1 * p1[i]);
             Vec<T>::store(dst + (int64_t)zp * ld_out, acc);
         }
     }

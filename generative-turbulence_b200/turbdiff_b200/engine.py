@@ -86,6 +86,7 @@ class DenoiserEngine:
         self.train_graph = os.environ.get("TURBDIFF_B200_TRAIN_GRAPH", "1") != "0"
         self._train_graphs = {}
         self._train_replay = None
+        self.replayed_launches = 0  # C-ABI launches re-issued by training-graph replays (tdb_launch_count() only sees eager ones)
         self._plans = {}
         self._wcache = None
         self._wversion = None
@@ -163,7 +164,9 @@ class DenoiserEngine:
             pair = self.fold2 and cin % 64 == 0 and cout in (32, 64) and 9 * cin * 3 * cout * 2 > 112 * 1024
             return "fold2" if pair else "fold"
         if self.fold2 and self.fold_wide and cout % 128 == 0 and cout <= 512 and cin % 64 == 0 and level <= self.model.u_net_levels - 1:
-            return "fold2"
+            # wide layers: N tiles of 128 channels with streamed weights; the row-window kernel double-buffers its
+            # accumulators and keeps all 128 rows of a tile (3-20 % faster than the kz-folded pair kernel here)
+            return "win" if (self.win and zp <= 63) else "fold2"
         return None
 
     def pack_conv(self, wt, level):
@@ -527,6 +530,7 @@ class DenoiserEngine:
         if c_local is not None:
             tg["c"].copy_(c_local)
         tg["fwd"].replay()
+        self.replayed_launches += tg["n_fwd"]
         self._last_train_key = key[:3]
         self._train_replay = tg
         return tg["eps"]
@@ -538,6 +542,7 @@ class DenoiserEngine:
             return self.backward(g_eps)
         tg["g_eps"].copy_(g_eps)
         tg["bwd"].replay()
+        self.replayed_launches += tg["n_bwd"]
         return tg["grads"], tg["g_c_local"]
 
     def _capture_train(self, x, t, c_local, sig):
@@ -556,12 +561,15 @@ class DenoiserEngine:
         torch.cuda.current_stream().wait_stream(side)
         pool = torch.cuda.graph_pool_handle()
         g_f, g_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
         with torch.cuda.graph(g_f, pool=pool):
             self._wcache = None  # the kernel-layout weights are re-derived from the parameters inside the graph
             eps = self.forward(xs, ts, cs, train=True)
+        n1 = _lib.launch_count()
         with torch.cuda.graph(g_b, pool=pool):
             grads, g_c = BackwardProgram(self).run(gs)
-        return {"sig": sig, "x": xs, "t": ts, "c": cs, "g_eps": gs, "eps": eps, "fwd": g_f, "bwd": g_b, "grads": grads, "g_c_local": g_c}
+        n2 = _lib.launch_count()
+        return {"sig": sig, "n_fwd": n1 - n0, "n_bwd": n2 - n1, "x": xs, "t": ts, "c": cs, "g_eps": gs, "eps": eps, "fwd": g_f, "bwd": g_b, "grads": grads, "g_c_local": g_c}
 
     @staticmethod
     def to_ncdhw(v: View) -> torch.Tensor:

@@ -122,10 +122,11 @@ TDB_API int tdb_conv3d_bf16_fold2(const void* in, int ld_in, int pad_rows, const
 
 /* Row-window CTA-pair convolution (3x3x3 only): for one kx the nine (ky, kz) taps are nine row-shifted views of ONE
  * shared-memory window of 128 + 2*(Z+2) + 2 rows, so activations are staged 3x per channel chunk instead of 9x/27x and
- * all 128 rows of a tile are outputs.  w = the per-tap layout of tdb_conv3d_bf16 ([Cout][27*Cin] bf16), resident in
- * shared memory split over the pair: needs 27*Cin*Cout bytes <= ~116 KB, Cin % 32 == 0, Cout in {32, 64, 128},
- * Z + 2 <= 63.  No padding rows are required (TMA zero-fills outside the grid).  gn_stats / flags / w_proj, bias_proj,
- * out_proj, ld_outp as in tdb_conv3d_bf16_fold2. */
+ * all 128 rows of a tile are outputs.  w = the per-tap layout of tdb_conv3d_bf16 ([Cout][27*Cin] bf16).  Cin % 32 == 0,
+ * Cout in {32, 64, 128}: the weights stay resident in shared memory, split over the pair, when 27*Cin*Cout bytes leave
+ * room for two windows (<= ~116 KB); otherwise Cin % 64 == 0, Cout % 128 == 0 (<= 512): N tiles of 128 channels whose
+ * nine weight tiles stream with every window.  Z + 2 <= 63.  No padding rows are required (TMA zero-fills outside the
+ * grid).  gn_stats / flags / w_proj, bias_proj, out_proj, ld_outp as in tdb_conv3d_bf16_fold2. */
 TDB_API int tdb_conv3d_bf16_win(const void* in, int ld_in, const void* w, const float* bias, void* out, int ld_out, int B,
                         int X, int Y, int Z, int Cin, int Cout, double* gn_stats, int G, unsigned flags,
                         const void* w_proj, const float* bias_proj, void* out_proj, int ld_outp, void* stream);

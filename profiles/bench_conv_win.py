@@ -6,11 +6,14 @@ sys.path.insert(0, os.path.join(ROOT, "generative-turbulence_b200"))
 from turbdiff_b200 import _lib
 _lib.load()
 B = int(os.environ.get("B", 4))
-X, Y, Z = 194, 50, 50
-pad = (Y + 2) * (Z + 2) + 2 * (Z + 2) + 256
-rows = B * (X + 2) * (Y + 2) * (Z + 2)
 res = []
-for (Cin, Cout, old) in [(64, 64, "fold2"), (128, 32, "fold2"), (32, 32, "fold"), (32, 128, "v1"), (32, 64, "fold")]:
+LAYERS = [(194, 50, 50, 64, 64, "fold2"), (194, 50, 50, 128, 32, "fold2"), (194, 50, 50, 32, 32, "fold"), (194, 50, 50, 32, 128, "v1"),
+          (97, 25, 25, 64, 128, "fold2"), (97, 25, 25, 128, 128, "fold2"), (97, 25, 25, 64, 64, "fold2"),
+          (48, 12, 12, 128, 256, "fold2"), (48, 12, 12, 256, 256, "fold2"), (48, 12, 12, 512, 128, "fold2"),
+          (24, 6, 6, 256, 512, "fold2"), (24, 6, 6, 512, 512, "fold2"), (24, 6, 6, 1024, 256, "fold2")]
+for (X, Y, Z, Cin, Cout, old) in LAYERS:
+    pad = (Y + 2) * (Z + 2) + 2 * (Z + 2) + 256
+    rows = B * (X + 2) * (Y + 2) * (Z + 2)
     buf = torch.zeros((rows + 2 * pad, Cin), device="cuda", dtype=torch.bfloat16)
     buf[pad:pad + rows] = (torch.randn(rows, Cin, device="cuda") * 0.5).bfloat16()
     xin = buf[pad:pad + rows]
@@ -33,7 +36,7 @@ for (Cin, Cout, old) in [(64, 64, "fold2"), (128, 32, "fold2"), (32, 32, "fold")
     def run_win():
         _lib.call("tdb_conv3d_bf16_win", xin.data_ptr(), Cin, wk.data_ptr(), bias.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
                   None if old == "v1" else stats.data_ptr(), 8, 1 if old == "v1" else 0, None, None, None, 0, s())
-    row = {"layer": f"{Cin}->{Cout}", "gflop": 2 * 27 * Cin * Cout * B * X * Y * Z / 1e9, "old_kernel": old}
+    row = {"layer": f"{Cin}->{Cout} @{X}", "gflop": 2 * 27 * Cin * Cout * B * X * Y * Z / 1e9, "old_kernel": old}
     for name, fn in [("old", run_old), ("win", run_win)]:
         try:
             fn(); torch.cuda.synchronize()
