@@ -71,7 +71,7 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 6];
     constexpr bool resident = RES != 0;
-    __shared__ __align__(16) float s_biasp[COUT];
+    __shared__ __align__(16) float s_biasp[resident ? COUT : 512];
     __shared__ __align__(16) float s_bias[resident ? COUT : 512];
     __shared__ uint32_t tmem_base_slot;
 
@@ -88,13 +88,14 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const int n_b = resident ? 27 * chunks : 0;         // resident weight tiles (tap, channel chunk) of this CTA
     const uint32_t b_region = (uint32_t)n_b * bh_bytes;
     const uint32_t p_base_addr = smem_base + b_region;
-    const uint32_t p_region = P.proj ? (uint32_t)chunks * bh_bytes : 0u;
+    const uint32_t p_region = (resident && P.proj) ? (uint32_t)chunks * bh_bytes : 0u;
     const uint32_t stage_base = (smem_base + b_region + p_region + 1023u) & ~1023u;
     const uint32_t win_bytes = (uint32_t)P.win_rows * ROWB;
-    const uint32_t stage_bytes = win_bytes + (resident ? 0u : 9u * bh_bytes);
+    // streamed weights: nine (ky, kz) tiles per stage, plus a slot for the 1x1 projection tile (filled when kx == 1)
+    const uint32_t stage_bytes = win_bytes + (resident ? 0u : (9u + (P.proj ? 1u : 0u)) * bh_bytes);
 
     for (int i = threadIdx.x; i < P.cout_total; i += THREADS) s_bias[i] = bias ? bias[i] : 0.0f;
-    for (int i = threadIdx.x; i < COUT; i += THREADS) s_biasp[i] = (P.proj && bias_p) ? bias_p[i] : 0.0f;
+    for (int i = threadIdx.x; i < P.cout_total; i += THREADS) s_biasp[i] = (P.proj && bias_p) ? bias_p[i] : 0.0f;
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_b);
@@ -130,7 +131,7 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             if (rank == 0) ptx::mbar_arrive_expect_tx(b_full, 2u * b_region);
             else ptx::mbar_arrive_remote(b_full, 0);
         }
-        if (P.proj && ptx::elect_one()) {
+        if (resident && P.proj && ptx::elect_one()) {
             {
                 const uint32_t p_full_l = ptx::leader_addr(p_full);
                 for (int ch = 0; ch < chunks; ++ch)
@@ -158,8 +159,12 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                             for (int t = 0; t < 9; ++t)
                                 ptx::tma_load_3d_2sm(stage_base + s * stage_bytes + win_bytes + (uint32_t)t * bh_bytes, &map_b, full_l,
                                                      ch * KC, nt * COUT + (int)rank * NH, kx * 9 + t);
+                            if (P.proj && kx == 1)
+                                ptx::tma_load_3d_2sm(stage_base + s * stage_bytes + win_bytes + 9u * bh_bytes, &map_p, full_l, ch * KC,
+                                                     nt * COUT + (int)rank * NH, 0);
                         }
-                        if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar + 8 * s, 2u * stage_bytes);
+                        const uint32_t tx = resident ? win_bytes : win_bytes + (9u + ((P.proj && kx == 1) ? 1u : 0u)) * bh_bytes;
+                        if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar + 8 * s, 2u * tx);
                         else ptx::mbar_arrive_remote(full_bar + 8 * s, 0);
                     }
                     __syncwarp();
@@ -179,7 +184,7 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             constexpr uint32_t b_step = bh_bytes >> 4, row16 = ROWB >> 4;
             const uint32_t zrow16 = (uint32_t)P.Zp * row16;  // one y step = Zp rows
             if (resident) ptx::mbar_wait(b_full, 0);
-            if (P.proj) ptx::mbar_wait(p_full, 0);
+            if (resident && P.proj) ptx::mbar_wait(p_full, 0);
             ptx::tc_fence_after();
             uint32_t s = 0, ph = 0;
             int local = 0;
@@ -212,10 +217,11 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                             if (P.proj && kx == 1) {
                                 // centre tap: the same rows also feed the 1x1 projection (TMEM columns behind the conv's)
                                 const uint64_t a_t = a_st + (uint64_t)(zrow16 + row16);
+                                const uint64_t p_t = resident ? p_base + (uint64_t)((uint32_t)ch * b_step) : b_st + (uint64_t)(9u * b_step);
 #pragma unroll
                                 for (int k = 0; k < KC / 16; ++k)
-                                    ptx::umma_f16_2sm(d_addr + (uint32_t)COUT, a_t + (uint64_t)(2 * k),
-                                                      p_base + (uint64_t)((uint32_t)ch * b_step + 2 * k), idesc, (uint32_t)((ch | k) != 0));
+                                    ptx::umma_f16_2sm(d_addr + (uint32_t)COUT, a_t + (uint64_t)(2 * k), p_t + (uint64_t)(2 * k), idesc,
+                                                      (uint32_t)((ch | k) != 0));
                             }
                             ptx::umma_commit_2sm_mc(empty_bar + 8 * s, (uint16_t)0x3);  // frees the slot in both CTAs
                         }
@@ -304,12 +310,12 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&hi);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        h0[j] = __floats2bfloat162_rn(__uint_as_float(r3[2 * j]) + s_biasp[c + 2 * j],
-                                                      __uint_as_float(r3[2 * j + 1]) + s_biasp[c + 2 * j + 1]);
-                        h1[j] = __floats2bfloat162_rn(__uint_as_float(r3[8 + 2 * j]) + s_biasp[c + 8 + 2 * j],
-                                                      __uint_as_float(r3[8 + 2 * j + 1]) + s_biasp[c + 8 + 2 * j + 1]);
+                        h0[j] = __floats2bfloat162_rn(__uint_as_float(r3[2 * j]) + s_biasp[n0 + c + 2 * j],
+                                                      __uint_as_float(r3[2 * j + 1]) + s_biasp[n0 + c + 2 * j + 1]);
+                        h1[j] = __floats2bfloat162_rn(__uint_as_float(r3[8 + 2 * j]) + s_biasp[n0 + c + 8 + 2 * j],
+                                                      __uint_as_float(r3[8 + 2 * j + 1]) + s_biasp[n0 + c + 8 + 2 * j + 1]);
                     }
-                    bf16* prow = out_p + p * P.ld_outp;
+                    bf16* prow = out_p + p * P.ld_outp + n0;
                     *reinterpret_cast<uint4*>(prow + c) = lo;
                     *reinterpret_cast<uint4*>(prow + c + 8) = hi;
                 }
@@ -418,9 +424,9 @@ extern "C" int tdb_conv3d_bf16_win(const void* in, int ld_in, const void* w, con
     TDB_REQUIRE(P.win_rows <= 256, TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_win: Z + 2 = %d is too wide for one TMA box", g.Zp);
     P.proj = w_proj != nullptr ? 1 : 0;
     P.ld_outp = ld_outp;
-    TDB_REQUIRE(!P.proj || (Cout <= 64 && out_proj && ld_outp % 8 == 0 && ((uintptr_t)w_proj & 15) == 0 && ((uintptr_t)out_proj & 15) == 0 &&
+    TDB_REQUIRE(!P.proj || (out_proj && ld_outp % 8 == 0 && ((uintptr_t)w_proj & 15) == 0 && ((uintptr_t)out_proj & 15) == 0 &&
                             !(flags & TDB_CONV_ALL_ROWS)),
-                TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_win: the fused projection needs Cout <= 64 and aligned buffers");
+                TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_win: the fused projection needs aligned buffers and no ALL_ROWS");
     const int tile_n = Cout > 128 ? 128 : Cout;  // output channels per N tile
     P.n_tiles = Cout / tile_n;
     P.cout_total = Cout;
@@ -431,10 +437,10 @@ extern "C" int tdb_conv3d_bf16_win(const void* in, int ld_in, const void* w, con
     // all weights resident when they leave room for two windows; otherwise (Cin % 64 == 0 only) the nine weight
     // tiles of a (kx, channel chunk) stream with each window and Cout is walked in N tiles of 128
     const bool res = P.n_tiles == 1 && resident_bytes + 2048 + 2 * win_bytes <= budget;
-    TDB_REQUIRE(res || (KC == 64 && !P.proj && tile_n == 128), TDB_E_UNSUPPORTED,
-                "tdb_conv3d_bf16_win: streamed weights need Cin %% 64 == 0, Cout %% 128 == 0 and no fused projection (Cin=%d Cout=%d)", Cin, Cout);
+    TDB_REQUIRE(res || (KC == 64 && tile_n == 128), TDB_E_UNSUPPORTED,
+                "tdb_conv3d_bf16_win: streamed weights need Cin %% 64 == 0 and Cout %% 128 == 0 (Cin=%d Cout=%d)", Cin, Cout);
     const int fixed_bytes = res ? resident_bytes : 0;
-    const int stage_bytes = win_bytes + (res ? 0 : 9 * bh_bytes);
+    const int stage_bytes = win_bytes + (res ? 0 : (9 + (P.proj ? 1 : 0)) * bh_bytes);
     int stages = (budget - fixed_bytes - 2048) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     TDB_REQUIRE(stages >= 2, TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_win: two stages of %d bytes do not fit", stage_bytes);

@@ -306,8 +306,12 @@ class DenoiserEngine:
         call("tdb_trilinear", x.ptr, x.ld, Xi, Yi, Zi, out.ptr, out.ld, Xo, Yo, Zo, p["B"], x.C, self.dt, _lib.stream_ptr())
 
     def can_fuse_proj(self, x: View, cout) -> bool:
-        """The 1x1 residual projection rides on conv1's centre-tap tiles when conv1 runs on a CTA pair (Cout <= 64)."""
-        return self.fuse_proj and cout <= 64 and self.fold_kind(27, x.C, cout, x.level) in ("fold2", "win")
+        """The 1x1 residual projection rides on conv1's centre-tap tiles when conv1 runs on a CTA pair: Cout <= 64 on the
+        kz-folded / resident row-window kernels, and any 128-channel N tiling of the streamed row-window kernel."""
+        if not self.fuse_proj:
+            return False
+        kind = self.fold_kind(27, x.C, cout, x.level)
+        return (cout <= 64 and kind in ("fold2", "win")) or (kind == "win" and cout % 128 == 0)
 
     def _norm_conv(self, p, x: View, w, conv, norm, raw: View, stats_slot, proj=None):
         """conv (+bias) followed by GroupNorm moments of its output."""

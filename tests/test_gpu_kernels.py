@@ -485,7 +485,8 @@ WIN_CASES = [
     (2, 40, 20, 50, 32, 32, False),    # widest supported z-line class (Z + 2 = 52): 240-row windows
     (3, 21, 11, 9, 128, 32, False),
     # streamed weights, N tiles of 128 channels (weights too large to stay resident)
-    (2, 25, 13, 12, 64, 128, False), (1, 20, 12, 12, 128, 256, False), (2, 12, 6, 6, 256, 512, False), (1, 48, 12, 12, 128, 128, False),
+    (2, 25, 13, 12, 64, 128, True), (1, 20, 12, 12, 128, 256, True), (2, 12, 6, 6, 256, 512, False), (1, 48, 12, 12, 128, 128, False),
+    (1, 12, 6, 6, 512, 128, True),
 ]
 
 
