@@ -351,8 +351,13 @@ def run_ours(args):
         flops = conv_flops_per_sample(spec, geo.padded) * B
         ach = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         peak = pk["bf16_tflops_sustained"]
-        roof = {"bound": "tensor", "kernel": "tcgen05 convolution family: conv3d_bf16_fold2 / _fold / _tc kernels (all conv launches of one step)", "achieved": ach, "peak": peak,
-                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_src": f"{pk['src']} bf16 sustained (kernel timed inside a long step)",
+        # ncu --set full, profiles/r01_ncu_full_win_v40.json: the top kernel (row-window conv, 64->64 @194x50x50, B=8) moves
+        # 543 MB + 459 MB of DRAM traffic per launch = its algorithmic bytes (one read of the input, one write of the output)
+        traffic = 1.0015e9 if (B == 8 and args.precision == "bf16") else None
+        roof = {"bound": "tensor", "kernel": "tcgen05 convolution family: conv3d_bf16_win / _fold2 / _fold / _tc kernels (all conv launches of one step)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_of": "conv3d_bf16_win_kernel<64,64,1> per launch (ncu dram__bytes_read+write, round-1 capture)" if traffic else None,
+                "peak_src": f"{pk['src']} bf16 sustained (kernel timed inside a long step)",
                 "conv_ms_per_step": conv_ms, "kernel_ms_per_step": prof}
         # the bandwidth-bound update kernel against the HBM roofline: 6 tensors x 4 B per element
         st_ms = prof.get("tdb_ddpm_step", 0.0)
