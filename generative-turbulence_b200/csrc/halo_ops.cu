@@ -30,13 +30,13 @@ __global__ void __launch_bounds__(kThreads)
 encode_input_kernel(const float* __restrict__ x, const float* __restrict__ c_local,
                     const float* __restrict__ wx, const float* __restrict__ bx,
                     const float* __restrict__ wc, const float* __restrict__ bc, T* __restrict__ out,
-                    int ld_out, Grid3 g, int F, int Fc, int dim, int parts, RowSplit split, int chunks) {
+                    int ld_out, Grid3 g, int F, int Fc, int dim, int parts, RowSplit split, int chunks, int c_begin) {
     constexpr int N = Vec<T>::N;
     const int b = blockIdx.y;
     const int vox_step = kThreads / chunks;
     const int ch = threadIdx.x % chunks, lane_vox = threadIdx.x / chunks;
     if (lane_vox >= vox_step) return;
-    const int c0 = ch * N;
+    const int c0 = c_begin + ch * N;  // `chunks` covers only the requested half when parts selects one
     const bool c_half = c0 >= dim;
     if (c_half ? !(parts & 2) : !(parts & 1)) return;
     const int nf = c_half ? Fc : F;
@@ -76,21 +76,21 @@ encode_input_kernel(const float* __restrict__ x, const float* __restrict__ c_loc
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 decode_output_kernel(const T* __restrict__ act, int ld, const float* __restrict__ w,
-                     const float* __restrict__ bias, float* __restrict__ out, Grid3 g, int dim, int F) {
+                     const float* __restrict__ bias, float* __restrict__ out, Grid3 g, int dim, int F, FastDiv by_vox, FastDiv by_z,
+                     FastDiv by_y) {
     constexpr int N = Vec<T>::N;
     extern __shared__ float sw[];  // F*dim weights + F biases
     for (int i = threadIdx.x; i < F * dim; i += blockDim.x) sw[i] = w[i];
     for (int i = threadIdx.x; i < F; i += blockDim.x) sw[F * dim + i] = bias[i];
     __syncthreads();
     const int64_t nvox = (int64_t)g.X * g.Y * g.Z;
-    const int64_t total = (int64_t)g.B * nvox;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int b = (int)(idx / nvox);
-        int64_t v = idx % nvox;
-        const int z = (int)(v % g.Z);
-        const int y = (int)((v / g.Z) % g.Y);
-        const int x = (int)(v / ((int64_t)g.Z * g.Y));
+    const uint32_t total = (uint32_t)(g.B * nvox);
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        uint32_t bb, v, q, zz, xx, yy;
+        by_vox.divmod(idx, bb, v);
+        by_z.divmod(v, q, zz);
+        by_y.divmod(q, xx, yy);
+        const int b = (int)bb, x = (int)xx, y = (int)yy, z = (int)zz;
         const T* a = act + g.row(b, x, y, z) * ld;
         float acc[8];
 #pragma unroll
@@ -379,7 +379,10 @@ int tdb_encode_input(const float* x, const float* c_local, const float* wx, cons
                 "tdb_encode_input: dim/ld_out must be multiples of %d and out 16B aligned", n);
     Grid3 g(B, X, Y, Z);
     const int ctot = dim + (Fc > 0 ? dim : 0);
-    const int chunks = ctot / n;
+    // parts: bit 0 = the x half, bit 1 = the c_local half; a single half launches only its own channel chunks
+    const bool both = Fc > 0 && (parts & 3) == 3;
+    const int c_begin = (Fc > 0 && (parts & 3) == 2) ? dim : 0;
+    const int chunks = (both ? ctot : dim) / n;
     TDB_REQUIRE(g.vox_p < (1ll << 31) && chunks <= kThreads, TDB_E_UNSUPPORTED, "tdb_encode_input: grid too large for 32-bit indexing");
     dim3 grid((unsigned)blocks_per_sample(g.vox_p * chunks, B), (unsigned)B);
     const RowSplit split = make_split(g);
@@ -387,14 +390,14 @@ int tdb_encode_input(const float* x, const float* c_local, const float* wx, cons
     const bool small = F <= 4 && Fc <= 4;  // u+p and the 4-d cell-type embedding: keep the weights in 32 registers
     if (dtype == TDB_BF16) {
         if (small)
-            encode_input_kernel<bf16, 4><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (bf16*)out, ld_out, g, F, Fc, dim, parts, split, chunks);
+            encode_input_kernel<bf16, 4><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (bf16*)out, ld_out, g, F, Fc, dim, parts, split, chunks, c_begin);
         else
-            encode_input_kernel<bf16, 8><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (bf16*)out, ld_out, g, F, Fc, dim, parts, split, chunks);
+            encode_input_kernel<bf16, 8><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (bf16*)out, ld_out, g, F, Fc, dim, parts, split, chunks, c_begin);
     } else {
         if (small)
-            encode_input_kernel<float, 4><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (float*)out, ld_out, g, F, Fc, dim, parts, split, chunks);
+            encode_input_kernel<float, 4><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (float*)out, ld_out, g, F, Fc, dim, parts, split, chunks, c_begin);
         else
-            encode_input_kernel<float, 8><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (float*)out, ld_out, g, F, Fc, dim, parts, split, chunks);
+            encode_input_kernel<float, 8><<<grid, kThreads, 0, s>>>(x, c_local, wx, bx, wc, bc, (float*)out, ld_out, g, F, Fc, dim, parts, split, chunks, c_begin);
     }
     TDB_CHECK_LAUNCH("tdb_encode_input");
     return 0;
@@ -406,14 +409,16 @@ int tdb_decode_output(const void* act, int ld, const float* w, const float* b, f
     const int n = dtype == TDB_BF16 ? 8 : 4;
     TDB_REQUIRE(F >= 1 && F <= 8 && dim % n == 0 && ld % n == 0 && aligned16(act), TDB_E_UNSUPPORTED,
                 "tdb_decode_output: F <= 8, dim/ld multiples of %d", n);
+    TDB_REQUIRE((int64_t)B * X * Y * Z < (1ll << 31), TDB_E_UNSUPPORTED, "tdb_decode_output: grid too large for 32-bit indexing");
     Grid3 g(B, X, Y, Z);
+    const FastDiv by_vox((uint32_t)(X * Y * Z)), by_z((uint32_t)Z), by_y((uint32_t)Y);
     const int blocks = grid_for((int64_t)B * X * Y * Z);
     const size_t smem = (size_t)(F * dim + F) * sizeof(float);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == TDB_BF16)
-        decode_output_kernel<bf16><<<blocks, kThreads, smem, s>>>((const bf16*)act, ld, w, b, out, g, dim, F);
+        decode_output_kernel<bf16><<<blocks, kThreads, smem, s>>>((const bf16*)act, ld, w, b, out, g, dim, F, by_vox, by_z, by_y);
     else
-        decode_output_kernel<float><<<blocks, kThreads, smem, s>>>((const float*)act, ld, w, b, out, g, dim, F);
+        decode_output_kernel<float><<<blocks, kThreads, smem, s>>>((const float*)act, ld, w, b, out, g, dim, F, by_vox, by_z, by_y);
     TDB_CHECK_LAUNCH("tdb_decode_output");
     return 0;
 }
