@@ -40,10 +40,10 @@ class BackwardProgram:
 
     def _tmp(self, p, level, C, key) -> View:
         gb = p.setdefault("gbuf", {})
-        k = ("tmp", key, level)
-        if k not in gb or gb[k].t.shape[-1] < C:
-            gb[k] = p["grid"](level, max(C, p["max_c"].get(level, C)))
-        return gb[k].slice(0, C)
+        k = ("tmp", key, level, C)  # exact channel pitch: half-used 128-byte lines double the DRAM traffic
+        if k not in gb:
+            gb[k] = p["grid"](level, C)
+        return gb[k]
 
     def _dgrad_weights(self, conv, key, level):
         """Kernel-layout weights of the input-gradient convolution: W'[ci][co][k] = W[co][ci][2-k]."""

@@ -220,14 +220,16 @@ class DenoiserEngine:
         p["attn_qkv"] = grid(L, 3 * hid)
         p["attn_o"] = grid(L, hid)
         p["attn_proj"] = grid(L, center)
-        # scratch sized for the largest (rows x Cout) of any block at each level
+        # scratch per (level, channel count) with the EXACT channel pitch: a 32-channel tensor kept in a 64-channel-pitch
+        # buffer uses half of every 128-byte line, and DRAM/L2 move whole lines - ncu showed 2x the algorithmic read
+        # traffic for the 32->32 convolutions (and every streaming kernel over those tensors) with shared buffers
+        shapes = sorted({(self._block_level(name), bp.cout) for name, bp in self.blocks.items()})
         max_c = {}
-        for name, bp in self.blocks.items():
-            lvl = self._block_level(name)
-            max_c[lvl] = max(max_c.get(lvl, 0), bp.cout)
-        p["raw"] = {l: grid(l, c) for l, c in max_c.items()}
-        p["act"] = {l: grid(l, c) for l, c in max_c.items()}
-        p["res"] = {l: grid(l, c) for l, c in max_c.items()}
+        for lvl, c in shapes:
+            max_c[lvl] = max(max_c.get(lvl, 0), c)
+        p["raw"] = {k: grid(*k) for k in shapes}
+        p["act"] = {k: grid(*k) for k in shapes}
+        p["res"] = {k: grid(*k) for k in shapes}
         # fp32 split-K workspace of the tensor-core convolution: large enough for the two deepest levels
         deep = max(1, L - 1)
         Xd, Yd, Zd = sizes[deep]
@@ -346,18 +348,18 @@ class DenoiserEngine:
             raw, act, raw_b = sv["raw1"], sv["act1"], sv["raw2"]
             sv["x"], sv["out"], sv["slot"] = x, out, slot
         else:
-            raw = raw_b = p["raw"][lvl].slice(0, bp.cout)
-            act = p["act"][lvl].slice(0, bp.cout)
+            raw = raw_b = p["raw"][(lvl, bp.cout)]
+            act = p["act"][(lvl, bp.cout)]
         film_ptr = p["film"].data_ptr() + 4 * bp.film_offset
         proj = None
         if bp.has_proj and self.can_fuse_proj(x, bp.cout):
-            proj = (w[f"{name}.proj"], blk.conv.bias, p["res"][lvl].slice(0, bp.cout))
+            proj = (w[f"{name}.proj"], blk.conv.bias, p["res"][(lvl, bp.cout)])
         st, G = self._norm_conv(p, x, w[f"{name}.conv1"], blk.block1.conv, blk.block1.norm, raw, slot, proj=proj)
         self._pointwise(p, raw, st, blk.block1.norm, film_ptr, None, act, PW_SILU, G)
         raw = raw_b
         st, G = self._norm_conv(p, act, w[f"{name}.conv2"], blk.block2.conv, blk.block2.norm, raw, slot + 1)
         if bp.has_proj:
-            res = p["res"][lvl].slice(0, bp.cout)
+            res = p["res"][(lvl, bp.cout)]
             if proj is None:
                 self._conv(p, x, w[f"{name}.proj"], blk.conv.bias, res, 1)
         else:
