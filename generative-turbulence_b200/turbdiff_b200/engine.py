@@ -156,9 +156,13 @@ class DenoiserEngine:
         if self.precision != "bf16" or not self.fold or ntaps != 27:
             return None
         zp = self._level_zp.get(level, 1 << 30)
-        if self.win and cout in (64, 128) and cin % 32 == 0 and 27 * cin * cout <= 116 * 1024 and zp <= 63:
-            # row-window CTA-pair kernel: weights resident, activations staged 3x instead of 9x; needs N >= 64 (with
-            # N = 32 every MMA is bound by its 4 KB shared-memory read of A: measured slower than the kz-folded kernels)
+        resident = cin % 32 == 0 and 27 * cin * cout <= 116 * 1024
+        if self.win and resident and zp <= 63 and ((cout == 32 and cin >= 64) or cout == 64):
+            # row-window CTA pair with kz folded into N (N = 3*Cout): one window per kx instead of nine tiles per chunk
+            # (128->32: 0.48 -> 0.35 ms at B=4, L2 -> SM traffic / 1.6), fat MMAs for the narrow layers
+            return "winz"
+        if self.win and resident and zp <= 63 and cout == 128:
+            # row-window CTA-pair kernel, N = Cout: weights resident, activations staged 3x instead of 9x
             return "win"
         if cout in (16, 32, 64):
             pair = self.fold2 and cin % 64 == 0 and cout in (32, 64) and 9 * cin * 3 * cout * 2 > 112 * 1024
@@ -270,9 +274,9 @@ class DenoiserEngine:
         flags = _lib.CONV_ALL_ROWS if all_rows else 0
         if self.precision == "fp32":
             call("tdb_conv3d_f32", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ntaps, s)
-        elif self.fold_kind(ntaps, x.C, out.C, x.level) == "win":
+        elif self.fold_kind(ntaps, x.C, out.C, x.level) in ("win", "winz"):
             pw, pb, pv = proj if proj is not None else (None, None, None)
-            call("tdb_conv3d_bf16_win", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ptr(stats), G,
+            call("tdb_conv3d_bf16_" + self.fold_kind(ntaps, x.C, out.C, x.level), x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ptr(stats), G,
                  flags, ptr(pw), ptr(pb), pv.ptr if pv is not None else None, pv.ld if pv is not None else 0, s)
         elif self.fold_kind(ntaps, x.C, out.C, x.level) == "fold2":
             # proj = (weights [Cout][Cin] bf16, bias, output view): the block's 1x1 residual projection, fused
@@ -313,7 +317,7 @@ class DenoiserEngine:
         if not self.fuse_proj:
             return False
         kind = self.fold_kind(27, x.C, cout, x.level)
-        return (cout <= 64 and kind in ("fold2", "win")) or (kind == "win" and cout % 128 == 0)
+        return (cout <= 64 and kind in ("fold2", "win", "winz")) or (kind == "win" and cout % 128 == 0)
 
     def _norm_conv(self, p, x: View, w, conv, norm, raw: View, stats_slot, proj=None):
         """conv (+bias) followed by GroupNorm moments of its output."""

@@ -131,6 +131,15 @@ TDB_API int tdb_conv3d_bf16_win(const void* in, int ld_in, const void* w, const 
                         int X, int Y, int Z, int Cin, int Cout, double* gn_stats, int G, unsigned flags,
                         const void* w_proj, const float* bias_proj, void* out_proj, int ld_outp, void* stream);
 
+/* Row-window CTA-pair convolution with kz folded into N (N = 3*Cout): one shared-memory window per kx viewed at the
+ * three ky offsets, the +-1 row shift of kz applied in the epilogue (tiles of 128 rows advancing by 126).  For the
+ * narrow layers: Cout in {32, 64}, Cin % 32 == 0, folded weights (layout of tdb_conv3d_bf16_fold2: [3*Cout][9*Cin])
+ * resident in shared memory split over the pair (27*Cin*Cout bytes <= ~116 KB), Z + 2 <= 64.  Other arguments as
+ * tdb_conv3d_bf16_win. */
+TDB_API int tdb_conv3d_bf16_winz(const void* in, int ld_in, const void* w_fold, const float* bias, void* out, int ld_out,
+                         int B, int X, int Y, int Z, int Cin, int Cout, double* gn_stats, int G, unsigned flags,
+                         const void* w_proj, const float* bias_proj, void* out_proj, int ld_outp, void* stream);
+
 /* ---- normalisation / pointwise --------------------------------------------------------- */
 
 /* GroupNorm statistics over the interior voxels of a halo grid (ddpm.py:165,170,472):

@@ -36,8 +36,14 @@ for (X, Y, Z, Cin, Cout, old) in LAYERS:
     def run_win():
         _lib.call("tdb_conv3d_bf16_win", xin.data_ptr(), Cin, wk.data_ptr(), bias.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
                   None if old == "v1" else stats.data_ptr(), 8, 1 if old == "v1" else 0, None, None, None, 0, s())
+    def run_winz():
+        _lib.call("tdb_conv3d_bf16_winz", xin.data_ptr(), Cin, wf.data_ptr(), bias.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
+                  None if old == "v1" else stats.data_ptr(), 8, 1 if old == "v1" else 0, None, None, None, 0, s())
     row = {"layer": f"{Cin}->{Cout} @{X}", "gflop": 2 * 27 * Cin * Cout * B * X * Y * Z / 1e9, "old_kernel": old}
-    for name, fn in [("old", run_old), ("win", run_win)]:
+    cands = [("old", run_old), ("win", run_win)]
+    if Cout in (32, 64) and 27 * Cin * Cout <= 116 * 1024:
+        cands.append(("winz", run_winz))
+    for name, fn in cands:
         try:
             fn(); torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -49,7 +55,7 @@ for (X, Y, Z, Cin, Cout, old) in LAYERS:
             row[name + "_ms"] = round(ms, 4); row[name + "_tflops"] = round(row["gflop"] / ms, 1)
         except Exception as ex:  # noqa
             row[name + "_err"] = str(ex)[:300]
-            break
+            continue
     print(json.dumps(row), flush=True)
     res.append(row)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "bench_conv_win.json"), "w"), indent=1)

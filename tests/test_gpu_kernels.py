@@ -490,15 +490,24 @@ WIN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", WIN_CASES)
+WINZ_CASES = [c for c in WIN_CASES if c[5] in (32, 64) and 27 * c[4] * c[5] <= 116 * 1024] + [
+    (1, 30, 12, 62, 32, 32, False),    # Z + 2 = 64: the widest window (256 rows)
+    (2, 11, 5, 3, 64, 32, True), (1, 194, 6, 5, 128, 32, True),
+]
+
+
+@pytest.mark.parametrize("case,entry", [(c, "tdb_conv3d_bf16_win") for c in WIN_CASES] + [(c, "tdb_conv3d_bf16_winz") for c in WINZ_CASES])
 @pytest.mark.parametrize("variant", ["plain", "stats", "all_rows"])
-def test_conv3d_bf16_row_window(lib, case, variant):
+def test_conv3d_bf16_row_window(lib, case, entry, variant):
     B, X, Y, Z, Cin, Cout, with_proj = case
     x = gen(B, Cin, X, Y, Z, seed=1).bfloat16().float()
     w = gen(Cout, Cin, 3, 3, 3, seed=2, scale=1 / math.sqrt(Cin * 27)).bfloat16().float()
     b = gen(Cout, seed=3, scale=0.1)
     xin = to_halo(x, dtype=torch.bfloat16, ld=Cin + 8, c0=8)  # channel-pitched input view, no padding rows
-    wk = w.permute(0, 2, 3, 4, 1).reshape(Cout, 27 * Cin).contiguous().bfloat16()
+    if entry.endswith("winz"):  # kz folded into N: row = kz*Cout + co, column = (kx*3 + ky)*Cin + ci
+        wk = w.permute(4, 0, 2, 3, 1).reshape(3 * Cout, 9 * Cin).contiguous().bfloat16()
+    else:
+        wk = w.permute(0, 2, 3, 4, 1).reshape(Cout, 27 * Cin).contiguous().bfloat16()
     out = torch.zeros((B, X + 2, Y + 2, Z + 2, Cout), device="cuda", dtype=torch.bfloat16)
     G = 8
     stats = torch.zeros((B, G, 2), dtype=torch.float64, device="cuda")
@@ -510,7 +519,7 @@ def test_conv3d_bf16_row_window(lib, case, variant):
         outp = torch.zeros((B, X + 2, Y + 2, Z + 2, Cout + 8), device="cuda", dtype=torch.bfloat16)
         wpp = wp.reshape(Cout, Cin).contiguous().bfloat16()
         extra = (wpp.data_ptr(), bp.data_ptr(), outp.data_ptr() + 16, Cout + 8)
-    lib.call("tdb_conv3d_bf16_win", xin.data_ptr() + 16, Cin + 8, wk.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin,
+    lib.call(entry, xin.data_ptr() + 16, Cin + 8, wk.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin,
              Cout, stats.data_ptr() if variant == "stats" else None, G, lib.CONV_ALL_ROWS if variant == "all_rows" else 0, *extra,
              lib.stream_ptr())
     torch.cuda.synchronize()
@@ -527,7 +536,7 @@ def test_conv3d_bf16_row_window(lib, case, variant):
         # input gradients: the input has a ZERO halo, and every row (halo rows too) is the zero-padded convolution
         xz = torch.zeros((B, X + 2, Y + 2, Z + 2, Cin + 8), device="cuda", dtype=torch.bfloat16)
         xz[:, 1:-1, 1:-1, 1:-1, 8:] = x.permute(0, 2, 3, 4, 1).bfloat16()
-        lib.call("tdb_conv3d_bf16_win", xz.data_ptr() + 16, Cin + 8, wk.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z,
+        lib.call(entry, xz.data_ptr() + 16, Cin + 8, wk.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z,
                  Cin, Cout, None, G, lib.CONV_ALL_ROWS, None, None, None, 0, lib.stream_ptr())
         torch.cuda.synchronize()
         full = F.conv3d(F.pad(F.pad(x.double().cpu(), (1,) * 6), (1,) * 6), w.double().cpu(), b.double().cpu())
