@@ -11,7 +11,10 @@ LAYERS = [(194, 50, 50, 64, 64, "fold2"), (194, 50, 50, 128, 32, "fold2"), (194,
           (97, 25, 25, 64, 128, "fold2"), (97, 25, 25, 128, 128, "fold2"), (97, 25, 25, 64, 64, "fold2"),
           (48, 12, 12, 128, 256, "fold2"), (48, 12, 12, 256, 256, "fold2"), (48, 12, 12, 512, 128, "fold2"),
           (24, 6, 6, 256, 512, "fold2"), (24, 6, 6, 512, 512, "fold2"), (24, 6, 6, 1024, 256, "fold2")]
+ONLY = os.environ.get("ONLY")  # e.g. ONLY=32-32 restricts the run to one layer shape (for ncu)
 for (X, Y, Z, Cin, Cout, old) in LAYERS:
+    if ONLY and ONLY != f"{Cin}-{Cout}":
+        continue
     pad = (Y + 2) * (Z + 2) + 2 * (Z + 2) + 256
     rows = B * (X + 2) * (Y + 2) * (Z + 2)
     buf = torch.zeros((rows + 2 * pad, Cin), device="cuda", dtype=torch.bfloat16)
