@@ -47,6 +47,8 @@ SIGNATURES = {
     "tdb_conv3d_wgrad_tc": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _u, _p],
     "tdb_trilinear_bwd": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_attention_bwd": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "tdb_grad_sqnorm": [_p, _p, _p, _p, _i, _i, _p, _p],
+    "tdb_radam_step": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _f, _f, _f, _f, _f, _f, _i, _p],
     "tdb_cl_nc_outer": [_p, _i, _p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_where_cells": [_p, _p, _p, _p, _l, _l, _p],
     "tdb_select_cells": [_p, _p, _p, _l, _l, _l, _p],

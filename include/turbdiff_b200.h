@@ -57,6 +57,23 @@ extern "C" {
 #define TDB_STEP_CLIP 2u      /* clip_denoised: clamp x0 to [-1,1]  */
 #define TDB_STEP_FINAL 4u     /* after the update also pin non-inside voxels to x_bcs (ddpm.py:814) */
 
+/* ---- fused optimiser step (training path; reference: torch.optim.RAdam, turbdiff/models/diffusion.py:216, with
+ * Lightning's gradient_clip_val = 0.1 / norm, config/shapes_experiment.yaml:50-51) ---------------------------------
+ * All tensors fp32.  *_ptrs are device arrays of device addresses (one per tensor), numel the element counts;
+ * (chunk_tensor[i], chunk_off[i]) name the tensor and element offset of work chunk i (`chunk` elements, one block). */
+
+/* out (pre-zeroed double) += sum over all gradient elements of g*g. */
+TDB_API int tdb_grad_sqnorm(const int64_t* grad_ptrs, const int64_t* numel, const int* chunk_tensor, const int64_t* chunk_off,
+                    int n_chunks, int chunk, double* out, void* stream);
+
+/* One RAdam step on every tensor.  sqnorm != NULL: gradients are scaled by min(1, max_norm / (sqrt(*sqnorm) + 1e-6))
+ * on the fly (clip_grad_norm_).  step_size and `rectified` are the step-dependent scalars of torch's RAdam:
+ * rectified ? lr*rect*sqrt(1-beta2^t)/(1-beta1^t) : lr/(1-beta1^t). */
+TDB_API int tdb_radam_step(const int64_t* param_ptrs, const int64_t* grad_ptrs, const int64_t* exp_avg_ptrs,
+                   const int64_t* exp_avg_sq_ptrs, const int64_t* numel, const int* chunk_tensor, const int64_t* chunk_off,
+                   int n_chunks, int chunk, const double* sqnorm, float max_norm, float step_size, float beta1, float beta2,
+                   float eps, float weight_decay, int rectified, void* stream);
+
 TDB_API const char* tdb_last_error(void);
 TDB_API int tdb_version(void);
 /* number of kernel launches issued through this library by the calling process */
