@@ -47,14 +47,21 @@ class _Denoise(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_eps):
         model = ctx.model
-        grads, g_c_local = model.engine().train_backward(g_eps)
+        eng = model.engine()
+        grads, g_c_local = eng.train_backward(g_eps)
+        g_c = None if g_c_local is None else g_c_local.clone()
+        if torch.is_tensor(grads):
+            # graph replay: one flat buffer in parameter order; a single copy detaches it from the graph's static memory
+            tg = eng._train_replay
+            out = [v.view(shape) for v, shape in zip(grads.clone().split(tg["sizes"]), tg["shapes"])]
+            return (None, None, None, g_c, *out)
         out = []
         for name, prm in model.named_parameters():
             g = grads.get(name)
             if g is None:
                 raise RuntimeError(f"turbdiff_b200: no gradient produced for parameter {name}")
             out.append(g.to(prm.dtype).reshape(prm.shape).clone())  # the program's buffers are reused by the next step
-        return (None, None, None, None if g_c_local is None else g_c_local.clone(), *out)
+        return (None, None, None, g_c, *out)
 
 
 def denoise_with_grad(model, x, t, c_local):

