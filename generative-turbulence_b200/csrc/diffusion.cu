@@ -156,6 +156,47 @@ scatter_cells_kernel(const float* __restrict__ samples, const int64_t* __restric
     }
 }
 
+// the steps either side of the sampler, fused.
+// grid[b][f][v] = fma(scale[f], value, shift[f]) with value = samples[b][j][f] on voxel cell_idx[j] and 0 elsewhere:
+// OpenFOAMData.grid_embedding (data/ofles.py:220-232) followed by Normalization.normalize_grid
+// (models/normalization.py:20-24: addcmul(-mean/std, 1/std, x)); scale = 1/std, shift = -mean/std as torch computed them.
+__global__ void __launch_bounds__(kThreads)
+scatter_normalize_kernel(const float* __restrict__ samples, const int64_t* __restrict__ cell_idx, const uint8_t* __restrict__ mask,
+                         const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ grid, int B, int F,
+                         int64_t nvox, int64_t n_cells) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // voxels that are not cells: the normalised zero
+    const int64_t total_fill = (int64_t)B * F * nvox;
+    for (int64_t i = t0; i < total_fill; i += stride) {
+        const int64_t v = i % nvox;
+        const int f = (int)((i / nvox) % F);
+        if (!mask[v]) grid[i] = __fmaf_rn(scale[f], 0.0f, shift[f]);
+    }
+    // cells (disjoint from the voxels above)
+    const int64_t total = (int64_t)B * n_cells * F;
+    for (int64_t i = t0; i < total; i += stride) {
+        const int f = (int)(i % F);
+        const int64_t j = (i / F) % n_cells;
+        const int64_t b = i / ((int64_t)F * n_cells);
+        grid[(b * F + f) * nvox + cell_idx[j]] = __fmaf_rn(scale[f], samples[i], shift[f]);
+    }
+}
+
+// out[b][j][f] = fma(scale[f], x[b][f][cell_idx[j]], shift[f]): Normalization.denormalize_grid (normalization.py:26-30,
+// addcmul(mean, std, x)), select_cells and the "b f c -> b c f" rearrangement of SampleStore.add_samples
+// (models/metrics.py:50-57); scale = std, shift = mean.
+__global__ void __launch_bounds__(kThreads)
+gather_denormalize_kernel(const float* __restrict__ x, const int64_t* __restrict__ cell_idx, const float* __restrict__ scale,
+                          const float* __restrict__ shift, float* __restrict__ out, int B, int F, int64_t nvox, int64_t n_cells) {
+    const int64_t total = (int64_t)B * n_cells * F;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(i % F);
+        const int64_t j = (i / F) % n_cells;
+        const int64_t b = i / ((int64_t)F * n_cells);
+        out[i] = __fmaf_rn(scale[f], x[(b * F + f) * nvox + cell_idx[j]], shift[f]);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 build_mask_kernel(const int64_t* __restrict__ cell_idx, uint8_t* __restrict__ mask, int64_t n_cells, int64_t nvox) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += (int64_t)gridDim.x * blockDim.x) {
@@ -240,6 +281,26 @@ int tdb_scatter_cells(const float* samples, const int64_t* cell_idx, float* grid
     scatter_cells_kernel<<<blocks_for((int64_t)B * F * n_cells), kThreads, 0, (cudaStream_t)stream>>>(samples, cell_idx, grid,
                                                                                                        B, F, nvox, n_cells);
     TDB_CHECK_LAUNCH("tdb_scatter_cells");
+    return 0;
+}
+
+int tdb_scatter_normalize(const float* samples, const int64_t* cell_idx, const uint8_t* mask, const float* scale, const float* shift,
+                          float* grid, int B, int F, int64_t nvox, int64_t n_cells, void* stream) {
+    if ((int64_t)B * F * nvox == 0) return 0;
+    TDB_REQUIRE(cell_idx && mask && scale && shift && grid && (samples || n_cells == 0), TDB_E_BADARG, "tdb_scatter_normalize: null pointer");
+    scatter_normalize_kernel<<<blocks_for((int64_t)B * F * nvox), kThreads, 0, (cudaStream_t)stream>>>(samples, cell_idx, mask, scale, shift,
+                                                                                                      grid, B, F, nvox, n_cells);
+    TDB_CHECK_LAUNCH("tdb_scatter_normalize");
+    return 0;
+}
+
+int tdb_gather_denormalize(const float* x, const int64_t* cell_idx, const float* scale, const float* shift, float* out, int B, int F,
+                           int64_t nvox, int64_t n_cells, void* stream) {
+    if ((int64_t)B * F * n_cells == 0) return 0;
+    TDB_REQUIRE(x && cell_idx && scale && shift && out, TDB_E_BADARG, "tdb_gather_denormalize: null pointer");
+    gather_denormalize_kernel<<<blocks_for((int64_t)B * F * n_cells), kThreads, 0, (cudaStream_t)stream>>>(x, cell_idx, scale, shift, out, B,
+                                                                                                          F, nvox, n_cells);
+    TDB_CHECK_LAUNCH("tdb_gather_denormalize");
     return 0;
 }
 

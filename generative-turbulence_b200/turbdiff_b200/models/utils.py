@@ -58,3 +58,37 @@ def where_cells(cell_idx, cell_values: torch.Tensor, other: torch.Tensor | None 
     call("tdb_where_cells", a.data_ptr(), ptr(o), mask.data_ptr(), out.data_ptr(), a.numel() // nvox if nvox else 0, nvox,
          _lib.stream_ptr())
     return out
+
+
+def scatter_normalize(samples: torch.Tensor, cell_idx: torch.Tensor, cell_counts, mean: torch.Tensor, std: torch.Tensor):
+    """Fused ``OpenFOAMData.grid_embedding`` + ``Normalization.normalize_grid`` (data/ofles.py:220-232,
+    models/normalization.py:20-24): (B, n_cells, F) channels-last cell values -> normalised (B, F, *cell_counts) grid,
+    non-cell voxels holding the normalised zero.  One launch; bit-exact with the reference's op sequence.  (FIXED_VALUE
+    boundary cells, if any, are written by the caller: ``grid[..., f, idx] = addcmul(-mean/std, 1/std, value)``.)"""
+    _lib.require_cuda(samples, "samples")
+    B, n_cells, F = samples.shape
+    nvox = int(cell_counts[0]) * int(cell_counts[1]) * int(cell_counts[2])
+    s = samples.to(torch.float32).contiguous()
+    idx = cell_idx.to(device=s.device, dtype=torch.int64).contiguous()
+    mean, std = mean.to(s.device, torch.float32), std.to(s.device, torch.float32)
+    scale, shift = torch.reciprocal(std).contiguous(), (-mean / std).contiguous()  # exactly the reference's operands
+    grid = torch.empty((B, F, *cell_counts), dtype=torch.float32, device=s.device)
+    call("tdb_scatter_normalize", s.data_ptr(), idx.data_ptr(), inside_mask(idx, nvox).data_ptr(), scale.data_ptr(), shift.data_ptr(),
+         grid.data_ptr(), B, F, nvox, idx.numel(), _lib.stream_ptr())
+    return grid
+
+
+def gather_denormalize(x: torch.Tensor, cell_idx: torch.Tensor, mean: torch.Tensor, std: torch.Tensor):
+    """Fused ``Normalization.denormalize_grid`` + ``select_cells`` + channels-last rearrangement of
+    ``SampleStore.add_samples`` (models/normalization.py:26-30, models/utils.py:14-15, models/metrics.py:50-57):
+    (B, F, X, Y, Z) samples -> de-normalised (B, n_cells, F) cell values."""
+    _lib.require_cuda(x, "x")
+    B, F = x.shape[:2]
+    nvox = x.shape[-3] * x.shape[-2] * x.shape[-1]
+    xf = x.to(torch.float32).contiguous()
+    idx = cell_idx.to(device=x.device, dtype=torch.int64).contiguous()
+    scale, shift = std.to(x.device, torch.float32).contiguous(), mean.to(x.device, torch.float32).contiguous()
+    out = torch.empty((B, idx.numel(), F), dtype=torch.float32, device=x.device)
+    call("tdb_gather_denormalize", xf.data_ptr(), idx.data_ptr(), scale.data_ptr(), shift.data_ptr(), out.data_ptr(), B, F, nvox,
+         idx.numel(), _lib.stream_ptr())
+    return out

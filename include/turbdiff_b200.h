@@ -304,6 +304,15 @@ TDB_API int tdb_select_cells(const float* x, const int64_t* cell_idx, float* out
 /* grid[b][f][cell_idx[j]] = samples[b][j][f] on a pre-zeroed grid: data/ofles.py:220-232. */
 TDB_API int tdb_scatter_cells(const float* samples, const int64_t* cell_idx, float* grid, int B, int F,
                       int64_t nvox, int64_t n_cells, void* stream);
+/* Fused scatter + normalise: grid[b][f][v] = fma(scale[f], value, shift[f]) with value =
+ * samples[b][j][f] on voxel cell_idx[j] and 0 on every other voxel (mask = tdb_build_mask of cell_idx): data/ofles.py:220-232
+ * followed by models/normalization.py:20-24; scale = 1/std, shift = -mean/std.  Bit-exact with torch.addcmul. */
+TDB_API int tdb_scatter_normalize(const float* samples, const int64_t* cell_idx, const uint8_t* mask, const float* scale,
+                          const float* shift, float* grid, int B, int F, int64_t nvox, int64_t n_cells, void* stream);
+/* Fused de-normalise + gather, channels-last: out[b][j][f] = fma(scale[f], x[b][f][cell_idx[j]], shift[f]):
+ * models/normalization.py:26-30 + models/utils.py:14-15 + the "b f c -> b c f" of models/metrics.py:50-57; scale = std, shift = mean. */
+TDB_API int tdb_gather_denormalize(const float* x, const int64_t* cell_idx, const float* scale, const float* shift, float* out,
+                           int B, int F, int64_t nvox, int64_t n_cells, void* stream);
 /* mask[cell_idx[j]] = 1 on a pre-zeroed mask. */
 TDB_API int tdb_build_mask(const int64_t* cell_idx, uint8_t* mask, int64_t n_cells, int64_t nvox, void* stream);
 

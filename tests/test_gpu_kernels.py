@@ -541,3 +541,42 @@ def test_conv3d_bf16_row_window(lib, case, entry, variant):
         torch.cuda.synchronize()
         full = F.conv3d(F.pad(F.pad(x.double().cpu(), (1,) * 6), (1,) * 6), w.double().cpu(), b.double().cpu())
         assert rel_l2(out.permute(0, 4, 1, 2, 3).float(), full) < 4e-3
+
+
+# --------------------------------------------------------------------------- fused scatter/normalise, gather/de-normalise
+@pytest.mark.parametrize("B", [1, 3])
+def test_scatter_normalize_and_gather_denormalize(lib, B):
+    """grid_embedding + normalize_grid, and denormalize_grid + select_cells + 'b f c -> b c f', each in
+    one launch - bit-exact against the reference's torch op sequence on the same device, and equal to the CPU oracle."""
+    from oracle import grid_ref
+    from turbdiff_b200.models import utils as U
+
+    geo = grid_ref.channel_geometry(cells=(12, 7, 5), hole=((3, 6), (2, 5), (0, 3)), seed=3)
+    n_cells, F = len(geo.cell_idx), 4
+    g = torch.Generator().manual_seed(5)
+    samples = torch.randn(B, n_cells, F, generator=g)
+    mean = torch.tensor([0.3, -1.2, 0.05, 101.5])
+    std = torch.tensor([1.7, 0.4, 2.5, 13.0])
+    idx = torch.from_numpy(geo.cell_idx).cuda()
+
+    # reference op sequence (ofles.py:220-232, normalization.py:20-24) with torch on the GPU
+    x = torch.zeros((B, F, geo.n_vox), device="cuda")
+    x.transpose(-1, -2)[..., idx, :] = samples.cuda()
+    x = x.view(B, F, *geo.padded)
+    m3, s3 = mean.cuda().view(F, 1, 1, 1), std.cuda().view(F, 1, 1, 1)
+    want = torch.addcmul(-m3 / s3, torch.reciprocal(s3), x)
+    got = U.scatter_normalize(samples.cuda(), idx, geo.padded, mean, std)
+    assert torch.equal(got, want)
+    oracle = grid_ref.normalize_grid(grid_ref.grid_embedding(geo, [samples.numpy()], [{}]), mean.numpy(), std.numpy())
+    np.testing.assert_allclose(got.cpu().numpy(), oracle, rtol=1e-6, atol=1e-6)
+
+    # denormalize_grid + select_cells + rearrange (normalization.py:26-30, utils.py:14-15, metrics.py:50-57)
+    xs = torch.randn(B, F, *geo.padded, generator=g).cuda()
+    want2 = torch.addcmul(m3, s3, xs).flatten(-3)[..., idx].permute(0, 2, 1).contiguous()
+    got2 = U.gather_denormalize(xs, idx, mean, std)
+    assert torch.equal(got2, want2)
+    oracle2 = np.swapaxes(grid_ref.select_cells(grid_ref.denormalize_grid(xs.cpu().numpy(), mean.numpy(), std.numpy()), geo.cell_idx), 1, 2)
+    np.testing.assert_allclose(got2.cpu().numpy(), oracle2, rtol=1e-6, atol=1e-5)
+    # round trip: scatter/normalise then de-normalise/gather returns the samples (to fp32 rounding)
+    back = U.gather_denormalize(got, idx, mean, std)
+    np.testing.assert_allclose(back.cpu().numpy(), samples.numpy(), rtol=1e-5, atol=2e-5)
