@@ -140,7 +140,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             f = [c.strip() for c in r.split(",")]
@@ -151,11 +151,17 @@ class ClockSampler:
                 mx.append(float(f[1]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[2]))
+            except ValueError:
+                pass
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
+        # power_w: the board power during the timed region - SM clocks below max at ~1 kW are the power limiter at work
+        # even when the 20 ms sampling misses the sw_power_cap flag
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "power_w": statistics.median(pw) if pw else None}
 
 
 def time_cpu_reference(T, n_steps, warm, threads=None):
@@ -351,12 +357,12 @@ def run_ours(args):
         flops = conv_flops_per_sample(spec, geo.padded) * B
         ach = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         peak = pk["bf16_tflops_sustained"]
-        # ncu --set full, profiles/r01_ncu_full_win_v40.json: the top kernel (row-window conv, 64->64 @194x50x50, B=8) moves
-        # 543 MB + 459 MB of DRAM traffic per launch = its algorithmic bytes (one read of the input, one write of the output)
+        # ncu (profiles/r01_launches_v48_b8.csv, r01_ncu_full_win_v40.json): the top kernel (row-window conv, 64->64
+        # @194x50x50, B=8) moves 543 MB + 456 MB of DRAM traffic per launch = its algorithmic bytes (input read once, output written once)
         traffic = 1.0015e9 if (B == 8 and args.precision == "bf16") else None
-        roof = {"bound": "tensor", "kernel": "tcgen05 convolution family: conv3d_bf16_win / _fold2 / _fold / _tc kernels (all conv launches of one step)",
+        roof = {"bound": "tensor", "kernel": "tcgen05 convolution family: conv3d_bf16_winz / _win / _fold2 / _fold / _tc kernels (all conv launches of one step)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
-                "traffic_of": "conv3d_bf16_win_kernel<64,64,1> per launch (ncu dram__bytes_read+write, round-1 capture)" if traffic else None,
+                "traffic_of": "conv3d_bf16_winz_kernel<64,64> per launch (ncu dram__bytes_read+write, round-1 capture)" if traffic else None,
                 "peak_src": f"{pk['src']} bf16 sustained (kernel timed inside a long step)",
                 "conv_ms_per_step": conv_ms, "kernel_ms_per_step": prof}
         # the bandwidth-bound update kernel against the HBM roofline: 6 tensors x 4 B per element
