@@ -284,6 +284,11 @@ class DenoiserEngine:
             call("tdb_conv3d_bf16_fold2", x.ptr, x.ld, self.pad_rows((X, Y, Z)), w.data_ptr(), ptr(bias), out.ptr, out.ld,
                  B, X, Y, Z, x.C, out.C, ptr(stats), G, flags, ptr(pw), ptr(pb), pv.ptr if pv is not None else None,
                  pv.ld if pv is not None else 0, s)
+        elif (self.fold_kind(ntaps, x.C, out.C, x.level) == "fold" and self.win and x.C == 32 and out.C == 32 and x.ld == 32
+              and x.ptr % 128 == 0 and (Z + 2) % 2 == 0 and Z + 2 <= 128):
+            # 32 -> 32 with an exact input pitch: two grid rows per 128-byte TMA row (same folded weight layout)
+            call("tdb_conv3d_bf16_winp", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ptr(stats), G,
+                 flags, s)
         elif self.fold_kind(ntaps, x.C, out.C, x.level) == "fold":
             call("tdb_conv3d_bf16_fold", x.ptr, x.ld, self.pad_rows((X, Y, Z)), w.data_ptr(), ptr(bias), out.ptr, out.ld,
                  B, X, Y, Z, x.C, out.C, ptr(stats), G, flags, s)

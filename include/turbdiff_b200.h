@@ -157,6 +157,13 @@ TDB_API int tdb_conv3d_bf16_winz(const void* in, int ld_in, const void* w_fold, 
                          int B, int X, int Y, int Z, int Cin, int Cout, double* gn_stats, int G, unsigned flags,
                          const void* w_proj, const float* bias_proj, void* out_proj, int ld_outp, void* stream);
 
+/* 32 -> 32 channels, input pitch exactly 32 (64-byte rows): the kz-folded row-window kernel over PAIRED rows - two
+ * consecutive grid rows are fetched as one 128-byte line (half the TMA requests) and the K index of the MMA selects the
+ * parity.  Needs an even Z + 2 (<= 128) and a 128-byte aligned input; w_fold as tdb_conv3d_bf16_fold ([96][288]). */
+TDB_API int tdb_conv3d_bf16_winp(const void* in, int ld_in, const void* w_fold, const float* bias, void* out, int ld_out,
+                         int B, int X, int Y, int Z, int Cin, int Cout, double* gn_stats, int G, unsigned flags,
+                         void* stream);
+
 /* ---- normalisation / pointwise --------------------------------------------------------- */
 
 /* GroupNorm statistics over the interior voxels of a halo grid (ddpm.py:165,170,472):

@@ -43,7 +43,12 @@ for (X, Y, Z, Cin, Cout, old) in LAYERS:
         _lib.call("tdb_conv3d_bf16_winz", xin.data_ptr(), Cin, wf.data_ptr(), bias.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
                   None if old == "v1" else stats.data_ptr(), 8, 1 if old == "v1" else 0, None, None, None, 0, s())
     row = {"layer": f"{Cin}->{Cout} @{X}", "gflop": 2 * 27 * Cin * Cout * B * X * Y * Z / 1e9, "old_kernel": old}
+    def run_winp():
+        _lib.call("tdb_conv3d_bf16_winp", xin.data_ptr(), Cin, wf.data_ptr(), bias.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
+                  stats.data_ptr(), 8, 0, s())
     cands = [("old", run_old), ("win", run_win)]
+    if Cin == 32 and Cout == 32:
+        cands.append(("winp", run_winp))
     if Cout in (32, 64) and 27 * Cin * Cout <= 116 * 1024:
         cands.append(("winz", run_winz))
     for name, fn in cands:

@@ -580,3 +580,36 @@ def test_scatter_normalize_and_gather_denormalize(lib, B):
     # round trip: scatter/normalise then de-normalise/gather returns the samples (to fp32 rounding)
     back = U.gather_denormalize(got, idx, mean, std)
     np.testing.assert_allclose(back.cpu().numpy(), samples.numpy(), rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("case", [(2, 9, 7, 6), (2, 40, 20, 50), (1, 30, 12, 62), (3, 21, 11, 8), (1, 194, 6, 4)])
+@pytest.mark.parametrize("variant", ["plain", "stats", "all_rows"])
+def test_conv3d_bf16_paired_rows_32_to_32(lib, case, variant):
+    """tdb_conv3d_bf16_winp: 32 -> 32 channels with two grid rows per 128-byte TMA row (even Z + 2, input pitch 32)."""
+    B, X, Y, Z = case
+    Cin = Cout = 32
+    x = gen(B, Cin, X, Y, Z, seed=1).bfloat16().float()
+    w = gen(Cout, Cin, 3, 3, 3, seed=2, scale=1 / math.sqrt(Cin * 27)).bfloat16().float()
+    b = gen(Cout, seed=3, scale=0.1)
+    wk = w.permute(4, 0, 2, 3, 1).reshape(3 * Cout, 9 * Cin).contiguous().bfloat16()
+    out = torch.zeros((B, X + 2, Y + 2, Z + 2, Cout), device="cuda", dtype=torch.bfloat16)
+    G = 8
+    stats = torch.zeros((B, G, 2), dtype=torch.float64, device="cuda")
+    if variant == "all_rows":  # input gradients: zero halo in, every row out
+        xin = torch.zeros((B, X + 2, Y + 2, Z + 2, Cin), device="cuda", dtype=torch.bfloat16)
+        xin[:, 1:-1, 1:-1, 1:-1] = x.permute(0, 2, 3, 4, 1).bfloat16()
+    else:
+        xin = to_halo(x, dtype=torch.bfloat16)
+    lib.call("tdb_conv3d_bf16_winp", xin.data_ptr(), Cin, wk.data_ptr(), b.data_ptr(), out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
+             stats.data_ptr() if variant == "stats" else None, G, lib.CONV_ALL_ROWS if variant == "all_rows" else 0, lib.stream_ptr())
+    torch.cuda.synchronize()
+    if variant == "all_rows":
+        full = F.conv3d(F.pad(F.pad(x.double().cpu(), (1,) * 6), (1,) * 6), w.double().cpu(), b.double().cpu())
+        assert rel_l2(out.permute(0, 4, 1, 2, 3).float(), full) < 4e-3
+        return
+    want = _conv_ref(x.double().cpu(), w.double().cpu(), b.double().cpu(), 27)
+    assert rel_l2(from_halo(out), want) < 4e-3
+    if variant == "stats":
+        wg = want.reshape(B, G, -1)
+        np.testing.assert_allclose(stats[..., 0].cpu().numpy(), wg.sum(-1).numpy(), rtol=1e-4, atol=1e-2)
+        np.testing.assert_allclose(stats[..., 1].cpu().numpy(), (wg**2).sum(-1).numpy(), rtol=1e-4)
