@@ -33,8 +33,6 @@ for p in (ROOT, ROOT / "generative-turbulence_b200"):
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-CELLS = (192, 48, 48)
-HOLE = ((12, 24), (16, 32), (0, 32))  # scripts/generate-performance-dataset.py:25 ("wide pillar")
 METRIC = "ddpm_samples_per_sec"
 UNIT = "samples/s"
 
@@ -71,44 +69,17 @@ def shapes_spec(T):
 
 
 def synthetic_inputs(B, seed):
-    """x_bcs ~ N(0,1) on the padded grid, cell-type conditioning from a seeded 6x4 table."""
-    from oracle import grid_ref
+    """x_bcs ~ N(0,1) on the padded grid and the cell-type conditioning (turbdiff_b200.synthetic: no oracle involved)."""
+    from turbdiff_b200.synthetic import synthetic_inputs as make
 
-    geo = grid_ref.channel_geometry(cells=CELLS, hole=HOLE, seed=0)
-    rng = np.random.Generator(np.random.PCG64(seed))
-    table = rng.standard_normal((6, 4)).astype(np.float32)
-    c_local = torch.from_numpy(np.ascontiguousarray(grid_ref.cell_type_embedding(geo, table)))
-    x = torch.from_numpy(rng.standard_normal((B, 4, *geo.padded)).astype(np.float32))
-    return geo, x, c_local
+    return make(B, seed)
 
 
-def conv_flops_per_sample(spec, spatial):
-    """Algorithmic FLOPs of one denoiser forward (2*Cin*Cout*k^3*voxels summed over the 3x3x3 and
-    1x1x1 convs; SURVEY.md section 8a: 666.2 GFLOP at the shapes config)."""
-    from oracle.unet_ref import level_sizes
+def conv_flops_per_sample(spatial):
+    """Algorithmic FLOPs of one denoiser forward (666.2 GFLOP at the shapes config)."""
+    from turbdiff_b200.synthetic import conv_flops_per_sample as flops
 
-    sizes = level_sizes(spatial, spec.u_net_levels)
-    vox = [int(np.prod(s)) for s in sizes]
-    d = spec.dim
-    total = 0.0
-
-    def rb(cin, cout, lvl):
-        f = 2.0 * 27 * vox[lvl] * (cin * cout + cout * cout)
-        if cin != cout:
-            f += 2.0 * vox[lvl] * cin * cout
-        return f
-
-    total += 2.0 * vox[0] * (spec.in_features * d + spec.c_local_features * d)  # encoders
-    for l, (cin, cout) in enumerate(spec.down_channels()):
-        total += rb(cin, cout, l)
-    L = spec.u_net_levels
-    cd = spec.center_dim
-    total += 2 * rb(cd, cd, L)
-    total += 2.0 * vox[L] * (cd * 384 + 128 * cd)
-    for i, (cin, cout) in enumerate(spec.up_channels()):
-        total += rb(cin, cout, L - 1 - i)
-    total += rb(d, d, 0) + 2.0 * vox[0] * d * spec.out_features
-    return total
+    return flops(spatial)
 
 
 class ClockSampler:
@@ -216,7 +187,6 @@ def run_reference(args):
 def run_ours(args):
     import torch.distributed as dist
 
-    from oracle.unet_ref import synth_state_dict
     from turbdiff_b200 import DenoisingModel, GaussianDiffusion, _lib
     from turbdiff_b200.models.conditioning import Conditioning
     from turbdiff_b200.models.utils import inside_mask
@@ -229,10 +199,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     T, B = args.timesteps, args.batch
-    spec = shapes_spec(T)
+    torch.manual_seed(0)  # random-init weights of the architecture (the reference's own initialisers, same order)
     model = DenoisingModel(in_features=4, out_features=4, c_local_features=4, c_global_features=0, timesteps=T, dim=32, u_net_levels=4,
                            norm_type="group", precision=args.precision)
-    model.load_state_dict(synth_state_dict(spec, 0))
     model = model.to(dev).eval()
     gd = GaussianDiffusion(model, timesteps=T, beta_schedule="log-snr-linear", loss_type="l2", noise_bcs=True).to(dev)
     geo, x_host, c_local = synthetic_inputs(B, 100 + rank)
@@ -354,7 +323,7 @@ def run_ours(args):
         graph = graph_saved
         pk = peaks()
         conv_ms = sum(v for k, v in prof.items() if k.startswith("tdb_conv3d"))  # all convolution kernels of one step
-        flops = conv_flops_per_sample(spec, geo.padded) * B
+        flops = conv_flops_per_sample(geo.padded) * B
         ach = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         peak = pk["bf16_tflops_sustained"]
         # ncu (profiles/r01_launches_v48_b8.csv, r01_ncu_full_win_v40.json): the top kernel (row-window conv, 64->64
@@ -436,7 +405,7 @@ def run_ours(args):
                  "kernel_ms_per_step": train_prof, "host_enqueue_ms_per_step": host_ms,
                  "loss": float(loss.item()), "kernel_launches_per_step": n_train_launches,
                  "includes": "q_sample + U-Net forward + backward + bucketed NCCL gradient all-reduce (N>1) + fused clip_grad_norm(0.1) + RAdam step (turbdiff_b200.optim.FusedRAdam)",
-                 "train_flops_per_step": 3 * conv_flops_per_sample(spec, geo.padded) * TB}
+                 "train_flops_per_step": 3 * conv_flops_per_sample(geo.padded) * TB}
         train["tflops"] = train["train_flops_per_step"] / (train["ms_per_step"] * 1e-3) / 1e12
         model.eval()
 

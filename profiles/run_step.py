@@ -15,7 +15,6 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 import bench  # noqa: E402
-from oracle.unet_ref import synth_state_dict  # noqa: E402
 from turbdiff_b200 import DenoisingModel, GaussianDiffusion, _lib  # noqa: E402
 from turbdiff_b200.models.utils import inside_mask  # noqa: E402
 
@@ -26,10 +25,9 @@ ap.add_argument("--steps", type=int, default=1)
 a = ap.parse_args()
 T, B = 1000, a.batch
 dev = torch.device("cuda", 0)
-spec = bench.shapes_spec(T)
+torch.manual_seed(0)
 m = DenoisingModel(in_features=4, out_features=4, c_local_features=4, c_global_features=0, timesteps=T, dim=32, u_net_levels=4,
                    norm_type="group", precision=a.precision)
-m.load_state_dict(synth_state_dict(spec, 0))
 m = m.to(dev).eval()
 gd = GaussianDiffusion(m, timesteps=T, beta_schedule="log-snr-linear", noise_bcs=True).to(dev)
 geo, x, c_local = bench.synthetic_inputs(B, 100)
