@@ -94,10 +94,30 @@ def check(rc: int, what: str = "") -> None:
 # launching stream around each C-ABI call.  None = off (the normal case: zero overhead).
 PROFILE: dict | None = None
 
+# TURBDIFF_B200_DEBUG_CAPTURE=1: after every C-ABI call made while a CUDA graph is being captured, ask the runtime
+# whether the capture is still valid and name the first call after which it is not (diagnostic).
+import os as _os
+
+_DEBUG_CAPTURE = _os.environ.get("TURBDIFF_B200_DEBUG_CAPTURE", "0") == "1"
+_capture_was = [False]
+
+
+def _capture_probe(name):
+    try:
+        now = torch.cuda.is_current_stream_capturing()
+    except Exception as e:  # invalidated captures raise here
+        print(f"[capture-probe] capture INVALID after {name}: {str(e)[:120]}", flush=True)
+        raise
+    if _capture_was[0] and not now:
+        print(f"[capture-probe] capture ended/invalid after {name}", flush=True)
+    _capture_was[0] = now
+
 
 def call(name: str, *args) -> None:
     if PROFILE is None:
         check(getattr(load(), name)(*args), name)
+        if _DEBUG_CAPTURE:
+            _capture_probe(name)
         return
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
