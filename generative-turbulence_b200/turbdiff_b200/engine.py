@@ -539,7 +539,16 @@ class DenoiserEngine:
         sig = tuple(q.data_ptr() for q in self.model.parameters())
         tg = self._train_graphs.get(key)
         if tg is None or tg["sig"] != sig:
-            tg = self._train_graphs[key] = self._capture_train(x, t, c_local, sig)
+            try:
+                tg = self._train_graphs[key] = self._capture_train(x, t, c_local, sig)
+            except RuntimeError as e:  # a failed capture is not fatal: the same kernels run from the eager launch programs
+                import warnings
+
+                warnings.warn(f"turbdiff_b200: CUDA-graph capture of the training step failed ({str(e)[:200]}); using the eager launch programs")
+                self.train_graph = False
+                self._train_replay = None
+                torch.cuda.synchronize()
+                return self.forward(x, t, c_local, train=True)
         tg["x"].copy_(x)
         tg["t"].copy_(t)
         if c_local is not None:

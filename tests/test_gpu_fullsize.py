@@ -116,7 +116,7 @@ def _loss_and_grads(full, precision, direction=None, eps=0.0):
     out = m(full["x"], t, {_key(): cl})
     loss = (out.double() * G.double()).sum()
     loss.backward()
-    return float(loss), {k: p.grad.clone() for k, p in m.named_parameters()}, G
+    return float(loss.detach()), {k: p.grad.clone() for k, p in m.named_parameters()}, G
 
 
 def test_full_size_gradients(full):
