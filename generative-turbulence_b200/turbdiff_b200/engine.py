@@ -514,8 +514,16 @@ class DenoiserEngine:
                 self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=False)
             torch.cuda.current_stream().wait_stream(side)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=True)
+            try:
+                with torch.cuda.graph(g):
+                    self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=True)
+            except RuntimeError as e:  # not fatal: the same launch program runs eagerly
+                import warnings
+
+                warnings.warn(f"turbdiff_b200: CUDA-graph capture of the denoiser failed ({str(e)[:200]}); using the eager launch program")
+                self.use_graph = False
+                torch.cuda.synchronize()
+                return self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=True)
             st["graph"], st["wver"] = g, self._wversion
         st["graph"].replay()
         B = st["x_t"].shape[0]
