@@ -326,7 +326,7 @@ def run_ours(args):
         flops = conv_flops_per_sample(geo.padded) * B
         ach = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         peak = pk["bf16_tflops_sustained"]
-        # ncu (profiles/r01_launches_v48_b8.csv, r01_ncu_full_win_v40.json): the top kernel (row-window conv, 64->64
+        # ncu (profiles/r01_launches_v52_b8.csv, r01_ncu_full_win_v40.json): the top kernel (row-window conv, 64->64
         # @194x50x50, B=8) moves 543 MB + 456 MB of DRAM traffic per launch = its algorithmic bytes (input read once, output written once)
         traffic = 1.0015e9 if (B == 8 and args.precision == "bf16") else None
         roof = {"bound": "tensor", "kernel": "tcgen05 convolution family: conv3d_bf16_winz / _win / _fold2 / _fold / _tc kernels (all conv launches of one step)",
