@@ -149,10 +149,13 @@ class DenoiserEngine:
         return (Y + 2) * (Z + 2) + 2 * (Z + 2) + 256
 
     def fold_kind(self, ntaps, cin, cout, level):
-        """Which bf16 kernel a convolution runs on: None = per-tap kernel (tdb_conv3d_bf16), "fold" = kz-folded
-        persistent kernel, "fold2" = its cta_group::2 (CTA pair) variant.  Pairs take the shapes whose folded
-        weights do not fit one SM (half the weight ingest per SM, resident when the half fits) and, as 128-channel
-        N tiles, the wide layers of every level but the bottleneck (tiny M, huge K: split-K territory)."""
+        """Which bf16 kernel a 3x3x3 convolution runs on (None = per-tap kernel tdb_conv3d_bf16):
+        "winz"  kz-folded row-window CTA pair, resident weights: Cout 64 and 128 -> 32 (narrow, full resolution);
+        "win"   row-window CTA pair: 32 -> 128 resident, and every Cout % 128 == 0 layer as N tiles with streamed weights;
+        "fold2" kz-folded CTA pair with nine tiles per chunk: what the row-window kernels cannot take (256 -> 64);
+        "fold"  single-CTA kz-folded kernel: Cout <= 64 leftovers (32 -> 32 switches to the paired-row kernel in _conv
+                when the input pitch is exactly 32, 128-byte aligned and Z + 2 is even).
+        The bottleneck level (tiny M, huge K) stays on the per-tap kernel with split-K."""
         if self.precision != "bf16" or not self.fold or ntaps != 27:
             return None
         zp = self._level_zp.get(level, 1 << 30)
