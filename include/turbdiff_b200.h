@@ -137,7 +137,8 @@ TDB_API int tdb_conv3d_bf16_fold2(const void* in, int ld_in, int pad_rows, const
                           int G, unsigned flags, const void* w_proj, const float* bias_proj, void* out_proj,
                           int ld_outp, void* stream);
 
-/* Row-window CTA-pair convolution (3x3x3 only): for one kx the nine (ky, kz) taps are nine row-shifted views of ONE
+/* Row-window CTA-pair convolution (3x3x3 only; replaces nn.Conv3d(3, padding_mode="replicate") + res_conv of reference
+ * turbdiff/models/ddpm.py:164,188,197): for one kx the nine (ky, kz) taps are nine row-shifted views of ONE
  * shared-memory window of 128 + 2*(Z+2) + 2 rows, so activations are staged 3x per channel chunk instead of 9x/27x and
  * all 128 rows of a tile are outputs.  w = the per-tap layout of tdb_conv3d_bf16 ([Cout][27*Cin] bf16).  Cin % 32 == 0,
  * Cout in {32, 64, 128}: the weights stay resident in shared memory, split over the pair, when 27*Cin*Cout bytes leave
@@ -148,7 +149,7 @@ TDB_API int tdb_conv3d_bf16_win(const void* in, int ld_in, const void* w, const 
                         int X, int Y, int Z, int Cin, int Cout, double* gn_stats, int G, unsigned flags,
                         const void* w_proj, const float* bias_proj, void* out_proj, int ld_outp, void* stream);
 
-/* Row-window CTA-pair convolution with kz folded into N (N = 3*Cout): one shared-memory window per kx viewed at the
+/* Row-window CTA-pair convolution with kz folded into N (N = 3*Cout; same reference call sites, ddpm.py:164,188,197): one shared-memory window per kx viewed at the
  * three ky offsets, the +-1 row shift of kz applied in the epilogue (tiles of 128 rows advancing by 126).  For the
  * narrow layers: Cout in {32, 64}, Cin % 32 == 0, folded weights (layout of tdb_conv3d_bf16_fold2: [3*Cout][9*Cin])
  * resident in shared memory split over the pair (27*Cin*Cout bytes <= ~116 KB), Z + 2 <= 64.  Other arguments as
@@ -157,7 +158,7 @@ TDB_API int tdb_conv3d_bf16_winz(const void* in, int ld_in, const void* w_fold, 
                          int B, int X, int Y, int Z, int Cin, int Cout, double* gn_stats, int G, unsigned flags,
                          const void* w_proj, const float* bias_proj, void* out_proj, int ld_outp, void* stream);
 
-/* 32 -> 32 channels, input pitch exactly 32 (64-byte rows): the kz-folded row-window kernel over PAIRED rows - two
+/* 32 -> 32 channels (reference ddpm.py:164 in the full-resolution blocks), input pitch exactly 32 (64-byte rows): the kz-folded row-window kernel over PAIRED rows - two
  * consecutive grid rows are fetched as one 128-byte line (half the TMA requests) and the K index of the MMA selects the
  * parity.  Needs an even Z + 2 (<= 128) and a 128-byte aligned input; w_fold as tdb_conv3d_bf16_fold ([96][288]). */
 TDB_API int tdb_conv3d_bf16_winp(const void* in, int ld_in, const void* w_fold, const float* bias, void* out, int ld_out,
@@ -279,7 +280,8 @@ TDB_API int tdb_pointwise_bwd_apply(const void* g_out, int ld_g, const void* raw
 TDB_API int tdb_conv3d_wgrad(const void* in, int ld_in, const void* d_out, int ld_do, float* dw, int B, int X, int Y,
                      int Z, int Cin, int Cout, int ntaps, int dtype, unsigned flags, void* stream);
 
-/* The bf16 tensor-core form of tdb_conv3d_wgrad (tcgen05.mma with MN-major operands straight from the halo grids);
+/* The bf16 tensor-core form of tdb_conv3d_wgrad (reference: torch.autograd's conv weight gradient behind ddpm.py:164,188
+ * when GaussianDiffusion.forward's loss is back-propagated, ddpm.py:874-882) (tcgen05.mma with MN-major operands straight from the halo grids);
  * same contract as TDB_WGRAD_ZERO_HALO (d_out zero on halo rows); needs Cin % 32 == 0 and Cout in {32, 64*n <= 256,
  * 256*n}.  tdb_conv3d_wgrad dispatches here when it can.  mode: TDB_WGRAD_SHARE_KZ = load one row window per
  * (kx, ky) and use it for the three kz taps through row-shifted matrix descriptors (0 = one window per tap). */
