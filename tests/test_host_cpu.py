@@ -127,3 +127,40 @@ def test_launch_program_is_well_formed(built_lib, monkeypatch):
     assert n["tdb_attention"] == 1 and n["tdb_time_film"] == 1 and n["tdb_encode_input"] == 1 and n["tdb_decode_output"] == 1
     # level sizes follow max(int(s/2), 3)
     assert engine.level_sizes((194, 50, 50), 4) == [(194, 50, 50), (97, 25, 25), (48, 12, 12), (24, 6, 6), (12, 3, 3)]
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the product package may import it (bench.py may, in its CPU arms only)."""
+    import pathlib
+    import re
+
+    root = pathlib.Path(__file__).resolve().parents[1]
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b", re.M)
+    for f in (root / "generative-turbulence_b200").rglob("*.py"):
+        assert not pat.search(f.read_text()), f
+    bench_src = (root / "bench.py").read_text()
+    gpu_arm = bench_src[bench_src.index("def run_ours("):]
+    assert not pat.search(gpu_arm), "the GPU arm of bench.py must not touch oracle/"
+
+
+def test_synthetic_workload_matches_the_survey_numbers():
+    from turbdiff_b200 import synthetic
+
+    geo = synthetic.channel_geometry()
+    assert geo.padded == (194, 50, 50) and geo.cell_type.shape == geo.padded
+    # 192*48*48 cells minus the 12x16x32 pillar
+    assert len(geo.cell_idx) == 192 * 48 * 48 - 12 * 16 * 32 == len(set(geo.cell_idx.tolist()))
+    assert (geo.cell_type.reshape(-1)[geo.cell_idx] == synthetic.INSIDE).all()
+    assert abs(synthetic.conv_flops_per_sample(geo.padded) / 1e9 - 666.2) < 0.1  # SURVEY.md section 8a
+
+
+def test_fused_radam_refuses_cpu_tensors():
+    from turbdiff_b200.optim import FusedRAdam
+
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    opt = FusedRAdam([p], lr=1e-3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        opt.step()
+    with pytest.raises(ValueError):
+        FusedRAdam([p], lr=-1.0)
