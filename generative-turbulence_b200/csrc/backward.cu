@@ -196,7 +196,7 @@ __device__ __forceinline__ PwCoef pw_coef(int b, int c, int C, int G, const doub
     return r;
 }
 
-// red[b][c] = (sum g_u, sum g_u*xhat, sum raw) over interior voxels (pre-zeroed): fp32 per thread (<= 32 voxels),
+// red[b][c] = (sum g_u, sum g_u*xhat, sum raw, sum g_out) over interior voxels (pre-zeroed): fp32 per thread (<= 32 voxels),
 // fp32 shared atomics per CTA, one double atomic per (CTA, channel, moment).  The third sum lets the host derive the
 // per-channel sum of d_raw (= the bias gradient of the convolution below) without another pass over d_raw.
 template <typename T>
@@ -206,8 +206,8 @@ pw_bwd_reduce_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict_
                      const float* __restrict__ film, int film_ld, double* __restrict__ red, Grid3 gr, int C, int G, float eps,
                      unsigned flags, int vox_per_block, FastDiv by_z, FastDiv by_y) {
     constexpr int N = Vec<T>::N;
-    extern __shared__ float sred[];  // [C][3]
-    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sred[i] = 0.0f;
+    extern __shared__ float sred[];  // [C][4]
+    for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) sred[i] = 0.0f;
     __syncthreads();
     const int b = blockIdx.y;
     const int chunks = C / N;
@@ -231,9 +231,9 @@ pw_bwd_reduce_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict_
         const uint32_t v_end = min(nvox, v_begin + (uint32_t)vox_per_block);
         const T* rb = raw + (int64_t)b * gr.vox_p * ld_raw + c0;
         const T* gb = g_out + (int64_t)b * gr.vox_p * ld_g + c0;
-        float a1[N], a2[N], a3[N];
+        float a1[N], a2[N], a3[N], a4[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) a1[i] = a2[i] = a3[i] = 0.0f;
+        for (int i = 0; i < N; ++i) a1[i] = a2[i] = a3[i] = a4[i] = 0.0f;
         auto row_of = [&](uint32_t v) {
             uint32_t q, z, x, y;
             by_z.divmod(v, q, z);
@@ -248,6 +248,7 @@ pw_bwd_reduce_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict_
                 a1[i] += gu;
                 a2[i] = fmaf(gu, xv[i], a2[i]);
                 a3[i] += xv[i];
+                a4[i] += gv[i];
             }
         };
         uint32_t v = v_begin + lane_vox;
@@ -268,22 +269,39 @@ pw_bwd_reduce_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict_
             Vec<T>::load(gb + r0 * ld_g, g0);
             accumulate(x0, g0);
         }
+        // lanes of a warp that own the same channel chunk (lane % chunks) are combined by shuffles first, so that only
+        // `chunks` lanes per warp touch the shared accumulators (the per-thread shared atomics used to dominate this kernel)
+        const bool shuffle = chunks <= 32 && (chunks & (chunks - 1)) == 0;
+        const int lane = threadIdx.x & 31;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            atomicAdd(&sred[3 * (c0 + i)], a1[i]);
-            atomicAdd(&sred[3 * (c0 + i) + 1], a2[i]);
-            atomicAdd(&sred[3 * (c0 + i) + 2], a3[i]);
+            float v1 = a1[i], v2 = a2[i], v3 = a3[i], v4 = a4[i];
+            if (shuffle) {
+                for (int o = 16; o >= chunks; o >>= 1) {
+                    v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                    v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+                    v3 += __shfl_xor_sync(0xffffffffu, v3, o);
+                    v4 += __shfl_xor_sync(0xffffffffu, v4, o);
+                }
+            }
+            if (!shuffle || lane < chunks) {
+                atomicAdd(&sred[4 * (c0 + i)], v1);
+                atomicAdd(&sred[4 * (c0 + i) + 1], v2);
+                atomicAdd(&sred[4 * (c0 + i) + 2], v3);
+                atomicAdd(&sred[4 * (c0 + i) + 3], v4);
+            }
         }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const double inv_n = 1.0 / ((double)(C / G) * gr.X * gr.Y * gr.Z);
         const PwCoef k = pw_coef(b, c, C, G, stats, gamma, beta, film, film_ld, inv_n, eps);
-        const float s1 = sred[3 * c], s2 = sred[3 * c + 1], s3 = sred[3 * c + 2];
-        double* dst = red + ((int64_t)b * C + c) * 3;
+        const float s1 = sred[4 * c], s2 = sred[4 * c + 1], s3 = sred[4 * c + 2];
+        double* dst = red + ((int64_t)b * C + c) * 4;
         atomicAdd(dst, (double)s1);
         atomicAdd(dst + 1, (double)(k.rstd * (s2 - k.mean * s1)));  // sum g_u * xhat
         atomicAdd(dst + 2, (double)s3);
+        atomicAdd(dst + 3, (double)sred[4 * c + 3]);                // sum g_out (bias gradient of a residual projection)
     }
 }
 
@@ -341,14 +359,15 @@ pw_bwd_apply_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict__
 }
 
 // ---------------------------------------------------------------- pointwise backward: group / parameter bookkeeping
-// One block.  From red[b][c] = (A1, A2, Sx) and the forward moments: grp[b][g] = (m1, m2) for the apply pass,
+// One block.  From red[b][c] = (A1, A2, Sx, Sg) and the forward moments: grp[b][g] = (m1, m2) for the apply pass,
 // colsum[c] = sum over samples and voxels of d_raw (bias gradient of the convolution that produced raw),
-// gw[c] / gb[c] = GroupNorm weight / bias gradients, dfilm[b][c], dfilm[b][C + c] = FiLM scale / shift gradients.
+// gw[c] / gb[c] = GroupNorm weight / bias gradients, dfilm[b][c], dfilm[b][C + c] = FiLM scale / shift gradients,
+// gsum[c] = sum of the incoming gradient g_out (bias gradient of a 1x1 residual projection applied to the same output).
 __global__ void __launch_bounds__(kThreads)
 pw_bwd_finalize_kernel(const double* __restrict__ red, const double* __restrict__ stats, const float* __restrict__ gamma,
                        const float* __restrict__ beta, const float* __restrict__ film, int film_ld, float* __restrict__ grp,
-                       float* __restrict__ colsum, float* __restrict__ gw, float* __restrict__ gb, float* __restrict__ dfilm,
-                       int dfilm_ld, int B, int C, int G, double nv, double eps) {
+                       float* __restrict__ colsum, float* __restrict__ gw, float* __restrict__ gb, float* __restrict__ gsum,
+                       float* __restrict__ dfilm, int dfilm_ld, int B, int C, int G, double nv, double eps) {
     extern __shared__ double sg[];  // [B*G][4] = mean, rstd, m1, m2
     const int cpg = C / G;
     const double n = (double)cpg * nv;
@@ -361,8 +380,8 @@ pw_bwd_finalize_kernel(const double* __restrict__ red, const double* __restrict_
         for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
             double k = (double)gamma[c];
             if (film) k *= (double)film[(int64_t)b * film_ld + c] + 1.0;
-            m1 += k * red[((int64_t)b * C + c) * 3];
-            m2 += k * red[((int64_t)b * C + c) * 3 + 1];
+            m1 += k * red[((int64_t)b * C + c) * 4];
+            m2 += k * red[((int64_t)b * C + c) * 4 + 1];
         }
         m1 /= n;
         m2 /= n;
@@ -373,9 +392,10 @@ pw_bwd_finalize_kernel(const double* __restrict__ red, const double* __restrict_
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g = c / cpg;
-        double cs = 0.0, w = 0.0, bsum = 0.0;
+        double cs = 0.0, w = 0.0, bsum = 0.0, gs = 0.0;
         for (int b = 0; b < B; ++b) {
-            const double* r = red + ((int64_t)b * C + c) * 3;
+            const double* r = red + ((int64_t)b * C + c) * 4;
+            gs += r[3];
             const double* q = sg + 4 * (b * G + g);
             const double sc = film ? (double)film[(int64_t)b * film_ld + c] + 1.0 : 1.0;
             const double k = (double)gamma[c] * sc;
@@ -390,6 +410,7 @@ pw_bwd_finalize_kernel(const double* __restrict__ red, const double* __restrict_
         colsum[c] = (float)cs;
         gw[c] = (float)w;
         gb[c] = (float)bsum;
+        if (gsum) gsum[c] = (float)gs;
     }
 }
 
@@ -840,18 +861,18 @@ int tdb_pointwise_bwd_reduce(const void* g_out, int ld_g, const void* raw, int l
     dim3 grid((unsigned)ceil_div((int64_t)X * Y * Z, vox_per_block), (unsigned)B);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == TDB_BF16)
-        pw_bwd_reduce_kernel<bf16><<<grid, kThreads, (size_t)3 * C * sizeof(float), s>>>((const bf16*)g_out, ld_g, (const bf16*)raw, ld_raw, stats, gamma, beta,
+        pw_bwd_reduce_kernel<bf16><<<grid, kThreads, (size_t)4 * C * sizeof(float), s>>>((const bf16*)g_out, ld_g, (const bf16*)raw, ld_raw, stats, gamma, beta,
                                                               film, film_ld, red, gr, C, G, eps, flags, vox_per_block, FastDiv((uint32_t)Z), FastDiv((uint32_t)Y));
     else
-        pw_bwd_reduce_kernel<float><<<grid, kThreads, (size_t)3 * C * sizeof(float), s>>>((const float*)g_out, ld_g, (const float*)raw, ld_raw, stats, gamma,
+        pw_bwd_reduce_kernel<float><<<grid, kThreads, (size_t)4 * C * sizeof(float), s>>>((const float*)g_out, ld_g, (const float*)raw, ld_raw, stats, gamma,
                                                                beta, film, film_ld, red, gr, C, G, eps, flags, vox_per_block, FastDiv((uint32_t)Z), FastDiv((uint32_t)Y));
     TDB_CHECK_LAUNCH("tdb_pointwise_bwd_reduce");
     return 0;
 }
 
 int tdb_pointwise_bwd_finalize(const double* red, const double* stats, const float* gamma, const float* beta, const float* film,
-                               int film_ld, float* grp, float* colsum, float* gw, float* gb, float* dfilm, int dfilm_ld, int B,
-                               int X, int Y, int Z, int C, int G, float eps, void* stream) {
+                               int film_ld, float* grp, float* colsum, float* gw, float* gb, float* gsum, float* dfilm, int dfilm_ld,
+                               int B, int X, int Y, int Z, int C, int G, float eps, void* stream) {
     TDB_REQUIRE(red && stats && gamma && beta && grp && colsum && gw && gb, TDB_E_BADARG, "tdb_pointwise_bwd_finalize: null pointer");
     const size_t smem = (size_t)B * G * 4 * sizeof(double);
     TDB_REQUIRE(G >= 1 && C % G == 0 && smem <= 200 * 1024, TDB_E_UNSUPPORTED,
@@ -861,7 +882,7 @@ int tdb_pointwise_bwd_finalize(const double* red, const double* stats, const flo
         TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_pointwise_bwd_finalize: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
     pw_bwd_finalize_kernel<<<1, kThreads, smem, (cudaStream_t)stream>>>(
-        red, stats, gamma, beta, film, film_ld, grp, colsum, gw, gb, dfilm, dfilm_ld, B, C, G, (double)X * Y * Z, (double)eps);
+        red, stats, gamma, beta, film, film_ld, grp, colsum, gw, gb, gsum, dfilm, dfilm_ld, B, C, G, (double)X * Y * Z, (double)eps);
     TDB_CHECK_LAUNCH("tdb_pointwise_bwd_finalize");
     return 0;
 }

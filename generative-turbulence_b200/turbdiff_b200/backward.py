@@ -84,17 +84,19 @@ class BackwardProgram:
         B, C = p["B"], raw.C
         dev = raw.t.device
         film_ptr = None if film_view is None else film_view.data_ptr()
-        red = torch.zeros((B, C, 3), dtype=torch.float64, device=dev)
+        red = torch.zeros((B, C, 4), dtype=torch.float64, device=dev)
         call("tdb_pointwise_bwd_reduce", g_out.ptr, g_out.ld, raw.ptr, raw.ld, ptr(stats), ptr(norm.weight), ptr(norm.bias), film_ptr,
              eng.film_rows, red.data_ptr(), B, X, Y, Z, C, G, GN_EPS, flags, eng.dt, _lib.stream_ptr())
-        out = torch.empty((3, C), dtype=torch.float32, device=dev)
+        out = torch.empty((4, C), dtype=torch.float32, device=dev)
         grp = torch.empty((B, G, 2), dtype=torch.float32, device=dev)
         dfilm_ptr = None if d_film is None else d_film.data_ptr() + 4 * film_offset
         call("tdb_pointwise_bwd_finalize", red.data_ptr(), ptr(stats), ptr(norm.weight), ptr(norm.bias), film_ptr, eng.film_rows,
-             grp.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), dfilm_ptr, eng.film_rows, B, X, Y, Z, C, G,
+             grp.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), dfilm_ptr, eng.film_rows, B, X, Y, Z,
+             C, G,
              GN_EPS, _lib.stream_ptr())
         call("tdb_pointwise_bwd_apply", g_out.ptr, g_out.ld, raw.ptr, raw.ld, ptr(stats), ptr(norm.weight), ptr(norm.bias), film_ptr,
              eng.film_rows, grp.data_ptr(), d_raw.ptr, d_raw.ld, B, X, Y, Z, C, G, GN_EPS, flags, eng.dt, _lib.stream_ptr())
+        self._g_colsum = out[3]  # sum of g_out per channel: bias gradient of a 1x1 residual projection on the same output
         return out[1], out[2], out[0]
 
     def _add_interior(self, p, a: View, b: View):
@@ -122,6 +124,7 @@ class BackwardProgram:
 
         # block2: pointwise (norm, SiLU, + residual) then conv2
         gw, gb, bias2 = self._pw_bwd(p, g_out, sv["raw2"], p["stats"][slot + 1], blk.block2.norm, None, d_raw, PW_SILU, G)
+        g_out_colsum = self._g_colsum
         grads[f"{pre}.block2.norm.weight"] = gw
         grads[f"{pre}.block2.norm.bias"] = gb
         grads[f"{pre}.block2.conv.weight"] = self._wgrad(p, sv["act1"], d_raw, blk.block2.conv, 27, zero_halo=True)
@@ -144,7 +147,7 @@ class BackwardProgram:
         if bp.has_proj:
             # g_out is a folded gradient: tdb_halo_fold left its halo rows zero
             grads[f"{pre}.conv.weight"] = self._wgrad(p, x, g_out, blk.conv, 1, zero_halo=True)
-            grads[f"{pre}.conv.bias"] = self._colsum(p, g_out)
+            grads[f"{pre}.conv.bias"] = g_out_colsum  # from block2's reduction over the same g_out (no extra pass)
             g_res = self._tmp(p, lvl, x.C, "g_res")
             eng._conv(p, g_out, self._dgrad_weights(blk.conv, f"{name}.proj", lvl), None, g_res, 1, all_rows=True)
             self._add_interior(p, g_x, g_res)

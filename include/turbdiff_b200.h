@@ -247,10 +247,11 @@ TDB_API int tdb_masked_loss(const float* eps, const float* noise, const uint8_t*
  * (in place); the halo rows are then set to zero, so a folded gradient qualifies for TDB_WGRAD_ZERO_HALO. */
 TDB_API int tdb_halo_fold(void* g, int ld, int B, int X, int Y, int Z, int C, int dtype, void* stream);
 
-/* Backward of tdb_pointwise, pass 1: red[b][c] = (sum g_u, sum g_u*xhat, sum raw) over interior voxels in
- * double (pre-zeroed, B*C*3), where u is the forward pre-activation, g_u = g_out*silu'(u) (or g_out) and
+/* Backward of tdb_pointwise, pass 1: red[b][c] = (sum g_u, sum g_u*xhat, sum raw, sum g_out) over interior voxels in
+ * double (pre-zeroed, B*C*4), where u is the forward pre-activation, g_u = g_out*silu'(u) (or g_out) and
  * xhat = (raw-mean)*rstd.  g_out must already be folded.  (sum raw gives the host the per-channel sum of d_raw,
- * i.e. the bias gradient of the preceding convolution, without another pass.) */
+ * i.e. the bias gradient of the preceding convolution, without another pass; sum g_out is the bias gradient of a
+ * residual 1x1 projection added to the same block output.) */
 TDB_API int tdb_pointwise_bwd_reduce(const void* g_out, int ld_g, const void* raw, int ld_raw, const double* stats,
                              const float* gamma, const float* beta, const float* film, int film_ld, double* red,
                              int B, int X, int Y, int Z, int C, int G, float eps, unsigned flags, int dtype,
@@ -258,12 +259,12 @@ TDB_API int tdb_pointwise_bwd_reduce(const void* g_out, int ld_g, const void* ra
 
 /* Between the two passes (one block): from red and the forward moments `stats`, grp[b][g] = (m1, m2) for pass 2,
  * colsum[c] = sum of d_raw over samples and interior voxels (= bias gradient of the convolution that produced raw),
- * gw[c] / gb[c] = gradients of the GroupNorm weight / bias, and (dfilm != NULL) the FiLM gradients
+ * gw[c] / gb[c] = gradients of the GroupNorm weight / bias, gsum[c] (nullable) = sum of g_out, and (dfilm != NULL) the FiLM gradients
  * dfilm[b][c] = d scale, dfilm[b][C + c] = d shift (reference: autograd through ddpm.py:168-177). */
 TDB_API int tdb_pointwise_bwd_finalize(const double* red, const double* stats, const float* gamma, const float* beta,
                                const float* film, int film_ld, float* grp, float* colsum, float* gw, float* gb,
-                               float* dfilm, int dfilm_ld, int B, int X, int Y, int Z, int C, int G, float eps,
-                               void* stream);
+                               float* gsum, float* dfilm, int dfilm_ld, int B, int X, int Y, int Z, int C, int G,
+                               float eps, void* stream);
 
 /* Pass 2: d_raw = rstd*(k*g_u - m1 - xhat*m2) on interior rows and 0 on halo rows, k = gamma*(scale+1),
  * grp[b][g] = (m1, m2) = group means of k*A1 and k*A2 (fp32).  Without stats: d_raw = g_u. */
