@@ -329,7 +329,7 @@ def run_ours(args):
         # ncu (profiles/r01_launches_v52_b8.csv, r01_ncu_full_win_v40.json): the top kernel (row-window conv, 64->64
         # @194x50x50, B=8) moves 543 MB + 456 MB of DRAM traffic per launch = its algorithmic bytes (input read once, output written once)
         traffic = 1.0015e9 if (B == 8 and args.precision == "bf16") else None
-        roof = {"bound": "tensor", "kernel": "tcgen05 convolution family: conv3d_bf16_winz / _win / _fold2 / _fold / _tc kernels (all conv launches of one step)",
+        roof = {"bound": "tensor", "kernel": "tcgen05 convolution family: conv3d_bf16_winz / _win / _winp / _fold2 / _tc kernels (all conv launches of one step)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "traffic_of": "conv3d_bf16_winz_kernel<64,64> per launch (ncu dram__bytes_read+write, round-1 capture)" if traffic else None,
                 "peak_src": f"{pk['src']} bf16 sustained (kernel timed inside a long step)",
