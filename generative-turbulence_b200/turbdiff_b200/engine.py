@@ -90,6 +90,8 @@ class DenoiserEngine:
         self._plans = {}
         self._wcache = None
         self._wversion = None
+        self._wgen = 0        # bumped whenever _wcache is REPLACED: captured sampler graphs hold its addresses
+        self.graph_fallbacks = 0  # CUDA-graph captures that failed and fell back to the eager launch programs
         self._last_train_key = None
 
         m = model
@@ -141,6 +143,7 @@ class DenoiserEngine:
         w["film_w"] = torch.cat([self.blocks[n].blk.project_onto_scale_shift.weight.detach() for n in self.block_order]).t().contiguous().float()
         w["film_b"] = torch.cat([self.blocks[n].blk.project_onto_scale_shift.bias.detach() for n in self.block_order]).contiguous().float()
         self._wcache, self._wversion = w, ver
+        self._wgen += 1
         return w
 
     @staticmethod
@@ -501,15 +504,37 @@ class DenoiserEngine:
             }
         if c_local is not None:
             st["c_local"].copy_(c_local)
+        # the reference re-encodes C on every call (ddpm.py:496-501); the captured graph only rewrites the x half of the
+        # concat buffer, so the c_local half is re-encoded once per chain (forward_graphed) - a training forward or another
+        # chain with a different geometry may have overwritten it since
+        st["c_dirty"] = True
         return st
+
+    def _encode_c_half(self, st):
+        """encode_c_local(c_local) into its channel half of the level-0 concat buffer (one launch, no x half)."""
+        m = self.model
+        Fc = m.c_local_features
+        x_t = st["x_t"]
+        if Fc > 0:
+            B, F = x_t.shape[:2]
+            X, Y, Z = x_t.shape[2:]
+            p = self.plan(B, (X, Y, Z), x_t.device)
+            xin0 = p["xin0"]
+            call("tdb_encode_input", x_t.data_ptr(), ptr(st["c_local"]), m.encode_x.weight.data_ptr(), m.encode_x.bias.data_ptr(),
+                 ptr(m.encode_c_local.weight), ptr(m.encode_c_local.bias), xin0.ptr, xin0.ld, B, F, Fc, m.dim, X, Y, Z, 2, self.dt,
+                 _lib.stream_ptr())
+            p["c_valid"] = True
+        st["c_dirty"] = False
 
     def forward_graphed(self, st):
         """eps for the sampler state `st` (x_t, t_vec, c_local buffers); captures the graph on first use."""
         self._set_geometry(st["x_t"].shape[2:])
         self.weights()
         if not self.use_graph:
-            return self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=True)
-        if st["graph"] is None or st["wver"] != self._wversion:
+            static = not st.get("c_dirty", True)
+            st["c_dirty"] = False
+            return self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=static)
+        if st["graph"] is None or st["wver"] != self._wgen:
             # eager warm-up on a side stream (also (re)writes the c_local half), then capture
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -525,9 +550,14 @@ class DenoiserEngine:
 
                 warnings.warn(f"turbdiff_b200: CUDA-graph capture of the denoiser failed ({str(e)[:200]}); using the eager launch program")
                 self.use_graph = False
+                self.graph_fallbacks += 1
                 torch.cuda.synchronize()
-                return self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=True)
-            st["graph"], st["wver"] = g, self._wversion
+                st["c_dirty"] = False
+                return self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=False)
+            st["graph"], st["wver"] = g, self._wgen
+            st["c_dirty"] = False  # the warm-up wrote both halves from st["c_local"]
+        if st.get("c_dirty", True):
+            self._encode_c_half(st)
         st["graph"].replay()
         B = st["x_t"].shape[0]
         return self.plan(B, tuple(st["x_t"].shape[2:]), st["x_t"].device)["eps"]
@@ -557,6 +587,7 @@ class DenoiserEngine:
 
                 warnings.warn(f"turbdiff_b200: CUDA-graph capture of the training step failed ({str(e)[:200]}); using the eager launch programs")
                 self.train_graph = False
+                self.graph_fallbacks += 1
                 self._train_replay = None
                 torch.cuda.synchronize()
                 return self.forward(x, t, c_local, train=True)
@@ -602,8 +633,13 @@ class DenoiserEngine:
         # shape may load a module / allocate a workspace on this thread - legal, but rejected by the default "global" mode
         # (measured: the capture of the dim-16 test configuration was invalidated whenever nothing had warmed cuBLAS up)
         n0 = _lib.launch_count()
+        # the kernel-layout weights are re-derived from the parameters INSIDE the forward graph (every replay sees the
+        # parameters of that moment).  Those copies live in the graph's private pool and are only valid between the
+        # forward and the backward replay of one step, so the engine-level cache (what eager forwards and the sampler
+        # graphs use) is saved here and restored after the capture instead of being left pointing into the pool.
+        keep = (self._wcache, self._wversion)
         with torch.cuda.graph(g_f, pool=pool, capture_error_mode="relaxed"):
-            self._wcache = None  # the kernel-layout weights are re-derived from the parameters inside the graph
+            self._wcache = None
             eps = self.forward(xs, ts, cs, train=True)
         n1 = _lib.launch_count()
         named = list(self.model.named_parameters())
@@ -616,7 +652,10 @@ class DenoiserEngine:
             # then hands them out with a single copy instead of one per tensor
             torch._foreach_copy_(views, [grads[n].reshape(q.shape) for n, q in named])
         n2 = _lib.launch_count()
-        return {"sig": sig, "n_fwd": n1 - n0, "n_bwd": n2 - n1, "flat": flat, "sizes": sizes, "shapes": [q.shape for _, q in named], "x": xs, "t": ts, "c": cs, "g_eps": gs, "eps": eps, "fwd": g_f, "bwd": g_b, "grads": grads, "g_c_local": g_c}
+        pool_w = self._wcache  # kept alive by the returned record: the graphs hold raw addresses into it
+        self._wcache, self._wversion = keep
+        self._wgen += 1
+        return {"sig": sig, "n_fwd": n1 - n0, "n_bwd": n2 - n1, "flat": flat, "sizes": sizes, "shapes": [q.shape for _, q in named], "x": xs, "t": ts, "c": cs, "g_eps": gs, "eps": eps, "fwd": g_f, "bwd": g_b, "grads": grads, "g_c_local": g_c, "pool_w": pool_w}
 
     @staticmethod
     def to_ncdhw(v: View) -> torch.Tensor:

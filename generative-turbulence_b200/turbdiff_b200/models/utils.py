@@ -25,14 +25,17 @@ def inside_mask(cell_idx: torch.Tensor, nvox: int) -> torch.Tensor:
     """uint8 (nvox,) mask with 1 on the voxels listed in cell_idx (cached per index tensor)."""
     _lib.require_cuda(cell_idx, "cell_idx")
     key = (cell_idx.data_ptr(), cell_idx.numel(), cell_idx._version, nvox, str(cell_idx.device))
-    m = _mask_cache.get(key)
-    if m is None:
-        if len(_mask_cache) > 64:
-            _mask_cache.clear()
-        idx = cell_idx.to(torch.int64).contiguous()
-        m = torch.zeros(nvox, dtype=torch.uint8, device=cell_idx.device)
-        call("tdb_build_mask", idx.data_ptr(), m.data_ptr(), idx.numel(), nvox, _lib.stream_ptr())
-        _mask_cache[key] = m
+    hit = _mask_cache.get(key)
+    # an entry is valid only for the very tensor object it was built from: the cache keeps that tensor alive, so its
+    # address cannot be recycled for another geometry with the same cell count while the entry exists
+    if hit is not None and hit[0] is cell_idx:
+        return hit[1]
+    if len(_mask_cache) >= 8:
+        _mask_cache.pop(next(iter(_mask_cache)))
+    idx = cell_idx.to(torch.int64).contiguous()
+    m = torch.zeros(nvox, dtype=torch.uint8, device=cell_idx.device)
+    call("tdb_build_mask", idx.data_ptr(), m.data_ptr(), idx.numel(), nvox, _lib.stream_ptr())
+    _mask_cache[key] = (cell_idx, m)
     return m
 
 

@@ -31,12 +31,13 @@ class FusedRAdam(torch.optim.Optimizer):
 
     def _table(self, gi, params):
         """Device pointer / chunk tables of one parameter group, rebuilt only when an address changed."""
-        sig = tuple((p.data_ptr(), p.grad.data_ptr()) for p in params)
+        st = [self.state[p] for p in params]
+        # moments are part of the signature: load_state_dict() replaces them without touching the parameters
+        sig = tuple((p.data_ptr(), p.grad.data_ptr(), s["exp_avg"].data_ptr(), s["exp_avg_sq"].data_ptr()) for p, s in zip(params, st))
         tb = self._tables.get(gi)
         if tb is not None and tb["sig"] == sig:
             return tb
         dev = params[0].device
-        st = [self.state[p] for p in params]
         ptrs = [[p.data_ptr() for p in params], [p.grad.data_ptr() for p in params], [s["exp_avg"].data_ptr() for s in st],
                 [s["exp_avg_sq"].data_ptr() for s in st], [p.numel() for p in params]]
         chunk_tensor, chunk_off = [], []
@@ -49,6 +50,10 @@ class FusedRAdam(torch.optim.Optimizer):
               "chunk_off": torch.tensor(chunk_off, dtype=torch.int64).to(dev, non_blocking=True), "n_chunks": len(chunk_tensor)}
         self._tables[gi] = tb
         return tb
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tables = {}  # the moment tensors were replaced
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -103,4 +108,7 @@ class FusedRAdam(torch.optim.Optimizer):
                  tb["chunk_tensor"].data_ptr(), tb["chunk_off"].data_ptr(), tb["n_chunks"], CHUNK, None if sq is None else sq.data_ptr(),
                  float(self.max_grad_norm or 0.0), float(step_size), float(beta1), float(beta2), float(group["eps"]),
                  float(group["weight_decay"]), rectified, s)
+            # the kernel wrote the parameters through raw pointers: tell autograd (and every cache keyed on
+            # Tensor._version, e.g. the engine's kernel-layout weights) that they changed, like an in-place torch op would
+            torch.autograd.graph.increment_version(params)
         return loss

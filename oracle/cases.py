@@ -51,3 +51,30 @@ def case_inputs(case):
     table = rng.standard_normal((6, spec.c_local_features)).astype(np.float32)
     c_local = np.ascontiguousarray(grid_ref.cell_type_embedding(geo, table))
     return torch.from_numpy(x), torch.from_numpy(t), torch.from_numpy(c_local), geo
+
+
+# ---- full shapes configuration (BASELINE.json configs[1]/[2]) --------------------------------------------------------
+SHAPES_T = 500  # config/model/diffusion.yaml:12 of the reference
+SHAPES_SEED = 0          # synth_state_dict seed of the full-size fixtures
+SHAPES_INPUT_SEED = 100  # turbdiff_b200.synthetic.synthetic_inputs(1, SHAPES_INPUT_SEED)
+SHAPES_FWD_T = 137       # timestep of the full-size forward fixture
+
+
+def shapes_spec(T: int = SHAPES_T) -> UNetSpec:
+    return UNetSpec(in_features=4, out_features=4, c_local_features=4, timesteps=T, dim=32, u_net_levels=4, groups=8)
+
+
+def sub3(v):
+    """Strided sub-sample of the trailing three (spatial) axes used by the full-size fixtures (every 3rd voxel)."""
+    return v[..., ::3, ::3, ::3]
+
+
+def tap_sample(v):
+    """Sub-sample of a per-block tap (B, C, X, Y, Z): every 4th channel, every 5th voxel per axis (offset 1)."""
+    return v[:, ::4, 1::5, 1::5, 1::5]
+
+
+def grad_sample(g):
+    """<= 1024 evenly strided entries of a flattened gradient tensor."""
+    flat = g.reshape(-1)
+    return flat[:: max(1, flat.numel() // 1024)][:1024]

@@ -62,7 +62,8 @@ from turbdiff.models.cell_type_embeddings import CellTypeLearnedEmbedding  # noq
 from turbdiff.models.conditioning import Conditioning  # noqa: E402
 
 from oracle import grid_ref  # noqa: E402
-from oracle.cases import CASES, case_inputs  # noqa: E402
+from oracle.cases import (CASES, SHAPES_FWD_T, SHAPES_INPUT_SEED, SHAPES_SEED, SHAPES_T, case_inputs, grad_sample,  # noqa: E402
+                          shapes_spec, sub3, tap_sample)
 from oracle.unet_ref import UNetSpec, state_dict_layout, synth_state_dict  # noqa: E402
 
 NORM_NAME = {8: "group", 1: "layer", None: "instance"}
@@ -238,13 +239,74 @@ def gen_grid():
     print("grid", grid.shape, np.bincount(out["cell_types"].ravel(), minlength=6))
 
 
+def gen_shapes():
+    """The FULL shapes configuration (BASELINE.json configs[1]/[2]: dim 32, 4 levels, 194x50x50 padded grid, u+p,
+    55.2 M parameters) through the unmodified reference at B=1: denoiser output + per-block taps (checksums and strided
+    sub-samples), one training loss with every parameter gradient (checksums + sub-samples), and a 3-step sampling
+    chain.  Inputs: turbdiff_b200.synthetic.synthetic_inputs(1, 100) (numpy-seeded, no model code involved), weights
+    oracle.unet_ref.synth_state_dict(spec, 0).  ~25 s of CPU time, ~6 GB of memory."""
+    sys.path.insert(0, str(ROOT / "generative-turbulence_b200"))
+    from turbdiff_b200.synthetic import synthetic_inputs
+
+    spec = shapes_spec()
+    sd = synth_state_dict(spec, SHAPES_SEED)
+    geo, x, c_local = synthetic_inputs(1, SHAPES_INPUT_SEED)
+    cell_idx = torch.from_numpy(geo.cell_idx)
+    C = {Conditioning.Type.CELL_TYPE: c_local}
+    t = torch.tensor([SHAPES_FWD_T], dtype=torch.long)
+    out = {"t": t.numpy()}
+    m = build_ref_model(spec, sd)
+    taps, hooks = {}, []
+
+    def grab(name):
+        def hook(_mod, _inp, outp):
+            taps[name] = outp.detach()
+        return hook
+
+    un = m.u_net
+    for i, blk in enumerate(un.downsampling_blocks):
+        hooks.append(blk.register_forward_hook(grab(f"down{i}")))
+    for i, blk in enumerate(un.upsampling_blocks):
+        hooks.append(blk.register_forward_hook(grab(f"up{i}")))
+    for i in range(3):
+        hooks.append(un.center_block[i].register_forward_hook(grab(f"center{i}")))
+    hooks.append(m.decode[0].register_forward_hook(grab("decode0")))
+    with torch.no_grad():
+        y = m(x, t, C)
+    for h in hooks:
+        h.remove()
+    out["out/sub"] = sub3(y).numpy()
+    out["out/sum"] = np.array([y.double().sum().item(), y.double().pow(2).sum().item()])
+    for k, v in taps.items():
+        out[f"tap/{k}/sub"] = tap_sample(v).numpy()
+        out[f"tap/{k}/sum"] = np.array([v.double().sum().item(), v.double().pow(2).sum().item()])
+    print("shapes forward", tuple(y.shape), float(y.abs().mean()))
+
+    gd = ref.GaussianDiffusion(m, timesteps=SHAPES_T, beta_schedule="log-snr-linear", loss_type="l2", noise_bcs=True)
+    torch.manual_seed(77)
+    s = gd.p_sample_loop(x, C, cell_idx, start_from=3)
+    out["sample_from3/sub"] = sub3(s).numpy()
+    out["sample_from3/sum"] = np.array([s.double().sum().item(), s.double().pow(2).sum().item()])
+    print("shapes 3-step chain", float(s.abs().mean()))
+
+    m.train()
+    torch.manual_seed(4321)
+    loss, tdraw = gd(x, C, _MD(cell_idx), None)
+    loss.backward()
+    out["loss"] = np.array(loss.item())
+    out["loss_t"] = tdraw.numpy()
+    for k, p in m.named_parameters():
+        g = p.grad
+        out[f"grad/{k}/sub"] = grad_sample(g).numpy()
+        out[f"grad/{k}/sum"] = np.array([g.double().sum().item(), g.double().pow(2).sum().item()])
+    print("shapes loss", loss.item(), "t", tdraw.tolist())
+    np.savez_compressed(HERE / "shapes.npz", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    gen_layout()
-    gen_schedules()
-    gen_time_embedding()
-    gen_grid()
-    gen_unet()
-    gen_diffusion()
+    todo = sys.argv[1:] or ["layout", "schedules", "time_embedding", "grid", "unet", "diffusion", "shapes"]
+    for name in todo:
+        globals()[f"gen_{name}"]()
     for f in sorted(HERE.glob("*.npz")):
         print(f.name, f.stat().st_size // 1024, "KiB")

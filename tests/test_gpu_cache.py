@@ -1,0 +1,212 @@
+"""Derived-state hazards of the launch-program engine (round-1 review): kernel-layout weight cache after an optimiser
+step, sampler graphs across a training-graph capture, the cached c_local half of the input buffer across chains with
+different conditioning, the inside-mask cache under address reuse, FusedRAdam.load_state_dict.
+
+Reference behaviour being matched: turbdiff/models/diffusion.py:160-174 (training steps followed by validation
+sampling with the updated weights) and ddpm.py:496-501 (C is re-encoded on every call)."""
+
+import numpy as np
+import pytest
+import torch
+
+from util import cpu_seeded_randn, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(case, precision, sd=None):
+    from oracle.unet_ref import synth_state_dict
+    from turbdiff_b200 import DenoisingModel
+
+    spec = case["spec"]
+    m = DenoisingModel(in_features=spec.in_features, out_features=spec.out_features, c_local_features=spec.c_local_features,
+                       c_global_features=0, timesteps=spec.timesteps, dim=spec.dim, u_net_levels=spec.u_net_levels,
+                       norm_type="group", precision=precision)
+    m.load_state_dict(sd if sd is not None else synth_state_dict(spec, case["seed"]), strict=True)
+    return m.cuda()
+
+
+def _diffusion(m, spec):
+    from turbdiff_b200 import GaussianDiffusion
+
+    return GaussianDiffusion(m, timesteps=spec.timesteps, beta_schedule="log-snr-linear", loss_type="l2", noise_bcs=True).cuda()
+
+
+def _key():
+    from turbdiff_b200.models.conditioning import Conditioning
+
+    return Conditioning.Type.CELL_TYPE
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("train_graph", [True, False])
+@pytest.mark.parametrize("optimizer", ["fused", "torch"])
+def test_sample_train_sample_uses_updated_weights(precision, train_graph, optimizer):
+    """p_sample_loop -> 2 optimiser steps -> eval forward + p_sample_loop must equal a model rebuilt from the updated
+    state_dict (fresh engine, fresh caches, fresh graphs): bit-exact, the kernels and the weights are the same."""
+    from oracle.cases import CASES, case_inputs
+    from turbdiff_b200.optim import FusedRAdam
+
+    case = CASES["tiny"]
+    spec = case["spec"]
+    x, t, c_local, geo = case_inputs(case)
+    x, t, c_local = x.cuda(), t.cuda(), c_local.cuda()
+    idx = torch.from_numpy(geo.cell_idx).cuda()
+    C = {_key(): c_local}
+
+    m = _model(case, precision)
+    m.engine().train_graph = train_graph
+    gd = _diffusion(m, spec)
+    m.eval()
+    with cpu_seeded_randn(5):
+        s0 = gd.p_sample_loop(x, C, idx, start_from=2)  # captures the sampler graph with the initial weights
+    with torch.no_grad():
+        e0 = m(x, t, C)
+
+    class MD:
+        cell_idx = idx
+
+    if optimizer == "fused":
+        opt = FusedRAdam(m.parameters(), lr=3e-3, max_grad_norm=0.1)  # large lr: two steps must visibly move the output
+    else:
+        opt = torch.optim.RAdam(m.parameters(), lr=3e-3)
+    m.train()
+    for step in range(2):
+        opt.zero_grad(set_to_none=True)
+        with cpu_seeded_randn(100 + step):
+            loss, _ = gd(x, C, MD, None)
+        loss.backward()
+        opt.step()
+    m.eval()
+    assert m.engine().graph_fallbacks == 0, "a CUDA-graph capture fell back to the eager launch program"
+
+    with torch.no_grad():
+        e1 = m(x, t, C)
+    with cpu_seeded_randn(5):
+        s1 = gd.p_sample_loop(x, C, idx, start_from=2)
+    assert rel_l2(e1, e0) > 1e-3, "the optimiser steps did not change the eval forward: stale kernel-layout weights"
+
+    fresh = _model(case, precision, sd={k: v.detach().clone() for k, v in m.state_dict().items()}).eval()
+    gdf = _diffusion(fresh, spec)
+    with torch.no_grad():
+        ef = fresh(x, t, C)
+    with cpu_seeded_randn(5):
+        sf = gdf.p_sample_loop(x, C, idx, start_from=2)
+    # same kernels, same weights: equal up to the summation order of the split-K atomics of the bottleneck convolutions
+    assert rel_l2(e1, ef) < 1e-5, rel_l2(e1, ef)
+    assert rel_l2(s1, sf) < 1e-5, rel_l2(s1, sf)
+    assert rel_l2(s1, s0) > 1e-3
+
+    # one more training step after the sampling: the training graph must still see the live parameters
+    m.train()
+    opt.zero_grad(set_to_none=True)
+    with cpu_seeded_randn(200):
+        loss_a, _ = gd(x, C, MD, None)
+    loss_a.backward()
+    fresh.train()
+    with cpu_seeded_randn(200):
+        loss_b, _ = gdf(x, C, MD, None)
+    loss_b.backward()
+    assert abs(float(loss_a) - float(loss_b)) < 1e-5 * abs(float(loss_b))
+    ga = dict(m.named_parameters())
+    for n, q in fresh.named_parameters():
+        assert rel_l2(ga[n].grad, q.grad) < 1e-4, n
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_sampling_twice_with_different_conditioning(precision, use_graph):
+    """Same (B, grid) plan, different C: the second chain must be conditioned on ITS C (ddpm.py:496-501), also when a
+    training forward with a third C ran in between."""
+    from oracle.cases import CASES, case_inputs
+
+    case = CASES["tiny"]
+    spec = case["spec"]
+    x, t, c_local, geo = case_inputs(case)
+    x, t = x.cuda(), t.cuda()
+    idx = torch.from_numpy(geo.cell_idx).cuda()
+    c1 = c_local.cuda()
+    c2 = (c_local.flip(1) * 1.7 + 0.3).contiguous().cuda()
+    c3 = torch.randn_like(c1)
+
+    m = _model(case, precision).eval()
+    m.engine().use_graph = use_graph
+    gd = _diffusion(m, spec)
+    with cpu_seeded_randn(9):
+        a1 = gd.p_sample_loop(x, {_key(): c1}, idx, start_from=3)
+    with cpu_seeded_randn(9):
+        a2 = gd.p_sample_loop(x, {_key(): c2}, idx, start_from=3)
+
+    class MD:
+        cell_idx = idx
+
+    m.train()
+    with cpu_seeded_randn(3):
+        loss, _ = gd(x, {_key(): c3}, MD, None)  # rewrites both halves of the input buffer with c3
+    loss.backward()
+    m.eval()
+    with cpu_seeded_randn(9):
+        a1_again = gd.p_sample_loop(x, {_key(): c1}, idx, start_from=3)
+
+    fresh = _model(case, precision).eval()
+    fresh.engine().use_graph = use_graph
+    gdf = _diffusion(fresh, spec)
+    with cpu_seeded_randn(9):
+        b2 = gdf.p_sample_loop(x, {_key(): c2}, idx, start_from=3)
+    assert rel_l2(a1, a2) > 1e-3
+    assert rel_l2(a2, b2) < 1e-5, rel_l2(a2, b2)
+    assert rel_l2(a1_again, a1) < 1e-5, rel_l2(a1_again, a1)
+
+
+def test_inside_mask_cache_survives_address_reuse():
+    """Two geometries with the same cell count: a fresh index tensor on the recycled address must get ITS mask."""
+    from turbdiff_b200.models.utils import inside_mask
+
+    nvox, n = 4096, 1000
+    rng = np.random.Generator(np.random.PCG64(1))
+    for trial in range(4):
+        perm = rng.permutation(nvox)[:n].astype(np.int64)
+        idx = torch.from_numpy(perm).cuda()
+        addr = idx.data_ptr()
+        m = inside_mask(idx, nvox)
+        want = np.zeros(nvox, dtype=np.uint8)
+        want[perm] = 1
+        np.testing.assert_array_equal(m.cpu().numpy(), want)
+        del idx  # the allocator is now free to hand the same block to the next trial's tensor
+    # a hit on the same live tensor returns the cached mask; an in-place edit invalidates it
+    idx = torch.arange(n, device="cuda")
+    m1 = inside_mask(idx, nvox)
+    assert inside_mask(idx, nvox) is m1
+    idx += 7
+    m2 = inside_mask(idx, nvox)
+    assert int(m2[:7].sum()) == 0 and int(m2.sum()) == n
+
+
+def test_fused_radam_load_state_dict_replaces_moments():
+    from turbdiff_b200.optim import FusedRAdam
+
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(257, 33, device="cuda")), torch.nn.Parameter(torch.randn(1000, device="cuda"))]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    a, b = FusedRAdam(ps, lr=1e-2), torch.optim.RAdam(ref, lr=1e-2)
+
+    def step(seed):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        for p, q in zip(ps, ref):
+            p.grad = torch.randn(p.shape, device="cuda", generator=g)
+            q.grad = p.grad.clone()
+        a.step()
+        b.step()
+
+    for i in range(7):
+        step(i)
+    v0 = ps[0]._version
+    # reload the state of the torch optimiser (new moment tensors, same parameters), then keep stepping
+    a.load_state_dict(b.state_dict())
+    for i in range(7, 10):
+        step(i)
+    assert ps[0]._version > v0  # raw-pointer updates are reported to autograd's version counter
+    for p, q in zip(ps, ref):
+        assert rel_l2(p, q) < 1e-6
+    for p, q in zip(ps, ref):
+        assert rel_l2(a.state[p]["exp_avg_sq"], b.state[q]["exp_avg_sq"]) < 1e-6

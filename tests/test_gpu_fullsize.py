@@ -1,5 +1,10 @@
 """Parity at BASELINE.json's FULL shapes configuration (194x50x50 padded grid, u+p, dim 32, 4 levels, 55.2 M
-parameters), where the CPU oracle is too slow to be the checker.  The checks are size-independent properties:
+parameters).
+
+First against the UNMODIFIED REFERENCE: tests/golden/shapes.npz holds the reference's full-size denoiser output, its
+twelve per-block taps, a 3-step sampling chain and one training loss with all 139 parameter gradients (strided
+sub-samples + checksums, tests/golden/make_golden.py gen_shapes); fp32 path <= 1e-5 per block, bf16 path <= 2e-2
+(BASELINE.json north_star).  Then size-independent properties:
 
 * the bf16 tensor-core path against the fp32 parity path of the same library (the fp32 path is pinned to the
   reference's golden vectors at small sizes; tolerance = BASELINE north_star's 2e-2);
@@ -139,3 +144,104 @@ def test_full_size_gradients(full):
     fd = (lp - lm) / (2 * h)
     print("full-size directional derivative: analytic", gnorm, "finite difference", fd, "loss", l32)
     assert abs(fd - gnorm) <= 5e-2 * gnorm
+
+
+# ---- against the unmodified reference at full size (tests/golden/shapes.npz) ------------------------------------------
+
+
+@pytest.fixture(scope="module")
+def shapes():
+    from oracle.cases import SHAPES_INPUT_SEED, SHAPES_SEED, SHAPES_T, shapes_spec
+    from oracle.unet_ref import synth_state_dict
+    from turbdiff_b200 import DenoisingModel, GaussianDiffusion
+    from turbdiff_b200.synthetic import synthetic_inputs
+
+    sd = synth_state_dict(shapes_spec(), SHAPES_SEED)
+    geo, x, c_local = synthetic_inputs(1, SHAPES_INPUT_SEED)
+
+    def make(precision):
+        m = DenoisingModel(in_features=4, out_features=4, c_local_features=4, c_global_features=0, timesteps=SHAPES_T, dim=32,
+                           u_net_levels=4, norm_type="group", precision=precision)
+        m.load_state_dict(sd, strict=True)
+        m = m.cuda().eval()
+        gd = GaussianDiffusion(m, timesteps=SHAPES_T, beta_schedule="log-snr-linear", loss_type="l2", noise_bcs=True).cuda()
+        return m, gd
+
+    return {"geo": geo, "x": x.cuda(), "c_local": c_local.cuda(), "idx": torch.from_numpy(geo.cell_idx).cuda(), "make": make}
+
+
+TOL = {"fp32": 1e-5, "bf16": 2e-2}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_size_forward_matches_reference_golden(golden, shapes, precision):
+    """DenoisingModel.forward (ddpm.py:477-505) at 194x50x50 / 4 levels / 512-1024 channels: output and every block."""
+    from oracle.cases import SHAPES_FWD_T, sub3, tap_sample
+
+    g = golden["shapes"]
+    m, _ = shapes["make"](precision)
+    t = torch.tensor([SHAPES_FWD_T], dtype=torch.long, device="cuda")
+    taps = {}
+    with torch.no_grad():
+        eps = m.engine().forward(shapes["x"], t, shapes["c_local"], taps=taps).clone()
+    errs = {"out": rel_l2(sub3(eps), g["out/sub"])}
+    for name, v in taps.items():
+        errs[name] = rel_l2(tap_sample(v), g[f"tap/{name}/sub"])
+        np.testing.assert_allclose(v.double().pow(2).sum().item(), g[f"tap/{name}/sum"][1], rtol=1e-4 if precision == "fp32" else 2e-2,
+                                   err_msg=name)
+    print("full-size vs reference", precision, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert len(taps) == 12
+    assert max(errs.values()) < TOL[precision], errs
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_size_sampling_chain_matches_reference_golden(golden, shapes, precision):
+    """p_sample_loop(start_from=3) (ddpm.py:767-816) on the reference's noise stream."""
+    from oracle.cases import sub3
+    from util import cpu_seeded_randn
+
+    g = golden["shapes"]
+    _, gd = shapes["make"](precision)
+    C = {_key(): shapes["c_local"]}
+    with cpu_seeded_randn(77):
+        s = gd.p_sample_loop(shapes["x"], C, shapes["idx"], start_from=3)
+    err = rel_l2(sub3(s), g["sample_from3/sub"])
+    print("full-size 3-step chain vs reference", precision, err)
+    assert err < (2e-5 if precision == "fp32" else 2e-2)
+    np.testing.assert_allclose(s.double().pow(2).sum().item(), g["sample_from3/sum"][1], rtol=1e-4 if precision == "fp32" else 2e-2)
+
+
+GRAD_TOL = {"fp32": 2e-4, "bf16": 4e-2}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_size_training_step_matches_reference_golden(golden, shapes, precision):
+    """GaussianDiffusion.forward + loss.backward() (ddpm.py:833-882): loss and every one of the 139 gradients."""
+    from oracle.cases import grad_sample
+    from util import cpu_seeded_randn
+
+    g = golden["shapes"]
+    m, gd = shapes["make"](precision)
+    m.train()
+
+    class MD:
+        cell_idx = shapes["idx"]
+
+    with cpu_seeded_randn(4321):
+        loss, t = gd(shapes["x"], {_key(): shapes["c_local"]}, MD, None)
+    np.testing.assert_array_equal(t.cpu().numpy(), g["loss_t"])
+    np.testing.assert_allclose(loss.item(), g["loss"], rtol=2e-5 if precision == "fp32" else 2e-2)
+    loss.backward()
+    assert m.engine().graph_fallbacks == 0
+    errs = {}
+    for k, p in m.named_parameters():
+        want = g[f"grad/{k}/sub"]
+        if np.abs(want).max() < 1e-7:  # conv bias in front of GroupNorm: zero up to rounding noise
+            assert float(p.grad.abs().max()) < 1e-4, k
+            continue
+        errs[k] = rel_l2(grad_sample(p.grad), want)
+        np.testing.assert_allclose(p.grad.double().pow(2).sum().item(), g[f"grad/{k}/sum"][1], rtol=1e-3 if precision == "fp32" else 8e-2,
+                                   err_msg=k)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+    print("full-size gradients vs reference", precision, [(k, f"{v:.2e}") for k, v in worst])
+    assert worst[0][1] < GRAD_TOL[precision], worst

@@ -170,3 +170,59 @@ def test_training_loss_and_grads(golden, cname, noise_bcs):
         d1, _, x, idx = _diffusion(cname, noise_bcs, "l1")
         torch.manual_seed(4321)
         np.testing.assert_allclose(d1.forward(x, idx)[0].item(), g[f"{tag}/loss_l1"], rtol=1e-5)
+
+
+# ---- the FULL shapes configuration (194x50x50, 4 levels, 55.2 M parameters): oracle vs the reference's golden ---------
+
+
+@pytest.fixture(scope="module")
+def shapes_case():
+    from oracle.cases import SHAPES_INPUT_SEED, SHAPES_SEED, shapes_spec
+    from turbdiff_b200.synthetic import synthetic_inputs
+
+    spec = shapes_spec()
+    geo, x, c_local = synthetic_inputs(1, SHAPES_INPUT_SEED)
+    return spec, synth_state_dict(spec, SHAPES_SEED), geo, x, c_local
+
+
+def test_full_size_denoiser_forward(golden, shapes_case):
+    from oracle.cases import SHAPES_FWD_T, sub3, tap_sample
+
+    g = golden["shapes"]
+    spec, sd, geo, x, c_local = shapes_case
+    taps = {}
+    with torch.no_grad():
+        y = denoiser_forward(sd, spec, x, torch.tensor([SHAPES_FWD_T]), c_local, taps)
+    assert y.shape == (1, 4, 194, 50, 50)
+    assert rel_l2(sub3(y), g["out/sub"]) < 1e-5
+    np.testing.assert_allclose(y.double().pow(2).sum().item(), g["out/sum"][1], rtol=1e-4)
+    names = [k.split("/")[1] for k in g.files if k.startswith("tap/") and k.endswith("/sub")]
+    assert len(names) == 12
+    for name in names:
+        assert rel_l2(tap_sample(taps[name]), g[f"tap/{name}/sub"]) < 1e-5, name
+        np.testing.assert_allclose(taps[name].double().pow(2).sum().item(), g[f"tap/{name}/sum"][1], rtol=1e-4, err_msg=name)
+
+
+def test_full_size_sampling_and_training_step(golden, shapes_case):
+    from oracle.cases import SHAPES_T, grad_sample, sub3
+
+    g = golden["shapes"]
+    spec, sd, geo, x, c_local = shapes_case
+    sd = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    idx = torch.from_numpy(geo.cell_idx)
+    d = DiffusionRef(lambda x_t, tt: denoiser_forward(sd, spec, x_t, tt, c_local), timesteps=SHAPES_T, beta_schedule="log-snr-linear",
+                     loss_type="l2", noise_bcs=True)
+    torch.manual_seed(77)
+    with torch.no_grad():
+        s = d.sample_loop(x, idx, start_from=3)
+    assert rel_l2(sub3(s), g["sample_from3/sub"]) < 1e-5
+    torch.manual_seed(4321)
+    loss, t = d.forward(x, idx)
+    np.testing.assert_array_equal(t.numpy(), g["loss_t"])
+    np.testing.assert_allclose(loss.item(), g["loss"], rtol=1e-5)
+    loss.backward()
+    for k, p in sd.items():
+        want = g[f"grad/{k}/sub"]
+        if np.abs(want).max() < 1e-7:  # conv bias in front of GroupNorm: exactly zero up to rounding noise
+            continue
+        assert rel_l2(grad_sample(p.grad), want) < 2e-4, k
