@@ -2,8 +2,9 @@
 """Benchmark of the TurbDiff denoising hot path (BASELINE.json metric: DDPM samples/sec at
 192x48x48 on 1/2/4/8 B200).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
-    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
+    python bench.py --gpus N --steps K --warmup W                # this repo's sm_100a path
+    python bench.py --impl reference --steps K --warmup W        # the UNMODIFIED reference on the host cores (CPU)
+    python bench.py --impl reference-gpu --steps K --warmup W    # the unmodified reference on one B200 (torch eager)
 
 One "step" = one ancestral-sampling step of the shapes-config model (dim 32, 4 levels, padded grid
 194x50x50, u+p) over a batch of B samples per GPU: U-Net forward, two Gaussian draws and the fused
@@ -40,9 +41,9 @@ UNIT = "samples/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--batch", type=int, default=8, help="samples per GPU per sampling step (configs[2]: 64 samples over 8 GPUs)")
     ap.add_argument("--train-batch", type=int, default=4, help="samples per GPU per training step (configs[1]: batch 4)")
     ap.add_argument("--timesteps", type=int, default=1000, help="T of the sampled chain (BASELINE configs[2]: 1000)")
@@ -50,6 +51,9 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=16, help="chain length of one end-to-end public-API call")
     ap.add_argument("--train-steps", type=int, default=5, help="timed training steps (configs[1]/[3]: fwd+bwd+all-reduce+optimizer); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the gpu_reference block (the reference under torch eager on this GPU)")
+    ap.add_argument("--ref-mode", default="tf32", choices=["tf32", "bf16", "fp32"], help="--impl reference-gpu: TF32 (the reference's "
+                    "shapes experiment, matmul_precision=medium), bf16 autocast, or strict fp32")
     ap.add_argument("--no-graph", action="store_true")
     return ap.parse_args()
 
@@ -135,49 +139,149 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "power_w": statistics.median(pw) if pw else None}
 
 
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def workload(T):
+    return f"configs[2] DDPM ancestral sampling, shapes config 194x50x50 u+p (dim 32, 4 levels, 55.2M params), T={T}"
+
+
+def build_reference(T, device, seed=0):
+    """The unmodified reference's DenoisingModel + GaussianDiffusion (oracle/ref_shim.py) at the shapes configuration
+    (config/model/diffusion.yaml of the reference), random init under torch.manual_seed(seed)."""
+    from oracle import ref_shim
+
+    ns = ref_shim.load()
+    torch.manual_seed(seed)
+    m = ns.ddpm.DenoisingModel(in_features=4, out_features=4, c_local_features=4, c_global_features=0, timesteps=T, dim=32,
+                               u_net_levels=4, norm_type="group")
+    gd = ns.ddpm.GaussianDiffusion(m, timesteps=T, beta_schedule="log-snr-linear", loss_type="l2", noise_bcs=True)
+    return ns, gd.to(device).eval()
+
+
 def time_cpu_reference(T, n_steps, warm, threads=None):
-    """The reference algorithm (CPU oracle port: oracle/unet_ref.py + oracle/diffusion_ref.py) on the host
-    cores: B=1 denoise steps of the shapes config.  Returns (seconds per step, cores)."""
+    """The reference's own CPU path of the hot loop on the host cores: `GaussianDiffusion.p_sample_loop` (ddpm.py:767-816)
+    of the UNMODIFIED reference (kind "reference": /root/reference or the oracle/_ref install) over `n_steps` ancestral
+    steps of ONE sample of the shapes config; the CPU oracle port (kind "port") only if the reference is not installed.
+    torchrun exports OMP_NUM_THREADS=1, so the thread count is set explicitly to every host core this process may use.
+    Returns (seconds per step, threads, kind)."""
+    from oracle import ref_shim
+
+    threads = threads or host_cores()
+    torch.set_num_threads(threads)
+    geo, x, c_local = synthetic_inputs(1, 1)
+    idx = torch.from_numpy(geo.cell_idx)
+    if ref_shim.available():
+        ns, gd = build_reference(T, "cpu")
+        C = {ns.Conditioning.Type.CELL_TYPE: c_local}
+        with torch.no_grad():
+            if warm > 0:
+                gd.p_sample_loop(x, C, idx, start_from=warm)
+            t0 = time.perf_counter()
+            gd.p_sample_loop(x, C, idx, start_from=n_steps)
+            sec = (time.perf_counter() - t0) / n_steps
+        return sec, torch.get_num_threads(), "reference"
     from oracle.diffusion_ref import DiffusionRef
     from oracle.unet_ref import denoiser_forward, synth_state_dict
 
-    if threads:
-        torch.set_num_threads(threads)
     spec = shapes_spec(T)
     sd = synth_state_dict(spec, 0)
-    geo, x, c_local = synthetic_inputs(1, 1)
-    idx = torch.from_numpy(geo.cell_idx)
     d = DiffusionRef(lambda xt, tt: denoiser_forward(sd, spec, xt, tt, c_local), timesteps=T, beta_schedule="log-snr-linear", noise_bcs=True)
-    times = []
     with torch.no_grad():
-        xt = torch.randn_like(x)
-        for i in range(warm + n_steps):
-            t0 = time.perf_counter()
-            tt = torch.full((1,), T - 1 - i, dtype=torch.long)
-            _, _, mean, log_var = d.predictions(xt, tt, idx)
-            z = torch.randn_like(xt)
-            xt = mean + (log_var / 2).exp() * z
-            from oracle.diffusion_ref import where_cells
+        if warm > 0:
+            d.sample_loop(x, idx, start_from=warm)
+        t0 = time.perf_counter()
+        d.sample_loop(x, idx, start_from=n_steps)
+        sec = (time.perf_counter() - t0) / n_steps
+    return sec, torch.get_num_threads(), "port"
 
-            xt = where_cells(idx, xt, d.q_sample(x, tt, torch.randn_like(x)))
-            if i >= warm:
-                times.append(time.perf_counter() - t0)
-    return sum(times) / len(times), torch.get_num_threads()
+
+def time_gpu_reference(T, B, n_steps, warm, mode, dev):
+    """the same reference code under this image's torch (eager, cuDNN) on this B200, timed with the
+    protocol of scripts/evaluate-runtime.py:64-82 (synchronize around the sampling call) on `p_sample_loop` chains of
+    `n_steps` steps at batch B.  mode "tf32" = matmul_precision medium (train.py:144-150, config/shapes_experiment.yaml:59),
+    "bf16" = the same under torch.autocast(bfloat16), "fp32" = matmul_precision highest."""
+    ns, gd = build_reference(T, dev)
+    geo, x, c_local = synthetic_inputs(B, 100)
+    x = x.to(dev)
+    C = {ns.Conditioning.Type.CELL_TYPE: c_local.to(dev)}
+    idx = torch.from_numpy(geo.cell_idx).to(dev)
+    old = (torch.get_float32_matmul_precision(), torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        torch.set_float32_matmul_precision("highest" if mode == "fp32" else "medium")
+        torch.backends.cuda.matmul.allow_tf32 = mode != "fp32"
+        torch.backends.cudnn.allow_tf32 = mode != "fp32"
+        ctx = torch.autocast("cuda", dtype=torch.bfloat16) if mode == "bf16" else torch.autocast("cuda", enabled=False)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.no_grad(), ctx:
+            gd.p_sample_loop(x, C, idx, start_from=max(1, warm))
+            torch.cuda.synchronize()
+            e0.record()
+            gd.p_sample_loop(x, C, idx, start_from=n_steps)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n_steps
+    finally:
+        torch.set_float32_matmul_precision(old[0])
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old[1], old[2]
+        del gd
+        torch.cuda.empty_cache()
+    return ms
+
+
+def gpu_reference_block(T, B, dev, ours_ms_per_step):
+    """`gpu_reference` of the bench line: the unmodified reference on this GPU in the two precisions it is run at
+    (TF32 = its shapes experiment; bf16 autocast), beside this repo's step time.  A baseline leg like cpu_baseline:
+    reported, never part of the measured path."""
+    from oracle import ref_shim
+
+    if not ref_shim.available():
+        return {"unavailable": "reference package not installed (oracle/install_ref.py)"}
+    torch.cuda.empty_cache()
+    out = {"batch_per_gpu": B, "how": "unmodified reference GaussianDiffusion.p_sample_loop, torch eager + cuDNN, 6 timed + 2 warm-up steps"}
+    for mode in ("tf32", "bf16"):
+        try:
+            ms_ref = time_gpu_reference(T, B, 6, 2, mode, dev)
+            out[mode] = {"ms_per_step": ms_ref, "value": B / (T * ms_ref * 1e-3), "unit": UNIT, "speedup_of_this_repo": ms_ref / ours_ms_per_step}
+        except Exception as e:  # the bar is reported, never allowed to break the bench line
+            out[mode] = {"error": str(e)[:200]}
+    return out
 
 
 def run_reference(args):
+    """Reference arm.  Under torchrun only rank 0 works (and uses every host core); the other ranks exit."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     T = args.timesteps
-    sec, cores = time_cpu_reference(T, max(1, args.steps), max(0, args.warmup))
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    if args.impl == "reference-gpu":
+        if not torch.cuda.is_available():
+            _emit({"impl": "reference-gpu", "unavailable": "no CUDA device"})
+            return
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        torch.cuda.set_device(dev)
+        ms = time_gpu_reference(T, args.batch, steps, warm, args.ref_mode, dev)
+        value = args.batch / (T * ms * 1e-3)
+        _emit({"impl": "reference-gpu", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warm,
+               "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.ref_mode, "data": "synthetic",
+               "config": {"workload": workload(T), "batch_per_gpu": args.batch, "timesteps": T},
+               "how": "unmodified reference GaussianDiffusion.p_sample_loop under torch eager on this GPU (scripts/evaluate-runtime.py protocol)"})
+        return
+    sec, cores, kind = time_cpu_reference(T, steps, warm)
     value = 1.0 / (sec * T)
-    sample = f"B=1 single denoise steps of the shapes config ({args.steps} timed, {args.warmup} warm-up), extrapolated to T={T} steps per sample"
+    sample = (f"{steps} timed + {warm} warm-up ancestral steps of ONE of the batch's {args.batch} samples through "
+              f"{'the unmodified reference GaussianDiffusion.p_sample_loop' if kind == 'reference' else 'the CPU oracle port'} "
+              f"on {cores} host threads ({sec:.2f} s/step); samples/s = 1 / (s_per_step * T) - per-sample cost, batch independent")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[2] DDPM ancestral sampling, shapes config 194x50x50 u+p, T={T}", "batch_per_step": 1, "timesteps": T},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload(T), "batch_per_gpu": args.batch, "timesteps": T},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -250,6 +354,7 @@ def run_ours(args):
     one_step()
     torch.cuda.synchronize()
     launches_per_unet = None
+    used_graph = not args.no_graph
     if not args.no_graph:
         n0 = _lib.launch_count()
         side = torch.cuda.Stream()
@@ -326,12 +431,18 @@ def run_ours(args):
         flops = conv_flops_per_sample(geo.padded) * B
         ach = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         peak = pk["bf16_tflops_sustained"]
-        # ncu (profiles/r01_launches_v52_b8.csv, r01_ncu_full_win_v40.json): the top kernel (row-window conv, 64->64
-        # @194x50x50, B=8) moves 543 MB + 456 MB of DRAM traffic per launch = its algorithmic bytes (input read once, output written once)
-        traffic = 1.0015e9 if (B == 8 and args.precision == "bf16") else None
+        # DRAM traffic of the top kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
+        # capture of THIS workload, committed under profiles/ (bench.py cannot run under ncu itself); null when the
+        # capture does not match the run's batch / precision
+        traffic, traffic_of = None, None
+        tf = ROOT / "profiles" / "ncu_traffic.json"
+        if tf.exists():
+            td = json.loads(tf.read_text())
+            if td.get("batch") == B and td.get("precision") == args.precision:
+                traffic, traffic_of = td["dram_bytes_per_launch"], f"{td['kernel']} ({td['source']})"
         roof = {"bound": "tensor", "kernel": "tcgen05 convolution family: conv3d_bf16_winz / _win / _winp / _fold2 / _tc kernels (all conv launches of one step)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
-                "traffic_of": "conv3d_bf16_winz_kernel<64,64> per launch (ncu dram__bytes_read+write, round-1 capture)" if traffic else None,
+                "traffic_of": traffic_of,
                 "peak_src": f"{pk['src']} bf16 sustained (kernel timed inside a long step)",
                 "conv_ms_per_step": conv_ms, "kernel_ms_per_step": prof}
         # the bandwidth-bound update kernel against the HBM roofline: 6 tensors x 4 B per element
@@ -411,9 +522,16 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sec, cores = time_cpu_reference(T, 3, 1)
-        cpu = {"value": 1.0 / (sec * T), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"3 timed B=1 denoise steps of the same workload on the host ({sec:.2f} s/step), extrapolated to T={T}"}
+        sec, cores, kind = time_cpu_reference(T, 4, 1)
+        cpu = {"value": 1.0 / (sec * T), "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"4 timed + 1 warm-up ancestral steps of ONE sample of the same workload through "
+                         f"{'the unmodified reference p_sample_loop' if kind == 'reference' else 'the CPU oracle port'} on {cores} host "
+                         f"threads ({sec:.2f} s/step), samples/s = 1 / (s_per_step * T)"}
+
+    # the reference's own code on THIS GPU (torch eager + cuDNN): the throughput bar of SURVEY 8(d)(ii)
+    gpu_ref = None
+    if rank == 0 and world == 1 and not args.no_gpu_reference:
+        gpu_ref = gpu_reference_block(T, B, dev, ms_per_step)
 
     if rank == 0:
         h2d = x_pinned.numel() * 4
@@ -421,14 +539,17 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": f"configs[2] DDPM ancestral sampling, shapes config 194x50x50 u+p (dim 32, 4 levels, 55.2M params), T={T}",
-                       "batch_per_gpu": B, "timesteps": T, "step": "one denoise step of the whole batch (U-Net forward + 2 randn + fused update)",
-                       "l2": "activations exceed L2 (>= 270 MB per level-0 tensor), no flush needed", "cuda_graph": graph is not None,
+            "config": {"workload": workload(T), "batch_per_gpu": B, "timesteps": T, "step": "one denoise step of the whole batch (U-Net forward + 2 randn + fused update)",
+                       "l2": "activations exceed L2 (>= 270 MB per level-0 tensor), no flush needed", "cuda_graph": used_graph,
                        "samples_per_sec_T500": value * T / 500},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
                     "how": f"GaussianDiffusion.p_sample_loop(start_from={S}) on pinned host x_bcs -> pinned host sample, scaled by T/{S}"},
-            "roofline": roof, "cpu_baseline": cpu, "train": train,
+            "roofline": roof, "cpu_baseline": cpu, "gpu_reference": gpu_ref,
+            "train_steps_per_sec": None if train is None else train["steps_per_sec"],
+            "train_ms_per_step": None if train is None else train["ms_per_step"],
+            "train_samples_per_sec": None if train is None else train["steps_per_sec"] * train["global_batch"],
+            "train": train,
         }
         _emit(line)
     if world > 1:
@@ -449,7 +570,7 @@ def main():
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)  # C-level writers to fd 1 (e.g. the "NCCL version" banner) must not pollute the JSON line
     args = parse()
-    if args.impl == "reference":
+    if args.impl in ("reference", "reference-gpu"):
         run_reference(args)
     else:
         if not torch.cuda.is_available():

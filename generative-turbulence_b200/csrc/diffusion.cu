@@ -157,28 +157,42 @@ scatter_cells_kernel(const float* __restrict__ samples, const int64_t* __restric
 }
 
 // the steps either side of the sampler, fused.
-// grid[b][f][v] = fma(scale[f], value, shift[f]) with value = samples[b][j][f] on voxel cell_idx[j] and 0 elsewhere:
-// OpenFOAMData.grid_embedding (data/ofles.py:220-232) followed by Normalization.normalize_grid
-// (models/normalization.py:20-24: addcmul(-mean/std, 1/std, x)); scale = 1/std, shift = -mean/std as torch computed them.
+// grid[b][f][v] = fma(scale[f], value, shift[f]): OpenFOAMData.grid_embedding (data/ofles.py:220-240) followed by
+// Normalization.normalize_grid (models/normalization.py:20-24: addcmul(-mean/std, 1/std, x)); scale = 1/std,
+// shift = -mean/std as torch computed them.  value =
+//   * the FIXED_VALUE boundary value of channel f where the voxel's boundary class fixes it (ofles.py:233-238;
+//     written AFTER the cell samples in the reference, so it wins over a cell value),
+//   * samples[b][j][f] on voxel cell_idx[j],
+//   * 0 elsewhere.
+// code[v]: bit 0 = voxel is a cell, bits 1..7 = boundary class (0 = none); bc_has / bc_val [class][F] say which
+// channels the class fixes and to what (the host resolves overlapping boundaries in the reference's write order).
+// Without boundary tables code is the plain inside mask (0 / 1).  Every grid element is written exactly once.
 __global__ void __launch_bounds__(kThreads)
-scatter_normalize_kernel(const float* __restrict__ samples, const int64_t* __restrict__ cell_idx, const uint8_t* __restrict__ mask,
-                         const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ grid, int B, int F,
-                         int64_t nvox, int64_t n_cells) {
+scatter_normalize_kernel(const float* __restrict__ samples, const int64_t* __restrict__ cell_idx, const uint8_t* __restrict__ code,
+                         const uint8_t* __restrict__ bc_has, const float* __restrict__ bc_val, const float* __restrict__ scale,
+                         const float* __restrict__ shift, float* __restrict__ grid, int B, int F, int64_t nvox, int64_t n_cells) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    // voxels that are not cells: the normalised zero
+    // voxels whose value does not come from a cell sample: boundary value or the normalised zero
     const int64_t total_fill = (int64_t)B * F * nvox;
     for (int64_t i = t0; i < total_fill; i += stride) {
         const int64_t v = i % nvox;
         const int f = (int)((i / nvox) % F);
-        if (!mask[v]) grid[i] = __fmaf_rn(scale[f], 0.0f, shift[f]);
+        const int c = code[v];
+        const int cls = c >> 1;
+        const bool fixed = cls != 0 && bc_has != nullptr && bc_has[cls * F + f];
+        if (fixed) grid[i] = __fmaf_rn(scale[f], bc_val[cls * F + f], shift[f]);
+        else if (!(c & 1)) grid[i] = __fmaf_rn(scale[f], 0.0f, shift[f]);
     }
-    // cells (disjoint from the voxels above)
+    // cells (disjoint from the elements written above)
     const int64_t total = (int64_t)B * n_cells * F;
     for (int64_t i = t0; i < total; i += stride) {
         const int f = (int)(i % F);
         const int64_t j = (i / F) % n_cells;
         const int64_t b = i / ((int64_t)F * n_cells);
-        grid[(b * F + f) * nvox + cell_idx[j]] = __fmaf_rn(scale[f], samples[i], shift[f]);
+        const int64_t v = cell_idx[j];
+        const int cls = code[v] >> 1;
+        if (cls != 0 && bc_has != nullptr && bc_has[cls * F + f]) continue;  // a fixed boundary value overrides the sample
+        grid[(b * F + f) * nvox + v] = __fmaf_rn(scale[f], samples[i], shift[f]);
     }
 }
 
@@ -284,12 +298,14 @@ int tdb_scatter_cells(const float* samples, const int64_t* cell_idx, float* grid
     return 0;
 }
 
-int tdb_scatter_normalize(const float* samples, const int64_t* cell_idx, const uint8_t* mask, const float* scale, const float* shift,
-                          float* grid, int B, int F, int64_t nvox, int64_t n_cells, void* stream) {
+int tdb_scatter_normalize(const float* samples, const int64_t* cell_idx, const uint8_t* code, const uint8_t* bc_has, const float* bc_val,
+                          const float* scale, const float* shift, float* grid, int B, int F, int64_t nvox, int64_t n_cells, void* stream) {
     if ((int64_t)B * F * nvox == 0) return 0;
-    TDB_REQUIRE(cell_idx && mask && scale && shift && grid && (samples || n_cells == 0), TDB_E_BADARG, "tdb_scatter_normalize: null pointer");
-    scatter_normalize_kernel<<<blocks_for((int64_t)B * F * nvox), kThreads, 0, (cudaStream_t)stream>>>(samples, cell_idx, mask, scale, shift,
-                                                                                                      grid, B, F, nvox, n_cells);
+    TDB_REQUIRE((cell_idx || n_cells == 0) && code && scale && shift && grid && (samples || n_cells == 0), TDB_E_BADARG,
+                "tdb_scatter_normalize: null pointer");
+    TDB_REQUIRE((bc_has == nullptr) == (bc_val == nullptr), TDB_E_BADARG, "tdb_scatter_normalize: bc_has and bc_val come together");
+    scatter_normalize_kernel<<<blocks_for((int64_t)B * F * nvox), kThreads, 0, (cudaStream_t)stream>>>(samples, cell_idx, code, bc_has, bc_val,
+                                                                                                      scale, shift, grid, B, F, nvox, n_cells);
     TDB_CHECK_LAUNCH("tdb_scatter_normalize");
     return 0;
 }

@@ -63,11 +63,71 @@ def where_cells(cell_idx, cell_values: torch.Tensor, other: torch.Tensor | None 
     return out
 
 
-def scatter_normalize(samples: torch.Tensor, cell_idx: torch.Tensor, cell_counts, mean: torch.Tensor, std: torch.Tensor):
-    """Fused ``OpenFOAMData.grid_embedding`` + ``Normalization.normalize_grid`` (data/ofles.py:220-232,
-    models/normalization.py:20-24): (B, n_cells, F) channels-last cell values -> normalised (B, F, *cell_counts) grid,
-    non-cell voxels holding the normalised zero.  One launch; bit-exact with the reference's op sequence.  (FIXED_VALUE
-    boundary cells, if any, are written by the caller: ``grid[..., f, idx] = addcmul(-mean/std, 1/std, value)``.)"""
+def fixed_values_of(metadata, variables):
+    """The FIXED_VALUE boundary writes of ``OpenFOAMData.grid_embedding`` (data/ofles.py:233-238) as a list of
+    ``(voxel_idx, first_channel, values)`` in the reference's write order, read off a reference ``OpenFOAMMetadata``
+    (duck-typed: ``boundary_conditions[v][name].type / .value``, ``boundaries[name]["idx"]``, ``v.dims``)."""
+    out, f0 = [], 0
+    for v in variables:
+        for name, desc in metadata.boundary_conditions.get(v, {}).items():
+            if getattr(desc.type, "name", str(desc.type)) == "FIXED_VALUE":
+                out.append((metadata.boundaries[name]["idx"], f0, torch.as_tensor(desc.value, dtype=torch.float32).reshape(-1)))
+        f0 += v.dims
+    return out
+
+
+def boundary_code(cell_idx: torch.Tensor, nvox: int, F: int, fixed_values):
+    """Per-voxel code byte + class tables for tdb_scatter_normalize.  Overlapping boundaries are resolved per channel
+    in write order (a later write wins, as the reference's sequential index assignments do); voxels with the same
+    per-channel winners share a class.  Tiny torch ops on the index tensors, once per geometry."""
+    code = inside_mask(cell_idx, nvox).clone()
+    if not fixed_values:
+        return code, None, None
+    cls, bc_has, bc_val = boundary_classes(nvox, F, fixed_values, cell_idx.device)
+    code |= (cls << 1).to(torch.uint8)
+    return code, bc_has, bc_val
+
+
+def boundary_classes(nvox: int, F: int, fixed_values, dev):
+    """(class per voxel, bc_has [n_cls+1][F] uint8, bc_val [n_cls+1][F] fp32) - pure index arithmetic (see boundary_code)."""
+    winner = torch.zeros((F, nvox), dtype=torch.int64, device=dev)  # per channel: 1 + index of the write that wins
+    vals = [None]
+    for k, (idx, f0, value) in enumerate(fixed_values):
+        idx = idx.to(device=dev, dtype=torch.int64)
+        winner[f0 : f0 + value.numel(), idx] = k + 1
+        vals.append((f0, value.to(dev)))
+    key = torch.zeros(nvox, dtype=torch.int64, device=dev)
+    for f in range(F):
+        key = key * (len(fixed_values) + 1) + winner[f]
+    uniq, inv = torch.unique(key, return_inverse=True)  # uniq[0] == 0 (no write) whenever some voxel is untouched
+    has_zero = bool(uniq[0] == 0)
+    n_cls = uniq.numel() - (1 if has_zero else 0)
+    if n_cls > 127:
+        raise RuntimeError(f"turbdiff_b200: {n_cls} distinct boundary-value classes (max 127)")
+    cls = inv + (0 if has_zero else 1)
+    # class tables from one representative voxel per class
+    rep = torch.zeros(n_cls + 1, dtype=torch.int64, device=dev)
+    rep[cls] = torch.arange(nvox, device=dev)
+    w = winner[:, rep]                                   # (F, n_cls + 1)
+    bc_has = (w > 0).t().contiguous().to(torch.uint8)    # (n_cls + 1, F)
+    bc_has[0] = 0
+    bc_val = torch.zeros((n_cls + 1, F), dtype=torch.float32, device=dev)
+    for k in range(1, len(vals)):
+        f0, value = vals[k]
+        for d in range(value.numel()):
+            sel = w[f0 + d] == k
+            bc_val[sel, f0 + d] = value[d]
+    bc_val[0] = 0
+    return cls, bc_has, bc_val
+
+
+def scatter_normalize(samples: torch.Tensor, cell_idx: torch.Tensor, cell_counts, mean: torch.Tensor, std: torch.Tensor,
+                      fixed_values=None, tables=None):
+    """Fused ``OpenFOAMData.grid_embedding`` + ``Normalization.normalize_grid`` (data/ofles.py:220-240,
+    models/normalization.py:20-24): (B, n_cells, F) channels-last cell values -> normalised (B, F, *cell_counts) grid with
+    the FIXED_VALUE boundary values written into their padding voxels and every other non-cell voxel holding the
+    normalised zero.  One launch; bit-exact with the reference's op sequence.  ``fixed_values``: see
+    :func:`fixed_values_of`; ``tables`` = a cached :func:`boundary_code` result for this geometry."""
     _lib.require_cuda(samples, "samples")
     B, n_cells, F = samples.shape
     nvox = int(cell_counts[0]) * int(cell_counts[1]) * int(cell_counts[2])
@@ -76,8 +136,9 @@ def scatter_normalize(samples: torch.Tensor, cell_idx: torch.Tensor, cell_counts
     mean, std = mean.to(s.device, torch.float32), std.to(s.device, torch.float32)
     scale, shift = torch.reciprocal(std).contiguous(), (-mean / std).contiguous()  # exactly the reference's operands
     grid = torch.empty((B, F, *cell_counts), dtype=torch.float32, device=s.device)
-    call("tdb_scatter_normalize", s.data_ptr(), idx.data_ptr(), inside_mask(idx, nvox).data_ptr(), scale.data_ptr(), shift.data_ptr(),
-         grid.data_ptr(), B, F, nvox, idx.numel(), _lib.stream_ptr())
+    code, bc_has, bc_val = tables if tables is not None else boundary_code(idx, nvox, F, fixed_values)
+    call("tdb_scatter_normalize", s.data_ptr(), idx.data_ptr(), code.data_ptr(), ptr(bc_has), ptr(bc_val), scale.data_ptr(),
+         shift.data_ptr(), grid.data_ptr(), B, F, nvox, idx.numel(), _lib.stream_ptr())
     return grid
 
 

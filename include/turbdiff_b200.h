@@ -314,11 +314,15 @@ TDB_API int tdb_select_cells(const float* x, const int64_t* cell_idx, float* out
 /* grid[b][f][cell_idx[j]] = samples[b][j][f] on a pre-zeroed grid: data/ofles.py:220-232. */
 TDB_API int tdb_scatter_cells(const float* samples, const int64_t* cell_idx, float* grid, int B, int F,
                       int64_t nvox, int64_t n_cells, void* stream);
-/* Fused scatter + normalise: grid[b][f][v] = fma(scale[f], value, shift[f]) with value =
- * samples[b][j][f] on voxel cell_idx[j] and 0 on every other voxel (mask = tdb_build_mask of cell_idx): data/ofles.py:220-232
- * followed by models/normalization.py:20-24; scale = 1/std, shift = -mean/std.  Bit-exact with torch.addcmul. */
-TDB_API int tdb_scatter_normalize(const float* samples, const int64_t* cell_idx, const uint8_t* mask, const float* scale,
-                          const float* shift, float* grid, int B, int F, int64_t nvox, int64_t n_cells, void* stream);
+/* Fused scatter + FIXED_VALUE boundary writes + normalise: grid[b][f][v] = fma(scale[f], value, shift[f])
+ * with value = the fixed boundary value of channel f where the voxel's boundary class fixes it, else samples[b][j][f] on voxel
+ * cell_idx[j], else 0: OpenFOAMData.grid_embedding data/ofles.py:220-240 (cell scatter :231-232, boundary writes :233-238)
+ * followed by Normalization.normalize_grid models/normalization.py:20-24; scale = 1/std, shift = -mean/std.
+ * code[v]: bit 0 = cell (tdb_build_mask), bits 1..7 = boundary class (0 = none); bc_has / bc_val: [n_classes + 1][F] tables
+ * (row 0 unused), both NULL when the case fixes no boundary values.  Bit-exact with the reference's torch op sequence. */
+TDB_API int tdb_scatter_normalize(const float* samples, const int64_t* cell_idx, const uint8_t* code, const uint8_t* bc_has,
+                          const float* bc_val, const float* scale, const float* shift, float* grid, int B, int F, int64_t nvox,
+                          int64_t n_cells, void* stream);
 /* Fused de-normalise + gather, channels-last: out[b][j][f] = fma(scale[f], x[b][f][cell_idx[j]], shift[f]):
  * models/normalization.py:26-30 + models/utils.py:14-15 + the "b f c -> b c f" of models/metrics.py:50-57; scale = std, shift = mean. */
 TDB_API int tdb_gather_denormalize(const float* x, const int64_t* cell_idx, const float* scale, const float* shift, float* out,

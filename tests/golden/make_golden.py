@@ -11,10 +11,8 @@ denoising path.  Inputs and weights come from numpy PCG64 seeds
 ``tests/test_oracle_golden.py`` rebuilds the inputs and checks the oracle against them.
 """
 
-import importlib.machinery
 import json
 import sys
-import types
 from pathlib import Path
 
 import numpy as np
@@ -23,43 +21,17 @@ import torch
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parents[1]
 sys.path.insert(0, str(ROOT))
-sys.path.insert(0, "/root/reference")
 
-
-def _stub(name, pkg=False, **attrs):
-    m = types.ModuleType(name)
-    m.__dict__.update(attrs)
-    m.__spec__ = importlib.machinery.ModuleSpec(name, None, is_package=pkg)
-    if pkg:
-        m.__path__ = []
-    sys.modules[name] = m
-    return m
-
-
-class _LM(torch.nn.Module):
-    pass
-
-
-_stub("h5py", File=object, Group=object)
-_pl = _stub("pytorch_lightning", pkg=True, LightningModule=_LM, LightningDataModule=object, Callback=object, Trainer=object)
-_stub("pytorch_lightning.callbacks", ModelCheckpoint=object)
-_stub("pytorch_lightning.utilities", rank_zero_only=lambda f: f)
-_pl.loggers = _stub("pytorch_lightning.loggers", Logger=object)
-_stub("lightning_utilities", pkg=True)
-_stub("lightning_utilities.core", pkg=True)
-_stub("lightning_utilities.core.apply_func", apply_to_collection=lambda *a, **k: None)
-_stub("more_itertools", chunked=lambda it, n: [it[i : i + n] for i in range(0, len(it), n)])
-_stub("omegaconf", DictConfig=dict, OmegaConf=object)
 
 import warnings  # noqa: E402
 
 warnings.filterwarnings("ignore")
 
-import turbdiff.models.ddpm as ref  # noqa: E402
-from turbdiff.data import ofles  # noqa: E402
-from turbdiff.models import utils as ref_utils  # noqa: E402
-from turbdiff.models.cell_type_embeddings import CellTypeLearnedEmbedding  # noqa: E402
-from turbdiff.models.conditioning import Conditioning  # noqa: E402
+from oracle import ref_shim  # noqa: E402  (stubs the absent third-party packages, then imports the unmodified reference)
+
+_ns = ref_shim.load()
+ref, ofles, ref_utils = _ns.ddpm, _ns.ofles, _ns.utils
+CellTypeLearnedEmbedding, Conditioning = _ns.CellTypeLearnedEmbedding, _ns.Conditioning
 
 from oracle import grid_ref  # noqa: E402
 from oracle.cases import (CASES, SHAPES_FWD_T, SHAPES_INPUT_SEED, SHAPES_SEED, SHAPES_T, case_inputs, grad_sample,  # noqa: E402

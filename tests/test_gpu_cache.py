@@ -95,7 +95,7 @@ def test_sample_train_sample_uses_updated_weights(precision, train_graph, optimi
     # same kernels, same weights: equal up to the summation order of the split-K atomics of the bottleneck convolutions
     assert rel_l2(e1, ef) < 1e-5, rel_l2(e1, ef)
     assert rel_l2(s1, sf) < 1e-5, rel_l2(s1, sf)
-    assert rel_l2(s1, s0) > 1e-3
+    assert rel_l2(s1, s0) > 1e-4  # two clipped steps move a 2-step chain by ~5e-4; the stale-graph error would be exactly 0
 
     # one more training step after the sampling: the training graph must still see the live parameters
     m.train()
@@ -107,10 +107,12 @@ def test_sample_train_sample_uses_updated_weights(precision, train_graph, optimi
     with cpu_seeded_randn(200):
         loss_b, _ = gdf(x, C, MD, None)
     loss_b.backward()
-    assert abs(float(loss_a) - float(loss_b)) < 1e-5 * abs(float(loss_b))
+    assert abs(float(loss_a.detach()) - float(loss_b.detach())) < 1e-5 * abs(float(loss_b.detach()))
     ga = dict(m.named_parameters())
+    # bf16: the order of the fp32 atomics of the fused GroupNorm moments flips bf16 roundings downstream (measured 6e-4)
+    tol = 1e-4 if precision == "fp32" else 5e-3
     for n, q in fresh.named_parameters():
-        assert rel_l2(ga[n].grad, q.grad) < 1e-4, n
+        assert rel_l2(ga[n].grad, q.grad) < tol, n
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
@@ -202,7 +204,9 @@ def test_fused_radam_load_state_dict_replaces_moments():
         step(i)
     v0 = ps[0]._version
     # reload the state of the torch optimiser (new moment tensors, same parameters), then keep stepping
-    a.load_state_dict(b.state_dict())
+    import copy
+
+    a.load_state_dict(copy.deepcopy(b.state_dict()))  # (torch aliases the tensors of an in-memory state dict)
     for i in range(7, 10):
         step(i)
     assert ps[0]._version > v0  # raw-pointer updates are reported to autograd's version counter

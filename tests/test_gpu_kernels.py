@@ -582,6 +582,38 @@ def test_scatter_normalize_and_gather_denormalize(lib, B):
     np.testing.assert_allclose(back.cpu().numpy(), samples.numpy(), rtol=1e-5, atol=2e-5)
 
 
+def test_scatter_normalize_writes_fixed_value_boundaries(lib, golden):
+    """data/ofles.py:233-238: FIXED_VALUE boundary vectors (inlet U = (20,0,0), wall U = 0, outlet p = 0) written into the
+    padding voxels by the same launch: identity normalisation against the reference's grid_embedding golden (bit-exact),
+    a real normalisation against the reference's torch op sequence on the device (bit-exact)."""
+    from test_host_cpu import _golden_grid_case
+    from turbdiff_b200.models import utils as U
+
+    geo, samples, fixed = _golden_grid_case()
+    idx = torch.from_numpy(geo.cell_idx).cuda()
+    F_ = 4
+    got = U.scatter_normalize(samples.cuda(), idx, geo.padded, torch.zeros(F_), torch.ones(F_), fixed_values=fixed)
+    np.testing.assert_array_equal(got.cpu().numpy(), golden["grid"]["grid_embedding"])
+
+    mean, std = torch.tensor([0.3, -1.2, 0.05, 101.5]), torch.tensor([1.7, 0.4, 2.5, 13.0])
+    x = torch.zeros((2, F_, geo.n_vox), device="cuda")
+    xt = x.transpose(-1, -2)
+    xt[..., idx, :] = samples.cuda()
+    for bidx, f0, v in fixed:
+        xt[..., bidx.cuda(), f0 : f0 + v.numel()] = v.cuda()
+    m3, s3 = mean.cuda().view(F_, 1, 1, 1), std.cuda().view(F_, 1, 1, 1)
+    want = torch.addcmul(-m3 / s3, torch.reciprocal(s3), x.view(2, F_, *geo.padded))
+    tables = U.boundary_code(idx, geo.n_vox, F_, fixed)
+    got = U.scatter_normalize(samples.cuda(), idx, geo.padded, mean, std, tables=tables)
+    assert torch.equal(got, want)
+    # a boundary that overlaps cells and another boundary: the later write wins, per channel
+    over = fixed + [(torch.from_numpy(geo.cell_idx[:5].copy()), 1, torch.tensor([4.5])), (fixed[0][0][:3], 0, torch.tensor([1.0, 2.0, 3.0]))]
+    for bidx, f0, v in over[-2:]:
+        xt[..., bidx.cuda(), f0 : f0 + v.numel()] = v.cuda()
+    want = torch.addcmul(-m3 / s3, torch.reciprocal(s3), x.view(2, F_, *geo.padded))
+    assert torch.equal(U.scatter_normalize(samples.cuda(), idx, geo.padded, mean, std, fixed_values=over), want)
+
+
 @pytest.mark.parametrize("case", [(2, 9, 7, 6), (2, 40, 20, 50), (1, 30, 12, 62), (3, 21, 11, 8), (1, 194, 6, 4)])
 @pytest.mark.parametrize("variant", ["plain", "stats", "all_rows"])
 def test_conv3d_bf16_paired_rows_32_to_32(lib, case, variant):

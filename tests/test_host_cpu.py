@@ -164,3 +164,64 @@ def test_fused_radam_refuses_cpu_tensors():
         opt.step()
     with pytest.raises(ValueError):
         FusedRAdam([p], lr=-1.0)
+
+
+def _golden_grid_case():
+    """Inputs of tests/golden/make_golden.py gen_grid (the reference's OpenFOAMData.grid_embedding fixture)."""
+    from oracle import grid_ref
+
+    geo = grid_ref.channel_geometry(cells=(12, 6, 5), hole=((3, 6), (1, 4), (0, 3)), seed=3)
+    rng = np.random.Generator(np.random.PCG64(11))
+    B, n = 2, len(geo.cell_idx)
+    u = rng.standard_normal((B, n, 3)).astype(np.float32)
+    p = rng.standard_normal((B, n, 1)).astype(np.float32)
+    fixed = [(torch.from_numpy(geo.boundaries["inlets"]), 0, torch.tensor([20.0, 0.0, 0.0])),
+             (torch.from_numpy(geo.boundaries["walls"]), 0, torch.tensor([0.0, 0.0, 0.0])),
+             (torch.from_numpy(geo.boundaries["outlets"]), 3, torch.tensor([0.0]))]
+    return geo, torch.from_numpy(np.concatenate([u, p], axis=-1)), fixed
+
+
+def _emulate_scatter(samples, cell_idx, nvox, cls, bc_has, bc_val):
+    """What tdb_scatter_normalize computes (identity normalisation), in torch on the CPU."""
+    B, n, F = samples.shape
+    grid = torch.zeros((B, F, nvox))
+    grid[:, :, cell_idx] = samples.permute(0, 2, 1)
+    fixed = bc_has[cls].bool().t()           # (F, nvox)
+    vals = bc_val[cls].t()                    # (F, nvox)
+    return torch.where(fixed[None], vals[None].expand(B, -1, -1), grid)
+
+
+def test_boundary_class_tables_reproduce_reference_grid_embedding(golden):
+    """FIXED_VALUE boundary writes (data/ofles.py:233-238) as per-voxel classes: the host tables of
+    turbdiff_b200.models.utils.boundary_classes against the reference's grid_embedding golden (bit-exact)."""
+    from turbdiff_b200.models.utils import boundary_classes
+
+    geo, samples, fixed = _golden_grid_case()
+    cls, bc_has, bc_val = boundary_classes(geo.n_vox, 4, fixed, torch.device("cpu"))
+    assert int(cls.max()) <= 127 and bc_has.shape == bc_val.shape == (int(cls.max()) + 1, 4)
+    got = _emulate_scatter(samples, torch.from_numpy(geo.cell_idx), geo.n_vox, cls, bc_has, bc_val)
+    want = golden["grid"]["grid_embedding"]
+    np.testing.assert_array_equal(got.reshape(want.shape).numpy(), want)
+    inlet = torch.from_numpy(geo.boundaries["inlets"])
+    assert torch.equal(got[0, :3, inlet[0]], torch.tensor([20.0, 0.0, 0.0]))
+
+
+def test_boundary_class_tables_overlaps_follow_write_order():
+    """Two boundaries sharing voxels, and a boundary voxel that is also a cell: the later write wins per channel."""
+    from turbdiff_b200.models.utils import boundary_classes
+
+    nvox, F = 40, 4
+    a = torch.tensor([3, 4, 5, 6])
+    b = torch.tensor([5, 6, 7])
+    c = torch.tensor([6, 30])
+    fixed = [(a, 0, torch.tensor([1.0, 2.0, 3.0])), (b, 0, torch.tensor([-1.0, -2.0, -3.0])), (c, 3, torch.tensor([9.0])),
+             (c, 1, torch.tensor([7.0]))]
+    cls, bc_has, bc_val = boundary_classes(nvox, F, fixed, torch.device("cpu"))
+    cell_idx = torch.tensor([30, 31, 2])  # voxel 30 is both a cell and a boundary voxel of channels 1 and 3
+    samples = torch.arange(1 * 3 * F, dtype=torch.float32).reshape(1, 3, F) + 100
+    got = _emulate_scatter(samples, cell_idx, nvox, cls, bc_has, bc_val)
+    want = torch.zeros((1, F, nvox))
+    want[:, :, cell_idx] = samples.permute(0, 2, 1)
+    for idx, f0, v in fixed:  # the reference's sequential writes
+        want[:, f0 : f0 + v.numel(), idx] = v[None, :, None]
+    assert torch.equal(got, want)
