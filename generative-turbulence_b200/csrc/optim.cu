@@ -62,14 +62,13 @@ __global__ void __launch_bounds__(kOptThreads)
 radam_step_kernel(const int64_t* __restrict__ pp, const int64_t* __restrict__ gp, const int64_t* __restrict__ mp,
                   const int64_t* __restrict__ vp, const int64_t* __restrict__ numel, const int* __restrict__ chunk_tensor,
                   const int64_t* __restrict__ chunk_off, int chunk, const double* __restrict__ sqnorm, float max_norm, float step_size,
-                  float beta1, float beta2, float eps, float weight_decay, int rectified) {
+                  float beta1, float beta2, float w1, float w2, float eps, float weight_decay, int rectified) {
     const ChunkRef c = chunk_of(pp, gp, mp, vp, numel, chunk_tensor, chunk_off, chunk);
     float coef = 1.0f;
     if (sqnorm) {
         const float total = (float)sqrt(*sqnorm);
         coef = fminf(max_norm / (total + 1e-6f), 1.0f);
     }
-    const float w1 = 1.0f - beta1, w2 = 1.0f - beta2;
     for (int i = threadIdx.x; i < c.n; i += kOptThreads) {
         float g = c.g[i] * coef;
         const float p = c.p[i];
@@ -100,14 +99,15 @@ int tdb_grad_sqnorm(const int64_t* grad_ptrs, const int64_t* numel, const int* c
 
 int tdb_radam_step(const int64_t* param_ptrs, const int64_t* grad_ptrs, const int64_t* exp_avg_ptrs, const int64_t* exp_avg_sq_ptrs,
                    const int64_t* numel, const int* chunk_tensor, const int64_t* chunk_off, int n_chunks, int chunk, const double* sqnorm,
-                   float max_norm, float step_size, float beta1, float beta2, float eps, float weight_decay, int rectified, void* stream) {
+                   float max_norm, float step_size, double beta1, double beta2, float eps, float weight_decay, int rectified, void* stream) {
     TDB_REQUIRE(param_ptrs && grad_ptrs && exp_avg_ptrs && exp_avg_sq_ptrs && numel && chunk_tensor && chunk_off, TDB_E_BADARG,
                 "tdb_radam_step: null pointer");
     TDB_REQUIRE(chunk >= kOptThreads && n_chunks >= 0, TDB_E_BADARG, "tdb_radam_step: bad chunking");
     if (n_chunks == 0) return 0;
     radam_step_kernel<<<n_chunks, kOptThreads, 0, (cudaStream_t)stream>>>(param_ptrs, grad_ptrs, exp_avg_ptrs, exp_avg_sq_ptrs, numel,
-                                                                         chunk_tensor, chunk_off, chunk, sqnorm, max_norm, step_size, beta1,
-                                                                         beta2, eps, weight_decay, rectified);
+                                                                         chunk_tensor, chunk_off, chunk, sqnorm, max_norm, step_size, (float)beta1,
+                                                                         (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), eps,
+                                                                         weight_decay, rectified);
     TDB_CHECK_LAUNCH("tdb_radam_step");
     return 0;
 }

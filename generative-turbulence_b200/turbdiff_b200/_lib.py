@@ -19,7 +19,7 @@ CONV_ALL_ROWS = 1
 CONV_CLUSTER_MC = 2
 WGRAD_ZERO_HALO = 1
 
-_p, _i, _l, _u, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint, C.c_float
+_p, _i, _l, _u, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint, C.c_float, C.c_double
 
 # name -> argument types (all return int unless noted)
 SIGNATURES = {
@@ -49,7 +49,7 @@ SIGNATURES = {
     "tdb_trilinear_bwd": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_attention_bwd": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_grad_sqnorm": [_p, _p, _p, _p, _i, _i, _p, _p],
-    "tdb_radam_step": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _f, _f, _f, _f, _f, _f, _i, _p],
+    "tdb_radam_step": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _f, _f, _d, _d, _f, _f, _i, _p],
     "tdb_cl_nc_outer": [_p, _i, _p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_scatter_normalize": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _l, _l, _p],
     "tdb_gather_denormalize": [_p, _p, _p, _p, _p, _i, _i, _l, _l, _p],

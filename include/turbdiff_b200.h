@@ -71,7 +71,7 @@ TDB_API int tdb_grad_sqnorm(const int64_t* grad_ptrs, const int64_t* numel, cons
  * rectified ? lr*rect*sqrt(1-beta2^t)/(1-beta1^t) : lr/(1-beta1^t). */
 TDB_API int tdb_radam_step(const int64_t* param_ptrs, const int64_t* grad_ptrs, const int64_t* exp_avg_ptrs,
                    const int64_t* exp_avg_sq_ptrs, const int64_t* numel, const int* chunk_tensor, const int64_t* chunk_off,
-                   int n_chunks, int chunk, const double* sqnorm, float max_norm, float step_size, float beta1, float beta2,
+                   int n_chunks, int chunk, const double* sqnorm, float max_norm, float step_size, double beta1, double beta2,
                    float eps, float weight_decay, int rectified, void* stream);
 
 TDB_API const char* tdb_last_error(void);

@@ -213,4 +213,4 @@ def test_fused_radam_load_state_dict_replaces_moments():
     for p, q in zip(ps, ref):
         assert rel_l2(p, q) < 1e-6
     for p, q in zip(ps, ref):
-        assert rel_l2(a.state[p]["exp_avg_sq"], b.state[q]["exp_avg_sq"]) < 1e-6
+        assert rel_l2(a.state[p]["exp_avg_sq"], b.state[q]["exp_avg_sq"]) < 1e-5

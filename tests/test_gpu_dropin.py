@@ -17,7 +17,7 @@ from util import cpu_seeded_randn, rel_l2
 
 pytestmark = pytest.mark.gpu
 
-KW = dict(dim=8, cell_type_embedding_type="learned", cell_type_embedding_dim=4, normalization_mode="u:norm-max;p:abs-max",
+KW = dict(dim=16, cell_type_embedding_type="learned", cell_type_embedding_dim=4, normalization_mode="u:norm-max;p:abs-max",
           beta_schedule="log-snr-linear", timesteps=10, learning_rate=3e-3, min_learning_rate=1e-6, lr_decay="exp", loss="l2",
           noise_bcs=True, optimizer="radam", norm_type="group", with_geometry_embedding=False)
 
@@ -83,10 +83,13 @@ def test_reference_task_with_the_import_swap(ns, tmp_path, monkeypatch, precisio
     assert abs(float(loss.detach()) - float(ref_loss.detach())) < tol * abs(float(ref_loss.detach()))
     ref_grads = dict(ref_task.named_parameters())
     errs = {}
+    gmax = max(float(q.grad.abs().max()) for q in ref_grads.values())
     for k, p in task.named_parameters():
         assert p.grad is not None, k
         g = ref_grads[k].grad
-        if float(g.abs().max()) < 1e-8:
+        if float(g.abs().max()) < 1e-6 * gmax:
+            # a conv bias in front of a GroupNorm has an exactly zero gradient: the reference holds rounding noise there
+            assert float(p.grad.abs().max()) < 1e-4 * gmax, k
             continue
         errs[k] = rel_l2(p.grad, g)
     assert "cell_type_embedding.embedding.weight" in errs  # the gradient reaches the conditioning's 24 weights through C

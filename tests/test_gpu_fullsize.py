@@ -211,7 +211,7 @@ def test_full_size_sampling_chain_matches_reference_golden(golden, shapes, preci
     np.testing.assert_allclose(s.double().pow(2).sum().item(), g["sample_from3/sum"][1], rtol=1e-4 if precision == "fp32" else 2e-2)
 
 
-GRAD_TOL = {"fp32": 2e-4, "bf16": 4e-2}
+GRAD_TOL = {"fp32": 5e-5, "bf16": 3e-2}  # measured on B200: 1.3e-5 / 1.75e-2
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

@@ -153,7 +153,7 @@ def _oracle_grads(case, G, dtype=torch.float64):
 
 
 @pytest.mark.parametrize("cname,precision,tol", [("micro", "fp32", 2e-4), ("tiny", "fp32", 2e-4), ("micro-layer", "fp32", 2e-4),
-                                                  ("tiny", "bf16", 6e-2), ("dim32", "bf16", 6e-2)])
+                                                  ("tiny", "bf16", 3e-2), ("dim32", "bf16", 3e-2)])  # bf16: measured <= 2.4e-2
 def test_denoiser_backward_matches_oracle(cname, precision, tol):
     from oracle.cases import CASES, case_inputs
 
