@@ -334,14 +334,23 @@ def run_ours(args):
             return eng.plan(B, geo.padded, dev)["eps"]
         return eng.forward(x_t, t_vec, cl, c_static=True)  # inside a sampling chain C is constant (as in p_sample_loop)
 
+    rng_stream = torch.cuda.Stream(device=dev)
+
     def one_step():
         t = T - 1 - (step_no[0] % (T - 1))
         step_no[0] += 1
         t_dev.fill_(t)
         t_vec.fill_(t)
+        main = torch.cuda.current_stream()
+        # as GaussianDiffusion.p_sample_loop does: the two Gaussian draws overlap the denoiser on a side stream
+        rng_stream.wait_stream(main)
+        with torch.cuda.stream(rng_stream):
+            z = torch.randn_like(x_t)
+            z_bc = torch.randn_like(x_bcs)
+        z.record_stream(main)
+        z_bc.record_stream(main)
         eps = unet()
-        z = torch.randn_like(x_t)
-        z_bc = torch.randn_like(x_bcs)
+        main.wait_stream(rng_stream)
         _lib.call("tdb_ddpm_step", x_t.data_ptr(), eps.data_ptr(), z.data_ptr(), z_bc.data_ptr(), x_bcs.data_ptr(), mask.data_ptr(),
                   coef.data_ptr(), t_dev.data_ptr(), x_t.data_ptr(), B, 4, nvox, flags, _lib.stream_ptr())
 

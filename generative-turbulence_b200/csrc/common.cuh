@@ -79,6 +79,11 @@ struct Vec;
 template <>
 struct Vec<float> {
     static constexpr int N = 4;
+    // raw 16-byte register image: lets a kernel issue several independent loads before it converts / uses any of them
+    __device__ static uint4 load_raw(const float* p) { return *reinterpret_cast<const uint4*>(p); }
+    __device__ static void unpack(const uint4& t, float (&v)[4]) {
+        v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+    }
     __device__ static void load(const float* p, float (&v)[4]) {
         float4 t = *reinterpret_cast<const float4*>(p);
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -91,6 +96,14 @@ struct Vec<float> {
 template <>
 struct Vec<__nv_bfloat16> {
     static constexpr int N = 8;
+    __device__ static uint4 load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+    __device__ static void unpack(const uint4& t, float (&v)[8]) {
+        // bf16 -> fp32 is a 16-bit shift: two integer ops per pair instead of the cvt path
+        v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xFFFF0000u);
+        v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xFFFF0000u);
+        v[4] = __uint_as_float(t.z << 16); v[5] = __uint_as_float(t.z & 0xFFFF0000u);
+        v[6] = __uint_as_float(t.w << 16); v[7] = __uint_as_float(t.w & 0xFFFF0000u);
+    }
     __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
         uint4 t = *reinterpret_cast<const uint4*>(p);
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
@@ -111,6 +124,14 @@ struct Vec<__nv_bfloat16> {
 };
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
+// x * sigmoid(x) = h + h * tanh(h), h = x / 2: ONE special-function op (tanh.approx.f32, abs. error 2^-11) instead of
+// ex2 + rcp.  Only for bf16-stored results (output rounding 2^-9); the fp32 parity path keeps silu_f.
+__device__ __forceinline__ float silu_tanh(float v) {
+    const float h = 0.5f * v;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

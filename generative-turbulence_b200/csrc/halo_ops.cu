@@ -52,62 +52,93 @@ encode_input_kernel(const float* __restrict__ x, const float* __restrict__ c_loc
     const int64_t nvox = (int64_t)g.X * g.Y * g.Z;
     const float* src0 = c_half ? c_local : x + (int64_t)b * F * nvox;
     const uint32_t total = (uint32_t)g.vox_p;
-    for (uint32_t r = blockIdx.x * vox_step + lane_vox; r < total; r += gridDim.x * vox_step) {
-        int xp, yp, zp;
-        split(r, xp, yp, zp);
-        const int xs = clampi(xp - 1, 0, g.X - 1), ys = clampi(yp - 1, 0, g.Y - 1), zs = clampi(zp - 1, 0, g.Z - 1);
-        const float* src = src0 + ((int64_t)xs * g.Y + ys) * g.Z + zs;
-        float in[FMAX];
+    // U voxels per trip: all U * nf scalar loads are issued before the first is used (memory-level parallelism -
+    // one load in flight per thread left the kernel latency-bound at 40 % of the HBM rate)
+    constexpr int U = 4;
+    const uint32_t stride = gridDim.x * vox_step;
+    for (uint32_t r0 = blockIdx.x * vox_step + lane_vox; r0 < total; r0 += stride * U) {
+        float in[U][FMAX];
 #pragma unroll
-        for (int f = 0; f < FMAX; ++f) in[f] = f < nf ? __ldg(src + (int64_t)f * nvox) : 0.0f;
-        float o[N];
+        for (int u = 0; u < U; ++u) {
+            const uint32_t r = min(r0 + u * stride, total - 1);
+            int xp, yp, zp;
+            split(r, xp, yp, zp);
+            const int xs = clampi(xp - 1, 0, g.X - 1), ys = clampi(yp - 1, 0, g.Y - 1), zs = clampi(zp - 1, 0, g.Z - 1);
+            const float* src = src0 + ((int64_t)xs * g.Y + ys) * g.Z + zs;
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            float acc = br[i];
-#pragma unroll
-            for (int f = 0; f < FMAX; ++f) acc = fmaf(wr[i][f], in[f], acc);
-            o[i] = acc;
+            for (int f = 0; f < FMAX; ++f) in[u][f] = f < nf ? __ldg(src + (int64_t)f * nvox) : 0.0f;
         }
-        Vec<T>::store(out + ((int64_t)b * g.vox_p + r) * ld_out + c0, o);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t r = r0 + u * stride;
+            if (r >= total) break;
+            float o[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                float acc = br[i];
+#pragma unroll
+                for (int f = 0; f < FMAX; ++f) acc = fmaf(wr[i][f], in[u][f], acc);
+                o[i] = acc;
+            }
+            Vec<T>::store(out + ((int64_t)b * g.vox_p + r) * ld_out + c0, o);
+        }
     }
 }
 
 // ---------------------------------------------------------------- decode[1]
-template <typename T>
+// DV = dim / N channel vectors per voxel, all loaded (for U voxels) before the first is used.
+template <typename T, int DV>
 __global__ void __launch_bounds__(kThreads)
 decode_output_kernel(const T* __restrict__ act, int ld, const float* __restrict__ w,
                      const float* __restrict__ bias, float* __restrict__ out, Grid3 g, int dim, int F, FastDiv by_vox, FastDiv by_z,
                      FastDiv by_y) {
     constexpr int N = Vec<T>::N;
+    constexpr int U = DV >= 8 ? 1 : 2;
     extern __shared__ float sw[];  // F*dim weights + F biases
     for (int i = threadIdx.x; i < F * dim; i += blockDim.x) sw[i] = w[i];
     for (int i = threadIdx.x; i < F; i += blockDim.x) sw[F * dim + i] = bias[i];
     __syncthreads();
     const int64_t nvox = (int64_t)g.X * g.Y * g.Z;
     const uint32_t total = (uint32_t)(g.B * nvox);
-    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        uint32_t bb, v, q, zz, xx, yy;
-        by_vox.divmod(idx, bb, v);
-        by_z.divmod(v, q, zz);
-        by_y.divmod(q, xx, yy);
-        const int b = (int)bb, x = (int)xx, y = (int)yy, z = (int)zz;
-        const T* a = act + g.row(b, x, y, z) * ld;
-        float acc[8];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t idx0 = blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += stride * U) {
+        uint4 raw[U][DV];
+        int bs[U];
+        uint32_t vs[U];
 #pragma unroll
-        for (int f = 0; f < 8; ++f) acc[f] = f < F ? sw[F * dim + f] : 0.0f;
-        for (int c0 = 0; c0 < dim; c0 += N) {
-            float vv[N];
-            Vec<T>::load(a + c0, vv);
+        for (int u = 0; u < U; ++u) {
+            const uint32_t idx = min(idx0 + u * stride, total - 1);
+            uint32_t bb, v, q, zz, xx, yy;
+            by_vox.divmod(idx, bb, v);
+            by_z.divmod(v, q, zz);
+            by_y.divmod(q, xx, yy);
+            bs[u] = (int)bb;
+            vs[u] = v;
+            const T* a = act + g.row((int)bb, (int)xx, (int)yy, (int)zz) * ld;
 #pragma unroll
-            for (int f = 0; f < 8; ++f)
-                if (f < F) {
-#pragma unroll
-                    for (int i = 0; i < N; ++i) acc[f] = fmaf(sw[f * dim + c0 + i], vv[i], acc[f]);
-                }
+            for (int k = 0; k < DV; ++k) raw[u][k] = Vec<T>::load_raw(a + k * N);
         }
 #pragma unroll
-        for (int f = 0; f < 8; ++f)
-            if (f < F) out[((int64_t)b * F + f) * nvox + v] = acc[f];
+        for (int u = 0; u < U; ++u) {
+            if (idx0 + u * stride >= total) break;
+            float acc[8];
+#pragma unroll
+            for (int f = 0; f < 8; ++f) acc[f] = f < F ? sw[F * dim + f] : 0.0f;
+#pragma unroll
+            for (int k = 0; k < DV; ++k) {
+                float vv[N];
+                Vec<T>::unpack(raw[u][k], vv);
+#pragma unroll
+                for (int f = 0; f < 8; ++f)
+                    if (f < F) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) acc[f] = fmaf(sw[f * dim + k * N + i], vv[i], acc[f]);
+                    }
+            }
+#pragma unroll
+            for (int f = 0; f < 8; ++f)
+                if (f < F) out[((int64_t)bs[u] * F + f) * nvox + vs[u]] = acc[f];
+        }
     }
 }
 
@@ -174,8 +205,8 @@ gn_stats_kernel(const T* __restrict__ raw, int ld, double* __restrict__ stats, G
 // ---------------------------------------------------------------- fused pointwise
 template <typename T>
 __device__ __forceinline__ float act_silu(float v) {
-    if constexpr (sizeof(T) == 2)  // bf16 storage: the fast exp/rcp are far below the output rounding
-        return __fdividef(v, 1.0f + __expf(-v));
+    if constexpr (sizeof(T) == 2)  // bf16 storage: one special-function op (tanh.approx), error far below the output rounding
+        return silu_tanh(v);
     else
         return silu_f(v);
 }
@@ -232,26 +263,44 @@ pointwise_kernel(const T* __restrict__ raw, int ld_raw, const double* __restrict
     const bool interior_only = flags & TDB_PW_NOHALO;
     const bool act = flags & TDB_PW_SILU;
     const uint32_t total = (uint32_t)g.vox_p;
-    for (uint32_t r = blockIdx.x * vox_step + lane_vox; r < total; r += gridDim.x * vox_step) {
-        int xp, yp, zp;
-        split(r, xp, yp, zp);
-        const int xs = clampi(xp, 1, g.X), ys = clampi(yp, 1, g.Y), zs = clampi(zp, 1, g.Z);
-        if (interior_only && (xs != xp || ys != yp || zs != zp)) continue;
-        const int64_t src = (int64_t)b * g.vox_p + ((int64_t)xs * g.Yp + ys) * g.Zp + zs;
-        float v[N];
-        Vec<T>::load(raw + src * ld_raw + c0, v);
+    // U rows per trip, every load issued before the first use: with one 16-byte load in flight per thread the kernel was
+    // latency-bound (2048 threads x 16 B per SM = 4.8 MB in flight chip-wide against ~6.5 MB needed at the HBM rate)
+    constexpr int U = 4;
+    const uint32_t stride = gridDim.x * vox_step;
+    const int64_t base = (int64_t)b * g.vox_p;
+    for (uint32_t r0 = blockIdx.x * vox_step + lane_vox; r0 < total; r0 += stride * U) {
+        uint4 rv[U], sv[U];
+        bool ok[U];
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const float y = fmaf(ca[i], v[i], co[i]);
-            v[i] = act ? act_silu<T>(y) : y;
+        for (int u = 0; u < U; ++u) {
+            const uint32_t r = r0 + u * stride;
+            ok[u] = r < total;
+            int xp, yp, zp;
+            split(ok[u] ? r : total - 1, xp, yp, zp);
+            const int xs = clampi(xp, 1, g.X), ys = clampi(yp, 1, g.Y), zs = clampi(zp, 1, g.Z);
+            if (interior_only && (xs != xp || ys != yp || zs != zp)) ok[u] = false;
+            const int64_t src = base + ((int64_t)xs * g.Yp + ys) * g.Zp + zs;
+            rv[u] = Vec<T>::load_raw(raw + src * ld_raw + c0);
+            if (res) sv[u] = Vec<T>::load_raw(res + src * ld_res + c0);
         }
-        if (res) {
-            float rr[N];
-            Vec<T>::load(res + src * ld_res + c0, rr);
 #pragma unroll
-            for (int i = 0; i < N; ++i) v[i] += rr[i];
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            float v[N];
+            Vec<T>::unpack(rv[u], v);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const float y = fmaf(ca[i], v[i], co[i]);
+                v[i] = act ? act_silu<T>(y) : y;
+            }
+            if (res) {
+                float rr[N];
+                Vec<T>::unpack(sv[u], rr);
+#pragma unroll
+                for (int i = 0; i < N; ++i) v[i] += rr[i];
+            }
+            Vec<T>::store(out + (base + r0 + u * stride) * ld_out + c0, v);
         }
-        Vec<T>::store(out + ((int64_t)b * g.vox_p + r) * ld_out + c0, v);
     }
 }
 
@@ -271,72 +320,69 @@ __device__ __forceinline__ Lerp axis_lerp(int o, int n_in, float scale) {
     return r;
 }
 
-// grid = (blocks per sample, B)
+// grid = (blocks per sample, B).  Gather form: a thread owns one 16-byte channel vector of one OUTPUT row (haloed rows
+// included: their source is the clamped interior voxel), fetches its eight source vectors and blends them - x/y first,
+// then z, the order ATen's separable kernel and the fp32 parity tests use.  Consecutive threads walk the channel vectors
+// of a row and then the next row (= next z), so stores are fully coalesced and the (up to 8x smaller or 8x larger)
+// source is read through L1/L2; U rows per trip keep 16 independent loads in flight per thread.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 trilinear_kernel(const T* __restrict__ in, int ld_in, Grid3 gi, T* __restrict__ out, int ld_out, Grid3 go, int C,
                  RowSplit split, int chunks, float sx, float sy, float sz) {
     constexpr int N = Vec<T>::N;
+    constexpr int U = 2;
     const int b = blockIdx.y;
     const int vox_step = kThreads / chunks;
     const int ch = threadIdx.x % chunks, lane_vox = threadIdx.x / chunks;
     if (lane_vox >= vox_step) return;
     const int c0 = ch * N;
-    // line walker over the output grid: x/y interpolation and the four input line bases once per (x, y) line
-    const uint32_t lines = (uint32_t)(go.Xp * go.Yp);
-    for (uint32_t line = blockIdx.x * vox_step + lane_vox; line < lines; line += gridDim.x * vox_step) {
-        uint32_t xq, yq;
-        split.by_y.divmod(line, xq, yq);
-        const Lerp lx = axis_lerp(clampi((int)xq - 1, 0, go.X - 1), gi.X, sx);
-        const Lerp ly = axis_lerp(clampi((int)yq - 1, 0, go.Y - 1), gi.Y, sy);
-        const T* base[4];
-        float wxy[4];
+    const uint32_t total = (uint32_t)go.vox_p;
+    const uint32_t stride = gridDim.x * vox_step;
+    const T* in_b = in + (int64_t)b * gi.vox_p * ld_in + c0;
+    T* out_b = out + (int64_t)b * go.vox_p * ld_out + c0;
+    for (uint32_t r0 = blockIdx.x * vox_step + lane_vox; r0 < total; r0 += stride * U) {
+        uint4 v[U][2][4];
+        float wxy[U][4], wz[U][2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int xi = (k & 2) ? lx.i1 : lx.i0, yi = (k & 1) ? ly.i1 : ly.i0;
-            base[k] = in + gi.row(b, xi, yi, 0) * ld_in + c0;
-            wxy[k] = ((k & 2) ? lx.l1 : lx.l0) * ((k & 1) ? ly.l1 : ly.l0);
-        }
-        T* dst = out + ((int64_t)b * go.vox_p + (int64_t)line * go.Zp) * ld_out + c0;
-        // the x/y-interpolated input planes P(iz) are kept in registers while the walk moves along z: an output is
-        // l0*P(i0) + l1*P(i1), and when upsampling each P is reused by about two outputs (i0/i1 are warp-uniform)
-        auto plane = [&](int iz, float (&pl)[N]) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) pl[i] = 0.0f;
+        for (int u = 0; u < U; ++u) {
+            const uint32_t r = min(r0 + u * stride, total - 1);
+            int xq, yq, zq;
+            split(r, xq, yq, zq);
+            const Lerp lx = axis_lerp(clampi(xq - 1, 0, go.X - 1), gi.X, sx);
+            const Lerp ly = axis_lerp(clampi(yq - 1, 0, go.Y - 1), gi.Y, sy);
+            const Lerp lz = axis_lerp(clampi(zq - 1, 0, go.Z - 1), gi.Z, sz);
+            wz[u][0] = lz.l0;
+            wz[u][1] = lz.l1;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                float v[N];
-                Vec<T>::load(base[k] + (int64_t)iz * ld_in, v);
-#pragma unroll
-                for (int i = 0; i < N; ++i) pl[i] = fmaf(wxy[k], v[i], pl[i]);
+                const int xi = (k & 2) ? lx.i1 : lx.i0, yi = (k & 1) ? ly.i1 : ly.i0;
+                wxy[u][k] = ((k & 2) ? lx.l1 : lx.l0) * ((k & 1) ? ly.l1 : ly.l0);
+                const int64_t line = ((int64_t)(xi + 1) * gi.Yp + (yi + 1)) * gi.Zp + 1;
+                v[u][0][k] = Vec<T>::load_raw(in_b + (line + lz.i0) * ld_in);
+                v[u][1][k] = Vec<T>::load_raw(in_b + (line + lz.i1) * ld_in);
             }
-        };
-        int c_i0 = -1, c_i1 = -1;
-        float p0[N], p1[N];
-        for (int zp = 0; zp < go.Zp; ++zp) {
-            const Lerp lz = axis_lerp(clampi(zp - 1, 0, go.Z - 1), gi.Z, sz);
-            if (lz.i0 != c_i0) {
-                if (lz.i0 == c_i1) {
+        }
 #pragma unroll
-                    for (int i = 0; i < N; ++i) p0[i] = p1[i];
-                } else {
-                    plane(lz.i0, p0);
-                }
-                c_i0 = lz.i0;
-            }
-            if (lz.i1 != c_i1) {
-                if (lz.i1 == c_i0) {
+        for (int u = 0; u < U; ++u) {
+            const uint32_t r = r0 + u * stride;
+            if (r >= total) break;
+            float p[2][N];
 #pragma unroll
-                    for (int i = 0; i < N; ++i) p1[i] = p0[i];
-                } else {
-                    plane(lz.i1, p1);
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) p[h][i] = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float t[N];
+                    Vec<T>::unpack(v[u][h][k], t);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) p[h][i] = fmaf(wxy[u][k], t[i], p[h][i]);
                 }
-                c_i1 = lz.i1;
             }
             float acc[N];
 #pragma unroll
-            for (int i = 0; i < N; ++i) acc[i] = fmaf(lz.l0, p0[i], lz.l1 * p1[i]);
-            Vec<T>::store(dst + (int64_t)zp * ld_out, acc);
+            for (int i = 0; i < N; ++i) acc[i] = fmaf(wz[u][0], p[0][i], wz[u][1] * p[1][i]);
+            Vec<T>::store(out_b + (int64_t)r * ld_out, acc);
         }
     }
 }
@@ -415,10 +461,24 @@ int tdb_decode_output(const void* act, int ld, const float* w, const float* b, f
     const int blocks = grid_for((int64_t)B * X * Y * Z);
     const size_t smem = (size_t)(F * dim + F) * sizeof(float);
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == TDB_BF16)
-        decode_output_kernel<bf16><<<blocks, kThreads, smem, s>>>((const bf16*)act, ld, w, b, out, g, dim, F, by_vox, by_z, by_y);
-    else
-        decode_output_kernel<float><<<blocks, kThreads, smem, s>>>((const float*)act, ld, w, b, out, g, dim, F, by_vox, by_z, by_y);
+    const int dv = dim / n;
+#define TDB_DECODE(DV)                                                                                                                \
+    case DV:                                                                                                                          \
+        if (dtype == TDB_BF16)                                                                                                        \
+            decode_output_kernel<bf16, DV><<<blocks, kThreads, smem, s>>>((const bf16*)act, ld, w, b, out, g, dim, F, by_vox, by_z, by_y); \
+        else                                                                                                                          \
+            decode_output_kernel<float, DV><<<blocks, kThreads, smem, s>>>((const float*)act, ld, w, b, out, g, dim, F, by_vox, by_z, by_y); \
+        break;
+    switch (dv) {
+        TDB_DECODE(1)
+        TDB_DECODE(2)
+        TDB_DECODE(4)
+        TDB_DECODE(8)
+        TDB_DECODE(16)
+        default:
+            TDB_REQUIRE(false, TDB_E_UNSUPPORTED, "tdb_decode_output: dim=%d must be 1, 2, 4, 8 or 16 channel vectors of %d", dim, n);
+    }
+#undef TDB_DECODE
     TDB_CHECK_LAUNCH("tdb_decode_output");
     return 0;
 }
@@ -486,7 +546,7 @@ int tdb_trilinear(const void* in, int ld_in, int Xi, int Yi, int Zi, void* out, 
     Grid3 gi(B, Xi, Yi, Zi), go(B, Xo, Yo, Zo);
     const int chunks = C / n;
     TDB_REQUIRE(go.vox_p < (1ll << 31) && chunks <= kThreads, TDB_E_UNSUPPORTED, "tdb_trilinear: grid too large for 32-bit indexing");
-    dim3 grid((unsigned)blocks_per_sample((int64_t)go.Xp * go.Yp * chunks, B), (unsigned)B);
+    dim3 grid((unsigned)blocks_per_sample(go.vox_p * chunks, B), (unsigned)B);
     const RowSplit split = make_split(go);
     auto scale_of = [](int n_in, int n_out) { return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.0f; };
     const float sx = scale_of(Xi, Xo), sy = scale_of(Yi, Yo), sz = scale_of(Zi, Zo);

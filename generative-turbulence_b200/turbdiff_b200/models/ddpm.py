@@ -412,16 +412,29 @@ class GaussianDiffusion(nn.Module):
             from tqdm.auto import tqdm
 
             steps = tqdm(steps, desc="sampling loop time step", total=T, position=1)
+        main = torch.cuda.current_stream()
+        rng = st.get("rng_stream")
+        if rng is None:
+            rng = st["rng_stream"] = torch.cuda.Stream(device=dev)
         for t in steps:
             t_dev.fill_(t)
             t_vec.fill_(t)
+            if t > 0:
+                # the step's Gaussian draws do not depend on eps: they are issued (same generator, same order as the
+                # reference: z, then z' for the boundary cells) on a side stream and overlap the denoiser
+                rng.wait_stream(main)
+                with torch.cuda.stream(rng):
+                    z = torch.randn_like(x_t)
+                    z_bc = torch.randn_like(x_bcs) if self.noise_bcs else None
+                for q in (z, z_bc):
+                    if q is not None:
+                        q.record_stream(main)  # allocated on the side stream, consumed by the update kernel on `main`
+            else:
+                z, z_bc = x_t, (x_t if self.noise_bcs else None)  # ignored at t == 0
             # C is constant along the chain: encode_c_local's half of the input buffer is written once
             eps = eng.forward_graphed(st)
             if t > 0:
-                z = torch.randn_like(x_t)
-                z_bc = torch.randn_like(x_bcs) if self.noise_bcs else None
-            else:
-                z, z_bc = x_t, (x_t if self.noise_bcs else None)  # ignored at t == 0
+                main.wait_stream(rng)
             call("tdb_ddpm_step", x_t.data_ptr(), eps.data_ptr(), z.data_ptr(), ptr(z_bc), x_bcs.data_ptr(), mask.data_ptr(),
                  coef.data_ptr(), t_dev.data_ptr(), x_t.data_ptr(), B, F, nvox, flags | (STEP_FINAL if t == 0 else 0), s())
         out = x_t.clone()  # outputs are freshly allocated; the state buffer is reused by the next chain
