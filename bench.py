@@ -335,6 +335,7 @@ def run_ours(args):
         return eng.forward(x_t, t_vec, cl, c_static=True)  # inside a sampling chain C is constant (as in p_sample_loop)
 
     rng_stream = torch.cuda.Stream(device=dev)
+    side_rng = os.environ.get("TURBDIFF_B200_RNG_STREAM", "1") != "0"
 
     def one_step():
         t = T - 1 - (step_no[0] % (T - 1))
@@ -342,15 +343,20 @@ def run_ours(args):
         t_dev.fill_(t)
         t_vec.fill_(t)
         main = torch.cuda.current_stream()
-        # as GaussianDiffusion.p_sample_loop does: the two Gaussian draws overlap the denoiser on a side stream
-        rng_stream.wait_stream(main)
-        with torch.cuda.stream(rng_stream):
+        if side_rng:
+            # as GaussianDiffusion.p_sample_loop does: the two Gaussian draws overlap the denoiser on a side stream
+            rng_stream.wait_stream(main)
+            with torch.cuda.stream(rng_stream):
+                z = torch.randn_like(x_t)
+                z_bc = torch.randn_like(x_bcs)
+            z.record_stream(main)
+            z_bc.record_stream(main)
+            eps = unet()
+            main.wait_stream(rng_stream)
+        else:
+            eps = unet()
             z = torch.randn_like(x_t)
             z_bc = torch.randn_like(x_bcs)
-        z.record_stream(main)
-        z_bc.record_stream(main)
-        eps = unet()
-        main.wait_stream(rng_stream)
         _lib.call("tdb_ddpm_step", x_t.data_ptr(), eps.data_ptr(), z.data_ptr(), z_bc.data_ptr(), x_bcs.data_ptr(), mask.data_ptr(),
                   coef.data_ptr(), t_dev.data_ptr(), x_t.data_ptr(), B, 4, nvox, flags, _lib.stream_ptr())
 
@@ -474,7 +480,7 @@ def run_ours(args):
         # the reference's optimiser (torch.optim.RAdam, diffusion.py:216) with Lightning's gradient_clip_val 0.1 (norm):
         # both in the fused two-launch step
         opt = FusedRAdam(model.parameters(), lr=1e-4, max_grad_norm=0.1)
-        reducer = GradientAllReduce(model.parameters())
+        reducer = GradientAllReduce(model.parameters()).attach(model)  # all-reduce on the backward program's flat gradient buffer
 
         class MD:
             pass
@@ -524,7 +530,7 @@ def run_ours(args):
         train = {"steps_per_sec": 1e3 / float(tt.item()), "ms_per_step": float(tt.item()), "batch_per_gpu": TB, "global_batch": TB * world,
                  "kernel_ms_per_step": train_prof, "host_enqueue_ms_per_step": host_ms,
                  "loss": float(loss.item()), "kernel_launches_per_step": n_train_launches,
-                 "includes": "q_sample + U-Net forward + backward + bucketed NCCL gradient all-reduce (N>1) + fused clip_grad_norm(0.1) + RAdam step (turbdiff_b200.optim.FusedRAdam)",
+                 "includes": "q_sample + U-Net forward + backward + NCCL gradient all-reduce on the flat gradient buffer (N>1) + fused clip_grad_norm(0.1) + RAdam step (turbdiff_b200.optim.FusedRAdam)",
                  "train_flops_per_step": 3 * conv_flops_per_sample(geo.padded) * TB}
         train["tflops"] = train["train_flops_per_step"] / (train["ms_per_step"] * 1e-3) / 1e12
         model.eval()

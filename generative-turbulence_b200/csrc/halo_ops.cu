@@ -86,59 +86,41 @@ encode_input_kernel(const float* __restrict__ x, const float* __restrict__ c_loc
 }
 
 // ---------------------------------------------------------------- decode[1]
-// DV = dim / N channel vectors per voxel, all loaded (for U voxels) before the first is used.
-template <typename T, int DV>
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
 decode_output_kernel(const T* __restrict__ act, int ld, const float* __restrict__ w,
                      const float* __restrict__ bias, float* __restrict__ out, Grid3 g, int dim, int F, FastDiv by_vox, FastDiv by_z,
                      FastDiv by_y) {
     constexpr int N = Vec<T>::N;
-    constexpr int U = DV >= 8 ? 1 : 2;
     extern __shared__ float sw[];  // F*dim weights + F biases
     for (int i = threadIdx.x; i < F * dim; i += blockDim.x) sw[i] = w[i];
     for (int i = threadIdx.x; i < F; i += blockDim.x) sw[F * dim + i] = bias[i];
     __syncthreads();
     const int64_t nvox = (int64_t)g.X * g.Y * g.Z;
     const uint32_t total = (uint32_t)(g.B * nvox);
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t idx0 = blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += stride * U) {
-        uint4 raw[U][DV];
-        int bs[U];
-        uint32_t vs[U];
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        uint32_t bb, v, q, zz, xx, yy;
+        by_vox.divmod(idx, bb, v);
+        by_z.divmod(v, q, zz);
+        by_y.divmod(q, xx, yy);
+        const int b = (int)bb, x = (int)xx, y = (int)yy, z = (int)zz;
+        const T* a = act + g.row(b, x, y, z) * ld;
+        float acc[8];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t idx = min(idx0 + u * stride, total - 1);
-            uint32_t bb, v, q, zz, xx, yy;
-            by_vox.divmod(idx, bb, v);
-            by_z.divmod(v, q, zz);
-            by_y.divmod(q, xx, yy);
-            bs[u] = (int)bb;
-            vs[u] = v;
-            const T* a = act + g.row((int)bb, (int)xx, (int)yy, (int)zz) * ld;
-#pragma unroll
-            for (int k = 0; k < DV; ++k) raw[u][k] = Vec<T>::load_raw(a + k * N);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (idx0 + u * stride >= total) break;
-            float acc[8];
-#pragma unroll
-            for (int f = 0; f < 8; ++f) acc[f] = f < F ? sw[F * dim + f] : 0.0f;
-#pragma unroll
-            for (int k = 0; k < DV; ++k) {
-                float vv[N];
-                Vec<T>::unpack(raw[u][k], vv);
-#pragma unroll
-                for (int f = 0; f < 8; ++f)
-                    if (f < F) {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) acc[f] = fmaf(sw[f * dim + k * N + i], vv[i], acc[f]);
-                    }
-            }
+        for (int f = 0; f < 8; ++f) acc[f] = f < F ? sw[F * dim + f] : 0.0f;
+        for (int c0 = 0; c0 < dim; c0 += N) {
+            float vv[N];
+            Vec<T>::load(a + c0, vv);
 #pragma unroll
             for (int f = 0; f < 8; ++f)
-                if (f < F) out[((int64_t)bs[u] * F + f) * nvox + vs[u]] = acc[f];
+                if (f < F) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) acc[f] = fmaf(sw[f * dim + c0 + i], vv[i], acc[f]);
+                }
         }
+#pragma unroll
+        for (int f = 0; f < 8; ++f)
+            if (f < F) out[((int64_t)b * F + f) * nvox + v] = acc[f];
     }
 }
 
@@ -221,32 +203,25 @@ pointwise_kernel(const T* __restrict__ raw, int ld_raw, const double* __restrict
                  T* __restrict__ out, int ld_out, Grid3 g, int C, int G, float eps, unsigned flags,
                  RowSplit split, int chunks) {
     constexpr int N = Vec<T>::N;
+    extern __shared__ float s_coef[];  // [C][2]: per-channel scale / offset of this sample
     const int b = blockIdx.y;
     const int vox_step = kThreads / chunks;
     const int ch = threadIdx.x % chunks, lane_vox = threadIdx.x / chunks;
-    if (lane_vox >= vox_step) return;
     const int c0 = ch * N;
-    float ca[N], co[N];
+    // the affine coefficients depend on (sample, channel) only: computed once per block (one thread per channel, the
+    // group moments in double once per thread), not once per thread - on the small levels the per-thread prologue
+    // (8 channels x gamma / beta / FiLM / moments) used to cost more than the rows themselves
     {
         const int cpg = C / G;
         const double inv_n = 1.0 / ((double)cpg * g.X * g.Y * g.Z);
-        // group moments: the (few) double-precision operations are done once per group, not per channel -
-        // fp64 issues at 1/64 rate on this part and used to dominate the small launches
-        int g_cached = -1;
-        float mean_f = 0.0f, rstd = 1.0f;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const int c = c0 + i;
+        for (int c = threadIdx.x; c < C; c += kThreads) {
             float a = 1.0f, o = 0.0f;
             if (stats) {
                 const int gi = c / cpg;
-                if (gi != g_cached) {
-                    const double mean = stats[((int64_t)b * G + gi) * 2] * inv_n;
-                    const double var = fma(-mean, mean, stats[((int64_t)b * G + gi) * 2 + 1] * inv_n);
-                    mean_f = (float)mean;
-                    rstd = 1.0f / sqrtf(fmaxf((float)var, 0.0f) + eps);
-                    g_cached = gi;
-                }
+                const double mean = stats[((int64_t)b * G + gi) * 2] * inv_n;
+                const double var = fma(-mean, mean, stats[((int64_t)b * G + gi) * 2 + 1] * inv_n);
+                const float mean_f = (float)mean;
+                const float rstd = 1.0f / sqrtf(fmaxf((float)var, 0.0f) + eps);
                 a = rstd * gamma[c];
                 o = beta[c] - mean_f * a;
             }
@@ -256,9 +231,17 @@ pointwise_kernel(const T* __restrict__ raw, int ld_raw, const double* __restrict
                 a *= sc;
                 o = fmaf(o, sc, sh);
             }
-            ca[i] = a;
-            co[i] = o;
+            s_coef[2 * c] = a;
+            s_coef[2 * c + 1] = o;
         }
+    }
+    __syncthreads();
+    if (lane_vox >= vox_step) return;
+    float ca[N], co[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        ca[i] = s_coef[2 * (c0 + i)];
+        co[i] = s_coef[2 * (c0 + i) + 1];
     }
     const bool interior_only = flags & TDB_PW_NOHALO;
     const bool act = flags & TDB_PW_SILU;
@@ -320,14 +303,84 @@ __device__ __forceinline__ Lerp axis_lerp(int o, int n_in, float scale) {
     return r;
 }
 
-// grid = (blocks per sample, B).  Gather form: a thread owns one 16-byte channel vector of one OUTPUT row (haloed rows
+// grid = (blocks per sample, B)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+trilinear_kernel(const T* __restrict__ in, int ld_in, Grid3 gi, T* __restrict__ out, int ld_out, Grid3 go, int C,
+                 RowSplit split, int chunks, float sx, float sy, float sz) {
+    constexpr int N = Vec<T>::N;
+    const int b = blockIdx.y;
+    const int vox_step = kThreads / chunks;
+    const int ch = threadIdx.x % chunks, lane_vox = threadIdx.x / chunks;
+    if (lane_vox >= vox_step) return;
+    const int c0 = ch * N;
+    // line walker over the output grid: x/y interpolation and the four input line bases once per (x, y) line
+    const uint32_t lines = (uint32_t)(go.Xp * go.Yp);
+    for (uint32_t line = blockIdx.x * vox_step + lane_vox; line < lines; line += gridDim.x * vox_step) {
+        uint32_t xq, yq;
+        split.by_y.divmod(line, xq, yq);
+        const Lerp lx = axis_lerp(clampi((int)xq - 1, 0, go.X - 1), gi.X, sx);
+        const Lerp ly = axis_lerp(clampi((int)yq - 1, 0, go.Y - 1), gi.Y, sy);
+        const T* base[4];
+        float wxy[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xi = (k & 2) ? lx.i1 : lx.i0, yi = (k & 1) ? ly.i1 : ly.i0;
+            base[k] = in + gi.row(b, xi, yi, 0) * ld_in + c0;
+            wxy[k] = ((k & 2) ? lx.l1 : lx.l0) * ((k & 1) ? ly.l1 : ly.l0);
+        }
+        T* dst = out + ((int64_t)b * go.vox_p + (int64_t)line * go.Zp) * ld_out + c0;
+        // the x/y-interpolated input planes P(iz) are kept in registers while the walk moves along z: an output is
+        // l0*P(i0) + l1*P(i1), and when upsampling each P is reused by about two outputs (i0/i1 are warp-uniform)
+        auto plane = [&](int iz, float (&pl)[N]) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) pl[i] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float v[N];
+                Vec<T>::load(base[k] + (int64_t)iz * ld_in, v);
+#pragma unroll
+                for (int i = 0; i < N; ++i) pl[i] = fmaf(wxy[k], v[i], pl[i]);
+            }
+        };
+        int c_i0 = -1, c_i1 = -1;
+        float p0[N], p1[N];
+        for (int zp = 0; zp < go.Zp; ++zp) {
+            const Lerp lz = axis_lerp(clampi(zp - 1, 0, go.Z - 1), gi.Z, sz);
+            if (lz.i0 != c_i0) {
+                if (lz.i0 == c_i1) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) p0[i] = p1[i];
+                } else {
+                    plane(lz.i0, p0);
+                }
+                c_i0 = lz.i0;
+            }
+            if (lz.i1 != c_i1) {
+                if (lz.i1 == c_i0) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) p1[i] = p0[i];
+                } else {
+                    plane(lz.i1, p1);
+                }
+                c_i1 = lz.i1;
+            }
+            float acc[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) acc[i] = fmaf(lz.l0, p0[i], lz.l1 * p1[i]);
+            Vec<T>::store(dst + (int64_t)zp * ld_out, acc);
+        }
+    }
+}
+
+// DOWN-sampling variant, grid = (blocks per sample, B).  Gather form: a thread owns one 16-byte channel vector of one OUTPUT row (haloed rows
 // included: their source is the clamped interior voxel), fetches its eight source vectors and blends them - x/y first,
 // then z, the order ATen's separable kernel and the fp32 parity tests use.  Consecutive threads walk the channel vectors
 // of a row and then the next row (= next z), so stores are fully coalesced and the (up to 8x smaller or 8x larger)
 // source is read through L1/L2; U rows per trip keep 16 independent loads in flight per thread.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-trilinear_kernel(const T* __restrict__ in, int ld_in, Grid3 gi, T* __restrict__ out, int ld_out, Grid3 go, int C,
+trilinear_gather_kernel(const T* __restrict__ in, int ld_in, Grid3 gi, T* __restrict__ out, int ld_out, Grid3 go, int C,
                  RowSplit split, int chunks, float sx, float sy, float sz) {
     constexpr int N = Vec<T>::N;
     constexpr int U = 2;
@@ -461,24 +514,10 @@ int tdb_decode_output(const void* act, int ld, const float* w, const float* b, f
     const int blocks = grid_for((int64_t)B * X * Y * Z);
     const size_t smem = (size_t)(F * dim + F) * sizeof(float);
     cudaStream_t s = (cudaStream_t)stream;
-    const int dv = dim / n;
-#define TDB_DECODE(DV)                                                                                                                \
-    case DV:                                                                                                                          \
-        if (dtype == TDB_BF16)                                                                                                        \
-            decode_output_kernel<bf16, DV><<<blocks, kThreads, smem, s>>>((const bf16*)act, ld, w, b, out, g, dim, F, by_vox, by_z, by_y); \
-        else                                                                                                                          \
-            decode_output_kernel<float, DV><<<blocks, kThreads, smem, s>>>((const float*)act, ld, w, b, out, g, dim, F, by_vox, by_z, by_y); \
-        break;
-    switch (dv) {
-        TDB_DECODE(1)
-        TDB_DECODE(2)
-        TDB_DECODE(4)
-        TDB_DECODE(8)
-        TDB_DECODE(16)
-        default:
-            TDB_REQUIRE(false, TDB_E_UNSUPPORTED, "tdb_decode_output: dim=%d must be 1, 2, 4, 8 or 16 channel vectors of %d", dim, n);
-    }
-#undef TDB_DECODE
+    if (dtype == TDB_BF16)
+        decode_output_kernel<bf16><<<blocks, kThreads, smem, s>>>((const bf16*)act, ld, w, b, out, g, dim, F, by_vox, by_z, by_y);
+    else
+        decode_output_kernel<float><<<blocks, kThreads, smem, s>>>((const float*)act, ld, w, b, out, g, dim, F, by_vox, by_z, by_y);
     TDB_CHECK_LAUNCH("tdb_decode_output");
     return 0;
 }
@@ -522,15 +561,17 @@ int tdb_pointwise(const void* raw, int ld_raw, const double* stats, const float*
     Grid3 g(B, X, Y, Z);
     const int chunks = C / n;
     TDB_REQUIRE(g.vox_p < (1ll << 31) && chunks <= kThreads, TDB_E_UNSUPPORTED, "tdb_pointwise: grid too large for 32-bit indexing");
-    dim3 grid((unsigned)blocks_per_sample(g.vox_p * chunks, B), (unsigned)B);
+    // at least two trips of four rows per thread: the per-block prologue and the launch tail stay small on the deep levels
+    dim3 grid((unsigned)blocks_per_sample(ceil_div(g.vox_p * chunks, 8), B), (unsigned)B);
     const RowSplit split = make_split(g);
     cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem = (size_t)2 * C * sizeof(float);
     if (dtype == TDB_BF16)
-        pointwise_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)raw, ld_raw, stats, gamma, beta, film, film_ld,
+        pointwise_kernel<bf16><<<grid, kThreads, smem, s>>>((const bf16*)raw, ld_raw, stats, gamma, beta, film, film_ld,
                                                              (const bf16*)res, ld_res, (bf16*)out, ld_out, g, C, G, eps,
                                                              flags, split, chunks);
     else
-        pointwise_kernel<float><<<grid, kThreads, 0, s>>>((const float*)raw, ld_raw, stats, gamma, beta, film, film_ld,
+        pointwise_kernel<float><<<grid, kThreads, smem, s>>>((const float*)raw, ld_raw, stats, gamma, beta, film, film_ld,
                                                               (const float*)res, ld_res, (float*)out, ld_out, g, C, G, eps,
                                                               flags, split, chunks);
     TDB_CHECK_LAUNCH("tdb_pointwise");
@@ -546,11 +587,22 @@ int tdb_trilinear(const void* in, int ld_in, int Xi, int Yi, int Zi, void* out, 
     Grid3 gi(B, Xi, Yi, Zi), go(B, Xo, Yo, Zo);
     const int chunks = C / n;
     TDB_REQUIRE(go.vox_p < (1ll << 31) && chunks <= kThreads, TDB_E_UNSUPPORTED, "tdb_trilinear: grid too large for 32-bit indexing");
-    dim3 grid((unsigned)blocks_per_sample(go.vox_p * chunks, B), (unsigned)B);
+    dim3 grid((unsigned)blocks_per_sample((int64_t)go.Xp * go.Yp * chunks, B), (unsigned)B);
     const RowSplit split = make_split(go);
     auto scale_of = [](int n_in, int n_out) { return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.0f; };
     const float sx = scale_of(Xi, Xo), sy = scale_of(Yi, Yo), sz = scale_of(Zi, Zo);
     cudaStream_t s = (cudaStream_t)stream;
+    if ((int64_t)Xo * Yo * Zo < (int64_t)Xi * Yi * Zi) {
+        // down-sampling: (nearly) every input voxel is read exactly once, so the gather form costs no extra traffic and
+        // exposes rows x chunks parallelism (the line walker has only lines x chunks work items: 4.5 blocks per SM at level 0)
+        dim3 ggrid((unsigned)blocks_per_sample(ceil_div(go.vox_p * chunks, 2), B), (unsigned)B);
+        if (dtype == TDB_BF16)
+            trilinear_gather_kernel<bf16><<<ggrid, kThreads, 0, s>>>((const bf16*)in, ld_in, gi, (bf16*)out, ld_out, go, C, split, chunks, sx, sy, sz);
+        else
+            trilinear_gather_kernel<float><<<ggrid, kThreads, 0, s>>>((const float*)in, ld_in, gi, (float*)out, ld_out, go, C, split, chunks, sx, sy, sz);
+        TDB_CHECK_LAUNCH("tdb_trilinear");
+        return 0;
+    }
     if (dtype == TDB_BF16)
         trilinear_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)in, ld_in, gi, (bf16*)out, ld_out, go, C, split, chunks, sx, sy, sz);
     else

@@ -53,6 +53,8 @@ class _Denoise(torch.autograd.Function):
         if torch.is_tensor(grads):
             # graph replay: one flat buffer in parameter order; a single copy detaches it from the graph's static memory
             tg = eng._train_replay
+            if eng.grad_sync is not None:
+                eng.grad_sync(grads)  # data-parallel exchange on the flat buffer (parallel.GradientAllReduce.attach)
             out = [v.view(shape) for v, shape in zip(grads.clone().split(tg["sizes"]), tg["shapes"])]
             return (None, None, None, g_c, *out)
         out = []

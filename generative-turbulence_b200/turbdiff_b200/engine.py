@@ -79,6 +79,7 @@ class DenoiserEngine:
         self.win = True       # row-window CTA-pair kernel for resident-weight layers with Cout >= 64
         self._level_zp = {}   # level -> Z + 2 of the plan in use (the window kernel needs Z + 2 <= 63)
         self.fold_wide = True
+        self.win_center = os.environ.get("TURBDIFF_B200_WIN_CENTER", "1") != "0"  # bottleneck convolutions on the row-window pair kernel
         self.fuse_proj = True
         self.use_graph = True  # p_sample_loop replays the denoiser from a CUDA graph
         # training: weight repack + forward program and the backward program are replayed from two CUDA graphs
@@ -93,6 +94,7 @@ class DenoiserEngine:
         self._wgen = 0        # bumped whenever _wcache is REPLACED: captured sampler graphs hold its addresses
         self.graph_fallbacks = 0  # CUDA-graph captures that failed and fell back to the eager launch programs
         self._last_train_key = None
+        self.grad_sync = None  # optional hook(flat_grads): in-place data-parallel reduction of the backward program's flat gradient buffer
 
         m = model
         un = m.u_net
@@ -173,9 +175,14 @@ class DenoiserEngine:
         if cout in (16, 32, 64):
             pair = self.fold2 and cin % 64 == 0 and cout in (32, 64) and 9 * cin * 3 * cout * 2 > 112 * 1024
             return "fold2" if pair else "fold"
-        if self.fold2 and self.fold_wide and cout % 128 == 0 and cout <= 512 and cin % 64 == 0 and level <= self.model.u_net_levels - 1:
+        if self.fold2 and self.fold_wide and cout % 128 == 0 and cout <= 512 and cin % 64 == 0:
             # wide layers: N tiles of 128 channels with streamed weights; the row-window kernel double-buffers its
-            # accumulators and keeps all 128 rows of a tile (3-20 % faster than the kz-folded pair kernel here)
+            # accumulators and keeps all 128 rows of a tile (3-20 % faster than the kz-folded pair kernel here).
+            # The bottleneck level runs on it too (round 2): with 2800 haloed rows at B = 8 the per-tap split-K kernel
+            # pushed every weight byte through the L2 -> SM fabric 22 times (one 128-row M tile each) and needed a
+            # finalize and a moments pass (48 + 6 + 9 us per convolution); 256-row pair tiles with fused moments do not.
+            if level == self.model.u_net_levels and not self.win_center:
+                return None
             return "win" if (self.win and zp <= 63) else "fold2"
         return None
 

@@ -416,10 +416,14 @@ class GaussianDiffusion(nn.Module):
         rng = st.get("rng_stream")
         if rng is None:
             rng = st["rng_stream"] = torch.cuda.Stream(device=dev)
+        side_rng = os.environ.get("TURBDIFF_B200_RNG_STREAM", "1") != "0"
         for t in steps:
             t_dev.fill_(t)
             t_vec.fill_(t)
-            if t > 0:
+            if t > 0 and not side_rng:
+                z = torch.randn_like(x_t)
+                z_bc = torch.randn_like(x_bcs) if self.noise_bcs else None
+            elif t > 0:
                 # the step's Gaussian draws do not depend on eps: they are issued (same generator, same order as the
                 # reference: z, then z' for the boundary cells) on a side stream and overlap the denoiser
                 rng.wait_stream(main)
@@ -433,7 +437,7 @@ class GaussianDiffusion(nn.Module):
                 z, z_bc = x_t, (x_t if self.noise_bcs else None)  # ignored at t == 0
             # C is constant along the chain: encode_c_local's half of the input buffer is written once
             eps = eng.forward_graphed(st)
-            if t > 0:
+            if t > 0 and side_rng:
                 main.wait_stream(rng)
             call("tdb_ddpm_step", x_t.data_ptr(), eps.data_ptr(), z.data_ptr(), ptr(z_bc), x_bcs.data_ptr(), mask.data_ptr(),
                  coef.data_ptr(), t_dev.data_ptr(), x_t.data_ptr(), B, F, nvox, flags | (STEP_FINAL if t == 0 else 0), s())

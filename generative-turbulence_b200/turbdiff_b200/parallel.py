@@ -59,19 +59,32 @@ def gather_shards(local: torch.Tensor, n_total: int, dst: int = 0):
 
 
 class GradientAllReduce:
-    """Bucketed average all-reduce of `.grad` over the data-parallel group.
+    """Average all-reduce of the gradients over the data-parallel group (the ONE exchange step of the training path).
 
-    Parameters are packed (in registration order) into flat fp32 buckets of ~`bucket_mb`; every
-    bucket is one asynchronous all-reduce, so the first buckets travel while later gradients are
-    still being unpacked / clipped.  With equal per-rank batch sizes the average of the rank losses'
-    gradients equals the gradient of the global-batch loss (the loss is a mean over samples)."""
+    Fast path (``attach(denoiser)``): the backward launch program already leaves every denoiser gradient in ONE flat
+    fp32 buffer (engine._capture_train), so the exchange is a handful of large NCCL all-reduces over slices of that
+    buffer, issued from inside ``backward`` before the gradients are handed to autograd - no per-parameter packing,
+    no ~420 small torch ops on the host.  Parameters that are not part of an attached denoiser (e.g. the task's
+    cell-type embedding) and eager-mode training use the generic path: flat fp32 buckets of ~``bucket_mb``, one
+    asynchronous all-reduce per bucket.  With equal per-rank batch sizes the average of the rank losses' gradients
+    equals the gradient of the global-batch loss (the loss is a mean over samples, ddpm.py:848-852)."""
 
-    def __init__(self, params, bucket_mb: float = 64.0, group=None):
+    def __init__(self, params, bucket_mb: float = 64.0, group=None, flat_chunks: int = 4):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
+        self.bucket_mb = bucket_mb
+        self.flat_chunks = max(1, int(flat_chunks))
+        self._flat_synced: set[int] = set()   # ids of parameters whose gradient was already reduced inside backward
+        self._attached = []
+        self._buckets_for = None
         self.buckets: list[list[torch.nn.Parameter]] = []
-        cur, cur_bytes, cap = [], 0, int(bucket_mb * 2**20)
-        for p in self.params:
+        self._flat: list[torch.Tensor | None] = []
+        self._make_buckets(self.params)
+
+    def _make_buckets(self, params):
+        self.buckets = []
+        cur, cur_bytes, cap = [], 0, int(self.bucket_mb * 2**20)
+        for p in params:
             cur.append(p)
             cur_bytes += p.numel() * 4
             if cur_bytes >= cap:
@@ -79,32 +92,69 @@ class GradientAllReduce:
                 cur, cur_bytes = [], 0
         if cur:
             self.buckets.append(cur)
-        self._flat: list[torch.Tensor | None] = [None] * len(self.buckets)
+        self._flat = [None] * len(self.buckets)
+        self._buckets_for = tuple(id(p) for p in params)
 
+    # ---- fast path: all-reduce the backward program's flat gradient buffer ----------------------------------------
+    def attach(self, denoiser):
+        """Reduce `denoiser`'s gradients inside its backward (engine.grad_sync hook).  Returns self."""
+        eng = denoiser.engine()
+        ids = {id(p) for p in denoiser.parameters()}
+
+        def sync(flat: torch.Tensor):
+            if self._world() == 1:
+                return
+            self.reduce_flat(flat)
+            self._flat_synced |= ids
+
+        eng.grad_sync = sync
+        self._attached.append(denoiser)
+        return self
+
+    def _world(self):
+        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    def reduce_flat(self, flat: torch.Tensor):
+        """In-place average of a flat gradient buffer over the group: `flat_chunks` asynchronous all-reduces (the first
+        slices travel while the later ones are being enqueued), then one stream-ordered wait."""
+        world = self._world()
+        avg = dist.get_backend(self.group) == "nccl"
+        n = flat.numel()
+        step = -(-n // self.flat_chunks)
+        work = [dist.all_reduce(flat[i : i + step], op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.group, async_op=True)
+                for i in range(0, n, step)]
+        for w in work:
+            w.wait()
+        if not avg:
+            flat.div_(world)
+
+    # ---- generic path --------------------------------------------------------------------------------------------
     def __call__(self):
-        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+        if self._world() == 1:
+            self._flat_synced.clear()
             return
-        world = dist.get_world_size(self.group)
+        todo = [p for p in self.params if id(p) not in self._flat_synced]
+        self._flat_synced.clear()
+        if not todo:
+            return
+        if self._buckets_for != tuple(id(p) for p in todo):
+            self._make_buckets(todo)
+        world = self._world()
         work = []
         for i, bucket in enumerate(self.buckets):
             n = sum(p.numel() for p in bucket)
             flat = self._flat[i]
             if flat is None or flat.device != bucket[0].device:
                 flat = self._flat[i] = torch.empty(n, dtype=torch.float32, device=bucket[0].device)
-            off = 0
-            for p in bucket:
-                g = p.grad if p.grad is not None else torch.zeros_like(p)
-                flat[off : off + p.numel()].copy_(g.reshape(-1))
-                off += p.numel()
+            views = list(flat.split([p.numel() for p in bucket]))
+            torch._foreach_copy_(views, [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in bucket])
             work.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         for i, bucket in enumerate(self.buckets):
             work[i].wait()
             flat = self._flat[i]
-            off = 0
-            for p in bucket:
-                g = flat[off : off + p.numel()].view_as(p) / world
+            flat.div_(world)
+            views = [v.view_as(p) for v, p in zip(flat.split([p.numel() for p in bucket]), bucket)]
+            for p, v in zip(bucket, views):
                 if p.grad is None:
-                    p.grad = g.clone()
-                else:
-                    p.grad.copy_(g)
-                off += p.numel()
+                    p.grad = torch.empty_like(p)
+            torch._foreach_copy_([p.grad for p in bucket], views)

@@ -52,6 +52,31 @@ def _worker(rank, world, port, ret):
             extra.grad = torch.ones(3)
         GradientAllReduce([extra])()
         ok = ok and torch.allclose(extra.grad, torch.full((3,), 1.0 / world))
+        # fast path: the exchange on an attached denoiser's flat gradient buffer (engine.grad_sync hook), after which the
+        # generic call only reduces the parameters that were not covered
+        class _Eng:
+            grad_sync = None
+
+        class _Den(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.a = torch.nn.Parameter(torch.zeros(5))
+                self.b = torch.nn.Parameter(torch.zeros(2, 3))
+                self._eng = _Eng()
+
+            def engine(self):
+                return self._eng
+
+        den = _Den()
+        other = torch.nn.Parameter(torch.zeros(4))
+        red = GradientAllReduce(list(den.parameters()) + [other], flat_chunks=3).attach(den)
+        flat = torch.arange(11.0) * (rank + 1)              # what the backward program would hand out on this rank
+        den.engine().grad_sync(flat)
+        ok = ok and torch.allclose(flat, torch.arange(11.0) * (sum(range(1, world + 1)) / world))
+        den.a.grad, den.b.grad = flat[:5].clone(), flat[5:].view(2, 3).clone()
+        other.grad = torch.full((4,), float(rank))
+        red()                                               # must not reduce den's gradients a second time
+        ok = ok and torch.allclose(den.a.grad, flat[:5]) and torch.allclose(other.grad, torch.full((4,), (world - 1) / 2))
         # gather of sharded "samples" restores the original order on rank 0
         full = torch.arange(10.0).reshape(5, 2)
         mine = full[shard_range(5, rank, world).start : shard_range(5, rank, world).stop]
