@@ -14,27 +14,36 @@ namespace {
 constexpr int kThreads = 256;
 
 struct StepCoef {
-    float recip, recipm1, c1, c2, sigma, sa, s1m;
+    float recip, recipm1, c1, c2, sigma, sa, s1m, plv;  // learned variances: sigma slot = log beta_t, plv = posterior log-variance
 };
 
 __device__ __forceinline__ StepCoef load_coef(const float* __restrict__ coef, int t) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(coef + (int64_t)t * 8));
     const float4 b = __ldg(reinterpret_cast<const float4*>(coef + (int64_t)t * 8 + 4));
-    return StepCoef{a.x, a.y, a.z, a.w, b.x, b.y, b.z};
+    return StepCoef{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+}
+
+// learned variances (ddpm.py:732-741, 804-805): std = exp(lerp(log beta_t, posterior log-variance, sigmoid(v)) / 2) per voxel;
+// torch.lerp's two-sided formula (weight < 0.5: start + w*(end - start), else end - (end - start)*(1 - w))
+__device__ __forceinline__ float learned_sigma(float vw, const StepCoef& k) {
+    const float w = 1.0f / (1.0f + expf(-vw));
+    const float d = k.plv - k.sigma;
+    const float lv = w < 0.5f ? fmaf(w, d, k.sigma) : fmaf(-d, 1.0f - w, k.plv);
+    return expf(0.5f * lv);
 }
 
 __device__ __forceinline__ float step_one(float xt, float e, float z, float zbc, float xb, bool inside,
-                                          const StepCoef& k, bool t0, unsigned flags) {
+                                          const StepCoef& k, bool t0, unsigned flags, float sigma) {
     float x0 = __fsub_rn(__fmul_rn(k.recip, xt), __fmul_rn(k.recipm1, e));
     if (!(flags & TDB_STEP_NOISE_BCS) && !inside) x0 = xt;
     if (flags & TDB_STEP_CLIP) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
     float x = __fadd_rn(__fmul_rn(k.c1, x0), __fmul_rn(k.c2, xt));
     if (!t0) {
         if (flags & TDB_STEP_NOISE_BCS) {
-            x = __fadd_rn(x, __fmul_rn(k.sigma, z));
+            x = __fadd_rn(x, __fmul_rn(sigma, z));
             if (!inside) x = __fadd_rn(__fmul_rn(k.sa, xb), __fmul_rn(k.s1m, zbc));
         } else {
-            x = __fadd_rn(x, __fmul_rn(k.sigma, inside ? z : 0.0f));
+            x = __fadd_rn(x, __fmul_rn(sigma, inside ? z : 0.0f));
         }
     }
     if ((flags & TDB_STEP_FINAL) && !inside) x = xb;
@@ -47,10 +56,14 @@ __global__ void __launch_bounds__(kThreads)
 ddpm_step_kernel(const float* __restrict__ x_t, const float* __restrict__ eps, const float* __restrict__ z,
                  const float* __restrict__ z_bc, const float* __restrict__ x_bcs, const uint8_t* __restrict__ mask,
                  const float* __restrict__ coef, const int32_t* __restrict__ t_ptr, float* __restrict__ x_out,
-                 int64_t rows, int64_t nvox, unsigned flags) {
+                 int64_t rows, int64_t nvox, unsigned flags, int F) {
     const int t = *t_ptr;
     const StepCoef k = load_coef(coef, t);
     const bool t0 = t == 0;
+    // learned variances: eps is the (B, 2F, nvox) model output - noise prediction in the first F channels of a sample,
+    // variance weights in the last F
+    const bool lvar = flags & TDB_STEP_LEARNED_VAR;
+    const int64_t fn = (int64_t)F * nvox;
     const bool need_z = !t0;
     const bool need_zbc = !t0 && (flags & TDB_STEP_NOISE_BCS);
     const bool need_xb = need_zbc || (flags & TDB_STEP_FINAL);
@@ -59,23 +72,30 @@ ddpm_step_kernel(const float* __restrict__ x_t, const float* __restrict__ eps, c
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t v = (i % per_row) * VEC;
         const int64_t off = i * VEC;
+        const int64_t eoff = lvar ? off + (off / fn) * fn : off;
         if constexpr (VEC == 4) {
             const float4 xt = *reinterpret_cast<const float4*>(x_t + off);
-            const float4 e = *reinterpret_cast<const float4*>(eps + off);
+            const float4 e = *reinterpret_cast<const float4*>(eps + eoff);
+            float4 sg = make_float4(k.sigma, k.sigma, k.sigma, k.sigma);
+            if (lvar && !t0) {
+                const float4 vw = *reinterpret_cast<const float4*>(eps + eoff + fn);
+                sg = make_float4(learned_sigma(vw.x, k), learned_sigma(vw.y, k), learned_sigma(vw.z, k), learned_sigma(vw.w, k));
+            }
             const uchar4 m = *reinterpret_cast<const uchar4*>(mask + v);
             float4 zz = make_float4(0, 0, 0, 0), zb = zz, xb = zz;
             if (need_z) zz = *reinterpret_cast<const float4*>(z + off);
             if (need_zbc) zb = *reinterpret_cast<const float4*>(z_bc + off);
             if (need_xb) xb = *reinterpret_cast<const float4*>(x_bcs + off);
             float4 o;
-            o.x = step_one(xt.x, e.x, zz.x, zb.x, xb.x, m.x != 0, k, t0, flags);
-            o.y = step_one(xt.y, e.y, zz.y, zb.y, xb.y, m.y != 0, k, t0, flags);
-            o.z = step_one(xt.z, e.z, zz.z, zb.z, xb.z, m.z != 0, k, t0, flags);
-            o.w = step_one(xt.w, e.w, zz.w, zb.w, xb.w, m.w != 0, k, t0, flags);
+            o.x = step_one(xt.x, e.x, zz.x, zb.x, xb.x, m.x != 0, k, t0, flags, sg.x);
+            o.y = step_one(xt.y, e.y, zz.y, zb.y, xb.y, m.y != 0, k, t0, flags, sg.y);
+            o.z = step_one(xt.z, e.z, zz.z, zb.z, xb.z, m.z != 0, k, t0, flags, sg.z);
+            o.w = step_one(xt.w, e.w, zz.w, zb.w, xb.w, m.w != 0, k, t0, flags, sg.w);
             *reinterpret_cast<float4*>(x_out + off) = o;
         } else {
-            x_out[off] = step_one(x_t[off], eps[off], need_z ? z[off] : 0.f, need_zbc ? z_bc[off] : 0.f,
-                                  need_xb ? x_bcs[off] : 0.f, mask[v] != 0, k, t0, flags);
+            const float sg = (lvar && !t0) ? learned_sigma(eps[eoff + fn], k) : k.sigma;
+            x_out[off] = step_one(x_t[off], eps[eoff], need_z ? z[off] : 0.f, need_zbc ? z_bc[off] : 0.f,
+                                  need_xb ? x_bcs[off] : 0.f, mask[v] != 0, k, t0, flags, sg);
         }
     }
 }
@@ -242,10 +262,10 @@ int tdb_ddpm_step(const float* x_t, const float* eps, const float* z, const floa
     cudaStream_t s = (cudaStream_t)stream;
     if (vec)
         ddpm_step_kernel<4><<<blocks_for(rows * nvox / 4), kThreads, 0, s>>>(x_t, eps, z, z_bc, x_bcs, mask, coef, t_ptr,
-                                                                              x_out, rows, nvox, flags);
+                                                                              x_out, rows, nvox, flags, F);
     else
         ddpm_step_kernel<1><<<blocks_for(rows * nvox), kThreads, 0, s>>>(x_t, eps, z, z_bc, x_bcs, mask, coef, t_ptr, x_out,
-                                                                          rows, nvox, flags);
+                                                                          rows, nvox, flags, F);
     TDB_CHECK_LAUNCH("tdb_ddpm_step");
     return 0;
 }

@@ -14,7 +14,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libturbdiff_b200.so"
 
 F32, BF16 = 0, 1
 PW_SILU, PW_NOHALO = 1, 2
-STEP_NOISE_BCS, STEP_CLIP, STEP_FINAL = 1, 2, 4
+STEP_NOISE_BCS, STEP_CLIP, STEP_FINAL, STEP_LEARNED_VAR = 1, 2, 4, 8
 CONV_ALL_ROWS = 1
 CONV_CLUSTER_MC = 2
 WGRAD_ZERO_HALO = 1
@@ -57,6 +57,7 @@ SIGNATURES = {
     "tdb_select_cells": [_p, _p, _p, _l, _l, _l, _p],
     "tdb_scatter_cells": [_p, _p, _p, _i, _i, _l, _l, _p],
     "tdb_build_mask": [_p, _p, _l, _l, _p],
+    "tdb_tke_spectrum": [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _i, _p, _p, _p],
 }
 OTHER = {"tdb_last_error": ([], C.c_char_p), "tdb_version": ([], _i), "tdb_launch_count": ([], _l)}
 

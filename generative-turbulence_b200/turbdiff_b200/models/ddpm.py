@@ -24,7 +24,7 @@ import torch
 from torch import nn
 
 from .. import _lib
-from .._lib import STEP_CLIP, STEP_FINAL, STEP_NOISE_BCS, call, ptr
+from .._lib import STEP_CLIP, STEP_FINAL, STEP_LEARNED_VAR, STEP_NOISE_BCS, call, ptr
 from ..engine import DenoiserEngine
 from .conditioning import global_conditioning, local_conditioning
 from .utils import broadcast_right, inside_mask, ravel_cells, where_cells
@@ -302,8 +302,6 @@ class GaussianDiffusion(nn.Module):
         self.detach_elbo_mean = detach_elbo_mean
         if beta_schedule not in _SCHEDULES:
             raise ValueError(f"unknown beta schedule {beta_schedule}")
-        if learned_variances:
-            raise NotImplementedError("learned_variances is not on the accelerated path yet (shapes config uses fixed variances)")
         betas = _SCHEDULES[beta_schedule](timesteps)
         alphas = 1.0 - betas
         acp = torch.cumprod(alphas, dim=0)
@@ -333,11 +331,12 @@ class GaussianDiffusion(nn.Module):
     def _coef_table(self, device):
         c = self._coef_cache
         if c is None or c.device != torch.device(device):
-            z = torch.zeros_like(self.betas)
+            # slots 4 / 7: fixed variances -> (exp(log_betas / 2), 0); learned variances -> (log_betas, posterior_log_var)
+            s4 = self.log_betas if self.learned_variances else (self.log_betas / 2).exp()
+            s7 = self.posterior_log_var if self.learned_variances else torch.zeros_like(self.betas)
             c = torch.stack(
                 (self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod, self.posterior_mean_coef1,
-                 self.posterior_mean_coef2, (self.log_betas / 2).exp(), self.sqrt_alphas_cumprod,
-                 self.sqrt_one_minus_alphas_cumprod, z), dim=1,
+                 self.posterior_mean_coef2, s4, self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod, s7), dim=1,
             ).to(device=device, dtype=torch.float32).contiguous()
             self._coef_cache = c
         return c
@@ -363,14 +362,21 @@ class GaussianDiffusion(nn.Module):
         return out
 
     def model_predictions(self, x_t, t, C, cell_idx, clip_x_start=False):
-        eps = self.model(x_t, t, C)
+        out = self.model(x_t, t, C)
+        if self.learned_variances:
+            # ddpm.py:732-741: the model predicts 2F channels; the per-voxel log-variance interpolates between
+            # log beta_t and the posterior log-variance with weight sigmoid(v)
+            eps, vw = out.chunk(2, dim=1)
+            log_var = torch.lerp(broadcast_right(self.log_betas[t], vw), broadcast_right(self.posterior_log_var[t], vw), torch.sigmoid(vw))
+        else:
+            eps, log_var = out, self.log_betas[t]
         x0 = self.predict_start_from_noise(x_t, t, eps)
         if not self.noise_bcs:
             x0 = where_cells(cell_idx, x0, x_t)
         if clip_x_start:
             x0 = torch.clamp(x0, min=-1.0, max=1.0)
         mean, _ = self.q_posterior(x0, x_t, t)
-        return ModelPrediction(noise=eps, x_start=x0, mean=mean, log_var=self.log_betas[t])
+        return ModelPrediction(noise=eps, x_start=x0, mean=mean, log_var=log_var)
 
     @torch.no_grad()
     def p_sample(self, x_t, t: int, C, cell_idx):
@@ -407,6 +413,10 @@ class GaussianDiffusion(nn.Module):
         x_t, t_dev, t_vec = st["x_t"], st["t_dev"], st["t_vec"]
         x_t.copy_(x_init)
         flags = (STEP_NOISE_BCS if self.noise_bcs else 0) | (STEP_CLIP if self.clip_denoised else 0)
+        if self.learned_variances:
+            # (the reference's own loop raises here - broadcast_right on the 5-D std, ddpm.py:805 / models/utils.py:11; this
+            # is the update it spells out, x <- mean + exp(log_var / 2) * z with the per-voxel log-variance of :732-741)
+            flags |= STEP_LEARNED_VAR
         steps = reversed(range(0, T))
         if pbar:
             from tqdm.auto import tqdm
@@ -472,8 +482,26 @@ class GaussianDiffusion(nn.Module):
         x_t = torch.empty_like(x_start)
         call("tdb_q_sample", x_start.data_ptr(), noise.data_ptr(), t.data_ptr(), self._coef_table(dev).data_ptr(),
              mask.data_ptr(), x_t.data_ptr(), B, F, nvox, 1 if self.noise_bcs else 0, _lib.stream_ptr())
-        eps = self.model(x_t, t, C)
-        loss = masked_loss(eps, noise, mask, int(cell_idx.numel()), self.loss_type == "l1")
+        if not self.learned_variances:
+            eps = self.model(x_t, t, C)
+            loss = masked_loss(eps, noise, mask, int(cell_idx.numel()), self.loss_type == "l1")
+            return loss, t
+        # learned variances (ddpm.py:732-741, 853-870): the simple loss on the noise half, plus the variational bound
+        # that trains the variance half.  The elementwise bookkeeping of this non-default variant is written with torch
+        # ops on the device (autograd differentiates it); the denoiser itself runs on the launch programs.
+        pred = self.model_predictions(x_t, t, C, cell_idx, clip_x_start=self.clip_denoised)
+        loss = masked_loss(pred.noise.contiguous(), noise, mask, int(cell_idx.numel()), self.loss_type == "l1")
+        if self.elbo_weight is not None:
+            true_mean, true_log_var = self.q_posterior(x_start, x_t, t)
+            model_mean = pred.mean.detach() if self.detach_elbo_mean else pred.mean
+            kl = normal_kl(true_mean, true_log_var, model_mean, pred.log_var)
+            log_lk = normal_log_lk(x_t, model_mean, pred.log_var)
+
+            def batch_mean_inside(v):
+                return ravel_cells(v)[..., cell_idx].flatten(1).mean(dim=1)
+
+            elbo = torch.where(t == 0, -batch_mean_inside(log_lk), batch_mean_inside(kl))
+            loss = loss + self.elbo_weight * elbo.mean()
         return loss, t
 
     def forward(self, x, *args, **kwargs):

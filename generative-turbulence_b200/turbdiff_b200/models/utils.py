@@ -54,6 +54,11 @@ def select_cells(x: torch.Tensor, cell_idx: torch.Tensor):
 def where_cells(cell_idx, cell_values: torch.Tensor, other: torch.Tensor | None = None):
     _lib.require_cuda(cell_values, "cell_values")
     nvox = cell_values.shape[-3] * cell_values.shape[-2] * cell_values.shape[-1]
+    if torch.is_grad_enabled() and (cell_values.requires_grad or (other is not None and other.requires_grad)):
+        # differentiable use (the learned-variance ELBO differentiates through x_start, ddpm.py:745-747, 853-870): the same
+        # select as a torch op, so that autograd sees it; values are identical
+        m = inside_mask(cell_idx.to(cell_values.device), nvox).bool().view(cell_values.shape[-3:])
+        return torch.where(m, cell_values, torch.zeros_like(cell_values) if other is None else other.expand_as(cell_values))
     a = cell_values.to(torch.float32).contiguous()
     o = None if other is None else other.to(torch.float32).expand_as(a).contiguous()
     mask = inside_mask(cell_idx.to(cell_values.device), nvox)

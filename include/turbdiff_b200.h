@@ -56,6 +56,7 @@ extern "C" {
 #define TDB_STEP_NOISE_BCS 1u /* GaussianDiffusion(noise_bcs=True)  */
 #define TDB_STEP_CLIP 2u      /* clip_denoised: clamp x0 to [-1,1]  */
 #define TDB_STEP_FINAL 4u     /* after the update also pin non-inside voxels to x_bcs (ddpm.py:814) */
+#define TDB_STEP_LEARNED_VAR 8u /* learned_variances (ddpm.py:732-741): eps is the (B,2F,nvox) model output, per-voxel variance */
 
 /* ---- fused optimiser step (training path; reference: torch.optim.RAdam, turbdiff/models/diffusion.py:216, with
  * Lightning's gradient_clip_val = 0.1 / norm, config/shapes_experiment.yaml:50-51) ---------------------------------
@@ -73,6 +74,16 @@ TDB_API int tdb_radam_step(const int64_t* param_ptrs, const int64_t* grad_ptrs, 
                    const int64_t* exp_avg_sq_ptrs, const int64_t* numel, const int* chunk_tensor, const int64_t* chunk_off,
                    int n_chunks, int chunk, const double* sqnorm, float max_norm, float step_size, double beta1, double beta2,
                    float eps, float weight_decay, int rectified, void* stream);
+
+/* ---- TKE-spectrum statistic ---------------------------------------------------------------- */
+
+/* E[b][j] = 4 pi k_j^2 * sum_p w_p exp(trilinear(log |fftshift(fftn(tke_b))|^2, k_j * points_p + centre)) with
+ * tke_b = |u_b - u_mean|^2 / 2: TurbulentKineticEnergySpectrum.forward (turbdiff/models/metrics.py:296-320) with the
+ * log-domain interp3 (:211-267).  u: (B,3,n0,n1,n2) fp32; u_mean: (3,n0,n1,n2) or NULL (u is already the perturbation);
+ * k: (K) radii; points (P,3) / weights (P): sphere quadrature (the reference's Lebedev nodes); work: 4*B*n0*n1*n2
+ * floats of scratch; E: (B,K).  Axes <= 64 (the reference evaluates 48^3 cubes). */
+TDB_API int tdb_tke_spectrum(const float* u, const float* u_mean, int B, int n0, int n1, int n2, const float* k, int K,
+                     const float* points, const float* weights, int P, float* work, float* E, void* stream);
 
 TDB_API const char* tdb_last_error(void);
 TDB_API int tdb_version(void);
@@ -222,7 +233,10 @@ TDB_API int tdb_time_film(const int64_t* t, const float* emb_scale, const float*
  *   t_ptr: device int32 holding the current step t (so a captured graph can be replayed)
  *   mask: uint8 (nvox), 1 on inside cells (== where_cells' cell_idx set)
  *   z: posterior noise; z_bc: boundary re-noising draw (NULL unless NOISE_BCS). At t==0 the
- *   noise tensors are ignored (x <- mean). x_out may alias x_t. */
+ *   noise tensors are ignored (x <- mean). x_out may alias x_t.
+ *   TDB_STEP_LEARNED_VAR: eps is the model's (B,2F,nvox) output (noise prediction | variance weights v) and the step's
+ *   standard deviation is exp(lerp(log_betas[t], posterior_log_var[t], sigmoid(v)) / 2) per voxel; the coefficient row
+ *   then holds log_betas[t] in slot 4 and posterior_log_var[t] in slot 7. */
 TDB_API int tdb_ddpm_step(const float* x_t, const float* eps, const float* z, const float* z_bc,
                   const float* x_bcs, const uint8_t* mask, const float* coef, const int32_t* t_ptr,
                   float* x_out, int B, int F, int64_t nvox, unsigned flags, void* stream);

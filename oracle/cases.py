@@ -78,3 +78,18 @@ def grad_sample(g):
     """<= 1024 evenly strided entries of a flattened gradient tensor."""
     flat = g.reshape(-1)
     return flat[:: max(1, flat.numel() // 1024)][:1024]
+
+
+# ---- learned variances (ddpm.py:732-741, 853-870) --------------------------------------------------------------------
+LV_ELBO_WEIGHT = 0.05
+LV_VARIANTS = ((True, True), (False, True), (True, False))  # (noise_bcs, detach_elbo_mean)
+LV_SEEDS = (4321, 4)  # both draw t = 0 for one of the two samples: the log-likelihood branch of the ELBO is exercised
+
+
+def lv_case():
+    """micro configuration with learned variances: the denoiser predicts 2F channels (diffusion.py:114)."""
+    import dataclasses
+
+    case = dict(CASES["micro"])
+    case["spec"] = dataclasses.replace(case["spec"], out_features=2 * case["spec"].in_features)
+    return case

@@ -125,12 +125,16 @@ class DiffusionRef:
     callable (the conditioning is closed over by the caller)."""
 
     def __init__(self, eps_model, *, timesteps=1000, beta_schedule="sigmoid", loss_type="l2",
-                 clip_denoised=False, noise_bcs=False, dtype=torch.float32):
+                 clip_denoised=False, noise_bcs=False, learned_variances=False, elbo_weight=None, detach_elbo_mean=True,
+                 dtype=torch.float32):
         self.eps_model = eps_model
         self.T = timesteps
         self.loss_type = loss_type
         self.clip_denoised = clip_denoised
         self.noise_bcs = noise_bcs
+        self.learned_variances = learned_variances  # the model then returns 2F channels: eps | variance weights
+        self.elbo_weight = elbo_weight
+        self.detach_elbo_mean = detach_elbo_mean
         self.buf = {k: v.to(dtype) for k, v in diffusion_buffers(beta_schedule, timesteps).items()}
 
     # ddpm.py:818-822
@@ -148,15 +152,21 @@ class DiffusionRef:
         b = self.buf
         return _bc(b["posterior_mean_coef1"][t], x_t) * x0 + _bc(b["posterior_mean_coef2"][t], x_t) * x_t
 
-    # ddpm.py:730-756 (fixed variances)
+    # ddpm.py:730-756
     def predictions(self, x_t, t, cell_idx):
-        eps = self.eps_model(x_t, t)
+        out = self.eps_model(x_t, t)
+        if self.learned_variances:
+            # ddpm.py:732-741: per-voxel log-variance interpolated between log beta_t and the posterior log-variance
+            eps, vw = out.chunk(2, dim=1)
+            log_var = torch.lerp(_bc(self.buf["log_betas"][t], vw), _bc(self.buf["posterior_log_var"][t], vw), torch.sigmoid(vw))
+        else:
+            eps, log_var = out, self.buf["log_betas"][t]
         x0 = self.predict_start(x_t, t, eps)
         if not self.noise_bcs:
             x0 = where_cells(cell_idx, x0, x_t)
         if self.clip_denoised:
             x0 = x0.clamp(-1.0, 1.0)
-        return eps, x0, self.posterior_mean(x0, x_t, t), self.buf["log_betas"][t]
+        return eps, x0, self.posterior_mean(x0, x_t, t), log_var
 
     # ddpm.py:767-816
     @torch.no_grad()
@@ -187,13 +197,13 @@ class DiffusionRef:
                 trace.append(x.clone())
         return where_cells(cell_idx, x, x_bcs)
 
-    # ddpm.py:833-852 (no ELBO term)
+    # ddpm.py:833-872
     def losses(self, x0, t, cell_idx):
         noise = torch.randn_like(x0)
         x_t = self.q_sample(x0, t, noise)
         if not self.noise_bcs:
             x_t = where_cells(cell_idx, x_t, x0)
-        eps, _, _, _ = self.predictions(x_t, t, cell_idx)
+        eps, _, mean, log_var = self.predictions(x_t, t, cell_idx)
         if self.loss_type == "l2":
             per = (eps - noise) ** 2
         elif self.loss_type == "l1":
@@ -201,7 +211,19 @@ class DiffusionRef:
         else:
             raise ValueError(f"invalid loss type {self.loss_type}")
         per = flat3(per)[..., cell_idx]
-        return per.reshape(per.shape[0], -1).mean(dim=1).mean()
+        loss = per.reshape(per.shape[0], -1).mean(dim=1).mean()
+        if self.elbo_weight is not None and self.learned_variances:
+            # ddpm.py:853-870: KL(q(x_{t-1}|x_t,x_0) || p) for t > 0, -log p(x_0|x_1) at t = 0, inside cells only
+            b = self.buf
+            true_mean = self.posterior_mean(x0, x_t, t)
+            true_lv = _bc(b["posterior_log_var"][t], x_t)
+            m = mean.detach() if self.detach_elbo_mean else mean
+            kl = 0.5 * (-1.0 + log_var - true_lv + torch.exp(true_lv - log_var) + ((true_mean - m) ** 2) * torch.exp(-log_var))
+            log_lk = -0.5 * (log_var + math.log(2 * math.pi) + (x_t - m) ** 2 * torch.exp(-log_var))
+            bm = lambda v: flat3(v)[..., cell_idx].reshape(v.shape[0], -1).mean(dim=1)  # noqa: E731
+            elbo = torch.where(t == 0, -bm(log_lk), bm(kl))
+            loss = loss + self.elbo_weight * elbo.mean()
+        return loss
 
     # ddpm.py:874-882
     def forward(self, x0, cell_idx):

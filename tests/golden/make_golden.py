@@ -34,8 +34,8 @@ ref, ofles, ref_utils = _ns.ddpm, _ns.ofles, _ns.utils
 CellTypeLearnedEmbedding, Conditioning = _ns.CellTypeLearnedEmbedding, _ns.Conditioning
 
 from oracle import grid_ref  # noqa: E402
-from oracle.cases import (CASES, SHAPES_FWD_T, SHAPES_INPUT_SEED, SHAPES_SEED, SHAPES_T, case_inputs, grad_sample,  # noqa: E402
-                          shapes_spec, sub3, tap_sample)
+from oracle.cases import (CASES, LV_ELBO_WEIGHT, LV_SEEDS, LV_VARIANTS, SHAPES_FWD_T, SHAPES_INPUT_SEED, SHAPES_SEED, SHAPES_T, case_inputs, grad_sample,  # noqa: E402
+                          lv_case, shapes_spec, sub3, tap_sample)
 from oracle.unet_ref import UNetSpec, state_dict_layout, synth_state_dict  # noqa: E402
 
 NORM_NAME = {8: "group", 1: "layer", None: "instance"}
@@ -172,6 +172,113 @@ def gen_diffusion():
     np.savez_compressed(HERE / "diffusion.npz", **out)
 
 
+def gen_diffusion_lv():
+    """learned_variances=True (ddpm.py:732-741) with the ELBO term (ddpm.py:853-870): sampling chains, p_sample,
+    training loss and every gradient of the unmodified reference."""
+    out = {}
+    case = lv_case()
+    spec = case["spec"]
+    sd = synth_state_dict(spec, case["seed"])
+    x, t, c_local, geo = case_inputs(case)
+    cell_idx = torch.from_numpy(geo.cell_idx)
+    C = {Conditioning.Type.CELL_TYPE: c_local}
+    for noise_bcs, detach in LV_VARIANTS:
+        tag = f"noise_bcs={int(noise_bcs)}/detach={int(detach)}"
+        m = build_ref_model(spec, sd)
+        gd = ref.GaussianDiffusion(m, timesteps=spec.timesteps, beta_schedule="log-snr-linear", loss_type="l2", noise_bcs=noise_bcs,
+                                   learned_variances=True, elbo_weight=LV_ELBO_WEIGHT, detach_elbo_mean=detach)
+        if detach:
+            # (p_sample_loop itself cannot be pinned: with learned variances the reference raises "only one dimension
+            # can be inferred" at ddpm.py:805 - broadcast_right (models/utils.py:11) reshapes the 5-D std with five -1s)
+            try:
+                gd.p_sample_loop(x, C, cell_idx, start_from=2)
+                raise AssertionError("the reference's learned-variance sampling loop unexpectedly works: pin it")
+            except RuntimeError as e:
+                out[f"{tag}/sample_loop_error"] = np.array(str(e))
+            for tt in (3, 0):
+                mean, lv = gd.p_sample(x, tt, C, cell_idx)
+                out[f"{tag}/p_sample_mean/{tt}"] = mean.numpy()
+                out[f"{tag}/p_sample_logvar/{tt}"] = lv.numpy()
+        m.train()
+        for seed in LV_SEEDS:
+            torch.manual_seed(seed)
+            loss, tdraw = gd(x, C, _MD(cell_idx), None)
+            m.zero_grad()
+            loss.backward()
+            out[f"{tag}/loss/{seed}"] = np.array(loss.item())
+            out[f"{tag}/t/{seed}"] = tdraw.numpy()
+            for k, p in m.named_parameters():
+                g = p.grad
+                if g.numel() <= 4096:
+                    out[f"{tag}/grad/{seed}/{k}"] = g.numpy().copy()
+                out[f"{tag}/gradsum/{seed}/{k}"] = np.array([g.double().sum().item(), g.double().pow(2).sum().item()])
+            print(tag, "seed", seed, "loss", loss.item(), "t", tdraw.tolist())
+    np.savez_compressed(HERE / "diffusion_lv.npz", **out)
+
+
+TKE_STAT_SEEDS = tuple(range(900, 908))  # 8 chains of the tiny configuration x batch 2 = 16 samples
+
+
+def tke_cubes(samples):
+    """The two 16^3 cubes of the tiny configuration's 32x16x16 interior, velocity channels only: (N, 2, 3, 16, 16, 16)
+    (the reference cuts cube regions of edge min(Y, Z) out of the channel the same way, metrics.py:424-449)."""
+    u = samples[:, :3, 1:-1, 1:-1, 1:-1]
+    return torch.stack((u[..., :16, :, :], u[..., 16:, :, :]), dim=1)
+
+
+def gen_tke():
+    """TKE-spectrum statistic through the UNMODIFIED reference classes (models/metrics.py:270-378): known-answer spectra
+    and distance matrices on synthetic fields, and the spectra of 16 reference sampling chains of the tiny configuration
+    (north_star: "agreement of sample TKE/energy-spectrum statistics")."""
+    from oracle import tke_ref
+
+    M = ref_shim.load(with_task=True).metrics
+    out = {}
+    spec = M.TurbulentKineticEnergySpectrum(n=110)
+    out["p110"], out["w110"] = spec.p.numpy(), spec.w.numpy()  # the Lebedev quadrature the fixtures were made with
+    for n, seed in ((16, 1), (24, 2)):
+        u = torch.from_numpy(tke_ref.synthetic_velocity(3, n, seed))
+        um = u.mean(0)
+        dist = M.LogTKESpectrumL2Distance(spec, n=16)
+        D, la, lb, k = dist(u[:2], u[1:], um)
+        out[f"synthetic/{n}/E"] = spec(u - um, k).numpy()
+        out[f"synthetic/{n}/D"], out[f"synthetic/{n}/log_a"], out[f"synthetic/{n}/log_b"], out[f"synthetic/{n}/k"] = (
+            D.numpy(), la.numpy(), lb.numpy(), k.numpy())
+    # the production size: one 48^3 cube, 64 radii, 5810 Lebedev points (only the outputs are stored)
+    big = M.LogTKESpectrumL2Distance(M.TurbulentKineticEnergySpectrum(), n=64)
+    u = torch.from_numpy(tke_ref.synthetic_velocity(2, 48, 3))
+    D, la, lb, k = big(u[:1], u[1:], u.mean(0))
+    out["synthetic/48/D"], out["synthetic/48/log_a"], out["synthetic/48/log_b"], out["synthetic/48/k"] = D.numpy(), la.numpy(), lb.numpy(), k.numpy()
+
+    # sample statistics of the tiny configuration: 16 chains of the reference
+    case = CASES["tiny"]
+    spec_t = case["spec"]
+    m = build_ref_model(spec_t, synth_state_dict(spec_t, case["seed"]))
+    gd = ref.GaussianDiffusion(m, timesteps=spec_t.timesteps, beta_schedule="log-snr-linear", loss_type="l2", noise_bcs=True)
+    x, _, c_local, geo = case_inputs(case)
+    C = {Conditioning.Type.CELL_TYPE: c_local}
+    idx = torch.from_numpy(geo.cell_idx)
+    chains = []
+    for seed in TKE_STAT_SEEDS:
+        torch.manual_seed(seed)
+        chains.append(gd.p_sample_loop(x, C, idx))
+    cubes = tke_cubes(torch.cat(chains))            # (16, 2, 3, 16, 16, 16)
+    u_mean = cubes.mean(0)
+    dist = M.LogTKESpectrumL2Distance(spec, n=16)
+    logs = []
+    for c in range(2):
+        D, la, _, k = dist(cubes[:, c], cubes[:, c], u_mean[c])
+        logs.append(la)
+        out[f"stat/D/{c}"] = D.numpy()
+    out["stat/log_tke"] = torch.stack(logs, dim=1).numpy()   # (16, 2, 16)
+    out["stat/u_mean"] = u_mean.numpy()
+    out["stat/k"] = k.numpy()
+    out["stat/seeds"] = np.array(TKE_STAT_SEEDS)
+    np.savez_compressed(HERE / "tke.npz", **out)
+    print("tke: D(16^3)", out["synthetic/16/D"].round(3).tolist(), "sample spectra", out["stat/log_tke"].shape,
+          "median off-diagonal D", float(np.median(out["stat/D/0"][~np.eye(16, dtype=bool)])))
+
+
 def gen_grid():
     """grid_embedding / cell types / cell helpers through the reference's own dataclasses
     (SURVEY.md appendix C)."""
@@ -277,7 +384,7 @@ def gen_shapes():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    todo = sys.argv[1:] or ["layout", "schedules", "time_embedding", "grid", "unet", "diffusion", "shapes"]
+    todo = sys.argv[1:] or ["layout", "schedules", "time_embedding", "grid", "unet", "diffusion", "diffusion_lv", "tke", "shapes"]
     for name in todo:
         globals()[f"gen_{name}"]()
     for f in sorted(HERE.glob("*.npz")):

@@ -207,3 +207,74 @@ def test_training_step_gradients_match_reference_golden(golden, noise_bcs):
         key = f"{tag}/grad/{k}"
         if key in g.files and np.abs(g[key]).max() > 1e-7:
             assert rel_l2(p.grad, g[key]) < 5e-4, k
+
+
+# ---- learned variances + ELBO (ddpm.py:732-741, 853-870) -------------------------------------------------------------
+
+
+def _lv_setup(noise_bcs, detach, precision="fp32"):
+    from oracle.cases import LV_ELBO_WEIGHT, case_inputs, lv_case
+    from turbdiff_b200 import GaussianDiffusion
+
+    case = lv_case()
+    m = build(case, precision)
+    gd = GaussianDiffusion(m, timesteps=case["spec"].timesteps, beta_schedule="log-snr-linear", loss_type="l2", noise_bcs=noise_bcs,
+                           learned_variances=True, elbo_weight=LV_ELBO_WEIGHT, detach_elbo_mean=detach).cuda()
+    x, _, c_local, geo = case_inputs(case)
+    return case, m, gd, x.cuda(), {key_of(): c_local.cuda()}, torch.from_numpy(geo.cell_idx).cuda(), c_local
+
+
+@pytest.mark.parametrize("noise_bcs,detach", [(True, True), (False, True), (True, False)])
+def test_learned_variances_training_step_matches_reference_golden(golden, noise_bcs, detach):
+    """GaussianDiffusion(learned_variances=True, elbo_weight=...): p_sample (mean, per-voxel log-variance), the loss with
+    its ELBO term (both branches: t = 0 log-likelihood, t > 0 KL) and every gradient against the unmodified reference."""
+    from oracle.cases import LV_SEEDS
+
+    g = golden["diffusion_lv"]
+    tag = f"noise_bcs={int(noise_bcs)}/detach={int(detach)}"
+    case, m, gd, x, C, idx, _ = _lv_setup(noise_bcs, detach)
+    if detach:
+        for tt in (3, 0):
+            mean, lv = gd.p_sample(x, tt, C, idx)
+            assert rel_l2(mean, g[f"{tag}/p_sample_mean/{tt}"]) < 2e-5
+            assert rel_l2(lv, g[f"{tag}/p_sample_logvar/{tt}"]) < 2e-6
+
+    class MD:
+        cell_idx = idx
+
+    m.train()
+    for seed in LV_SEEDS:
+        m.zero_grad(set_to_none=True)
+        with cpu_seeded_randn(seed):
+            loss, t = gd(x, C, MD, None)
+        np.testing.assert_array_equal(t.cpu().numpy(), g[f"{tag}/t/{seed}"])
+        np.testing.assert_allclose(loss.item(), g[f"{tag}/loss/{seed}"], rtol=2e-5)
+        loss.backward()
+        for k, p in m.named_parameters():
+            np.testing.assert_allclose(p.grad.double().pow(2).sum().item(), g[f"{tag}/gradsum/{seed}/{k}"][1], rtol=2e-3, atol=1e-10, err_msg=k)
+            key = f"{tag}/grad/{seed}/{k}"
+            if key in g.files and np.abs(g[key]).max() > 1e-7:
+                assert rel_l2(p.grad, g[key]) < 5e-4, k
+
+
+@pytest.mark.parametrize("noise_bcs", [True, False])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
+def test_learned_variances_sampling_loop_matches_oracle(noise_bcs, precision, tol):
+    """Sampling with learned variances through the fused update kernel (TDB_STEP_LEARNED_VAR).  The reference's own loop
+    raises for this variant (recorded in tests/golden/diffusion_lv.npz), so the chain is held to the CPU oracle, whose
+    per-step pieces (p_sample mean / log-variance, loss, gradients) are pinned to the reference."""
+    from oracle.cases import LV_ELBO_WEIGHT
+    from oracle.diffusion_ref import DiffusionRef
+    from oracle.unet_ref import denoiser_forward, synth_state_dict
+
+    case, m, gd, x, C, idx, c_local = _lv_setup(noise_bcs, True, precision)
+    spec = case["spec"]
+    sd = synth_state_dict(spec, case["seed"])
+    ref = DiffusionRef(lambda xt, tt: denoiser_forward(sd, spec, xt, tt, c_local), timesteps=spec.timesteps, beta_schedule="log-snr-linear",
+                       noise_bcs=noise_bcs, learned_variances=True, elbo_weight=LV_ELBO_WEIGHT)
+    for start in (None, 4):
+        torch.manual_seed(1234)
+        want = ref.sample_loop(x.cpu(), idx.cpu(), start_from=start)
+        with cpu_seeded_randn(1234):
+            got = gd.p_sample_loop(x, C, idx, start_from=start)
+        assert rel_l2(got, want) < tol, (start, rel_l2(got, want))

@@ -119,10 +119,12 @@ def test_launch_program_is_well_formed(built_lib, monkeypatch):
     assert n["tdb_pointwise"] == 24 and n["tdb_trilinear"] == 8
     # Cout <= 64: down0, up2, up3, decode (two 3x3x3 convs each); the three 32->32 layers stay single-CTA
     # ... and the wide layers of levels 1-3 run as 128-channel N tiles on CTA pairs (down1-3, up0, up1: two convs each)
-    # kernels: 64->64 x3 and 128->32 on the kz-folded row-window pair kernel, the ten wide layers of levels 1-3 on the
-    # row-window pair kernel with streamed weights, 256->64 on the kz-folded pair kernel, 32->32 x3 single-CTA folded
-    # (32->32: the paired-row kernel when the input pitch is exactly 32, 128-byte aligned and Z + 2 is even)
-    assert n["tdb_conv3d_bf16_fold"] + n["tdb_conv3d_bf16_winp"] == 3 and n["tdb_conv3d_bf16_fold2"] == 1 and n["tdb_conv3d_bf16_win"] == 10
+    # kernels: 64->64 x3 and 128->32 on the kz-folded row-window pair kernel, the ten wide layers of levels 1-3 AND the four
+    # 512->512 bottleneck convolutions on the row-window pair kernel with streamed weights, 256->64 on the kz-folded pair
+    # kernel, 32->32 x3 single-CTA folded (the paired-row kernel when the input pitch is exactly 32, 128-byte aligned and
+    # Z + 2 is even); only the two 1x1 attention projections stay on the per-tap kernel
+    assert n["tdb_conv3d_bf16_fold"] + n["tdb_conv3d_bf16_winp"] == 3 and n["tdb_conv3d_bf16_fold2"] == 1 and n["tdb_conv3d_bf16_win"] == 14
+    assert n["tdb_conv3d_bf16"] == 2 and n["tdb_gn_stats"] == 1
     assert n["tdb_conv3d_bf16_winz"] == 4
     assert n["tdb_attention"] == 1 and n["tdb_time_film"] == 1 and n["tdb_encode_input"] == 1 and n["tdb_decode_output"] == 1
     # level sizes follow max(int(s/2), 3)

@@ -226,3 +226,83 @@ def test_full_size_sampling_and_training_step(golden, shapes_case):
         if np.abs(want).max() < 1e-7:  # conv bias in front of GroupNorm: exactly zero up to rounding noise
             continue
         assert rel_l2(grad_sample(p.grad), want) < 2e-4, k
+
+
+# ---- learned variances + ELBO (ddpm.py:732-741, 853-870) -------------------------------------------------------------
+
+
+def _lv_diffusion(noise_bcs, detach):
+    from oracle.cases import LV_ELBO_WEIGHT, lv_case
+
+    case = lv_case()
+    spec = case["spec"]
+    sd = {k: v.requires_grad_() for k, v in synth_state_dict(spec, case["seed"]).items()}
+    x, t, c_local, geo = case_inputs(case)
+    d = DiffusionRef(lambda x_t, tt: denoiser_forward(sd, spec, x_t, tt, c_local), timesteps=spec.timesteps, beta_schedule="log-snr-linear",
+                     loss_type="l2", noise_bcs=noise_bcs, learned_variances=True, elbo_weight=LV_ELBO_WEIGHT, detach_elbo_mean=detach)
+    return d, sd, x, torch.from_numpy(geo.cell_idx)
+
+
+@pytest.mark.parametrize("noise_bcs,detach", [(True, True), (False, True), (True, False)])
+def test_learned_variances_loss_and_grads(golden, noise_bcs, detach):
+    from oracle.cases import LV_SEEDS
+
+    g = golden["diffusion_lv"]
+    tag = f"noise_bcs={int(noise_bcs)}/detach={int(detach)}"
+    d, sd, x, idx = _lv_diffusion(noise_bcs, detach)
+    if detach:
+        assert "only one dimension" in str(g[f"{tag}/sample_loop_error"])  # the reference cannot sample this variant
+        for tt in (3, 0):
+            with torch.no_grad():
+                _, _, mean, lv = d.predictions(x, torch.full((x.shape[0],), tt), idx)
+            assert rel_l2(mean, g[f"{tag}/p_sample_mean/{tt}"]) < 1e-5
+            assert rel_l2(lv, g[f"{tag}/p_sample_logvar/{tt}"]) < 1e-6
+    for seed in LV_SEEDS:
+        for p in sd.values():
+            p.grad = None
+        torch.manual_seed(seed)
+        loss, t = d.forward(x, idx)
+        np.testing.assert_array_equal(t.numpy(), g[f"{tag}/t/{seed}"])
+        assert 0 in t.tolist()
+        np.testing.assert_allclose(loss.item(), g[f"{tag}/loss/{seed}"], rtol=1e-5)
+        loss.backward()
+        for k, p in sd.items():
+            key = f"{tag}/grad/{seed}/{k}"
+            if key in g.files and np.abs(g[key]).max() > 1e-7:
+                assert rel_l2(p.grad, g[key]) < 2e-4, k
+
+
+# ---- TKE-spectrum statistic (models/metrics.py:270-378) --------------------------------------------------------------
+
+
+@pytest.mark.parametrize("n", [16, 24])
+def test_tke_spectrum_and_distance(golden, n):
+    from oracle import tke_ref
+
+    g = golden["tke"]
+    p, w = torch.from_numpy(g["p110"]), torch.from_numpy(g["w110"])
+    u = torch.from_numpy(tke_ref.synthetic_velocity(3, n, {16: 1, 24: 2}[n]))
+    um = u.mean(0)
+    D, la, lb, k = tke_ref.log_tke_l2_distance(u[:2], u[1:], um, p, w, 16)
+    np.testing.assert_array_equal(k.numpy(), g[f"synthetic/{n}/k"])
+    assert rel_l2(tke_ref.tke_spectrum(u - um, k, p, w), g[f"synthetic/{n}/E"]) < 1e-6
+    assert rel_l2(la, g[f"synthetic/{n}/log_a"]) < 1e-6 and rel_l2(lb, g[f"synthetic/{n}/log_b"]) < 1e-6
+    np.testing.assert_allclose(D.numpy(), g[f"synthetic/{n}/D"], rtol=1e-4, atol=1e-5)
+
+
+def test_tke_spectrum_production_size(golden):
+    """One 48^3 cube, 64 Gauss-Legendre radii, 5810 Lebedev points (the reference's defaults); the quadrature comes from
+    the reference package (its numgrids.pickle), so this needs /root/reference or the oracle/_ref install."""
+    from oracle import ref_shim, tke_ref
+
+    if not ref_shim.available():
+        pytest.skip("reference package not installed")
+    import pickle
+
+    x, y, z, w = pickle.loads((ref_shim.reference_root() / "turbdiff" / "models" / "numgrids.pickle").read_bytes())[5810]
+    p, w = torch.tensor([x, y, z]).T.float(), torch.tensor(w).float()
+    g = golden["tke"]
+    u = torch.from_numpy(tke_ref.synthetic_velocity(2, 48, 3))
+    D, la, lb, k = tke_ref.log_tke_l2_distance(u[:1], u[1:], u.mean(0), p, w, 64)
+    assert rel_l2(la, g["synthetic/48/log_a"]) < 1e-6 and rel_l2(lb, g["synthetic/48/log_b"]) < 1e-6
+    np.testing.assert_allclose(D.numpy(), g["synthetic/48/D"], rtol=1e-4)
