@@ -215,14 +215,15 @@ class BackwardProgram:
         # decode[1]: 1x1 conv dim -> F read from NCDHW eps gradient
         dec = m.decode[1]
         dec_out = p["dec_out"]
-        dw = torch.zeros((m.dim, F), dtype=torch.float32, device=dev)
-        call("tdb_cl_nc_outer", dec_out.ptr, dec_out.ld, g_eps.data_ptr(), F * X * Y * Z, dw.data_ptr(), B, X, Y, Z, m.dim, F, dt, s())
+        Fo = m.out_features  # 2F with learned variances
+        dw = torch.zeros((m.dim, Fo), dtype=torch.float32, device=dev)
+        call("tdb_cl_nc_outer", dec_out.ptr, dec_out.ld, g_eps.data_ptr(), Fo * X * Y * Z, dw.data_ptr(), B, X, Y, Z, m.dim, Fo, dt, s())
         grads["decode.1.weight"] = dw.t().reshape(dec.weight.shape).contiguous()
         grads["decode.1.bias"] = g_eps.sum(dim=(0, 2, 3, 4))
         g_dec = self._gbuf(p, dec_out, ("g", "dec_out"))
-        wt = dec.weight.detach().reshape(F, m.dim).t().contiguous()  # (dim, F)
+        wt = dec.weight.detach().reshape(Fo, m.dim).t().contiguous()  # (dim, Fo)
         zero_b = torch.zeros(m.dim, dtype=torch.float32, device=dev)
-        call("tdb_encode_input", g_eps.data_ptr(), None, wt.data_ptr(), zero_b.data_ptr(), None, None, g_dec.ptr, g_dec.ld, B, F, 0,
+        call("tdb_encode_input", g_eps.data_ptr(), None, wt.data_ptr(), zero_b.data_ptr(), None, None, g_dec.ptr, g_dec.ld, B, Fo, 0,
              m.dim, X, Y, Z, 1, dt, s())  # halo rows hold copies, never read: the 1x1 conv only saw interior voxels
 
         g = self._resblock_bwd(p, "decode0", g_dec, grads, d_film)

@@ -86,10 +86,10 @@ LV_VARIANTS = ((True, True), (False, True), (True, False))  # (noise_bcs, detach
 LV_SEEDS = (4321, 4)  # both draw t = 0 for one of the two samples: the log-likelihood branch of the ELBO is exercised
 
 
-def lv_case():
-    """micro configuration with learned variances: the denoiser predicts 2F channels (diffusion.py:114)."""
+def lv_case(base: str = "micro"):
+    """A configuration with learned variances: the denoiser predicts 2F channels (diffusion.py:114)."""
     import dataclasses
 
-    case = dict(CASES["micro"])
+    case = dict(CASES[base])
     case["spec"] = dataclasses.replace(case["spec"], out_features=2 * case["spec"].in_features)
     return case

@@ -212,11 +212,11 @@ def test_training_step_gradients_match_reference_golden(golden, noise_bcs):
 # ---- learned variances + ELBO (ddpm.py:732-741, 853-870) -------------------------------------------------------------
 
 
-def _lv_setup(noise_bcs, detach, precision="fp32"):
+def _lv_setup(noise_bcs, detach, precision="fp32", base="micro"):
     from oracle.cases import LV_ELBO_WEIGHT, case_inputs, lv_case
     from turbdiff_b200 import GaussianDiffusion
 
-    case = lv_case()
+    case = lv_case(base)
     m = build(case, precision)
     gd = GaussianDiffusion(m, timesteps=case["spec"].timesteps, beta_schedule="log-snr-linear", loss_type="l2", noise_bcs=noise_bcs,
                            learned_variances=True, elbo_weight=LV_ELBO_WEIGHT, detach_elbo_mean=detach).cuda()
@@ -267,7 +267,8 @@ def test_learned_variances_sampling_loop_matches_oracle(noise_bcs, precision, to
     from oracle.diffusion_ref import DiffusionRef
     from oracle.unet_ref import denoiser_forward, synth_state_dict
 
-    case, m, gd, x, C, idx, c_local = _lv_setup(noise_bcs, True, precision)
+    # (the bf16 tensor-core kernels need channel counts that are multiples of 16: the dim-16 configuration there)
+    case, m, gd, x, C, idx, c_local = _lv_setup(noise_bcs, True, precision, base="micro" if precision == "fp32" else "tiny")
     spec = case["spec"]
     sd = synth_state_dict(spec, case["seed"])
     ref = DiffusionRef(lambda xt, tt: denoiser_forward(sd, spec, xt, tt, c_local), timesteps=spec.timesteps, beta_schedule="log-snr-linear",

@@ -51,7 +51,9 @@ def test_tke_spectrum_production_size(golden):
     u = torch.from_numpy(tke_ref.synthetic_velocity(2, 48, 3)).cuda()
     D, la, lb, k = dist(u[:1], u[1:], u.mean(0))
     assert rel_l2(la, g["synthetic/48/log_a"]) < 1e-5 and rel_l2(lb, g["synthetic/48/log_b"]) < 1e-5
-    np.testing.assert_allclose(D.cpu().numpy(), g["synthetic/48/D"], rtol=2e-3)
+    # (two fields and their own mean: the perturbations are each other's negatives, the spectra coincide and D is pure
+    # rounding noise - 8e-7 in the reference, 2e-6 here)
+    np.testing.assert_allclose(D.cpu().numpy(), g["synthetic/48/D"], atol=2e-5)
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2)])
