@@ -321,19 +321,18 @@ def run_ours(args):
     eng = model.engine()
     flags = _lib.STEP_NOISE_BCS
 
-    x_t = torch.randn_like(x_bcs)
-    t_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-    t_vec = torch.zeros(B, dtype=torch.int64, device=dev)
+    # The step is issued exactly as GaussianDiffusion.p_sample_loop issues it: the engine's persistent sampler state, the
+    # denoiser launch program replayed from a CUDA graph, the two Gaussian draws on a side stream, and the fused step
+    # tail (decoder block tail + decode.1 + posterior update + next step's encode_x in one kernel).
+    st = eng.sampler_state(B, tuple(geo.padded), dev, cl)
+    x_t, t_dev, t_vec = st["x_t"], st["t_dev"], st["t_vec"]
+    x_t.copy_(torch.randn_like(x_bcs))
+    eng.use_graph = not args.no_graph
+    fused = eng.can_fuse_tail()
+    state = {"cur": x_t, "nxt": st["x_t2"]}
+    if fused:
+        eng.encode_state(st, x_t)
     step_no = [0]
-
-    graph = None
-
-    def unet():
-        if graph is not None:
-            graph.replay()
-            return eng.plan(B, geo.padded, dev)["eps"]
-        return eng.forward(x_t, t_vec, cl, c_static=True)  # inside a sampling chain C is constant (as in p_sample_loop)
-
     rng_stream = torch.cuda.Stream(device=dev)
     side_rng = os.environ.get("TURBDIFF_B200_RNG_STREAM", "1") != "0"
 
@@ -344,44 +343,44 @@ def run_ours(args):
         t_vec.fill_(t)
         main = torch.cuda.current_stream()
         if side_rng:
-            # as GaussianDiffusion.p_sample_loop does: the two Gaussian draws overlap the denoiser on a side stream
             rng_stream.wait_stream(main)
             with torch.cuda.stream(rng_stream):
                 z = torch.randn_like(x_t)
                 z_bc = torch.randn_like(x_bcs)
             z.record_stream(main)
             z_bc.record_stream(main)
-            eps = unet()
+            eps = eng.forward_graphed(st, tail=fused)
             main.wait_stream(rng_stream)
         else:
-            eps = unet()
+            eps = eng.forward_graphed(st, tail=fused)
             z = torch.randn_like(x_t)
             z_bc = torch.randn_like(x_bcs)
-        _lib.call("tdb_ddpm_step", x_t.data_ptr(), eps.data_ptr(), z.data_ptr(), z_bc.data_ptr(), x_bcs.data_ptr(), mask.data_ptr(),
-                  coef.data_ptr(), t_dev.data_ptr(), x_t.data_ptr(), B, 4, nvox, flags, _lib.stream_ptr())
+        cur, nxt = state["cur"], state["nxt"]
+        if fused:
+            eng.step_tail(st, cur, nxt, z, z_bc, x_bcs, mask, coef, t_dev, flags)
+            state["cur"], state["nxt"] = nxt, cur
+        else:
+            _lib.call("tdb_ddpm_step", cur.data_ptr(), eps.data_ptr(), z.data_ptr(), z_bc.data_ptr(), x_bcs.data_ptr(), mask.data_ptr(),
+                      coef.data_ptr(), t_dev.data_ptr(), cur.data_ptr(), B, 4, nvox, flags, _lib.stream_ptr())
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # warm-up (also builds the plan and the packed-weight cache), then capture the U-Net launch program
+    # warm-up: builds the plan and the packed-weight cache and captures the denoiser graph (engine.forward_graphed)
     one_step()
     torch.cuda.synchronize()
+    used_graph = eng.use_graph
     launches_per_unet = None
-    used_graph = not args.no_graph
-    if not args.no_graph:
+    if used_graph:
+        # C-ABI launches the graph re-issues per replay: counted once from an eager pass of the same program
         n0 = _lib.launch_count()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            eng.forward(x_t, t_vec, cl, c_static=True)
-        torch.cuda.current_stream().wait_stream(side)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            eng.forward(x_t, t_vec, cl, c_static=True)
-        launches_per_unet = (_lib.launch_count() - n0) // 2
-        graph = g
+        eng.use_graph = False
+        eng.forward_graphed(st, tail=fused)
+        eng.use_graph = True
+        launches_per_unet = _lib.launch_count() - n0
+        torch.cuda.synchronize()
     for _ in range(max(args.warmup, 3)):
         one_step()
 
@@ -397,7 +396,7 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - n_l0
-    if graph is not None:
+    if used_graph:
         launches += launches_per_unet * args.steps  # graph replays re-issue the captured C-ABI launches
     clk = clocks.stop()
     tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -409,8 +408,6 @@ def run_ours(args):
 
     # ---- end to end through the public API: host buffers in, host buffers out -----------------------
     S = max(2, args.e2e_steps)
-    graph_saved, graph = graph, None
-
     def e2e_call():
         xb = x_pinned.to(dev, non_blocking=True)
         s = gd.p_sample_loop(xb, C, cell_idx, start_from=S)
@@ -428,19 +425,20 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * B / (float(e2e_ms.item()) * 1e-3 * T / S)
-    graph = graph_saved
+    if fused:
+        eng.encode_state(st, state["cur"])  # the public-API chains reused the plan's input buffer
 
     # ---- per-kernel device times (CUDA events around every C-ABI launch, eager, after the timed region)
     roof = None
     if rank == 0:
         _lib.PROFILE = {}
-        graph_saved, graph = graph, None
+        eng.use_graph = False  # eager launch program: one pair of CUDA events around every C-ABI call
         for _ in range(3):
             one_step()
         torch.cuda.synchronize()
         prof = {k: sum(a.elapsed_time(b) for a, b, _ in v) / 3 for k, v in _lib.PROFILE.items()}
         _lib.PROFILE = None
-        graph = graph_saved
+        eng.use_graph = used_graph
         pk = peaks()
         conv_ms = sum(v for k, v in prof.items() if k.startswith("tdb_conv3d"))  # all convolution kernels of one step
         flops = conv_flops_per_sample(geo.padded) * B
@@ -461,6 +459,15 @@ def run_ours(args):
                 "peak_src": f"{pk['src']} bf16 sustained (kernel timed inside a long step)",
                 "conv_ms_per_step": conv_ms, "kernel_ms_per_step": prof}
         # the bandwidth-bound update kernel against the HBM roofline: 6 tensors x 4 B per element
+        tl_ms = prof.get("tdb_step_tail", 0.0)
+        if tl_ms > 0:
+            # fused step tail: reads raw2 + res (bf16 halo grids, dim channels), x_t / z / z' / x_bcs, writes x' and the next step's
+            # encoded input rows (bf16 halo grid, dim channels)
+            rows_p = B * int(np.prod([d + 2 for d in geo.padded]))
+            esz = 2 if args.precision == "bf16" else 4
+            bytes_tail = 3 * rows_p * 32 * esz + 5 * 4 * B * 4 * nvox + nvox
+            roof["step_tail"] = {"bound": "hbm", "achieved": bytes_tail / (tl_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                 "frac": bytes_tail / (tl_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "algorithmic_bytes": bytes_tail}
         st_ms = prof.get("tdb_ddpm_step", 0.0)
         if st_ms > 0:
             bytes_step = 6 * 4 * B * 4 * nvox + nvox
@@ -472,7 +479,6 @@ def run_ours(args):
     if args.train_steps > 0:
         from turbdiff_b200.parallel import GradientAllReduce
 
-        graph = None
         torch.cuda.empty_cache()
         model.train()
         from turbdiff_b200.optim import FusedRAdam

@@ -82,6 +82,7 @@ class DenoiserEngine:
         self.win_center = os.environ.get("TURBDIFF_B200_WIN_CENTER", "1") != "0"  # bottleneck convolutions on the row-window pair kernel
         self.fuse_proj = True
         self.use_graph = True  # p_sample_loop replays the denoiser from a CUDA graph
+        self.fuse_tail = os.environ.get("TURBDIFF_B200_FUSE_TAIL", "1") != "0"  # sampler: fused step tail (tdb_step_tail)
         # training: weight repack + forward program and the backward program are replayed from two CUDA graphs
         # (TURBDIFF_B200_TRAIN_GRAPH=0 keeps the eager launch programs)
         self.train_graph = os.environ.get("TURBDIFF_B200_TRAIN_GRAPH", "1") != "0"
@@ -360,7 +361,9 @@ class DenoiserEngine:
             sv[name] = {k: p["grid"](lvl, bp.cout) for k in ("raw1", "act1", "raw2")}
         return sv[name]
 
-    def _resblock(self, p, name, x: View, out: View, slot, train=False):
+    def _resblock(self, p, name, x: View, out: View, slot, train=False, defer_out=False):
+        """defer_out: stop before the block's last pointwise (GroupNorm + SiLU + residual) and leave its operands in
+        p["tail"] - the sampler's fused step tail (tdb_step_tail) consumes them."""
         bp = self.blocks[name]
         w = self.weights()
         lvl = x.level
@@ -386,6 +389,9 @@ class DenoiserEngine:
                 self._conv(p, x, w[f"{name}.proj"], blk.conv.bias, res, 1)
         else:
             res = x
+        if defer_out:
+            p["tail"] = {"raw": raw, "stats": st, "G": G, "norm": blk.block2.norm, "res": res}
+            return
         self._pointwise(p, raw, st, blk.block2.norm, None, res, out, PW_SILU, G)
 
     def _attention(self, p, x: View, out: View, slot):
@@ -408,9 +414,12 @@ class DenoiserEngine:
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, x: torch.Tensor, t: torch.Tensor, c_local: torch.Tensor | None, taps: dict | None = None, train: bool = False,
-                c_static: bool = False):
+                c_static: bool = False, tail: bool = False, encode_x: bool = True):
         """eps = U-Net(x, t, c_local).  x (B,F,X,Y,Z) fp32 CUDA contiguous, t int64 (B,).
-        train=True keeps every block's intermediates in dedicated buffers for `backward`."""
+        train=True keeps every block's intermediates in dedicated buffers for `backward`.
+        Sampler mode: tail=True stops after decode.0's last convolution (the fused step tail finishes the step and
+        returns nothing here); encode_x=False leaves the x half of the level-0 input buffer as the previous step's
+        tail wrote it."""
         m = self.model
         _lib.require_cuda(x, "x")
         if x.dtype != torch.float32:
@@ -443,10 +452,13 @@ class DenoiserEngine:
         # its half of the concat buffer is rewritten only when c_local or the encoder weights changed
         # (c_static=True is the caller's promise that c_local and the weights are those of the previous call on this plan)
         parts = 1 if (c_static and Fc > 0 and p.get("c_valid") and not train) else 3
+        if not encode_x:
+            parts &= 2
         p["c_valid"] = Fc > 0
-        call("tdb_encode_input", x.data_ptr(), ptr(c_local), m.encode_x.weight.data_ptr(), m.encode_x.bias.data_ptr(),
-             ptr(m.encode_c_local.weight) if Fc > 0 else None, ptr(m.encode_c_local.bias) if Fc > 0 else None,
-             xin0.ptr, xin0.ld, B, F, Fc, m.dim, X, Y, Z, parts, self.dt, s)
+        if parts:
+            call("tdb_encode_input", x.data_ptr(), ptr(c_local), m.encode_x.weight.data_ptr(), m.encode_x.bias.data_ptr(),
+                 ptr(m.encode_c_local.weight) if Fc > 0 else None, ptr(m.encode_c_local.bias) if Fc > 0 else None,
+                 xin0.ptr, xin0.ld, B, F, Fc, m.dim, X, Y, Z, parts, self.dt, s)
 
         def tap(name, v: View):
             if taps is not None:
@@ -482,7 +494,9 @@ class DenoiserEngine:
             slot += 2
             tap(f"up{i}", p["up_out"][l])
             cur = p["up_out"][l]
-        self._resblock(p, "decode0", cur, p["dec_out"], slot, train)
+        self._resblock(p, "decode0", cur, p["dec_out"], slot, train, defer_out=tail)
+        if tail:
+            return None
         tap("decode0", p["dec_out"])
         dec = m.decode[1]
         eps = p["eps"]
@@ -504,10 +518,11 @@ class DenoiserEngine:
         if st is None:
             st = p["sampler"] = {
                 "x_t": torch.zeros((B, m.in_features, *spatial), dtype=torch.float32, device=device),
+                "x_t2": torch.zeros((B, m.in_features, *spatial), dtype=torch.float32, device=device),  # fused tail: double-buffered state
                 "t_vec": torch.zeros(B, dtype=torch.int64, device=device),
                 "t_dev": torch.zeros(1, dtype=torch.int32, device=device),
                 "c_local": None if c_local is None else torch.zeros_like(c_local, dtype=torch.float32),
-                "graph": None, "wver": None,
+                "graph": None, "wver": None, "graph_tail": None, "wver_tail": None,
             }
         if c_local is not None:
             st["c_local"].copy_(c_local)
@@ -533,25 +548,60 @@ class DenoiserEngine:
             p["c_valid"] = True
         st["c_dirty"] = False
 
-    def forward_graphed(self, st):
-        """eps for the sampler state `st` (x_t, t_vec, c_local buffers); captures the graph on first use."""
+    def can_fuse_tail(self) -> bool:
+        """tdb_step_tail covers the whole step tail when the model fits its register plan."""
+        m = self.model
+        return m.dim in (8, 16, 32, 64) and m.in_features <= 4 and m.in_features <= m.out_features <= 8 and self.fuse_tail
+
+    def encode_state(self, st, x: torch.Tensor):
+        """encode_x(x) into the x half of the level-0 input buffer (start of a chain in fused-tail mode)."""
+        m = self.model
+        B, F = x.shape[:2]
+        X, Y, Z = x.shape[2:]
+        p = self.plan(B, (X, Y, Z), x.device)
+        xin0 = p["xin0"]
+        Fc = m.c_local_features
+        call("tdb_encode_input", x.data_ptr(), ptr(st["c_local"]), m.encode_x.weight.data_ptr(), m.encode_x.bias.data_ptr(),
+             ptr(m.encode_c_local.weight) if Fc > 0 else None, ptr(m.encode_c_local.bias) if Fc > 0 else None,
+             xin0.ptr, xin0.ld, B, F, Fc, m.dim, X, Y, Z, 1, self.dt, _lib.stream_ptr())
+
+    def step_tail(self, st, x_in, x_out, z, z_bc, x_bcs, mask, coef, t_dev, flags, eps_out=None):
+        """The fused tail of one sampling step over the operands forward(tail=True) left in the plan: decode.0's last
+        pointwise + decode.1 + posterior update (x_in -> x_out) + encode_x of the next step."""
+        m = self.model
+        B, F = x_in.shape[:2]
+        X, Y, Z = x_in.shape[2:]
+        p = self.plan(B, (X, Y, Z), x_in.device)
+        tl, xin0, dec = p["tail"], p["xin0"], m.decode[1]
+        call("tdb_step_tail", tl["raw"].ptr, tl["raw"].ld, tl["stats"].data_ptr(), tl["norm"].weight.data_ptr(), tl["norm"].bias.data_ptr(),
+             tl["res"].ptr, tl["res"].ld, dec.weight.data_ptr(), dec.bias.data_ptr(), m.out_features, x_in.data_ptr(), ptr(z), ptr(z_bc),
+             ptr(x_bcs), mask.data_ptr(), coef.data_ptr(), t_dev.data_ptr(), x_out.data_ptr(), ptr(eps_out), F, flags,
+             m.encode_x.weight.data_ptr(), m.encode_x.bias.data_ptr(), xin0.ptr, xin0.ld, B, X, Y, Z, m.dim, tl["G"], GN_EPS, self.dt,
+             _lib.stream_ptr())
+
+    def forward_graphed(self, st, tail: bool = False):
+        """eps for the sampler state `st` (x_t, t_vec, c_local buffers); captures the graph on first use.  tail=True:
+        the sampler's fused-tail mode - the program neither encodes x (the previous tail did) nor finishes decode.0 /
+        decode.1 (the next tail will); returns None."""
         self._set_geometry(st["x_t"].shape[2:])
         self.weights()
+        kw = {"tail": True, "encode_x": False} if tail else {}
+        gk, wk = ("graph_tail", "wver_tail") if tail else ("graph", "wver")
         if not self.use_graph:
             static = not st.get("c_dirty", True)
             st["c_dirty"] = False
-            return self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=static)
-        if st["graph"] is None or st["wver"] != self._wgen:
+            return self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=static, **kw)
+        if st[gk] is None or st[wk] != self._wgen:
             # eager warm-up on a side stream (also (re)writes the c_local half), then capture
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=False)
+                self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=False, **kw)
             torch.cuda.current_stream().wait_stream(side)
             g = torch.cuda.CUDAGraph()
             try:
                 with torch.cuda.graph(g):
-                    self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=True)
+                    self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=True, **kw)
             except RuntimeError as e:  # not fatal: the same launch program runs eagerly
                 import warnings
 
@@ -560,12 +610,14 @@ class DenoiserEngine:
                 self.graph_fallbacks += 1
                 torch.cuda.synchronize()
                 st["c_dirty"] = False
-                return self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=False)
-            st["graph"], st["wver"] = g, self._wgen
-            st["c_dirty"] = False  # the warm-up wrote both halves from st["c_local"]
+                return self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=False, **kw)
+            st[gk], st[wk] = g, self._wgen
+            st["c_dirty"] = False  # the warm-up wrote the c_local half from st["c_local"]
         if st.get("c_dirty", True):
             self._encode_c_half(st)
-        st["graph"].replay()
+        st[gk].replay()
+        if tail:
+            return None
         B = st["x_t"].shape[0]
         return self.plan(B, tuple(st["x_t"].shape[2:]), st["x_t"].device)["eps"]
 

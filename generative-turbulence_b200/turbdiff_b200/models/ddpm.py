@@ -417,6 +417,12 @@ class GaussianDiffusion(nn.Module):
             # (the reference's own loop raises here - broadcast_right on the 5-D std, ddpm.py:805 / models/utils.py:11; this
             # is the update it spells out, x <- mean + exp(log_var / 2) * z with the per-voxel log-variance of :732-741)
             flags |= STEP_LEARNED_VAR
+        # fused-tail mode: ONE kernel finishes the step (last GroupNorm/SiLU/residual of the decoder block, decode.1, the
+        # posterior update) and writes encode_x of the next step; the state is double-buffered (cur -> nxt)
+        fused = eng.can_fuse_tail() and T > 0
+        cur, nxt = x_t, st["x_t2"]
+        if fused:
+            eng.encode_state(st, cur)
         steps = reversed(range(0, T))
         if pbar:
             from tqdm.auto import tqdm
@@ -444,13 +450,20 @@ class GaussianDiffusion(nn.Module):
                     if q is not None:
                         q.record_stream(main)  # allocated on the side stream, consumed by the update kernel on `main`
             else:
-                z, z_bc = x_t, (x_t if self.noise_bcs else None)  # ignored at t == 0
+                z, z_bc = None, None  # ignored at t == 0
             # C is constant along the chain: encode_c_local's half of the input buffer is written once
-            eps = eng.forward_graphed(st)
+            eps = eng.forward_graphed(st, tail=fused)
             if t > 0 and side_rng:
                 main.wait_stream(rng)
-            call("tdb_ddpm_step", x_t.data_ptr(), eps.data_ptr(), z.data_ptr(), ptr(z_bc), x_bcs.data_ptr(), mask.data_ptr(),
-                 coef.data_ptr(), t_dev.data_ptr(), x_t.data_ptr(), B, F, nvox, flags | (STEP_FINAL if t == 0 else 0), s())
+            step_flags = flags | (STEP_FINAL if t == 0 else 0)
+            if fused:
+                eng.step_tail(st, cur, nxt, z, z_bc, x_bcs, mask, coef, t_dev, step_flags)
+                cur, nxt = nxt, cur
+            else:
+                zz = cur if z is None else z
+                call("tdb_ddpm_step", cur.data_ptr(), eps.data_ptr(), zz.data_ptr(), ptr(z_bc if z_bc is not None else (cur if self.noise_bcs else None)),
+                     x_bcs.data_ptr(), mask.data_ptr(), coef.data_ptr(), t_dev.data_ptr(), cur.data_ptr(), B, F, nvox, step_flags, s())
+        x_t = cur
         out = x_t.clone()  # outputs are freshly allocated; the state buffer is reused by the next chain
         if T == 0:
             out = where_cells(cell_idx, out, x_bcs)

@@ -241,6 +241,20 @@ TDB_API int tdb_ddpm_step(const float* x_t, const float* eps, const float* z, co
                   const float* x_bcs, const uint8_t* mask, const float* coef, const int32_t* t_ptr,
                   float* x_out, int B, int F, int64_t nvox, unsigned flags, void* stream);
 
+/* Fused tail of one sampling step (everything between the denoiser's last convolution and the next step's first):
+ * decode.0's second GroupNorm + SiLU + residual (ddpm.py:168-177,197) -> decode.1 1x1x1 conv (ddpm.py:459,505) -> the
+ * tdb_ddpm_step update (same flags / coefficient table / bit-exact arithmetic) -> encode_x of the NEXT step written into
+ * the level-0 input halo grid `xin0` (ddpm.py:495), halo rows included.  raw / res: halo grids of decode.0 block2's
+ * convolution output and of the block input (dim channels), stats: that norm's [B][G][2] double moments; w_dec (Fo,dim),
+ * b_dec (Fo); w_enc (dim,F), b_enc (dim); x_in / z / z_bc / x_bcs / x_out: (B,F,nvox) fp32 NCDHW, x_out != x_in (halo rows
+ * still read the old state); eps_out: optional (B,Fo,nvox) copy of the model output (NULL = not stored).
+ * dim in {8,16,32,64}, F <= 4, Fo <= 8.  Results equal the unfused launches bit for bit given the same moments. */
+TDB_API int tdb_step_tail(const void* raw, int ld_raw, const double* stats, const float* gamma, const float* beta, const void* res,
+                  int ld_res, const float* w_dec, const float* b_dec, int Fo, const float* x_in, const float* z,
+                  const float* z_bc, const float* x_bcs, const uint8_t* mask, const float* coef, const int32_t* t_ptr,
+                  float* x_out, float* eps_out, int F, unsigned flags, const float* w_enc, const float* b_enc, void* xin0,
+                  int ld_xin0, int B, int X, int Y, int Z, int dim, int G, float eps_gn, int dtype, void* stream);
+
 /* q_sample with optional inside-cell masking (ddpm.py:818-822,837-838):
  * out = sqrt_acp[t_b]*x0 + sqrt(1-acp)[t_b]*noise ; where mask==0 and !noise_bcs: out = x0.
  * t: int64 (B,) device. coef as in tdb_ddpm_step. */

@@ -279,3 +279,29 @@ def test_learned_variances_sampling_loop_matches_oracle(noise_bcs, precision, to
         with cpu_seeded_randn(1234):
             got = gd.p_sample_loop(x, C, idx, start_from=start)
         assert rel_l2(got, want) < tol, (start, rel_l2(got, want))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("noise_bcs", [True, False])
+def test_fused_step_tail_equals_the_unfused_launches(precision, noise_bcs):
+    """tdb_step_tail (decoder block tail + decode.1 + posterior update + next step's encode_x in one kernel) against the four
+    separate launches it replaces, through the public sampling loop: fp32 bit for bit (every intermediate is rounded where
+    the unfused kernels round it); bf16 up to the summation order of the fused GroupNorm moments."""
+    from oracle.cases import CASES, case_inputs
+    from turbdiff_b200 import GaussianDiffusion
+
+    case = CASES["tiny"]
+    x, _, c_local, geo = case_inputs(case)
+    idx = torch.from_numpy(geo.cell_idx).cuda()
+    outs = []
+    for fuse in (True, False):
+        m = build(case, precision)
+        m.engine().fuse_tail = fuse
+        gd = GaussianDiffusion(m, timesteps=case["spec"].timesteps, beta_schedule="log-snr-linear", noise_bcs=noise_bcs, clip_denoised=not noise_bcs).cuda()
+        assert m.engine().can_fuse_tail() == fuse
+        with cpu_seeded_randn(77):
+            outs.append(gd.p_sample_loop(x.cuda(), {key_of(): c_local.cuda()}, idx, start_from=5))
+    err = rel_l2(outs[0], outs[1])
+    print("fused vs unfused step tail", precision, noise_bcs, err)
+    # fp32: identical arithmetic (only the order of the double atomics of the GroupNorm moments may differ between runs)
+    assert err < (1e-6 if precision == "fp32" else 2e-3)
