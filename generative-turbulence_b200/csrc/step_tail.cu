@@ -8,20 +8,29 @@
 //
 // Unfused, these are four launches (pointwise, decode_output, ddpm_step, encode_input) that write and re-read dec_out
 // (2 x 271 MB at B = 8), eps and x_t; fused, act and eps never leave registers: 1.12 GB instead of 2.3 GB per step.
-// Every intermediate is rounded exactly where the unfused kernels round it (act to the storage type, eps / x' fp32); the only
-// difference is the summation order of the dim -> F decode (a shuffle butterfly here), i.e. ~1e-7 relative.
+// Every intermediate is rounded exactly where the unfused kernels round it (act to the storage type, eps / x' fp32), so the
+// two paths agree bit for bit given the same GroupNorm moments.
 //
-// DIM / 8 (bf16) lanes per haloed row, 16-byte accesses fully coalesced; halo rows recompute their clamped source voxel (all
-// loads hit L1/L2) and only write the encoded row; x' goes to a SECOND state buffer because halo rows still read the old state.
+// One thread per haloed row (its DIM channels in registers); halo rows recompute their clamped source voxel (all loads hit
+// L1/L2) and only write the encoded row; x' goes to a SECOND state buffer because halo rows still read the old state.
 #include "common.cuh"
 #include "diffusion_step.cuh"
+
+#include <cstdlib>
 
 using namespace tdb;
 using bf16 = __nv_bfloat16;
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;
+constexpr int FMAX = 8, DMAX = 64;
+// decode.1 / encode_x weights of the running chain at FIXED offsets (immediate constant-bank operands): w_dec [Fo][dim] at 0,
+// b_dec at OFF_BDEC, w_enc [dim][4] at OFF_WENC, b_enc at OFF_BENC; copied here device-to-device (stream ordered) by every
+// tdb_step_tail call.  Constant-bank operands feed the FMAs directly: the 1x1x1 convolutions
+// cost no load instructions (as shared-memory tables they were ~380 LDS per row and the kernel was LSU bound).
+constexpr int OFF_BDEC = FMAX * DMAX, OFF_WENC = OFF_BDEC + FMAX, OFF_BENC = OFF_WENC + DMAX * 4;
+__constant__ float c_tail[OFF_BENC + DMAX];
 
 struct TailArgs {
     const void* raw; int ld_raw;
@@ -47,16 +56,11 @@ __device__ __forceinline__ float act_silu(float v) {
     else return silu_f(v);
 }
 
-// L = DIM / N lanes share one row: lane j owns channel vector j (coalesced 16-byte accesses, like tdb_pointwise), the
-// 1x1x1 decode is a per-lane partial product reduced with a shuffle butterfly, state feature f is updated by lane f % L.
-template <typename T, int DIM>
-__global__ void __launch_bounds__(kThreads, 4)
+template <typename T, int DIM, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 step_tail_kernel(const TailArgs A) {
-    constexpr int N = Vec<T>::N, L = DIM / N;
-    constexpr int FMAX = 8;
-    static_assert(L >= 1 && L <= 32 && (L & (L - 1)) == 0, "lanes per row must be a power of two");
-    constexpr int ROWS = kThreads / L;
-    __shared__ __align__(16) float s_ca[DIM], s_co[DIM], s_wdec[FMAX * DIM], s_bdec[FMAX], s_wenc[DIM * 4], s_benc[DIM];
+    constexpr int N = Vec<T>::N, NV = DIM / N;
+    __shared__ __align__(16) float s_ca[DIM], s_co[DIM];
     const Grid3& g = A.g;
     const int b = blockIdx.y;
     const int F = A.F, Fo = A.Fo;
@@ -72,12 +76,12 @@ step_tail_kernel(const TailArgs A) {
             const float a = rstd * A.gamma[c];
             s_ca[c] = a;
             s_co[c] = A.beta[c] - mean_f * a;
-            s_benc[c] = A.b_enc[c];
         }
-        for (int i = threadIdx.x; i < Fo * DIM; i += kThreads) s_wdec[i] = A.w_dec[i];
-        for (int i = threadIdx.x; i < Fo; i += kThreads) s_bdec[i] = A.b_dec[i];
-        for (int i = threadIdx.x; i < DIM * F; i += kThreads) s_wenc[i] = A.w_enc[i];
     }
+    const float* c_wdec = c_tail;               // [Fo][DIM]
+    const float* c_bdec = c_tail + OFF_BDEC;    // [Fo]
+    const float* c_wenc = c_tail + OFF_WENC;    // [DIM][4]
+    const float* c_benc = c_tail + OFF_BENC;    // [DIM]
     __syncthreads();
 
     const int t = *A.t_ptr;
@@ -92,73 +96,61 @@ step_tail_kernel(const TailArgs A) {
     const T* raw = static_cast<const T*>(A.raw);
     const T* res = static_cast<const T*>(A.res);
     T* xin0 = static_cast<T*>(A.xin0);
-    const int lane = threadIdx.x % L, row_in_block = threadIdx.x / L;
-    const int c0 = lane * N;
-    // per-lane constants: affine coefficients, decode / encode weights of this lane's N channels
-    float ca[N], co[N], benc[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        ca[i] = s_ca[c0 + i];
-        co[i] = s_co[c0 + i];
-        benc[i] = s_benc[c0 + i];
-    }
 
-    // every lane group walks the same number of trips (the shuffles below need the whole warp converged)
-    const uint32_t total = (uint32_t)g.vox_p;
-    const uint32_t stride = gridDim.x * ROWS;
-    const uint32_t trips = (total + stride - 1) / stride;
-    for (uint32_t it = 0; it < trips; ++it) {
-        const uint32_t r_raw = it * stride + blockIdx.x * ROWS + row_in_block;
-        const bool live = r_raw < total;
-        const uint32_t r = live ? r_raw : total - 1;
+    for (uint32_t r = blockIdx.x * kThreads + threadIdx.x; r < (uint32_t)g.vox_p; r += gridDim.x * kThreads) {
         uint32_t q, zz, xx, yy;
         A.by_z.divmod(r, q, zz);
         A.by_y.divmod(q, xx, yy);
         const int xp = (int)xx, yp = (int)yy, zp = (int)zz;
         const int xs = clampi(xp, 1, g.X), ys = clampi(yp, 1, g.Y), zs = clampi(zp, 1, g.Z);
-        const bool own = live && xs == xp && ys == yp && zs == zp;  // interior row: its lanes also own the voxel's state update
+        const bool own = xs == xp && ys == yp && zs == zp;  // interior row: this thread also owns the voxel's state update
         const int64_t src = base + ((int64_t)xs * g.Yp + ys) * g.Zp + zs;
         const int64_t v = ((int64_t)(xs - 1) * g.Y + (ys - 1)) * g.Z + (zs - 1);
 
-        const uint4 rv = Vec<T>::load_raw(raw + src * A.ld_raw + c0);
-        const uint4 sv = Vec<T>::load_raw(res + src * A.ld_res + c0);
-        // state feature(s) of this lane: f = lane, lane + L, ... (< F <= 4)
+        uint4 rv[NV], sv[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            rv[j] = Vec<T>::load_raw(raw + src * A.ld_raw + j * N);
+            sv[j] = Vec<T>::load_raw(res + src * A.ld_res + j * N);
+        }
         float xt[4], zn[4], zb[4], xb[4];
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
-            const bool mine = f < F && (f % L) == lane;
             const int64_t o = ((int64_t)b * F + f) * nvox + v;
-            xt[f] = mine ? A.x_in[o] : 0.0f;
-            zn[f] = (mine && need_z) ? A.z[o] : 0.0f;
-            zb[f] = (mine && need_zbc) ? A.z_bc[o] : 0.0f;
-            xb[f] = (mine && need_xb) ? A.x_bcs[o] : 0.0f;
+            const bool on = f < F;
+            xt[f] = on ? A.x_in[o] : 0.0f;
+            zn[f] = (on && need_z) ? A.z[o] : 0.0f;
+            zb[f] = (on && need_zbc) ? A.z_bc[o] : 0.0f;
+            xb[f] = (on && need_xb) ? A.x_bcs[o] : 0.0f;
         }
         const bool inside = A.mask[v] != 0;
 
         // decode.0 block 2: GroupNorm apply + SiLU + residual, rounded to the storage type like tdb_pointwise's output
-        float act[N];
-        {
-            float a[N], rr[N];
-            Vec<T>::unpack(rv, a);
-            Vec<T>::unpack(sv, rr);
+        float act[DIM];
 #pragma unroll
-            for (int i = 0; i < N; ++i) act[i] = round_to<T>(act_silu<T>(fmaf(ca[i], a[i], co[i])) + rr[i]);
+        for (int j = 0; j < NV; ++j) {
+            float a[N], rr[N];
+            Vec<T>::unpack(rv[j], a);
+            Vec<T>::unpack(sv[j], rr);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const int c = j * N + i;
+                act[c] = round_to<T>(act_silu<T>(fmaf(s_ca[c], a[i], s_co[c])) + rr[i]);
+            }
         }
-        // decode.1: per-lane partial products over its N channels, butterfly over the L lanes of the row, then the bias
+        // decode.1 (same accumulation order as decode_output_kernel)
         float eps[FMAX];
 #pragma unroll
         for (int f = 0; f < FMAX; ++f) {
-            float acc = 0.0f;
+            float acc = f < Fo ? c_bdec[f] : 0.0f;
             if (f < Fo) {
 #pragma unroll
-                for (int i = 0; i < N; ++i) acc = fmaf(s_wdec[f * DIM + c0 + i], act[i], acc);
+                for (int c = 0; c < DIM; ++c) acc = fmaf(c_wdec[f * DIM + c], act[c], acc);
             }
-#pragma unroll
-            for (int o = L / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            eps[f] = f < Fo ? acc + s_bdec[f] : 0.0f;
+            eps[f] = acc;
         }
-        // posterior update of this lane's feature(s); every lane then fetches all F new values
-        float mine_x[4];
+        // posterior update
+        float xn[4];
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
             float sg = k.sigma;
@@ -169,45 +161,47 @@ step_tail_kernel(const TailArgs A) {
                     if (j == F + f) vw = eps[j];
                 sg = learned_sigma(vw, k);
             }
-            mine_x[f] = f < F ? step_one(xt[f], eps[f], zn[f], zb[f], xb[f], inside, k, t0, A.flags, sg) : 0.0f;
+            xn[f] = f < F ? step_one(xt[f], eps[f], zn[f], zb[f], xb[f], inside, k, t0, A.flags, sg) : 0.0f;
         }
-        float xn[4];
-        const int lane0 = (threadIdx.x % 32) - lane;  // first lane of this row's group within the warp
-#pragma unroll
-        for (int f = 0; f < 4; ++f) xn[f] = __shfl_sync(0xffffffffu, mine_x[f], lane0 + (f % L));
         if (own) {
 #pragma unroll
             for (int f = 0; f < 4; ++f)
-                if (f < F && (f % L) == lane) A.x_out[((int64_t)b * F + f) * nvox + v] = xn[f];
+                if (f < F) A.x_out[((int64_t)b * F + f) * nvox + v] = xn[f];
             if (A.eps_out) {
 #pragma unroll
                 for (int f = 0; f < FMAX; ++f)
-                    if (f < Fo && (f % L) == lane) A.eps_out[((int64_t)b * Fo + f) * nvox + v] = eps[f];
+                    if (f < Fo) A.eps_out[((int64_t)b * Fo + f) * nvox + v] = eps[f];
             }
         }
         // encode_x of the next step (same accumulation order as encode_input_kernel), halo rows included
-        if (live) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
             float o[N];
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                float acc = benc[i];
+                const int c = j * N + i;
+                float acc = c_benc[c];
 #pragma unroll
                 for (int f = 0; f < 4; ++f)
-                    if (f < F) acc = fmaf(s_wenc[(c0 + i) * F + f], xn[f], acc);
+                    if (f < F) acc = fmaf(c_wenc[c * 4 + f], xn[f], acc);
                 o[i] = acc;
             }
-            Vec<T>::store(xin0 + (base + r) * A.ld_xin0 + c0, o);
+            Vec<T>::store(xin0 + (base + r) * A.ld_xin0 + j * N, o);
         }
     }
 }
 
 template <typename T, int DIM>
 int launch(const TailArgs& A, int B, cudaStream_t s) {
-    constexpr int L = DIM / Vec<T>::N;
-    int64_t blocks = ceil_div(A.g.vox_p * L, kThreads);
-    const int64_t cap = (148 * 16) / (B < 1 ? 1 : B);
+    int64_t blocks = ceil_div(A.g.vox_p, kThreads);
+    const int64_t cap = (148 * 32) / (B < 1 ? 1 : B);
     if (blocks > cap) blocks = cap < 8 ? 8 : cap;
-    step_tail_kernel<T, DIM><<<dim3((unsigned)blocks, (unsigned)B), kThreads, 0, s>>>(A);
+    // registers per thread trade against resident warps (the kernel is issue / latency bound: ~800 instructions per row)
+    static const int variant = std::getenv("TDB_TAIL_MINB") ? std::atoi(std::getenv("TDB_TAIL_MINB")) : 4;
+    const dim3 grid((unsigned)blocks, (unsigned)B);
+    if (variant >= 8) step_tail_kernel<T, DIM, 8><<<grid, kThreads, 0, s>>>(A);
+    else if (variant >= 6) step_tail_kernel<T, DIM, 6><<<grid, kThreads, 0, s>>>(A);
+    else step_tail_kernel<T, DIM, 4><<<grid, kThreads, 0, s>>>(A);
     return 0;
 }
 
@@ -238,6 +232,21 @@ extern "C" int tdb_step_tail(const void* raw, int ld_raw, const double* stats, c
     A.by_z = FastDiv((uint32_t)A.g.Zp); A.by_y = FastDiv((uint32_t)A.g.Yp);
     TDB_REQUIRE(A.g.vox_p < (1ll << 31), TDB_E_UNSUPPORTED, "tdb_step_tail: grid too large for 32-bit indexing");
     cudaStream_t s = (cudaStream_t)stream;
+    {
+        // [w_dec | b_dec | w_enc | b_enc] -> constant bank, device to device on the launch stream (graph capturable)
+        auto put = [&](const float* p, size_t n, size_t off) {
+            return cudaMemcpyToSymbolAsync(c_tail, p, n * sizeof(float), off * sizeof(float), cudaMemcpyDeviceToDevice, s);
+        };
+        cudaError_t e = put(w_dec, (size_t)Fo * dim, 0);
+        if (e == cudaSuccess) e = put(b_dec, (size_t)Fo, OFF_BDEC);
+        if (e == cudaSuccess) e = put(b_enc, (size_t)dim, OFF_BENC);
+        if (F == 4) {
+            if (e == cudaSuccess) e = put(w_enc, (size_t)dim * 4, OFF_WENC);
+        } else {  // rows of F < 4 weights into the fixed pitch of 4
+            for (int c = 0; c < dim && e == cudaSuccess; ++c) e = put(w_enc + (size_t)c * F, (size_t)F, OFF_WENC + (size_t)c * 4);
+        }
+        TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_step_tail: cudaMemcpyToSymbolAsync: %s", cudaGetErrorString(e));
+    }
 #define TDB_TAIL(D)                                                   \
     case D:                                                           \
         if (dtype == TDB_BF16) launch<bf16, D>(A, B, s);              \

@@ -248,7 +248,7 @@ TDB_API int tdb_ddpm_step(const float* x_t, const float* eps, const float* z, co
  * convolution output and of the block input (dim channels), stats: that norm's [B][G][2] double moments; w_dec (Fo,dim),
  * b_dec (Fo); w_enc (dim,F), b_enc (dim); x_in / z / z_bc / x_bcs / x_out: (B,F,nvox) fp32 NCDHW, x_out != x_in (halo rows
  * still read the old state); eps_out: optional (B,Fo,nvox) copy of the model output (NULL = not stored).
- * dim in {8,16,32,64}, F <= 4, Fo <= 8.  Equals the unfused launches up to the summation order of the dim -> Fo decode. */
+ * dim in {8,16,32,64}, F <= 4, Fo <= 8.  Results equal the unfused launches bit for bit given the same moments. */
 TDB_API int tdb_step_tail(const void* raw, int ld_raw, const double* stats, const float* gamma, const float* beta, const void* res,
                   int ld_res, const float* w_dec, const float* b_dec, int Fo, const float* x_in, const float* z,
                   const float* z_bc, const float* x_bcs, const uint8_t* mask, const float* coef, const int32_t* t_ptr,
