@@ -42,6 +42,7 @@ struct WinpParams {
     int G;
     int num_super;      // pairs of tiles
     int all_rows;
+    int tma_out;        // 1: the tile is staged in shared memory and written by one TMA store (needs ld_out == 32)
 };
 
 __device__ __forceinline__ bool interior_row(int64_t p, const WinpParams& P, int& b) {
@@ -59,7 +60,7 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" 
 
 __global__ void __launch_bounds__(THREADS, 1)
 conv3d_bf16_winp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                        const float* __restrict__ bias, bf16* __restrict__ out, double* __restrict__ gn_stats, const WinpParams P) {
+                        const __grid_constant__ CUtensorMap map_o, const float* __restrict__ bias, bf16* __restrict__ out, double* __restrict__ gn_stats, const WinpParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 6];
@@ -78,12 +79,14 @@ conv3d_bf16_winp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     constexpr uint32_t b_region = 9u * bh_bytes;
     const uint32_t stage_base = (smem_base + b_region + 1023u) & ~1023u;
     const uint32_t stage_bytes = (uint32_t)P.win_rows * ROWA;
+    const uint32_t out_stage = (stage_base + (uint32_t)P.stages * stage_bytes + 1023u) & ~1023u;  // [2][128 super-rows][128 B], swizzled
     const int zh = P.Zp / 2, yzh = (P.Yp * P.Zp) / 2;  // row shifts in super-rows
 
     for (int i = threadIdx.x; i < COUT; i += THREADS) s_bias[i] = bias ? bias[i] : 0.0f;
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_b);
+        if (P.tma_out) ptx::prefetch_tensormap(&map_o);
         for (int s = 0; s < P.stages; ++s) {
             ptx::mbar_init(full_bar + 8 * s, 2);   // leader's arm (expect_tx for both CTAs' bytes) + peer's arrival
             ptx::mbar_init(empty_bar + 8 * s, 1);
@@ -210,7 +213,7 @@ conv3d_bf16_winp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             }
         };
 
-        int local = 0;
+        int local = 0, prev_tile = 0;
         for (int w = cluster_id; w < P.num_super; w += n_clusters, ++local, xpar ^= 1u) {
             const int tile = 2 * w + (int)rank;
             const int as = local & 1;
@@ -261,7 +264,14 @@ conv3d_bf16_winp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 #pragma unroll
                 for (int j = 0; j < 16; ++j) s_xch[xpar][1][lg][c + j] = __uint_as_float(e2[j]);
             }
-            epi_barrier();
+            const bool issuer = P.tma_out && threadIdx.x == 64;
+            if (issuer) ptx::bulk_wait_read_all();  // the store that last read this tile's staging buffer (two tiles ago) is done with it
+            epi_barrier();  // also: every warp has staged (and fenced) the previous tile
+            if (issuer && local > 0) {
+                ptx::tma_store_2d(&map_o, out_stage + (uint32_t)((local - 1) & 1) * (BM * ROWA), 0, prev_tile * SR_OUT);
+                ptx::bulk_commit_group();
+            }
+            prev_tile = tile;
             float ve[16], vo[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -272,6 +282,40 @@ conv3d_bf16_winp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                 const float bj = s_bias[c + j];
                 ve[j] = (up + __uint_as_float(e1[j])) + (__uint_as_float(o2[j]) + bj);   // out[2m]   = D0_odd[m-1] + D1_even[m] + D2_odd[m]
                 vo[j] = (__uint_as_float(e0[j]) + __uint_as_float(o1[j])) + (dn + bj);   // out[2m+1] = D0_even[m]  + D1_odd[m]  + D2_even[m+1]
+            }
+            auto stage_row = [&](const float (&v)[16], int odd, bool valid) {
+                // super-row m of the tile -> staging row m - 1 (the store box starts at the first owned super-row); 16-byte chunk
+                // j of the 128-byte line sits at j ^ (row % 8) (CU_TENSOR_MAP_SWIZZLE_128B), which also spreads the warp over all banks
+                uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;  // rows that are not stored stay zero (halo rows of a convolution output)
+                if (valid) {
+                    __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&lo);
+                    __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&hi);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        h0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                        h1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
+                    }
+                    if (do_stats) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            st_s[j] += v[2 * j] + v[2 * j + 1];
+                            st_q[j] = fmaf(v[2 * j], v[2 * j], fmaf(v[2 * j + 1], v[2 * j + 1], st_q[j]));
+                        }
+                    }
+                }
+                const uint32_t r = (uint32_t)(m - 1);
+                const uint32_t j0 = (uint32_t)(odd * 4 + c / 8);
+                const uint32_t row_addr = out_stage + (uint32_t)(local & 1) * (BM * ROWA) + r * ROWA;
+                ptx::st_shared_v4(row_addr + ((j0 ^ (r & 7u)) << 4), lo);
+                ptx::st_shared_v4(row_addr + (((j0 + 1u) ^ (r & 7u)) << 4), hi);
+            };
+            if (P.tma_out) {
+                if (own) {
+                    stage_row(ve, 0, v0);
+                    stage_row(vo, 1, v1);
+                }
+                ptx::fence_proxy_async();
+                continue;
             }
             auto store_row = [&](const float (&v)[16], int64_t p, bool valid) {
                 if (!valid) return;
@@ -296,6 +340,14 @@ conv3d_bf16_winp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             };
             store_row(ve, p0, v0);
             store_row(vo, p0 + 1, v1);
+        }
+        if (P.tma_out) {
+            epi_barrier();  // the last tile is staged
+            if (threadIdx.x == 64 && local > 0) {
+                ptx::tma_store_2d(&map_o, out_stage + (uint32_t)((local - 1) & 1) * (BM * ROWA), 0, prev_tile * SR_OUT);
+                ptx::bulk_commit_group();
+                ptx::bulk_wait_all();
+            }
         }
         if (do_stats && st_b >= 0) flush_stats();
     }
@@ -342,7 +394,8 @@ extern "C" int tdb_conv3d_bf16_winp(const void* in, int ld_in, const void* w_fol
     const int resident = 9 * (int)bh_bytes;
     const int stage_bytes = P.win_rows * (int)ROWA;
     const int budget = 216 * 1024;
-    int stages = (budget - resident - 2048) / stage_bytes;
+    const int out_stage_bytes = 2 * BM * (int)ROWA + 1024;  // staged output tiles (TMA store)
+    int stages = (budget - resident - 2048 - out_stage_bytes) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     TDB_REQUIRE(stages >= 2, TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_winp: two windows of %d bytes do not fit", stage_bytes);
     P.stages = stages;
@@ -354,8 +407,15 @@ extern "C" int tdb_conv3d_bf16_winp(const void* in, int ld_in, const void* w_fol
     P.all_rows = (flags & TDB_CONV_ALL_ROWS) ? 1 : 0;
     TDB_REQUIRE(!(P.all_rows && gn_stats), TDB_E_BADARG, "tdb_conv3d_bf16_winp: fused moments are not available with ALL_ROWS");
 
-    CUtensorMap map_a, map_b;
+    CUtensorMap map_a, map_b, map_o;
     TDB_REQUIRE(encode_fn() != nullptr, TDB_E_NODEVICE, "tdb_conv3d_bf16_winp: cuTensorMapEncodeTiled unavailable (no driver)");
+    // output with the exact pitch: [rows / 2][64] super-rows, one box = the 126 owned super-rows of a tile
+    P.tma_out = (ld_out == COUT && ((uintptr_t)out & 127) == 0) ? 1 : 0;
+    if (P.tma_out)
+        TDB_REQUIRE(make_map_2d_bf16(&map_o, out, 64, (uint64_t)super_rows, 64, 64, (uint32_t)SR_OUT), TDB_E_BADARG,
+                    "tdb_conv3d_bf16_winp: tensor map (output) rejected");
+    else
+        map_o = CUtensorMap{};
     // activations viewed as [rows / 2][64]: one super-row = two consecutive 32-channel grid rows = one 128-byte line
     TDB_REQUIRE(make_map_2d_bf16(&map_a, in, 64, (uint64_t)super_rows, 64, 64, (uint32_t)P.win_rows), TDB_E_BADARG,
                 "tdb_conv3d_bf16_winp: tensor map (activations) rejected");
@@ -366,7 +426,7 @@ extern "C" int tdb_conv3d_bf16_winp(const void* in, int ld_in, const void* w_fol
         const uint32_t box[3] = {(uint32_t)CIN, (uint32_t)NH, 1};
         TDB_REQUIRE(make_map_bf16(&map_b, w_fold, 3, dims, strides, box), TDB_E_BADARG, "tdb_conv3d_bf16_winp: tensor map (weights) rejected");
     }
-    const size_t smem = (size_t)resident + 1024 + (size_t)stages * stage_bytes + 1024;
+    const size_t smem = (size_t)resident + 1024 + (size_t)stages * stage_bytes + 1024 + out_stage_bytes;
     auto kern = conv3d_bf16_winp_kernel;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_conv3d_bf16_winp: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
@@ -385,7 +445,7 @@ extern "C" int tdb_conv3d_bf16_winp(const void* in, int ld_in, const void* w_fol
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, map_a, map_b, bias, (bf16*)out, gn_stats, P);
+    e = cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_o, bias, (bf16*)out, gn_stats, P);
     TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_conv3d_bf16_winp: launch: %s", cudaGetErrorString(e));
     TDB_CHECK_LAUNCH("tdb_conv3d_bf16_winp");
     return 0;
