@@ -162,12 +162,17 @@ halo_fold_border_kernel(T* __restrict__ g, int ld, Grid3 gr, BorderEnum e, int c
 // ---------------------------------------------------------------- pointwise backward
 template <typename T>
 __device__ __forceinline__ float dsilu(float u) {
-    float s;
-    if constexpr (sizeof(T) == 2)  // bf16 storage: fast exp / reciprocal are far below the output rounding
-        s = __fdividef(1.0f, 1.0f + __expf(-u));
-    else
-        s = 1.0f / (1.0f + expf(-u));
-    return s * (1.0f + u * (1.0f - s));
+    if constexpr (sizeof(T) == 2) {
+        // bf16 storage: sigmoid(u) = (1 + t)/2 with t = tanh(u/2), so silu'(u) = (1 + t + (u/2)(1 - t^2))/2 - ONE
+        // special-function op (tanh.approx.f32, abs. error 2^-11, far below the bf16 rounding of the result)
+        const float h = 0.5f * u;
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+        return fmaf(0.5f, fmaf(h, fmaf(-t, t, 1.0f), t), 0.5f);
+    } else {
+        const float s = 1.0f / (1.0f + expf(-u));
+        return s * (1.0f + u * (1.0f - s));
+    }
 }
 
 struct PwCoef {  // per channel: forward affine u = a*x + o; xhat = (x - mean) * rstd
@@ -196,39 +201,50 @@ __device__ __forceinline__ PwCoef pw_coef(int b, int c, int C, int G, const doub
     return r;
 }
 
-// red[b][c] = (sum g_u, sum g_u*xhat, sum raw, sum g_out) over interior voxels (pre-zeroed): fp32 per thread (<= 32 voxels),
+// red[b][c] = (sum g_u, sum g_u*xhat, sum raw, sum g_out) over interior voxels (pre-zeroed): fp32 per thread (~100 voxels),
 // fp32 shared atomics per CTA, one double atomic per (CTA, channel, moment).  The third sum lets the host derive the
 // per-channel sum of d_raw (= the bias gradient of the convolution below) without another pass over d_raw.
+// Per-channel coefficients (the only fp64 arithmetic) are computed once per block by one thread per channel; the
+// streaming loop issues the 2 x U loads of U voxels before it uses any of them.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 pw_bwd_reduce_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict__ raw, int ld_raw,
                      const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                      const float* __restrict__ film, int film_ld, double* __restrict__ red, Grid3 gr, int C, int G, float eps,
-                     unsigned flags, int vox_per_block, FastDiv by_z, FastDiv by_y) {
+                     unsigned flags, FastDiv by_z, FastDiv by_y) {
     constexpr int N = Vec<T>::N;
-    extern __shared__ float sred[];  // [C][4]
-    for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) sred[i] = 0.0f;
-    __syncthreads();
+    constexpr int U = 4;
+    extern __shared__ float sm_red[];  // [C][4] partial sums, then [C][4] = (a, o, mean, rstd)
+    float* sred = sm_red;
+    float* scoef = sm_red + 4 * C;
     const int b = blockIdx.y;
+    {
+        const double inv_n = 1.0 / ((double)(C / G) * gr.X * gr.Y * gr.Z);
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const PwCoef k = pw_coef(b, c, C, G, stats, gamma, beta, film, film_ld, inv_n, eps);
+            scoef[4 * c] = k.a;
+            scoef[4 * c + 1] = k.o;
+            scoef[4 * c + 2] = k.mean;
+            scoef[4 * c + 3] = k.rstd;
+            sred[4 * c] = sred[4 * c + 1] = sred[4 * c + 2] = sred[4 * c + 3] = 0.0f;
+        }
+    }
+    __syncthreads();
     const int chunks = C / N;
     const int vox_step = kThreads / chunks;
     const int ch = threadIdx.x % chunks, lane_vox = threadIdx.x / chunks;
     if (lane_vox < vox_step) {
         const int c0 = ch * N;
-        const double inv_n = 1.0 / ((double)(C / G) * gr.X * gr.Y * gr.Z);
         // the loop accumulates raw moments (sum g_u, sum g_u*raw, sum raw); xhat = (raw-mean)*rstd is applied to the
         // block's partial sums at the flush, which keeps mean/rstd out of the registers of the streaming loop
         float ka[N], ko[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const PwCoef k = pw_coef(b, c0 + i, C, G, stats, gamma, beta, film, film_ld, inv_n, eps);
-            ka[i] = k.a;
-            ko[i] = k.o;
+            ka[i] = scoef[4 * (c0 + i)];
+            ko[i] = scoef[4 * (c0 + i) + 1];
         }
         const bool act = flags & TDB_PW_SILU;
         const uint32_t nvox = (uint32_t)(gr.X * gr.Y * gr.Z);
-        const uint32_t v_begin = blockIdx.x * (uint32_t)vox_per_block;
-        const uint32_t v_end = min(nvox, v_begin + (uint32_t)vox_per_block);
         const T* rb = raw + (int64_t)b * gr.vox_p * ld_raw + c0;
         const T* gb = g_out + (int64_t)b * gr.vox_p * ld_g + c0;
         float a1[N], a2[N], a3[N], a4[N];
@@ -240,34 +256,34 @@ pw_bwd_reduce_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict_
             by_y.divmod(q, x, y);
             return ((int64_t)(x + 1) * gr.Yp + (y + 1)) * gr.Zp + (z + 1);
         };
-        auto accumulate = [&](const float (&xv)[N], const float (&gv)[N]) {
+        const uint32_t stride = gridDim.x * (uint32_t)vox_step;
+        for (uint32_t v0 = blockIdx.x * (uint32_t)vox_step + lane_vox; v0 < nvox; v0 += U * stride) {
+            uint4 xr[U], gv[U];
+            bool ok[U];
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const float u = fmaf(ka[i], xv[i], ko[i]);
-                const float gu = act ? gv[i] * dsilu<T>(u) : gv[i];
-                a1[i] += gu;
-                a2[i] = fmaf(gu, xv[i], a2[i]);
-                a3[i] += xv[i];
-                a4[i] += gv[i];
+            for (int u = 0; u < U; ++u) {
+                const uint32_t v = v0 + u * stride;
+                ok[u] = v < nvox;
+                const int64_t r = row_of(ok[u] ? v : nvox - 1);
+                xr[u] = Vec<T>::load_raw(rb + r * ld_raw);
+                gv[u] = Vec<T>::load_raw(gb + r * ld_g);
             }
-        };
-        uint32_t v = v_begin + lane_vox;
-        for (; v + vox_step < v_end; v += 2 * vox_step) {  // two voxels in flight
-            const int64_t r0 = row_of(v), r1 = row_of(v + vox_step);
-            float x0[N], g0[N], x1[N], g1[N];
-            Vec<T>::load(rb + r0 * ld_raw, x0);
-            Vec<T>::load(gb + r0 * ld_g, g0);
-            Vec<T>::load(rb + r1 * ld_raw, x1);
-            Vec<T>::load(gb + r1 * ld_g, g1);
-            accumulate(x0, g0);
-            accumulate(x1, g1);
-        }
-        if (v < v_end) {
-            const int64_t r0 = row_of(v);
-            float x0[N], g0[N];
-            Vec<T>::load(rb + r0 * ld_raw, x0);
-            Vec<T>::load(gb + r0 * ld_g, g0);
-            accumulate(x0, g0);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!ok[u]) continue;
+                float x[N], g[N];
+                Vec<T>::unpack(xr[u], x);
+                Vec<T>::unpack(gv[u], g);
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const float uu = fmaf(ka[i], x[i], ko[i]);
+                    const float gu = act ? g[i] * dsilu<T>(uu) : g[i];
+                    a1[i] += gu;
+                    a2[i] = fmaf(gu, x[i], a2[i]);
+                    a3[i] += x[i];
+                    a4[i] += g[i];
+                }
+            }
         }
         // lanes of a warp that own the same channel chunk (lane % chunks) are combined by shuffles first, so that only
         // `chunks` lanes per warp touch the shared accumulators (the per-thread shared atomics used to dominate this kernel)
@@ -294,14 +310,13 @@ pw_bwd_reduce_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict_
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const double inv_n = 1.0 / ((double)(C / G) * gr.X * gr.Y * gr.Z);
-        const PwCoef k = pw_coef(b, c, C, G, stats, gamma, beta, film, film_ld, inv_n, eps);
+        const float mean = scoef[4 * c + 2], rstd = scoef[4 * c + 3];
         const float s1 = sred[4 * c], s2 = sred[4 * c + 1], s3 = sred[4 * c + 2];
         double* dst = red + ((int64_t)b * C + c) * 4;
         atomicAdd(dst, (double)s1);
-        atomicAdd(dst + 1, (double)(k.rstd * (s2 - k.mean * s1)));  // sum g_u * xhat
+        atomicAdd(dst + 1, (double)(rstd * (s2 - mean * s1)));  // sum g_u * xhat
         atomicAdd(dst + 2, (double)s3);
-        atomicAdd(dst + 3, (double)sred[4 * c + 3]);                // sum g_out (bias gradient of a residual projection)
+        atomicAdd(dst + 3, (double)sred[4 * c + 3]);            // sum g_out (bias gradient of a residual projection)
     }
 }
 
@@ -313,48 +328,77 @@ pw_bwd_apply_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict__
                     const float* __restrict__ film, int film_ld, const float* __restrict__ grp, T* __restrict__ d_raw, int ld_d,
                     Grid3 gr, int C, int G, float eps, unsigned flags, RowSplit split, int chunks) {
     constexpr int N = Vec<T>::N;
+    constexpr int U = 4;
+    extern __shared__ float s_apply[];  // [C][5] = (a, o, c1, c2, c3): d_raw = c1*g_u + c2*raw + c3
     const int b = blockIdx.y;
+    {
+        const double inv_n = 1.0 / ((double)(C / G) * gr.X * gr.Y * gr.Z);
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const PwCoef k = pw_coef(b, c, C, G, stats, gamma, beta, film, film_ld, inv_n, eps);
+            const int gi = c / (C / G);
+            const float m1 = stats ? grp[((int64_t)b * G + gi) * 2] : 0.0f;
+            const float m2 = stats ? grp[((int64_t)b * G + gi) * 2 + 1] : 0.0f;
+            const float c2 = stats ? -k.rstd * k.rstd * m2 : 0.0f;
+            s_apply[5 * c] = k.a;
+            s_apply[5 * c + 1] = k.o;
+            s_apply[5 * c + 2] = stats ? k.rstd * k.k : 1.0f;
+            s_apply[5 * c + 3] = c2;
+            s_apply[5 * c + 4] = stats ? -k.rstd * m1 - c2 * k.mean : 0.0f;
+        }
+    }
+    __syncthreads();
     const int vox_step = kThreads / chunks;
     const int ch = threadIdx.x % chunks, lane_vox = threadIdx.x / chunks;
     if (lane_vox >= vox_step) return;
     const int c0 = ch * N;
-    const double inv_n = 1.0 / ((double)(C / G) * gr.X * gr.Y * gr.Z);
-    // d_raw = rstd*(k*g_u - m1 - xhat*m2) = c1*g_u + c2*raw + c3 with per-channel constants
     float ka[N], ko[N], c1[N], c2[N], c3[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        const PwCoef k = pw_coef(b, c0 + i, C, G, stats, gamma, beta, film, film_ld, inv_n, eps);
-        const int gi = (c0 + i) / (C / G);
-        const float m1 = stats ? grp[((int64_t)b * G + gi) * 2] : 0.0f;
-        const float m2 = stats ? grp[((int64_t)b * G + gi) * 2 + 1] : 0.0f;
-        ka[i] = k.a;
-        ko[i] = k.o;
-        c1[i] = stats ? k.rstd * k.k : 1.0f;
-        c2[i] = stats ? -k.rstd * k.rstd * m2 : 0.0f;
-        c3[i] = stats ? -k.rstd * m1 - c2[i] * k.mean : 0.0f;
+        ka[i] = s_apply[5 * (c0 + i)];
+        ko[i] = s_apply[5 * (c0 + i) + 1];
+        c1[i] = s_apply[5 * (c0 + i) + 2];
+        c2[i] = s_apply[5 * (c0 + i) + 3];
+        c3[i] = s_apply[5 * (c0 + i) + 4];
     }
     const bool act = flags & TDB_PW_SILU;
-    for (uint32_t r = blockIdx.x * vox_step + lane_vox; r < (uint32_t)gr.vox_p; r += gridDim.x * vox_step) {
-        int xp, yp, zp;
-        split(r, xp, yp, zp);
-        const bool interior = xp >= 1 && xp <= gr.X && yp >= 1 && yp <= gr.Y && zp >= 1 && zp <= gr.Z;
-        const int64_t row = (int64_t)b * gr.vox_p + r;
-        float o[N];
-        if (interior) {
-            float xv[N], gv[N];
-            Vec<T>::load(raw + row * ld_raw + c0, xv);
-            Vec<T>::load(g_out + row * ld_g + c0, gv);
+    const uint32_t total = (uint32_t)gr.vox_p;
+    const uint32_t stride = gridDim.x * (uint32_t)vox_step;
+    const int64_t base = (int64_t)b * gr.vox_p;
+    for (uint32_t r0 = blockIdx.x * (uint32_t)vox_step + lane_vox; r0 < total; r0 += U * stride) {
+        uint4 xr[U], gv[U];
+        bool ok[U], inter[U];
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const float u = fmaf(ka[i], xv[i], ko[i]);
-                const float gu = act ? gv[i] * dsilu<T>(u) : gv[i];
-                o[i] = fmaf(c1[i], gu, fmaf(c2[i], xv[i], c3[i]));
+        for (int u = 0; u < U; ++u) {
+            const uint32_t r = r0 + u * stride;
+            ok[u] = r < total;
+            int xp, yp, zp;
+            split(ok[u] ? r : total - 1, xp, yp, zp);
+            inter[u] = ok[u] && xp >= 1 && xp <= gr.X && yp >= 1 && yp <= gr.Y && zp >= 1 && zp <= gr.Z;
+            if (inter[u]) {
+                xr[u] = Vec<T>::load_raw(raw + (base + r) * ld_raw + c0);
+                gv[u] = Vec<T>::load_raw(g_out + (base + r) * ld_g + c0);
             }
-        } else {
-#pragma unroll
-            for (int i = 0; i < N; ++i) o[i] = 0.0f;
         }
-        Vec<T>::store(d_raw + row * ld_d + c0, o);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            float o[N];
+            if (inter[u]) {
+                float x[N], g[N];
+                Vec<T>::unpack(xr[u], x);
+                Vec<T>::unpack(gv[u], g);
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const float uu = fmaf(ka[i], x[i], ko[i]);
+                    const float gu = act ? g[i] * dsilu<T>(uu) : g[i];
+                    o[i] = fmaf(c1[i], gu, fmaf(c2[i], x[i], c3[i]));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; ++i) o[i] = 0.0f;
+            }
+            Vec<T>::store(d_raw + (base + r0 + u * stride) * ld_d + c0, o);
+        }
     }
 }
 
@@ -615,7 +659,7 @@ __device__ __forceinline__ int axis_sources(int i, int n_in, int n_out, float sc
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 trilinear_bwd_kernel(const T* __restrict__ g_out, int ld_g, Grid3 go, T* __restrict__ d_in, int ld_d, Grid3 gi, int C,
-                     RowSplit split, int chunks, float sx, float sy, float sz) {
+                     RowSplit split, int chunks, float sx, float sy, float sz, int accumulate) {
     constexpr int N = Vec<T>::N;
     const int b = blockIdx.y;
     const int vox_step = kThreads / chunks;
@@ -626,10 +670,13 @@ trilinear_bwd_kernel(const T* __restrict__ g_out, int ld_g, Grid3 go, T* __restr
         int xp, yp, zp;
         split(r, xp, yp, zp);
         const bool interior = xp >= 1 && xp <= gi.X && yp >= 1 && yp <= gi.Y && zp >= 1 && zp <= gi.Z;
+        if (accumulate && !interior) continue;  // d_in += ...: halo rows stay as they are
         float acc[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) acc[i] = 0.0f;
+        T* dst = d_in + ((int64_t)b * gi.vox_p + r) * ld_d + c0;
         if (interior) {
+            if (accumulate) Vec<T>::load(dst, acc);
             int ox[12], oy[12], oz[12];
             float wx[12], wy[12], wz[12];
             const int nx = axis_sources(xp - 1, gi.X, go.X, sx, ox, wx);
@@ -645,7 +692,127 @@ trilinear_bwd_kernel(const T* __restrict__ g_out, int ld_g, Grid3 go, T* __restr
                         for (int i = 0; i < N; ++i) acc[i] = fmaf(w, v[i], acc[i]);
                     }
         }
-        Vec<T>::store(d_in + ((int64_t)b * gi.vox_p + r) * ld_d + c0, acc);
+        Vec<T>::store(dst, acc);
+    }
+}
+
+// Column walker (the form the training step runs on): a thread owns one (x, y) column of the INPUT-side grid and one
+// 16-byte channel chunk.  The forward op is out[o] = l0*in[i0] + l1*in[i1] per axis, so along x and y the column
+// gathers its <= 6 source lines per axis (tables per block in shared memory), and along z it walks the output-side
+// z index once, scattering every x/y-reduced value into the two running accumulators of in[i0], in[i0+1] and storing
+// an input voxel as soon as the walk has passed it.  Each source row is read by ~2x2 columns (instead of by every
+// input voxel it touches: 4^3 reads per voxel for the adjoint of the 2x upsampling), the loads of one source x are
+// issued together, and nothing is re-derived per voxel.  accumulate: d_in += (halo rows untouched) - the skip
+// connection's gradient is added in the same pass.
+constexpr int TB_S = 6;  // sources per axis (scale >= 0.4: at most ceil(2 / scale) + 1)
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+trilinear_bwd_walk_kernel(const T* __restrict__ g_out, int ld_g, Grid3 go, T* __restrict__ d_in, int ld_d, Grid3 gi, int chunks,
+                          int tx, int ty, int tiles_y, float sx, float sy, float sz, int accumulate) {
+    constexpr int N = Vec<T>::N;
+    __shared__ int s_ox[32][TB_S], s_oy[32][TB_S], s_nx[32], s_ny[32];
+    __shared__ float s_wx[32][TB_S], s_wy[32][TB_S];
+    const int b = blockIdx.y;
+    const int bx = blockIdx.x / tiles_y, by = blockIdx.x % tiles_y;
+    if ((int)threadIdx.x < tx + ty) {
+        // one thread per tile row / tile column: sources of that input index along x / y
+        const bool is_x = (int)threadIdx.x < tx;
+        const int j = is_x ? (int)threadIdx.x : (int)threadIdx.x - tx;
+        const int p = (is_x ? bx * tx : by * ty) + j;  // haloed coordinate
+        const int n_in = is_x ? gi.X : gi.Y, n_out = is_x ? go.X : go.Y;
+        int oo[12];
+        float ww[12];
+        int n = 0;
+        if (p >= 1 && p <= n_in) n = axis_sources(p - 1, n_in, n_out, is_x ? sx : sy, oo, ww);
+        if (n > TB_S) n = TB_S;  // excluded by the host (scale >= 0.4)
+        for (int k = 0; k < TB_S; ++k) {
+            (is_x ? s_ox : s_oy)[j][k] = k < n ? oo[k] : 0;
+            (is_x ? s_wx : s_wy)[j][k] = k < n ? ww[k] : 0.0f;
+        }
+        (is_x ? s_nx : s_ny)[j] = n;
+    }
+    __syncthreads();
+    const int ch = threadIdx.x % chunks, col = threadIdx.x / chunks;
+    if (col >= tx * ty) return;
+    const int jx = col / ty, jy = col % ty;
+    const int xp = bx * tx + jx, yp = by * ty + jy;
+    if (xp >= gi.Xp || yp >= gi.Yp) return;
+    const int c0 = ch * N;
+    T* dcol = d_in + ((int64_t)b * gi.vox_p + ((int64_t)xp * gi.Yp + yp) * gi.Zp) * ld_d + c0;
+    float zero[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) zero[i] = 0.0f;
+    const bool interior = xp >= 1 && xp <= gi.X && yp >= 1 && yp <= gi.Y;
+    if (!interior) {
+        if (!accumulate)
+            for (int zp = 0; zp < gi.Zp; ++zp) Vec<T>::store(dcol + (int64_t)zp * ld_d, zero);
+        return;
+    }
+    const int nx = s_nx[jx], ny = s_ny[jy];
+    int64_t yoff[TB_S];
+    float wy[TB_S];
+#pragma unroll
+    for (int k = 0; k < TB_S; ++k) {
+        yoff[k] = (int64_t)(s_oy[jy][k] + 1) * go.Zp * ld_g;
+        wy[k] = s_wy[jy][k];
+    }
+    const T* gb = g_out + (int64_t)b * go.vox_p * ld_g + c0;
+    float acc0[N], acc1[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc0[i] = acc1[i] = 0.0f;
+    int cur = 0;  // input-side z index held by acc0 (acc1: cur + 1)
+    auto flush = [&]() {
+        T* dst = dcol + (int64_t)(cur + 1) * ld_d;
+        if (accumulate) {
+            float e[N];
+            Vec<T>::load(dst, e);
+#pragma unroll
+            for (int i = 0; i < N; ++i) acc0[i] += e[i];
+        }
+        Vec<T>::store(dst, acc0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            acc0[i] = acc1[i];
+            acc1[i] = 0.0f;
+        }
+        ++cur;
+    };
+    for (int oz = 0; oz < go.Z; ++oz) {
+        const Lerp lz = axis_lerp(oz, gi.Z, sz);
+        float s[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) s[i] = 0.0f;
+        for (int a = 0; a < nx; ++a) {
+            const T* gx = gb + ((int64_t)(s_ox[jx][a] + 1) * go.Yp * go.Zp + (oz + 1)) * ld_g;
+            const float wxa = s_wx[jx][a];
+            uint4 raw[TB_S];
+#pragma unroll
+            for (int k = 0; k < TB_S; ++k)
+                if (k < ny) raw[k] = Vec<T>::load_raw(gx + yoff[k]);
+#pragma unroll
+            for (int k = 0; k < TB_S; ++k)
+                if (k < ny) {
+                    float v[N];
+                    Vec<T>::unpack(raw[k], v);
+                    const float w = wxa * wy[k];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) s[i] = fmaf(w, v[i], s[i]);
+                }
+        }
+        while (cur < lz.i0) flush();
+        const bool same = lz.i1 == lz.i0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            acc0[i] = fmaf(lz.l0, s[i], acc0[i]);
+            if (same) acc0[i] = fmaf(lz.l1, s[i], acc0[i]);
+            else acc1[i] = fmaf(lz.l1, s[i], acc1[i]);
+        }
+    }
+    while (cur < gi.Z) flush();
+    if (!accumulate) {
+        Vec<T>::store(dcol, zero);
+        Vec<T>::store(dcol + (int64_t)(gi.Zp - 1) * ld_d, zero);
     }
 }
 
@@ -857,15 +1024,19 @@ int tdb_pointwise_bwd_reduce(const void* g_out, int ld_g, const void* raw, int l
     if (G < 1) G = 1;
     Grid3 gr(B, X, Y, Z);
     const int chunks = C / n;
-    const int vox_per_block = (kThreads / chunks) * 32;
-    dim3 grid((unsigned)ceil_div((int64_t)X * Y * Z, vox_per_block), (unsigned)B);
+    const int64_t trip = (int64_t)(kThreads / chunks) * 4;  // voxels one block handles per trip
+    int64_t blocks = ceil_div((int64_t)X * Y * Z, trip);
+    const int64_t cap = (148 * 4) / (B < 1 ? 1 : B) < 1 ? 1 : (148 * 4) / (B < 1 ? 1 : B);
+    if (blocks > cap) blocks = cap;
+    dim3 grid((unsigned)blocks, (unsigned)B);
     cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem = (size_t)8 * C * sizeof(float);
     if (dtype == TDB_BF16)
-        pw_bwd_reduce_kernel<bf16><<<grid, kThreads, (size_t)4 * C * sizeof(float), s>>>((const bf16*)g_out, ld_g, (const bf16*)raw, ld_raw, stats, gamma, beta,
-                                                              film, film_ld, red, gr, C, G, eps, flags, vox_per_block, FastDiv((uint32_t)Z), FastDiv((uint32_t)Y));
+        pw_bwd_reduce_kernel<bf16><<<grid, kThreads, smem, s>>>((const bf16*)g_out, ld_g, (const bf16*)raw, ld_raw, stats, gamma, beta,
+                                                              film, film_ld, red, gr, C, G, eps, flags, FastDiv((uint32_t)Z), FastDiv((uint32_t)Y));
     else
-        pw_bwd_reduce_kernel<float><<<grid, kThreads, (size_t)4 * C * sizeof(float), s>>>((const float*)g_out, ld_g, (const float*)raw, ld_raw, stats, gamma,
-                                                               beta, film, film_ld, red, gr, C, G, eps, flags, vox_per_block, FastDiv((uint32_t)Z), FastDiv((uint32_t)Y));
+        pw_bwd_reduce_kernel<float><<<grid, kThreads, smem, s>>>((const float*)g_out, ld_g, (const float*)raw, ld_raw, stats, gamma,
+                                                               beta, film, film_ld, red, gr, C, G, eps, flags, FastDiv((uint32_t)Z), FastDiv((uint32_t)Y));
     TDB_CHECK_LAUNCH("tdb_pointwise_bwd_reduce");
     return 0;
 }
@@ -899,13 +1070,17 @@ int tdb_pointwise_bwd_apply(const void* g_out, int ld_g, const void* raw, int ld
     if (G < 1) G = 1;
     Grid3 gr(B, X, Y, Z);
     const int chunks = C / n;
-    dim3 grid((unsigned)blocks_per_sample(gr.vox_p * chunks, B), (unsigned)B);
+    int64_t blocks = ceil_div(gr.vox_p, (int64_t)(kThreads / chunks) * 4);
+    const int64_t cap = (148 * 8) / (B < 1 ? 1 : B) < 1 ? 1 : (148 * 8) / (B < 1 ? 1 : B);
+    if (blocks > cap) blocks = cap;
+    dim3 grid((unsigned)blocks, (unsigned)B);
     cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem = (size_t)5 * C * sizeof(float);
     if (dtype == TDB_BF16)
-        pw_bwd_apply_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)g_out, ld_g, (const bf16*)raw, ld_raw, stats, gamma, beta, film,
+        pw_bwd_apply_kernel<bf16><<<grid, kThreads, smem, s>>>((const bf16*)g_out, ld_g, (const bf16*)raw, ld_raw, stats, gamma, beta, film,
                                                              film_ld, grp, (bf16*)d_raw, ld_d, gr, C, G, eps, flags, make_split(gr), chunks);
     else
-        pw_bwd_apply_kernel<float><<<grid, kThreads, 0, s>>>((const float*)g_out, ld_g, (const float*)raw, ld_raw, stats, gamma, beta,
+        pw_bwd_apply_kernel<float><<<grid, kThreads, smem, s>>>((const float*)g_out, ld_g, (const float*)raw, ld_raw, stats, gamma, beta,
                                                               film, film_ld, grp, (float*)d_raw, ld_d, gr, C, G, eps, flags,
                                                               make_split(gr), chunks);
     TDB_CHECK_LAUNCH("tdb_pointwise_bwd_apply");
@@ -955,25 +1130,42 @@ int tdb_conv3d_wgrad(const void* in, int ld_in, const void* d_out, int ld_do, fl
 }
 
 int tdb_trilinear_bwd(const void* g_out, int ld_g, int Xo, int Yo, int Zo, void* d_in, int ld_d, int Xi, int Yi, int Zi, int B,
-                      int C, int dtype, void* stream) {
+                      int C, int dtype, unsigned flags, void* stream) {
     TDB_REQUIRE(g_out && d_in, TDB_E_BADARG, "tdb_trilinear_bwd: null pointer");
     const int n = dtype == TDB_BF16 ? 8 : 4;
     TDB_REQUIRE(C % n == 0 && ld_g % n == 0 && ld_d % n == 0 && C / n <= kThreads && aligned16(g_out) && aligned16(d_in),
                 TDB_E_UNSUPPORTED, "tdb_trilinear_bwd: C/ld must be multiples of %d", n);
     Grid3 gi(B, Xi, Yi, Zi), go(B, Xo, Yo, Zo);
     const int chunks = C / n;
-    dim3 grid((unsigned)blocks_per_sample(gi.vox_p * chunks, B), (unsigned)B);
+    const int accumulate = (flags & TDB_TRIBWD_ACCUMULATE) ? 1 : 0;
     auto scale_of = [](int n_in, int n_out) { return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.0f; };
     const float sx = scale_of(Xi, Xo), sy = scale_of(Yi, Yo), sz = scale_of(Zi, Zo);
     auto ok = [](float sc, int n_out) { return n_out == 1 || sc >= 0.2f; };
     TDB_REQUIRE(ok(sx, Xo) && ok(sy, Yo) && ok(sz, Zo), TDB_E_UNSUPPORTED, "tdb_trilinear_bwd: upsampling factor above 5 per axis");
     cudaStream_t s = (cudaStream_t)stream;
+    // column walker: <= 6 sources per axis (up-sampling factor <= 2.5) and a power-of-two number of channel chunks
+    auto few = [](float sc, int n_out) { return n_out == 1 || sc >= 0.4f; };
+    if (few(sx, Xo) && few(sy, Yo) && (chunks & (chunks - 1)) == 0) {
+        const int cols = kThreads / chunks;       // columns per block: a tx x ty tile of (x, y)
+        const int ty = cols < 8 ? cols : 8, tx = cols / ty;
+        const int tiles_y = (int)ceil_div(gi.Yp, ty), tiles_x = (int)ceil_div(gi.Xp, tx);
+        dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)B);
+        if (dtype == TDB_BF16)
+            trilinear_bwd_walk_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)g_out, ld_g, go, (bf16*)d_in, ld_d, gi, chunks, tx, ty,
+                                                                       tiles_y, sx, sy, sz, accumulate);
+        else
+            trilinear_bwd_walk_kernel<float><<<grid, kThreads, 0, s>>>((const float*)g_out, ld_g, go, (float*)d_in, ld_d, gi, chunks, tx,
+                                                                        ty, tiles_y, sx, sy, sz, accumulate);
+        TDB_CHECK_LAUNCH("tdb_trilinear_bwd");
+        return 0;
+    }
+    dim3 grid((unsigned)blocks_per_sample(gi.vox_p * chunks, B), (unsigned)B);
     if (dtype == TDB_BF16)
         trilinear_bwd_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)g_out, ld_g, go, (bf16*)d_in, ld_d, gi, C, make_split(gi), chunks,
-                                                              sx, sy, sz);
+                                                              sx, sy, sz, accumulate);
     else
         trilinear_bwd_kernel<float><<<grid, kThreads, 0, s>>>((const float*)g_out, ld_g, go, (float*)d_in, ld_d, gi, C, make_split(gi),
-                                                               chunks, sx, sy, sz);
+                                                               chunks, sx, sy, sz, accumulate);
     TDB_CHECK_LAUNCH("tdb_trilinear_bwd");
     return 0;
 }

@@ -18,6 +18,7 @@ STEP_NOISE_BCS, STEP_CLIP, STEP_FINAL, STEP_LEARNED_VAR = 1, 2, 4, 8
 CONV_ALL_ROWS = 1
 CONV_CLUSTER_MC = 2
 WGRAD_ZERO_HALO = 1
+TRIBWD_ACCUMULATE = 1
 
 _p, _i, _l, _u, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint, C.c_float, C.c_double
 
@@ -47,7 +48,7 @@ SIGNATURES = {
     "tdb_pointwise_bwd_apply": [_p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _u, _i, _p],
     "tdb_conv3d_wgrad": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _u, _p],
     "tdb_conv3d_wgrad_tc": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _u, _p],
-    "tdb_trilinear_bwd": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "tdb_trilinear_bwd": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _u, _p],
     "tdb_attention_bwd": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_grad_sqnorm": [_p, _p, _p, _p, _i, _i, _p, _p],
     "tdb_radam_step": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _f, _f, _d, _d, _f, _f, _i, _p],

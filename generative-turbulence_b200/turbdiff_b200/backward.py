@@ -237,7 +237,7 @@ class BackwardProgram:
             Xo, Yo, Zo = p["sizes"][l]
             Xi, Yi, Zi = p["sizes"][l + 1]
             up_half = g_cat.slice(0, C)
-            call("tdb_trilinear_bwd", up_half.ptr, up_half.ld, Xo, Yo, Zo, g.ptr, g.ld, Xi, Yi, Zi, B, C, dt, s())
+            call("tdb_trilinear_bwd", up_half.ptr, up_half.ld, Xo, Yo, Zo, g.ptr, g.ld, Xi, Yi, Zi, B, C, dt, 0, s())
             p.setdefault("g_skip", {})[l] = g_cat.slice(C, C)
         # centre
         g = self._resblock_bwd(p, "center2", g, grads, d_film)
@@ -248,9 +248,8 @@ class BackwardProgram:
             g_skip = p["g_skip"][l]
             Xi, Yi, Zi = p["sizes"][l]
             Xo, Yo, Zo = p["sizes"][l + 1]
-            tmp = self._tmp(p, l, g_skip.C, "g_down")
-            call("tdb_trilinear_bwd", g.ptr, g.ld, Xo, Yo, Zo, tmp.ptr, tmp.ld, Xi, Yi, Zi, B, g_skip.C, dt, s())
-            self._add_interior(p, g_skip, tmp)
+            # skip gradient += gradient through the down-sampling, in one pass (no temporary grid, no separate add)
+            call("tdb_trilinear_bwd", g.ptr, g.ld, Xo, Yo, Zo, g_skip.ptr, g_skip.ld, Xi, Yi, Zi, B, g_skip.C, dt, _lib.TRIBWD_ACCUMULATE, s())
             g = self._resblock_bwd(p, f"down{l}", g_skip, grads, d_film)
 
         # encoders (g = folded gradient of xin0: [encode_x | encode_c_local])

@@ -318,9 +318,13 @@ TDB_API int tdb_conv3d_wgrad(const void* in, int ld_in, const void* d_out, int l
 TDB_API int tdb_conv3d_wgrad_tc(const void* in, int ld_in, const void* d_out, int ld_do, float* dw, int B, int X, int Y,
                         int Z, int Cin, int Cout, int ntaps, unsigned mode, void* stream);
 
-/* Transpose of tdb_trilinear: d_in (interior rows; halo rows zero) from the folded output gradient. */
+/* Transpose of tdb_trilinear (reference: autograd of F.interpolate(mode="trilinear", align_corners=True), ddpm.py:358-369):
+ * d_in (interior rows; halo rows zero) from the output gradient's interior rows.
+ * flags & TDB_TRIBWD_ACCUMULATE: d_in += the transposed gradient on interior rows, halo rows untouched (the skip
+ * connection's gradient and the gradient through the down-sampling are summed in one pass). */
+#define TDB_TRIBWD_ACCUMULATE 1u
 TDB_API int tdb_trilinear_bwd(const void* g_out, int ld_g, int Xo, int Yo, int Zo, void* d_in, int ld_d, int Xi,
-                      int Yi, int Zi, int B, int C, int dtype, void* stream);
+                      int Yi, int Zi, int B, int C, int dtype, unsigned flags, void* stream);
 
 /* Backward of tdb_attention: d_qkv (q|k|v gradient, interior rows) from qkv and d_out. S <= 128. */
 TDB_API int tdb_attention_bwd(const void* qkv, int ld_qkv, const void* d_out, int ld_do, void* d_qkv, int ld_dq, int B,

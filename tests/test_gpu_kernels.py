@@ -206,6 +206,94 @@ def test_trilinear(lib, prec, sizes):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("C", [16, 64, 512])
+@pytest.mark.parametrize("sizes", [((11, 7, 5), (5, 3, 3)), ((5, 3, 3), (11, 7, 5)), ((12, 3, 3), (24, 6, 6)), ((6, 6, 6), (6, 6, 6)),
+                                   ((3, 3, 3), (6, 6, 6)), ((24, 6, 6), (12, 3, 3)), ((25, 12, 12), (50, 25, 25)), ((4, 3, 3), (14, 9, 3))])
+def test_trilinear_bwd_is_adjoint(lib, prec, C, sizes):
+    """tdb_trilinear_bwd = autograd of F.interpolate(trilinear, align_corners=True) (reference ddpm.py:358-369), halo rows of
+    the result zero; with TDB_TRIBWD_ACCUMULATE the transposed gradient is added onto d_in's interior and its halo is kept."""
+    code, td = _dt(prec)
+    (Xi, Yi, Zi), (Xo, Yo, Zo) = sizes
+    if C == 512 and Xi * Yi * Zi > 2000:
+        pytest.skip("large grid x wide channels adds nothing")
+    B = 2
+    g = gen(B, C, Xo, Yo, Zo, seed=19).to(td).float()
+    x = torch.zeros(B, C, Xi, Yi, Zi, dtype=torch.float64, requires_grad=True)
+    (want,) = torch.autograd.grad(F.interpolate(x, size=(Xo, Yo, Zo), mode="trilinear", align_corners=True), x, g.double().cpu())
+    gg = to_halo(g, dtype=td, ld=2 * C, c0=C)
+    gg[:, 0] = 55.0  # halo rows of the incoming gradient are never read
+    d_in = torch.full((B, Xi + 2, Yi + 2, Zi + 2, C), 3.0, device="cuda", dtype=td)
+    off = C * gg.element_size()
+    lib.call("tdb_trilinear_bwd", gg.data_ptr() + off, 2 * C, Xo, Yo, Zo, d_in.data_ptr(), C, Xi, Yi, Zi, B, C, code, 0, lib.stream_ptr())
+    tol = 2e-6 if prec == "fp32" else 6e-3
+    assert rel_l2(from_halo(d_in), want) < tol
+    halo = d_in.clone()
+    halo[:, 1:-1, 1:-1, 1:-1] = 0
+    assert float(halo.float().abs().max()) == 0.0
+    # accumulate form
+    base = gen(B, C, Xi, Yi, Zi, seed=20).to(td).float()
+    acc = to_halo(base, dtype=td)
+    acc[:, 0] = 7.0
+    lib.call("tdb_trilinear_bwd", gg.data_ptr() + off, 2 * C, Xo, Yo, Zo, acc.data_ptr(), C, Xi, Yi, Zi, B, C, code,
+             lib.TRIBWD_ACCUMULATE, lib.stream_ptr())
+    assert rel_l2(from_halo(acc), want + base.double().cpu()) < tol
+    assert float(acc[:, 0].float().min()) == 7.0 and float(acc[:, 0].float().max()) == 7.0
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("C,G,with_film,size", [(64, 8, True, (9, 7, 6)), (16, 8, False, (7, 5, 6)), (32, 1, True, (20, 9, 11)),
+                                                (512, 8, True, (6, 3, 3)), (32, 32, False, (40, 12, 10))])
+def test_pointwise_bwd_matches_autograd(lib, prec, C, G, with_film, size):
+    """tdb_pointwise_bwd_reduce / _finalize / _apply against torch.autograd of GroupNorm -> FiLM -> SiLU
+    (reference Block.forward, ddpm.py:168-177): input gradient, norm / FiLM / bias-sum gradients."""
+    code, td = _dt(prec)
+    X, Y, Z = size
+    B = 2
+    x = (gen(B, C, X, Y, Z, seed=4) * 1.5 + 0.3).to(td).float()
+    g = gen(B, C, X, Y, Z, seed=5).to(td).float()
+    gamma, beta = gen(C, seed=6) * 0.2 + 1, gen(C, seed=7) * 0.1
+    film = gen(B, 2 * C, seed=8) * 0.3
+    xd = x.double().cpu().requires_grad_(True)
+    gm, bt, fl = gamma.double().cpu().requires_grad_(True), beta.double().cpu().requires_grad_(True), film.double().cpu().requires_grad_(True)
+    h = F.group_norm(xd, G, gm, bt, eps=1e-5)
+    if with_film:
+        h = fl[:, C:, None, None, None] + (fl[:, :C, None, None, None] + 1) * h
+    y = F.silu(h)
+    want = torch.autograd.grad(y, [xd, gm, bt] + ([fl] if with_film else []), g.double().cpu())
+
+    raw = to_halo(x, dtype=td)
+    raw[:, 0] = 77.0
+    gg = to_halo(g, dtype=td)
+    gg[:, 0] = -31.0
+    stats = torch.zeros((B, G, 2), dtype=torch.float64, device="cuda")
+    lib.call("tdb_gn_stats", raw.data_ptr(), C, stats.data_ptr(), B, X, Y, Z, C, G, code, lib.stream_ptr())
+    red = torch.zeros((B, C, 4), dtype=torch.float64, device="cuda")
+    fptr = film.data_ptr() if with_film else None
+    lib.call("tdb_pointwise_bwd_reduce", gg.data_ptr(), C, raw.data_ptr(), C, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), fptr,
+             2 * C, red.data_ptr(), B, X, Y, Z, C, G, 1e-5, lib.PW_SILU, code, lib.stream_ptr())
+    out = torch.empty((4, C), dtype=torch.float32, device="cuda")
+    grp = torch.empty((B, G, 2), dtype=torch.float32, device="cuda")
+    dfilm = torch.zeros((B, 2 * C), dtype=torch.float32, device="cuda")
+    lib.call("tdb_pointwise_bwd_finalize", red.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), fptr, 2 * C,
+             grp.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(),
+             dfilm.data_ptr() if with_film else None, 2 * C, B, X, Y, Z, C, G, 1e-5, lib.stream_ptr())
+    d_raw = torch.full((B, X + 2, Y + 2, Z + 2, C), 9.0, device="cuda", dtype=td)
+    lib.call("tdb_pointwise_bwd_apply", gg.data_ptr(), C, raw.data_ptr(), C, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), fptr,
+             2 * C, grp.data_ptr(), d_raw.data_ptr(), C, B, X, Y, Z, C, G, 1e-5, lib.PW_SILU, code, lib.stream_ptr())
+    tol = 2e-5 if prec == "fp32" else 1.2e-2
+    assert rel_l2(from_halo(d_raw), want[0]) < tol
+    halo = d_raw.clone()
+    halo[:, 1:-1, 1:-1, 1:-1] = 0
+    assert float(halo.float().abs().max()) == 0.0
+    ptol = 2e-5 if prec == "fp32" else 4e-3
+    assert rel_l2(out[1], want[1]) < ptol and rel_l2(out[2], want[2]) < ptol
+    assert rel_l2(out[0], want[0].sum(dim=(0, 2, 3, 4))) < (1e-3 if prec == "fp32" else 3e-2) or float(want[0].sum(dim=(0, 2, 3, 4)).abs().max()) < 1e-6
+    assert rel_l2(out[3], g.double().cpu().sum(dim=(0, 2, 3, 4))) < 1e-5
+    if with_film:
+        assert rel_l2(dfilm, want[3]) < ptol
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
 @pytest.mark.parametrize("spatial", [(12, 3, 3), (8, 4, 4), (4, 2, 2)])
 def test_attention(lib, prec, spatial):
     code, td = _dt(prec)
