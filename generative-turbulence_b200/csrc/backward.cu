@@ -696,77 +696,88 @@ trilinear_bwd_kernel(const T* __restrict__ g_out, int ld_g, Grid3 go, T* __restr
     }
 }
 
-// Column walker (the form the training step runs on): a thread owns one (x, y) column of the INPUT-side grid and one
-// 16-byte channel chunk.  The forward op is out[o] = l0*in[i0] + l1*in[i1] per axis, so along x and y the column
-// gathers its <= 6 source lines per axis (tables per block in shared memory), and along z it walks the output-side
-// z index once, scattering every x/y-reduced value into the two running accumulators of in[i0], in[i0+1] and storing
-// an input voxel as soon as the walk has passed it.  Each source row is read by ~2x2 columns (instead of by every
-// input voxel it touches: 4^3 reads per voxel for the adjoint of the 2x upsampling), the loads of one source x are
-// issued together, and nothing is re-derived per voxel.  accumulate: d_in += (halo rows untouched) - the skip
-// connection's gradient is added in the same pass.
+// Line walker (the form the training step runs on): a thread owns one (y, z) line of the INPUT-side grid, one 16-byte
+// channel chunk and a segment of x.  The forward op is out[o] = l0*in[i0] + l1*in[i1] per axis, so along y and z the
+// line gathers its <= 6 source lines per axis (tables per block in shared memory), and along x it walks the output-side
+// x index once, scattering every y/z-reduced value into the two running accumulators of in[i0], in[i0+1] and storing an
+// input voxel as soon as the walk has passed it.  Consecutive threads are consecutive z, so at every step a block
+// touches contiguous runs of memory; each source row is read by ~2x2 lines (instead of by every input voxel it touches:
+// 4^3 reads per voxel for the adjoint of the 2x upsampling) and nothing is re-derived per voxel.  accumulate: d_in +=
+// (halo rows untouched) - the skip connection's gradient is added in the same pass.
 constexpr int TB_S = 6;  // sources per axis (scale >= 0.4: at most ceil(2 / scale) + 1)
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 trilinear_bwd_walk_kernel(const T* __restrict__ g_out, int ld_g, Grid3 go, T* __restrict__ d_in, int ld_d, Grid3 gi, int chunks,
-                          int tx, int ty, int tiles_y, float sx, float sy, float sz, int accumulate) {
+                          int seg_len, float sx, float sy, float sz, int accumulate, FastDiv by_zp) {
     constexpr int N = Vec<T>::N;
-    __shared__ int s_ox[32][TB_S], s_oy[32][TB_S], s_nx[32], s_ny[32];
-    __shared__ float s_wx[32][TB_S], s_wy[32][TB_S];
+    extern __shared__ int s_tab[];  // per haloed y, then per haloed z: [TB_S] source offsets, [TB_S] weights, count
+    constexpr int ENT = 2 * TB_S + 1;
     const int b = blockIdx.y;
-    const int bx = blockIdx.x / tiles_y, by = blockIdx.x % tiles_y;
-    if ((int)threadIdx.x < tx + ty) {
-        // one thread per tile row / tile column: sources of that input index along x / y
-        const bool is_x = (int)threadIdx.x < tx;
-        const int j = is_x ? (int)threadIdx.x : (int)threadIdx.x - tx;
-        const int p = (is_x ? bx * tx : by * ty) + j;  // haloed coordinate
-        const int n_in = is_x ? gi.X : gi.Y, n_out = is_x ? go.X : go.Y;
+    for (int e = threadIdx.x; e < gi.Yp + gi.Zp; e += blockDim.x) {
+        const bool is_y = e < gi.Yp;
+        const int p = is_y ? e : e - gi.Yp;  // haloed coordinate
+        const int n_in = is_y ? gi.Y : gi.Z, n_out = is_y ? go.Y : go.Z;
         int oo[12];
         float ww[12];
         int n = 0;
-        if (p >= 1 && p <= n_in) n = axis_sources(p - 1, n_in, n_out, is_x ? sx : sy, oo, ww);
+        if (p >= 1 && p <= n_in) n = axis_sources(p - 1, n_in, n_out, is_y ? sy : sz, oo, ww);
         if (n > TB_S) n = TB_S;  // excluded by the host (scale >= 0.4)
+        int* t = s_tab + e * ENT;
         for (int k = 0; k < TB_S; ++k) {
-            (is_x ? s_ox : s_oy)[j][k] = k < n ? oo[k] : 0;
-            (is_x ? s_wx : s_wy)[j][k] = k < n ? ww[k] : 0.0f;
+            t[k] = k < n ? (oo[k] + 1) * (is_y ? go.Zp : 1) : 0;  // row offset of the source inside an x plane
+            t[TB_S + k] = __float_as_int(k < n ? ww[k] : 0.0f);
         }
-        (is_x ? s_nx : s_ny)[j] = n;
+        t[2 * TB_S] = n;
     }
     __syncthreads();
-    const int ch = threadIdx.x % chunks, col = threadIdx.x / chunks;
-    if (col >= tx * ty) return;
-    const int jx = col / ty, jy = col % ty;
-    const int xp = bx * tx + jx, yp = by * ty + jy;
-    if (xp >= gi.Xp || yp >= gi.Yp) return;
+    const int ch = threadIdx.x % chunks;
+    const uint32_t col = blockIdx.x * (uint32_t)(kThreads / chunks) + threadIdx.x / chunks;
+    if (threadIdx.x / chunks >= kThreads / chunks || col >= (uint32_t)(gi.Yp * gi.Zp)) return;
+    uint32_t ypu, zpu;
+    by_zp.divmod(col, ypu, zpu);
+    const int yp = (int)ypu, zp = (int)zpu;
     const int c0 = ch * N;
-    T* dcol = d_in + ((int64_t)b * gi.vox_p + ((int64_t)xp * gi.Yp + yp) * gi.Zp) * ld_d + c0;
+    const int i_lo = blockIdx.z * seg_len, i_hi = min(gi.X, i_lo + seg_len);  // input-side x range of this segment
+    const int64_t plane_d = (int64_t)gi.Yp * gi.Zp * ld_d;
+    T* dline = d_in + ((int64_t)b * gi.vox_p + (int64_t)yp * gi.Zp + zp) * ld_d + c0;  // x = halo plane 0 of this line
     float zero[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) zero[i] = 0.0f;
-    const bool interior = xp >= 1 && xp <= gi.X && yp >= 1 && yp <= gi.Y;
+    const bool interior = yp >= 1 && yp <= gi.Y && zp >= 1 && zp <= gi.Z;
     if (!interior) {
-        if (!accumulate)
-            for (int zp = 0; zp < gi.Zp; ++zp) Vec<T>::store(dcol + (int64_t)zp * ld_d, zero);
+        if (!accumulate) {
+            const int x_end = i_hi == gi.X ? gi.Xp : i_hi + 1;
+            for (int xp = i_lo == 0 ? 0 : i_lo + 1; xp < x_end; ++xp) Vec<T>::store(dline + xp * plane_d, zero);
+        }
         return;
     }
-    const int nx = s_nx[jx], ny = s_ny[jy];
-    int64_t yoff[TB_S];
-    float wy[TB_S];
+    const int* ty = s_tab + yp * ENT;
+    const int* tz = s_tab + (gi.Yp + zp) * ENT;
+    const int ny = ty[2 * TB_S], nz = tz[2 * TB_S];
+    int zoff[TB_S];
+    float wz[TB_S];
 #pragma unroll
     for (int k = 0; k < TB_S; ++k) {
-        yoff[k] = (int64_t)(s_oy[jy][k] + 1) * go.Zp * ld_g;
-        wy[k] = s_wy[jy][k];
+        zoff[k] = tz[k] * ld_g;  // element offset inside an x plane (< 2^31: checked on the host)
+        wz[k] = __int_as_float(tz[TB_S + k]);
     }
     const T* gb = g_out + (int64_t)b * go.vox_p * ld_g + c0;
+    const int64_t plane_g = (int64_t)go.Yp * go.Zp;
     float acc0[N], acc1[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) acc0[i] = acc1[i] = 0.0f;
-    int cur = 0;  // input-side z index held by acc0 (acc1: cur + 1)
+    int cur = i_lo;  // input-side x index held by acc0 (acc1: cur + 1)
+    // accumulate: the existing values of the next two voxels of the line are fetched ahead of their flush
+    uint4 e0 = make_uint4(0u, 0u, 0u, 0u), e1 = e0;
+    auto existing = [&](int i) { return (accumulate && i < i_hi) ? Vec<T>::load_raw(dline + (int64_t)(i + 1) * plane_d) : make_uint4(0u, 0u, 0u, 0u); };
+    e0 = existing(cur);
+    e1 = existing(cur + 1);
     auto flush = [&]() {
-        T* dst = dcol + (int64_t)(cur + 1) * ld_d;
+        T* dst = dline + (int64_t)(cur + 1) * plane_d;
         if (accumulate) {
             float e[N];
-            Vec<T>::load(dst, e);
+            Vec<T>::unpack(e0, e);
 #pragma unroll
             for (int i = 0; i < N; ++i) acc0[i] += e[i];
         }
@@ -777,42 +788,58 @@ trilinear_bwd_walk_kernel(const T* __restrict__ g_out, int ld_g, Grid3 go, T* __
             acc1[i] = 0.0f;
         }
         ++cur;
+        e0 = e1;
+        e1 = existing(cur + 1);
     };
-    for (int oz = 0; oz < go.Z; ++oz) {
-        const Lerp lz = axis_lerp(oz, gi.Z, sz);
+    // output-side x range that touches [i_lo, i_hi): a little wider than needed, contributions outside are dropped
+    int o_lo = 0, o_hi = go.X - 1;
+    if (sx > 0.0f) {
+        o_lo = max(0, (int)floorf((float)(i_lo - 1) / sx) - 1);
+        o_hi = min(go.X - 1, (int)ceilf((float)i_hi / sx) + 1);
+    }
+    for (int ox = o_lo; ox <= o_hi; ++ox) {
+        const Lerp lx = axis_lerp(ox, gi.X, sx);
+        if (lx.i1 < i_lo) continue;
+        if (lx.i0 >= i_hi) break;
         float s[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) s[i] = 0.0f;
-        for (int a = 0; a < nx; ++a) {
-            const T* gx = gb + ((int64_t)(s_ox[jx][a] + 1) * go.Yp * go.Zp + (oz + 1)) * ld_g;
-            const float wxa = s_wx[jx][a];
-            uint4 raw[TB_S];
+        const T* gx = gb + (int64_t)(ox + 1) * plane_g * ld_g;
+        for (int a = 0; a < ny; ++a) {
+            const T* gy = gx + ty[a] * ld_g;
+            const float wya = __int_as_float(ty[TB_S + a]);
 #pragma unroll
-            for (int k = 0; k < TB_S; ++k)
-                if (k < ny) raw[k] = Vec<T>::load_raw(gx + yoff[k]);
+            for (int k0 = 0; k0 < TB_S; k0 += 3) {  // three loads in flight (six would cost the occupancy they are meant to replace)
+                if (k0 >= nz) break;
+                uint4 raw[3];
 #pragma unroll
-            for (int k = 0; k < TB_S; ++k)
-                if (k < ny) {
-                    float v[N];
-                    Vec<T>::unpack(raw[k], v);
-                    const float w = wxa * wy[k];
+                for (int k = 0; k < 3; ++k)
+                    if (k0 + k < nz) raw[k] = Vec<T>::load_raw(gy + zoff[k0 + k]);
 #pragma unroll
-                    for (int i = 0; i < N; ++i) s[i] = fmaf(w, v[i], s[i]);
-                }
+                for (int k = 0; k < 3; ++k)
+                    if (k0 + k < nz) {
+                        float v[N];
+                        Vec<T>::unpack(raw[k], v);
+                        const float w = wya * wz[k0 + k];
+#pragma unroll
+                        for (int i = 0; i < N; ++i) s[i] = fmaf(w, v[i], s[i]);
+                    }
+            }
         }
-        while (cur < lz.i0) flush();
-        const bool same = lz.i1 == lz.i0;
+        while (cur < lx.i0 && cur < i_hi) flush();
+        // targets (i0, l0) and (i1, l1): acc0 holds cur, acc1 holds cur + 1, anything else lies outside this segment
+        const float w0 = (lx.i0 == cur ? lx.l0 : 0.0f) + (lx.i1 == cur ? lx.l1 : 0.0f);
+        const float w1 = lx.i1 == cur + 1 ? lx.l1 : 0.0f;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            acc0[i] = fmaf(lz.l0, s[i], acc0[i]);
-            if (same) acc0[i] = fmaf(lz.l1, s[i], acc0[i]);
-            else acc1[i] = fmaf(lz.l1, s[i], acc1[i]);
+            acc0[i] = fmaf(w0, s[i], acc0[i]);
+            acc1[i] = fmaf(w1, s[i], acc1[i]);
         }
     }
-    while (cur < gi.Z) flush();
+    while (cur < i_hi) flush();
     if (!accumulate) {
-        Vec<T>::store(dcol, zero);
-        Vec<T>::store(dcol + (int64_t)(gi.Zp - 1) * ld_d, zero);
+        if (i_lo == 0) Vec<T>::store(dline, zero);
+        if (i_hi == gi.X) Vec<T>::store(dline + (int64_t)(gi.Xp - 1) * plane_d, zero);
     }
 }
 
@@ -1111,7 +1138,7 @@ int tdb_conv3d_wgrad(const void* in, int ld_in, const void* d_out, int ld_do, fl
     if (dtype == TDB_BF16 && (flags & TDB_WGRAD_ZERO_HALO) && Cin % 32 == 0 &&
         (Cout == 32 || (Cout <= 256 && Cout % 64 == 0) || Cout % 256 == 0) && ld_in % 8 == 0 && ld_do % 8 == 0 && aligned16(in) &&
         aligned16(d_out) && aligned16(dw))
-        return tdb_conv3d_wgrad_tc(in, ld_in, d_out, ld_do, dw, B, X, Y, Z, Cin, Cout, ntaps, TDB_WGRAD_SHARE_KZ, stream);
+        return tdb_conv3d_wgrad_tc(in, ld_in, d_out, ld_do, dw, B, X, Y, Z, Cin, Cout, ntaps, TDB_WGRAD_SHARE_KZ | TDB_WGRAD_KZ_ON_N, stream);
     const bool tensor_path = dtype == TDB_BF16 && (flags & TDB_WGRAD_ZERO_HALO) && Cin % 8 == 0 && Cout % 8 == 0 && ld_in % 8 == 0 &&
                              ld_do % 8 == 0 && aligned16(in) && aligned16(d_out);
     if (tensor_path) {
@@ -1143,19 +1170,27 @@ int tdb_trilinear_bwd(const void* g_out, int ld_g, int Xo, int Yo, int Zo, void*
     auto ok = [](float sc, int n_out) { return n_out == 1 || sc >= 0.2f; };
     TDB_REQUIRE(ok(sx, Xo) && ok(sy, Yo) && ok(sz, Zo), TDB_E_UNSUPPORTED, "tdb_trilinear_bwd: upsampling factor above 5 per axis");
     cudaStream_t s = (cudaStream_t)stream;
-    // column walker: <= 6 sources per axis (up-sampling factor <= 2.5) and a power-of-two number of channel chunks
+    // line walker: <= 6 sources per axis in y and z (up-sampling factor <= 2.5)
     auto few = [](float sc, int n_out) { return n_out == 1 || sc >= 0.4f; };
-    if (few(sx, Xo) && few(sy, Yo) && (chunks & (chunks - 1)) == 0) {
-        const int cols = kThreads / chunks;       // columns per block: a tx x ty tile of (x, y)
-        const int ty = cols < 8 ? cols : 8, tx = cols / ty;
-        const int tiles_y = (int)ceil_div(gi.Yp, ty), tiles_x = (int)ceil_div(gi.Xp, tx);
-        dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)B);
+    if (few(sy, Yo) && few(sz, Zo) && kThreads % chunks == 0 && gi.Yp * gi.Zp < (1 << 24) && B <= 65535) {
+        const int cols = kThreads / chunks;  // (y, z) lines per block
+        const int n_blocks = (int)ceil_div((int64_t)gi.Yp * gi.Zp, cols);
+        // x segments: enough threads to fill the machine (the lines alone are few on the coarse side of an up-sampling)
+        int64_t nseg = ceil_div((int64_t)148 * 2048, (int64_t)n_blocks * kThreads * B);
+        if (nseg > Xi / 4) nseg = Xi / 4;
+        if (nseg < 1) nseg = 1;
+        const int seg_len = (int)ceil_div(Xi, nseg);
+        nseg = ceil_div(Xi, seg_len);
+        dim3 grid((unsigned)n_blocks, (unsigned)B, (unsigned)nseg);
+        const size_t smem = (size_t)(gi.Yp + gi.Zp) * (2 * TB_S + 1) * sizeof(int);
+        TDB_REQUIRE(smem <= 40 * 1024, TDB_E_UNSUPPORTED, "tdb_trilinear_bwd: %d + %d lines exceed the source tables", gi.Yp, gi.Zp);
+        const FastDiv by_zp((uint32_t)gi.Zp);
         if (dtype == TDB_BF16)
-            trilinear_bwd_walk_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)g_out, ld_g, go, (bf16*)d_in, ld_d, gi, chunks, tx, ty,
-                                                                       tiles_y, sx, sy, sz, accumulate);
+            trilinear_bwd_walk_kernel<bf16><<<grid, kThreads, smem, s>>>((const bf16*)g_out, ld_g, go, (bf16*)d_in, ld_d, gi, chunks,
+                                                                          seg_len, sx, sy, sz, accumulate, by_zp);
         else
-            trilinear_bwd_walk_kernel<float><<<grid, kThreads, 0, s>>>((const float*)g_out, ld_g, go, (float*)d_in, ld_d, gi, chunks, tx,
-                                                                        ty, tiles_y, sx, sy, sz, accumulate);
+            trilinear_bwd_walk_kernel<float><<<grid, kThreads, smem, s>>>((const float*)g_out, ld_g, go, (float*)d_in, ld_d, gi, chunks,
+                                                                           seg_len, sx, sy, sz, accumulate, by_zp);
         TDB_CHECK_LAUNCH("tdb_trilinear_bwd");
         return 0;
     }

@@ -315,6 +315,9 @@ TDB_API int tdb_conv3d_wgrad(const void* in, int ld_in, const void* d_out, int l
  * 256*n}.  tdb_conv3d_wgrad dispatches here when it can.  mode: TDB_WGRAD_SHARE_KZ = load one row window per
  * (kx, ky) and use it for the three kz taps through row-shifted matrix descriptors (0 = one window per tap). */
 #define TDB_WGRAD_SHARE_KZ 1u
+/* Cout in {32, 64}, 27 taps: the three kz taps are stacked on the GEMM's N side (N = 3*Cout) - one activation window per
+ * (kx, ky, channel chunk) and one output-gradient window whose three swizzle atoms start one row apart. */
+#define TDB_WGRAD_KZ_ON_N 2u
 TDB_API int tdb_conv3d_wgrad_tc(const void* in, int ld_in, const void* d_out, int ld_do, float* dw, int B, int X, int Y,
                         int Z, int Cin, int Cout, int ntaps, unsigned mode, void* stream);
 

@@ -16,6 +16,11 @@ LAYERS = [  # X, Y, Z, Cin, Cout
     (25, 7, 7, 256, 512), (25, 7, 7, 512, 512), (25, 7, 7, 1024, 256),
     (13, 4, 4, 512, 512),
 ]
+if os.environ.get("WGRAD_LAYERS"):
+    LAYERS = [LAYERS[int(i)] for i in os.environ["WGRAD_LAYERS"].split(",")]
+MODES = [("tc0", 0), ("tc1", 1), ("tc3", 3)]
+if os.environ.get("WGRAD_MODES"):
+    MODES = [(f"tc{m}", int(m)) for m in os.environ["WGRAD_MODES"].split(",")]
 res = []
 for (X, Y, Z, Cin, Cout) in LAYERS:
     rows = B * (X + 2) * (Y + 2) * (Z + 2)
@@ -24,7 +29,7 @@ for (X, Y, Z, Cin, Cout) in LAYERS:
     dy[:, 1:-1, 1:-1, 1:-1] = torch.randn(B, X, Y, Z, Cout, device="cuda").bfloat16()
     dws = {}
     row = {"layer": f"{Cin}->{Cout} @{X}x{Y}x{Z}", "gflop": 2 * 27 * Cin * Cout * B * X * Y * Z / 1e9}
-    for name, mode in [("tc0", 0), ("tc1", 1)]:
+    for name, mode in MODES:
         dw = torch.zeros((27, Cin, Cout), dtype=torch.float32, device="cuda")
         def run():
             if mode is None:
@@ -38,7 +43,7 @@ for (X, Y, Z, Cin, Cout) in LAYERS:
             torch.cuda.synchronize()
             dws[name] = dw.clone()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            n = 3
+            n = 20
             e0.record()
             for _ in range(n):
                 run()

@@ -482,6 +482,9 @@ WGRAD_CASES = [
     (1, 6, 3, 3, 512, 512, 27),
     (2, 10, 6, 6, 64, 128, 1),
     (1, 34, 18, 18, 64, 64, 27),
+    (1, 40, 20, 50, 32, 32, 27),
+    (2, 20, 12, 12, 256, 64, 27),
+    (1, 30, 12, 30, 128, 32, 27),
 ]
 
 
@@ -510,9 +513,10 @@ def _dw_to_torch(dw, ntaps, Cin, Cout):
 
 
 @pytest.mark.parametrize("case", WGRAD_CASES)
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 3])
 def test_conv3d_wgrad_tensor_core(lib, case, mode):
-    """tcgen05 weight gradient (MN-major operands from the halo grids); mode 1 shares one row window per kz triple."""
+    """tcgen05 weight gradient (MN-major operands from the halo grids); mode 1 shares one row window per kz triple,
+    mode 3 additionally stacks the kz taps on the N side for Cout in {32, 64}."""
     B, X, Y, Z, Cin, Cout, ntaps = case
     ld_extra = 8 if Cin == 64 else 0  # channel-pitched input view (concat slices)
     x, dy, xin, dyh = _wgrad_inputs(case, ld_extra)
