@@ -41,6 +41,7 @@ struct WinParams {
     int all_rows;
     int proj;
     int ld_outp;
+    int add2;        // 1: a 1x1 convolution of a SECOND input (same channel count) accumulates into the same output tile
 };
 
 __device__ __forceinline__ bool interior_row(int64_t p, const WinParams& P, int& b) {
@@ -59,7 +60,8 @@ __device__ __forceinline__ bool interior_row(int64_t p, const WinParams& P, int&
 template <int COUT, int KC, int RES>
 __global__ void __launch_bounds__(THREADS, 1)
 conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                       const __grid_constant__ CUtensorMap map_p, const float* __restrict__ bias, bf16* __restrict__ out,
+                       const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_g,
+                       const float* __restrict__ bias, bf16* __restrict__ out,
                        double* __restrict__ gn_stats, const float* __restrict__ bias_p, bf16* __restrict__ out_p,
                        const WinParams P) {
     constexpr int NH = COUT / 2;             // weight rows each CTA contributes to the pair's MMA
@@ -88,7 +90,7 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const int n_b = resident ? 27 * chunks : 0;         // resident weight tiles (tap, channel chunk) of this CTA
     const uint32_t b_region = (uint32_t)n_b * bh_bytes;
     const uint32_t p_base_addr = smem_base + b_region;
-    const uint32_t p_region = (resident && P.proj) ? (uint32_t)chunks * bh_bytes : 0u;
+    const uint32_t p_region = (resident && (P.proj || P.add2)) ? (uint32_t)chunks * bh_bytes : 0u;
     const uint32_t stage_base = (smem_base + b_region + p_region + 1023u) & ~1023u;
     const uint32_t win_bytes = (uint32_t)P.win_rows * ROWB;
     // streamed weights: nine (ky, kz) tiles per stage, plus a slot for the 1x1 projection tile (filled when kx == 1)
@@ -99,6 +101,7 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_b);
+        if (P.add2) ptx::prefetch_tensormap(&map_g);
         for (int s = 0; s < P.stages; ++s) {
             ptx::mbar_init(full_bar + 8 * s, 2);   // leader's arm (expect_tx for both CTAs' bytes) + peer's arrival
             ptx::mbar_init(empty_bar + 8 * s, 1);
@@ -131,7 +134,7 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             if (rank == 0) ptx::mbar_arrive_expect_tx(b_full, 2u * b_region);
             else ptx::mbar_arrive_remote(b_full, 0);
         }
-        if (resident && P.proj && ptx::elect_one()) {
+        if (resident && (P.proj || P.add2) && ptx::elect_one()) {
             {
                 const uint32_t p_full_l = ptx::leader_addr(p_full);
                 for (int ch = 0; ch < chunks; ++ch)
@@ -171,6 +174,24 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
                 }
             }
+            if (P.add2) {
+                // second input: the tile's own 128 rows (no shift), one stage per channel chunk (+ its 1x1 weight tile)
+                for (int ch = 0; ch < chunks; ++ch) {
+                    ptx::mbar_wait(empty_bar + 8 * s, ph);
+                    if (ptx::elect_one()) {
+                        const uint32_t full_l = ptx::leader_addr(full_bar + 8 * s);
+                        ptx::tma_load_2d_2sm(stage_base + s * stage_bytes, &map_g, full_l, ch * KC, tile * BM);
+                        if (!resident)
+                            ptx::tma_load_3d_2sm(stage_base + s * stage_bytes + win_bytes, &map_p, full_l, ch * KC,
+                                                 nt * COUT + (int)rank * NH, 0);
+                        const uint32_t tx = (uint32_t)BM * ROWB + (resident ? 0u : bh_bytes);
+                        if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar + 8 * s, 2u * tx);
+                        else ptx::mbar_arrive_remote(full_bar + 8 * s, 0);
+                    }
+                    __syncwarp();
+                    if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
+                }
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: leader CTA only; every MMA is 256 rows (128 per CTA) x COUT x 16 =====
@@ -184,7 +205,7 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             constexpr uint32_t b_step = bh_bytes >> 4, row16 = ROWB >> 4;
             const uint32_t zrow16 = (uint32_t)P.Zp * row16;  // one y step = Zp rows
             if (resident) ptx::mbar_wait(b_full, 0);
-            if (resident && P.proj) ptx::mbar_wait(p_full, 0);
+            if (resident && (P.proj || P.add2)) ptx::mbar_wait(p_full, 0);
             ptx::tc_fence_after();
             uint32_t s = 0, ph = 0;
             int local = 0;
@@ -224,6 +245,22 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                                                       (uint32_t)((ch | k) != 0));
                             }
                             ptx::umma_commit_2sm_mc(empty_bar + 8 * s, (uint16_t)0x3);  // frees the slot in both CTAs
+                        }
+                        __syncwarp();
+                        if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
+                    }
+                }
+                if (P.add2) {
+                    for (int ch = 0; ch < chunks; ++ch) {
+                        ptx::mbar_wait(full_bar + 8 * s, ph);
+                        ptx::tc_fence_after();
+                        if (ptx::elect_one()) {
+                            const uint64_t a_st = a_base + (uint64_t)(s * st_step);
+                            const uint64_t p_t = resident ? p_base + (uint64_t)((uint32_t)ch * b_step) : a_st + (uint64_t)(win_bytes >> 4);
+#pragma unroll
+                            for (int k = 0; k < KC / 16; ++k)
+                                ptx::umma_f16_2sm(d_addr, a_st + (uint64_t)(2 * k), p_t + (uint64_t)(2 * k), idesc, 1u);
+                            ptx::umma_commit_2sm_mc(empty_bar + 8 * s, (uint16_t)0x3);
                         }
                         __syncwarp();
                         if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
@@ -365,7 +402,7 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 int g_num_sms_win = 0;
 
 template <int COUT, int KC, int RES>
-int launch_win(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap& map_p, const float* bias, bf16* out,
+int launch_win(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap& map_p, const CUtensorMap& map_g, const float* bias, bf16* out,
                double* gn_stats, const float* bias_p, bf16* out_p, const WinParams& P, size_t smem, cudaStream_t stream) {
     auto kern = conv3d_bf16_win_kernel<COUT, KC, RES>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -385,7 +422,7 @@ int launch_win(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtenso
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_p, bias, out, gn_stats, bias_p, out_p, P);
+    e = cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_p, map_g, bias, out, gn_stats, bias_p, out_p, P);
     TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_conv3d_bf16_win: launch: %s", cudaGetErrorString(e));
     TDB_CHECK_LAUNCH("tdb_conv3d_bf16_win");
     return 0;
@@ -393,9 +430,11 @@ int launch_win(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtenso
 
 }  // namespace
 
-extern "C" int tdb_conv3d_bf16_win(const void* in, int ld_in, const void* w, const float* bias, void* out, int ld_out, int B, int X,
-                                   int Y, int Z, int Cin, int Cout, double* gn_stats, int G, unsigned flags, const void* w_proj,
-                                   const float* bias_proj, void* out_proj, int ld_outp, void* stream) {
+namespace {
+// in2 / ld_in2 / w2: optional second input (Cin channels) whose 1x1 convolution with w2 [Cout][Cin] is added to the output
+int win_impl(const void* in, int ld_in, const void* w, const float* bias, void* out, int ld_out, int B, int X, int Y, int Z, int Cin,
+             int Cout, double* gn_stats, int G, unsigned flags, const void* w_proj, const float* bias_proj, void* out_proj,
+             int ld_outp, const void* in2, int ld_in2, const void* w2, void* stream) {
     TDB_REQUIRE(in && w && out, TDB_E_BADARG, "tdb_conv3d_bf16_win: null pointer");
     TDB_REQUIRE(Cin % 32 == 0 && (Cout == 32 || Cout == 64 || (Cout % 128 == 0 && Cout <= 512)) && ld_in % 8 == 0 && ld_out % 8 == 0,
                 TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_win: need Cin %% 32 == 0 and Cout in {32,64,128k<=512} (Cin=%d Cout=%d)", Cin, Cout);
@@ -424,6 +463,9 @@ extern "C" int tdb_conv3d_bf16_win(const void* in, int ld_in, const void* w, con
     TDB_REQUIRE(P.win_rows <= 256, TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_win: Z + 2 = %d is too wide for one TMA box", g.Zp);
     P.proj = w_proj != nullptr ? 1 : 0;
     P.ld_outp = ld_outp;
+    P.add2 = in2 != nullptr ? 1 : 0;
+    TDB_REQUIRE(!P.add2 || (!P.proj && w2 && ld_in2 % 8 == 0 && ((uintptr_t)in2 & 15) == 0 && ((uintptr_t)w2 & 15) == 0), TDB_E_UNSUPPORTED,
+                "tdb_conv3d_bf16_win: the added 1x1 convolution needs aligned buffers and excludes the fused projection");
     TDB_REQUIRE(!P.proj || (out_proj && ld_outp % 8 == 0 && ((uintptr_t)w_proj & 15) == 0 && ((uintptr_t)out_proj & 15) == 0 &&
                             !(flags & TDB_CONV_ALL_ROWS)),
                 TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_win: the fused projection needs aligned buffers and no ALL_ROWS");
@@ -433,7 +475,7 @@ extern "C" int tdb_conv3d_bf16_win(const void* in, int ld_in, const void* w, con
     const int bh_bytes = (tile_n / 2) * KC * 2;
     const int win_bytes = P.win_rows * KC * 2;
     const int budget = 221 * 1024;
-    const int resident_bytes = (27 + (P.proj ? 1 : 0)) * P.chunks * bh_bytes;
+    const int resident_bytes = (27 + ((P.proj || P.add2) ? 1 : 0)) * P.chunks * bh_bytes;
     // all weights resident when they leave room for two windows; otherwise (Cin % 64 == 0 only) the nine weight
     // tiles of a (kx, channel chunk) stream with each window and Cout is walked in N tiles of 128
     const bool res = P.n_tiles == 1 && resident_bytes + 2048 + 2 * win_bytes <= budget;
@@ -455,7 +497,7 @@ extern "C" int tdb_conv3d_bf16_win(const void* in, int ld_in, const void* w, con
     P.all_rows = (flags & TDB_CONV_ALL_ROWS) ? 1 : 0;
     TDB_REQUIRE(!(P.all_rows && gn_stats), TDB_E_BADARG, "tdb_conv3d_bf16_win: fused moments are not available with ALL_ROWS");
 
-    CUtensorMap map_a, map_b, map_p;
+    CUtensorMap map_a, map_b, map_p, map_g;
     TDB_REQUIRE(encode_fn() != nullptr, TDB_E_NODEVICE, "tdb_conv3d_bf16_win: cuTensorMapEncodeTiled unavailable (no driver)");
     TDB_REQUIRE(make_map_2d_bf16(&map_a, in, (uint64_t)Cin, (uint64_t)g.rows, (uint64_t)ld_in, (uint32_t)KC, (uint32_t)P.win_rows),
                 TDB_E_BADARG, "tdb_conv3d_bf16_win: tensor map (activations) rejected");
@@ -467,18 +509,22 @@ extern "C" int tdb_conv3d_bf16_win(const void* in, int ld_in, const void* w, con
         TDB_REQUIRE(make_map_bf16(&map_b, w, 3, dims, strides, box), TDB_E_BADARG, "tdb_conv3d_bf16_win: tensor map (weights) rejected");
     }
     {
-        const void* wp = P.proj ? w_proj : w;
+        const void* wp = P.proj ? w_proj : (P.add2 ? w2 : w);
         const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 1};
-        const uint64_t strides[2] = {(uint64_t)(P.proj ? Cin : 27 * Cin), (uint64_t)Cin * Cout};
+        const uint64_t strides[2] = {(uint64_t)((P.proj || P.add2) ? Cin : 27 * Cin), (uint64_t)Cin * Cout};
         const uint32_t box[3] = {(uint32_t)KC, (uint32_t)(tile_n / 2), 1};
         TDB_REQUIRE(make_map_bf16(&map_p, wp, 3, dims, strides, box), TDB_E_BADARG, "tdb_conv3d_bf16_win: tensor map (projection) rejected");
     }
+    // second input: the 128 rows of a tile
+    TDB_REQUIRE(make_map_2d_bf16(&map_g, P.add2 ? in2 : in, (uint64_t)Cin, (uint64_t)g.rows, (uint64_t)(P.add2 ? ld_in2 : ld_in), (uint32_t)KC,
+                                 (uint32_t)BM),
+                TDB_E_BADARG, "tdb_conv3d_bf16_win: tensor map (second input) rejected");
     const size_t smem = (size_t)fixed_bytes + 1024 + (size_t)stages * stage_bytes + 1024;
     cudaStream_t s = (cudaStream_t)stream;
     bf16* o = (bf16*)out;
     bf16* op = (bf16*)out_proj;
 #define TDB_WIN_CASE(CO, K, R) \
-    if (tile_n == CO && KC == K && (int)res == R) return launch_win<CO, K, R>(map_a, map_b, map_p, bias, o, gn_stats, bias_proj, op, P, smem, s)
+    if (tile_n == CO && KC == K && (int)res == R) return launch_win<CO, K, R>(map_a, map_b, map_p, map_g, bias, o, gn_stats, bias_proj, op, P, smem, s)
     TDB_WIN_CASE(32, 64, 1);
     TDB_WIN_CASE(64, 64, 1);
     TDB_WIN_CASE(128, 64, 1);
@@ -489,4 +535,20 @@ extern "C" int tdb_conv3d_bf16_win(const void* in, int ld_in, const void* w, con
 #undef TDB_WIN_CASE
     tdb::set_error("tdb_conv3d_bf16_win: no kernel for Cout=%d KC=%d", Cout, KC);
     return TDB_E_UNSUPPORTED;
+}
+}  // namespace
+
+extern "C" int tdb_conv3d_bf16_win(const void* in, int ld_in, const void* w, const float* bias, void* out, int ld_out, int B, int X,
+                                   int Y, int Z, int Cin, int Cout, double* gn_stats, int G, unsigned flags, const void* w_proj,
+                                   const float* bias_proj, void* out_proj, int ld_outp, void* stream) {
+    return win_impl(in, ld_in, w, bias, out, ld_out, B, X, Y, Z, Cin, Cout, gn_stats, G, flags, w_proj, bias_proj, out_proj, ld_outp,
+                    nullptr, 0, nullptr, stream);
+}
+
+extern "C" int tdb_conv3d_bf16_win_add1x1(const void* in, int ld_in, const void* w, const float* bias, void* out, int ld_out, int B,
+                                          int X, int Y, int Z, int Cin, int Cout, unsigned flags, const void* in2, int ld_in2,
+                                          const void* w2, void* stream) {
+    TDB_REQUIRE(in2 && w2, TDB_E_BADARG, "tdb_conv3d_bf16_win_add1x1: null pointer");
+    return win_impl(in, ld_in, w, bias, out, ld_out, B, X, Y, Z, Cin, Cout, nullptr, 0, flags, nullptr, nullptr, nullptr, 0, in2, ld_in2,
+                    w2, stream);
 }

@@ -31,6 +31,7 @@ SIGNATURES = {
     "tdb_conv3d_bf16_fold": [_p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _u, _p],
     "tdb_conv3d_bf16_fold2": [_p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _u, _p, _p, _p, _i, _p],
     "tdb_conv3d_bf16_win": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _u, _p, _p, _p, _i, _p],
+    "tdb_conv3d_bf16_win_add1x1": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _u, _p, _i, _p, _p],
     "tdb_conv3d_bf16_winz": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _u, _p, _p, _p, _i, _p],
     "tdb_conv3d_bf16_winp": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _u, _p],
     "tdb_gn_stats": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],

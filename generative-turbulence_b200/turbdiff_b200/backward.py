@@ -140,7 +140,11 @@ class BackwardProgram:
         grads[f"{pre}.block1.conv.weight"] = self._wgrad(p, x, d_raw, blk.block1.conv, 27, zero_halo=True)
         grads[f"{pre}.block1.conv.bias"] = bias1
         g_x = self._gbuf(p, x, ("g", name))
-        eng._conv(p, d_raw, self._dgrad_weights(blk.block1.conv, f"{name}.conv1", lvl), None, g_x, 27, all_rows=True)
+        # residual projection: its input gradient res_conv^T(g_out) rides on conv1's input-gradient kernel when that is the
+        # row-window pair kernel (g_out is a folded gradient - zero halo rows - so the sum may be folded afterwards)
+        fuse_res = bp.has_proj and eng.can_add1x1(C, x.C, lvl)
+        eng._conv(p, d_raw, self._dgrad_weights(blk.block1.conv, f"{name}.conv1", lvl), None, g_x, 27, all_rows=True,
+                  add1x1=(g_out, self._dgrad_weights(blk.conv, f"{name}.proj", lvl)) if fuse_res else None)
         self._fold(p, g_x)
 
         # residual branch
@@ -148,9 +152,10 @@ class BackwardProgram:
             # g_out is a folded gradient: tdb_halo_fold left its halo rows zero
             grads[f"{pre}.conv.weight"] = self._wgrad(p, x, g_out, blk.conv, 1, zero_halo=True)
             grads[f"{pre}.conv.bias"] = g_out_colsum  # from block2's reduction over the same g_out (no extra pass)
-            g_res = self._tmp(p, lvl, x.C, "g_res")
-            eng._conv(p, g_out, self._dgrad_weights(blk.conv, f"{name}.proj", lvl), None, g_res, 1, all_rows=True)
-            self._add_interior(p, g_x, g_res)
+            if not fuse_res:
+                g_res = self._tmp(p, lvl, x.C, "g_res")
+                eng._conv(p, g_out, self._dgrad_weights(blk.conv, f"{name}.proj", lvl), None, g_res, 1, all_rows=True)
+                self._add_interior(p, g_x, g_res)
         else:
             self._add_interior(p, g_x, g_out)
         return g_x

@@ -279,14 +279,24 @@ class DenoiserEngine:
         return C if g is None else g
 
     # ------------------------------------------------------------------ kernels
-    def _conv(self, p, x: View, w, bias, out: View, ntaps, stats=None, G=0, all_rows=False, proj=None):
+    def can_add1x1(self, cin, cout, level) -> bool:
+        """out = conv3x3x3(x) + conv1x1(x2) in one launch: the row-window pair kernel without kz folding."""
+        return self.precision == "bf16" and self.fold_kind(27, cin, cout, level) == "win"
+
+    def _conv(self, p, x: View, w, bias, out: View, ntaps, stats=None, G=0, all_rows=False, proj=None, add1x1=None):
         """3x3x3 / 1x1x1 convolution over halo grids.  all_rows: also store the halo rows of the output
-        (input-gradient convolutions; the fp32 kernel always stores every row)."""
+        (input-gradient convolutions; the fp32 kernel always stores every row).  add1x1 = (x2 view with x.C channels,
+        w2 [Cout][Cin] bf16): the 1x1 convolution of a second input is accumulated in the same tile (can_add1x1())."""
         B = p["B"]
         X, Y, Z = p["sizes"][x.level]
         s = _lib.stream_ptr()
         flags = _lib.CONV_ALL_ROWS if all_rows else 0
-        if self.precision == "fp32":
+        if add1x1 is not None:
+            x2, w2 = add1x1
+            assert self.can_add1x1(x.C, out.C, x.level) and x2.C == x.C and stats is None and proj is None
+            call("tdb_conv3d_bf16_win_add1x1", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, flags,
+                 x2.ptr, x2.ld, w2.data_ptr(), s)
+        elif self.precision == "fp32":
             call("tdb_conv3d_f32", x.ptr, x.ld, w.data_ptr(), ptr(bias), out.ptr, out.ld, B, X, Y, Z, x.C, out.C, ntaps, s)
         elif self.fold_kind(ntaps, x.C, out.C, x.level) in ("win", "winz"):
             pw, pb, pv = proj if proj is not None else (None, None, None)

@@ -160,6 +160,14 @@ TDB_API int tdb_conv3d_bf16_win(const void* in, int ld_in, const void* w, const 
                         int X, int Y, int Z, int Cin, int Cout, double* gn_stats, int G, unsigned flags,
                         const void* w_proj, const float* bias_proj, void* out_proj, int ld_outp, void* stream);
 
+/* tdb_conv3d_bf16_win plus a 1x1 convolution of a second input accumulated in the same output tile:
+ *   out = conv3x3x3(in, w) + bias + conv1x1(in2, w2),   in2 [rows][ld_in2] with Cin channels, w2 [Cout][Cin] bf16.
+ * The training backward of a ResnetBlock with a residual projection (reference ddpm.py:190-197 through autograd):
+ * grad_x = dgrad(block1.conv)(d_raw1) + res_conv^T(grad_out) - one kernel instead of two convolutions and an add pass. */
+TDB_API int tdb_conv3d_bf16_win_add1x1(const void* in, int ld_in, const void* w, const float* bias, void* out, int ld_out, int B,
+                               int X, int Y, int Z, int Cin, int Cout, unsigned flags, const void* in2, int ld_in2,
+                               const void* w2, void* stream);
+
 /* Row-window CTA-pair convolution with kz folded into N (N = 3*Cout; same reference call sites, ddpm.py:164,188,197): one shared-memory window per kx viewed at the
  * three ky offsets, the +-1 row shift of kz applied in the epilogue (tiles of 128 rows advancing by 126).  For the
  * narrow layers: Cout in {32, 64}, Cin % 32 == 0, folded weights (layout of tdb_conv3d_bf16_fold2: [3*Cout][9*Cin])

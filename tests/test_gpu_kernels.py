@@ -635,6 +635,36 @@ def test_conv3d_bf16_row_window(lib, case, entry, variant):
         assert rel_l2(out.permute(0, 4, 1, 2, 3).float(), full) < 4e-3
 
 
+ADD1X1_CASES = [c for c in WIN_CASES if c[5] == 128 or c[5] % 128 == 0] + [(2, 20, 10, 10, 32, 128, False), (1, 25, 13, 13, 64, 256, False)]
+
+
+@pytest.mark.parametrize("case", ADD1X1_CASES)
+def test_conv3d_bf16_row_window_add1x1(lib, case):
+    """tdb_conv3d_bf16_win_add1x1: out = conv3x3x3(in) + conv1x1(in2) in one launch, every row stored - the input gradient
+    of a ResnetBlock's first convolution plus that of its residual projection (autograd of reference ddpm.py:190-197)."""
+    B, X, Y, Z, Cin, Cout, _ = case
+    x = gen(B, Cin, X, Y, Z, seed=1).bfloat16().float()
+    x2 = gen(B, Cin, X, Y, Z, seed=11).bfloat16().float()
+    w = gen(Cout, Cin, 3, 3, 3, seed=2, scale=1 / math.sqrt(Cin * 27)).bfloat16().float()
+    w2 = gen(Cout, Cin, 1, 1, 1, seed=12, scale=1 / math.sqrt(Cin)).bfloat16().float()
+    wk = w.permute(0, 2, 3, 4, 1).reshape(Cout, 27 * Cin).contiguous().bfloat16()
+    w2k = w2.reshape(Cout, Cin).contiguous().bfloat16()
+
+    def zero_halo(v, ld, c0):
+        g = torch.zeros((B, X + 2, Y + 2, Z + 2, ld), device="cuda", dtype=torch.bfloat16)
+        g[:, 1:-1, 1:-1, 1:-1, c0 : c0 + Cin] = v.permute(0, 2, 3, 4, 1).bfloat16()
+        return g
+
+    xz, x2z = zero_halo(x, Cin + 8, 8), zero_halo(x2, 2 * Cin, Cin)
+    out = torch.full((B, X + 2, Y + 2, Z + 2, Cout), 3.0, device="cuda", dtype=torch.bfloat16)
+    lib.call("tdb_conv3d_bf16_win_add1x1", xz.data_ptr() + 16, Cin + 8, wk.data_ptr(), None, out.data_ptr(), Cout, B, X, Y, Z, Cin, Cout,
+             lib.CONV_ALL_ROWS, x2z.data_ptr() + 2 * Cin, 2 * Cin, w2k.data_ptr(), lib.stream_ptr())
+    torch.cuda.synchronize()
+    full = F.conv3d(F.pad(F.pad(x.double().cpu(), (1,) * 6), (1,) * 6), w.double().cpu())
+    full = full + F.pad(F.conv3d(x2.double().cpu(), w2.double().cpu()), (1,) * 6)
+    assert rel_l2(out.permute(0, 4, 1, 2, 3).float(), full) < 4e-3
+
+
 # --------------------------------------------------------------------------- fused scatter/normalise, gather/de-normalise
 @pytest.mark.parametrize("B", [1, 3])
 def test_scatter_normalize_and_gather_denormalize(lib, B):
