@@ -930,11 +930,22 @@ attention_bwd_kernel(const T* __restrict__ qkv, int ld_qkv, const T* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 cl_nc_outer_kernel(const T* __restrict__ G, int ld, const float* __restrict__ Q, int64_t q_bstride, float* __restrict__ out,
-                   Grid3 gr, int C, int F, int vox_per_block) {
+                   float* __restrict__ colsum, Grid3 gr, int C, int F, int vox_per_block) {
     const int b = blockIdx.y;
     const int64_t nvox = (int64_t)gr.X * gr.Y * gr.Z;
     const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
     const int64_t v_end = min(nvox, v_begin + vox_per_block);
+    if (colsum)
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float acc = 0.0f;
+            for (int64_t v = v_begin; v < v_end; ++v) {
+                const int z = (int)(v % gr.Z);
+                const int y = (int)((v / gr.Z) % gr.Y);
+                const int x = (int)(v / ((int64_t)gr.Z * gr.Y));
+                acc += (float)G[gr.row(b, x, y, z) * ld + c];
+            }
+            atomicAdd(&colsum[c], acc);
+        }
     for (int pair = threadIdx.x; pair < C * F; pair += blockDim.x) {
         const int c = pair % C, f = pair / C;
         const float* q = Q + (int64_t)b * q_bstride + (int64_t)f * nvox;
@@ -950,14 +961,16 @@ cl_nc_outer_kernel(const T* __restrict__ G, int ld, const float* __restrict__ Q,
 }
 
 // Vector form (C/N a power of two <= 32, pitch and base 16-byte aligned): thread = (voxel lane, 16-byte channel
-// chunk) with FMAX x N accumulators in registers; warp shuffles over the voxel lanes, shared-memory atomics over
-// the warps, then one global atomicAdd per (c, f) and block.
+// chunk) with FMAX x N accumulators in registers (+ N for the optional per-channel sum of G); U voxels per trip with
+// all loads issued up front; warp shuffles over the voxel lanes, shared-memory atomics over the warps, then one global
+// atomicAdd per (c, f) and block.
 template <typename T, int FMAX>
 __global__ void __launch_bounds__(kThreads)
 cl_nc_outer_vec_kernel(const T* __restrict__ G, int ld, const float* __restrict__ Q, int64_t q_bstride, float* __restrict__ out,
-                       Grid3 gr, int C, int F, int chunks, int vox_per_block, FastDiv by_z, FastDiv by_y) {
+                       float* __restrict__ colsum, Grid3 gr, int C, int F, int chunks, int vox_per_block, FastDiv by_z, FastDiv by_y) {
     constexpr int N = Vec<T>::N;
-    __shared__ float sred[32 * N * FMAX];
+    constexpr int U = 4;
+    __shared__ float sred[32 * N * (FMAX + 1)];
     const int b = blockIdx.y;
     const uint32_t nvox = (uint32_t)(gr.X * gr.Y * gr.Z);
     const uint32_t v_begin = blockIdx.x * (uint32_t)vox_per_block;
@@ -966,41 +979,54 @@ cl_nc_outer_vec_kernel(const T* __restrict__ G, int ld, const float* __restrict_
     const T* gb = G + (int64_t)b * gr.vox_p * ld + ch * N;
     for (int f0 = 0; f0 < F; f0 += FMAX) {
         const int nf = min(FMAX, F - f0);
-        for (int i = threadIdx.x; i < C * FMAX; i += kThreads) sred[i] = 0.0f;
+        const bool want_sum = colsum != nullptr && f0 == 0;
+        for (int i = threadIdx.x; i < C * (FMAX + 1); i += kThreads) sred[i] = 0.0f;
         __syncthreads();
-        float acc[FMAX][N];
+        float acc[FMAX + 1][N];
 #pragma unroll
-        for (int f = 0; f < FMAX; ++f)
+        for (int f = 0; f <= FMAX; ++f)
 #pragma unroll
             for (int i = 0; i < N; ++i) acc[f][i] = 0.0f;
         const float* qb = Q + (int64_t)b * q_bstride + (int64_t)f0 * nvox;
-        for (uint32_t v = v_begin + lane_vox; v < v_end; v += vox_lanes) {
-            uint32_t q, z, x, y;
-            by_z.divmod(v, q, z);
-            by_y.divmod(q, x, y);
-            float g[N];
-            Vec<T>::load(gb + (((int64_t)(x + 1) * gr.Yp + (y + 1)) * gr.Zp + (z + 1)) * ld, g);
+        for (uint32_t v0 = v_begin + lane_vox; v0 < v_end; v0 += U * vox_lanes) {
+            uint4 graw[U];
+            float qv[U][FMAX];
 #pragma unroll
-            for (int f = 0; f < FMAX; ++f) {
-                if (f < nf) {
-                    const float qv = __ldg(qb + (int64_t)f * nvox + v);
+            for (int u = 0; u < U; ++u) {
+                const uint32_t v = min(v0 + u * vox_lanes, v_end - 1);
+                uint32_t q, z, x, y;
+                by_z.divmod(v, q, z);
+                by_y.divmod(q, x, y);
+                graw[u] = Vec<T>::load_raw(gb + (((int64_t)(x + 1) * gr.Yp + (y + 1)) * gr.Zp + (z + 1)) * ld);
 #pragma unroll
-                    for (int i = 0; i < N; ++i) acc[f][i] = fmaf(g[i], qv, acc[f][i]);
-                }
+                for (int f = 0; f < FMAX; ++f) qv[u][f] = f < nf ? __ldg(qb + (int64_t)f * nvox + v) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (v0 + u * vox_lanes >= v_end) break;
+                float g[N];
+                Vec<T>::unpack(graw[u], g);
+#pragma unroll
+                for (int f = 0; f < FMAX; ++f)
+#pragma unroll
+                    for (int i = 0; i < N; ++i) acc[f][i] = fmaf(g[i], qv[u][f], acc[f][i]);
+#pragma unroll
+                for (int i = 0; i < N; ++i) acc[FMAX][i] += g[i];
             }
         }
 #pragma unroll
-        for (int f = 0; f < FMAX; ++f)
+        for (int f = 0; f <= FMAX; ++f)
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 float v = acc[f][i];
                 for (int o = 16; o >= chunks; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if ((threadIdx.x & 31) < chunks && f < nf) atomicAdd(&sred[(ch * N + i) * FMAX + f], v);
+                if ((threadIdx.x & 31) < chunks && (f < nf || (f == FMAX && want_sum))) atomicAdd(&sred[(ch * N + i) * (FMAX + 1) + f], v);
             }
         __syncthreads();
-        for (int i = threadIdx.x; i < C * FMAX; i += kThreads) {
-            const int c = i / FMAX, f = i % FMAX;
+        for (int i = threadIdx.x; i < C * (FMAX + 1); i += kThreads) {
+            const int c = i / (FMAX + 1), f = i % (FMAX + 1);
             if (f < nf) atomicAdd(&out[(int64_t)c * F + f0 + f], sred[i]);
+            else if (f == FMAX && want_sum) atomicAdd(&colsum[c], sred[i]);
         }
         __syncthreads();
     }
@@ -1051,8 +1077,10 @@ int tdb_pointwise_bwd_reduce(const void* g_out, int ld_g, const void* raw, int l
     if (G < 1) G = 1;
     Grid3 gr(B, X, Y, Z);
     const int chunks = C / n;
-    const int64_t trip = (int64_t)(kThreads / chunks) * 4;  // voxels one block handles per trip
-    int64_t blocks = ceil_div((int64_t)X * Y * Z, trip);
+    // blocks per sample: every block ends with 4*C double atomics into red[] (~6.5 G/s device-wide, measured), so a block
+    // streams at least ~512 KB of its two inputs; the coarse levels then run on a few dozen blocks instead of 148 per sample
+    const int64_t bytes_per_sample = (int64_t)X * Y * Z * C * (dtype == TDB_BF16 ? 2 : 4) * 2;
+    int64_t blocks = ceil_div(bytes_per_sample, 512 * 1024);
     const int64_t cap = (148 * 4) / (B < 1 ? 1 : B) < 1 ? 1 : (148 * 4) / (B < 1 ? 1 : B);
     if (blocks > cap) blocks = cap;
     dim3 grid((unsigned)blocks, (unsigned)B);
@@ -1231,8 +1259,8 @@ int tdb_attention_bwd(const void* qkv, int ld_qkv, const void* d_out, int ld_do,
     return 0;
 }
 
-int tdb_cl_nc_outer(const void* G, int ld, const float* Q, int64_t q_bstride, float* out, int B, int X, int Y, int Z, int C, int F,
-                    int dtype, void* stream) {
+int tdb_cl_nc_outer(const void* G, int ld, const float* Q, int64_t q_bstride, float* out, float* colsum, int B, int X, int Y, int Z,
+                    int C, int F, int dtype, void* stream) {
     TDB_REQUIRE(G && Q && out, TDB_E_BADARG, "tdb_cl_nc_outer: null pointer");
     Grid3 gr(B, X, Y, Z);
     cudaStream_t s = (cudaStream_t)stream;
@@ -1248,20 +1276,20 @@ int tdb_cl_nc_outer(const void* G, int ld, const float* Q, int64_t q_bstride, fl
         dim3 grid((unsigned)ceil_div(nvox, vpb), (unsigned)B);
         const FastDiv by_z((uint32_t)Z), by_y((uint32_t)Y);
         if (dtype == TDB_BF16)
-            cl_nc_outer_vec_kernel<bf16, 4><<<grid, kThreads, 0, s>>>((const bf16*)G, ld, Q, q_bstride, out, gr, C, F, chunks, (int)vpb, by_z,
-                                                                     by_y);
+            cl_nc_outer_vec_kernel<bf16, 4><<<grid, kThreads, 0, s>>>((const bf16*)G, ld, Q, q_bstride, out, colsum, gr, C, F, chunks, (int)vpb,
+                                                                     by_z, by_y);
         else
-            cl_nc_outer_vec_kernel<float, 4><<<grid, kThreads, 0, s>>>((const float*)G, ld, Q, q_bstride, out, gr, C, F, chunks, (int)vpb,
-                                                                      by_z, by_y);
+            cl_nc_outer_vec_kernel<float, 4><<<grid, kThreads, 0, s>>>((const float*)G, ld, Q, q_bstride, out, colsum, gr, C, F, chunks,
+                                                                      (int)vpb, by_z, by_y);
         TDB_CHECK_LAUNCH("tdb_cl_nc_outer");
         return 0;
     }
     const int vox_per_block = 512;
     dim3 grid((unsigned)ceil_div((int64_t)X * Y * Z, vox_per_block), (unsigned)B);
     if (dtype == TDB_BF16)
-        cl_nc_outer_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)G, ld, Q, q_bstride, out, gr, C, F, vox_per_block);
+        cl_nc_outer_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16*)G, ld, Q, q_bstride, out, colsum, gr, C, F, vox_per_block);
     else
-        cl_nc_outer_kernel<float><<<grid, kThreads, 0, s>>>((const float*)G, ld, Q, q_bstride, out, gr, C, F, vox_per_block);
+        cl_nc_outer_kernel<float><<<grid, kThreads, 0, s>>>((const float*)G, ld, Q, q_bstride, out, colsum, gr, C, F, vox_per_block);
     TDB_CHECK_LAUNCH("tdb_cl_nc_outer");
     return 0;
 }

@@ -53,7 +53,7 @@ SIGNATURES = {
     "tdb_attention_bwd": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_grad_sqnorm": [_p, _p, _p, _p, _i, _i, _p, _p],
     "tdb_radam_step": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _f, _f, _d, _d, _f, _f, _i, _p],
-    "tdb_cl_nc_outer": [_p, _i, _p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "tdb_cl_nc_outer": [_p, _i, _p, _l, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_scatter_normalize": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _l, _l, _p],
     "tdb_gather_denormalize": [_p, _p, _p, _p, _p, _i, _i, _l, _l, _p],
     "tdb_where_cells": [_p, _p, _p, _p, _l, _l, _p],

@@ -222,7 +222,7 @@ class BackwardProgram:
         dec_out = p["dec_out"]
         Fo = m.out_features  # 2F with learned variances
         dw = torch.zeros((m.dim, Fo), dtype=torch.float32, device=dev)
-        call("tdb_cl_nc_outer", dec_out.ptr, dec_out.ld, g_eps.data_ptr(), Fo * X * Y * Z, dw.data_ptr(), B, X, Y, Z, m.dim, Fo, dt, s())
+        call("tdb_cl_nc_outer", dec_out.ptr, dec_out.ld, g_eps.data_ptr(), Fo * X * Y * Z, dw.data_ptr(), None, B, X, Y, Z, m.dim, Fo, dt, s())
         grads["decode.1.weight"] = dw.t().reshape(dec.weight.shape).contiguous()
         grads["decode.1.bias"] = g_eps.sum(dim=(0, 2, 3, 4))
         g_dec = self._gbuf(p, dec_out, ("g", "dec_out"))
@@ -261,17 +261,19 @@ class BackwardProgram:
         dim, Fc = m.dim, m.c_local_features
         nvox = X * Y * Z
         gx = g.slice(0, dim)
+        bx = torch.zeros(dim, dtype=torch.float32, device=dev)
         dwx = torch.zeros((dim, F), dtype=torch.float32, device=dev)
-        call("tdb_cl_nc_outer", gx.ptr, gx.ld, x_in.data_ptr(), F * nvox, dwx.data_ptr(), B, X, Y, Z, dim, F, dt, s())
+        call("tdb_cl_nc_outer", gx.ptr, gx.ld, x_in.data_ptr(), F * nvox, dwx.data_ptr(), bx.data_ptr(), B, X, Y, Z, dim, F, dt, s())
         grads["encode_x.weight"] = dwx.reshape(m.encode_x.weight.shape)
-        grads["encode_x.bias"] = self._colsum(p, gx)
+        grads["encode_x.bias"] = bx
         g_c_local = None
         if Fc > 0:
             gc = g.slice(dim, dim)
             dwc = torch.zeros((dim, Fc), dtype=torch.float32, device=dev)
-            call("tdb_cl_nc_outer", gc.ptr, gc.ld, c_local.data_ptr(), 0, dwc.data_ptr(), B, X, Y, Z, dim, Fc, dt, s())
+            bc = torch.zeros(dim, dtype=torch.float32, device=dev)
+            call("tdb_cl_nc_outer", gc.ptr, gc.ld, c_local.data_ptr(), 0, dwc.data_ptr(), bc.data_ptr(), B, X, Y, Z, dim, Fc, dt, s())
             grads["encode_c_local.weight"] = dwc.reshape(m.encode_c_local.weight.shape)
-            grads["encode_c_local.bias"] = self._colsum(p, gc)
+            grads["encode_c_local.bias"] = bc
             wct = m.encode_c_local.weight.detach().reshape(dim, Fc).t().contiguous()  # (Fc, dim)
             zb = torch.zeros(Fc, dtype=torch.float32, device=dev)
             per_sample = torch.empty((B, Fc, X, Y, Z), dtype=torch.float32, device=dev)

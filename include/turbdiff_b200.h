@@ -342,9 +342,11 @@ TDB_API int tdb_attention_bwd(const void* qkv, int ld_qkv, const void* d_out, in
                       int X, int Y, int Z, int heads, int dh, int dtype, void* stream);
 
 /* out[c][f] += sum_{b, interior v} G[b,v][c] * Q[b*q_bstride + f*nvox + v]: weight gradients of the 1x1x1
- * encoders / decoder between a halo grid G and NCDHW planes Q (q_bstride = 0 for an unbatched Q). */
-TDB_API int tdb_cl_nc_outer(const void* G, int ld, const float* Q, int64_t q_bstride, float* out, int B, int X, int Y,
-                    int Z, int C, int F, int dtype, void* stream);
+ * encoders / decoder (reference ddpm.py:433,436,459 through autograd) between a halo grid G and NCDHW planes Q
+ * (q_bstride = 0 for an unbatched Q).  colsum (optional, fp32 [C], accumulated): colsum[c] += sum_{b, interior v} G[b,v][c],
+ * the bias gradient of the same 1x1x1 convolution, from the same pass. */
+TDB_API int tdb_cl_nc_outer(const void* G, int ld, const float* Q, int64_t q_bstride, float* out, float* colsum, int B, int X,
+                    int Y, int Z, int C, int F, int dtype, void* stream);
 
 /* ---- cell indexing (bit-exact) -------------------------------------------------------------------- */
 

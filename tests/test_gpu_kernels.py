@@ -545,6 +545,33 @@ def test_conv3d_wgrad_dispatch(lib, case, prec, zero_halo):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("C,F_,size", [(32, 4, (21, 9, 7)), (16, 8, (6, 5, 4)), (32, 3, (40, 12, 11)), (24, 4, (5, 4, 3))])
+def test_cl_nc_outer_and_colsum(lib, prec, C, F_, size):
+    """tdb_cl_nc_outer: weight (and bias) gradient of a 1x1x1 convolution between a halo grid and NCDHW planes
+    (reference encode_x / encode_c_local / decode[1], ddpm.py:433,436,459, through autograd)."""
+    code, td = _dt(prec)
+    X, Y, Z = size
+    B = 3
+    g = gen(B, C, X, Y, Z, seed=51).to(td).float()
+    q = gen(B, F_, X, Y, Z, seed=52)
+    gh = to_halo(g, dtype=td, ld=C + 8, c0=8)
+    gh[:, 0] = 9.0
+    out = torch.zeros((C, F_), dtype=torch.float32, device="cuda")
+    cs = torch.zeros(C, dtype=torch.float32, device="cuda")
+    lib.call("tdb_cl_nc_outer", gh.data_ptr() + 8 * gh.element_size(), C + 8, q.data_ptr(), F_ * X * Y * Z, out.data_ptr(), cs.data_ptr(),
+             B, X, Y, Z, C, F_, code, lib.stream_ptr())
+    want = torch.einsum("bcxyz,bfxyz->cf", g.double().cpu(), q.double().cpu())
+    assert rel_l2(out, want) < 1e-5
+    assert rel_l2(cs, g.double().cpu().sum(dim=(0, 2, 3, 4))) < 1e-5
+    # unbatched Q (q_bstride = 0), no colsum
+    out2 = torch.zeros((C, F_), dtype=torch.float32, device="cuda")
+    lib.call("tdb_cl_nc_outer", gh.data_ptr() + 8 * gh.element_size(), C + 8, q.data_ptr(), 0, out2.data_ptr(), None, B, X, Y, Z, C, F_, code,
+             lib.stream_ptr())
+    want2 = torch.einsum("bcxyz,fxyz->cf", g.double().cpu(), q[0].double().cpu())
+    assert rel_l2(out2, want2) < 1e-5
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
 @pytest.mark.parametrize("size", [(6, 4, 3), (2, 5, 2), (4, 1, 3), (13, 4, 4)])
 def test_halo_fold_is_adjoint_of_replicate_pad(lib, prec, size):
     """tdb_halo_fold: border voxels collect the gradient of their halo images (autograd of F.pad(mode="replicate")),
