@@ -28,6 +28,8 @@ class BackwardProgram:
     def __init__(self, eng):
         self.eng = eng
         self.m = eng.model
+        self.side = None
+        self._readers = {}
 
     # ------------------------------------------------------------------ helpers
     def _gbuf(self, p, v: View, key) -> View:
@@ -59,13 +61,57 @@ class BackwardProgram:
         call("tdb_halo_fold", g.ptr, g.ld, p["B"], X, Y, Z, g.C, self.eng.dt, _lib.stream_ptr())
 
     def _wgrad(self, p, x: View, d_out: View, conv, ntaps, zero_halo=False):
-        """zero_halo: d_out comes from tdb_pointwise_bwd_apply (halo rows are zero) - lets the bf16 path use tensor cores."""
+        """zero_halo: d_out comes from tdb_pointwise_bwd_apply (halo rows are zero) - lets the bf16 path use tensor cores.
+        Weight gradients are leaves of the backward walk (nothing downstream reads them before the optimizer), so they
+        run on a side stream: the tensor-bound tcgen05 kernel then overlaps the HBM-bound halo fold / GroupNorm-SiLU
+        backward passes of the next layer on the main stream.  The buffers it reads are protected by events
+        (_wait_readers before they are overwritten); run() joins the side stream at the end."""
         X, Y, Z = p["sizes"][x.level]
-        dw = torch.zeros((ntaps, x.C, d_out.C), dtype=torch.float32, device=x.t.device)
-        call("tdb_conv3d_wgrad", x.ptr, x.ld, d_out.ptr, d_out.ld, dw.data_ptr(), p["B"], X, Y, Z, x.C, d_out.C, ntaps, self.eng.dt,
-             _lib.WGRAD_ZERO_HALO if zero_halo else 0, _lib.stream_ptr())
         k = 3 if ntaps == 27 else 1
-        return dw.view(k, k, k, x.C, d_out.C).permute(4, 3, 0, 1, 2).contiguous()
+
+        def launch():
+            dw = torch.zeros((ntaps, x.C, d_out.C), dtype=torch.float32, device=x.t.device)
+            call("tdb_conv3d_wgrad", x.ptr, x.ld, d_out.ptr, d_out.ld, dw.data_ptr(), p["B"], X, Y, Z, x.C, d_out.C, ntaps, self.eng.dt,
+                 _lib.WGRAD_ZERO_HALO if zero_halo else 0, _lib.stream_ptr())
+            return dw.view(k, k, k, x.C, d_out.C).permute(4, 3, 0, 1, 2).contiguous()
+
+        side = self.side
+        if side is None:
+            return launch()
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            res = launch()
+            done = torch.cuda.Event()
+            done.record(side)
+        if not torch.cuda.is_current_stream_capturing():
+            res.record_stream(main)  # (inside a capture every result lives until the join at the end of run())
+        self._readers[d_out.t.data_ptr()] = done
+        return res
+
+    def _leaf(self, fn):
+        """Run a gradient leaf (reads only tensors that nothing overwrites before the end of run()) on the side stream."""
+        side = self.side
+        if side is None:
+            return fn()
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            res = fn()
+        if not torch.cuda.is_current_stream_capturing():
+            for t in res:
+                t.record_stream(main)
+        return res
+
+    def _wait_readers(self, v: View):
+        """Before `v` is overwritten on the main stream: wait for the side-stream kernel that still reads it."""
+        ev = self._readers.pop(v.t.data_ptr(), None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
 
     def _colsum(self, p, g: View):
         """Per-channel sum over interior voxels and samples (conv bias gradients)."""
@@ -90,6 +136,7 @@ class BackwardProgram:
         out = torch.empty((4, C), dtype=torch.float32, device=dev)
         grp = torch.empty((B, G, 2), dtype=torch.float32, device=dev)
         dfilm_ptr = None if d_film is None else d_film.data_ptr() + 4 * film_offset
+        self._wait_readers(d_raw)
         call("tdb_pointwise_bwd_finalize", red.data_ptr(), ptr(stats), ptr(norm.weight), ptr(norm.bias), film_ptr, eng.film_rows,
              grp.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), dfilm_ptr, eng.film_rows, B, X, Y, Z,
              C, G,
@@ -119,7 +166,10 @@ class BackwardProgram:
         G = eng._groups(C)
         pre = self.prefix[name]
         film = p["film"][:, bp.film_offset : bp.film_offset + 2 * C]
+        # two d_raw buffers per (level, channels): block1's pointwise backward writes the other one while block2's weight
+        # gradient may still be reading the first on the side stream
         d_raw = self._tmp(p, lvl, C, "d_raw")
+        d_raw1 = self._tmp(p, lvl, C, "d_raw1") if self.side is not None else d_raw
         g_act = self._tmp(p, lvl, C, "g_act")
 
         # block2: pointwise (norm, SiLU, + residual) then conv2
@@ -127,17 +177,20 @@ class BackwardProgram:
         g_out_colsum = self._g_colsum
         grads[f"{pre}.block2.norm.weight"] = gw
         grads[f"{pre}.block2.norm.bias"] = gb
-        grads[f"{pre}.block2.conv.weight"] = self._wgrad(p, sv["act1"], d_raw, blk.block2.conv, 27, zero_halo=True)
         grads[f"{pre}.block2.conv.bias"] = bias2
+        # the input gradient (main stream, critical path) is enqueued BEFORE the weight gradient (side stream): both want
+        # every SM, so the weight gradient starts as the input gradient's CTAs retire and then overlaps the bandwidth-bound
+        # fold / GroupNorm-SiLU backward of the next layer
         eng._conv(p, d_raw, self._dgrad_weights(blk.block2.conv, f"{name}.conv2", lvl), None, g_act, 27, all_rows=True)
+        grads[f"{pre}.block2.conv.weight"] = self._wgrad(p, sv["act1"], d_raw, blk.block2.conv, 27, zero_halo=True)
         self._fold(p, g_act)
 
         # block1: pointwise (norm, FiLM, SiLU) then conv1; the FiLM scale/shift gradients go straight into d_film
+        d_raw = d_raw1
         gw, gb, bias1 = self._pw_bwd(p, g_act, sv["raw1"], p["stats"][slot], blk.block1.norm, film, d_raw, PW_SILU, G,
                                      d_film=d_film, film_offset=bp.film_offset)
         grads[f"{pre}.block1.norm.weight"] = gw
         grads[f"{pre}.block1.norm.bias"] = gb
-        grads[f"{pre}.block1.conv.weight"] = self._wgrad(p, x, d_raw, blk.block1.conv, 27, zero_halo=True)
         grads[f"{pre}.block1.conv.bias"] = bias1
         g_x = self._gbuf(p, x, ("g", name))
         # residual projection: its input gradient res_conv^T(g_out) rides on conv1's input-gradient kernel when that is the
@@ -145,6 +198,7 @@ class BackwardProgram:
         fuse_res = bp.has_proj and eng.can_add1x1(C, x.C, lvl)
         eng._conv(p, d_raw, self._dgrad_weights(blk.block1.conv, f"{name}.conv1", lvl), None, g_x, 27, all_rows=True,
                   add1x1=(g_out, self._dgrad_weights(blk.conv, f"{name}.proj", lvl)) if fuse_res else None)
+        grads[f"{pre}.block1.conv.weight"] = self._wgrad(p, x, d_raw, blk.block1.conv, 27, zero_halo=True)
         self._fold(p, g_x)
 
         # residual branch
@@ -209,6 +263,8 @@ class BackwardProgram:
         dt = eng.dt
         eng._set_geometry(key[1])
         eng.weights()
+        self.side = eng.side_stream(dev) if eng.wgrad_side_stream else None
+        self._readers = {}
         g_eps = g_eps.to(torch.float32).contiguous()
         grads: dict[str, torch.Tensor] = {}
         d_film = torch.zeros((B, eng.film_rows), dtype=torch.float32, device=dev)
@@ -221,10 +277,13 @@ class BackwardProgram:
         dec = m.decode[1]
         dec_out = p["dec_out"]
         Fo = m.out_features  # 2F with learned variances
-        dw = torch.zeros((m.dim, Fo), dtype=torch.float32, device=dev)
-        call("tdb_cl_nc_outer", dec_out.ptr, dec_out.ld, g_eps.data_ptr(), Fo * X * Y * Z, dw.data_ptr(), None, B, X, Y, Z, m.dim, Fo, dt, s())
-        grads["decode.1.weight"] = dw.t().reshape(dec.weight.shape).contiguous()
-        grads["decode.1.bias"] = g_eps.sum(dim=(0, 2, 3, 4))
+
+        def dec_grads():
+            dw = torch.zeros((m.dim, Fo), dtype=torch.float32, device=dev)
+            call("tdb_cl_nc_outer", dec_out.ptr, dec_out.ld, g_eps.data_ptr(), Fo * X * Y * Z, dw.data_ptr(), None, B, X, Y, Z, m.dim, Fo, dt, s())
+            return dw.t().reshape(dec.weight.shape).contiguous(), g_eps.sum(dim=(0, 2, 3, 4))
+
+        grads["decode.1.weight"], grads["decode.1.bias"] = self._leaf(dec_grads)
         g_dec = self._gbuf(p, dec_out, ("g", "dec_out"))
         wt = dec.weight.detach().reshape(Fo, m.dim).t().contiguous()  # (dim, Fo)
         zero_b = torch.zeros(m.dim, dtype=torch.float32, device=dev)
@@ -310,4 +369,7 @@ class BackwardProgram:
             grads[f"{self.prefix[n]}.project_onto_scale_shift.weight"] = g_film_w[off : off + rows]
             grads[f"{self.prefix[n]}.project_onto_scale_shift.bias"] = g_film_b[off : off + rows]
             off += rows
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)  # join: every weight gradient is complete
+            self._readers.clear()
         return grads, g_c_local

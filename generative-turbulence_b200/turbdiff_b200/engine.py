@@ -95,6 +95,9 @@ class DenoiserEngine:
         self._wgen = 0        # bumped whenever _wcache is REPLACED: captured sampler graphs hold its addresses
         self.graph_fallbacks = 0  # CUDA-graph captures that failed and fell back to the eager launch programs
         self._last_train_key = None
+        # training: weight-gradient kernels on a side stream, overlapping the bandwidth-bound passes of the next layer
+        self.wgrad_side_stream = os.environ.get("TURBDIFF_B200_WGRAD_STREAM", "1") != "0"
+        self._side = {}
         self.grad_sync = None  # optional hook(flat_grads): in-place data-parallel reduction of the backward program's flat gradient buffer
 
         m = model
@@ -111,6 +114,12 @@ class DenoiserEngine:
             off += 2 * bp.cout
         self.film_rows = off
         self.block_order = [n for n, _ in order]
+
+    def side_stream(self, device):
+        key = str(device)
+        if key not in self._side:
+            self._side[key] = torch.cuda.Stream(device=device)
+        return self._side[key]
 
     # ------------------------------------------------------------------ derived weight cache
     def _param_version(self):
