@@ -227,3 +227,32 @@ def test_boundary_class_tables_overlaps_follow_write_order():
     for idx, f0, v in fixed:  # the reference's sequential writes
         want[:, f0 : f0 + v.numel(), idx] = v[None, :, None]
     assert torch.equal(got, want)
+
+
+def test_pipeline_host_read_matches_reference_read_data():
+    """turbdiff_b200.pipeline.read_channels_last = OpenFOAMDataRepository.read_data (ofles.py:396-418): sorted unique hyperslab
+    read, scalar fields get a feature axis, the requested order (with duplicates) is restored."""
+    import numpy as np
+
+    from turbdiff_b200.pipeline import read_channels_last, sorted_unique_read_plan
+
+    class H5Like:
+        def __init__(self, arr):
+            self.arr = arr
+
+        def __getitem__(self, idx):
+            idx = np.asarray(idx)
+            assert np.all(np.diff(idx) > 0), "h5py requires sorted unique indices"
+            return self.arr[idx]
+
+    rng = np.random.default_rng(1)
+    u, p = rng.standard_normal((12, 7, 3)).astype(np.float32), rng.standard_normal((12, 7)).astype(np.float32)
+    idxs = [9, 3, 3, 0, 11, 9]
+    uniq, inv = sorted_unique_read_plan(idxs)
+    assert list(uniq) == [0, 3, 9, 11] and list(uniq[inv]) == idxs
+    got = read_channels_last([(H5Like(u), 3), (H5Like(p), 1)], idxs)
+    want = np.concatenate([u[idxs], p[idxs][..., None]], axis=-1)
+    assert got.dtype == np.float32 and np.array_equal(got, want)
+    out = np.full((8, 7, 4), 5.0, dtype=np.float32)
+    view = read_channels_last([(H5Like(u), 3), (H5Like(p), 1)], idxs, out=out)
+    assert np.array_equal(view, want) and np.all(out[6:] == 5.0)
