@@ -520,11 +520,15 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         # one more step with per-kernel events (every rank takes part: the step contains a collective)
+        # (ALL ranks switch to the per-call profiling mode: it runs the eager launch programs, whose gradient exchange is the
+        # bucketed generic path - a rank left in graph mode would issue the flat-buffer collectives instead and the two
+        # sequences would never match)
         train_prof = None
-        if rank == 0:
-            _lib.PROFILE = {}
+        _lib.PROFILE = {}
         train_step()
         torch.cuda.synchronize()
+        if rank != 0:
+            _lib.PROFILE = None
         if rank == 0:
             train_prof = {k: sum(a.elapsed_time(b) for a, b, _ in v) for k, v in _lib.PROFILE.items()}
             if os.environ.get("TDB_PROFILE_CALLS"):  # per-call dump (name, ms, small integer arguments) for kernel work
