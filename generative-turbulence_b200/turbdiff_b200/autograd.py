@@ -57,12 +57,19 @@ class _Denoise(torch.autograd.Function):
                 eng.grad_sync(grads)  # data-parallel exchange on the flat buffer (parallel.GradientAllReduce.attach)
             out = [v.view(shape) for v, shape in zip(grads.clone().split(tg["sizes"]), tg["shapes"])]
             return (None, None, None, g_c, *out)
-        out = []
-        for name, prm in model.named_parameters():
-            g = grads.get(name)
-            if g is None:
+        named = list(model.named_parameters())
+        for name, _ in named:
+            if grads.get(name) is None:
                 raise RuntimeError(f"turbdiff_b200: no gradient produced for parameter {name}")
-            out.append(g.to(prm.dtype).reshape(prm.shape).clone())  # the program's buffers are reused by the next step
+        if eng.grad_sync is not None:
+            # eager launch programs under data parallelism: the SAME exchange as the graph path (one flat fp32 buffer in
+            # parameter order, same chunking), so ranks may mix the two modes (a rank whose graph capture fell back to the
+            # eager programs must still issue the collectives its peers issue)
+            flat = torch.cat([grads[name].reshape(-1).to(torch.float32) for name, _ in named])
+            eng.grad_sync(flat)
+            out = [v.view(prm.shape).to(prm.dtype) for v, (_, prm) in zip(flat.split([prm.numel() for _, prm in named]), named)]
+            return (None, None, None, g_c, *out)
+        out = [grads[name].to(prm.dtype).reshape(prm.shape).clone() for name, prm in named]  # the program's buffers are reused by the next step
         return (None, None, None, g_c, *out)
 
 

@@ -86,7 +86,17 @@ def _worker(rank, world, port, ret):
         GradientAllReduce(m.parameters(), bucket_mb=0.5)()
         worst = max(float((p.grad - w).norm() / w.norm().clamp_min(1e-12)) for p, w in zip(m.parameters(), want) if float(w.abs().max()) > 1e-8)
         ok = ok and worst < 2e-4
-        ret[rank] = (bool(ok), worst)
+
+        # ---- attached fast path, MIXED modes: rank 0 runs the eager launch programs, rank 1 the CUDA-graph replay; both
+        # must issue the same collectives (flat buffer, same chunks) and arrive at the global-batch gradients
+        red = GradientAllReduce(m.parameters(), flat_chunks=3).attach(m)
+        m.engine().train_graph = rank != 0
+        for _ in range(2):
+            run(x[sl], t_all[sl], noise[sl].contiguous())
+            red()
+        worst2 = max(float((p.grad - w).norm() / w.norm().clamp_min(1e-12)) for p, w in zip(m.parameters(), want) if float(w.abs().max()) > 1e-8)
+        ok = ok and worst2 < 2e-4
+        ret[rank] = (bool(ok), max(worst, worst2))
     finally:
         dist.destroy_process_group()
 
