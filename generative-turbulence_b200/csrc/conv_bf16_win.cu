@@ -158,10 +158,10 @@ conv3d_bf16_win_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                         const uint32_t full_l = ptx::leader_addr(full_bar + 8 * s);
                         ptx::tma_load_2d_2sm(stage_base + s * stage_bytes, &map_a, full_l, ch * KC, row);
                         if (!resident) {
-#pragma unroll
-                            for (int t = 0; t < 9; ++t)
-                                ptx::tma_load_3d_2sm(stage_base + s * stage_bytes + win_bytes + (uint32_t)t * bh_bytes, &map_b, full_l,
-                                                     ch * KC, nt * COUT + (int)rank * NH, kx * 9 + t);
+                            // the nine (ky, kz) weight tiles of this (kx, channel chunk): ONE box [9 taps][NH rows][KC] (nine
+                            // 4-8 KB boxes cost nine TMA instructions and nine L2 request trains per stage)
+                            ptx::tma_load_3d_2sm(stage_base + s * stage_bytes + win_bytes, &map_b, full_l, ch * KC,
+                                                 nt * COUT + (int)rank * NH, kx * 9);
                             if (P.proj && kx == 1)
                                 ptx::tma_load_3d_2sm(stage_base + s * stage_bytes + win_bytes + 9u * bh_bytes, &map_p, full_l, ch * KC,
                                                      nt * COUT + (int)rank * NH, 0);
@@ -469,7 +469,12 @@ int win_impl(const void* in, int ld_in, const void* w, const float* bias, void* 
     TDB_REQUIRE(!P.proj || (out_proj && ld_outp % 8 == 0 && ((uintptr_t)w_proj & 15) == 0 && ((uintptr_t)out_proj & 15) == 0 &&
                             !(flags & TDB_CONV_ALL_ROWS)),
                 TDB_E_UNSUPPORTED, "tdb_conv3d_bf16_win: the fused projection needs aligned buffers and no ALL_ROWS");
-    const int tile_n = Cout > 128 ? 128 : Cout;  // output channels per N tile
+    int tile_n = Cout > 128 ? 128 : Cout;  // output channels per N tile
+    // tiny grids (the bottleneck level): with 128-channel N tiles the whole layer is a few dozen work items, one per CTA
+    // pair, each a serial walk over all of K (49 us at 512 -> 512 whatever the batch).  64-channel tiles double the
+    // items while they still fit one wave, and their 54 KB stages pipeline four deep instead of two.
+    if (Cout % 128 == 0 && Cout >= 256 && KC == 64 && ceil_div(g.rows, 2 * BM) * (Cout / 128) * 2 <= (g_num_sms_win / 2))
+        tile_n = 64;
     P.n_tiles = Cout / tile_n;
     P.cout_total = Cout;
     const int bh_bytes = (tile_n / 2) * KC * 2;
@@ -479,7 +484,7 @@ int win_impl(const void* in, int ld_in, const void* w, const float* bias, void* 
     // all weights resident when they leave room for two windows; otherwise (Cin % 64 == 0 only) the nine weight
     // tiles of a (kx, channel chunk) stream with each window and Cout is walked in N tiles of 128
     const bool res = P.n_tiles == 1 && resident_bytes + 2048 + 2 * win_bytes <= budget;
-    TDB_REQUIRE(res || (KC == 64 && tile_n == 128), TDB_E_UNSUPPORTED,
+    TDB_REQUIRE(res || (KC == 64 && (tile_n == 128 || tile_n == 64)), TDB_E_UNSUPPORTED,
                 "tdb_conv3d_bf16_win: streamed weights need Cin %% 64 == 0 and Cout %% 128 == 0 (Cin=%d Cout=%d)", Cin, Cout);
     const int fixed_bytes = res ? resident_bytes : 0;
     const int stage_bytes = win_bytes + (res ? 0 : (9 + (P.proj ? 1 : 0)) * bh_bytes);
@@ -505,7 +510,7 @@ int win_impl(const void* in, int ld_in, const void* w, const float* bias, void* 
         // weights [Cout][27][Cin]; one box = the Cout/2 rows of a CTA for one (tap, channel chunk)
         const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 27};
         const uint64_t strides[2] = {27ull * Cin, (uint64_t)Cin};
-        const uint32_t box[3] = {(uint32_t)KC, (uint32_t)(tile_n / 2), 1};
+        const uint32_t box[3] = {(uint32_t)KC, (uint32_t)(tile_n / 2), res ? 1u : 9u};  // streamed: the nine taps of a kx at once
         TDB_REQUIRE(make_map_bf16(&map_b, w, 3, dims, strides, box), TDB_E_BADARG, "tdb_conv3d_bf16_win: tensor map (weights) rejected");
     }
     {
@@ -532,6 +537,7 @@ int win_impl(const void* in, int ld_in, const void* w, const float* bias, void* 
     TDB_WIN_CASE(64, 32, 1);
     TDB_WIN_CASE(128, 32, 1);
     TDB_WIN_CASE(128, 64, 0);
+    TDB_WIN_CASE(64, 64, 0);
 #undef TDB_WIN_CASE
     tdb::set_error("tdb_conv3d_bf16_win: no kernel for Cout=%d KC=%d", Cout, KC);
     return TDB_E_UNSUPPORTED;

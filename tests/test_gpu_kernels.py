@@ -606,6 +606,8 @@ WIN_CASES = [
     # streamed weights, N tiles of 128 channels (weights too large to stay resident)
     (2, 25, 13, 12, 64, 128, True), (1, 20, 12, 12, 128, 256, True), (2, 12, 6, 6, 256, 512, False), (1, 48, 12, 12, 128, 128, False),
     (1, 12, 6, 6, 512, 128, True),
+    # tiny grids: 64-channel N tiles of the streamed-weight variant (the bottleneck level)
+    (4, 12, 3, 3, 512, 512, False), (1, 12, 3, 3, 256, 256, True),
 ]
 
 
