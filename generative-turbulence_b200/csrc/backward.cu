@@ -321,23 +321,98 @@ pw_bwd_reduce_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict_
 }
 
 // d_raw = rstd * (k*g_u - m1 - xhat*m2) on interior rows, 0 on halo rows.  grp[b][g] = (m1, m2) fp32.
+// Fused form (fin.red != nullptr): the group sums m1, m2 are derived from the reduce kernel's red[] in every block's
+// prologue (one thread per channel, double shared-memory atomics), and gridDim.x - 1 is an EXTRA block per sample that
+// streams nothing and writes the parameter gradients instead (what pw_bwd_finalize_kernel computes).  The separate
+// one-block finalize launch sat on the critical path between reduce and apply with a serial chain of dependent global
+// loads per (sample, group) - measured 1.3 ms per training step for its 23 launches.
+struct PwFinal {
+    const double* red;  // [B][C][4] = (A1, A2, Sx, Sg)
+    float *colsum, *gw, *gb, *gsum, *dfilm;
+    int dfilm_ld, B;
+};
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 pw_bwd_apply_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict__ raw, int ld_raw,
                     const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                     const float* __restrict__ film, int film_ld, const float* __restrict__ grp, T* __restrict__ d_raw, int ld_d,
-                    Grid3 gr, int C, int G, float eps, unsigned flags, RowSplit split, int chunks) {
+                    Grid3 gr, int C, int G, float eps, unsigned flags, RowSplit split, int chunks, PwFinal fin) {
     constexpr int N = Vec<T>::N;
     constexpr int U = 4;
-    extern __shared__ float s_apply[];  // [C][5] = (a, o, c1, c2, c3): d_raw = c1*g_u + c2*raw + c3
+    extern __shared__ double s_apply_d[];  // fused form: [4*B*G] doubles (mean, rstd, m1, m2 per (sample, group)); then the floats
+    const bool fused = fin.red != nullptr;
+    const int n_d = fused ? 4 * fin.B * G : 0;
+    float* s_apply = reinterpret_cast<float*>(s_apply_d + n_d);  // [C][5] = (a, o, c1, c2, c3): d_raw = c1*g_u + c2*raw + c3
     const int b = blockIdx.y;
+    const int cpg = C / G;
+    const double nv = (double)gr.X * gr.Y * gr.Z;
+    const int n_stream = fused ? (int)gridDim.x - 1 : (int)gridDim.x;  // blocks that stream rows
+    if (fused) {
+        // (m1, m2) of this sample's groups - or of every sample's in the extra block of sample 0 (cross-sample sums)
+        const bool extra = (int)blockIdx.x == n_stream;
+        const int b_lo = (extra && b == 0) ? 0 : b, b_hi = (extra && b == 0) ? fin.B : b + 1;
+        for (int i = threadIdx.x; i < 4 * fin.B * G; i += blockDim.x) s_apply_d[i] = 0.0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < (b_hi - b_lo) * C; i += blockDim.x) {
+            const int bb = b_lo + i / C, c = i % C;
+            double k = (double)gamma[c];
+            if (film) k *= (double)film[(int64_t)bb * film_ld + c] + 1.0;
+            const double* r = fin.red + ((int64_t)bb * C + c) * 4;
+            atomicAdd(&s_apply_d[4 * (bb * G + c / cpg) + 2], k * r[0]);
+            atomicAdd(&s_apply_d[4 * (bb * G + c / cpg) + 3], k * r[1]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < (b_hi - b_lo) * G; i += blockDim.x) {
+            const int q = (b_lo + i / G) * G + i % G;
+            const double n = (double)cpg * nv;
+            const double mean = stats[(int64_t)q * 2] / n;
+            const double var = fmax(stats[(int64_t)q * 2 + 1] / n - mean * mean, 0.0);
+            s_apply_d[4 * q] = mean;
+            s_apply_d[4 * q + 1] = 1.0 / sqrt(var + (double)eps);
+            s_apply_d[4 * q + 2] /= n;
+            s_apply_d[4 * q + 3] /= n;
+        }
+        __syncthreads();
+        if (extra) {
+            // parameter gradients (same arithmetic as pw_bwd_finalize_kernel): FiLM scale / shift of this sample, and in the
+            // block of sample 0 the sums over samples
+            for (int c = threadIdx.x; c < C; c += blockDim.x) {
+                const double* r = fin.red + ((int64_t)b * C + c) * 4;
+                if (fin.dfilm) {
+                    fin.dfilm[(int64_t)b * fin.dfilm_ld + c] = (float)((double)gamma[c] * r[1] + (double)beta[c] * r[0]);
+                    fin.dfilm[(int64_t)b * fin.dfilm_ld + C + c] = (float)r[0];
+                }
+                if (b != 0) continue;
+                double cs = 0.0, w = 0.0, bsum = 0.0, gs = 0.0;
+                for (int bb = 0; bb < fin.B; ++bb) {
+                    const double* rr = fin.red + ((int64_t)bb * C + c) * 4;
+                    const double* q = s_apply_d + 4 * (bb * G + c / cpg);
+                    const double sc = film ? (double)film[(int64_t)bb * film_ld + c] + 1.0 : 1.0;
+                    const double k = (double)gamma[c] * sc;
+                    gs += rr[3];
+                    cs += q[1] * (k * rr[0] - nv * q[2] - q[3] * q[1] * (rr[2] - nv * q[0]));
+                    w += sc * rr[1];
+                    bsum += sc * rr[0];
+                }
+                fin.colsum[c] = (float)cs;
+                fin.gw[c] = (float)w;
+                fin.gb[c] = (float)bsum;
+                if (fin.gsum) fin.gsum[c] = (float)gs;
+            }
+            return;
+        }
+    }
     {
-        const double inv_n = 1.0 / ((double)(C / G) * gr.X * gr.Y * gr.Z);
+        const double inv_n = 1.0 / ((double)cpg * nv);
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
             const PwCoef k = pw_coef(b, c, C, G, stats, gamma, beta, film, film_ld, inv_n, eps);
-            const int gi = c / (C / G);
-            const float m1 = stats ? grp[((int64_t)b * G + gi) * 2] : 0.0f;
-            const float m2 = stats ? grp[((int64_t)b * G + gi) * 2 + 1] : 0.0f;
+            const int gi = c / cpg;
+            float m1 = 0.0f, m2 = 0.0f;
+            if (stats) {
+                m1 = fused ? (float)s_apply_d[4 * (b * G + gi) + 2] : grp[((int64_t)b * G + gi) * 2];
+                m2 = fused ? (float)s_apply_d[4 * (b * G + gi) + 3] : grp[((int64_t)b * G + gi) * 2 + 1];
+            }
             const float c2 = stats ? -k.rstd * k.rstd * m2 : 0.0f;
             s_apply[5 * c] = k.a;
             s_apply[5 * c + 1] = k.o;
@@ -362,7 +437,7 @@ pw_bwd_apply_kernel(const T* __restrict__ g_out, int ld_g, const T* __restrict__
     }
     const bool act = flags & TDB_PW_SILU;
     const uint32_t total = (uint32_t)gr.vox_p;
-    const uint32_t stride = gridDim.x * (uint32_t)vox_step;
+    const uint32_t stride = (uint32_t)n_stream * (uint32_t)vox_step;
     const int64_t base = (int64_t)b * gr.vox_p;
     for (uint32_t r0 = blockIdx.x * (uint32_t)vox_step + lane_vox; r0 < total; r0 += U * stride) {
         uint4 xr[U], gv[U];
@@ -1113,32 +1188,67 @@ int tdb_pointwise_bwd_finalize(const double* red, const double* stats, const flo
     return 0;
 }
 
-int tdb_pointwise_bwd_apply(const void* g_out, int ld_g, const void* raw, int ld_raw, const double* stats, const float* gamma,
-                            const float* beta, const float* film, int film_ld, const float* grp, void* d_raw, int ld_d, int B,
-                            int X, int Y, int Z, int C, int G, float eps, unsigned flags, int dtype, void* stream) {
-    TDB_REQUIRE(g_out && raw && d_raw, TDB_E_BADARG, "tdb_pointwise_bwd_apply: null pointer");
-    TDB_REQUIRE(!stats || (gamma && beta && grp && G >= 1 && C % G == 0), TDB_E_BADARG, "tdb_pointwise_bwd_apply: norm args");
+static int launch_pw_bwd_apply(const char* who, const void* g_out, int ld_g, const void* raw, int ld_raw, const double* stats, const float* gamma,
+                               const float* beta, const float* film, int film_ld, const float* grp, void* d_raw, int ld_d, int B, int X,
+                               int Y, int Z, int C, int G, float eps, unsigned flags, int dtype, PwFinal fin, void* stream) {
     const int n = dtype == TDB_BF16 ? 8 : 4;
     TDB_REQUIRE(C % n == 0 && ld_g % n == 0 && ld_raw % n == 0 && ld_d % n == 0 && C / n <= kThreads && aligned16(g_out) &&
                     aligned16(raw) && aligned16(d_raw),
-                TDB_E_UNSUPPORTED, "tdb_pointwise_bwd_apply: C/ld must be multiples of %d", n);
+                TDB_E_UNSUPPORTED, "%s: C/ld must be multiples of %d", who, n);
     if (G < 1) G = 1;
     Grid3 gr(B, X, Y, Z);
     const int chunks = C / n;
     int64_t blocks = ceil_div(gr.vox_p, (int64_t)(kThreads / chunks) * 4);
     const int64_t cap = (148 * 8) / (B < 1 ? 1 : B) < 1 ? 1 : (148 * 8) / (B < 1 ? 1 : B);
     if (blocks > cap) blocks = cap;
-    dim3 grid((unsigned)blocks, (unsigned)B);
+    const bool fused = fin.red != nullptr;
+    dim3 grid((unsigned)(blocks + (fused ? 1 : 0)), (unsigned)B);  // fused: one extra block per sample for the parameter gradients
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t smem = (size_t)5 * C * sizeof(float);
-    if (dtype == TDB_BF16)
-        pw_bwd_apply_kernel<bf16><<<grid, kThreads, smem, s>>>((const bf16*)g_out, ld_g, (const bf16*)raw, ld_raw, stats, gamma, beta, film,
-                                                             film_ld, grp, (bf16*)d_raw, ld_d, gr, C, G, eps, flags, make_split(gr), chunks);
-    else
-        pw_bwd_apply_kernel<float><<<grid, kThreads, smem, s>>>((const float*)g_out, ld_g, (const float*)raw, ld_raw, stats, gamma, beta,
-                                                              film, film_ld, grp, (float*)d_raw, ld_d, gr, C, G, eps, flags,
-                                                              make_split(gr), chunks);
+    const size_t smem = (size_t)5 * C * sizeof(float) + (fused ? (size_t)4 * B * G * sizeof(double) : 0);
+    TDB_REQUIRE(smem <= 200 * 1024, TDB_E_UNSUPPORTED, "%s: B*G=%d groups do not fit in shared memory", who, B * G);
+    cudaError_t e = cudaSuccess;
+    if (dtype == TDB_BF16) {
+        if (smem > 40 * 1024) e = cudaFuncSetAttribute(pw_bwd_apply_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            pw_bwd_apply_kernel<bf16><<<grid, kThreads, smem, s>>>((const bf16*)g_out, ld_g, (const bf16*)raw, ld_raw, stats, gamma, beta, film,
+                                                                 film_ld, grp, (bf16*)d_raw, ld_d, gr, C, G, eps, flags, make_split(gr), chunks,
+                                                                 fin);
+    } else {
+        if (smem > 40 * 1024) e = cudaFuncSetAttribute(pw_bwd_apply_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            pw_bwd_apply_kernel<float><<<grid, kThreads, smem, s>>>((const float*)g_out, ld_g, (const float*)raw, ld_raw, stats, gamma, beta,
+                                                                  film, film_ld, grp, (float*)d_raw, ld_d, gr, C, G, eps, flags,
+                                                                  make_split(gr), chunks, fin);
+    }
+    TDB_REQUIRE(e == cudaSuccess, (int)e, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
+    return 0;
+}
+
+int tdb_pointwise_bwd_apply(const void* g_out, int ld_g, const void* raw, int ld_raw, const double* stats, const float* gamma,
+                            const float* beta, const float* film, int film_ld, const float* grp, void* d_raw, int ld_d, int B,
+                            int X, int Y, int Z, int C, int G, float eps, unsigned flags, int dtype, void* stream) {
+    TDB_REQUIRE(g_out && raw && d_raw, TDB_E_BADARG, "tdb_pointwise_bwd_apply: null pointer");
+    TDB_REQUIRE(!stats || (gamma && beta && grp && G >= 1 && C % G == 0), TDB_E_BADARG, "tdb_pointwise_bwd_apply: norm args");
+    PwFinal fin{};
+    const int rc = launch_pw_bwd_apply("tdb_pointwise_bwd_apply", g_out, ld_g, raw, ld_raw, stats, gamma, beta, film, film_ld, grp, d_raw, ld_d,
+                                       B, X, Y, Z, C, G, eps, flags, dtype, fin, stream);
+    if (rc) return rc;
     TDB_CHECK_LAUNCH("tdb_pointwise_bwd_apply");
+    return 0;
+}
+
+int tdb_pointwise_bwd_apply_fused(const void* g_out, int ld_g, const void* raw, int ld_raw, const double* stats, const float* gamma,
+                                  const float* beta, const float* film, int film_ld, const double* red, void* d_raw, int ld_d,
+                                  float* colsum, float* gw, float* gb, float* gsum, float* dfilm, int dfilm_ld, int B, int X, int Y,
+                                  int Z, int C, int G, float eps, unsigned flags, int dtype, void* stream) {
+    TDB_REQUIRE(g_out && raw && d_raw && red && stats && gamma && beta && colsum && gw && gb, TDB_E_BADARG,
+                "tdb_pointwise_bwd_apply_fused: null pointer");
+    TDB_REQUIRE(G >= 1 && C % G == 0, TDB_E_BADARG, "tdb_pointwise_bwd_apply_fused: norm args");
+    PwFinal fin{red, colsum, gw, gb, gsum, dfilm, dfilm_ld, B};
+    const int rc = launch_pw_bwd_apply("tdb_pointwise_bwd_apply_fused", g_out, ld_g, raw, ld_raw, stats, gamma, beta, film, film_ld, nullptr,
+                                       d_raw, ld_d, B, X, Y, Z, C, G, eps, flags, dtype, fin, stream);
+    if (rc) return rc;
+    TDB_CHECK_LAUNCH("tdb_pointwise_bwd_apply_fused");
     return 0;
 }
 

@@ -47,6 +47,7 @@ SIGNATURES = {
     "tdb_pointwise_bwd_reduce": [_p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _f, _u, _i, _p],
     "tdb_pointwise_bwd_finalize": [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p],
     "tdb_pointwise_bwd_apply": [_p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _u, _i, _p],
+    "tdb_pointwise_bwd_apply_fused": [_p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _u, _i, _p],
     "tdb_conv3d_wgrad": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _u, _p],
     "tdb_conv3d_wgrad_tc": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _u, _p],
     "tdb_trilinear_bwd": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _u, _p],

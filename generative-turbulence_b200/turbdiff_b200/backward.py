@@ -134,15 +134,13 @@ class BackwardProgram:
         call("tdb_pointwise_bwd_reduce", g_out.ptr, g_out.ld, raw.ptr, raw.ld, ptr(stats), ptr(norm.weight), ptr(norm.bias), film_ptr,
              eng.film_rows, red.data_ptr(), B, X, Y, Z, C, G, GN_EPS, flags, eng.dt, _lib.stream_ptr())
         out = torch.empty((4, C), dtype=torch.float32, device=dev)
-        grp = torch.empty((B, G, 2), dtype=torch.float32, device=dev)
         dfilm_ptr = None if d_film is None else d_film.data_ptr() + 4 * film_offset
         self._wait_readers(d_raw)
-        call("tdb_pointwise_bwd_finalize", red.data_ptr(), ptr(stats), ptr(norm.weight), ptr(norm.bias), film_ptr, eng.film_rows,
-             grp.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), dfilm_ptr, eng.film_rows, B, X, Y, Z,
-             C, G,
-             GN_EPS, _lib.stream_ptr())
-        call("tdb_pointwise_bwd_apply", g_out.ptr, g_out.ld, raw.ptr, raw.ld, ptr(stats), ptr(norm.weight), ptr(norm.bias), film_ptr,
-             eng.film_rows, grp.data_ptr(), d_raw.ptr, d_raw.ld, B, X, Y, Z, C, G, GN_EPS, flags, eng.dt, _lib.stream_ptr())
+        # group sums + parameter gradients + input gradient in ONE launch (the one-block finalize kernel between reduce and
+        # apply was a serial chain of dependent loads on the critical path: 1.3 ms per step for its 23 launches)
+        call("tdb_pointwise_bwd_apply_fused", g_out.ptr, g_out.ld, raw.ptr, raw.ld, ptr(stats), ptr(norm.weight), ptr(norm.bias), film_ptr,
+             eng.film_rows, red.data_ptr(), d_raw.ptr, d_raw.ld, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(),
+             dfilm_ptr, eng.film_rows, B, X, Y, Z, C, G, GN_EPS, flags, eng.dt, _lib.stream_ptr())
         self._g_colsum = out[3]  # sum of g_out per channel: bias gradient of a 1x1 residual projection on the same output
         return out[1], out[2], out[0]
 

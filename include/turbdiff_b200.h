@@ -309,6 +309,15 @@ TDB_API int tdb_pointwise_bwd_apply(const void* g_out, int ld_g, const void* raw
                             const float* grp, void* d_raw, int ld_d, int B, int X, int Y, int Z, int C, int G,
                             float eps, unsigned flags, int dtype, void* stream);
 
+/* tdb_pointwise_bwd_finalize + tdb_pointwise_bwd_apply in one launch: every block derives the group sums from `red`
+ * (the reduce kernel's output) in its prologue and one extra block per sample writes the parameter gradients
+ * (colsum, gw, gb, gsum [C]; dfilm [B][dfilm_ld] may be null).  Same results as the two-launch sequence. */
+TDB_API int tdb_pointwise_bwd_apply_fused(const void* g_out, int ld_g, const void* raw, int ld_raw, const double* stats,
+                                  const float* gamma, const float* beta, const float* film, int film_ld,
+                                  const double* red, void* d_raw, int ld_d, float* colsum, float* gw, float* gb,
+                                  float* gsum, float* dfilm, int dfilm_ld, int B, int X, int Y, int Z, int C, int G,
+                                  float eps, unsigned flags, int dtype, void* stream);
+
 /* Weight gradient of tdb_conv3d_*: dw[tap][ci][co] += sum over interior rows p of
  * in[p+delta(tap)][ci]*d_out[p][co]; dw fp32 [ntaps][Cin][Cout], accumulated (pre-zero it).
  * flags & TDB_WGRAD_ZERO_HALO: the caller guarantees that d_out is zero on halo rows and that `in` is readable

@@ -291,6 +291,16 @@ def test_pointwise_bwd_matches_autograd(lib, prec, C, G, with_film, size):
     assert rel_l2(out[3], g.double().cpu().sum(dim=(0, 2, 3, 4))) < 1e-5
     if with_film:
         assert rel_l2(dfilm, want[3]) < ptol
+    # the fused form (finalize folded into apply) gives the same input gradient and parameter gradients
+    d_raw2 = torch.full_like(d_raw, 9.0)
+    out2 = torch.empty_like(out)
+    dfilm2 = torch.zeros_like(dfilm)
+    lib.call("tdb_pointwise_bwd_apply_fused", gg.data_ptr(), C, raw.data_ptr(), C, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), fptr,
+             2 * C, red.data_ptr(), d_raw2.data_ptr(), C, out2[0].data_ptr(), out2[1].data_ptr(), out2[2].data_ptr(), out2[3].data_ptr(),
+             dfilm2.data_ptr() if with_film else None, 2 * C, B, X, Y, Z, C, G, 1e-5, lib.PW_SILU, code, lib.stream_ptr())
+    assert torch.equal(d_raw2, d_raw)
+    torch.testing.assert_close(out2, out, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(dfilm2, dfilm, rtol=1e-6, atol=1e-6)
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
