@@ -41,7 +41,7 @@ UNIT = "samples/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--batch", type=int, default=8, help="samples per GPU per sampling step (configs[2]: 64 samples over 8 GPUs)")
