@@ -45,7 +45,139 @@ time_film_kernel(const int64_t* __restrict__ t, const float* __restrict__ emb_sc
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Backward of the timestep conditioning (autograd of ddpm.py:447-452, 184/191 in the reference): two launches instead
+// of ~20 small torch kernels with cuBLAS matmuls (which also kept the backward CUDA graph from being captured in the
+// default capture mode).
+//   A (grid over FiLM rows): g_film_w[r][k] = sum_b d_film[b][r] c[b][k],  g_film_b[r] = sum_b d_film[b][r],
+//                            dc[b][k] += sum_r d_film[b][r] film_w[r][k]           (block partials, fp32 atomics)
+//   B (one block):           the 32 -> 128 -> 32 MLP with SiLU after both linears, differentiated by hand
+__device__ __forceinline__ float dsilu_exact(float z) {
+    const float s = 1.0f / (1.0f + expf(-z));
+    return s * (1.0f + z * (1.0f - s));
+}
+
+__global__ void __launch_bounds__(256)
+time_film_bwd_rows_kernel(const float* __restrict__ d_film, const float* __restrict__ c, const float* __restrict__ film_wt,
+                          float* __restrict__ g_film_w, float* __restrict__ g_film_b, float* __restrict__ dc, int B, int dim,
+                          int film_rows) {
+    extern __shared__ float sm[];
+    float* sc = sm;              // [B][dim]
+    float* sdc = sc + B * dim;   // [B][dim] block partial of dc
+    for (int i = threadIdx.x; i < B * dim; i += blockDim.x) {
+        sc[i] = c[i];
+        sdc[i] = 0.0f;
+    }
+    __syncthreads();
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = r < film_rows;
+    float gb = 0.0f;
+    for (int k = 0; k < dim; ++k) {
+        const float w = on ? film_wt[(int64_t)k * film_rows + r] : 0.0f;
+        float gw = 0.0f;
+        for (int b = 0; b < B; ++b) {
+            const float d = on ? d_film[(int64_t)b * film_rows + r] : 0.0f;  // (L1-resident after the first k)
+            gw = fmaf(d, sc[b * dim + k], gw);
+            const float part = warp_sum(d * w);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&sdc[b * dim + k], part);
+            if (k == 0) gb += d;
+        }
+        if (on) g_film_w[(int64_t)r * dim + k] = gw;
+    }
+    if (on) g_film_b[r] = gb;
+    __syncthreads();
+    for (int i = threadIdx.x; i < B * dim; i += blockDim.x) atomicAdd(&dc[i], sdc[i]);
+}
+
+__global__ void __launch_bounds__(256)
+time_film_bwd_mlp_kernel(const int64_t* __restrict__ t, const float* __restrict__ emb_scale, const float* __restrict__ emb_bias,
+                         const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                         const float* __restrict__ b2, const float* __restrict__ dc, float* __restrict__ g_w1,
+                         float* __restrict__ g_b1, float* __restrict__ g_w2, float* __restrict__ g_b2, int B, int dim) {
+    extern __shared__ float sm[];
+    const int H = 4 * dim;
+    float* emb = sm;             // [B][dim]
+    float* z1 = emb + B * dim;   // [B][H]
+    float* h1 = z1 + B * H;      // [B][H]
+    float* dz2 = h1 + B * H;     // [B][dim]
+    float* dz1 = dz2 + B * dim;  // [B][H]
+    for (int i = threadIdx.x; i < B * dim; i += blockDim.x) {
+        const int b = i / dim, k = i % dim;
+        emb[i] = sinf(fmaf(emb_scale[k], (float)t[b], emb_bias[k]));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < B * H; i += blockDim.x) {
+        const int b = i / H, r = i % H;
+        float acc = b1[r];
+        for (int k = 0; k < dim; ++k) acc = fmaf(w1[r * dim + k], emb[b * dim + k], acc);
+        z1[i] = acc;
+        h1[i] = silu_f(acc);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < B * dim; i += blockDim.x) {
+        const int b = i / dim, r = i % dim;
+        float acc = b2[r];
+        for (int k = 0; k < H; ++k) acc = fmaf(w2[r * H + k], h1[b * H + k], acc);
+        dz2[i] = dc[i] * dsilu_exact(acc);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < B * H; i += blockDim.x) {
+        const int b = i / H, j = i % H;
+        float acc = 0.0f;
+        for (int r = 0; r < dim; ++r) acc = fmaf(dz2[b * dim + r], w2[r * H + j], acc);
+        dz1[i] = acc * dsilu_exact(z1[i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < dim * H; i += blockDim.x) {  // g_w2 [dim][H]
+        const int r = i / H, j = i % H;
+        float acc = 0.0f;
+        for (int b = 0; b < B; ++b) acc = fmaf(dz2[b * dim + r], h1[b * H + j], acc);
+        g_w2[i] = acc;
+    }
+    for (int i = threadIdx.x; i < H * dim; i += blockDim.x) {  // g_w1 [H][dim]
+        const int j = i / dim, k = i % dim;
+        float acc = 0.0f;
+        for (int b = 0; b < B; ++b) acc = fmaf(dz1[b * H + j], emb[b * dim + k], acc);
+        g_w1[i] = acc;
+    }
+    for (int r = threadIdx.x; r < dim; r += blockDim.x) {
+        float acc = 0.0f;
+        for (int b = 0; b < B; ++b) acc += dz2[b * dim + r];
+        g_b2[r] = acc;
+    }
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        float acc = 0.0f;
+        for (int b = 0; b < B; ++b) acc += dz1[b * H + j];
+        g_b1[j] = acc;
+    }
+}
+
 }  // namespace
+
+extern "C" int tdb_time_film_bwd(const int64_t* t, const float* emb_scale, const float* emb_bias, const float* w1, const float* b1,
+                                 const float* w2, const float* b2, const float* film_wt, const float* c, const float* d_film,
+                                 float* g_film_w, float* g_film_b, float* g_w1, float* g_b1, float* g_w2, float* g_b2,
+                                 float* dc_scratch, int B, int dim, int film_rows, void* stream) {
+    TDB_REQUIRE(t && emb_scale && emb_bias && w1 && b1 && w2 && b2 && film_wt && c && d_film && g_film_w && g_film_b && g_w1 && g_b1 &&
+                    g_w2 && g_b2 && dc_scratch,
+                TDB_E_BADARG, "tdb_time_film_bwd: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem_a = (size_t)2 * B * dim * sizeof(float);
+    const size_t smem_b = (size_t)B * dim * 14 * sizeof(float);  // emb + dz2: 2*dim, z1 + h1 + dz1: 12*dim per sample
+    TDB_REQUIRE(smem_a <= 48 * 1024 && smem_b <= 200 * 1024, TDB_E_UNSUPPORTED, "tdb_time_film_bwd: batch %d x dim %d does not fit", B, dim);
+    cudaError_t e = cudaMemsetAsync(dc_scratch, 0, (size_t)B * dim * sizeof(float), s);
+    TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_time_film_bwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
+    time_film_bwd_rows_kernel<<<(unsigned)ceil_div(film_rows > 0 ? film_rows : 1, 256), 256, smem_a, s>>>(d_film, c, film_wt, g_film_w, g_film_b,
+                                                                                                      dc_scratch, B, dim, film_rows);
+    TDB_CHECK_LAUNCH("tdb_time_film_bwd (rows)");
+    if (smem_b > 40 * 1024) {
+        e = cudaFuncSetAttribute(time_film_bwd_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+        TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_time_film_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    time_film_bwd_mlp_kernel<<<1, 256, smem_b, s>>>(t, emb_scale, emb_bias, w1, b1, w2, b2, dc_scratch, g_w1, g_b1, g_w2, g_b2, B, dim);
+    TDB_CHECK_LAUNCH("tdb_time_film_bwd (mlp)");
+    return 0;
+}
 
 extern "C" int tdb_time_film(const int64_t* t, const float* emb_scale, const float* emb_bias, const float* w1,
                              const float* b1, const float* w2, const float* b2, const float* film_wt,

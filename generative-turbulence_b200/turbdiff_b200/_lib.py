@@ -39,6 +39,7 @@ SIGNATURES = {
     "tdb_trilinear": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_attention": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_time_film": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "tdb_time_film_bwd": [_p] * 17 + [_i, _i, _i, _p],
     "tdb_ddpm_step": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _l, _u, _p],
     "tdb_step_tail": [_p, _i, _p, _p, _p, _p, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _u, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p],
     "tdb_q_sample": [_p, _p, _p, _p, _p, _p, _i, _i, _l, _i, _p],

@@ -337,33 +337,25 @@ class BackwardProgram:
             call("tdb_decode_output", gc.ptr, gc.ld, wct.data_ptr(), zb.data_ptr(), per_sample.data_ptr(), B, X, Y, Z, dim, Fc, dt, s())
             g_c_local = per_sample.sum(0)
 
-        # timestep MLP + FiLM projections (ddpm.py:447-452, :184): (B, <=128)-sized matrices, differentiated by hand with
-        # a few torch matmuls (no nested autograd: the whole program must be CUDA-graph capturable)
+        # timestep MLP + FiLM projections (ddpm.py:447-452, :184): two launches of tdb_time_film_bwd (no cuBLAS / torch ops, so
+        # the whole program captures into a CUDA graph in the default capture mode)
         pc = m.process_c
-        W0, b0, W2, b2 = pc[0].weight.detach(), pc[0].bias.detach(), pc[2].weight.detach(), pc[2].bias.detach()
-        lin = [eng.blocks[n].blk.project_onto_scale_shift for n in eng.block_order]
-        film_w = torch.cat([q.weight.detach() for q in lin])  # (film_rows, dim_c)
-        emb = torch.addcmul(m.encode_t.bias, m.encode_t.scale, t[..., None].to(torch.float32)).sin()
-        z1 = torch.nn.functional.linear(emb, W0, b0)
-        h1 = torch.nn.functional.silu(z1)
-        z2 = torch.nn.functional.linear(h1, W2, b2)
-        c = torch.nn.functional.silu(z2)
-
-        def dsilu(z):
-            sg = torch.sigmoid(z)
-            return sg * (1.0 + z * (1.0 - sg))
-
-        g_film_w = d_film.t() @ c          # (film_rows, dim_c)
-        g_film_b = d_film.sum(0)
-        dz2 = (d_film @ film_w) * dsilu(z2)
-        dz1 = (dz2 @ W2) * dsilu(z1)
-        grads["process_c.2.weight"] = dz2.t() @ h1
-        grads["process_c.2.bias"] = dz2.sum(0)
-        grads["process_c.0.weight"] = dz1.t() @ emb
-        grads["process_c.0.bias"] = dz1.sum(0)
+        w = eng.weights()
+        R, dimc = eng.film_rows, m.dim
+        g_film_w = torch.empty((R, dimc), dtype=torch.float32, device=dev)
+        g_film_b = torch.empty(R, dtype=torch.float32, device=dev)
+        g_w1, g_b1 = torch.empty_like(pc[0].weight), torch.empty_like(pc[0].bias)
+        g_w2, g_b2 = torch.empty_like(pc[2].weight), torch.empty_like(pc[2].bias)
+        dc = torch.empty((B, dimc), dtype=torch.float32, device=dev)
+        call("tdb_time_film_bwd", t.data_ptr(), m.encode_t.scale.data_ptr(), m.encode_t.bias.data_ptr(), pc[0].weight.data_ptr(),
+             pc[0].bias.data_ptr(), pc[2].weight.data_ptr(), pc[2].bias.data_ptr(), w["film_w"].data_ptr(), p["c"].data_ptr(),
+             d_film.data_ptr(), g_film_w.data_ptr(), g_film_b.data_ptr(), g_w1.data_ptr(), g_b1.data_ptr(), g_w2.data_ptr(),
+             g_b2.data_ptr(), dc.data_ptr(), B, dimc, R, s())
+        grads["process_c.0.weight"], grads["process_c.0.bias"] = g_w1, g_b1
+        grads["process_c.2.weight"], grads["process_c.2.bias"] = g_w2, g_b2
         off = 0
-        for n, q in zip(eng.block_order, lin):
-            rows = q.weight.shape[0]
+        for n in eng.block_order:
+            rows = eng.blocks[n].blk.project_onto_scale_shift.weight.shape[0]
             grads[f"{self.prefix[n]}.project_onto_scale_shift.weight"] = g_film_w[off : off + rows]
             grads[f"{self.prefix[n]}.project_onto_scale_shift.bias"] = g_film_b[off : off + rows]
             off += rows

@@ -707,16 +707,17 @@ class DenoiserEngine:
         torch.cuda.current_stream().wait_stream(side)
         pool = torch.cuda.graph_pool_handle()
         g_f, g_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        # capture_error_mode="relaxed": the backward program contains cuBLAS matmuls (timestep MLP) whose first use for a new
-        # shape may load a module / allocate a workspace on this thread - legal, but rejected by the default "global" mode
-        # (measured: the capture of the dim-16 test configuration was invalidated whenever nothing had warmed cuBLAS up)
+        # capture_error_mode="thread_local": both programs consist of this library's launches plus allocator-backed torch
+        # element-wise ops only (the timestep-MLP backward is tdb_time_film_bwd since round 2: no cuBLAS in the capture), so
+        # the strict mode holds for this thread; other threads (data-pipeline workers, pinned-memory threads) may keep
+        # calling into the runtime while the capture is open
         n0 = _lib.launch_count()
         # the kernel-layout weights are re-derived from the parameters INSIDE the forward graph (every replay sees the
         # parameters of that moment).  Those copies live in the graph's private pool and are only valid between the
         # forward and the backward replay of one step, so the engine-level cache (what eager forwards and the sampler
         # graphs use) is saved here and restored after the capture instead of being left pointing into the pool.
         keep = (self._wcache, self._wversion)
-        with torch.cuda.graph(g_f, pool=pool, capture_error_mode="relaxed"):
+        with torch.cuda.graph(g_f, pool=pool, capture_error_mode="thread_local"):
             self._wcache = None
             eps = self.forward(xs, ts, cs, train=True)
         n1 = _lib.launch_count()
@@ -724,7 +725,7 @@ class DenoiserEngine:
         sizes = [q.numel() for _, q in named]
         flat = torch.empty(sum(sizes), dtype=torch.float32, device=x.device)
         views = [v.view(q.shape) for v, (_, q) in zip(flat.split(sizes), named)]
-        with torch.cuda.graph(g_b, pool=pool, capture_error_mode="relaxed"):
+        with torch.cuda.graph(g_b, pool=pool, capture_error_mode="thread_local"):
             grads, g_c = BackwardProgram(self).run(gs)
             # all parameter gradients packed into one flat buffer (parameter registration order): the autograd glue
             # then hands them out with a single copy instead of one per tensor

@@ -232,6 +232,15 @@ TDB_API int tdb_time_film(const int64_t* t, const float* emb_scale, const float*
                   const float* film_b, float* c, float* film, int B, int dim, int film_rows,
                   void* stream);
 
+/* Backward of tdb_time_film (autograd of ddpm.py:447-452, 184/191): from d_film (B, film_rows) = the FiLM scale/shift
+ * gradients of every block, and c (B, dim) = the forward's conditioning vector, the gradients of all FiLM projections
+ * (g_film_w (film_rows, dim), g_film_b (film_rows)) and of the process_c MLP (g_w1 (4dim, dim), g_b1, g_w2 (dim, 4dim),
+ * g_b2).  dc_scratch: (B, dim) floats of workspace (zeroed by the call).  Two launches, no library calls. */
+TDB_API int tdb_time_film_bwd(const int64_t* t, const float* emb_scale, const float* emb_bias, const float* w1,
+                      const float* b1, const float* w2, const float* b2, const float* film_wt, const float* c,
+                      const float* d_film, float* g_film_w, float* g_film_b, float* g_w1, float* g_b1, float* g_w2,
+                      float* g_b2, float* dc_scratch, int B, int dim, int film_rows, void* stream);
+
 /* ---- diffusion process ------------------------------------------------------------------------ */
 
 /* One ancestral sampling update, masked to inside cells, as a single bandwidth-bound

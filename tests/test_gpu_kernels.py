@@ -345,6 +345,38 @@ def test_time_film(lib):
 
 
 # --------------------------------------------------------------------------- encode / decode
+@pytest.mark.parametrize("B", [1, 4, 9])
+def test_time_film_backward_matches_autograd(lib, B):
+    """tdb_time_film_bwd against torch.autograd of the Nyquist embedding -> process_c MLP -> FiLM projections
+    (reference ddpm.py:147-148, 447-452, 184/191)."""
+    dim, rows, T = 32, 2 * (32 + 64 + 64 + 128) + 14, 500
+    g = torch.Generator().manual_seed(17)
+    scale, bias = torch.rand(dim, generator=g) * 0.9 + 0.01, torch.rand(dim, generator=g) * 1.5
+    w1, b1 = torch.randn(4 * dim, dim, generator=g) * 0.2, torch.randn(4 * dim, generator=g) * 0.1
+    w2, b2 = torch.randn(dim, 4 * dim, generator=g) * 0.1, torch.randn(dim, generator=g) * 0.1
+    fw, fb = torch.randn(rows, dim, generator=g) * 0.2, torch.randn(rows, generator=g) * 0.1
+    t = torch.randint(0, T, (B,), generator=g)
+    d_film = torch.randn(B, rows, generator=g)
+    P = [v.double().requires_grad_(True) for v in (w1, b1, w2, b2, fw, fb)]
+    emb = torch.sin(bias.double() + scale.double() * t.double()[:, None])
+    c = F.silu(F.linear(F.silu(F.linear(emb, P[0], P[1])), P[2], P[3]))
+    film = F.linear(c, P[4], P[5])
+    want = torch.autograd.grad(film, P, d_film.double())
+    dev = [v.cuda().contiguous() for v in (t, scale, bias, w1, b1, w2, b2, fw.t().contiguous(), d_film)]
+    c_dev = torch.empty((B, dim), device="cuda")
+    film_dev = torch.empty((B, rows), device="cuda")
+    lib.call("tdb_time_film", dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), dev[3].data_ptr(), dev[4].data_ptr(), dev[5].data_ptr(),
+             dev[6].data_ptr(), dev[7].data_ptr(), fb.cuda().data_ptr(), c_dev.data_ptr(), film_dev.data_ptr(), B, dim, rows, lib.stream_ptr())
+    assert rel_l2(film_dev, film) < 1e-5
+    out = [torch.full(s, 7.0, device="cuda") for s in ((rows, dim), (rows,), (4 * dim, dim), (4 * dim,), (dim, 4 * dim), (dim,), (B, dim))]
+    lib.call("tdb_time_film_bwd", dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), dev[3].data_ptr(), dev[4].data_ptr(),
+             dev[5].data_ptr(), dev[6].data_ptr(), dev[7].data_ptr(), c_dev.data_ptr(), dev[8].data_ptr(), *(o.data_ptr() for o in out), B, dim,
+             rows, lib.stream_ptr())
+    got = {"w1": out[2], "b1": out[3], "w2": out[4], "b2": out[5], "fw": out[0], "fb": out[1]}
+    for name, w in zip(("w1", "b1", "w2", "b2", "fw", "fb"), want):
+        assert rel_l2(got[name], w) < 2e-5, name
+
+
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 def test_encode_decode(lib, prec):
     code, td = _dt(prec)
