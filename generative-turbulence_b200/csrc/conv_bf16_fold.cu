@@ -303,8 +303,7 @@ conv3d_bf16_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                             h0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
                             h1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
                         }
-                        *reinterpret_cast<uint4*>(orow + c) = lo;
-                        *reinterpret_cast<uint4*>(orow + c + 8) = hi;
+                        ptx::st_global_32B(orow + c, lo, hi);
                         if (do_stats) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {

@@ -328,8 +328,7 @@ conv3d_bf16_winp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                     h1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
                 }
                 bf16* orow = out + p * P.ld_out + c;
-                *reinterpret_cast<uint4*>(orow) = lo;
-                *reinterpret_cast<uint4*>(orow + 8) = hi;
+                ptx::st_global_32B(orow, lo, hi);
                 if (do_stats) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {

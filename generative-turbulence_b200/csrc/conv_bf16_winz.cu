@@ -313,8 +313,7 @@ conv3d_bf16_winz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                                                       __uint_as_float(r3[8 + 2 * j + 1]) + s_biasp[c + 8 + 2 * j + 1]);
                     }
                     bf16* prow = out_p + p * P.ld_outp;
-                    *reinterpret_cast<uint4*>(prow + c) = lo;
-                    *reinterpret_cast<uint4*>(prow + c + 8) = hi;
+                    ptx::st_global_32B(prow + c, lo, hi);
                 }
                 float v[16];
 #pragma unroll
@@ -334,8 +333,7 @@ conv3d_bf16_winz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                         h0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
                         h1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
                     }
-                    *reinterpret_cast<uint4*>(orow + c) = lo;
-                    *reinterpret_cast<uint4*>(orow + c + 8) = hi;
+                    ptx::st_global_32B(orow + c, lo, hi);
                     if (do_stats) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {

@@ -241,6 +241,19 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
     return d;
 }
 // Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, dense.
+// 32 contiguous bytes from one thread: ONE 256-bit store (st.global.v8.b32, sm_100) when the address allows it - a full
+// 32-byte sector per thread and half the store instructions of the epilogues' row-strided 16-byte pairs.
+__device__ __forceinline__ void st_global_32B(void* p, const uint4& lo, const uint4& hi) {
+    if ((reinterpret_cast<uintptr_t>(p) & 31u) == 0) {
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
+                     "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                     : "memory");
+    } else {
+        reinterpret_cast<uint4*>(p)[0] = lo;
+        reinterpret_cast<uint4*>(p)[1] = hi;
+    }
+}
+
 __host__ __device__ inline uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
