@@ -48,27 +48,36 @@ class _Denoise(torch.autograd.Function):
     def backward(ctx, g_eps):
         model = ctx.model
         eng = model.engine()
+        from .backward import grad_phase
+
         grads, g_c_local = eng.train_backward(g_eps)
         g_c = None if g_c_local is None else g_c_local.clone()
+        named = list(model.named_parameters())
         if torch.is_tensor(grads):
-            # graph replay: one flat buffer in parameter order; a single copy detaches it from the graph's static memory
+            # graph replay: one flat buffer (phase-1 parameters first); a single copy detaches it from the graph's static
+            # memory.  The data-parallel exchange (parallel.GradientAllReduce.attach) was started by train_backward - the
+            # phase-1 part already while the second backward graph ran - and is completed here.
             tg = eng._train_replay
             if eng.grad_sync is not None:
-                eng.grad_sync(grads)  # data-parallel exchange on the flat buffer (parallel.GradientAllReduce.attach)
-            out = [v.view(shape) for v, shape in zip(grads.clone().split(tg["sizes"]), tg["shapes"])]
-            return (None, None, None, g_c, *out)
-        named = list(model.named_parameters())
+                eng.grad_sync.finish()
+            piece = {n: v.view(shape) for n, v, shape in zip(tg["order"], grads.clone().split(tg["sizes"]), tg["shapes"])}
+            return (None, None, None, g_c, *(piece[n] for n, _ in named))
         for name, _ in named:
             if grads.get(name) is None:
                 raise RuntimeError(f"turbdiff_b200: no gradient produced for parameter {name}")
         if eng.grad_sync is not None:
-            # eager launch programs under data parallelism: the SAME exchange as the graph path (one flat fp32 buffer in
-            # parameter order, same chunking), so ranks may mix the two modes (a rank whose graph capture fell back to the
-            # eager programs must still issue the collectives its peers issue)
-            flat = torch.cat([grads[name].reshape(-1).to(torch.float32) for name, _ in named])
-            eng.grad_sync(flat)
-            out = [v.view(prm.shape).to(prm.dtype) for v, (_, prm) in zip(flat.split([prm.numel() for _, prm in named]), named)]
-            return (None, None, None, g_c, *out)
+            # eager launch programs under data parallelism: the SAME exchange as the graph path (flat fp32 buffers of the
+            # phase-1 and phase-2 parameters, same chunking), so ranks may mix the two modes (a rank whose graph capture
+            # fell back to the eager programs must still issue the collectives its peers issue)
+            out = {}
+            for phase in (1, 2):
+                part = [(n, prm) for n, prm in named if grad_phase(n) == phase]
+                flat = torch.cat([grads[n].reshape(-1).to(torch.float32) for n, _ in part])
+                eng.grad_sync.start(flat)
+                for v, (n, prm) in zip(flat.split([prm.numel() for _, prm in part]), part):
+                    out[n] = v.view(prm.shape).to(prm.dtype)
+            eng.grad_sync.finish()
+            return (None, None, None, g_c, *(out[n] for n, _ in named))
         out = [grads[name].to(prm.dtype).reshape(prm.shape).clone() for name, prm in named]  # the program's buffers are reused by the next step
         return (None, None, None, g_c, *out)
 

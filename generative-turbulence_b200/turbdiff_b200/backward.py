@@ -24,6 +24,15 @@ from ._lib import PW_NOHALO, PW_SILU, call, ptr
 from .engine import GN_EPS, View
 
 
+def grad_phase(name: str) -> int:
+    """1: the gradient of parameter `name` is complete after BackwardProgram.phase1 (decoder, up path, centre);
+    2: after phase2 (down path, encoders, and everything fed by the timestep conditioning - its gradient sums over all
+    blocks).  Data-parallel training exchanges the phase-1 gradients while phase 2 is still running."""
+    late = ("project_onto_scale_shift" in name or name.startswith("process_c") or name.startswith("encode_")
+            or "downsampling_blocks" in name)
+    return 2 if late else 1
+
+
 class BackwardProgram:
     def __init__(self, eng):
         self.eng = eng
@@ -247,11 +256,23 @@ class BackwardProgram:
     # ------------------------------------------------------------------ whole network
     @torch.no_grad()
     def run(self, g_eps: torch.Tensor):
+        """Both phases back to back: (parameter gradients by name, gradient of c_local)."""
+        self.phase1(g_eps)
+        return self.phase2()
+
+    def _join(self):
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)  # every weight gradient issued so far is complete
+            self._readers.clear()
+
+    def phase1(self, g_eps: torch.Tensor):
+        """Decoder, up path and centre: when it returns, every gradient of `grad_phase(name) == 1` parameters is complete
+        (data-parallel training exchanges them while phase 2 runs)."""
         eng, m = self.eng, self.m
         key = eng._last_train_key
         if key is None or key not in eng._plans:
             raise RuntimeError("turbdiff_b200: backward called without a preceding forward(train=True)")
-        p = eng._plans[key]
+        p = self.p = eng._plans[key]
         x_in, t, c_local = p["last_input"]
         B, F = x_in.shape[:2]
         X, Y, Z = x_in.shape[2:]
@@ -264,8 +285,8 @@ class BackwardProgram:
         self.side = eng.side_stream(dev) if eng.wgrad_side_stream else None
         self._readers = {}
         g_eps = g_eps.to(torch.float32).contiguous()
-        grads: dict[str, torch.Tensor] = {}
-        d_film = torch.zeros((B, eng.film_rows), dtype=torch.float32, device=dev)
+        grads = self.grads = {}
+        d_film = self.d_film = torch.zeros((B, eng.film_rows), dtype=torch.float32, device=dev)
         self.prefix = {"decode0": "decode.0", "center0": "u_net.center_block.0", "center2": "u_net.center_block.2"}
         for i in range(L):
             self.prefix[f"down{i}"] = f"u_net.downsampling_blocks.{i}"
@@ -304,7 +325,19 @@ class BackwardProgram:
         # centre
         g = self._resblock_bwd(p, "center2", g, grads, d_film)
         g = self._attention_bwd(p, g, grads)
-        g = self._resblock_bwd(p, "center0", g, grads, d_film)
+        self.g = self._resblock_bwd(p, "center0", g, grads, d_film)
+        self._join()
+
+    def phase2(self):
+        """Down path, encoders, timestep MLP / FiLM projections.  Returns (all parameter gradients by name, gradient of c_local)."""
+        eng, m, p, grads, d_film, g = self.eng, self.m, self.p, self.grads, self.d_film, self.g
+        x_in, t, c_local = p["last_input"]
+        B, F = x_in.shape[:2]
+        X, Y, Z = x_in.shape[2:]
+        L = m.u_net_levels
+        dev = x_in.device
+        s = _lib.stream_ptr
+        dt = eng.dt
         # down path (reverse): skip gradient + gradient through the downsampling
         for l in reversed(range(L)):
             g_skip = p["g_skip"][l]
@@ -313,7 +346,6 @@ class BackwardProgram:
             # skip gradient += gradient through the down-sampling, in one pass (no temporary grid, no separate add)
             call("tdb_trilinear_bwd", g.ptr, g.ld, Xo, Yo, Zo, g_skip.ptr, g_skip.ld, Xi, Yi, Zi, B, g_skip.C, dt, _lib.TRIBWD_ACCUMULATE, s())
             g = self._resblock_bwd(p, f"down{l}", g_skip, grads, d_film)
-
         # encoders (g = folded gradient of xin0: [encode_x | encode_c_local])
         dim, Fc = m.dim, m.c_local_features
         nvox = X * Y * Z
@@ -359,7 +391,5 @@ class BackwardProgram:
             grads[f"{self.prefix[n]}.project_onto_scale_shift.weight"] = g_film_w[off : off + rows]
             grads[f"{self.prefix[n]}.project_onto_scale_shift.bias"] = g_film_b[off : off + rows]
             off += rows
-        if self.side is not None:
-            torch.cuda.current_stream().wait_stream(self.side)  # join: every weight gradient is complete
-            self._readers.clear()
+        self._join()
         return grads, g_c_local

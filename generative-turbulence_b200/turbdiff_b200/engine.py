@@ -681,13 +681,22 @@ class DenoiserEngine:
 
     def train_backward(self, g_eps):
         """Backward of the last train_forward: (parameter gradients, gradient of c_local).  Eager mode returns the
-        gradients as a dict by parameter name; graph mode returns ONE flat fp32 buffer holding them in parameter
-        registration order (self._train_replay["sizes"] / ["shapes"] describe the split)."""
+        gradients as a dict by parameter name; graph mode returns ONE flat fp32 buffer holding them in the order
+        self._train_replay["order"] (phase-1 parameters first, see backward.grad_phase; ["sizes"] / ["shapes"] describe the
+        split).  With a data-parallel hook attached (self.grad_sync) the exchange of the phase-1 gradients is started
+        between the two backward graphs, so it travels while the down path is still being differentiated; the caller
+        finishes it with grad_sync.finish()."""
         tg = self._train_replay
         if tg is None:
             return self.backward(g_eps)
         tg["g_eps"].copy_(g_eps)
+        sync = self.grad_sync
         tg["bwd"].replay()
+        if sync is not None:
+            sync.start(tg["flat"][: tg["n1"]])
+        tg["bwd2"].replay()
+        if sync is not None:
+            sync.start(tg["flat"][tg["n1"] :])
         self.replayed_launches += tg["n_bwd"]
         return tg["flat"], tg["g_c_local"]
 
@@ -720,21 +729,39 @@ class DenoiserEngine:
         with torch.cuda.graph(g_f, pool=pool, capture_error_mode="thread_local"):
             self._wcache = None
             eps = self.forward(xs, ts, cs, train=True)
-        n1 = _lib.launch_count()
-        named = list(self.model.named_parameters())
-        sizes = [q.numel() for _, q in named]
+        n_l1 = _lib.launch_count()
+        from .backward import grad_phase
+
+        # flat gradient buffer: phase-1 parameters (decoder, up path, centre) first, then phase 2 - each phase's gradients are
+        # packed at the end of ITS graph, so a data-parallel exchange of the first part overlaps the second graph
+        by_name = dict(self.model.named_parameters())
+        order = [n for n in by_name if grad_phase(n) == 1] + [n for n in by_name if grad_phase(n) == 2]
+        sizes = [by_name[n].numel() for n in order]
+        n1 = sum(by_name[n].numel() for n in order if grad_phase(n) == 1)
         flat = torch.empty(sum(sizes), dtype=torch.float32, device=x.device)
-        views = [v.view(q.shape) for v, (_, q) in zip(flat.split(sizes), named)]
+        views = {n: v.view(by_name[n].shape) for v, n in zip(flat.split(sizes), order)}
+        g_b2 = torch.cuda.CUDAGraph()
+        bp = BackwardProgram(self)
         with torch.cuda.graph(g_b, pool=pool, capture_error_mode="thread_local"):
-            grads, g_c = BackwardProgram(self).run(gs)
-            # all parameter gradients packed into one flat buffer (parameter registration order): the autograd glue
-            # then hands them out with a single copy instead of one per tensor
-            torch._foreach_copy_(views, [grads[n].reshape(q.shape) for n, q in named])
+            bp.phase1(gs)
+            first = [n for n in order if grad_phase(n) == 1]
+            missing = [n for n in first if n not in bp.grads]
+            if missing:
+                raise RuntimeError(f"turbdiff_b200: phase 1 of the backward program left no gradient for {missing[:3]}")
+            # all gradients of this phase packed into the flat buffer: the autograd glue then hands them out with a single
+            # copy instead of one per tensor
+            torch._foreach_copy_([views[n] for n in first], [bp.grads[n].reshape(by_name[n].shape) for n in first])
+        with torch.cuda.graph(g_b2, pool=pool, capture_error_mode="thread_local"):
+            grads, g_c = bp.phase2()
+            second = [n for n in order if grad_phase(n) == 2]
+            torch._foreach_copy_([views[n] for n in second], [grads[n].reshape(by_name[n].shape) for n in second])
         n2 = _lib.launch_count()
         pool_w = self._wcache  # kept alive by the returned record: the graphs hold raw addresses into it
         self._wcache, self._wversion = keep
         self._wgen += 1
-        return {"sig": sig, "n_fwd": n1 - n0, "n_bwd": n2 - n1, "flat": flat, "sizes": sizes, "shapes": [q.shape for _, q in named], "x": xs, "t": ts, "c": cs, "g_eps": gs, "eps": eps, "fwd": g_f, "bwd": g_b, "grads": grads, "g_c_local": g_c, "pool_w": pool_w}
+        return {"sig": sig, "n_fwd": n_l1 - n0, "n_bwd": n2 - n_l1, "flat": flat, "order": order, "sizes": sizes, "n1": n1,
+                "shapes": [by_name[n].shape for n in order], "x": xs, "t": ts, "c": cs, "g_eps": gs, "eps": eps, "fwd": g_f, "bwd": g_b,
+                "bwd2": g_b2, "grads": grads, "g_c_local": g_c, "pool_w": pool_w}
 
     @staticmethod
     def to_ncdhw(v: View) -> torch.Tensor:

@@ -97,36 +97,61 @@ class GradientAllReduce:
 
     # ---- fast path: all-reduce the backward program's flat gradient buffer ----------------------------------------
     def attach(self, denoiser):
-        """Reduce `denoiser`'s gradients inside its backward (engine.grad_sync hook).  Returns self."""
+        """Reduce `denoiser`'s gradients inside its backward (engine.grad_sync hook: ``start(flat_part)`` is called once the
+        phase-1 gradients are complete and again after phase 2, ``finish()`` before the gradients are handed to autograd).
+        Returns self."""
         eng = denoiser.engine()
         ids = {id(p) for p in denoiser.parameters()}
+        outer = self
 
-        def sync(flat: torch.Tensor):
-            if self._world() == 1:
-                return
-            self.reduce_flat(flat)
-            self._flat_synced |= ids
+        class _Hook:
+            def __init__(self):
+                self.pending = []
 
-        eng.grad_sync = sync
+            def start(self, flat: torch.Tensor):
+                if outer._world() > 1 and flat.numel() > 0:
+                    self.pending.append(outer.start_flat(flat))
+
+            def finish(self):
+                for item in self.pending:
+                    outer.finish_flat(item)
+                self.pending = []
+                if outer._world() > 1:
+                    outer._flat_synced |= ids
+
+            def __call__(self, flat: torch.Tensor):  # whole buffer at once
+                self.start(flat)
+                self.finish()
+
+        eng.grad_sync = _Hook()
         self._attached.append(denoiser)
         return self
 
     def _world(self):
         return dist.get_world_size(self.group) if dist.is_initialized() else 1
 
-    def reduce_flat(self, flat: torch.Tensor):
-        """In-place average of a flat gradient buffer over the group: `flat_chunks` asynchronous all-reduces (the first
-        slices travel while the later ones are being enqueued), then one stream-ordered wait."""
-        world = self._world()
+    def start_flat(self, flat: torch.Tensor):
+        """Start the in-place average of a flat gradient buffer over the group: asynchronous all-reduces over chunks of
+        ~1/flat_chunks of the denoiser's gradients (the first chunks travel while the later ones are being enqueued and,
+        for the phase-1 part, while the rest of the backward pass runs)."""
         avg = dist.get_backend(self.group) == "nccl"
         n = flat.numel()
-        step = -(-n // self.flat_chunks)
+        total = sum(p.numel() for d in self._attached for p in d.parameters()) or n
+        step = max(1, -(-total // self.flat_chunks))
         work = [dist.all_reduce(flat[i : i + step], op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.group, async_op=True)
                 for i in range(0, n, step)]
+        return flat, work, avg
+
+    def finish_flat(self, item):
+        flat, work, avg = item
         for w in work:
             w.wait()
         if not avg:
-            flat.div_(world)
+            flat.div_(self._world())
+
+    def reduce_flat(self, flat: torch.Tensor):
+        """In-place average of a flat gradient buffer over the group (start_flat + finish_flat)."""
+        self.finish_flat(self.start_flat(flat))
 
     # ---- generic path --------------------------------------------------------------------------------------------
     def __call__(self):

@@ -77,6 +77,13 @@ def _worker(rank, world, port, ret):
         other.grad = torch.full((4,), float(rank))
         red()                                               # must not reduce den's gradients a second time
         ok = ok and torch.allclose(den.a.grad, flat[:5]) and torch.allclose(other.grad, torch.full((4,), (world - 1) / 2))
+        # split exchange: the phase-1 part is started while the backward pass still runs, the rest afterwards, one finish
+        flat2 = torch.arange(11.0) * (rank + 1)
+        hook = den.engine().grad_sync
+        hook.start(flat2[:4])
+        hook.start(flat2[4:])
+        hook.finish()
+        ok = ok and torch.allclose(flat2, torch.arange(11.0) * (sum(range(1, world + 1)) / world)) and not hook.pending
         # gather of sharded "samples" restores the original order on rank 0
         full = torch.arange(10.0).reshape(5, 2)
         mine = full[shard_range(5, rank, world).start : shard_range(5, rank, world).stop]
