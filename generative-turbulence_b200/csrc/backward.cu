@@ -1151,11 +1151,13 @@ int tdb_pointwise_bwd_reduce(const void* g_out, int ld_g, const void* raw, int l
                 TDB_E_UNSUPPORTED, "tdb_pointwise_bwd_reduce: C/ld must be multiples of %d", n);
     if (G < 1) G = 1;
     Grid3 gr(B, X, Y, Z);
-    const int chunks = C / n;
     // blocks per sample: every block ends with 4*C double atomics into red[] (~6.5 G/s device-wide, measured), so a block
     // streams at least ~512 KB of its two inputs; the coarse levels then run on a few dozen blocks instead of 148 per sample
+    // - but on at least 8 (one trip each on the smallest grids: a lone block per sample walks its voxels serially)
     const int64_t bytes_per_sample = (int64_t)X * Y * Z * C * (dtype == TDB_BF16 ? 2 : 4) * 2;
     int64_t blocks = ceil_div(bytes_per_sample, 512 * 1024);
+    const int64_t trips = ceil_div((int64_t)X * Y * Z, (int64_t)(kThreads / (C / n)) * 4);
+    if (blocks < 8) blocks = trips < 8 ? trips : 8;
     const int64_t cap = (148 * 4) / (B < 1 ? 1 : B) < 1 ? 1 : (148 * 4) / (B < 1 ? 1 : B);
     if (blocks > cap) blocks = cap;
     dim3 grid((unsigned)blocks, (unsigned)B);
