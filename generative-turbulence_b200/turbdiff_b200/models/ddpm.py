@@ -433,7 +433,13 @@ class GaussianDiffusion(nn.Module):
         if rng is None:
             rng = st["rng_stream"] = torch.cuda.Stream(device=dev)
         side_rng = os.environ.get("TURBDIFF_B200_RNG_STREAM", "1") != "0"
+        # the host may run at most `ahead` steps in front of the device: every step allocates two noise tensors (the
+        # reference's torch.randn_like calls, 62 MB each at B = 8), and an unthrottled loop would queue hundreds of them
+        # (cudaMalloc storms, tens of GB held) before the first step has run
+        ahead, done = 3, []
         for t in steps:
+            if len(done) >= ahead:
+                done.pop(0).synchronize()
             t_dev.fill_(t)
             t_vec.fill_(t)
             if t > 0 and not side_rng:
@@ -463,6 +469,9 @@ class GaussianDiffusion(nn.Module):
                 zz = cur if z is None else z
                 call("tdb_ddpm_step", cur.data_ptr(), eps.data_ptr(), zz.data_ptr(), ptr(z_bc if z_bc is not None else (cur if self.noise_bcs else None)),
                      x_bcs.data_ptr(), mask.data_ptr(), coef.data_ptr(), t_dev.data_ptr(), cur.data_ptr(), B, F, nvox, step_flags, s())
+            ev = torch.cuda.Event()
+            ev.record(main)
+            done.append(ev)
         x_t = cur
         out = x_t.clone()  # outputs are freshly allocated; the state buffer is reused by the next chain
         if T == 0:

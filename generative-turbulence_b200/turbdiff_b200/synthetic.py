@@ -67,12 +67,14 @@ def synthetic_inputs(batch: int, seed: int, cells=CELLS, pillar=PILLAR):
 
 
 def conv_flops_per_sample(spatial, dim: int = 32, levels: int = 4, in_features: int = 4, c_local_features: int = 4, out_features: int = 4,
-                          attn_hidden: int = 128) -> float:
+                          attn_hidden: int = 128, haloed: bool = False) -> float:
     """Algorithmic FLOPs of one denoiser forward: 2*Cin*Cout*k^3*voxels over every 3x3x3 and 1x1x1 convolution
-    (666.2 GFLOP at the shapes configuration)."""
+    (666.2 GFLOP at the shapes configuration).  haloed=True counts the rows the implicit-GEMM kernels actually process:
+    the GEMM's M dimension runs over the halo grids ((X+2)(Y+2)(Z+2) rows per level), whose halo rows are computed and
+    discarded - 9 % more work at level 0, 3.2x at the 12x3x3 bottleneck."""
     from .engine import level_sizes
 
-    vox = [int(np.prod(s)) for s in level_sizes(tuple(spatial), levels)]
+    vox = [int(np.prod([d + 2 for d in s] if haloed else s)) for s in level_sizes(tuple(spatial), levels)]
 
     def block(cin, cout, lvl):
         f = 2.0 * 27 * vox[lvl] * (cin * cout + cout * cout)
