@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--timesteps", type=int, default=1000, help="T of the sampled chain (BASELINE configs[2]: 1000)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--e2e-steps", type=int, default=16, help="chain length of one end-to-end public-API call")
-    ap.add_argument("--train-steps", type=int, default=5, help="timed training steps (configs[1]/[3]: fwd+bwd+all-reduce+optimizer); 0 = skip")
+    ap.add_argument("--train-steps", type=int, default=20, help="timed training steps (configs[1]/[3]: fwd+bwd+all-reduce+optimizer); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the gpu_reference block (the reference under torch eager on this GPU)")
     ap.add_argument("--ref-mode", default="tf32", choices=["tf32", "bf16", "fp32"], help="--impl reference-gpu: TF32 (the reference's "
