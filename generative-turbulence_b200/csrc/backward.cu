@@ -919,7 +919,8 @@ trilinear_bwd_walk_kernel(const T* __restrict__ g_out, int ld_g, Grid3 go, T* __
 }
 
 // ---------------------------------------------------------------- attention backward
-// One CTA per (sample, head); q,k,v,dO and the S x S probability / score-gradient matrices live in smem.
+// ATT_SPLIT CTAs per (sample, head); q,k,v,dO and the S x S probability / score-gradient matrices live in smem.
+constexpr int ATT_SPLIT = 4;
 template <typename T>
 __global__ void __launch_bounds__(256)
 attention_bwd_kernel(const T* __restrict__ qkv, int ld_qkv, const T* __restrict__ d_out, int ld_do, T* __restrict__ d_qkv,
@@ -932,7 +933,10 @@ attention_bwd_kernel(const T* __restrict__ qkv, int ld_qkv, const T* __restrict_
     float* sdo = sv + (size_t)S * (DH + 1);
     float* sp = sdo + (size_t)S * (DH + 1);  // [S][S+1] probabilities
     float* sds = sp + (size_t)S * (S + 1);   // [S][S+1] dS
-    const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+    // ATT_SPLIT CTAs per (sample, head): each recomputes the (cheap) probability / score-gradient rows and produces a
+    // quarter of the dQ / dK / dV elements - the kernel sits on the critical path of the backward walk with B * heads CTAs
+    const int bh = blockIdx.x / ATT_SPLIT, part = blockIdx.x % ATT_SPLIT;
+    const int b = bh / heads, h = bh % heads;
     const int hid = heads * DH;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nwarps = blockDim.x / 32;
     const float scale = rsqrtf((float)DH);
@@ -985,7 +989,8 @@ attention_bwd_kernel(const T* __restrict__ qkv, int ld_qkv, const T* __restrict_
     }
     __syncthreads();
     // dQ[i] = sum_j dS[i][j] K[j];  dK[j] = sum_i dS[i][j] Q[i];  dV[j] = sum_i P[i][j] dO[i]
-    for (int idx = threadIdx.x; idx < S * DH; idx += blockDim.x) {
+    const int per = (S * DH + ATT_SPLIT - 1) / ATT_SPLIT;
+    for (int idx = part * per + threadIdx.x; idx < min(S * DH, (part + 1) * per); idx += blockDim.x) {
         const int s = idx / DH, d = idx % DH;
         float dq = 0.0f, dk = 0.0f, dv = 0.0f;
         for (int j = 0; j < S; ++j) {
@@ -1358,12 +1363,12 @@ int tdb_attention_bwd(const void* qkv, int ld_qkv, const void* d_out, int ld_do,
     if (dtype == TDB_BF16) {
         e = cudaFuncSetAttribute(attention_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess)
-            attention_bwd_kernel<bf16><<<B * heads, 256, smem, s>>>((const bf16*)qkv, ld_qkv, (const bf16*)d_out, ld_do, (bf16*)d_qkv, ld_dq,
+            attention_bwd_kernel<bf16><<<B * heads * ATT_SPLIT, 256, smem, s>>>((const bf16*)qkv, ld_qkv, (const bf16*)d_out, ld_do, (bf16*)d_qkv, ld_dq,
                                                                     g, heads, S);
     } else {
         e = cudaFuncSetAttribute(attention_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess)
-            attention_bwd_kernel<float><<<B * heads, 256, smem, s>>>((const float*)qkv, ld_qkv, (const float*)d_out, ld_do, (float*)d_qkv,
+            attention_bwd_kernel<float><<<B * heads * ATT_SPLIT, 256, smem, s>>>((const float*)qkv, ld_qkv, (const float*)d_out, ld_do, (float*)d_qkv,
                                                                      ld_dq, g, heads, S);
     }
     TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_attention_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -320,6 +320,27 @@ def test_attention(lib, prec, spatial):
     assert rel_l2(from_halo(out), want) < (2e-6 if prec == "fp32" else 5e-3)
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("spatial", [(12, 3, 3), (8, 4, 4), (5, 3, 2)])
+def test_attention_backward_matches_autograd(lib, prec, spatial):
+    """tdb_attention_bwd against torch.autograd of scaled_dot_product_attention (reference attention.py:9-15)."""
+    code, td = _dt(prec)
+    X, Y, Z = spatial
+    B, heads, dh = 3, 4, 32
+    hid, S = heads * dh, X * Y * Z
+    qkv = gen(B, 3 * hid, X, Y, Z, seed=10).to(td).float()
+    go = gen(B, hid, X, Y, Z, seed=11).to(td).float()
+    qd = qkv.double().cpu().requires_grad_(True)
+    q, k, v = (qd[:, i * hid : (i + 1) * hid].reshape(B, heads, dh, S).transpose(2, 3) for i in range(3))
+    o = F.scaled_dot_product_attention(q, k, v).transpose(2, 3).reshape(B, hid, X, Y, Z)
+    (want,) = torch.autograd.grad(o, qd, go.double().cpu())
+    qg, gg = to_halo(qkv, dtype=td), to_halo(go, dtype=td)
+    d_qkv = torch.zeros((B, X + 2, Y + 2, Z + 2, 3 * hid), device="cuda", dtype=td)
+    lib.call("tdb_attention_bwd", qg.data_ptr(), 3 * hid, gg.data_ptr(), hid, d_qkv.data_ptr(), 3 * hid, B, X, Y, Z, heads, dh, code,
+             lib.stream_ptr())
+    assert rel_l2(from_halo(d_qkv), want) < (5e-6 if prec == "fp32" else 8e-3)
+
+
 def test_time_film(lib):
     from oracle.unet_ref import UNetSpec, process_time, synth_state_dict
 
