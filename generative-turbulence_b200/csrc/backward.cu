@@ -780,6 +780,7 @@ trilinear_bwd_kernel(const T* __restrict__ g_out, int ld_g, Grid3 go, T* __restr
 // 4^3 reads per voxel for the adjoint of the 2x upsampling) and nothing is re-derived per voxel.  accumulate: d_in +=
 // (halo rows untouched) - the skip connection's gradient is added in the same pass.
 constexpr int TB_S = 6;  // sources per axis (scale >= 0.4: at most ceil(2 / scale) + 1)
+constexpr int TB_G = 4;  // z sources fetched per group (predicated-off slots still cost issue slots)
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 3)
@@ -884,15 +885,15 @@ trilinear_bwd_walk_kernel(const T* __restrict__ g_out, int ld_g, Grid3 go, T* __
             const T* gy = gx + ty[a] * ld_g;
             const float wya = __int_as_float(ty[TB_S + a]);
 #pragma unroll
-            for (int k0 = 0; k0 < TB_S; k0 += 3) {  // three loads in flight (six would cost the occupancy they are meant to replace)
+            for (int k0 = 0; k0 < TB_S; k0 += TB_G) {  // TB_G loads in flight: the 2x up-sampling has 4 sources per axis almost everywhere
                 if (k0 >= nz) break;
-                uint4 raw[3];
+                uint4 raw[TB_G];
 #pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    if (k0 + k < nz) raw[k] = Vec<T>::load_raw(gy + zoff[k0 + k]);
+                for (int k = 0; k < TB_G; ++k)
+                    if (k0 + k < TB_S && k0 + k < nz) raw[k] = Vec<T>::load_raw(gy + zoff[k0 + k]);
 #pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    if (k0 + k < nz) {
+                for (int k = 0; k < TB_G; ++k)
+                    if (k0 + k < TB_S && k0 + k < nz) {
                         float v[N];
                         Vec<T>::unpack(raw[k], v);
                         const float w = wya * wz[k0 + k];
@@ -1163,6 +1164,10 @@ int tdb_pointwise_bwd_reduce(const void* g_out, int ld_g, const void* raw, int l
     int64_t blocks = ceil_div(bytes_per_sample, 512 * 1024);
     const int64_t trips = ceil_div((int64_t)X * Y * Z, (int64_t)(kThreads / (C / n)) * 4);
     if (blocks < 8) blocks = trips < 8 ? trips : 8;
+    // whole waves: the kernel runs two blocks per SM (128 registers), so more than one wave's worth is rounded down to a
+    // multiple of it (124 blocks per sample at 32 channels were 1.7 waves)
+    const int64_t per_wave = (148 * 2) / (B < 1 ? 1 : B) < 1 ? 1 : (148 * 2) / (B < 1 ? 1 : B);
+    if (blocks > per_wave) blocks = (blocks / per_wave) * per_wave;
     const int64_t cap = (148 * 4) / (B < 1 ? 1 : B) < 1 ? 1 : (148 * 4) / (B < 1 ? 1 : B);
     if (blocks > cap) blocks = cap;
     dim3 grid((unsigned)blocks, (unsigned)B);
