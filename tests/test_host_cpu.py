@@ -256,3 +256,23 @@ def test_pipeline_host_read_matches_reference_read_data():
     out = np.full((8, 7, 4), 5.0, dtype=np.float32)
     view = read_channels_last([(H5Like(u), 3), (H5Like(p), 1)], idxs, out=out)
     assert np.array_equal(view, want) and np.all(out[6:] == 5.0)
+
+
+def test_gradient_phases_partition_the_state_dict():
+    """backward.grad_phase splits the 139 parameters into the part that is complete after the decoder / up path / centre
+    (exchanged while the rest of the backward pass runs) and the late part: down path, encoders and everything fed by the
+    timestep conditioning (its gradient sums over ALL blocks, so it is only complete at the very end)."""
+    from turbdiff_b200 import DenoisingModel
+    from turbdiff_b200.backward import grad_phase
+
+    m = DenoisingModel(in_features=4, out_features=4, c_local_features=4, c_global_features=0, timesteps=10, dim=16, u_net_levels=2,
+                       norm_type="group")
+    names = [n for n, _ in m.named_parameters()]
+    late = [n for n in names if grad_phase(n) == 2]
+    early = [n for n in names if grad_phase(n) == 1]
+    assert sorted(late + early) == sorted(names) and late and early
+    assert all("downsampling_blocks" in n or "project_onto_scale_shift" in n or n.startswith(("process_c", "encode_")) for n in late)
+    assert not any("downsampling_blocks" in n or "project_onto_scale_shift" in n or n.startswith(("process_c", "encode_")) for n in early)
+    # every FiLM projection is late, including those of phase-1 blocks
+    assert "decode.0.project_onto_scale_shift.weight" in late and "decode.0.block1.conv.weight" in early
+    assert "u_net.center_block.1.fn.fn.to_qkv.weight" in early and "decode.1.weight" in early
