@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--train-batch", type=int, default=4, help="samples per GPU per training step (configs[1]: batch 4)")
     ap.add_argument("--timesteps", type=int, default=1000, help="T of the sampled chain (BASELINE configs[2]: 1000)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--e2e-steps", type=int, default=16, help="chain length of one end-to-end public-API call")
+    ap.add_argument("--e2e-steps", type=int, default=64, help="chain length of one end-to-end public-API call")
     ap.add_argument("--train-steps", type=int, default=20, help="timed training steps (configs[1]/[3]: fwd+bwd+all-reduce+optimizer); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the gpu_reference block (the reference under torch eager on this GPU)")
@@ -423,7 +423,7 @@ def run_ours(args):
 
     e2e_call()
     barrier()
-    reps = 4
+    reps = 2
     e0.record()
     for _ in range(reps):
         e2e_call()
