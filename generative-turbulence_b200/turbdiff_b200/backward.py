@@ -61,8 +61,7 @@ class BackwardProgram:
         eng = self.eng
         cache = eng._wcache.setdefault("dgrad", {})
         if key not in cache:
-            wt = conv.weight.detach().flip(2, 3, 4).transpose(0, 1)  # (Cin, Cout, k, k, k): "Cout'" = Cin, "Cin'" = Cout
-            cache[key] = eng.pack_conv(wt, level)
+            cache[key] = eng.pack_conv(conv.weight.detach(), level, dgrad=True)  # (Cin, Cout, k, k, k): "Cout'" = Cin, "Cin'" = Cout
         return cache[key]
 
     def _fold(self, p, g: View):

@@ -196,15 +196,29 @@ class DenoiserEngine:
             return "win" if (self.win and zp <= 63) else "fold2"
         return None
 
-    def pack_conv(self, wt, level):
-        """Kernel layout of a (Cout, Cin, k, k, k) weight for the kernel fold_kind() selects at `level`."""
+    def pack_conv(self, wt, level, dgrad: bool = False):
+        """Kernel layout of a (Cout, Cin, k, k, k) weight for the kernel fold_kind() selects at `level`.  dgrad=True: the
+        weights of the input-gradient convolution, W'[ci][co][k] = W[co][ci][2-k] (logical Cout' = Cin, Cin' = Cout).
+        bf16 path on CUDA: one launch of tdb_pack_conv_weights per weight, straight from the fp32 parameter (as torch ops
+        this was a strided permute copy, a flip and a cast per weight: 178 launches per training step)."""
         cout, cin = wt.shape[:2]
         taps = wt.shape[2] * wt.shape[3] * wt.shape[4]
+        lo, li = (cin, cout) if dgrad else (cout, cin)  # logical output / input channels of the packed matrix
+        folded = self.precision == "bf16" and self.fold_kind(taps, li, lo, level) not in (None, "win")
+        tile = lo if lo < 128 else 128
+        if self.precision == "bf16" and wt.is_cuda and wt.dtype == torch.float32 and taps in (1, 27):
+            src = wt.detach().contiguous()
+            dst = torch.empty((3 * lo, 9 * li) if folded else (lo, taps * li), dtype=torch.bfloat16, device=wt.device)
+            call("tdb_pack_conv_weights", src.data_ptr(), dst.data_ptr(), cout, cin, taps, 1 if folded else 0, tile, 1 if dgrad else 0,
+                 _lib.stream_ptr())
+            return dst
+        if dgrad:
+            wt = wt.flip(2, 3, 4).transpose(0, 1)
+            cout, cin = lo, li
         if self.precision == "fp32":
             return wt.permute(2, 3, 4, 1, 0).reshape(taps, cin, cout).contiguous().float()
-        if self.fold_kind(taps, cin, cout, level) not in (None, "win"):
+        if folded:
             # kz folded into N, N tiles of <= 128 channels: row = (tile*3 + kz)*T + co, col = (kx*3+ky)*Cin + ci
-            tile = cout if cout < 128 else 128
             return (wt.reshape(cout // tile, tile, cin, 3, 3, 3).permute(0, 5, 1, 3, 4, 2)
                     .reshape(3 * cout, 9 * cin).contiguous().to(torch.bfloat16))
         return wt.permute(0, 2, 3, 4, 1).reshape(cout, taps * cin).contiguous().to(torch.bfloat16)

@@ -220,6 +220,14 @@ TDB_API int tdb_trilinear(const void* in, int ld_in, int Xi, int Yi, int Zi, voi
 TDB_API int tdb_attention(const void* qkv, int ld_qkv, void* out, int ld_out, int B, int X, int Y, int Z,
                   int heads, int dh, int dtype, void* stream);
 
+/* bf16 kernel-layout copy of one convolution weight straight from the fp32 parameter (reference layout (Cout, Cin, kD, kH, kW),
+ * nn.Conv3d at ddpm.py:164,188), one launch, no intermediates.  taps = 27 or 1.  folded = 0: per-tap layout [O][taps*I]
+ * (tdb_conv3d_bf16, _win); folded = 1: kz-folded [3*O][9*I] in N tiles of tile_n rows (_fold, _fold2, _winz, _winp).
+ * transpose = 1: the weights of the input-gradient convolution, W'[o = ci][i = co][tap] = W[co][ci][26 - tap]
+ * (O = Cin, I = Cout); transpose = 0: the forward weights (O = Cout, I = Cin). */
+TDB_API int tdb_pack_conv_weights(const float* w, void* dst, int Cout, int Cin, int taps, int folded, int tile_n,
+                          int transpose, void* stream);
+
 /* ---- timestep conditioning ------------------------------------------------------------------ */
 
 /* Nyquist embedding -> process_c MLP -> all FiLM projections of the network in one call

@@ -757,6 +757,30 @@ def test_conv3d_bf16_row_window_add1x1(lib, case):
     assert rel_l2(out.permute(0, 4, 1, 2, 3).float(), full) < 4e-3
 
 
+@pytest.mark.parametrize("cout,cin,taps", [(64, 64, 27), (32, 128, 27), (512, 256, 27), (16, 16, 27), (48, 80, 27), (384, 512, 1), (32, 128, 1)])
+@pytest.mark.parametrize("transpose", [0, 1])
+@pytest.mark.parametrize("folded", [0, 1])
+def test_pack_conv_weights_matches_the_torch_layouts(lib, cout, cin, taps, transpose, folded):
+    """tdb_pack_conv_weights: bf16 kernel layouts (per-tap / kz-folded, forward / tap-reversed transpose for input gradients)
+    bit-identical to the torch permute + flip + cast sequence they replace."""
+    if folded and taps != 27:
+        pytest.skip("the kz-folded layout exists for 3x3x3 weights only")
+    k = 3 if taps == 27 else 1
+    w = gen(cout, cin, k, k, k, seed=77)
+    wl = w.flip(2, 3, 4).transpose(0, 1) if transpose else w  # logical (O, I, k, k, k)
+    O, I = wl.shape[:2]
+    tile = O if O < 128 else 128
+    if folded and O % tile:
+        pytest.skip("N tile does not divide the channel count")
+    if folded:
+        want = wl.reshape(O // tile, tile, I, 3, 3, 3).permute(0, 5, 1, 3, 4, 2).reshape(3 * O, 9 * I).contiguous().to(torch.bfloat16)
+    else:
+        want = wl.permute(0, 2, 3, 4, 1).reshape(O, taps * I).contiguous().to(torch.bfloat16)
+    got = torch.full_like(want, 7.0)
+    lib.call("tdb_pack_conv_weights", w.data_ptr(), got.data_ptr(), cout, cin, taps, folded, tile, transpose, lib.stream_ptr())
+    assert torch.equal(got, want)
+
+
 # --------------------------------------------------------------------------- fused scatter/normalise, gather/de-normalise
 @pytest.mark.parametrize("B", [1, 3])
 def test_scatter_normalize_and_gather_denormalize(lib, B):
