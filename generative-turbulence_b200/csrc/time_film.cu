@@ -72,17 +72,28 @@ time_film_bwd_rows_kernel(const float* __restrict__ d_film, const float* __restr
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const bool on = r < film_rows;
     float gb = 0.0f;
-    for (int k = 0; k < dim; ++k) {
-        const float w = on ? film_wt[(int64_t)k * film_rows + r] : 0.0f;
-        float gw = 0.0f;
-        for (int b = 0; b < B; ++b) {
-            const float d = on ? d_film[(int64_t)b * film_rows + r] : 0.0f;  // (L1-resident after the first k)
-            gw = fmaf(d, sc[b * dim + k], gw);
-            const float part = warp_sum(d * w);
-            if ((threadIdx.x & 31) == 0) atomicAdd(&sdc[b * dim + k], part);
-            if (k == 0) gb += d;
+    constexpr int KU = 8;  // film_wt loads in flight (the k loop used to be a chain of dependent-latency loads)
+    for (int k0 = 0; k0 < dim; k0 += KU) {
+        float w[KU], gw[KU];
+#pragma unroll
+        for (int u = 0; u < KU; ++u) {
+            w[u] = (on && k0 + u < dim) ? film_wt[(int64_t)(k0 + u) * film_rows + r] : 0.0f;
+            gw[u] = 0.0f;
         }
-        if (on) g_film_w[(int64_t)r * dim + k] = gw;
+        for (int b = 0; b < B; ++b) {
+            const float d = on ? d_film[(int64_t)b * film_rows + r] : 0.0f;  // (L1-resident after the first trip)
+            if (k0 == 0) gb += d;
+#pragma unroll
+            for (int u = 0; u < KU; ++u) {
+                if (k0 + u >= dim) break;
+                gw[u] = fmaf(d, sc[b * dim + k0 + u], gw[u]);
+                const float part = warp_sum(d * w[u]);
+                if ((threadIdx.x & 31) == 0) atomicAdd(&sdc[b * dim + k0 + u], part);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < KU; ++u)
+            if (on && k0 + u < dim) g_film_w[(int64_t)r * dim + k0 + u] = gw[u];
     }
     if (on) g_film_b[r] = gb;
     __syncthreads();
@@ -91,7 +102,7 @@ time_film_bwd_rows_kernel(const float* __restrict__ d_film, const float* __restr
 
 __global__ void __launch_bounds__(256)
 time_film_bwd_mlp_kernel(const int64_t* __restrict__ t, const float* __restrict__ emb_scale, const float* __restrict__ emb_bias,
-                         const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                         const float* w1, const float* __restrict__ b1, const float* w2,
                          const float* __restrict__ b2, const float* __restrict__ dc, float* __restrict__ g_w1,
                          float* __restrict__ g_b1, float* __restrict__ g_w2, float* __restrict__ g_b2, int B, int dim) {
     extern __shared__ float sm[];
@@ -101,6 +112,15 @@ time_film_bwd_mlp_kernel(const int64_t* __restrict__ t, const float* __restrict_
     float* h1 = z1 + B * H;      // [B][H]
     float* dz2 = h1 + B * H;     // [B][dim]
     float* dz1 = dz2 + B * dim;  // [B][H]
+    float* sw1 = dz1 + B * H;    // [H][dim]   the two weight matrices, staged with coalesced loads: the loops below walk them
+    float* sw2 = sw1 + H * (dim + 1);  // [dim][H + 1]   along k, which from global memory is one latency per element
+    const int p1 = dim + 1, p2 = H + 1;       // padded pitches: threads walk different rows at the same k
+    for (int i = threadIdx.x; i < H * dim; i += blockDim.x) {
+        sw1[(i / dim) * p1 + i % dim] = w1[i];
+        sw2[(i / H) * p2 + i % H] = w2[i];
+    }
+    w1 = sw1;
+    w2 = sw2;
     for (int i = threadIdx.x; i < B * dim; i += blockDim.x) {
         const int b = i / dim, k = i % dim;
         emb[i] = sinf(fmaf(emb_scale[k], (float)t[b], emb_bias[k]));
@@ -109,7 +129,7 @@ time_film_bwd_mlp_kernel(const int64_t* __restrict__ t, const float* __restrict_
     for (int i = threadIdx.x; i < B * H; i += blockDim.x) {
         const int b = i / H, r = i % H;
         float acc = b1[r];
-        for (int k = 0; k < dim; ++k) acc = fmaf(w1[r * dim + k], emb[b * dim + k], acc);
+        for (int k = 0; k < dim; ++k) acc = fmaf(w1[r * p1 + k], emb[b * dim + k], acc);
         z1[i] = acc;
         h1[i] = silu_f(acc);
     }
@@ -117,14 +137,14 @@ time_film_bwd_mlp_kernel(const int64_t* __restrict__ t, const float* __restrict_
     for (int i = threadIdx.x; i < B * dim; i += blockDim.x) {
         const int b = i / dim, r = i % dim;
         float acc = b2[r];
-        for (int k = 0; k < H; ++k) acc = fmaf(w2[r * H + k], h1[b * H + k], acc);
+        for (int k = 0; k < H; ++k) acc = fmaf(w2[r * p2 + k], h1[b * H + k], acc);
         dz2[i] = dc[i] * dsilu_exact(acc);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < B * H; i += blockDim.x) {
         const int b = i / H, j = i % H;
         float acc = 0.0f;
-        for (int r = 0; r < dim; ++r) acc = fmaf(dz2[b * dim + r], w2[r * H + j], acc);
+        for (int r = 0; r < dim; ++r) acc = fmaf(dz2[b * dim + r], w2[r * p2 + j], acc);
         dz1[i] = acc * dsilu_exact(z1[i]);
     }
     __syncthreads();
@@ -163,7 +183,7 @@ extern "C" int tdb_time_film_bwd(const int64_t* t, const float* emb_scale, const
                 TDB_E_BADARG, "tdb_time_film_bwd: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
     const size_t smem_a = (size_t)2 * B * dim * sizeof(float);
-    const size_t smem_b = (size_t)B * dim * 14 * sizeof(float);  // emb + dz2: 2*dim, z1 + h1 + dz1: 12*dim per sample
+    const size_t smem_b = ((size_t)B * dim * 14 + (size_t)8 * dim * dim + 5 * dim) * sizeof(float);  // emb + dz2: 2*dim, z1 + h1 + dz1: 12*dim per sample; w1, w2 (padded)
     TDB_REQUIRE(smem_a <= 48 * 1024 && smem_b <= 200 * 1024, TDB_E_UNSUPPORTED, "tdb_time_film_bwd: batch %d x dim %d does not fit", B, dim);
     cudaError_t e = cudaMemsetAsync(dc_scratch, 0, (size_t)B * dim * sizeof(float), s);
     TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_time_film_bwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
