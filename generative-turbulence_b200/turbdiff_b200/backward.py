@@ -115,6 +115,19 @@ class BackwardProgram:
                 t.record_stream(main)
         return res
 
+    def _zeros64(self, n: int, dev):
+        """n zeroed doubles out of ONE buffer per backward pass (a torch.zeros per norm layer is a fill launch on the critical
+        path in front of each of the 23 reduce kernels)."""
+        pool = getattr(self, "_zpool", None)
+        if pool is None or self._zused + n > pool.numel():
+            B = self.p["B"]
+            total = B * 4 * (sum(2 * bp.cout for bp in self.eng.blocks.values()) + 2 * self.m.dim * 2 ** self.m.u_net_levels)
+            pool = self._zpool = torch.zeros(max(total, n), dtype=torch.float64, device=dev)
+            self._zused = 0
+        out = pool[self._zused : self._zused + n]
+        self._zused += n
+        return out
+
     def _wait_readers(self, v: View):
         """Before `v` is overwritten on the main stream: wait for the side-stream kernel that still reads it."""
         ev = self._readers.pop(v.t.data_ptr(), None)
@@ -138,7 +151,7 @@ class BackwardProgram:
         B, C = p["B"], raw.C
         dev = raw.t.device
         film_ptr = None if film_view is None else film_view.data_ptr()
-        red = torch.zeros((B, C, 4), dtype=torch.float64, device=dev)
+        red = self._zeros64(B * C * 4, dev).view(B, C, 4)
         call("tdb_pointwise_bwd_reduce", g_out.ptr, g_out.ld, raw.ptr, raw.ld, ptr(stats), ptr(norm.weight), ptr(norm.bias), film_ptr,
              eng.film_rows, red.data_ptr(), B, X, Y, Z, C, G, GN_EPS, flags, eng.dt, _lib.stream_ptr())
         out = torch.empty((4, C), dtype=torch.float32, device=dev)
@@ -283,6 +296,7 @@ class BackwardProgram:
         eng.weights()
         self.side = eng.side_stream(dev) if eng.wgrad_side_stream else None
         self._readers = {}
+        self._zpool = None
         g_eps = g_eps.to(torch.float32).contiguous()
         grads = self.grads = {}
         d_film = self.d_film = torch.zeros((B, eng.film_rows), dtype=torch.float32, device=dev)
