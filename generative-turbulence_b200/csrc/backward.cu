@@ -1120,30 +1120,35 @@ extern "C" {
 int tdb_halo_fold(void* g, int ld, int B, int X, int Y, int Z, int C, int dtype, void* stream) {
     TDB_REQUIRE(g, TDB_E_BADARG, "tdb_halo_fold: null pointer");
     const int n = dtype == TDB_BF16 ? 8 : 4;
-    TDB_REQUIRE(C % n == 0 && ld % n == 0 && C / n <= kThreads && aligned16(g), TDB_E_UNSUPPORTED, "tdb_halo_fold: C/ld must be multiples of %d", n);
+    TDB_REQUIRE(C % n == 0 && ld % n == 0 && aligned16(g), TDB_E_UNSUPPORTED, "tdb_halo_fold: C/ld must be multiples of %d", n);
     Grid3 gr(B, X, Y, Z);
-    const int chunks = C / n;
-    if (X >= 2 && Y >= 2 && Z >= 2) {
-        BorderEnum e;
-        e.n_xf = 2u * Y * Z;
-        e.n_yf = 2u * (X - 2) * Z;
-        e.n_total = e.n_xf + e.n_yf + 2u * (X - 2) * (Y - 2);
-        auto fd = [](int v) { return FastDiv((uint32_t)(v < 1 ? 1 : v)); };
-        e.by_yz = fd(Y * Z); e.by_z = fd(Z); e.by_xz = fd((X - 2) * Z); e.by_xy = fd((X - 2) * (Y - 2)); e.by_ym2 = fd(Y - 2);
-        dim3 grid((unsigned)ceil_div((int64_t)e.n_total * chunks, kThreads), (unsigned)B);  // one item per thread
-        if (dtype == TDB_BF16)
-            halo_fold_border_kernel<bf16><<<grid, kThreads, 0, (cudaStream_t)stream>>>((bf16*)g, ld, gr, e, chunks);
-        else
-            halo_fold_border_kernel<float><<<grid, kThreads, 0, (cudaStream_t)stream>>>((float*)g, ld, gr, e, chunks);
+    // a block covers at most kThreads 16-byte channel vectors per voxel: wider tensors (2048 fp32 channels in the first up
+    // block of a dim = 64 model) are folded in channel slices, one launch each
+    const int slice = kThreads * n;
+    for (int c0 = 0; c0 < C; c0 += slice) {
+        const int chunks = ((C - c0) < slice ? (C - c0) : slice) / n;
+        void* gs = (char*)g + (size_t)c0 * (dtype == TDB_BF16 ? 2 : 4);
+        if (X >= 2 && Y >= 2 && Z >= 2) {
+            BorderEnum e;
+            e.n_xf = 2u * Y * Z;
+            e.n_yf = 2u * (X - 2) * Z;
+            e.n_total = e.n_xf + e.n_yf + 2u * (X - 2) * (Y - 2);
+            auto fd = [](int v) { return FastDiv((uint32_t)(v < 1 ? 1 : v)); };
+            e.by_yz = fd(Y * Z); e.by_z = fd(Z); e.by_xz = fd((X - 2) * Z); e.by_xy = fd((X - 2) * (Y - 2)); e.by_ym2 = fd(Y - 2);
+            dim3 grid((unsigned)ceil_div((int64_t)e.n_total * chunks, kThreads), (unsigned)B);  // one item per thread
+            if (dtype == TDB_BF16)
+                halo_fold_border_kernel<bf16><<<grid, kThreads, 0, (cudaStream_t)stream>>>((bf16*)gs, ld, gr, e, chunks);
+            else
+                halo_fold_border_kernel<float><<<grid, kThreads, 0, (cudaStream_t)stream>>>((float*)gs, ld, gr, e, chunks);
+        } else {
+            dim3 grid((unsigned)blocks_per_sample(gr.vox_p * chunks, B), (unsigned)B);
+            if (dtype == TDB_BF16)
+                halo_fold_kernel<bf16><<<grid, kThreads, 0, (cudaStream_t)stream>>>((bf16*)gs, ld, gr, make_split(gr), chunks);
+            else
+                halo_fold_kernel<float><<<grid, kThreads, 0, (cudaStream_t)stream>>>((float*)gs, ld, gr, make_split(gr), chunks);
+        }
         TDB_CHECK_LAUNCH("tdb_halo_fold");
-        return 0;
     }
-    dim3 grid((unsigned)blocks_per_sample(gr.vox_p * chunks, B), (unsigned)B);
-    if (dtype == TDB_BF16)
-        halo_fold_kernel<bf16><<<grid, kThreads, 0, (cudaStream_t)stream>>>((bf16*)g, ld, gr, make_split(gr), chunks);
-    else
-        halo_fold_kernel<float><<<grid, kThreads, 0, (cudaStream_t)stream>>>((float*)g, ld, gr, make_split(gr), chunks);
-    TDB_CHECK_LAUNCH("tdb_halo_fold");
     return 0;
 }
 
@@ -1154,7 +1159,7 @@ int tdb_pointwise_bwd_reduce(const void* g_out, int ld_g, const void* raw, int l
     TDB_REQUIRE(!stats || (gamma && beta && G >= 1 && C % G == 0), TDB_E_BADARG, "tdb_pointwise_bwd_reduce: norm args");
     const int n = dtype == TDB_BF16 ? 8 : 4;
     TDB_REQUIRE(C % n == 0 && ld_g % n == 0 && ld_raw % n == 0 && C / n <= kThreads && aligned16(g_out) && aligned16(raw),
-                TDB_E_UNSUPPORTED, "tdb_pointwise_bwd_reduce: C/ld must be multiples of %d", n);
+                TDB_E_UNSUPPORTED, "tdb_pointwise_bwd_reduce: C/ld must be multiples of %d and C <= %d", n, n * kThreads);
     if (G < 1) G = 1;
     Grid3 gr(B, X, Y, Z);
     // blocks per sample: every block ends with 4*C double atomics into red[] (~6.5 G/s device-wide, measured), so a block
@@ -1206,7 +1211,7 @@ static int launch_pw_bwd_apply(const char* who, const void* g_out, int ld_g, con
     const int n = dtype == TDB_BF16 ? 8 : 4;
     TDB_REQUIRE(C % n == 0 && ld_g % n == 0 && ld_raw % n == 0 && ld_d % n == 0 && C / n <= kThreads && aligned16(g_out) &&
                     aligned16(raw) && aligned16(d_raw),
-                TDB_E_UNSUPPORTED, "%s: C/ld must be multiples of %d", who, n);
+                TDB_E_UNSUPPORTED, "%s: C/ld must be multiples of %d and C <= %d", who, n, n * kThreads);
     if (G < 1) G = 1;
     Grid3 gr(B, X, Y, Z);
     const int chunks = C / n;
@@ -1311,7 +1316,7 @@ int tdb_trilinear_bwd(const void* g_out, int ld_g, int Xo, int Yo, int Zo, void*
     TDB_REQUIRE(g_out && d_in, TDB_E_BADARG, "tdb_trilinear_bwd: null pointer");
     const int n = dtype == TDB_BF16 ? 8 : 4;
     TDB_REQUIRE(C % n == 0 && ld_g % n == 0 && ld_d % n == 0 && C / n <= kThreads && aligned16(g_out) && aligned16(d_in),
-                TDB_E_UNSUPPORTED, "tdb_trilinear_bwd: C/ld must be multiples of %d", n);
+                TDB_E_UNSUPPORTED, "tdb_trilinear_bwd: C/ld must be multiples of %d and C <= %d", n, n * kThreads);
     Grid3 gi(B, Xi, Yi, Zi), go(B, Xo, Yo, Zo);
     const int chunks = C / n;
     const int accumulate = (flags & TDB_TRIBWD_ACCUMULATE) ? 1 : 0;

@@ -482,7 +482,7 @@ int tdb_encode_input(const float* x, const float* c_local, const float* wx, cons
     const bool both = Fc > 0 && (parts & 3) == 3;
     const int c_begin = (Fc > 0 && (parts & 3) == 2) ? dim : 0;
     const int chunks = (both ? ctot : dim) / n;
-    TDB_REQUIRE(g.vox_p < (1ll << 31) && chunks <= kThreads, TDB_E_UNSUPPORTED, "tdb_encode_input: grid too large for 32-bit indexing");
+    TDB_REQUIRE(g.vox_p < (1ll << 31) && chunks <= kThreads, TDB_E_UNSUPPORTED, "tdb_encode_input: grid too large for 32-bit indexing, or more than %d channel vectors of 16 bytes per voxel", kThreads);
     dim3 grid((unsigned)blocks_per_sample(g.vox_p * chunks, B), (unsigned)B);
     const RowSplit split = make_split(g);
     cudaStream_t s = (cudaStream_t)stream;
@@ -560,7 +560,7 @@ int tdb_pointwise(const void* raw, int ld_raw, const double* stats, const float*
     if (G < 1) G = 1;
     Grid3 g(B, X, Y, Z);
     const int chunks = C / n;
-    TDB_REQUIRE(g.vox_p < (1ll << 31) && chunks <= kThreads, TDB_E_UNSUPPORTED, "tdb_pointwise: grid too large for 32-bit indexing");
+    TDB_REQUIRE(g.vox_p < (1ll << 31) && chunks <= kThreads, TDB_E_UNSUPPORTED, "tdb_pointwise: grid too large for 32-bit indexing, or more than %d channel vectors of 16 bytes per voxel", kThreads);
     // at least two trips of four rows per thread: the per-block prologue and the launch tail stay small on the deep levels
     dim3 grid((unsigned)blocks_per_sample(ceil_div(g.vox_p * chunks, 8), B), (unsigned)B);
     const RowSplit split = make_split(g);
@@ -586,7 +586,7 @@ int tdb_trilinear(const void* in, int ld_in, int Xi, int Yi, int Zi, void* out, 
                 TDB_E_UNSUPPORTED, "tdb_trilinear: channel counts / pitches must be multiples of %d", n);
     Grid3 gi(B, Xi, Yi, Zi), go(B, Xo, Yo, Zo);
     const int chunks = C / n;
-    TDB_REQUIRE(go.vox_p < (1ll << 31) && chunks <= kThreads, TDB_E_UNSUPPORTED, "tdb_trilinear: grid too large for 32-bit indexing");
+    TDB_REQUIRE(go.vox_p < (1ll << 31) && chunks <= kThreads, TDB_E_UNSUPPORTED, "tdb_trilinear: grid too large for 32-bit indexing, or more than %d channel vectors of 16 bytes per voxel", kThreads);
     dim3 grid((unsigned)blocks_per_sample((int64_t)go.Xp * go.Yp * chunks, B), (unsigned)B);
     const RowSplit split = make_split(go);
     auto scale_of = [](int n_in, int n_out) { return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.0f; };

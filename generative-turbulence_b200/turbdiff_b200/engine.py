@@ -185,6 +185,10 @@ class DenoiserEngine:
         if cout in (16, 32, 64):
             pair = self.fold2 and cin % 64 == 0 and cout in (32, 64) and 9 * cin * 3 * cout * 2 > 112 * 1024
             return "fold2" if pair else "fold"
+        if self.fold2 and self.fold_wide and self.win and zp <= 63 and cout % 512 == 0 and cout > 512 and cin % 64 == 0:
+            # Cout > 512 (the 256 -> 1024 input gradient of up0.block1): the row-window kernel in launches of 512 channels
+            # (the per-tap layout's row blocks are contiguous); _conv walks the halves
+            return "win"
         if self.fold2 and self.fold_wide and cout % 128 == 0 and cout <= 512 and cin % 64 == 0:
             # wide layers: N tiles of 128 channels with streamed weights; the row-window kernel double-buffers its
             # accumulators and keeps all 128 rows of a tile (3-20 % faster than the kz-folded pair kernel here).
@@ -314,6 +318,15 @@ class DenoiserEngine:
         X, Y, Z = p["sizes"][x.level]
         s = _lib.stream_ptr()
         flags = _lib.CONV_ALL_ROWS if all_rows else 0
+        if self.precision == "bf16" and ntaps == 27 and out.C > 512 and self.fold_kind(ntaps, x.C, out.C, x.level) == "win":
+            # more than 512 output channels: one launch per block of 512 (rows h*512 .. of the [Cout][27*Cin] weights)
+            assert stats is None and proj is None and out.C % 512 == 0
+            for h in range(out.C // 512):
+                wh = w[h * 512 : (h + 1) * 512]
+                bh = None if bias is None else bias[h * 512 : (h + 1) * 512]
+                a2 = None if add1x1 is None else (add1x1[0], add1x1[1][h * 512 : (h + 1) * 512])
+                self._conv(p, x, wh, bh, out.slice(h * 512, 512), ntaps, all_rows=all_rows, add1x1=a2)
+            return
         if add1x1 is not None:
             x2, w2 = add1x1
             assert self.can_add1x1(x.C, out.C, x.level) and x2.C == x.C and stats is None and proj is None
@@ -369,7 +382,8 @@ class DenoiserEngine:
         if not self.fuse_proj:
             return False
         kind = self.fold_kind(27, x.C, cout, x.level)
-        return (cout <= 64 and kind in ("fold2", "win", "winz")) or (kind == "win" and cout % 128 == 0)
+        # (more than 512 output channels run as several launches of the row-window kernel: no fused projection there)
+        return (cout <= 64 and kind in ("fold2", "win", "winz")) or (kind == "win" and cout % 128 == 0 and cout <= 512)
 
     def _norm_conv(self, p, x: View, w, conv, norm, raw: View, stats_slot, proj=None):
         """conv (+bias) followed by GroupNorm moments of its output."""
@@ -377,7 +391,8 @@ class DenoiserEngine:
         stats = p["stats"][stats_slot]
         cpg = raw.C // G
         if self.fold_kind(27, x.C, raw.C, x.level) is not None:
-            fused = self.fused_stats and cpg % 2 == 0
+            # (Cout > 512 is split into launches of 512 channels, whose [B][G] moment slots would not line up: gn_stats pass)
+            fused = self.fused_stats and cpg % 2 == 0 and raw.C <= 512
         else:
             fused = self.fused_stats and (cpg % 16 == 0 or 16 % cpg == 0)
         self._conv(p, x, w, conv.bias, raw, 27, stats if fused else None, G, proj=proj)
@@ -672,16 +687,24 @@ class DenoiserEngine:
         sig = tuple(q.data_ptr() for q in self.model.parameters())
         tg = self._train_graphs.get(key)
         if tg is None or tg["sig"] != sig:
-            try:
-                tg = self._train_graphs[key] = self._capture_train(x, t, c_local, sig)
-            except RuntimeError as e:  # a failed capture is not fatal: the same kernels run from the eager launch programs
+            tg = None
+            # strict capture first (thread_local: nothing in the programs needs more); if something outside them - e.g. the
+            # garbage collector releasing an older graph's memory on this thread in the middle of the capture - invalidates
+            # it, once more in relaxed mode; only then the eager launch programs
+            for mode in ("thread_local", "relaxed"):
+                try:
+                    tg = self._train_graphs[key] = self._capture_train(x, t, c_local, sig, mode)
+                    break
+                except RuntimeError as e:
+                    err = e
+                    torch.cuda.synchronize()
+            if tg is None:  # a failed capture is not fatal: the same kernels run from the eager launch programs
                 import warnings
 
-                warnings.warn(f"turbdiff_b200: CUDA-graph capture of the training step failed ({str(e)[:200]}); using the eager launch programs")
+                warnings.warn(f"turbdiff_b200: CUDA-graph capture of the training step failed ({str(err)[:200]}); using the eager launch programs")
                 self.train_graph = False
                 self.graph_fallbacks += 1
                 self._train_replay = None
-                torch.cuda.synchronize()
                 return self.forward(x, t, c_local, train=True)
         tg["x"].copy_(x)
         tg["t"].copy_(t)
@@ -714,7 +737,7 @@ class DenoiserEngine:
         self.replayed_launches += tg["n_bwd"]
         return tg["flat"], tg["g_c_local"]
 
-    def _capture_train(self, x, t, c_local, sig):
+    def _capture_train(self, x, t, c_local, sig, capture_mode="thread_local"):
         from .backward import BackwardProgram
 
         xs = x.detach().to(torch.float32).clone()
@@ -740,7 +763,17 @@ class DenoiserEngine:
         # forward and the backward replay of one step, so the engine-level cache (what eager forwards and the sampler
         # graphs use) is saved here and restored after the capture instead of being left pointing into the pool.
         keep = (self._wcache, self._wversion)
-        with torch.cuda.graph(g_f, pool=pool, capture_error_mode="thread_local"):
+        try:
+            return self._capture_train_graphs(xs, ts, cs, gs, x, sig, pool, g_f, g_b, n0, capture_mode)
+        finally:
+            # also after a FAILED capture: tensors created inside it were never computed, the cache must not point at them
+            self._wcache, self._wversion = keep
+            self._wgen += 1
+
+    def _capture_train_graphs(self, xs, ts, cs, gs, x, sig, pool, g_f, g_b, n0, capture_mode):
+        from .backward import BackwardProgram
+
+        with torch.cuda.graph(g_f, pool=pool, capture_error_mode=capture_mode):
             self._wcache = None
             eps = self.forward(xs, ts, cs, train=True)
         n_l1 = _lib.launch_count()
@@ -756,7 +789,7 @@ class DenoiserEngine:
         views = {n: v.view(by_name[n].shape) for v, n in zip(flat.split(sizes), order)}
         g_b2 = torch.cuda.CUDAGraph()
         bp = BackwardProgram(self)
-        with torch.cuda.graph(g_b, pool=pool, capture_error_mode="thread_local"):
+        with torch.cuda.graph(g_b, pool=pool, capture_error_mode=capture_mode):
             bp.phase1(gs)
             first = [n for n in order if grad_phase(n) == 1]
             missing = [n for n in first if n not in bp.grads]
@@ -765,14 +798,12 @@ class DenoiserEngine:
             # all gradients of this phase packed into the flat buffer: the autograd glue then hands them out with a single
             # copy instead of one per tensor
             torch._foreach_copy_([views[n] for n in first], [bp.grads[n].reshape(by_name[n].shape) for n in first])
-        with torch.cuda.graph(g_b2, pool=pool, capture_error_mode="thread_local"):
+        with torch.cuda.graph(g_b2, pool=pool, capture_error_mode=capture_mode):
             grads, g_c = bp.phase2()
             second = [n for n in order if grad_phase(n) == 2]
             torch._foreach_copy_([views[n] for n in second], [grads[n].reshape(by_name[n].shape) for n in second])
         n2 = _lib.launch_count()
         pool_w = self._wcache  # kept alive by the returned record: the graphs hold raw addresses into it
-        self._wcache, self._wversion = keep
-        self._wgen += 1
         return {"sig": sig, "n_fwd": n_l1 - n0, "n_bwd": n2 - n_l1, "flat": flat, "order": order, "sizes": sizes, "n1": n1,
                 "shapes": [by_name[n].shape for n in order], "x": xs, "t": ts, "c": cs, "g_eps": gs, "eps": eps, "fwd": g_f, "bwd": g_b,
                 "bwd2": g_b2, "grads": grads, "g_c_local": g_c, "pool_w": pool_w}

@@ -37,6 +37,16 @@ CASES = {
     ),
 }
 
+# Cases WITHOUT reference goldens (checked against the oracle only, which the cases above pin to the reference):
+# dim=64 with 4 levels doubles every channel count of the shapes config (128 ... 1024, 2048 -> 512 in the first up block),
+# i.e. more than 512 output channels per convolution and FiLM rows of 2048.
+WIDE_CASES = {
+    "dim64": dict(
+        spec=UNetSpec(dim=64, u_net_levels=4, timesteps=100, groups=8),
+        cells=(22, 6, 6), hole=None, batch=2, seed=606, save_taps=False,
+    ),
+}
+
 
 def case_inputs(case):
     """(x, t, c_local, geometry) for a case.  x ~ N(0,1) fp32 (B,F,X,Y,Z) on the padded

@@ -72,6 +72,47 @@ def test_denoiser_bf16_within_tolerance(golden, cname):
     assert max(errs.values()) < 2e-2, errs
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_wide_denoiser_matches_oracle(precision, tol):
+    """dim = 64, 4 levels: convolutions with 1024 (and, in the backward pass, 2048) output channels, 2048 FiLM rows, a
+    1024-channel bottleneck attention.  No reference golden for this case: per-block taps and output against the oracle."""
+    from oracle.cases import WIDE_CASES, case_inputs
+    from oracle.unet_ref import denoiser_forward, synth_state_dict
+
+    case = WIDE_CASES["dim64"]
+    m = build(case, precision)
+    x, t, c_local, _ = case_inputs(case)
+    taps, ref_taps = {}, {}
+    with torch.no_grad():
+        eps = m.engine().forward(x.cuda(), t.cuda(), c_local.cuda(), taps=taps).clone()
+        want = denoiser_forward(synth_state_dict(case["spec"], case["seed"], torch.float64), case["spec"], x.double(), t, c_local.double(), ref_taps)
+    errs = {name: rel_l2(v, ref_taps[name]) for name, v in taps.items()}
+    errs["out"] = rel_l2(eps, want)
+    print(precision, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < tol, errs
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2)])
+def test_wide_denoiser_backward_matches_oracle(precision, tol):
+    """Gradients of the dim = 64 case (input gradient of up0.block1 is a 512 -> 2048 convolution: four launches of the
+    row-window kernel on the bf16 path)."""
+    from oracle.cases import WIDE_CASES, case_inputs
+
+    case = WIDE_CASES["dim64"]
+    m = build(case, precision).train()
+    x, t, c_local, _ = case_inputs(case)
+    G = torch.randn(x.shape, generator=torch.Generator().manual_seed(9))
+    want, want_cl = _oracle_grads(case, G)
+    cl = c_local.cuda().requires_grad_()
+    eps = m(x.cuda(), t.cuda(), {key_of(): cl})
+    (eps * G.cuda()).sum().backward()
+    errs = {k: rel_l2(p.grad, want[k]) for k, p in m.named_parameters() if float(want[k].abs().max()) >= 1e-9}
+    errs["c_local"] = rel_l2(cl.grad, want_cl)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    print(precision, [(k, f"{v:.2e}") for k, v in worst])
+    assert worst[0][1] < tol, worst
+
+
 @pytest.mark.parametrize("cname", ["micro", "tiny"])
 @pytest.mark.parametrize("noise_bcs", [True, False])
 def test_sampling_loop_matches_reference_golden(golden, cname, noise_bcs):
