@@ -1006,6 +1006,128 @@ attention_bwd_kernel(const T* __restrict__ qkv, int ld_qkv, const T* __restrict_
     }
 }
 
+// Sequences whose S x S matrices do not fit in shared memory (S > 135): nothing quadratic is stored.  grid = (B * heads,
+// row chunks).  Phase 1 (K, V resident): every CTA recomputes the softmax statistics of ALL rows - log-sum-exp and
+// sum_j P_ij dP_ij, S^2 * 64 FMAs, cheap - and writes dQ for the rows of its chunk.  Phase 2 (Q, dO resident in the same
+// buffers): dK and dV of the chunk's keys, one warp per key, the column of P / dS rebuilt from the row statistics.
+constexpr int ATTB_WARPS = 8;
+constexpr int ATTB_ROWS = 32;  // rows (phase 1) and keys (phase 2) per CTA
+template <typename T>
+__global__ void __launch_bounds__(ATTB_WARPS * 32)
+attention_bwd_stream_kernel(const T* __restrict__ qkv, int ld_qkv, const T* __restrict__ d_out, int ld_do, T* __restrict__ d_qkv,
+                            int ld_dq, Grid3 g, int heads, int S) {
+    constexpr int DH = 32, P = DH + 1;
+    extern __shared__ float sm[];
+    float* sa = sm;                            // [S][P]  phase 1: K, phase 2: Q
+    float* sb = sa + (size_t)S * P;            // [S][P]  phase 1: V, phase 2: dO
+    float* lse = sb + (size_t)S * P;           // [S]
+    float* dsum = lse + S;                     // [S]
+    float* wbuf = dsum + S;                    // [WARPS][2][S]  probabilities / score gradients of the row (column) in flight
+    float* wvec = wbuf + (size_t)ATTB_WARPS * 2 * S;  // [WARPS][2][P]  q_i, dO_i (phase 1) / k_j, v_j (phase 2)
+    const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+    const int hid = heads * DH;
+    const int lo = blockIdx.y * ATTB_ROWS, hi = min(S, lo + ATTB_ROWS);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const float scale = rsqrtf((float)DH);
+    auto row_of = [&](int s) {
+        const int z = s % g.Z, y = (s / g.Z) % g.Y, x = s / (g.Z * g.Y);
+        return g.row(b, x, y, z);
+    };
+    for (int i = threadIdx.x; i < S * DH; i += blockDim.x) {
+        const int s = i / DH, d = i % DH;
+        const T* src = qkv + row_of(s) * ld_qkv + h * DH + d;
+        sa[s * P + d] = (float)src[hid];
+        sb[s * P + d] = (float)src[2 * hid];
+    }
+    __syncthreads();
+    float* p = wbuf + (size_t)warp * 2 * S;
+    float* ds = p + S;
+    float* v0 = wvec + warp * 2 * P;
+    float* v1 = v0 + P;
+    for (int i = warp; i < S; i += ATTB_WARPS) {
+        const int64_t row = row_of(i);
+        v0[lane] = (float)qkv[row * ld_qkv + h * DH + lane];
+        v1[lane] = (float)d_out[row * ld_do + h * DH + lane];
+        __syncwarp();
+        float mx = -INFINITY;
+        for (int j = lane; j < S; j += 32) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) acc = fmaf(v0[d], sa[j * P + d], acc);
+            acc *= scale;
+            p[j] = acc;
+            mx = fmaxf(mx, acc);
+        }
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int j = lane; j < S; j += 32) {
+            const float e = expf(p[j] - mx);
+            p[j] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        float dsm = 0.0f;
+        for (int j = lane; j < S; j += 32) {
+            const float pj = p[j] * inv;
+            float dp = 0.0f;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) dp = fmaf(v1[d], sb[j * P + d], dp);
+            p[j] = pj;
+            ds[j] = dp;
+            dsm = fmaf(pj, dp, dsm);
+        }
+        dsm = warp_sum(dsm);
+        if (lane == 0) {
+            lse[i] = mx + logf(sum);
+            dsum[i] = dsm;
+        }
+        if (i >= lo && i < hi) {
+            for (int j = lane; j < S; j += 32) ds[j] = p[j] * (ds[j] - dsm) * scale;
+            __syncwarp();
+            float dq = 0.0f;
+            for (int j = 0; j < S; ++j) dq = fmaf(ds[j], sa[j * P + lane], dq);
+            d_qkv[row * ld_dq + h * DH + lane] = (T)dq;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < S * DH; i += blockDim.x) {
+        const int s = i / DH, d = i % DH;
+        const int64_t row = row_of(s);
+        sa[s * P + d] = (float)qkv[row * ld_qkv + h * DH + d];
+        sb[s * P + d] = (float)d_out[row * ld_do + h * DH + d];
+    }
+    __syncthreads();
+    for (int j = lo + warp; j < hi; j += ATTB_WARPS) {
+        const int64_t row = row_of(j);
+        v0[lane] = (float)qkv[row * ld_qkv + hid + h * DH + lane];
+        v1[lane] = (float)qkv[row * ld_qkv + 2 * hid + h * DH + lane];
+        __syncwarp();
+        for (int i = lane; i < S; i += 32) {
+            float sc = 0.0f, dp = 0.0f;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) {
+                sc = fmaf(sa[i * P + d], v0[d], sc);
+                dp = fmaf(sb[i * P + d], v1[d], dp);
+            }
+            const float pij = expf(sc * scale - lse[i]);
+            p[i] = pij;
+            ds[i] = pij * (dp - dsum[i]) * scale;
+        }
+        __syncwarp();
+        float dk = 0.0f, dv = 0.0f;
+        for (int i = 0; i < S; ++i) {
+            dk = fmaf(ds[i], sa[i * P + lane], dk);
+            dv = fmaf(p[i], sb[i * P + lane], dv);
+        }
+        T* o = d_qkv + row * ld_dq + h * DH + lane;
+        o[hid] = (T)dk;
+        o[2 * hid] = (T)dv;
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------- channels-last x channels-first outer product
 // out[c][f] += sum_{b, v interior} G[b,v][c] * Q[b*q_bstride + f*nvox + v]   (thread = one (c,f) pair)
 template <typename T>
@@ -1366,7 +1488,29 @@ int tdb_attention_bwd(const void* qkv, int ld_qkv, const void* d_out, int ld_do,
     TDB_REQUIRE(dh == 32, TDB_E_UNSUPPORTED, "tdb_attention_bwd: dim_head must be 32 (got %d)", dh);
     const int S = X * Y * Z;
     const size_t smem = ((size_t)4 * S * 33 + (size_t)2 * S * (S + 1)) * sizeof(float);
-    TDB_REQUIRE(smem <= 220 * 1024, TDB_E_UNSUPPORTED, "tdb_attention_bwd: sequence of %d voxels exceeds shared memory", S);
+    if (smem > 220 * 1024) {
+        // the S x S form does not fit (S > 135): streaming form, same limit as the forward kernel's CUDA-core path and beyond
+        const size_t smem2 = ((size_t)2 * S * 33 + 2 * (size_t)S + (size_t)ATTB_WARPS * 2 * S + ATTB_WARPS * 2 * 33) * sizeof(float);
+        TDB_REQUIRE(smem2 <= 220 * 1024, TDB_E_UNSUPPORTED, "tdb_attention_bwd: sequence of %d voxels exceeds shared memory", S);
+        Grid3 g2(B, X, Y, Z);
+        cudaStream_t s2 = (cudaStream_t)stream;
+        dim3 grid((unsigned)(B * heads), (unsigned)((S + ATTB_ROWS - 1) / ATTB_ROWS));
+        cudaError_t e2;
+        if (dtype == TDB_BF16) {
+            e2 = cudaFuncSetAttribute(attention_bwd_stream_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            if (e2 == cudaSuccess)
+                attention_bwd_stream_kernel<bf16><<<grid, ATTB_WARPS * 32, smem2, s2>>>((const bf16*)qkv, ld_qkv, (const bf16*)d_out, ld_do,
+                                                                                       (bf16*)d_qkv, ld_dq, g2, heads, S);
+        } else {
+            e2 = cudaFuncSetAttribute(attention_bwd_stream_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            if (e2 == cudaSuccess)
+                attention_bwd_stream_kernel<float><<<grid, ATTB_WARPS * 32, smem2, s2>>>((const float*)qkv, ld_qkv, (const float*)d_out, ld_do,
+                                                                                        (float*)d_qkv, ld_dq, g2, heads, S);
+        }
+        TDB_REQUIRE(e2 == cudaSuccess, (int)e2, "tdb_attention_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e2));
+        TDB_CHECK_LAUNCH("tdb_attention_bwd (streaming)");
+        return 0;
+    }
     Grid3 g(B, X, Y, Z);
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;

@@ -169,8 +169,14 @@ class BackwardProgram:
         """a[interior] += b[interior] (halo rows of `a` untouched)."""
         eng = self.eng
         X, Y, Z = p["sizes"][a.level]
-        call("tdb_pointwise", a.ptr, a.ld, None, None, None, None, 0, b.ptr, b.ld, a.ptr, a.ld, p["B"], X, Y, Z, a.C, 1, GN_EPS,
-             PW_NOHALO, eng.dt, _lib.stream_ptr())
+        # the streaming kernels take at most 256 channel vectors of 16 bytes per voxel (2048 bf16 / 1024 fp32 channels): the
+        # 2048-channel input gradient of the first up block of a dim = 64 model is added in slices on the fp32 path
+        step = 256 * 16 // a.t.element_size()
+        for c0 in range(0, a.C, step):
+            n = min(step, a.C - c0)
+            sa, sb = a.slice(c0, n), b.slice(c0, n)
+            call("tdb_pointwise", sa.ptr, sa.ld, None, None, None, None, 0, sb.ptr, sb.ld, sa.ptr, sa.ld, p["B"], X, Y, Z, n, 1, GN_EPS,
+                 PW_NOHALO, eng.dt, _lib.stream_ptr())
 
     # ------------------------------------------------------------------ blocks
     def _resblock_bwd(self, p, name, g_out: View, grads: dict, d_film: torch.Tensor):

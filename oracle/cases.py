@@ -45,6 +45,13 @@ WIDE_CASES = {
         spec=UNetSpec(dim=64, u_net_levels=4, timesteps=100, groups=8),
         cells=(22, 6, 6), hole=None, batch=2, seed=606, save_taps=False,
     ),
+    # everything "odd" at once: velocity only (F = 3), cell-position features on top of the cell-type embedding (7 local
+    # channels, conditioning.py:52-61), an odd batch, and a grid whose z lines (66 voxels with the halo) are longer than
+    # what the row-window kernels take, so the bf16 path runs on the kz-folded / per-tap kernels.
+    "odd": dict(
+        spec=UNetSpec(in_features=3, out_features=3, c_local_features=7, dim=16, u_net_levels=2, timesteps=10, groups=8),
+        cells=(10, 6, 64), hole=((2, 5), (1, 4), (10, 30)), batch=3, seed=707, save_taps=False,
+    ),
 }
 
 

@@ -304,7 +304,7 @@ def test_pointwise_bwd_matches_autograd(lib, prec, C, G, with_film, size):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
-@pytest.mark.parametrize("spatial", [(12, 3, 3), (8, 4, 4), (4, 2, 2)])
+@pytest.mark.parametrize("spatial", [(12, 3, 3), (8, 4, 4), (4, 2, 2), (3, 3, 16), (10, 7, 7)])  # S = 108, 128, 16, 144, 490
 def test_attention(lib, prec, spatial):
     code, td = _dt(prec)
     X, Y, Z = spatial
@@ -321,9 +321,11 @@ def test_attention(lib, prec, spatial):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
-@pytest.mark.parametrize("spatial", [(12, 3, 3), (8, 4, 4), (5, 3, 2)])
+@pytest.mark.parametrize("spatial", [(12, 3, 3), (8, 4, 4), (5, 3, 2), (3, 3, 16), (9, 5, 5), (10, 7, 7)])
 def test_attention_backward_matches_autograd(lib, prec, spatial):
-    """tdb_attention_bwd against torch.autograd of scaled_dot_product_attention (reference attention.py:9-15)."""
+    """tdb_attention_bwd against torch.autograd of scaled_dot_product_attention (reference attention.py:9-15).  Sequences of
+    up to 135 voxels run on the kernel that keeps the S x S matrices in shared memory, longer ones (144, 225, 490 here) on
+    the streaming form."""
     code, td = _dt(prec)
     X, Y, Z = spatial
     B, heads, dh = 3, 4, 32
