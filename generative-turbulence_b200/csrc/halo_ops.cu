@@ -2,6 +2,7 @@
 // the fused GroupNorm/FiLM/SiLU/residual pointwise kernel and trilinear resampling.
 // Every thread moves one 16-byte channel vector of one voxel; consecutive threads walk the
 // channel vectors of a voxel and then the next voxel, so global accesses are fully coalesced.
+#include <cstdlib>
 #include "common.cuh"
 
 using namespace tdb;
@@ -373,6 +374,103 @@ trilinear_kernel(const T* __restrict__ in, int ld_in, Grid3 gi, T* __restrict__ 
     }
 }
 
+// UP-sampling, two stages per output line (ncu of the walker above at 97x25x25 -> 194x50x50: issue slots 66 % busy at 34 %
+// DRAM, ~110 instructions per 16-byte output vector - the z interpolation recomputed per thread and z, the x/y blend of
+// four input vectors rebuilt in registers per thread).  Here a WARP owns an output (x, y) line: stage 1 blends the four
+// input lines in x/y ONCE into shared memory (fp32, Zi x C), stage 2 blends two of those rows per output voxel with the z
+// weights of a per-block table.  Same arithmetic in the same order as the walker (bit-identical results; the packed
+// fma.rn.f32x2 / mul.rn.f32x2 round each lane like the scalar instructions), 25 % fewer instructions (134 M -> 101 M at the
+// level-0 shape, B = 8): 195 -> 177 us, where it stops being issue-bound (issue slots 54 %) and sits at 2.7 TB/s of
+// writes.  Lanes = CW channel vectors x (32 / CW) z positions; needs CW = C / N to divide 32.
+// packed fp32 pairs (sm_100a): d = a * b + c on two lanes, each rounded like a scalar fma.rn / mul.rn
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a, float b0, float b1, float c0, float c1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %2};\n\tmov.b64 rb, {%3, %4};\n\tmov.b64 rc, {%5, %6};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void mul2(float& d0, float& d1, float a, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %2};\n\tmov.b64 rb, {%3, %4};\n\t"
+        "mul.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a), "f"(b0), "f"(b1));
+}
+
+constexpr int TRI_WARPS = 4;
+template <typename T>
+__global__ void __launch_bounds__(TRI_WARPS * 32)
+trilinear_up_line_kernel(const T* __restrict__ in, int ld_in, Grid3 gi, T* __restrict__ out, int ld_out, Grid3 go, int C,
+                         RowSplit split, int cw, float sx, float sy, float sz) {
+    constexpr int N = Vec<T>::N;
+    extern __shared__ __align__(16) unsigned char tri_smem[];
+    int4* ztab = reinterpret_cast<int4*>(tri_smem);                      // [Zp] (i0, i1, l0, l1)
+    float* pl = reinterpret_cast<float*>(tri_smem + (size_t)go.Zp * sizeof(int4)) + (size_t)(threadIdx.x / 32) * gi.Z * C;  // [Zi][C]
+    for (int zp = threadIdx.x; zp < go.Zp; zp += blockDim.x) {
+        const Lerp lz = axis_lerp(clampi(zp - 1, 0, go.Z - 1), gi.Z, sz);
+        ztab[zp] = make_int4(lz.i0, lz.i1, __float_as_int(lz.l0), __float_as_int(lz.l1));
+    }
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int ch = lane % cw, zl = lane / cw, zstep = 32 / cw;
+    const int c0 = ch * N;
+    const uint32_t lines = (uint32_t)(go.Xp * go.Yp);
+    for (uint32_t line = blockIdx.x * TRI_WARPS + warp; line < lines; line += gridDim.x * TRI_WARPS) {
+        uint32_t xq, yq;
+        split.by_y.divmod(line, xq, yq);
+        const Lerp lx = axis_lerp(clampi((int)xq - 1, 0, go.X - 1), gi.X, sx);
+        const Lerp ly = axis_lerp(clampi((int)yq - 1, 0, go.Y - 1), gi.Y, sy);
+        const T* base[4];
+        float wxy[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xi = (k & 2) ? lx.i1 : lx.i0, yi = (k & 1) ? ly.i1 : ly.i0;
+            base[k] = in + gi.row(b, xi, yi, 0) * ld_in + c0;
+            wxy[k] = ((k & 2) ? lx.l1 : lx.l0) * ((k & 1) ? ly.l1 : ly.l0);
+        }
+        // stage 1: x/y-interpolated input line
+#pragma unroll 2
+        for (int iz = zl; iz < gi.Z; iz += zstep) {
+            uint4 raw[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) raw[k] = Vec<T>::load_raw(base[k] + iz * ld_in);
+            float acc[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) acc[i] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float v[N];
+                Vec<T>::unpack(raw[k], v);
+#pragma unroll
+                for (int i = 0; i < N; i += 2) fma2(acc[i], acc[i + 1], wxy[k], v[i], v[i + 1], acc[i], acc[i + 1]);
+            }
+            // row layout [N / 4][cw] float4: the cw lanes of a z position touch consecutive 16-byte words (no bank conflicts)
+            float4* dstp = reinterpret_cast<float4*>(pl + iz * C) + ch;
+#pragma unroll
+            for (int q = 0; q < N / 4; ++q) dstp[q * cw] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        }
+        __syncwarp();
+        // stage 2: z blend
+        T* dst = out + ((int64_t)b * go.vox_p + (int64_t)line * go.Zp) * ld_out + c0;
+        for (int zp = zl; zp < go.Zp; zp += zstep) {
+            const int4 e = ztab[zp];
+            const float l0 = __int_as_float(e.z), l1 = __int_as_float(e.w);
+            const float4* p0 = reinterpret_cast<const float4*>(pl + e.x * C) + ch;
+            const float4* p1 = reinterpret_cast<const float4*>(pl + e.y * C) + ch;
+            float acc[N];
+#pragma unroll
+            for (int q = 0; q < N / 4; ++q) {
+                const float4 a = p0[q * cw], c = p1[q * cw];
+                float m0, m1, m2, m3;
+                mul2(m0, m1, l1, c.x, c.y);
+                mul2(m2, m3, l1, c.z, c.w);
+                fma2(acc[4 * q], acc[4 * q + 1], l0, a.x, a.y, m0, m1);
+                fma2(acc[4 * q + 2], acc[4 * q + 3], l0, a.z, a.w, m2, m3);
+            }
+            Vec<T>::store(dst + (int64_t)zp * ld_out, acc);
+        }
+        __syncwarp();  // the next line's stage 1 overwrites the buffer
+    }
+}
+
 // DOWN-sampling variant, grid = (blocks per sample, B).  Gather form: a thread owns one 16-byte channel vector of one OUTPUT row (haloed rows
 // included: their source is the clamped interior voxel), fetches its eight source vectors and blends them - x/y first,
 // then z, the order ATen's separable kernel and the fp32 parity tests use.  Consecutive threads walk the channel vectors
@@ -580,6 +678,8 @@ int tdb_pointwise(const void* raw, int ld_raw, const double* stats, const float*
 
 int tdb_trilinear(const void* in, int ld_in, int Xi, int Yi, int Zi, void* out, int ld_out, int Xo,
                   int Yo, int Zo, int B, int C, int dtype, void* stream) {
+    const bool force_line = (dtype & TDB_TRILINEAR_LINE) != 0;
+    dtype &= ~TDB_TRILINEAR_LINE;
     TDB_REQUIRE(in && out, TDB_E_BADARG, "tdb_trilinear: null pointer");
     const int n = dtype == TDB_BF16 ? 8 : 4;
     TDB_REQUIRE(C % n == 0 && ld_in % n == 0 && ld_out % n == 0 && aligned16(in) && aligned16(out),
@@ -600,6 +700,33 @@ int tdb_trilinear(const void* in, int ld_in, int Xi, int Yi, int Zi, void* out, 
             trilinear_gather_kernel<bf16><<<ggrid, kThreads, 0, s>>>((const bf16*)in, ld_in, gi, (bf16*)out, ld_out, go, C, split, chunks, sx, sy, sz);
         else
             trilinear_gather_kernel<float><<<ggrid, kThreads, 0, s>>>((const float*)in, ld_in, gi, (float*)out, ld_out, go, C, split, chunks, sx, sy, sz);
+        TDB_CHECK_LAUNCH("tdb_trilinear");
+        return 0;
+    }
+    // up-sampling with a channel-vector count that divides a warp and an x/y-blended input line per warp that fits in
+    // shared memory: the two-stage line kernel (bit-identical to the walker, fewer instructions)
+    static const bool no_line = std::getenv("TURBDIFF_B200_TRILINEAR_WALKER") != nullptr;
+    const size_t line_smem = (size_t)go.Zp * sizeof(int4) + (size_t)TRI_WARPS * Zi * C * sizeof(float);
+    // (measured at B = 8: 194x50x50 output 195 -> 177 us; 97x25x25 and below 3-10 % slower than the walker: large outputs only)
+    const bool big = force_line || (int64_t)B * go.vox_p >= 1500000;
+    if (!no_line && big && chunks <= 32 && 32 % chunks == 0 && line_smem <= 48 * 1024 && (int64_t)Zi * ld_in < (1ll << 31)) {
+        const int64_t lines = (int64_t)go.Xp * go.Yp;
+        int64_t blocks = ceil_div(lines, TRI_WARPS);
+        const int64_t cap = (148 * 32) / (B < 1 ? 1 : B);  // a few waves of 8 resident blocks per SM
+        if (blocks > cap) blocks = cap < 8 ? 8 : cap;
+        dim3 lgrid((unsigned)blocks, (unsigned)B);
+        static const bool carve = [] {  // 26 KB per 4-warp block: let eight of them share an SM
+            cudaFuncSetAttribute(trilinear_up_line_kernel<bf16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(trilinear_up_line_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            return true;
+        }();
+        (void)carve;
+        if (dtype == TDB_BF16)
+            trilinear_up_line_kernel<bf16><<<lgrid, TRI_WARPS * 32, line_smem, s>>>((const bf16*)in, ld_in, gi, (bf16*)out, ld_out, go, C, split,
+                                                                                 chunks, sx, sy, sz);
+        else
+            trilinear_up_line_kernel<float><<<lgrid, TRI_WARPS * 32, line_smem, s>>>((const float*)in, ld_in, gi, (float*)out, ld_out, go, C, split,
+                                                                                  chunks, sx, sy, sz);
         TDB_CHECK_LAUNCH("tdb_trilinear");
         return 0;
     }

@@ -16,6 +16,7 @@ F32, BF16 = 0, 1
 PW_SILU, PW_NOHALO = 1, 2
 STEP_NOISE_BCS, STEP_CLIP, STEP_FINAL, STEP_LEARNED_VAR = 1, 2, 4, 8
 CONV_ALL_ROWS = 1
+TRILINEAR_LINE = 0x100  # tdb_trilinear: dtype | TRILINEAR_LINE forces the two-stage up-sampling kernel (tests)
 CONV_CLUSTER_MC = 2
 WGRAD_ZERO_HALO = 1
 TRIBWD_ACCUMULATE = 1

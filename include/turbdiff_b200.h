@@ -209,6 +209,10 @@ TDB_API int tdb_pointwise(const void* raw, int ld_raw, const double* stats, cons
 
 /* Trilinear resampling, align_corners=True, halo grid -> halo grid incl. halo
  * (ddpm.py:358-361,367-369): src = i*(n_in-1)/(n_out-1) per axis in fp32. */
+/* Up-sampling runs on one of two kernels with bit-identical results: a line walker, and - for outputs of 1.5 M rows and more
+ * whose channel vectors divide a warp - a two-stage kernel (x/y blend of the input line in shared memory, then the z blend).
+ * dtype | TDB_TRILINEAR_LINE selects the second one regardless of the size (kernel tests). */
+#define TDB_TRILINEAR_LINE 0x100
 TDB_API int tdb_trilinear(const void* in, int ld_in, int Xi, int Yi, int Zi, void* out, int ld_out, int Xo,
                   int Yo, int Zo, int B, int C, int dtype, void* stream);
 
@@ -363,7 +367,8 @@ TDB_API int tdb_conv3d_wgrad_tc(const void* in, int ld_in, const void* d_out, in
 TDB_API int tdb_trilinear_bwd(const void* g_out, int ld_g, int Xo, int Yo, int Zo, void* d_in, int ld_d, int Xi,
                       int Yi, int Zi, int B, int C, int dtype, unsigned flags, void* stream);
 
-/* Backward of tdb_attention: d_qkv (q|k|v gradient, interior rows) from qkv and d_out. S <= 128. */
+/* Backward of tdb_attention: d_qkv (q|k|v gradient, interior rows) from qkv and d_out.  S <= 135: the S x S probability /
+ * score-gradient matrices in shared memory; longer sequences (up to ~650 voxels): streaming form, nothing quadratic stored. */
 TDB_API int tdb_attention_bwd(const void* qkv, int ld_qkv, const void* d_out, int ld_do, void* d_qkv, int ld_dq, int B,
                       int X, int Y, int Z, int heads, int dh, int dtype, void* stream);
 

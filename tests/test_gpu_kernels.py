@@ -189,11 +189,15 @@ def test_gn_stats_and_pointwise(lib, prec, C, G):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
-@pytest.mark.parametrize("sizes", [((11, 7, 5), (5, 3, 3)), ((5, 3, 3), (11, 7, 5)), ((12, 3, 3), (24, 6, 6)), ((6, 6, 6), (6, 6, 6))])
-def test_trilinear(lib, prec, sizes):
+@pytest.mark.parametrize("C", [16, 24, 64, 256])  # 16-byte channel vectors per voxel: 2/3/8/32 (bf16), 4/6/16/64 (fp32)
+@pytest.mark.parametrize("sizes", [((11, 7, 5), (5, 3, 3)), ((5, 3, 3), (11, 7, 5)), ((12, 3, 3), (24, 6, 6)), ((6, 6, 6), (6, 6, 6)),
+                                   ((12, 6, 6), (25, 12, 12)), ((4, 3, 3), (14, 9, 3)), ((3, 3, 7), (5, 4, 30))])
+def test_trilinear(lib, prec, sizes, C):
+    """Down-sampling runs on the gather kernel; up-sampling on the line walker and, when forced (or for large outputs) and the
+    channel vectors of a voxel divide a warp (C = 16, 64, 256 in bf16; 16, 64 in fp32), on the two-stage line kernel."""
     code, td = _dt(prec)
     (Xi, Yi, Zi), (Xo, Yo, Zo) = sizes
-    B, C = 2, 16
+    B = 2
     x = gen(B, C, Xi, Yi, Zi, seed=9).to(td).float()
     xin = to_halo(x, dtype=td)
     out = torch.zeros((B, Xo + 2, Yo + 2, Zo + 2, 2 * C), device="cuda", dtype=td)
@@ -203,6 +207,12 @@ def test_trilinear(lib, prec, sizes):
     assert rel_l2(from_halo(out, C, C), want) < (2e-6 if prec == "fp32" else 5e-3)
     assert float(out[..., :C].float().abs().max()) == 0.0  # the other half of the concat buffer is untouched
     assert halo_is_replicated(out[..., C:].contiguous())
+    if Xo * Yo * Zo > Xi * Yi * Zi:
+        # the two-stage line kernel (production: outputs of >= 1.5 M rows) must equal the walker bit for bit
+        out2 = torch.zeros_like(out)
+        lib.call("tdb_trilinear", xin.data_ptr(), C, Xi, Yi, Zi, out2.data_ptr() + C * out.element_size(), 2 * C, Xo, Yo, Zo, B, C,
+                 code | lib.TRILINEAR_LINE, lib.stream_ptr())
+        assert torch.equal(out2, out)
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
