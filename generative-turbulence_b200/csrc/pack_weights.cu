@@ -18,11 +18,11 @@ namespace {
 constexpr int PT = 32;  // tile edge in both channel dimensions
 
 template <int taps>
-__global__ void __launch_bounds__(1024)
-pack_conv_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int Cout, int Cin, int folded, int tile_n, int transpose) {
+__device__ __forceinline__ void pack_tile(const float* __restrict__ w, bf16* __restrict__ dst, int Cout, int Cin, int folded, int tile_n,
+                                          int transpose, int bx, int by) {
     extern __shared__ float sm[];  // [PT co][PT*taps + 1]
     const int pitch = PT * taps + 1;
-    const int co0 = blockIdx.y * PT, ci0 = blockIdx.x * PT;
+    const int co0 = by * PT, ci0 = bx * PT;
     const int n_co = min(PT, Cout - co0), n_ci = min(PT, Cin - ci0);
     // read: for every co of the tile the contiguous run of n_ci*taps floats
     // (U loads in flight per thread: one load per trip left a single block at ~40 us whatever its size)
@@ -67,6 +67,35 @@ pack_conv_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int Cout, 
     }
 }
 
+template <int taps>
+__global__ void __launch_bounds__(1024)
+pack_conv_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int Cout, int Cin, int folded, int tile_n, int transpose) {
+    pack_tile<taps>(w, dst, Cout, Cin, folded, tile_n, transpose, blockIdx.x, blockIdx.y);
+}
+
+// Many weights in ONE launch: the job table travels as a kernel parameter (no device table, graph-capturable as is); a block
+// finds its job from the running block offsets.  62 one-weight launches of 4 .. 256 blocks were ~0.7 ms of serialized,
+// mostly latency-bound device time at the head of every training step.
+constexpr int PACK_BATCH = 64;
+struct PackJobDev {
+    const float* w;
+    bf16* dst;
+    int Cout, Cin, taps, folded, tile_n, transpose, block0, gx;
+};
+struct PackBatch {
+    PackJobDev j[PACK_BATCH];
+    int n;
+};
+__global__ void __launch_bounds__(1024) pack_conv_batch_kernel(const __grid_constant__ PackBatch P) {
+    int k = 0;
+    for (int q = 1; q < P.n; ++q)
+        if ((int)blockIdx.x >= P.j[q].block0) k = q;
+    const PackJobDev& J = P.j[k];
+    const int lb = (int)blockIdx.x - J.block0;
+    if (J.taps == 27) pack_tile<27>(J.w, J.dst, J.Cout, J.Cin, J.folded, J.tile_n, J.transpose, lb % J.gx, lb / J.gx);
+    else pack_tile<1>(J.w, J.dst, J.Cout, J.Cin, J.folded, J.tile_n, J.transpose, lb % J.gx, lb / J.gx);
+}
+
 }  // namespace
 
 // w: fp32 (Cout, Cin, taps) contiguous (taps = 27 or 1).  dst: bf16, Cout*Cin*taps elements.
@@ -89,5 +118,37 @@ extern "C" int tdb_pack_conv_weights(const float* w, void* dst, int Cout, int Ci
         pack_conv_kernel<1><<<grid, 1024, smem, (cudaStream_t)stream>>>(w, (bf16*)dst, Cout, Cin, folded, tile_n, transpose);
     }
     TDB_CHECK_LAUNCH("tdb_pack_conv_weights");
+    return 0;
+}
+
+// The same for n weights at once (launches of up to 64 weights each).  jobs: host array, read during the call only.
+extern "C" int tdb_pack_conv_weights_batch(const TdbPackJob* jobs, int n, void* stream) {
+    TDB_REQUIRE(jobs && n >= 0, TDB_E_BADARG, "tdb_pack_conv_weights_batch: null pointer");
+    const size_t smem = (size_t)PT * (PT * 27 + 1) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(pack_conv_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    TDB_REQUIRE(e == cudaSuccess, (int)e, "tdb_pack_conv_weights_batch: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    for (int first = 0; first < n; first += PACK_BATCH) {
+        PackBatch P;
+        P.n = n - first < PACK_BATCH ? n - first : PACK_BATCH;
+        int blocks = 0;
+        for (int q = 0; q < P.n; ++q) {
+            const TdbPackJob& a = jobs[first + q];
+            TDB_REQUIRE(a.w && a.dst, TDB_E_BADARG, "tdb_pack_conv_weights_batch: null pointer in job %d", first + q);
+            TDB_REQUIRE((a.taps == 27 || a.taps == 1) && a.Cout >= 1 && a.Cin >= 1, TDB_E_BADARG,
+                        "tdb_pack_conv_weights_batch: taps must be 27 or 1 (job %d)", first + q);
+            const int O = a.transpose ? a.Cin : a.Cout;
+            TDB_REQUIRE(!a.folded || (a.taps == 27 && a.tile_n >= 1 && O % a.tile_n == 0), TDB_E_BADARG,
+                        "tdb_pack_conv_weights_batch: the kz-folded layout needs 27 taps and an N tile that divides %d (job %d)", O, first + q);
+            PackJobDev& d = P.j[q];
+            d.w = a.w; d.dst = (bf16*)a.dst;
+            d.Cout = a.Cout; d.Cin = a.Cin; d.taps = a.taps; d.folded = a.folded; d.tile_n = a.tile_n; d.transpose = a.transpose;
+            d.block0 = blocks;
+            d.gx = (int)ceil_div(a.Cin, PT);
+            blocks += d.gx * (int)ceil_div(a.Cout, PT);
+        }
+        if (blocks == 0) continue;
+        pack_conv_batch_kernel<<<(unsigned)blocks, 1024, smem, (cudaStream_t)stream>>>(P);
+        TDB_CHECK_LAUNCH("tdb_pack_conv_weights_batch");
+    }
     return 0;
 }

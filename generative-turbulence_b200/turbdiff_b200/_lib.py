@@ -23,6 +23,12 @@ TRIBWD_ACCUMULATE = 1
 
 _p, _i, _l, _u, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint, C.c_float, C.c_double
 
+class PackJob(C.Structure):
+    """TdbPackJob of include/turbdiff_b200.h (tdb_pack_conv_weights_batch)."""
+
+    _fields_ = [("w", _p), ("dst", _p), ("Cout", _i), ("Cin", _i), ("taps", _i), ("folded", _i), ("tile_n", _i), ("transpose", _i)]
+
+
 # name -> argument types (all return int unless noted)
 SIGNATURES = {
     "tdb_encode_input": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
@@ -36,6 +42,7 @@ SIGNATURES = {
     "tdb_conv3d_bf16_winz": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _u, _p, _p, _p, _i, _p],
     "tdb_conv3d_bf16_winp": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _u, _p],
     "tdb_pack_conv_weights": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "tdb_pack_conv_weights_batch": [_p, _i, _p],
     "tdb_gn_stats": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_pointwise": [_p, _i, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _f, _u, _i, _p],
     "tdb_trilinear": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],

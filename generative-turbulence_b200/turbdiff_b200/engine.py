@@ -115,8 +115,8 @@ class DenoiserEngine:
         self.film_rows = off
         self.block_order = [n for n, _ in order]
 
-    def side_stream(self, device):
-        key = str(device)
+    def side_stream(self, device, role="wgrad"):
+        key = (str(device), role)
         if key not in self._side:
             self._side[key] = torch.cuda.Stream(device=device)
         return self._side[key]
@@ -130,27 +130,37 @@ class DenoiserEngine:
         sizes = level_sizes(tuple(spatial), self.model.u_net_levels)
         self._level_zp = {lvl: sz[2] + 2 for lvl, sz in enumerate(sizes)}
 
-    def weights(self):
+    def weights(self, train: bool = False):
         """Kernel-layout copies of the conv weights, refreshed when any parameter changed
-        (optimizer step / load_state_dict).  Layout: fp32 [ntaps][Cin][Cout]; bf16 [Cout][ntaps*Cin]."""
+        (optimizer step / load_state_dict).  Layout: fp32 [ntaps][Cin][Cout]; bf16 [Cout][ntaps*Cin].
+        bf16 path: every layout comes out of ONE launch (tdb_pack_conv_weights_batch, 64 weights per launch); train=True
+        also derives the input-gradient layouts the backward program will ask for (_dgrad_weights) in the same call - in
+        training all of them are rebuilt every step, and 62 one-weight launches were ~0.7 ms at the head of the step."""
         ver = (self._param_version(), tuple(sorted(self._level_zp.items())))  # kernel choice depends on the grid's Z
         if self._wcache is not None and ver == self._wversion:
             return self._wcache
         m = self.model
-        w = {}
-
-        def pack(conv, level):
-            return self.pack_conv(conv.weight.detach(), level)
-
-        for name, bp in self.blocks.items():
-            lvl = self._block_level(name)
-            w[f"{name}.conv1"] = pack(bp.blk.block1.conv, lvl)
-            w[f"{name}.conv2"] = pack(bp.blk.block2.conv, lvl)
-            if bp.has_proj:
-                w[f"{name}.proj"] = pack(bp.blk.conv, lvl)
         att = m.u_net.center_block[1].fn.fn
-        w["attn.qkv"] = pack(att.to_qkv, m.u_net_levels)
-        w["attn.out"] = pack(att.to_out, m.u_net_levels)
+        L = m.u_net_levels
+        jobs = []  # (key, conv, level) in the order the forward program uses them
+        for name in [f"down{i}" for i in range(L)] + ["center0", "attn", "center2"] + [f"up{i}" for i in range(L)] + ["decode0"]:
+            if name == "attn":
+                jobs.append(("attn.qkv", att.to_qkv, L))
+                jobs.append(("attn.out", att.to_out, L))
+                continue
+            bp, lvl = self.blocks[name], self._block_level(name)
+            jobs.append((f"{name}.conv1", bp.blk.block1.conv, lvl))
+            jobs.append((f"{name}.conv2", bp.blk.block2.conv, lvl))
+            if bp.has_proj:
+                jobs.append((f"{name}.proj", bp.blk.conv, lvl))
+        assert len(jobs) == 2 * len(self.blocks) + sum(bp.has_proj for bp in self.blocks.values()) + 2
+        items = [(conv.weight.detach(), lvl, False) for _, conv, lvl in jobs]
+        if train and self.precision == "bf16":
+            items += [(conv.weight.detach(), lvl, True) for _, conv, lvl in jobs]
+        packed = self.pack_many(items)
+        w = {key: packed[i] for i, (key, _, _) in enumerate(jobs)}
+        if len(items) > len(jobs):
+            w["dgrad"] = {key: packed[len(jobs) + i] for i, (key, _, _) in enumerate(jobs)}
         # stacked over blocks and transposed to (dim, film_rows) for coalesced reads in tdb_time_film
         w["film_w"] = torch.cat([self.blocks[n].blk.project_onto_scale_shift.weight.detach() for n in self.block_order]).t().contiguous().float()
         w["film_b"] = torch.cat([self.blocks[n].blk.project_onto_scale_shift.bias.detach() for n in self.block_order]).contiguous().float()
@@ -200,19 +210,48 @@ class DenoiserEngine:
             return "win" if (self.win and zp <= 63) else "fold2"
         return None
 
-    def pack_conv(self, wt, level, dgrad: bool = False):
-        """Kernel layout of a (Cout, Cin, k, k, k) weight for the kernel fold_kind() selects at `level`.  dgrad=True: the
-        weights of the input-gradient convolution, W'[ci][co][k] = W[co][ci][2-k] (logical Cout' = Cin, Cin' = Cout).
-        bf16 path on CUDA: one launch of tdb_pack_conv_weights per weight, straight from the fp32 parameter (as torch ops
-        this was a strided permute copy, a flip and a cast per weight: 178 launches per training step)."""
+    def _pack_spec(self, wt, level, dgrad):
+        """(Cout, Cin, taps, folded, N tile, shape of the packed matrix) of a (Cout, Cin, k, k, k) weight."""
         cout, cin = wt.shape[:2]
         taps = wt.shape[2] * wt.shape[3] * wt.shape[4]
         lo, li = (cin, cout) if dgrad else (cout, cin)  # logical output / input channels of the packed matrix
         folded = self.precision == "bf16" and self.fold_kind(taps, li, lo, level) not in (None, "win")
         tile = lo if lo < 128 else 128
+        return cout, cin, taps, folded, tile, ((3 * lo, 9 * li) if folded else (lo, taps * li))
+
+    def pack_many(self, items):
+        """pack_conv of every (weight, level, dgrad) item.  bf16 path on CUDA: one flat bf16 buffer and one launch per 64
+        weights (tdb_pack_conv_weights_batch); anything else item by item."""
+        ok = self.precision == "bf16" and len(items) > 0 and all(
+            wt.is_cuda and wt.dtype == torch.float32 and wt.shape[2] * wt.shape[3] * wt.shape[4] in (1, 27) for wt, _, _ in items)
+        if not ok:
+            return [self.pack_conv(wt, lvl, dg) for wt, lvl, dg in items]
+        specs = [self._pack_spec(wt, lvl, dg) for wt, lvl, dg in items]
+        offs, total = [], 0
+        for sp in specs:
+            offs.append(total)
+            total += -(-(sp[5][0] * sp[5][1]) // 256) * 256  # every layout starts on a 512-byte boundary (TMA base addresses)
+        flat = torch.empty(total, dtype=torch.bfloat16, device=items[0][0].device)
+        srcs = [wt.detach().contiguous() for wt, _, _ in items]
+        outs = [flat[o : o + sp[5][0] * sp[5][1]].view(sp[5]) for o, sp in zip(offs, specs)]
+        table = (_lib.PackJob * len(items))()
+        for j, (src, dst, sp, (_, _, dg)) in enumerate(zip(srcs, outs, specs, items)):
+            table[j] = _lib.PackJob(src.data_ptr(), dst.data_ptr(), sp[0], sp[1], sp[2], 1 if sp[3] else 0, sp[4], 1 if dg else 0)
+        import ctypes
+
+        call("tdb_pack_conv_weights_batch", ctypes.cast(table, ctypes.c_void_p), len(items), _lib.stream_ptr())
+        return outs
+
+    def pack_conv(self, wt, level, dgrad: bool = False):
+        """Kernel layout of a (Cout, Cin, k, k, k) weight for the kernel fold_kind() selects at `level`.  dgrad=True: the
+        weights of the input-gradient convolution, W'[ci][co][k] = W[co][ci][2-k] (logical Cout' = Cin, Cin' = Cout).
+        bf16 path on CUDA: one launch of tdb_pack_conv_weights per weight, straight from the fp32 parameter (as torch ops
+        this was a strided permute copy, a flip and a cast per weight: 178 launches per training step)."""
+        cout, cin, taps, folded, tile, shape = self._pack_spec(wt, level, dgrad)
+        lo, li = (cin, cout) if dgrad else (cout, cin)
         if self.precision == "bf16" and wt.is_cuda and wt.dtype == torch.float32 and taps in (1, 27):
             src = wt.detach().contiguous()
-            dst = torch.empty((3 * lo, 9 * li) if folded else (lo, taps * li), dtype=torch.bfloat16, device=wt.device)
+            dst = torch.empty(shape, dtype=torch.bfloat16, device=wt.device)
             call("tdb_pack_conv_weights", src.data_ptr(), dst.data_ptr(), cout, cin, taps, 1 if folded else 0, tile, 1 if dgrad else 0,
                  _lib.stream_ptr())
             return dst
@@ -479,7 +518,7 @@ class DenoiserEngine:
         L = m.u_net_levels
         p = self.plan(B, spatial, x.device)
         self._set_geometry(spatial)
-        w = self.weights()
+        w = self.weights(train=train)
         s = _lib.stream_ptr()
         X, Y, Z = spatial
         Fc = m.c_local_features

@@ -232,6 +232,16 @@ TDB_API int tdb_attention(const void* qkv, int ld_qkv, void* out, int ld_out, in
 TDB_API int tdb_pack_conv_weights(const float* w, void* dst, int Cout, int Cin, int taps, int folded, int tile_n,
                           int transpose, void* stream);
 
+/* The same for n weights in one launch per 64 weights (the job table is a kernel parameter).  In training every layout is
+ * re-derived after each optimizer step: 62 one-weight launches were ~0.7 ms at the head of the step.  `jobs` is a host
+ * array, read during the call only. */
+typedef struct TdbPackJob {
+    const float* w; /* fp32 (Cout, Cin, taps) */
+    void* dst;      /* bf16, Cout*Cin*taps elements */
+    int Cout, Cin, taps, folded, tile_n, transpose;
+} TdbPackJob;
+TDB_API int tdb_pack_conv_weights_batch(const TdbPackJob* jobs, int n, void* stream);
+
 /* ---- timestep conditioning ------------------------------------------------------------------ */
 
 /* Nyquist embedding -> process_c MLP -> all FiLM projections of the network in one call

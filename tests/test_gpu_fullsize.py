@@ -245,3 +245,28 @@ def test_full_size_training_step_matches_reference_golden(golden, shapes, precis
     worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
     print("full-size gradients vs reference", precision, [(k, f"{v:.2e}") for k, v in worst])
     assert worst[0][1] < GRAD_TOL[precision], worst
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_full_size_upsampling_kernels_agree(precision):
+    """The up-sampling into the level-0 concat buffer (97x25x25 -> 194x50x50, 64 channels into a 128-channel pitch) at the exact
+    shape the bench runs: the two-stage line kernel (what B >= 3 selects at this size) equals the line walker (B = 2: below the
+    1.5 M-row switch) bit for bit, and both equal torch's trilinear interpolation of the same input."""
+    import torch.nn.functional as F
+    from turbdiff_b200 import _lib
+
+    td, code = (torch.bfloat16, 1) if precision == "bf16" else (torch.float32, 0)  # TDB_BF16 / TDB_F32
+    B, C, (Xi, Yi, Zi), (Xo, Yo, Zo) = 2, 64, (97, 25, 25), (194, 50, 50)
+    x = torch.randn(B, C, Xi, Yi, Zi, generator=torch.Generator().manual_seed(3)).cuda().to(td)
+    xin = torch.zeros((B, Xi + 2, Yi + 2, Zi + 2, C), device="cuda", dtype=td)
+    xin[:, 1:-1, 1:-1, 1:-1] = x.permute(0, 2, 3, 4, 1)
+    outs = []
+    for flag in (0, _lib.TRILINEAR_LINE):
+        out = torch.zeros((B, Xo + 2, Yo + 2, Zo + 2, 2 * C), device="cuda", dtype=td)
+        _lib.call("tdb_trilinear", xin.data_ptr(), C, Xi, Yi, Zi, out.data_ptr(), 2 * C, Xo, Yo, Zo, B, C, code | flag, _lib.stream_ptr())
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    assert float(outs[1][..., C:].float().abs().max()) == 0.0  # the skip half of the concat buffer is untouched
+    want = F.interpolate(x.float(), size=(Xo, Yo, Zo), mode="trilinear", align_corners=True)
+    got = outs[1][:, 1:-1, 1:-1, 1:-1, :C].permute(0, 4, 1, 2, 3).float()
+    assert rel_l2(got, want) < (2e-6 if precision == "fp32" else 5e-3)

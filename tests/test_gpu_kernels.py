@@ -793,6 +793,37 @@ def test_pack_conv_weights_matches_the_torch_layouts(lib, cout, cin, taps, trans
     assert torch.equal(got, want)
 
 
+def test_pack_conv_weights_batch_equals_the_single_launches(lib):
+    """tdb_pack_conv_weights_batch (the job table as a kernel parameter, 64 weights per launch): 70 weights of mixed shapes,
+    tap counts and layouts in two launches, each bit-identical to its own tdb_pack_conv_weights launch."""
+    import ctypes
+
+    shapes = [(64, 64, 27), (32, 128, 27), (512, 256, 27), (16, 16, 27), (48, 80, 27), (384, 512, 1), (32, 128, 1), (128, 64, 27), (256, 128, 1),
+              (64, 32, 27)]
+    jobs, want, got, keep = [], [], [], []
+    for n in range(70):
+        cout, cin, taps = shapes[n % len(shapes)]
+        transpose = (n // 2) % 2
+        O = cin if transpose else cout
+        tile = O if O < 128 else 128
+        folded = 1 if (taps == 27 and O % tile == 0 and n % 3 == 0) else 0
+        k = 3 if taps == 27 else 1
+        w = gen(cout, cin, k, k, k, seed=300 + n)
+        a = torch.full((cout * cin * taps,), 7.0, device="cuda", dtype=torch.bfloat16)
+        b = torch.full_like(a, 5.0)
+        lib.call("tdb_pack_conv_weights", w.data_ptr(), a.data_ptr(), cout, cin, taps, folded, tile, transpose, lib.stream_ptr())
+        jobs.append(lib.PackJob(w.data_ptr(), b.data_ptr(), cout, cin, taps, folded, tile, transpose))
+        want.append(a)
+        got.append(b)
+        keep.append(w)
+    table = (lib.PackJob * len(jobs))(*jobs)
+    n0 = lib.launch_count()
+    lib.call("tdb_pack_conv_weights_batch", ctypes.cast(table, ctypes.c_void_p), len(jobs), lib.stream_ptr())
+    assert lib.launch_count() - n0 == 2
+    for n, (a, b) in enumerate(zip(want, got)):
+        assert torch.equal(a, b), n
+
+
 # --------------------------------------------------------------------------- fused scatter/normalise, gather/de-normalise
 @pytest.mark.parametrize("B", [1, 3])
 def test_scatter_normalize_and_gather_denormalize(lib, B):
