@@ -276,3 +276,32 @@ def test_gradient_phases_partition_the_state_dict():
     # every FiLM projection is late, including those of phase-1 blocks
     assert "decode.0.project_onto_scale_shift.weight" in late and "decode.0.block1.conv.weight" in early
     assert "u_net.center_block.1.fn.fn.to_qkv.weight" in early and "decode.1.weight" in early
+
+
+def test_weight_layout_jobs_cover_every_convolution_and_specs_match_the_torch_layouts(built_lib):
+    """Host logic of the batched weight re-layout (engine.weights / pack_many): the job list names every convolution weight of
+    the state dict exactly once, and the shape _pack_spec reserves in the flat buffer for a layout (forward and input-gradient
+    form, at the level whose kernel choice it follows) is the shape of the torch permute / flip / cast sequence it replaces."""
+    from turbdiff_b200 import DenoisingModel
+
+    m = DenoisingModel(in_features=4, out_features=4, c_local_features=4, c_global_features=0, timesteps=500, dim=32, u_net_levels=4,
+                       norm_type="group", precision="bf16")
+    eng = m.engine()
+    eng._set_geometry((194, 50, 50))
+    w = eng.weights()  # CPU parameters: the torch layouts
+    convs = {k for k, v in m.state_dict().items() if v.dim() == 5 and k.split(".")[0] not in ("encode_x", "encode_c_local", "decode")
+             or (k.startswith("decode.0") and v.dim() == 5)}
+    assert len([k for k in w if k not in ("film_w", "film_b", "dgrad")]) == len(convs) == 31
+    n = 0
+    for name, bp in eng.blocks.items():
+        lvl = eng._block_level(name)
+        for key, conv in ((f"{name}.conv1", bp.blk.block1.conv), (f"{name}.conv2", bp.blk.block2.conv)) + (((f"{name}.proj", bp.blk.conv),) if bp.has_proj else ()):
+            for dgrad in (False, True):
+                spec = eng._pack_spec(conv.weight, lvl, dgrad)
+                got = eng.pack_conv(conv.weight.detach(), lvl, dgrad)
+                assert tuple(got.shape) == tuple(spec[5]) and got.dtype == torch.bfloat16, (key, dgrad)
+                assert spec[5][0] * spec[5][1] == conv.weight.numel()
+                if not dgrad:
+                    assert torch.equal(got, w[key]), key
+                n += 1
+    assert n == 2 * 29
