@@ -96,7 +96,44 @@ __global__ void __launch_bounds__(1024) pack_conv_batch_kernel(const __grid_cons
     else pack_tile<1>(J.w, J.dst, J.Cout, J.Cin, J.folded, J.tile_n, J.transpose, lb % J.gx, lb / J.gx);
 }
 
+// Weight gradient from the kernels' accumulation layout to the parameter layout: dw [taps][Cin][Cout] fp32 ->
+// out (Cout, Cin, taps) fp32.  A block moves a (TCI ci x 32 co x all taps) tile through shared memory: 128-byte reads along
+// co, contiguous runs of TCI * taps floats per co on the write side.
+template <int taps, int TCI>
+__global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dw, float* __restrict__ out, int Cin, int Cout) {
+    __shared__ float sm[taps * TCI][33];
+    const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * TCI;
+    const int n_co = min(32, Cout - co0), n_ci = min(TCI, Cin - ci0);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    for (int r = warp; r < taps * n_ci; r += 8) {  // r = t * n_ci + ci_l
+        const int t = r / n_ci, ci_l = r % n_ci;
+        if (lane < n_co) sm[ci_l * taps + t][lane] = dw[((int64_t)t * Cin + ci0 + ci_l) * Cout + co0 + lane];
+    }
+    __syncthreads();
+    const int run = n_ci * taps;
+    for (int co_l = warp; co_l < n_co; co_l += 8) {
+        float* dst = out + ((int64_t)(co0 + co_l) * Cin + ci0) * taps;
+        for (int e = lane; e < run; e += 32) {
+            dst[e] = sm[e][co_l];  // row e = ci_l * taps + t: consecutive lanes read consecutive rows (33-float pitch: no conflicts)
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int tdb_unpack_wgrad(const float* dw, float* out, int Cout, int Cin, int taps, void* stream) {
+    TDB_REQUIRE(dw && out, TDB_E_BADARG, "tdb_unpack_wgrad: null pointer");
+    TDB_REQUIRE((taps == 27 || taps == 1) && Cout >= 1 && Cin >= 1, TDB_E_BADARG, "tdb_unpack_wgrad: taps must be 27 or 1");
+    if (taps == 27) {
+        dim3 grid((unsigned)ceil_div(Cout, 32), (unsigned)ceil_div(Cin, 8));
+        unpack_wgrad_kernel<27, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(dw, out, Cin, Cout);
+    } else {
+        dim3 grid((unsigned)ceil_div(Cout, 32), (unsigned)ceil_div(Cin, 32));
+        unpack_wgrad_kernel<1, 32><<<grid, 256, 0, (cudaStream_t)stream>>>(dw, out, Cin, Cout);
+    }
+    TDB_CHECK_LAUNCH("tdb_unpack_wgrad");
+    return 0;
+}
 
 // w: fp32 (Cout, Cin, taps) contiguous (taps = 27 or 1).  dst: bf16, Cout*Cin*taps elements.
 // folded: 0 = per-tap layout [O][taps*I]; 1 = kz-folded [3*O][9*I] in N tiles of tile_n rows (taps must be 27).

@@ -43,6 +43,7 @@ SIGNATURES = {
     "tdb_conv3d_bf16_winp": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _u, _p],
     "tdb_pack_conv_weights": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "tdb_pack_conv_weights_batch": [_p, _i, _p],
+    "tdb_unpack_wgrad": [_p, _p, _i, _i, _i, _p],
     "tdb_gn_stats": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "tdb_pointwise": [_p, _i, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _f, _u, _i, _p],
     "tdb_trilinear": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],

@@ -81,7 +81,9 @@ class BackwardProgram:
             dw = torch.zeros((ntaps, x.C, d_out.C), dtype=torch.float32, device=x.t.device)
             call("tdb_conv3d_wgrad", x.ptr, x.ld, d_out.ptr, d_out.ld, dw.data_ptr(), p["B"], X, Y, Z, x.C, d_out.C, ntaps, self.eng.dt,
                  _lib.WGRAD_ZERO_HALO if zero_halo else 0, _lib.stream_ptr())
-            return dw.view(k, k, k, x.C, d_out.C).permute(4, 3, 0, 1, 2).contiguous()
+            out = torch.empty((d_out.C, x.C, k, k, k), dtype=torch.float32, device=x.t.device)
+            call("tdb_unpack_wgrad", dw.data_ptr(), out.data_ptr(), d_out.C, x.C, ntaps, _lib.stream_ptr())  # -> (Cout, Cin, k, k, k)
+            return out
 
         side = self.side
         if side is None:

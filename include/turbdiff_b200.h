@@ -369,6 +369,11 @@ TDB_API int tdb_conv3d_wgrad(const void* in, int ld_in, const void* d_out, int l
 TDB_API int tdb_conv3d_wgrad_tc(const void* in, int ld_in, const void* d_out, int ld_do, float* dw, int B, int X, int Y,
                         int Z, int Cin, int Cout, int ntaps, unsigned mode, void* stream);
 
+/* dw [taps][Cin][Cout] fp32 (what tdb_conv3d_wgrad accumulates) -> the parameter layout (Cout, Cin, kD, kH, kW) fp32 of
+ * nn.Conv3d.weight.grad (ddpm.py:164,188), tiled through shared memory (as a torch permute + contiguous this was a strided
+ * copy at ~1 TB/s, 36 launches and 0.43 ms per training step). */
+TDB_API int tdb_unpack_wgrad(const float* dw, float* out, int Cout, int Cin, int taps, void* stream);
+
 /* Transpose of tdb_trilinear (reference: autograd of F.interpolate(mode="trilinear", align_corners=True), ddpm.py:358-369):
  * d_in (interior rows; halo rows zero) from the output gradient's interior rows.
  * flags & TDB_TRIBWD_ACCUMULATE: d_in += the transposed gradient on interior rows, halo rows untouched (the skip

@@ -793,6 +793,17 @@ def test_pack_conv_weights_matches_the_torch_layouts(lib, cout, cin, taps, trans
     assert torch.equal(got, want)
 
 
+@pytest.mark.parametrize("cout,cin,taps", [(64, 64, 27), (32, 128, 27), (512, 256, 27), (48, 80, 27), (20, 12, 27), (384, 512, 1), (128, 32, 1), (4, 32, 1)])
+def test_unpack_wgrad_equals_the_torch_permute(lib, cout, cin, taps):
+    """tdb_unpack_wgrad: [taps][Cin][Cout] -> (Cout, Cin, k, k, k), bit-identical to the permute + contiguous it replaces."""
+    k = 3 if taps == 27 else 1
+    dw = gen(taps, cin, cout, seed=88)
+    want = dw.view(k, k, k, cin, cout).permute(4, 3, 0, 1, 2).contiguous()
+    got = torch.full_like(want, 7.0)
+    lib.call("tdb_unpack_wgrad", dw.data_ptr(), got.data_ptr(), cout, cin, taps, lib.stream_ptr())
+    assert torch.equal(got, want)
+
+
 def test_pack_conv_weights_batch_equals_the_single_launches(lib):
     """tdb_pack_conv_weights_batch (the job table as a kernel parameter, 64 weights per launch): 70 weights of mixed shapes,
     tap counts and layouts in two launches, each bit-identical to its own tdb_pack_conv_weights launch."""
