@@ -78,7 +78,7 @@ class BackwardProgram:
         k = 3 if ntaps == 27 else 1
 
         def launch():
-            dw = torch.zeros((ntaps, x.C, d_out.C), dtype=torch.float32, device=x.t.device)
+            dw = self._dw_zeros(ntaps * x.C * d_out.C, x.t.device)
             call("tdb_conv3d_wgrad", x.ptr, x.ld, d_out.ptr, d_out.ld, dw.data_ptr(), p["B"], X, Y, Z, x.C, d_out.C, ntaps, self.eng.dt,
                  _lib.WGRAD_ZERO_HALO if zero_halo else 0, _lib.stream_ptr())
             out = torch.empty((d_out.C, x.C, k, k, k), dtype=torch.float32, device=x.t.device)
@@ -100,6 +100,23 @@ class BackwardProgram:
             res.record_stream(main)  # (inside a capture every result lives until the join at the end of run())
         self._readers[d_out.t.data_ptr()] = done
         return res
+
+    def _dw_zeros(self, n: int, dev):
+        """n zeroed floats for one weight gradient in the kernels' accumulation layout, out of ONE buffer per backward pass
+        (zeroed by a single fill on the stream of the first weight gradient instead of a torch.zeros launch in front of each)."""
+        pool = getattr(self, "_dw_pool", None)
+        if pool is None or self._dw_used + n > pool.numel():
+            m = self.m
+            convs = [bp.blk.block1.conv for bp in self.eng.blocks.values()] + [bp.blk.block2.conv for bp in self.eng.blocks.values()]
+            convs += [bp.blk.conv for bp in self.eng.blocks.values() if bp.has_proj]
+            att = m.u_net.center_block[1].fn.fn
+            convs += [att.to_qkv, att.to_out]
+            total = sum(-(-c.weight.numel() // 64) * 64 for c in convs)
+            pool = self._dw_pool = torch.zeros(max(total, n), dtype=torch.float32, device=dev)
+            self._dw_used = 0
+        out = pool[self._dw_used : self._dw_used + n]
+        self._dw_used += -(-n // 64) * 64  # 256-byte aligned slices
+        return out
 
     def _leaf(self, fn):
         """Run a gradient leaf (reads only tensors that nothing overwrites before the end of run()) on the side stream."""
@@ -305,6 +322,7 @@ class BackwardProgram:
         self.side = eng.side_stream(dev) if eng.wgrad_side_stream else None
         self._readers = {}
         self._zpool = None
+        self._dw_pool = None
         g_eps = g_eps.to(torch.float32).contiguous()
         grads = self.grads = {}
         d_film = self.d_film = torch.zeros((B, eng.film_rows), dtype=torch.float32, device=dev)

@@ -13,6 +13,8 @@ UNet.forward :351-372, ResnetBlock :190-197, Block :168-177, Attention :295-308.
 
 from __future__ import annotations
 
+import contextlib
+import gc
 from dataclasses import dataclass
 
 import os
@@ -44,6 +46,21 @@ class View:
 
     def slice(self, c0: int, C: int) -> "View":
         return View(self.t, self.c0 + c0, C, self.level)
+
+
+@contextlib.contextmanager
+def _gc_paused():
+    """No cyclic garbage collection while a CUDA graph is being captured: a collection that happens to run inside the capture
+    and releases an OLDER CUDAGraph / its memory pool (cudaGraphExecDestroy, cudaFree) is "an operation not permitted when
+    stream is capturing" and invalidates a strict capture (seen in the test suite, which builds many engines per process)."""
+    was = gc.isenabled()
+    gc.collect()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
 
 
 def level_sizes(spatial, levels):
@@ -687,7 +704,7 @@ class DenoiserEngine:
             torch.cuda.current_stream().wait_stream(side)
             g = torch.cuda.CUDAGraph()
             try:
-                with torch.cuda.graph(g):
+                with _gc_paused(), torch.cuda.graph(g):
                     self.forward(st["x_t"], st["t_vec"], st["c_local"], c_static=True, **kw)
             except RuntimeError as e:  # not fatal: the same launch program runs eagerly
                 import warnings
@@ -812,7 +829,7 @@ class DenoiserEngine:
     def _capture_train_graphs(self, xs, ts, cs, gs, x, sig, pool, g_f, g_b, n0, capture_mode):
         from .backward import BackwardProgram
 
-        with torch.cuda.graph(g_f, pool=pool, capture_error_mode=capture_mode):
+        with _gc_paused(), torch.cuda.graph(g_f, pool=pool, capture_error_mode=capture_mode):
             self._wcache = None
             eps = self.forward(xs, ts, cs, train=True)
         n_l1 = _lib.launch_count()
@@ -828,7 +845,7 @@ class DenoiserEngine:
         views = {n: v.view(by_name[n].shape) for v, n in zip(flat.split(sizes), order)}
         g_b2 = torch.cuda.CUDAGraph()
         bp = BackwardProgram(self)
-        with torch.cuda.graph(g_b, pool=pool, capture_error_mode=capture_mode):
+        with _gc_paused(), torch.cuda.graph(g_b, pool=pool, capture_error_mode=capture_mode):
             bp.phase1(gs)
             first = [n for n in order if grad_phase(n) == 1]
             missing = [n for n in first if n not in bp.grads]
@@ -837,7 +854,7 @@ class DenoiserEngine:
             # all gradients of this phase packed into the flat buffer: the autograd glue then hands them out with a single
             # copy instead of one per tensor
             torch._foreach_copy_([views[n] for n in first], [bp.grads[n].reshape(by_name[n].shape) for n in first])
-        with torch.cuda.graph(g_b2, pool=pool, capture_error_mode=capture_mode):
+        with _gc_paused(), torch.cuda.graph(g_b2, pool=pool, capture_error_mode=capture_mode):
             grads, g_c = bp.phase2()
             second = [n for n in order if grad_phase(n) == 2]
             torch._foreach_copy_([views[n] for n in second], [grads[n].reshape(by_name[n].shape) for n in second])
