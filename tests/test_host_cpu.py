@@ -305,3 +305,27 @@ def test_weight_layout_jobs_cover_every_convolution_and_specs_match_the_torch_la
                     assert torch.equal(got, w[key]), key
                 n += 1
     assert n == 2 * 29
+
+
+def test_gc_is_paused_only_for_the_duration_of_a_capture():
+    """engine._gc_paused (wrapped around every CUDA-graph capture): cyclic GC off inside, restored afterwards - also when the
+    capture raises, and left off if the caller had it off."""
+    import gc
+
+    from turbdiff_b200.engine import _gc_paused
+
+    assert gc.isenabled()
+    with _gc_paused():
+        assert not gc.isenabled()
+    assert gc.isenabled()
+    with pytest.raises(RuntimeError):
+        with _gc_paused():
+            raise RuntimeError("capture failed")
+    assert gc.isenabled()
+    gc.disable()
+    try:
+        with _gc_paused():
+            assert not gc.isenabled()
+        assert not gc.isenabled()
+    finally:
+        gc.enable()
